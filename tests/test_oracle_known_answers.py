@@ -1,0 +1,218 @@
+"""Known-answer tests that pin the oracle itself.
+
+The reference has no tests or golden vectors ("parity unpinned"); every expected value below is derived by hand
+from the cited reference line, not produced by running the oracle.
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from flex_dm_b200.spec import make_input_columns, make_synthetic_batch
+from oracle import mfp_oracle as O
+from oracle import philox
+
+
+def test_seq_mask_is_zero_based():
+    # architecture/mask.py:28-31: length += 1; sequence_mask
+    m = O.get_seq_mask(torch.tensor([[0], [2]]))
+    assert m.tolist() == [[True, False, False], [True, True, True]]
+
+
+def test_masking_constants():
+    # masking.py:8-15
+    assert O.MASK_VALUE == 10.0 and O.NULL_VALUE == 0.0 and O.MASK_PROB == 0.15
+    assert O.THRESH == pytest.approx(1.0 / 9.0)
+
+
+def test_apply_token_values():
+    # masking.py:80-93
+    col = {"type": "categorical", "input_dim": 6}
+    x = torch.tensor([[[3], [4]]], dtype=torch.int32)
+    m = torch.tensor([[True, False]])
+    assert O.apply_token(x, col, m, "masked").tolist() == [[[6], [4]]]
+    assert O.apply_token(x, col, m, "unused").tolist() == [[[7], [4]]]
+    ncol = {"type": "numerical"}
+    y = torch.full((1, 2, 4), 0.5)
+    assert O.apply_token(y, ncol, m, "masked")[0, 0].tolist() == [10.0] * 4
+    assert O.apply_token(y, ncol, m, "unused")[0, 0].tolist() == [0.0] * 4
+    assert O.apply_token(y, ncol, m, "masked")[0, 1].tolist() == [0.5] * 4
+
+
+def test_task_id_sets():
+    # mfp.py:35-36, masking.py:18-21, spec.py:364-377
+    crello, rico = make_input_columns("crello"), make_input_columns("rico")
+    assert O.get_task_names(crello) == ["random", "elem", "type", "pos", "attr", "img", "txt"]
+    assert O.get_task_names(rico) == ["random", "elem", "type", "pos", "attr"]
+
+    def ids(cols, method):
+        return {i for i, p in enumerate(O.task_probs(O.get_task_names(cols), method)) if p > 0}
+
+    assert ids(crello, "elem_pos_attr_img_txt") == {1, 3, 4, 5, 6}
+    assert ids(rico, "elem_pos_attr") == {1, 3, 4}
+    assert ids(crello, "random") == {0}
+
+
+def test_filter_padding_type_gate():
+    # masking.py:34-47 with crello-spec.yml:88-121: textElement (index 2) has no image_embedding
+    cols = OrderedDict((k, v) for k, v in make_input_columns("crello").items() if not v.get("demo_only"))
+    b = make_synthetic_batch(cols, 2, 4, seed=3)
+    b["type"][0, :, 0] = [2, 3, 4, 1]  # text, image, coloredBackground, svg
+    b["length"][:] = [[3], [1]]
+    t = {k: torch.as_tensor(v) for k, v in b.items()}
+    t["image_embedding"] = torch.ones(2, 4, 512)
+    t["text_embedding"] = torch.ones(2, 4, 512)
+    f = O.filter_padding(t, cols, O.get_seq_mask(t["length"], 4))
+    assert f["image_embedding"][0, :, 0].tolist() == [0.0, 1.0, 0.0, 1.0]
+    assert f["text_embedding"][0, :, 0].tolist() == [1.0, 0.0, 0.0, 0.0]
+    assert f["color"][0, :, 0].tolist()[1] == 17 and f["color"][0, :, 0].tolist()[3] == 17  # <UNUSED> = input_dim+1
+    assert f["font_family"][0, 0, 0].item() == b["font_family"][0, 0, 0]
+    assert f["font_family"][0, 1, 0].item() == cols["font_family"]["input_dim"] + 1
+    # padded positions of document 1 (length 2)
+    assert f["left"][1, 2:, 0].tolist() == [65, 65]
+
+
+def _zero_decoder(o):
+    for k in o.params:
+        if k.startswith("model/decoder"):
+            o.params[k].zero_()
+
+
+def test_ce_of_uniform_logits_is_log_input_dim():
+    # with all decoder kernels = 0 the CE of a masked categorical field = log(input_dim) per sub-target
+    cols = make_input_columns("crello")
+    o = O.OracleMFP(cols, num_blocks=1, dropout=0.0)
+    _zero_decoder(o)
+    b = make_synthetic_batch(cols, 3, 5, seed=1, lengths="ragged")
+    t = o.to_torch(b)
+    seq = O.get_seq_mask(t["length"], 5)
+    masks = O.get_initial_masks(o.input_columns, seq)
+    for key in ("left", "color", "text_embedding"):
+        masks[key] = seq
+    mod = O.preprocess_for_test(t, o.input_columns, masks)
+    out = O.model_forward(o.params, mod, o.input_columns, 1)
+    total, losses, scores, metrics = O.loss_layer(t, out, masks, cols)
+    n_valid = (t["length"].reshape(-1) + 1).to(torch.float64)
+    assert float(losses["left"]) == pytest.approx(float(n_valid.mean()) * math.log(64), rel=1e-9)
+    gate = torch.tensor(cols["color"]["loss_condition"]["mask"])[t["type"][..., 0].long()] & seq
+    assert float(losses["color"]) == pytest.approx(float(gate.sum()) / 3 * 3 * math.log(16), rel=1e-9)
+    # MSE branch = sum_d (yhat - y)^2 with yhat = 0 (metrics.py:246-248)
+    tgate = torch.tensor(cols["text_embedding"]["loss_condition"]["mask"])[t["type"][..., 0].long()] & seq
+    expect = float((t["text_embedding"].double() ** 2).sum(-1)[tgate].sum()) / 3
+    assert float(losses["text_embedding"]) == pytest.approx(expect, rel=1e-6)
+    # unmasked keys: den == 0 -> normalised score 1.0 (metrics.py:281)
+    assert float(metrics["top_score"]) == 1.0 and float(scores["top_score_den"]) == 0.0
+    assert float(metrics["total_score"]) == pytest.approx(sum(float(metrics[k + "_score"]) for k in O.get_valid_input_columns(cols)) / 18)
+
+
+def test_attention_masks_padded_keys_exactly():
+    # transformer.py:61-74: padded keys get exactly zero probability; a 1-element doc returns V[0] for every query
+    cols = make_input_columns("rico")
+    p = O.init_params(cols, 1, 256, seed=2, bias_scale=0.1)
+    x = torch.randn(2, 6, 256, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+    mask = O.get_seq_mask(torch.tensor([[0], [3]]), 6)
+    pre = "model/blocks/seq2seq/seq2seq_0/attn"
+    y = O.mhsa_forward(p, pre, x, mask)
+    v0 = O.dense(x[0, :1], p, pre + "/dense_value")
+    expect = O.dense(v0.expand(6, 256), p, pre + "/combine_heads")
+    assert torch.allclose(y[0], expect, atol=1e-12)
+    x2 = x.clone()
+    x2[1, 4:] += 100.0  # padded keys/values must not influence valid queries
+    y2 = O.mhsa_forward(p, pre, x2, mask)
+    assert torch.equal(y[1, :4], y2[1, :4])
+
+
+def test_sort_key_and_order():
+    # tensor_utils.py:15,31-34: key = base-100 digits of (type,left,top,width,height); padded += 100^5
+    cols = make_input_columns("rico")
+    b = make_synthetic_batch(cols, 1, 3, seed=0)
+    b["length"][:] = 1  # two valid elements
+    for k, vals in zip(O.SORT_KEYS, [(1, 1, 0), (2, 2, 0), (3, 3, 0), (4, 1, 0), (5, 5, 0)]):
+        b[k][0, :, 0] = vals
+    t = {k: torch.as_tensor(v) for k, v in b.items()}
+    out, idx = O.sort_inputs(t, O.get_valid_input_columns(cols))
+    # keys: 102030405, 102030105, 0 + 10^10 -> order [1, 0, 2]
+    assert idx.tolist() == [[1, 0, 2]]
+    assert out["width"][0, :, 0].tolist() == [1, 4, 0]
+    assert 1 * 100**4 + 2 * 100**3 + 3 * 100**2 + 4 * 100 + 5 == 102030405
+
+
+def test_layernorm_epsilon_and_biased_variance():
+    x = torch.tensor([[1.0, 3.0]], dtype=torch.float64)
+    y = O.layer_norm(x, torch.ones(2, dtype=torch.float64), torch.zeros(2, dtype=torch.float64))
+    assert y[0, 1].item() == pytest.approx(1.0 / math.sqrt(1.0 + 1e-3), rel=1e-12)
+
+
+def test_l2_has_no_half_and_covers_bias():
+    specs = OrderedDict([("a/kernel", ((2, 2), "glorot", True)), ("a/bias", ((2,), "zeros", True)), ("n/gamma", ((2,), "ones", False))])
+    p = {"a/kernel": torch.full((2, 2), 2.0), "a/bias": torch.full((2,), 3.0), "n/gamma": torch.full((2,), 5.0)}
+    assert float(O.l2_regulariser(p, specs, 0.01)) == pytest.approx(0.01 * (16.0 + 18.0))
+
+
+def test_clipnorm_is_per_variable_and_adam_is_tf_form():
+    p = OrderedDict(a=torch.zeros(2, dtype=torch.float64), b=torch.zeros(1, dtype=torch.float64))
+    g = OrderedDict(a=torch.tensor([3.0, 4.0], dtype=torch.float64), b=torch.tensor([0.5], dtype=torch.float64))
+    m = OrderedDict((k, torch.zeros_like(v)) for k, v in p.items())
+    v = OrderedDict((k, torch.zeros_like(v)) for k, v in p.items())
+    O.adam_step(p, g, m, v, 1, lr=1e-4, clipnorm=1.0)
+    # a: ||g|| = 5 -> g/5 = (0.6, 0.8); b untouched (0.5 < 1)
+    ga, gb = np.array([0.6, 0.8]), np.array([0.5])
+    alpha = 1e-4 * math.sqrt(1 - 0.999) / (1 - 0.9)
+    for name, gg in (("a", ga), ("b", gb)):
+        expect = -alpha * (0.1 * gg) / (np.sqrt(0.001 * gg * gg) + 1e-7)
+        assert np.allclose(p[name].numpy(), expect, rtol=1e-12)
+
+
+def test_ce_clip_semantics():
+    # A6: p clipped to [1e-7, 1-1e-7] before the log; a saturated wrong prediction costs -log(1e-7) + log(sum clipped)
+    logits = torch.tensor([[100.0, 0.0, 0.0]], dtype=torch.float64)
+    loss, score = O.categorical_metric(torch.tensor([1]), logits)
+    c = np.array([1 - 1e-7, 1e-7, 1e-7])
+    assert float(loss) == pytest.approx(-math.log(1e-7) + math.log(c.sum()), rel=1e-12)
+    assert float(score) == 0.0
+
+
+def test_continuous_score_is_half_cos_plus_half():
+    y = torch.tensor([[1.0, 0.0]], dtype=torch.float64)
+    p = torch.tensor([[0.0, 2.0]], dtype=torch.float64)
+    loss, score = O.continuous_metric(y, p)
+    assert float(loss) == pytest.approx((1.0 + 4.0) / 2)
+    assert float(score) == pytest.approx(0.5)
+
+
+def test_philox_known_answer():
+    # Random123 known-answer vectors for philox4x32-10
+    assert [int(x) for x in philox.philox4x32_10(0, 0, 0, 0, 0, 0)] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    out = philox.philox4x32_10(0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF)
+    assert [int(x) for x in out] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    out = philox.philox4x32_10(0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344, 0xA4093822, 0x299F31D0)
+    assert [int(x) for x in out] == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_random_masking_statistics_and_gating():
+    cols = make_input_columns("crello")
+    o = O.OracleMFP(cols, num_blocks=1)
+    b = make_synthetic_batch(cols, 64, 32, seed=5, lengths="ragged")
+    t = o.to_torch(b)
+    tasks = torch.zeros(64, dtype=torch.int32)
+    _, mod, masks = O.preprocess_for_train(t, o.input_columns, tasks, O.PhiloxDraws(7, 0))
+    seq = O.get_seq_mask(t["length"], 32)
+    frac = masks["left"][seq].float().mean().item()
+    assert 0.10 < frac < 0.20
+    assert not masks["left"][~seq].any()
+    changed = (mod["left"][..., 0] != O.filter_padding(t, o.input_columns, seq)["left"][..., 0])
+    assert (changed & ~masks["left"]).sum() == 0
+    is_mask_tok = mod["left"][..., 0] == 64
+    assert 0.6 < (is_mask_tok & masks["left"]).sum().item() / masks["left"].sum().item() < 0.9
+
+
+def test_train_step_runs_and_loss_decreases():
+    cols = make_input_columns("rico")
+    o = O.OracleMFP(cols, num_blocks=1, masking_method="elem_pos_attr", dropout=0.0, l2=None, learning_rate=1e-3)
+    b = make_synthetic_batch(cols, 8, 10, seed=0, lengths="ragged")
+    first = [o.train_step(b, seed=1, step=0)["data_loss"] for _ in range(1)][0]
+    for i in range(30):
+        last = o.train_step(b, seed=1, step=0)["data_loss"]
+    assert last < first
