@@ -1,0 +1,561 @@
+// C ABI of the MFP engine (include/flexdm_mfp.h): schema + parameter layout, workspace plan, and the host-side
+// orchestration of the forward / loss / backward / optimiser kernels on a caller-supplied stream.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace mfp {
+
+static thread_local char g_error[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+struct BlockLayout {
+  long long wqkv, bqkv, wo, bo, w1, b1, w2, b2, g1, be1, g2, be2;
+};
+
+struct Workspace {
+  // byte offsets into the caller's workspace
+  size_t vars, flags, x, ln1, qkv, attn, xmid, ln2, hid, stats, lse, logits, dlogits, dx, dtmp, dy, dqkv, dhid, dattn, dh0m, part, idx_true, idx_pred,
+      norms, total;
+};
+
+}  // namespace mfp
+
+using namespace mfp;
+
+struct mfp_engine {
+  mfp_config cfg;
+  Schema sc;
+  std::vector<std::string> field_names;
+  std::vector<mfp_variable> vars;
+  std::vector<BlockLayout> blocks;
+  long long wh = 0, bh = 0, param_count = 0;
+  // bound state
+  int B = 0, S = 0, T = 0;
+  uint8_t* ws = nullptr;
+  Workspace off{};
+  float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+  TensorMapCache* maps = nullptr;
+  int gemm_impl = 0;
+  int64_t launches = 0;
+};
+
+namespace mfp {
+
+static long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+
+static void add_var(mfp_engine* h, const std::string& name, long long off, int rows, int cols, int ld, int l2) {
+  mfp_variable v;
+  memset(&v, 0, sizeof(v));
+  snprintf(v.name, sizeof(v.name), "%s", name.c_str());
+  v.offset = off;
+  v.rows = rows;
+  v.cols = cols;
+  v.ld = ld;
+  v.l2 = l2;
+  h->vars.push_back(v);
+}
+
+static void build_layout(mfp_engine* h) {
+  const int D = kD, L = h->cfg.num_blocks;
+  long long cur = 0;
+  auto alloc = [&](long long n) {
+    const long long o = cur;
+    cur = align_up(cur + n, 64);
+    return o;
+  };
+  Schema& sc = h->sc;
+  // logits geometry: each head starts at a multiple of 4 columns
+  int lw = 0;
+  for (int f = 0; f < sc.F; ++f) {
+    FieldDev& fd = sc.f[f];
+    fd.logit_w = (fd.kind == 0) ? fd.C * fd.input_dim : fd.C;
+    fd.logit_off = lw;
+    lw += (fd.logit_w + 3) & ~3;
+  }
+  sc.LW = lw;
+  // encoder (encoder.py:72-92)
+  for (int f = 0; f < sc.F; ++f) {
+    FieldDev& fd = sc.f[f];
+    const std::string base = "model/encoder/input_layer/" + h->field_names[f];
+    if (fd.kind == 0) {
+      fd.table_off = alloc((long long)(fd.input_dim + 2) * D);
+      fd.kernel_off = fd.bias_off = -1;
+      add_var(h, base + "/embeddings", fd.table_off, fd.input_dim + 2, D, D, 1);
+    } else {
+      fd.table_off = alloc(2LL * D);
+      fd.kernel_off = alloc((long long)fd.C * D);
+      fd.bias_off = alloc(D);
+      add_var(h, base + "_special/embeddings", fd.table_off, 2, D, D, 1);
+      add_var(h, base + "/kernel", fd.kernel_off, fd.C, D, D, 1);
+      add_var(h, base + "/bias", fd.bias_off, 1, D, D, 1);
+    }
+  }
+  // blocks (transformer.py:54-57,161-173); Q|K|V kernels share one [D, 3D] matrix so the projection is one GEMM
+  h->blocks.resize(L);
+  for (int i = 0; i < L; ++i) {
+    BlockLayout& b = h->blocks[i];
+    b.wqkv = alloc(3LL * D * D); b.bqkv = alloc(3 * D);
+    b.wo = alloc((long long)D * D); b.bo = alloc(D);
+    b.w1 = alloc((long long)D * kF); b.b1 = alloc(kF);
+    b.w2 = alloc((long long)kF * D); b.b2 = alloc(D);
+    b.g1 = alloc(D); b.be1 = alloc(D); b.g2 = alloc(D); b.be2 = alloc(D);
+    char p[64];
+    snprintf(p, sizeof(p), "model/blocks/seq2seq/seq2seq_%d", i);
+    const std::string s(p);
+    const char* qkv_names[3] = {"dense_query", "dense_key", "dense_value"};
+    for (int j = 0; j < 3; ++j) {
+      add_var(h, s + "/attn/" + qkv_names[j] + "/kernel", b.wqkv + (long long)j * D, D, D, 3 * D, 1);
+      add_var(h, s + "/attn/" + qkv_names[j] + "/bias", b.bqkv + (long long)j * D, 1, D, D, 1);
+    }
+    add_var(h, s + "/attn/combine_heads/kernel", b.wo, D, D, D, 1);
+    add_var(h, s + "/attn/combine_heads/bias", b.bo, 1, D, D, 1);
+    add_var(h, s + "/mlp/layer_with_weights-0/kernel", b.w1, D, kF, kF, 1);
+    add_var(h, s + "/mlp/layer_with_weights-0/bias", b.b1, 1, kF, kF, 1);
+    add_var(h, s + "/mlp/layer_with_weights-1/kernel", b.w2, kF, D, D, 1);
+    add_var(h, s + "/mlp/layer_with_weights-1/bias", b.b2, 1, D, D, 1);
+    add_var(h, s + "/norm1/gamma", b.g1, 1, D, D, 0);
+    add_var(h, s + "/norm1/beta", b.be1, 1, D, D, 0);
+    add_var(h, s + "/norm2/gamma", b.g2, 1, D, D, 0);
+    add_var(h, s + "/norm2/beta", b.be2, 1, D, D, 0);
+  }
+  // decoder heads (decoder.py:32-43), concatenated into one [D, LW] matrix
+  h->wh = alloc((long long)D * sc.LW);
+  h->bh = alloc(sc.LW);
+  for (int f = 0; f < sc.F; ++f) {
+    const FieldDev& fd = sc.f[f];
+    const std::string base = "model/decoder/decoders/" + h->field_names[f];
+    add_var(h, base + "/kernel", h->wh + fd.logit_off, D, fd.logit_w, sc.LW, 1);
+    add_var(h, base + "/bias", h->bh + fd.logit_off, 1, fd.logit_w, sc.LW, 1);
+  }
+  h->param_count = cur;
+}
+
+static Workspace plan_workspace(const mfp_engine* h, int B, int S) {
+  Workspace w{};
+  const size_t T = (size_t)B * S, L = h->cfg.num_blocks, D = kD, F = h->sc.F;
+  size_t cur = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = cur;
+    cur = (cur + bytes + 255) / 256 * 256;
+    return o;
+  };
+  const size_t fl = sizeof(float);
+  w.vars = take(h->vars.size() * sizeof(VarDev));
+  w.flags = take((size_t)(h->sc.n_num > 0 ? h->sc.n_num : 1) * T);
+  w.x = take((L + 1) * T * D * fl);
+  w.ln1 = take(L * T * D * fl);
+  w.qkv = take(L * T * 3 * D * fl);
+  w.attn = take(L * T * D * fl);
+  w.xmid = take(L * T * D * fl);
+  w.ln2 = take(L * T * D * fl);
+  w.hid = take(L * T * kF * fl);
+  w.stats = take(L * 4 * T * fl);
+  w.lse = take(L * (size_t)B * kH * S * fl);
+  w.logits = take(T * h->sc.LW * fl);
+  w.dlogits = take(T * h->sc.LW * fl);
+  w.dx = take(T * D * fl);
+  w.dtmp = take(T * D * fl);
+  w.dy = take(T * D * fl);
+  w.dqkv = take(T * 3 * D * fl);
+  w.dhid = take(T * kF * fl);
+  w.dattn = take(T * D * fl);
+  w.dh0m = take((size_t)(h->sc.n_num > 0 ? h->sc.n_num : 1) * T * D * fl);
+  w.part = take(3 * F * T * fl);
+  w.idx_true = take(T * sizeof(int));
+  w.idx_pred = take(T * sizeof(int));
+  w.norms = take(2 * h->vars.size() * fl);
+  w.total = cur;
+  return w;
+}
+
+template <typename Tp>
+static Tp* wsp(const mfp_engine* h, size_t off) { return reinterpret_cast<Tp*>(h->ws + off); }
+
+static BatchPtrs to_batch(const mfp_engine* h, const mfp_batch* b) {
+  BatchPtrs p{};
+  p.length = b->length;
+  for (int f = 0; f < h->sc.F; ++f) p.cols[f] = b->cols[f];
+  return p;
+}
+
+static int check_bound(const mfp_engine* h) {
+  if (!h) { set_error("null engine"); return MFP_ERR_ARG; }
+  if (!h->ws) { set_error("engine is not bound: call mfp_bind first"); return MFP_ERR_STATE; }
+  return MFP_OK;
+}
+
+static int gemm(mfp_engine* h, const float* A, int a_mn, int lda, const float* Bp, int b_mn, int ldb, int M, int N, int K, const GemmEpilogue& ep,
+                int splits, cudaStream_t st) {
+  GemmCall c{};
+  c.a = GemmOperand{A, a_mn, lda};
+  c.b = GemmOperand{Bp, b_mn, ldb};
+  c.M = M; c.N = N; c.K = K;
+  c.splits = splits;
+  c.ep = ep;
+  h->launches++;
+  return launch_gemm(h->maps, c, h->gemm_impl, st);
+}
+
+// split-K factor of a weight-gradient GEMM (K = tokens): enough CTAs for ~2 per SM
+static int wgrad_splits(int M, int N, int K) {
+  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  int s = (2 * 148 + tiles - 1) / tiles;
+  const int kb = (K + 31) / 32;
+  if (s > kb / 4) s = kb / 4;
+  return s < 1 ? 1 : s;
+}
+
+}  // namespace mfp
+
+// ===================================================================================================== C ABI
+extern "C" {
+
+const char* mfp_last_error(void) { return g_error; }
+int mfp_version(void) { return 1; }
+
+int mfp_create(const mfp_config* cfg, const mfp_field_desc* fields, mfp_engine** out) {
+  if (!cfg || !fields || !out) { set_error("mfp_create: null argument"); return MFP_ERR_ARG; }
+  if (cfg->latent_dim != kD) { set_error("mfp_create: latent_dim must be %d in this build (got %d)", kD, cfg->latent_dim); return MFP_ERR_UNSUPPORTED; }
+  if (cfg->num_fields < 1 || cfg->num_fields > kMaxFields) { set_error("mfp_create: num_fields out of range"); return MFP_ERR_ARG; }
+  if (cfg->num_blocks < 1 || cfg->num_blocks > 64) { set_error("mfp_create: num_blocks out of range"); return MFP_ERR_ARG; }
+  mfp_engine* h = new mfp_engine();
+  h->cfg = *cfg;
+  memset(&h->sc, 0, sizeof(h->sc));
+  h->sc.F = cfg->num_fields;
+  h->sc.type_field = cfg->type_field;
+  for (int i = 0; i < 5; ++i) h->sc.sort_field[i] = cfg->sort_fields[i];
+  int n_num = 0;
+  for (int f = 0; f < cfg->num_fields; ++f) {
+    const mfp_field_desc& d = fields[f];
+    FieldDev& fd = h->sc.f[f];
+    fd.kind = d.kind;
+    fd.C = d.C;
+    fd.input_dim = d.input_dim;
+    fd.task_id = d.task_id;
+    fd.has_cond = d.has_cond;
+    fd.cond_mask = d.cond_mask;
+    fd.num_slot = (d.kind == 1) ? n_num++ : -1;
+    if (d.kind == 0 && (d.input_dim < 1 || d.input_dim > 256 || d.C < 1 || d.C > 32)) {
+      set_error("mfp_create: categorical field %s needs 1 <= input_dim <= 256 and 1 <= C <= 32", d.name);
+      delete h;
+      return MFP_ERR_UNSUPPORTED;
+    }
+    if (d.kind == 1 && (d.C % 32 != 0 || d.C < 32)) {
+      set_error("mfp_create: numerical field %s needs a width that is a multiple of 32", d.name);
+      delete h;
+      return MFP_ERR_UNSUPPORTED;
+    }
+    h->field_names.push_back(std::string(d.name, strnlen(d.name, sizeof(d.name))));
+  }
+  h->sc.n_num = n_num;
+  if (cfg->type_field < 0 || cfg->type_field >= cfg->num_fields || h->sc.f[cfg->type_field].kind != 0) {
+    set_error("mfp_create: type_field must index a categorical field");
+    delete h;
+    return MFP_ERR_ARG;
+  }
+  build_layout(h);
+  const char* impl = getenv("FLEXDM_GEMM");
+  h->gemm_impl = (impl && !strcmp(impl, "simt")) ? 1 : 0;
+  h->maps = tensor_map_cache_create();
+  *out = h;
+  return MFP_OK;
+}
+
+void mfp_destroy(mfp_engine* h) {
+  if (!h) return;
+  tensor_map_cache_destroy(h->maps);
+  delete h;
+}
+
+int64_t mfp_param_count(const mfp_engine* h) { return h ? h->param_count : 0; }
+int32_t mfp_num_variables(const mfp_engine* h) { return h ? (int32_t)h->vars.size() : 0; }
+int mfp_get_variable(const mfp_engine* h, int32_t index, mfp_variable* out) {
+  if (!h || !out || index < 0 || index >= (int32_t)h->vars.size()) { set_error("mfp_get_variable: bad index"); return MFP_ERR_ARG; }
+  *out = h->vars[index];
+  return MFP_OK;
+}
+int32_t mfp_logit_width(const mfp_engine* h) { return h ? h->sc.LW : 0; }
+int32_t mfp_field_logit_offset(const mfp_engine* h, int32_t field) {
+  if (!h || field < 0 || field >= h->sc.F) return -1;
+  return h->sc.f[field].logit_off;
+}
+
+int64_t mfp_workspace_bytes(const mfp_engine* h, int32_t B, int32_t S) {
+  if (!h || B < 1 || S < 1) return 0;
+  return (int64_t)plan_workspace(h, B, S).total;
+}
+
+int mfp_bind(mfp_engine* h, int32_t B, int32_t S, void* workspace, int64_t workspace_bytes, float* params, float* grads, float* adam_m,
+             float* adam_v) {
+  if (!h || !workspace || !params) { set_error("mfp_bind: null argument"); return MFP_ERR_ARG; }
+  if (B < 1 || S < 1) { set_error("mfp_bind: bad shape"); return MFP_ERR_ARG; }
+  if (S > 384) { set_error("mfp_bind: S = %d exceeds the attention kernels' shared-memory plan (max 384)", S); return MFP_ERR_UNSUPPORTED; }
+  const Workspace w = plan_workspace(h, B, S);
+  if ((size_t)workspace_bytes < w.total) { set_error("mfp_bind: workspace too small (%lld < %zu)", (long long)workspace_bytes, w.total); return MFP_ERR_ARG; }
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) { set_error("mfp_bind: workspace must be 256-byte aligned"); return MFP_ERR_ARG; }
+  h->B = B; h->S = S; h->T = B * S;
+  h->ws = reinterpret_cast<uint8_t*>(workspace);
+  h->off = w;
+  h->params = params; h->grads = grads; h->adam_m = adam_m; h->adam_v = adam_v;
+  std::vector<VarDev> vd(h->vars.size());
+  for (size_t i = 0; i < vd.size(); ++i) vd[i] = VarDev{h->vars[i].offset, h->vars[i].rows, h->vars[i].cols, h->vars[i].ld, h->vars[i].l2};
+  MFP_CUDA_OK(cudaMemcpy(h->ws + w.vars, vd.data(), vd.size() * sizeof(VarDev), cudaMemcpyHostToDevice));
+  return MFP_OK;
+}
+
+int mfp_sample_tasks(mfp_engine* h, const int32_t* allowed_host, int32_t n_allowed, uint32_t seed, uint32_t step, int32_t* tasks_out, void* stream) {
+  MFP_TRY(check_bound(h));
+  if (n_allowed < 1 || n_allowed > 16) { set_error("mfp_sample_tasks: 1..16 task ids"); return MFP_ERR_ARG; }
+  TaskSet ts{};
+  ts.n = n_allowed;
+  for (int i = 0; i < n_allowed; ++i) ts.ids[i] = allowed_host[i];
+  h->launches++;
+  return launch_sample_tasks(ts, h->B, seed, step, tasks_out, (cudaStream_t)stream);
+}
+
+int mfp_mask_corrupt(mfp_engine* h, const mfp_batch* inputs, const int32_t* tasks, uint32_t seed, uint32_t step, void* const* modified_cols,
+                     uint8_t* const* masks_out, void* stream) {
+  MFP_TRY(check_bound(h));
+  ModifiedPtrs out{};
+  for (int f = 0; f < h->sc.F; ++f) { out.cols[f] = modified_cols[f]; out.masks[f] = masks_out[f]; }
+  h->launches++;
+  return launch_mask_corrupt(h->sc, to_batch(h, inputs), tasks, nullptr, h->B, h->S, seed, step, out, (cudaStream_t)stream);
+}
+
+int mfp_mask_for_test(mfp_engine* h, const mfp_batch* inputs, const uint8_t* const* masks, void* const* modified_cols, void* stream) {
+  MFP_TRY(check_bound(h));
+  ModifiedPtrs out{};
+  MaskPtrs tm{};
+  for (int f = 0; f < h->sc.F; ++f) { out.cols[f] = modified_cols[f]; tm.m[f] = masks[f]; }
+  h->launches++;
+  return launch_mask_corrupt(h->sc, to_batch(h, inputs), nullptr, &tm, h->B, h->S, 0, 0, out, (cudaStream_t)stream);
+}
+
+int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint32_t seed, uint32_t step, float* logits_out, void* stream) {
+  MFP_TRY(check_bound(h));
+  cudaStream_t st = (cudaStream_t)stream;
+  const Schema& sc = h->sc;
+  const int T = h->T, D = kD, L = h->cfg.num_blocks;
+  const BatchPtrs mod = to_batch(h, modified);
+  const float* P = h->params;
+  unsigned char* flags = wsp<unsigned char>(h, h->off.flags);
+  float* x = wsp<float>(h, h->off.x);
+  const size_t TD = (size_t)T * D;
+  const bool drop = training && h->cfg.dropout > 0.f;
+
+  // ---- encoder (encoder.py:147-199)
+  MFP_TRY(launch_row_flags(sc, mod, T, flags, st));
+  MFP_TRY(launch_embed_fwd(sc, mod, flags, P, T, x, st));
+  h->launches += 2;
+  for (int f = 0; f < sc.F; ++f) {
+    const FieldDev& fd = sc.f[f];
+    if (fd.kind != 1) continue;
+    GemmEpilogue ep = make_epilogue(x, D);
+    ep.residual = x; ep.ldr = D;
+    ep.rowflag = flags + (size_t)fd.num_slot * T;
+    MFP_TRY(gemm(h, reinterpret_cast<const float*>(mod.cols[f]), 0, fd.C, P + fd.kernel_off, 1, D, T, D, fd.C, ep, 1, st));
+  }
+  // ---- blocks (transformer.py:208-229)
+  for (int i = 0; i < L; ++i) {
+    const BlockLayout& b = h->blocks[i];
+    float* xi = x + i * TD;
+    float* xo = x + (i + 1) * TD;
+    float* ln1 = wsp<float>(h, h->off.ln1) + i * TD;
+    float* qkv = wsp<float>(h, h->off.qkv) + i * 3 * TD;
+    float* attn = wsp<float>(h, h->off.attn) + i * TD;
+    float* xmid = wsp<float>(h, h->off.xmid) + i * TD;
+    float* ln2 = wsp<float>(h, h->off.ln2) + i * TD;
+    float* hid = wsp<float>(h, h->off.hid) + (size_t)i * T * kF;
+    float* stats = wsp<float>(h, h->off.stats) + (size_t)i * 4 * T;
+    float* lse = wsp<float>(h, h->off.lse) + (size_t)i * h->B * kH * h->S;
+
+    MFP_TRY(launch_layernorm_fwd(xi, P + b.g1, P + b.be1, T, ln1, stats, stats + T, st));
+    GemmEpilogue e1 = make_epilogue(qkv, 3 * D);
+    e1.bias = P + b.bqkv;
+    MFP_TRY(gemm(h, ln1, 0, D, P + b.wqkv, 1, 3 * D, T, 3 * D, D, e1, 1, st));
+    MFP_TRY(launch_attention_fwd(qkv, modified->length, h->B, h->S, attn, lse, st));
+    GemmEpilogue e2 = make_epilogue(xmid, D);
+    e2.bias = P + b.bo;
+    e2.residual = xi; e2.ldr = D;
+    if (drop) { e2.drop_enabled = 1; e2.drop_rate = h->cfg.dropout; e2.drop_seed = seed; e2.drop_step = step; e2.drop_site = kSiteDropout + 2 * i; }
+    MFP_TRY(gemm(h, attn, 0, D, P + b.wo, 1, D, T, D, D, e2, 1, st));
+    MFP_TRY(launch_layernorm_fwd(xmid, P + b.g2, P + b.be2, T, ln2, stats + 2 * T, stats + 3 * T, st));
+    GemmEpilogue e3 = make_epilogue(hid, kF);
+    e3.bias = P + b.b1;
+    e3.relu = 1;
+    MFP_TRY(gemm(h, ln2, 0, D, P + b.w1, 1, kF, T, kF, D, e3, 1, st));
+    GemmEpilogue e4 = make_epilogue(xo, D);
+    e4.bias = P + b.b2;
+    e4.residual = xmid; e4.ldr = D;
+    if (drop) { e4.drop_enabled = 1; e4.drop_rate = h->cfg.dropout; e4.drop_seed = seed; e4.drop_step = step; e4.drop_site = kSiteDropout + 2 * i + 1; }
+    MFP_TRY(gemm(h, hid, 0, kF, P + b.w2, 1, D, T, D, kF, e4, 1, st));
+    h->launches += 3;
+  }
+  // ---- decoder heads (decoder.py:72-111)
+  float* logits = wsp<float>(h, h->off.logits);
+  GemmEpilogue eh = make_epilogue(logits, sc.LW);
+  eh.bias = P + h->bh;
+  MFP_TRY(gemm(h, x + L * TD, 0, D, P + h->wh, 1, sc.LW, T, sc.LW, D, eh, 1, st));
+  if (logits_out) MFP_CUDA_OK(cudaMemcpyAsync(logits_out, logits, (size_t)T * sc.LW * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return MFP_OK;
+}
+
+int mfp_loss(mfp_engine* h, const mfp_batch* targets, const uint8_t* const* masks, const uint8_t* sort_flag, const int32_t* sort_tasks,
+             const float* logits_in, float inv_batch, int32_t compute_grad, float* metrics_out, void* stream) {
+  MFP_TRY(check_bound(h));
+  if (!metrics_out) { set_error("mfp_loss: metrics_out is required"); return MFP_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const BatchPtrs tg = to_batch(h, targets);
+  MaskPtrs mp{};
+  for (int f = 0; f < h->sc.F; ++f) mp.m[f] = masks[f];
+  LossBuffers buf{wsp<float>(h, h->off.part), wsp<int>(h, h->off.idx_true), wsp<int>(h, h->off.idx_pred)};
+  const float* logits = logits_in ? logits_in : wsp<float>(h, h->off.logits);
+  const int use_sort = (h->cfg.sort_pos && (sort_flag || sort_tasks)) ? 1 : 0;
+  if (use_sort) {
+    MFP_TRY(launch_sort_indices(h->sc, tg, logits, sort_flag, sort_tasks, h->cfg.pos_task_id, h->B, h->S, buf, st));
+    h->launches++;
+  }
+  h->launches += 3;
+  return launch_loss(h->sc, tg, mp, logits, use_sort, h->B, h->S, inv_batch, compute_grad ? wsp<float>(h, h->off.dlogits) : nullptr, buf, metrics_out, st);
+}
+
+int mfp_backward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint32_t seed, uint32_t step, void* stream) {
+  MFP_TRY(check_bound(h));
+  if (!h->grads) { set_error("mfp_backward: no gradient buffer bound"); return MFP_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const Schema& sc = h->sc;
+  const int T = h->T, D = kD, L = h->cfg.num_blocks;
+  const BatchPtrs mod = to_batch(h, modified);
+  const float* P = h->params;
+  float* G = h->grads;
+  const size_t TD = (size_t)T * D;
+  const bool drop = training && h->cfg.dropout > 0.f;
+  float* x = wsp<float>(h, h->off.x);
+  float* dlogits = wsp<float>(h, h->off.dlogits);
+  float* dx = wsp<float>(h, h->off.dx);
+  float* dtmp = wsp<float>(h, h->off.dtmp);
+  float* dyb = wsp<float>(h, h->off.dy);
+  float* dqkv = wsp<float>(h, h->off.dqkv);
+  float* dhid = wsp<float>(h, h->off.dhid);
+  float* dattn = wsp<float>(h, h->off.dattn);
+
+  MFP_CUDA_OK(cudaMemsetAsync(G, 0, (size_t)h->param_count * sizeof(float), st));
+  // ---- heads: dX = dlogits . Wh^T ; dWh = X^T . dlogits ; dbh = colsum(dlogits)
+  MFP_TRY(gemm(h, dlogits, 0, sc.LW, P + h->wh, 0, sc.LW, T, D, sc.LW, make_epilogue(dx, D), 1, st));
+  MFP_TRY(gemm(h, x + L * TD, 1, D, dlogits, 1, sc.LW, D, sc.LW, T, make_epilogue(G + h->wh, sc.LW), wgrad_splits(D, sc.LW, T), st));
+  MFP_TRY(launch_colsum(dlogits, T, sc.LW, sc.LW, G + h->bh, st));
+  h->launches++;
+  for (int i = L - 1; i >= 0; --i) {
+    const BlockLayout& b = h->blocks[i];
+    const float* xi = x + i * TD;
+    const float* ln1 = wsp<float>(h, h->off.ln1) + i * TD;
+    const float* qkv = wsp<float>(h, h->off.qkv) + i * 3 * TD;
+    const float* attn = wsp<float>(h, h->off.attn) + i * TD;
+    const float* xmid = wsp<float>(h, h->off.xmid) + i * TD;
+    const float* ln2 = wsp<float>(h, h->off.ln2) + i * TD;
+    const float* hid = wsp<float>(h, h->off.hid) + (size_t)i * T * kF;
+    const float* stats = wsp<float>(h, h->off.stats) + (size_t)i * 4 * T;
+    const float* lse = wsp<float>(h, h->off.lse) + (size_t)i * h->B * kH * h->S;
+
+    // FFN branch: x_out = xmid + drop(relu(ln2.W1 + b1).W2 + b2)
+    const float* dy = dx;
+    if (drop) {
+      MFP_TRY(launch_dropout_bwd(dx, T, h->cfg.dropout, seed, step, kSiteDropout + 2 * i + 1, dyb, st));
+      h->launches++;
+      dy = dyb;
+    }
+    MFP_TRY(gemm(h, hid, 1, kF, dy, 1, D, kF, D, T, make_epilogue(G + b.w2, D), wgrad_splits(kF, D, T), st));
+    MFP_TRY(launch_colsum(dy, T, D, D, G + b.b2, st));
+    GemmEpilogue eh = make_epilogue(dhid, kF);
+    eh.relu_src = hid; eh.ld_relu = kF;
+    MFP_TRY(gemm(h, dy, 0, D, P + b.w2, 0, D, T, kF, D, eh, 1, st));
+    MFP_TRY(gemm(h, ln2, 1, D, dhid, 1, kF, D, kF, T, make_epilogue(G + b.w1, kF), wgrad_splits(D, kF, T), st));
+    MFP_TRY(launch_colsum(dhid, T, kF, kF, G + b.b1, st));
+    MFP_TRY(gemm(h, dhid, 0, kF, P + b.w1, 0, kF, T, D, kF, make_epilogue(dtmp, D), 1, st));
+    MFP_TRY(launch_layernorm_bwd(xmid, dtmp, P + b.g2, stats + 2 * T, stats + 3 * T, dx, T, dx, G + b.g2, G + b.be2, st));
+    // attention branch: xmid = x_in + drop(attn.Wo + bo)
+    dy = dx;
+    if (drop) {
+      MFP_TRY(launch_dropout_bwd(dx, T, h->cfg.dropout, seed, step, kSiteDropout + 2 * i, dyb, st));
+      h->launches++;
+      dy = dyb;
+    }
+    MFP_TRY(gemm(h, attn, 1, D, dy, 1, D, D, D, T, make_epilogue(G + b.wo, D), wgrad_splits(D, D, T), st));
+    MFP_TRY(launch_colsum(dy, T, D, D, G + b.bo, st));
+    MFP_TRY(gemm(h, dy, 0, D, P + b.wo, 0, D, T, D, D, make_epilogue(dattn, D), 1, st));
+    MFP_TRY(launch_attention_bwd(qkv, attn, lse, dattn, modified->length, h->B, h->S, dqkv, st));
+    MFP_TRY(gemm(h, ln1, 1, D, dqkv, 1, 3 * D, D, 3 * D, T, make_epilogue(G + b.wqkv, 3 * D), wgrad_splits(D, 3 * D, T), st));
+    MFP_TRY(launch_colsum(dqkv, T, 3 * D, 3 * D, G + b.bqkv, st));
+    MFP_TRY(gemm(h, dqkv, 0, 3 * D, P + b.wqkv, 0, 3 * D, T, D, 3 * D, make_epilogue(dtmp, D), 1, st));
+    MFP_TRY(launch_layernorm_bwd(xi, dtmp, P + b.g1, stats, stats + T, dx, T, dx, G + b.g1, G + b.be1, st));
+    h->launches += 7;
+  }
+  // ---- encoder: tables / special rows / bias by shared-memory scatter; Dense kernels by wgrad GEMM
+  const unsigned char* flags = wsp<unsigned char>(h, h->off.flags);
+  float* dh0m = wsp<float>(h, h->off.dh0m);
+  MFP_TRY(launch_embed_bwd(sc, mod, flags, dx, T, G, dh0m, st));
+  h->launches++;
+  for (int f = 0; f < sc.F; ++f) {
+    const FieldDev& fd = sc.f[f];
+    if (fd.kind != 1) continue;
+    MFP_TRY(gemm(h, reinterpret_cast<const float*>(mod.cols[f]), 1, fd.C, dh0m + (size_t)fd.num_slot * TD, 1, D, fd.C, D, T,
+                 make_epilogue(G + fd.kernel_off, D), wgrad_splits(fd.C, D, T), st));
+  }
+  return MFP_OK;
+}
+
+int mfp_optimizer_step(mfp_engine* h, int32_t t, float learning_rate, float clipnorm, float* l2_loss_out, void* stream) {
+  MFP_TRY(check_bound(h));
+  if (!h->grads || !h->adam_m || !h->adam_v) { set_error("mfp_optimizer_step: gradient / Adam state buffers are not bound"); return MFP_ERR_STATE; }
+  if (t < 1) { set_error("mfp_optimizer_step: t is 1-based"); return MFP_ERR_ARG; }
+  h->launches += l2_loss_out ? 3 : 2;
+  return launch_optimizer(wsp<VarDev>(h, h->off.vars), (int)h->vars.size(), h->params, h->grads, h->adam_m, h->adam_v, wsp<float>(h, h->off.norms), t,
+                          learning_rate, clipnorm, h->cfg.l2, l2_loss_out, (cudaStream_t)stream);
+}
+
+int mfp_regularization_loss(mfp_engine* h, float* l2_loss_out, void* stream) {
+  MFP_TRY(check_bound(h));
+  if (!l2_loss_out) { set_error("mfp_regularization_loss: null output"); return MFP_ERR_ARG; }
+  h->launches += 2;
+  return launch_regularization_loss(wsp<VarDev>(h, h->off.vars), (int)h->vars.size(), h->params, wsp<float>(h, h->off.norms), h->cfg.l2, l2_loss_out,
+                                    (cudaStream_t)stream);
+}
+
+int mfp_merge_prediction(mfp_engine* h, int32_t field, const void* input_col, const uint8_t* mask, const float* logits_in, float* out, void* stream) {
+  MFP_TRY(check_bound(h));
+  if (field < 0 || field >= h->sc.F) { set_error("mfp_merge_prediction: bad field"); return MFP_ERR_ARG; }
+  h->launches++;
+  return launch_merge_prediction(h->sc, field, input_col, mask, logits_in ? logits_in : wsp<float>(h, h->off.logits), h->T, out, (cudaStream_t)stream);
+}
+
+int64_t mfp_launch_count(const mfp_engine* h) { return h ? h->launches : 0; }
+
+int mfp_debug_gemm(const float* A, int32_t a_mn, int32_t lda, const float* B, int32_t b_mn, int32_t ldb, float* D, int32_t ldd, int32_t M, int32_t N,
+                   int32_t K, const float* bias, int32_t relu, int32_t splits, int32_t impl, void* stream) {
+  static TensorMapCache* cache = tensor_map_cache_create();
+  GemmCall c{};
+  c.a = GemmOperand{A, a_mn, lda};
+  c.b = GemmOperand{B, b_mn, ldb};
+  c.M = M; c.N = N; c.K = K;
+  c.splits = splits;
+  c.ep = make_epilogue(D, ldd);
+  c.ep.bias = bias;
+  c.ep.relu = relu;
+  return launch_gemm(cache, c, impl, (cudaStream_t)stream);
+}
+
+}  // extern "C"

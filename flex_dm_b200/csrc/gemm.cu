@@ -1,0 +1,409 @@
+// TF32 tcgen05/TMA GEMM + a SIMT bring-up kernel with the same epilogue.  See gemm.cuh.
+#include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "gemm.cuh"
+
+namespace mfp {
+
+// ------------------------------------------------------------------------------------------------- epilogue
+__device__ __forceinline__ void epilogue_store4(float (&v)[4], int row, int col, int N, const GemmEpilogue& ep, bool lead_split) {
+  // col is a multiple of 4; N is a multiple of 4 (checked on the host).  bias/residual are added by split 0 only.
+  if (col >= N) return;
+  if (ep.bias && lead_split) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+  }
+  if (ep.relu) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
+  if (ep.relu_src) {
+    const float4 s = *reinterpret_cast<const float4*>(ep.relu_src + (size_t)row * ep.ld_relu + col);
+    v[0] = s.x > 0.0f ? v[0] : 0.0f; v[1] = s.y > 0.0f ? v[1] : 0.0f;
+    v[2] = s.z > 0.0f ? v[2] : 0.0f; v[3] = s.w > 0.0f ? v[3] : 0.0f;
+  }
+  if (ep.drop_enabled) dropout4(v, (uint32_t)row * (uint32_t)N + (uint32_t)col, ep.drop_rate, ep.drop_seed, ep.drop_step, ep.drop_site);
+  if (ep.rowflag && ep.rowflag[row]) { v[0] = v[1] = v[2] = v[3] = 0.0f; }
+  if (ep.residual && lead_split) {
+    const float4 r = *reinterpret_cast<const float4*>(ep.residual + (size_t)row * ep.ldr + col);
+    v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+  }
+  float* dst = ep.out + (size_t)row * ep.ldo + col;
+  if (ep.atomic) {
+    atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+  } else {
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// Bounded wait: a protocol bug must trap, not hang the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("mfp gemm: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (SWIZZLE_128B, Blackwell version bit) -- cute/arch/mma_sm100_desc.hpp layout.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;  // leading byte offset, bits [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;  // stride byte offset, bits [32,46)
+  d |= 1ull << 46;                                 // descriptor version (sm_100)
+  d |= 2ull << 61;                                 // SWIZZLE_128B
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------- tcgen05 kernel
+constexpr int kBM = 128;        // UMMA M (one TMEM lane per row)
+constexpr int kBK = 32;         // 32 fp32 = 128 B = one swizzle row
+constexpr int kUmmaK = 8;       // tf32: 32 B of K per instruction
+constexpr int kStages = 3;
+constexpr int kGemmThreads = 192;
+
+struct GemmTune {
+  uint32_t mn_lbo, mn_sbo, k_lbo, k_sbo;
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kABytes = kBM * kBK * 4;
+  static constexpr int kBBytes = BN * kBK * 4;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOff = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOff + 128 + 1024;  // + barriers + alignment slack
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, (BN <= 128) ? 2 : 1)
+gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                  int a_mn, int b_mn, int kb_per_split, GemmEpilogue ep, GemmTune tune) {
+  using L = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + L::kBarOff;
+  // barriers: full[kStages], empty[kStages], accum; then the TMEM base address slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * kStages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 1);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM;
+  const int n0 = blockIdx.y * BN;
+  const int num_kb = (K + kBK - 1) / kBK;
+  const int kb0 = blockIdx.z * kb_per_split;
+  const int kb1 = min(num_kb, kb0 + kb_per_split);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sa = base + stage * L::kStageBytes;
+        const uint32_t sb = sa + L::kABytes;
+        mbar_expect_tx(full_bar(stage), L::kStageBytes);
+        if (!a_mn) {
+          tma_load_2d(sa, &tmA, kb * kBK, m0, full_bar(stage));
+        } else {
+#pragma unroll
+          for (int j = 0; j < kBM / 32; ++j) tma_load_2d(sa + j * (kBK * 128), &tmA, m0 + 32 * j, kb * kBK, full_bar(stage));
+        }
+        if (!b_mn) {
+          tma_load_2d(sb, &tmB, kb * kBK, n0, full_bar(stage));
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * (kBK * 128), &tmB, n0 + 32 * j, kb * kBK, full_bar(stage));
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      // instruction descriptor: c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13), a_major bit15, b_major bit16, N>>3 [17,23), M>>4 [24,29)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn ? 1 : 0) << 15) | ((uint32_t)(b_mn ? 1 : 0) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tcgen05_fence_after();
+        const uint32_t sa = base + stage * L::kStageBytes;
+        const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+        for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
+          // K-major: 8 fp32 of K = 32 B inside the 128 B swizzle row.  MN-major: 8 K-rows = one 1024 B swizzle atom.
+          const uint64_t da = a_mn ? make_smem_desc(sa + kk * 1024, tune.mn_lbo, tune.mn_sbo) : make_smem_desc(sa + kk * 32, tune.k_lbo, tune.k_sbo);
+          const uint64_t db = b_mn ? make_smem_desc(sb + kk * 1024, tune.mn_lbo, tune.mn_sbo) : make_smem_desc(sb + kk * 32, tune.k_lbo, tune.k_sbo);
+          umma_tf32(tmem_base, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+        }
+        tcgen05_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+      tcgen05_commit(accum_bar);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> fused ops -> global =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(accum_bar, 0);
+    tcgen05_fence_after();
+    const bool lead_split = (blockIdx.z == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      if (row < M) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])};
+          epilogue_store4(v, row, n0 + c * 32 + j, N, ep, lead_split);
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- SIMT bring-up kernel
+__global__ void __launch_bounds__(256) gemm_simt(const float* __restrict__ A, int a_mn, int lda, const float* __restrict__ B, int b_mn, int ldb,
+                                                 int M, int N, int K, int k_per_split, GemmEpilogue ep) {
+  __shared__ float As[16][65];
+  __shared__ float Bs[16][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  const int k_begin = blockIdx.z * k_per_split, k_end = min(K, k_begin + k_per_split);
+  float acc[4][4] = {};
+  for (int k0 = k_begin; k0 < k_end; k0 += 16) {
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      const int kk = i & 15, mm = i >> 4;
+      const int k = k0 + kk;
+      float a = 0.f, b = 0.f;
+      if (k < k_end && m0 + mm < M) a = a_mn ? A[(size_t)k * lda + m0 + mm] : A[(size_t)(m0 + mm) * lda + k];
+      if (k < k_end && n0 + mm < N) b = b_mn ? B[(size_t)k * ldb + n0 + mm] : B[(size_t)(n0 + mm) * ldb + k];
+      As[kk][mm] = a;
+      Bs[kk][mm] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+    if (row >= M) continue;
+    float v[4] = {acc[i][0], acc[i][1], acc[i][2], acc[i][3]};
+    epilogue_store4(v, row, n0 + tx * 4, N, ep, blockIdx.z == 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  uint64_t inner, outer, ld;
+  uint32_t box_inner, box_outer;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    auto mix = [&](uint64_t v) { h ^= std::hash<uint64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.inner); mix(k.outer); mix(k.ld); mix(k.box_inner); mix(k.box_outer);
+    return h;
+  }
+};
+
+class TensorMapCache {
+ public:
+  // 2-D fp32 tensor [outer][inner] with row pitch ld (floats); box = [box_outer][box_inner], SWIZZLE_128B.
+  const CUtensorMap* get(const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+    MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+    auto it = maps_.find(key);
+    if (it != maps_.end()) return &it->second;
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)"); return nullptr; }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 4)) { set_error("TMA operand must be 16-byte aligned with a pitch multiple of 4 floats"); return nullptr; }
+    CUtensorMap m;
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld * sizeof(float)};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    static const bool plain_f32 = getenv("FLEXDM_TMA_F32") != nullptr;  // default: round operands to TF32 (RN) in the TMA unit
+    CUresult r = enc(&m, plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(ptr), dims, strides, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d (inner=%llu outer=%llu ld=%llu)", (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld); return nullptr; }
+    auto res = maps_.emplace(key, m);
+    return &res.first->second;
+  }
+
+ private:
+  std::unordered_map<MapKey, CUtensorMap, MapKeyHash> maps_;
+};
+
+TensorMapCache* tensor_map_cache_create() { return new TensorMapCache(); }
+void tensor_map_cache_destroy(TensorMapCache* c) { delete c; }
+
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+  const char* s = getenv(name);
+  return s ? (uint32_t)strtoul(s, nullptr, 0) : dflt;
+}
+
+template <int BN>
+static int launch_tcgen05(TensorMapCache* cache, const GemmCall& c, cudaStream_t stream) {
+  using L = GemmSmem<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MFP_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  const CUtensorMap* ma = c.a.mn_major ? cache->get(c.a.ptr, c.M, c.K, c.a.ld, 32, kBK) : cache->get(c.a.ptr, c.K, c.M, c.a.ld, kBK, kBM);
+  const CUtensorMap* mb = c.b.mn_major ? cache->get(c.b.ptr, c.N, c.K, c.b.ld, 32, kBK) : cache->get(c.b.ptr, c.K, c.N, c.b.ld, kBK, BN);
+  if (!ma || !mb) return MFP_ERR_CUDA;
+  static const GemmTune tune = {env_u32("FLEXDM_MN_LBO", kBK * 128), env_u32("FLEXDM_MN_SBO", 1024), env_u32("FLEXDM_K_LBO", 16), env_u32("FLEXDM_K_SBO", 1024)};
+  const int num_kb = (c.K + kBK - 1) / kBK;
+  int splits = c.splits < 1 ? 1 : c.splits;
+  if (splits > num_kb) splits = num_kb;
+  const int kb_per_split = (num_kb + splits - 1) / splits;
+  splits = (num_kb + kb_per_split - 1) / kb_per_split;  // no empty split
+  GemmEpilogue ep = c.ep;
+  if (splits > 1) ep.atomic = 1;
+  dim3 grid((c.M + kBM - 1) / kBM, (c.N + BN - 1) / BN, splits);
+  gemm_tf32_tcgen05<BN><<<grid, kGemmThreads, L::kTotal, stream>>>(*ma, *mb, c.M, c.N, c.K, c.a.mn_major, c.b.mn_major, kb_per_split, ep, tune);
+  MFP_CUDA_OK(cudaGetLastError());
+  return MFP_OK;
+}
+
+int launch_gemm(TensorMapCache* cache, const GemmCall& c, int impl, cudaStream_t stream) {
+  if (c.M <= 0 || c.N <= 0 || c.K <= 0) { set_error("gemm: empty problem %dx%dx%d", c.M, c.N, c.K); return MFP_ERR_ARG; }
+  if ((c.N % 4) || (c.ep.ldo % 4)) { set_error("gemm: N and ldo must be multiples of 4 (N=%d ldo=%d)", c.N, c.ep.ldo); return MFP_ERR_ARG; }
+  if (impl == 1) {
+    int splits = c.splits < 1 ? 1 : c.splits;
+    int k_per_split = ((c.K + splits - 1) / splits + 15) / 16 * 16;
+    splits = (c.K + k_per_split - 1) / k_per_split;
+    GemmEpilogue ep = c.ep;
+    if (splits > 1) ep.atomic = 1;
+    dim3 grid((c.M + 63) / 64, (c.N + 63) / 64, splits);
+    gemm_simt<<<grid, 256, 0, stream>>>(c.a.ptr, c.a.mn_major, c.a.ld, c.b.ptr, c.b.mn_major, c.b.ld, c.M, c.N, c.K, k_per_split, ep);
+    MFP_CUDA_OK(cudaGetLastError());
+    return MFP_OK;
+  }
+  return launch_tcgen05<128>(cache, c, stream);
+}
+
+}  // namespace mfp

@@ -1,0 +1,68 @@
+// TF32 GEMM of the MFP engine: D[M,N] (+)= A[M,K] . B[N,K]^T with a fused epilogue.
+// tcgen05.mma (kind::tf32, cta_group::1) with TMEM accumulators, operands staged by TMA (SWIZZLE_128B)
+// through a 3-stage mbarrier ring; warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue.
+#pragma once
+#include "common.cuh"
+
+namespace mfp {
+
+// Operand view. K-major: memory is [rows = M|N][cols = K] row-major with pitch ld (floats).
+//               MN-major: memory is [rows = K][cols = M|N] row-major with pitch ld.
+struct GemmOperand {
+  const float* ptr;
+  int mn_major;
+  int ld;
+};
+
+// Fused epilogue, applied per element in this order:
+//   v = acc; v += bias[col]; v = relu(v); v *= (relu_src[row,col] > 0); v = dropout(v);
+//   if (rowflag[row]) v = 0; v += residual[row,col]; out[row,col] = v   (or atomicAdd when atomic != 0)
+struct GemmEpilogue {
+  float* out;
+  int ldo;
+  const float* bias;
+  const float* residual;
+  int ldr;
+  const float* relu_src;
+  int ld_relu;
+  const unsigned char* rowflag;
+  int relu;
+  int atomic;
+  int drop_enabled;
+  float drop_rate;
+  uint32_t drop_seed, drop_step, drop_site;
+};
+
+inline GemmEpilogue make_epilogue(float* out, int ldo) {
+  GemmEpilogue e{};
+  e.out = out;
+  e.ldo = ldo;
+  return e;
+}
+
+struct GemmCall {
+  GemmOperand a, b;
+  int M, N, K;
+  int splits;  // split-K factor (>1 forces atomic accumulation into a zeroed/pre-filled output)
+  GemmEpilogue ep;
+};
+
+class TensorMapCache;
+TensorMapCache* tensor_map_cache_create();
+void tensor_map_cache_destroy(TensorMapCache*);
+
+// impl: 0 = tcgen05, 1 = SIMT bring-up kernel.  Returns MFP_OK or an error (message via set_error).
+int launch_gemm(TensorMapCache* cache, const GemmCall& call, int impl, cudaStream_t stream);
+
+// keep-mask/scale of the engine's dropout sites (shared by the GEMM epilogue and the backward pass)
+__device__ __forceinline__ void dropout4(float (&v)[4], uint32_t e0, float rate, uint32_t seed, uint32_t step, uint32_t site) {
+  // e0 = index of v[0] in the flattened [T, D] activation, multiple of 4
+  const U4 r = philox4x32_10(e0 >> 2, site, 0u, 0u, seed, step);
+  const float scale = 1.0f / (1.0f - rate);
+  v[0] = (u01(r.x) >= rate) ? v[0] * scale : 0.0f;
+  v[1] = (u01(r.y) >= rate) ? v[1] * scale : 0.0f;
+  v[2] = (u01(r.z) >= rate) ? v[2] * scale : 0.0f;
+  v[3] = (u01(r.w) >= rate) ? v[3] * scale : 0.0f;
+}
+
+}  // namespace mfp

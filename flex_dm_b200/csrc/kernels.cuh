@@ -1,0 +1,61 @@
+// Host launchers of the non-GEMM kernels of the MFP engine.  Every launcher returns MFP_OK or an error code.
+#pragma once
+#include "common.cuh"
+
+namespace mfp {
+
+struct TaskSet {
+  int n;
+  int ids[16];
+};
+
+struct ModifiedPtrs {
+  void* cols[kMaxFields];          // int32 [T,C] / float [T,C]
+  unsigned char* masks[kMaxFields];  // [T] (train mode only)
+};
+
+// masking.cu
+int launch_sample_tasks(const TaskSet& allowed, int B, uint32_t seed, uint32_t step, int* tasks, cudaStream_t st);
+int launch_mask_corrupt(const Schema& sc, const BatchPtrs& in, const int* tasks, const MaskPtrs* test_masks, int B, int S, uint32_t seed,
+                        uint32_t step, const ModifiedPtrs& out, cudaStream_t st);
+int launch_row_flags(const Schema& sc, const BatchPtrs& mod, int T, unsigned char* flags /*[n_num][T]*/, cudaStream_t st);
+
+// encoder.cu
+int launch_embed_fwd(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, const float* params, int T, float* h0, cudaStream_t st);
+int launch_embed_bwd(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, const float* dh0, int T, float* grads,
+                     float* dh0_masked /*[n_num][T*D]*/, cudaStream_t st);
+
+// transformer.cu
+int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, int T, float* y, float* mean, float* rstd, cudaStream_t st);
+int launch_layernorm_bwd(const float* x, const float* dy, const float* gamma, const float* mean, const float* rstd, const float* dres, int T,
+                         float* dx, float* dgamma, float* dbeta, cudaStream_t st);
+int launch_attention_fwd(const float* qkv, const int* length, int B, int S, float* out, float* lse, cudaStream_t st);
+int launch_attention_bwd(const float* qkv, const float* out, const float* lse, const float* dout, const int* length, int B, int S, float* dqkv,
+                         cudaStream_t st);
+int launch_dropout_bwd(const float* dx, int T, float rate, uint32_t seed, uint32_t step, uint32_t site, float* dy, cudaStream_t st);
+int launch_colsum(const float* x, int rows, int cols, int ld, float* out /*atomic accumulate*/, cudaStream_t st);
+
+// loss.cu
+struct LossBuffers {
+  float* part;      // [3][F][T]: loss, score, den per (field, position)
+  int* idx_true;    // [T] permutation within each document (identity unless sorted)
+  int* idx_pred;    // [T]
+};
+int launch_sort_indices(const Schema& sc, const BatchPtrs& targets, const float* logits, const unsigned char* sort_flag, const int* sort_tasks,
+                        int pos_task_id, int B, int S,
+                        const LossBuffers& buf, cudaStream_t st);
+int launch_loss(const Schema& sc, const BatchPtrs& targets, const MaskPtrs& masks, const float* logits, int use_sort, int B, int S, float inv_batch,
+                float* dlogits /*nullable*/, const LossBuffers& buf, float* metrics_out, cudaStream_t st);
+int launch_merge_prediction(const Schema& sc, int field, const void* input_col, const unsigned char* mask, const float* logits, int T, float* out,
+                            cudaStream_t st);
+
+// optimizer.cu
+struct VarDev {
+  long long off;
+  int rows, cols, ld, l2;
+};
+int launch_regularization_loss(const VarDev* vars, int V, const float* params, float* norms /*[2][V]*/, float l2, float* out, cudaStream_t st);
+int launch_optimizer(const VarDev* vars, int V, float* params, const float* grads, float* m, float* v, float* norms /*[2][V]*/, int t, float lr,
+                     float clipnorm, float l2, float* l2_loss_out, cudaStream_t st);
+
+}  // namespace mfp

@@ -1,0 +1,142 @@
+// Input corruption of the MFP train step: preprocess_for_train / preprocess_for_test
+// (reference: src/mfp/mfp/models/mfp.py:72-138, models/masking.py:24-155,227-269).
+// One warp per element (b, s); every field of the element is produced in one pass, and only the variant the
+// document's task id selects is generated (the reference materialises all variants, then tf.where-selects).
+#include "kernels.cuh"
+
+namespace mfp {
+
+__global__ void sample_tasks_kernel(TaskSet allowed, int B, uint32_t seed, uint32_t step, int* __restrict__ tasks) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const U4 r = philox4x32_10((uint32_t)b, kFieldTask, 0u, 0u, seed, step);
+  tasks[b] = allowed.ids[mulhi_range(r.x, (uint32_t)allowed.n)];
+}
+
+__device__ __forceinline__ float2 box_muller(uint32_t xa, uint32_t xb) {
+  const float u1 = ((float)(xa >> 8) + 1.0f) * 5.9604644775390625e-08f;
+  const float u2 = u01(xb);
+  const float r = sqrtf(-2.0f * logf(u1));
+  const float t = 6.283185307179586f * u2;
+  return make_float2(r * cosf(t), r * sinf(t));
+}
+
+// mode 0: train (tasks != null), mode 1: test (test_masks given)
+__global__ void __launch_bounds__(256) mask_corrupt_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs in,
+                                                           const int* __restrict__ tasks, const __grid_constant__ MaskPtrs test_masks, int mode, int B,
+                                                           int S, uint32_t seed, uint32_t step, const __grid_constant__ ModifiedPtrs out) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= B * S) return;
+  const int b = t / S, s = t - b * S;
+  const int n_valid = in.length[b] + 1;  // mask.py:28-29
+  const bool valid = s < n_valid;
+  const int type_c = sc.f[sc.type_field].C;
+  const int type_val = reinterpret_cast<const int*>(in.cols[sc.type_field])[(size_t)t * type_c];
+  const int task = (mode == 0) ? tasks[b] : -1;
+  int elem_sel = -1;
+  if (task == 1) {  // masking.py:98-113
+    const U4 r = philox4x32_10((uint32_t)b, kFieldElem, 0u, 0u, seed, step);
+    elem_sel = (int)(u01(r.x) * (float)n_valid);
+  }
+  for (int f = 0; f < sc.F; ++f) {
+    const FieldDev fd = sc.f[f];
+    // filter_padding (masking.py:24-53)
+    const bool unused = !valid || (fd.has_cond && !((fd.cond_mask >> type_val) & 1ull));
+    int action = 0;  // 0 keep filtered, 1 <MASK>, 2 random token
+    bool mfp = false;
+    if (mode == 1) {
+      mfp = test_masks.m[f][t] != 0;
+      action = mfp ? 1 : 0;
+    } else if (task == 0) {  // random_masking (masking.py:227-269)
+      const U4 r = philox4x32_10((uint32_t)t, (uint32_t)f, kStreamRandomU, 0u, seed, step);
+      mfp = valid && (u01(r.x) < kMaskProb);
+      const bool chg = mfp && (u01(r.y) < kChangeProb);
+      if (chg) action = (u01(r.z) >= kThresh) ? 1 : 2;
+    } else if (task == 1) {  // elem_masking (masking.py:136-155)
+      mfp = (s == elem_sel);
+      action = mfp ? 1 : 0;
+    } else {  // feat_masking of one attribute group (masking.py:116-133)
+      mfp = valid && (fd.task_id == task);
+      action = mfp ? 1 : 0;
+    }
+    if (mode == 0 && lane == 0) out.masks[f][t] = mfp ? 1 : 0;
+    if (fd.kind == 0) {
+      if (lane < fd.C) {
+        const int* src = reinterpret_cast<const int*>(in.cols[f]) + (size_t)t * fd.C;
+        int v = unused ? fd.input_dim + 1 : src[lane];
+        if (action == 1) v = fd.input_dim;
+        if (action == 2) {
+          const U4 r = philox4x32_10((uint32_t)t, (uint32_t)f, kStreamRandomCat + (uint32_t)lane, 0u, seed, step);
+          v = (int)mulhi_range(r.x, (uint32_t)fd.input_dim);
+        }
+        reinterpret_cast<int*>(out.cols[f])[(size_t)t * fd.C + lane] = v;
+      }
+    } else {
+      const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in.cols[f]) + (size_t)t * fd.C);
+      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out.cols[f]) + (size_t)t * fd.C);
+      for (int q = lane; q < fd.C / 4; q += 32) {
+        float4 v;
+        if (action == 1) {
+          v = make_float4(kMaskValue, kMaskValue, kMaskValue, kMaskValue);
+        } else if (action == 2) {
+          const U4 r = philox4x32_10((uint32_t)t, (uint32_t)f, kStreamRandomNum + (uint32_t)q, 0u, seed, step);
+          const float2 z0 = box_muller(r.x, r.y), z1 = box_muller(r.z, r.w);
+          v = make_float4(z0.x * 0.1f, z0.y * 0.1f, z1.x * 0.1f, z1.y * 0.1f);  // stddev 0.1, masking.py:91
+        } else if (unused) {
+          v = make_float4(kNullValue, kNullValue, kNullValue, kNullValue);
+        } else {
+          v = src[q];
+        }
+        dst[q] = v;
+      }
+    }
+  }
+}
+
+// Encoder special-token detection by value (encoder.py:165-166): 1 = all == MASK_VALUE, 2 = all == NULL_VALUE.
+__global__ void __launch_bounds__(256) row_flags_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs mod, int T,
+                                                        unsigned char* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  for (int f = 0; f < sc.F; ++f) {
+    if (sc.f[f].kind != 1) continue;
+    const int C = sc.f[f].C;
+    const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(mod.cols[f]) + (size_t)t * C);
+    bool all_mask = true, all_null = true;
+    for (int q = lane; q < C / 4; q += 32) {
+      const float4 v = src[q];
+      all_mask = all_mask && v.x == kMaskValue && v.y == kMaskValue && v.z == kMaskValue && v.w == kMaskValue;
+      all_null = all_null && v.x == kNullValue && v.y == kNullValue && v.z == kNullValue && v.w == kNullValue;
+    }
+    all_mask = __all_sync(0xffffffffu, all_mask);
+    all_null = __all_sync(0xffffffffu, all_null);
+    if (lane == 0) flags[(size_t)sc.f[f].num_slot * T + t] = all_null ? 2 : (all_mask ? 1 : 0);  // is_unused is applied last (encoder.py:174-175)
+  }
+}
+
+int launch_sample_tasks(const TaskSet& allowed, int B, uint32_t seed, uint32_t step, int* tasks, cudaStream_t st) {
+  sample_tasks_kernel<<<(B + 127) / 128, 128, 0, st>>>(allowed, B, seed, step, tasks);
+  MFP_CUDA_OK(cudaGetLastError());
+  return MFP_OK;
+}
+
+int launch_mask_corrupt(const Schema& sc, const BatchPtrs& in, const int* tasks, const MaskPtrs* test_masks, int B, int S, uint32_t seed,
+                        uint32_t step, const ModifiedPtrs& out, cudaStream_t st) {
+  MaskPtrs tm{};
+  if (test_masks) tm = *test_masks;
+  const int T = B * S;
+  mask_corrupt_kernel<<<(T + 7) / 8, 256, 0, st>>>(sc, in, tasks, tm, test_masks ? 1 : 0, B, S, seed, step, out);
+  MFP_CUDA_OK(cudaGetLastError());
+  return MFP_OK;
+}
+
+int launch_row_flags(const Schema& sc, const BatchPtrs& mod, int T, unsigned char* flags, cudaStream_t st) {
+  if (sc.n_num == 0) return MFP_OK;
+  row_flags_kernel<<<(T + 7) / 8, 256, 0, st>>>(sc, mod, T, flags);
+  MFP_CUDA_OK(cudaGetLastError());
+  return MFP_OK;
+}
+
+}  // namespace mfp

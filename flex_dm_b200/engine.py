@@ -1,0 +1,324 @@
+"""ctypes binding of ``libflexdm_mfp.so`` (the C ABI in ``include/flexdm_mfp.h``).
+
+PyTorch is used for device memory and streams only: every tensor handed to the library is a raw device pointer,
+every call runs on ``torch.cuda.current_stream()``.  There is no CPU fallback: if the library is missing or a
+call fails this module raises.
+"""
+import ctypes
+import os
+from collections import OrderedDict
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .spec import get_attribute_groups, get_dataset_name, get_valid_input_columns
+
+MAX_FIELDS = 16
+NAME_LEN = 96
+SORT_KEYS = ["type", "left", "top", "width", "height"]  # tensor_utils.py:11
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libflexdm_mfp.so")
+_lib = None
+
+
+class FieldDesc(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 48), ("kind", ctypes.c_int32), ("C", ctypes.c_int32), ("input_dim", ctypes.c_int32),
+                ("task_id", ctypes.c_int32), ("has_cond", ctypes.c_int32), ("reserved", ctypes.c_int32), ("cond_mask", ctypes.c_uint64)]
+
+
+class Config(ctypes.Structure):
+    _fields_ = [("num_fields", ctypes.c_int32), ("type_field", ctypes.c_int32), ("latent_dim", ctypes.c_int32), ("num_blocks", ctypes.c_int32),
+                ("sort_pos", ctypes.c_int32), ("pos_task_id", ctypes.c_int32), ("total_columns", ctypes.c_int32),
+                ("sort_fields", ctypes.c_int32 * 5), ("dropout", ctypes.c_float), ("l2", ctypes.c_float)]
+
+
+class Variable(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * NAME_LEN), ("offset", ctypes.c_int64), ("rows", ctypes.c_int32), ("cols", ctypes.c_int32),
+                ("ld", ctypes.c_int32), ("l2", ctypes.c_int32)]
+
+
+class Batch(ctypes.Structure):
+    _fields_ = [("length", ctypes.c_void_p), ("cols", ctypes.c_void_p * MAX_FIELDS)]
+
+
+_PTR_ARRAY = ctypes.c_void_p * MAX_FIELDS
+
+_SIGNATURES = {
+    "mfp_last_error": (ctypes.c_char_p, []),
+    "mfp_version": (ctypes.c_int, []),
+    "mfp_create": (ctypes.c_int, [ctypes.POINTER(Config), ctypes.POINTER(FieldDesc), ctypes.POINTER(ctypes.c_void_p)]),
+    "mfp_destroy": (None, [ctypes.c_void_p]),
+    "mfp_param_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "mfp_num_variables": (ctypes.c_int32, [ctypes.c_void_p]),
+    "mfp_get_variable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(Variable)]),
+    "mfp_logit_width": (ctypes.c_int32, [ctypes.c_void_p]),
+    "mfp_field_logit_offset": (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_int32]),
+    "mfp_workspace_bytes": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32]),
+    "mfp_bind": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "mfp_sample_tasks": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint32,
+                                        ctypes.c_void_p, ctypes.c_void_p]),
+    "mfp_mask_corrupt": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Batch), ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
+                                        ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
+    "mfp_mask_for_test": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Batch), ctypes.POINTER(ctypes.c_void_p),
+                                         ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
+    "mfp_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Batch), ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p,
+                                   ctypes.c_void_p]),
+    "mfp_loss": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Batch), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_void_p,
+                                ctypes.c_void_p, ctypes.c_float, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
+    "mfp_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Batch), ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]),
+    "mfp_optimizer_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    "mfp_regularization_loss": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "mfp_merge_prediction": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p]),
+    "mfp_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "mfp_debug_gemm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                      ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                      ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
+}
+
+
+def exported_symbols() -> List[str]:
+    return list(_SIGNATURES.keys())
+
+
+def load_library():
+    """Load the CUDA extension; raises if it has not been built (``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError("flex_dm_b200: %s is missing -- build the CUDA extension first (there is no CPU fallback)" % _LIB_PATH)
+    lib = ctypes.CDLL(_LIB_PATH)
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _check(lib, rc, what):
+    if rc != 0:
+        raise EngineError("%s failed (%d): %s" % (what, rc, lib.mfp_last_error().decode("utf-8", "replace")))
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+class Engine:
+    """One ``mfp_engine`` handle plus the device buffers it is bound to."""
+
+    def __init__(self, input_columns: Dict, num_blocks: int = 4, latent_dim: int = 256, dropout: float = 0.1, l2: Optional[float] = 1e-2,
+                 device: Optional[torch.device] = None):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("flex_dm_b200: a CUDA device is required (there is no CPU fallback)")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.all_columns = input_columns
+        self.columns = get_valid_input_columns(input_columns)
+        self.keys = list(self.columns.keys())
+        if len(self.keys) > MAX_FIELDS:
+            raise ValueError("too many sequence columns")
+        from .masking import get_task_names  # local import: masking imports engine types
+
+        self.task_names = get_task_names(input_columns)
+        groups = get_attribute_groups(input_columns.keys())
+        task_of = {}
+        for gi, (gname, members) in enumerate(groups.items()):
+            for m in members:
+                task_of[m] = 2 + gi
+        fields = (FieldDesc * len(self.keys))()
+        for i, key in enumerate(self.keys):
+            c = self.columns[key]
+            fields[i].name = key.encode()
+            fields[i].kind = 0 if c["type"] == "categorical" else 1
+            fields[i].C = int(c["shape"][-1])
+            fields[i].input_dim = int(c.get("input_dim", 0))
+            fields[i].task_id = task_of.get(key, -1)
+            cond = c.get("loss_condition")
+            fields[i].has_cond = 1 if cond else 0
+            mask = 0
+            if cond:
+                if cond["key"] != "type":
+                    raise ValueError("loss_condition key must be 'type'")
+                for j, flag in enumerate(cond["mask"]):
+                    if flag:
+                        mask |= 1 << j
+            fields[i].cond_mask = mask
+        cfg = Config()
+        cfg.num_fields = len(self.keys)
+        cfg.type_field = self.keys.index("type")
+        cfg.latent_dim = latent_dim
+        cfg.num_blocks = num_blocks
+        cfg.sort_pos = 1 if get_dataset_name(input_columns.keys()) == "rico" else 0
+        cfg.pos_task_id = self.task_names.index("pos")
+        cfg.total_columns = len(input_columns)
+        for i, k in enumerate(SORT_KEYS):
+            cfg.sort_fields[i] = self.keys.index(k)
+        cfg.dropout = float(dropout)
+        cfg.l2 = -1.0 if l2 is None else float(l2)
+        self.cfg = cfg
+        handle = ctypes.c_void_p()
+        _check(self.lib, self.lib.mfp_create(ctypes.byref(cfg), fields, ctypes.byref(handle)), "mfp_create")
+        self.handle = handle
+        self.num_fields = len(self.keys)
+        self.param_count = int(self.lib.mfp_param_count(handle))
+        self.logit_width = int(self.lib.mfp_logit_width(handle))
+        self.logit_offsets = [int(self.lib.mfp_field_logit_offset(handle, f)) for f in range(self.num_fields)]
+        self.variables = OrderedDict()
+        v = Variable()
+        for i in range(int(self.lib.mfp_num_variables(handle))):
+            _check(self.lib, self.lib.mfp_get_variable(handle, i, ctypes.byref(v)), "mfp_get_variable")
+            self.variables[v.name.decode()] = (int(v.offset), int(v.rows), int(v.cols), int(v.ld), bool(v.l2))
+        with torch.cuda.device(self.device):
+            self.params = torch.zeros(self.param_count, dtype=torch.float32, device=self.device)
+            self.grads = torch.zeros_like(self.params)
+            self.adam_m = torch.zeros_like(self.params)
+            self.adam_v = torch.zeros_like(self.params)
+        self.B = self.S = 0
+        self.workspace = None
+        self.metrics_width = 3 * self.num_fields + 2  # per field loss/score_num/score_den, data loss, l2 loss
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.mfp_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ parameters
+    def variable_view(self, name: str, buf: Optional[torch.Tensor] = None) -> torch.Tensor:
+        off, rows, cols, ld, _ = self.variables[name]
+        buf = self.params if buf is None else buf
+        return buf.as_strided((rows, cols), (ld, 1), off)
+
+    def variable_shape(self, name: str):
+        """Shape of the reference variable (1-D for biases / LayerNorm parameters)."""
+        _, rows, cols, _, _ = self.variables[name]
+        last = name.rsplit("/", 1)[-1]
+        return (cols,) if last in ("bias", "gamma", "beta") else (rows, cols)
+
+    def set_weights(self, weights: Dict[str, np.ndarray]):
+        for name in self.variables:
+            if name not in weights:
+                raise KeyError("missing variable %s" % name)
+            w = torch.as_tensor(np.asarray(weights[name], dtype=np.float32)).reshape(self.variable_view(name).shape)
+            self.variable_view(name).copy_(w.to(self.device))
+
+    def get_weights(self, buf: Optional[torch.Tensor] = None) -> "OrderedDict[str, np.ndarray]":
+        out = OrderedDict()
+        for name in self.variables:
+            out[name] = self.variable_view(name, buf).detach().cpu().numpy().reshape(self.variable_shape(name)).copy()
+        return out
+
+    # ------------------------------------------------------------------ shape binding
+    def bind(self, B: int, S: int):
+        if (B, S) == (self.B, self.S) and self.workspace is not None:
+            return
+        nbytes = int(self.lib.mfp_workspace_bytes(self.handle, B, S))
+        if nbytes <= 0:
+            raise EngineError("mfp_workspace_bytes failed for B=%d S=%d" % (B, S))
+        with torch.cuda.device(self.device):
+            self.workspace = None
+            self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            base = self.workspace.data_ptr()
+            self._ws_ptr = (base + 255) // 256 * 256
+            T = B * S
+            self.modified = []
+            self.masks = []
+            for key in self.keys:
+                c = self.columns[key]
+                dt = torch.int32 if c["type"] == "categorical" else torch.float32
+                self.modified.append(torch.zeros((B, S, int(c["shape"][-1])), dtype=dt, device=self.device))
+                self.masks.append(torch.zeros((B, S), dtype=torch.uint8, device=self.device))
+            self.tasks = torch.zeros((B,), dtype=torch.int32, device=self.device)
+            self.logits = None
+        _check(self.lib, self.lib.mfp_bind(self.handle, B, S, ctypes.c_void_p(self._ws_ptr), nbytes, _ptr(self.params), _ptr(self.grads),
+                                           _ptr(self.adam_m), _ptr(self.adam_v)), "mfp_bind")
+        self.B, self.S = B, S
+        self._mod_ptrs = _PTR_ARRAY(*[t.data_ptr() for t in self.modified])
+        self._mask_ptrs = _PTR_ARRAY(*[t.data_ptr() for t in self.masks])
+
+    def _batch(self, length: torch.Tensor, cols: List[torch.Tensor]) -> Batch:
+        b = Batch()
+        b.length = length.data_ptr()
+        for i, t in enumerate(cols):
+            b.cols[i] = t.data_ptr()
+        return b
+
+    def modified_batch(self, length: torch.Tensor) -> Batch:
+        return self._batch(length, self.modified)
+
+    # ------------------------------------------------------------------ calls
+    def sample_tasks(self, allowed: List[int], seed: int, step: int):
+        arr = (ctypes.c_int32 * len(allowed))(*allowed)
+        _check(self.lib, self.lib.mfp_sample_tasks(self.handle, arr, len(allowed), seed & 0xFFFFFFFF, step & 0xFFFFFFFF, _ptr(self.tasks), _stream()),
+               "mfp_sample_tasks")
+        return self.tasks
+
+    def mask_corrupt(self, length, cols, tasks, seed: int, step: int):
+        b = self._batch(length, cols)
+        _check(self.lib, self.lib.mfp_mask_corrupt(self.handle, ctypes.byref(b), _ptr(tasks), seed & 0xFFFFFFFF, step & 0xFFFFFFFF,
+                                                   ctypes.cast(self._mod_ptrs, ctypes.POINTER(ctypes.c_void_p)),
+                                                   ctypes.cast(self._mask_ptrs, ctypes.POINTER(ctypes.c_void_p)), _stream()), "mfp_mask_corrupt")
+
+    def mask_for_test(self, length, cols, masks: List[torch.Tensor]):
+        b = self._batch(length, cols)
+        mp = _PTR_ARRAY(*[m.data_ptr() for m in masks])
+        _check(self.lib, self.lib.mfp_mask_for_test(self.handle, ctypes.byref(b), ctypes.cast(mp, ctypes.POINTER(ctypes.c_void_p)),
+                                                    ctypes.cast(self._mod_ptrs, ctypes.POINTER(ctypes.c_void_p)), _stream()), "mfp_mask_for_test")
+
+    def forward(self, length, cols: Optional[List[torch.Tensor]] = None, training: bool = False, seed: int = 0, step: int = 0,
+                logits_out: Optional[torch.Tensor] = None):
+        b = self._batch(length, self.modified if cols is None else cols)
+        _check(self.lib, self.lib.mfp_forward(self.handle, ctypes.byref(b), 1 if training else 0, seed & 0xFFFFFFFF, step & 0xFFFFFFFF,
+                                              _ptr(logits_out), _stream()), "mfp_forward")
+
+    def loss(self, length, target_cols, masks, metrics_out, inv_batch: float, compute_grad: bool, sort_flag=None, sort_tasks=None,
+             logits_in=None):
+        b = self._batch(length, target_cols)
+        mp = _PTR_ARRAY(*[m.data_ptr() for m in masks])
+        _check(self.lib, self.lib.mfp_loss(self.handle, ctypes.byref(b), ctypes.cast(mp, ctypes.POINTER(ctypes.c_void_p)), _ptr(sort_flag),
+                                           _ptr(sort_tasks), _ptr(logits_in), float(inv_batch), 1 if compute_grad else 0, _ptr(metrics_out),
+                                           _stream()), "mfp_loss")
+
+    def backward(self, length, cols: Optional[List[torch.Tensor]] = None, training: bool = True, seed: int = 0, step: int = 0):
+        b = self._batch(length, self.modified if cols is None else cols)
+        _check(self.lib, self.lib.mfp_backward(self.handle, ctypes.byref(b), 1 if training else 0, seed & 0xFFFFFFFF, step & 0xFFFFFFFF, _stream()),
+               "mfp_backward")
+
+    def optimizer_step(self, t: int, learning_rate: float, clipnorm: Optional[float], l2_out: Optional[torch.Tensor] = None):
+        _check(self.lib, self.lib.mfp_optimizer_step(self.handle, int(t), float(learning_rate), float(clipnorm) if clipnorm else 0.0, _ptr(l2_out),
+                                                     _stream()), "mfp_optimizer_step")
+
+    def regularization_loss(self, l2_out: torch.Tensor):
+        _check(self.lib, self.lib.mfp_regularization_loss(self.handle, _ptr(l2_out), _stream()), "mfp_regularization_loss")
+
+    def merge_prediction(self, field: int, input_col, mask, out, logits_in=None):
+        _check(self.lib, self.lib.mfp_merge_prediction(self.handle, field, _ptr(input_col), _ptr(mask), _ptr(logits_in), _ptr(out), _stream()),
+               "mfp_merge_prediction")
+
+    def launch_count(self) -> int:
+        return int(self.lib.mfp_launch_count(self.handle))
+
+
+def debug_gemm(A: torch.Tensor, a_mn: bool, B: torch.Tensor, b_mn: bool, M: int, N: int, K: int, bias=None, relu=False, splits=1, impl=0,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """D[M,N] = A . B^T through the engine's GEMM (bring-up / unit tests)."""
+    lib = load_library()
+    D = torch.zeros((M, N), dtype=torch.float32, device=A.device) if out is None else out
+    _check(lib, lib.mfp_debug_gemm(_ptr(A), int(a_mn), A.stride(0), _ptr(B), int(b_mn), B.stride(0), _ptr(D), D.stride(0), M, N, K, _ptr(bias),
+                                   int(relu), splits, impl, _stream()), "mfp_debug_gemm")
+    return D

@@ -1,0 +1,367 @@
+"""Host-side mirror of ``mfp/models/mfp.py``: the ``MFP`` model behind the Keras-style surface that
+``train.py`` / ``eval.py`` / the notebooks drive:
+
+    MFP(input_columns, num_blocks, block_type, masking_method, seq_type, arch_type, context, latent_dim,
+        dropout, l2, input_dtype)                                  mfp.py:215-228, train.py:53-65
+    model(inputs, training=False, demo_args=None) -> dict          mfp.py:298-347
+    model.compile(optimizer=Adam(learning_rate, clipnorm=1.0))     train.py:71-77
+    model.fit(...) / model.evaluate(...) / model.metrics_names     train.py:79-92
+    model.load_weights(path) / model.save_weights(path)            train.py:67-69,94-97
+
+All tensor work is done by the CUDA engine (``engine.py`` -> ``libflexdm_mfp.so``); this file is argument
+handling, buffer staging and bookkeeping.  Tensors in and out are ``torch`` tensors (numpy accepted on input).
+"""
+import logging
+import math
+import os
+from collections import OrderedDict
+from typing import Dict, Iterable, List, Optional
+
+import numpy as np
+import torch
+
+from .engine import Engine
+from .masking import get_task_names
+from .spec import get_dataset_name, get_valid_input_columns
+
+logger = logging.getLogger(__name__)
+
+
+class Adam:
+    """``tf.keras.optimizers.Adam(learning_rate, clipnorm)`` configuration (train.py:72-75).  beta_1 = 0.9,
+    beta_2 = 0.999, epsilon = 1e-7 are the Keras defaults the reference uses; the update itself is
+    ``csrc/optimizer.cu``."""
+
+    def __init__(self, learning_rate: float = 1e-3, clipnorm: Optional[float] = None):
+        self.learning_rate = float(learning_rate)
+        self.clipnorm = clipnorm
+        self.iterations = 0
+
+
+def get_task_ids(task_names: List[str], masking_method: str) -> List[int]:
+    """get_task_cat_dist_sampler (mfp.py:34-43): uniform over the task names listed in ``masking_method``."""
+    used_names = masking_method.split("_")
+    ids = [i for i, name in enumerate(task_names) if name in used_names]
+    assert len(ids) > 0
+    return ids
+
+
+def init_weights(engine: Engine, seed: int = 0) -> "OrderedDict[str, np.ndarray]":
+    """Keras default initialisers: Dense glorot-uniform kernel / zero bias,
+    Embedding U(-0.05, 0.05), LayerNorm gamma = 1 / beta = 0."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = OrderedDict()
+    for name in engine.variables:
+        shape = engine.variable_shape(name)
+        last = name.rsplit("/", 1)[-1]
+        if last == "embeddings":
+            w = rng.uniform(-0.05, 0.05, size=shape)
+        elif last == "kernel":
+            limit = math.sqrt(6.0 / (shape[0] + shape[1]))
+            w = rng.uniform(-limit, limit, size=shape)
+        elif last == "gamma":
+            w = np.ones(shape)
+        else:
+            w = np.zeros(shape)
+        out[name] = w.astype(np.float32)
+    return out
+
+
+class MFP:
+    """MFP trainer (mfp.py:210-347) on the B200 engine."""
+
+    def __init__(
+        self,
+        input_columns: Dict,
+        num_blocks: int = 4,
+        block_type: str = "deepsvg",
+        masking_method: str = "random",
+        seq_type: str = "default",
+        arch_type: str = "oneshot",
+        context: Optional[str] = None,
+        input_dtype: str = "set",
+        name: str = "mfp",
+        use_elemwise_noise: bool = False,
+        seed: int = 0,
+        device=None,
+        **kwargs,  # keys are latent_dim, dropout, l2
+    ):
+        assert arch_type == "oneshot"  # mfp.py:230
+        for flag, value, supported in (("block_type", block_type, "deepsvg"), ("seq_type", seq_type, "default"),
+                                       ("context", context, None), ("input_dtype", input_dtype, "set"),
+                                       ("use_elemwise_noise", use_elemwise_noise, False)):
+            if value != supported:
+                raise NotImplementedError("%s=%r is outside the B200 hot path (SURVEY.md section 8f); supported: %r" % (flag, value, supported))
+        self.name = name
+        self.arch_type = arch_type
+        self.context = context
+        self.input_dtype = input_dtype
+        self.all_columns = input_columns
+        self.input_columns = OrderedDict((k, v) for (k, v) in input_columns.items() if not v.get("demo_only", False))  # mfp.py:235-237
+        self.is_autoreg = False
+        latent_dim = kwargs.pop("latent_dim", 256)
+        dropout = kwargs.pop("dropout", 0.1)
+        l2 = kwargs.pop("l2", None)
+        if kwargs:
+            raise TypeError("unexpected arguments: %s" % sorted(kwargs))
+        self.engine = Engine(input_columns, num_blocks=num_blocks, latent_dim=latent_dim, dropout=dropout, l2=l2, device=device)
+        self.device = self.engine.device
+        self.keys = self.engine.keys
+        self.task_names = get_task_names(input_columns)
+        self.task_ids = get_task_ids(self.task_names, masking_method)
+        self.sort_pos = get_dataset_name(input_columns.keys()) == "rico"  # mfp.py:293-296
+        self.seed = int(seed)
+        self.engine.set_weights(init_weights(self.engine, seed))
+        self.optimizer: Optional[Adam] = None
+        self._step = 0  # RNG step counter (masks / dropout), advances on every stochastic call
+        self._ring = None
+        self._ring_pos = 0
+        self._world = 1
+        self._dist = None
+        self.history: List[Dict[str, float]] = []
+
+    # ------------------------------------------------------------------ distributed (document-sharded DP)
+    def enable_data_parallel(self, dist_module, world_size: int):
+        """Shard batches over documents; one all-reduce of the flat gradient buffer per step."""
+        self._dist = dist_module
+        self._world = int(world_size)
+
+    # ------------------------------------------------------------------ Keras surface
+    def compile(self, optimizer=None, run_eagerly=None, **_):
+        if optimizer is None or isinstance(optimizer, str):
+            optimizer = Adam()
+        self.optimizer = optimizer
+
+    @property
+    def metrics_names(self) -> List[str]:
+        names = ["loss"]
+        for key in self.keys:
+            names.append(key + "_score")
+        for key in self.keys:
+            names.append(key + "_loss")
+        names.append("total_score")
+        return names
+
+    # ------------------------------------------------------------------ staging
+    def stage(self, inputs: Dict, non_blocking: bool = True) -> Dict[str, torch.Tensor]:
+        """Host -> device copy of the columns the path reads (pinned host tensors copy asynchronously)."""
+        out = {}
+        for key, column in self.input_columns.items():
+            if key not in inputs:
+                if key == "length" or column["is_sequence"]:
+                    raise KeyError("missing input column %s" % key)
+                continue
+            x = inputs[key]
+            if isinstance(x, np.ndarray):
+                x = torch.from_numpy(x)
+            want = torch.float32 if column.get("type") == "numerical" else torch.int32
+            if x.dtype != want:
+                x = x.to(want)
+            if x.device != self.device:
+                x = x.to(self.device, non_blocking=non_blocking)
+            out[key] = x.contiguous()
+        return out
+
+    def _bind(self, staged: Dict[str, torch.Tensor]):
+        B, S = staged[self.keys[0]].shape[:2]
+        self.engine.bind(int(B), int(S))
+        if self._ring is None:
+            self._ring = torch.zeros((256, self.engine.metrics_width), dtype=torch.float32, device=self.device)
+        return int(B), int(S), staged["length"].reshape(-1), [staged[k] for k in self.keys]
+
+    def _next_row(self) -> torch.Tensor:
+        row = self._ring[self._ring_pos % self._ring.shape[0]]
+        self._ring_pos += 1
+        return row
+
+    # ------------------------------------------------------------------ steps
+    def train_step(self, inputs: Dict, staged: bool = False) -> torch.Tensor:
+        """Keras default train_step: sample tasks, corrupt, forward, loss, backward,
+        [all-reduce], clip + Adam.  Returns the device row of raw metrics (see ``metrics_from_row``)."""
+        if self.optimizer is None:
+            raise RuntimeError("call compile(optimizer=Adam(...)) before training")
+        data = inputs if staged else self.stage(inputs)
+        B, S, length, cols = self._bind(data)
+        eng, seed, step = self.engine, self.seed, self._step
+        row = self._next_row()
+        tasks = eng.sample_tasks(self.task_ids, seed, step)
+        eng.mask_corrupt(length, cols, tasks, seed, step)
+        eng.forward(length, None, True, seed, step)
+        eng.loss(length, cols, eng.masks, row, 1.0 / (B * self._world), True, sort_tasks=tasks if self.sort_pos else None)
+        eng.backward(length, None, True, seed, step)
+        if self._world > 1:
+            self._dist.all_reduce(eng.grads)
+        self.optimizer.iterations += 1
+        eng.optimizer_step(self.optimizer.iterations, self.optimizer.learning_rate, self.optimizer.clipnorm, row[-1:])
+        self._step += 1
+        return row
+
+    def test_step(self, inputs: Dict, staged: bool = False) -> torch.Tensor:
+        """Keras default test_step: ``self(x, training=False)`` -> the train-time corruption without dropout or update."""
+        data = inputs if staged else self.stage(inputs)
+        B, S, length, cols = self._bind(data)
+        eng, seed, step = self.engine, self.seed, self._step
+        row = self._next_row()
+        tasks = eng.sample_tasks(self.task_ids, seed, step)
+        eng.mask_corrupt(length, cols, tasks, seed, step)
+        eng.forward(length, None, False, seed, step)
+        eng.loss(length, cols, eng.masks, row, 1.0 / (B * self._world), False, sort_tasks=tasks if self.sort_pos else None)
+        eng.regularization_loss(row[-1:])
+        self._step += 1
+        return row
+
+    def metrics_from_row(self, row) -> "OrderedDict[str, float]":
+        """Names and formulas of LossLayer's add_loss / add_metric (metrics.py:279-298) from one raw metrics row."""
+        r = row.detach().cpu().numpy() if isinstance(row, torch.Tensor) else np.asarray(row)
+        F = len(self.keys)
+        out = OrderedDict()
+        out["loss"] = float(r[3 * F] + r[3 * F + 1])
+        total = 0.0
+        for f, key in enumerate(self.keys):
+            num, den = float(r[3 * f + 1]), float(r[3 * f + 2])
+            score = 1.0 if den == 0.0 else num / den
+            out[key + "_score"] = score
+            total += score
+        for f, key in enumerate(self.keys):
+            out[key + "_loss"] = float(r[3 * f])
+        out["total_score"] = total / len(self.all_columns)
+        return out
+
+    def _reduce_rows(self, rows: torch.Tensor) -> torch.Tensor:
+        if self._world > 1:
+            rows = rows.clone()
+            l2 = rows[:, -1].clone()
+            self._dist.all_reduce(rows)
+            rows[:, -1] = l2
+        return rows
+
+    def _run_epoch(self, iterator, steps: int, train: bool) -> "OrderedDict[str, float]":
+        if steps > self._ring.shape[0] if self._ring is not None else False:
+            self._ring = torch.zeros((steps, self.engine.metrics_width), dtype=torch.float32, device=self.device)
+            self._ring_pos = 0
+        rows = []
+        for _ in range(steps):
+            batch = next(iterator)
+            rows.append(self.train_step(batch) if train else self.test_step(batch))
+            if len(rows) == self._ring.shape[0]:
+                break
+        stacked = self._reduce_rows(torch.stack(rows)).cpu().numpy()
+        per_step = [self.metrics_from_row(r) for r in stacked]
+        return OrderedDict((k, float(np.mean([m[k] for m in per_step]))) for k in per_step[0])  # A15: epoch mean of add_metric values
+
+    def fit(self, dataset: Iterable, steps_per_epoch: int, epochs: int = 1, validation_data: Optional[Iterable] = None,
+            validation_steps: Optional[int] = None, validation_freq: int = 1, callbacks=None, verbose: int = 2):
+        """train.py:79-88.  ``dataset`` yields batch dicts and repeats (train.py:44-46 ``repeat=True``)."""
+        iterator = iter(dataset)
+        for epoch in range(epochs):
+            logs = self._run_epoch(iterator, steps_per_epoch, True)
+            if validation_data is not None and (epoch + 1) % max(1, validation_freq) == 0:
+                val = self._run_epoch(iter(validation_data), validation_steps or 1, False)
+                logs.update(("val_" + k, v) for k, v in val.items())
+            if not math.isfinite(logs["loss"]):  # TerminateOnNaN (helpers/callbacks.py:57)
+                logger.error("loss is not finite, terminating")
+                self.history.append(logs)
+                break
+            self.history.append(logs)
+            for cb in callbacks or []:
+                cb(epoch, logs, self)
+            if verbose:
+                logger.info("Epoch %d/%d - %s", epoch + 1, epochs, " - ".join("%s: %.4f" % kv for kv in logs.items()))
+        return self.history
+
+    def evaluate(self, dataset: Iterable, batch_size=None, steps: Optional[int] = None) -> List[float]:
+        """train.py:90: returns values in ``metrics_names`` order."""
+        if steps is None:
+            dataset = list(dataset)
+            steps = len(dataset)
+        logs = self._run_epoch(iter(dataset), steps, False)
+        return [logs[k] for k in self.metrics_names]
+
+    # ------------------------------------------------------------------ call
+    def __call__(self, inputs: Dict, training: bool = False, demo_args: Optional[Dict] = None) -> Dict[str, torch.Tensor]:
+        """MFP.call (mfp.py:298-347)."""
+        is_demo = True if demo_args else False
+        staged = self.stage(inputs)
+        B, S, length, cols = self._bind(staged)
+        eng, seed, step = self.engine, self.seed, self._step
+        tasks = eng.sample_tasks(self.task_ids, seed, step)  # mfp.py:301
+        if is_demo:
+            masks = []
+            for key in self.keys:
+                m = demo_args["masks"][key]
+                m = torch.as_tensor(m) if not isinstance(m, torch.Tensor) else m
+                masks.append(m.to(self.device).to(torch.uint8).contiguous())
+            if int(demo_args.get("num_iter", 1)) > 1:
+                raise NotImplementedError("iterative_decode (mfp.py:141-207) is a 'next' row of SURVEY.md section 8f")
+            eng.mask_for_test(length, cols, masks)  # mfp.py:72-92
+            eng.forward(length, None, training, seed, step)
+            if "tasks" in demo_args:
+                t = demo_args["tasks"]
+                tasks = (torch.as_tensor(t) if not isinstance(t, torch.Tensor) else t).to(self.device)
+        else:
+            eng.mask_corrupt(length, cols, tasks, seed, step)  # mfp.py:95-138
+            eng.forward(length, None, training, seed, step)
+            row = self._next_row()
+            eng.loss(length, cols, eng.masks, row, 1.0 / (B * self._world), False, sort_tasks=tasks if self.sort_pos else None)
+            eng.regularization_loss(row[-1:])
+            self.last_metrics_row = row
+            masks = eng.masks
+        self._step += 1
+        # merge_inputs_and_prediction (mfp.py:46-69)
+        outputs = {}
+        for key, column in self.input_columns.items():
+            if not column["is_sequence"]:
+                if key in staged:
+                    outputs[key] = staged[key]
+        for f, key in enumerate(self.keys):
+            c = self.engine.columns[key]
+            shape = (B, S, c["shape"][-1], c["input_dim"]) if c["type"] == "categorical" else (B, S, c["shape"][-1])
+            out = torch.empty(shape, dtype=torch.float32, device=self.device)
+            eng.merge_prediction(f, cols[f], masks[f], out)
+            outputs[key] = out
+        for key, column in self.all_columns.items():  # copy unpredicted items for visualization (mfp.py:66-68)
+            if column.get("demo_only", False) and key in inputs:
+                outputs[key] = inputs[key]
+        outputs["tasks"] = tasks.clone()
+        return outputs
+
+    def model(self, modified_inputs: Dict, training: bool = False, seed: Optional[int] = None, step: int = 0) -> Dict[str, torch.Tensor]:
+        """The inner boundary ``self.model(modified_inputs, training)`` = ``Model.call`` (model.py:26-30):
+        encoder -> blocks -> decoder on already-corrupted inputs; returns the raw per-field outputs
+        (decoder.py:96-110): categorical ``(B,S,C,input_dim)``, numerical ``(B,S,C)``."""
+        staged = self.stage(modified_inputs)
+        B, S, length, cols = self._bind(staged)
+        eng = self.engine
+        logits = torch.empty((B * S, eng.logit_width), dtype=torch.float32, device=self.device)
+        eng.forward(length, cols, training, self.seed if seed is None else seed, step, logits_out=logits)
+        return self.split_logits(logits, B, S)
+
+    def split_logits(self, logits: torch.Tensor, B: int, S: int) -> Dict[str, torch.Tensor]:
+        out = OrderedDict()
+        for f, key in enumerate(self.keys):
+            c = self.engine.columns[key]
+            off = self.engine.logit_offsets[f]
+            if c["type"] == "categorical":
+                w = c["shape"][-1] * c["input_dim"]
+                out[key] = logits[:, off:off + w].reshape(B, S, c["shape"][-1], c["input_dim"])
+            else:
+                out[key] = logits[:, off:off + c["shape"][-1]].reshape(B, S, c["shape"][-1])
+        return out
+
+    # ------------------------------------------------------------------ weights
+    def get_weights(self):
+        return self.engine.get_weights()
+
+    def set_weights(self, weights):
+        self.engine.set_weights(weights)
+
+    def save_weights(self, path: str):
+        """train.py:94-97.  Stored as ``<path>.npz`` keyed by the reference's variable paths."""
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        np.savez(path if path.endswith(".npz") else path + ".npz", **self.engine.get_weights())
+
+    def load_weights(self, path: str):
+        """train.py:67-69, eval.py:169-172."""
+        path = path if path.endswith(".npz") else path + ".npz"
+        with np.load(path) as data:
+            self.engine.set_weights({k: data[k] for k in data.files})

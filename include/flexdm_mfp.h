@@ -1,0 +1,151 @@
+/* flexdm_mfp.h -- C ABI of the B200-native MFP (masked field prediction) train/eval step.
+ *
+ * The reference (CyberAgentAILab/flex-dm) has no FFI: the hot path sits behind the Keras Model/Layer
+ * protocol (src/mfp/mfp/models/mfp.py:298 MFP.call; train.py:67-97; eval.py:155-172).  Each entry point
+ * below names the reference code it replaces; INTEGRATION.md shows the ctypes binding a maintainer adds
+ * (flex_dm_b200/engine.py is that binding).
+ *
+ * Conventions: every pointer is a DEVICE pointer owned by the caller unless marked "host"; every call
+ * that launches work takes a cudaStream_t (passed as void*) and is asynchronous on it; calls return
+ * MFP_OK (0) or a negative error code, and mfp_last_error() returns the message (thread-local).
+ * One handle per GPU/rank; a handle is not re-entrant, distinct handles are independent.
+ * No hidden device allocation: the caller supplies parameters, optimiser state and a workspace.
+ */
+#ifndef FLEXDM_MFP_H_
+#define FLEXDM_MFP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFP_MAX_FIELDS 16
+#define MFP_NAME_LEN 96
+
+enum { MFP_OK = 0, MFP_ERR_ARG = -1, MFP_ERR_CUDA = -2, MFP_ERR_STATE = -3, MFP_ERR_UNSUPPORTED = -4 };
+
+/* One sequence column of DataSpec.make_input_columns (data/spec.py:144-211), in
+ * get_valid_input_columns order (data/spec.py:393-403). */
+typedef struct {
+  char name[48];
+  int32_t kind;       /* 0 = categorical, 1 = numerical */
+  int32_t C;          /* column["shape"][-1]: sub-targets (categorical) or vector width (numerical) */
+  int32_t input_dim;  /* categorical vocabulary size (0 for numerical) */
+  int32_t task_id;    /* index in get_task_names (masking.py:18-21) of the attribute group holding it */
+  int32_t has_cond;   /* "loss_condition" present (crello-spec.yml:88-121) */
+  int32_t reserved;
+  uint64_t cond_mask; /* bit i set <=> loss_condition["mask"][i] */
+} mfp_field_desc;
+
+/* MFP.__init__ keyword arguments (models/mfp.py:215-228) that shape the network. */
+typedef struct {
+  int32_t num_fields;
+  int32_t type_field;  /* index of the "type" column (loss_condition key; sort key) */
+  int32_t latent_dim;  /* must be 256 in this build (heads = 8, FFN = 2*latent_dim: transformer.py:43,164) */
+  int32_t num_blocks;
+  int32_t sort_pos;    /* 1 for rico: LossLayer sort branch (mfp.py:293-296, metrics.py:180-211) */
+  int32_t pos_task_id; /* task_names.index("pos") */
+  int32_t total_columns; /* len(input_columns) incl. demo-only: total_score divisor (metrics.py:298) */
+  int32_t sort_fields[5]; /* indices of type,left,top,width,height (tensor_utils.py:11) */
+  float dropout;       /* rate of the two residual-branch Dropouts (transformer.py:174-175) */
+  float l2;            /* make_dense_options / make_emb_options coefficient (architecture/utils.py:8-22); <0 = None */
+} mfp_config;
+
+/* One trainable variable of the reference model as a strided view of the flat
+ * parameter buffer: element (r, c) lives at params[offset + r*ld + c]. */
+typedef struct {
+  char name[MFP_NAME_LEN]; /* reference attribute path, e.g. model/blocks/seq2seq/seq2seq_0/attn/dense_query/kernel */
+  int64_t offset;
+  int32_t rows, cols, ld;
+  int32_t l2;             /* regularised (Dense kernel+bias, Embedding table; not LayerNorm) */
+} mfp_variable;
+
+/* A batch as DataSpec.parse_fn emits it (data/spec.py:255-287), restricted to what the path reads. */
+typedef struct {
+  const int32_t* length;             /* [B] zero-based (mask.py:28-29) */
+  const void* cols[MFP_MAX_FIELDS];  /* categorical: int32 [B,S,C]; numerical: float [B,S,C] */
+} mfp_batch;
+
+typedef struct mfp_engine mfp_engine;
+
+const char* mfp_last_error(void);
+int mfp_version(void);
+
+/* MFP.__init__ (models/mfp.py:215-296): builds the schema, the parameter layout and the variable table. */
+int mfp_create(const mfp_config* cfg, const mfp_field_desc* fields, mfp_engine** out);
+void mfp_destroy(mfp_engine* h);
+
+/* Parameter buffer geometry (floats).  Includes alignment padding that belongs to no variable. */
+int64_t mfp_param_count(const mfp_engine* h);
+int32_t mfp_num_variables(const mfp_engine* h);
+int mfp_get_variable(const mfp_engine* h, int32_t index, mfp_variable* out);
+int32_t mfp_logit_width(const mfp_engine* h);                      /* padded row width of the logits matrix */
+int32_t mfp_field_logit_offset(const mfp_engine* h, int32_t field); /* first column of a field's head (decoder.py:96-110) */
+
+/* Workspace for a (B, S) batch shape; mfp_bind fixes the shape and all buffers (TMA descriptors are built here). */
+int64_t mfp_workspace_bytes(const mfp_engine* h, int32_t B, int32_t S);
+int mfp_bind(mfp_engine* h, int32_t B, int32_t S, void* workspace, int64_t workspace_bytes,
+             float* params, float* grads, float* adam_m, float* adam_v);
+
+/* get_task_cat_dist_sampler(...).sample(B) (models/mfp.py:34-43,301): uniform over `allowed` task ids. */
+int mfp_sample_tasks(mfp_engine* h, const int32_t* allowed_host, int32_t n_allowed, uint32_t seed, uint32_t step,
+                     int32_t* tasks_out, void* stream);
+
+/* preprocess_for_train (models/mfp.py:95-138): filter_padding + random/elem/feat masking variants selected
+ * per document by task id (masking.py:24-53,116-155,227-269).  Writes modified columns and per-field masks [B,S]. */
+int mfp_mask_corrupt(mfp_engine* h, const mfp_batch* inputs, const int32_t* tasks, uint32_t seed, uint32_t step,
+                     void* const* modified_cols, uint8_t* const* masks_out, void* stream);
+
+/* preprocess_for_test (models/mfp.py:72-92): filter_padding + apply_token(masks, "masked"). */
+int mfp_mask_for_test(mfp_engine* h, const mfp_batch* inputs, const uint8_t* const* masks,
+                      void* const* modified_cols, void* stream);
+
+/* Model.call(modified_inputs, training) (models/model.py:26-30): encoder -> blocks -> decoder.
+ * Logits land in the workspace; `logits_out` (optional, [B*S, logit_width]) receives a copy. */
+int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint32_t seed, uint32_t step,
+                float* logits_out, void* stream);
+
+/* LossLayer.call (models/metrics.py:173-299), optionally with the rico sort branch: a document is sorted when
+ * sort_flag[b] != 0 (eval.py:105-106) or, if sort_flag is NULL, when sort_tasks[b] == pos_task_id (mfp.py:336-338);
+ * both NULL = no sorting.
+ * inv_batch = 1/B_global (reduce_mean over the batch, metrics.py:277).  With compute_grad != 0 also writes
+ * d(loss)/d(logits) into the workspace for mfp_backward.  logits_in: NULL = the logits mfp_forward left in the
+ * workspace (train path, mfp.py:335-340), else a [B*S, logit_width] matrix (eval.py:104-108 passes merged predictions).
+ * metrics_out (device, 3*F+1 floats): per field loss, score_num, score_den; then the data loss total. */
+int mfp_loss(mfp_engine* h, const mfp_batch* targets, const uint8_t* const* masks, const uint8_t* sort_flag,
+             const int32_t* sort_tasks, const float* logits_in, float inv_batch, int32_t compute_grad,
+             float* metrics_out, void* stream);
+
+/* GradientTape.gradient of the data loss w.r.t. every variable (Keras default train_step).
+ * Writes the flat gradient buffer bound in mfp_bind (overwrites; the L2 term is added in the optimiser). */
+int mfp_backward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint32_t seed, uint32_t step, void* stream);
+
+/* Adam(learning_rate, clipnorm) apply_gradients (train.py:71-77) + the L2 regularisers' gradient and loss term
+ * (architecture/utils.py:8-22): g += 2*l2*w; per-variable clip_by_norm; TF-form Adam.  t = 1-based step.
+ * l2_loss_out (device float, optional) receives l2 * sum w^2 evaluated BEFORE the update. */
+int mfp_optimizer_step(mfp_engine* h, int32_t t, float learning_rate, float clipnorm, float* l2_loss_out, void* stream);
+
+/* Sum of the Keras regularisation losses, l2 * sum w^2 (architecture/utils.py:8-22), without an update:
+ * Keras' test_step (model.evaluate, train.py:90) reports loss = add_loss + regularisers too. */
+int mfp_regularization_loss(mfp_engine* h, float* l2_loss_out, void* stream);
+
+/* merge_inputs_and_prediction (models/mfp.py:46-69) for one field: logits where masked, one-hot ground
+ * truth (categorical) / input (numerical) elsewhere.  out: float [B,S,C,input_dim] or [B,S,C]. */
+int mfp_merge_prediction(mfp_engine* h, int32_t field, const void* input_col, const uint8_t* mask, const float* logits_in,
+                         float* out, void* stream);
+
+/* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
+int64_t mfp_launch_count(const mfp_engine* h);
+
+/* Bring-up hook: D[M,N] = A . B^T through the same tcgen05/TMA GEMM the engine uses.
+ * a_mn / b_mn: 0 = operand is K-major ([rows=M|N][K] row-major, pitch ld), 1 = MN-major ([K][M|N] row-major).
+ * impl: 0 = tcgen05, 1 = SIMT bring-up kernel. */
+int mfp_debug_gemm(const float* A, int32_t a_mn, int32_t lda, const float* B, int32_t b_mn, int32_t ldb,
+                   float* D, int32_t ldd, int32_t M, int32_t N, int32_t K, const float* bias, int32_t relu,
+                   int32_t splits, int32_t impl, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLEXDM_MFP_H_ */

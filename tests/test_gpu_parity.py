@@ -1,0 +1,328 @@
+"""GPU parity tests: the CUDA engine (through the C ABI, via flex_dm_b200.engine / MFP) against the CPU oracle
+on identical seeded inputs and weights.  Integer / mask work is compared bit-exactly; floating point within the
+tolerances stated in tests/helpers.py."""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from flex_dm_b200.spec import make_input_columns, make_synthetic_batch
+from oracle import mfp_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = [
+    ("crello", "random", 4, 32, 2),                   # BASELINE.json configs[0] (cfg1)
+    ("crello", "elem_pos_attr_img_txt", 5, 20, 2),
+    ("rico", "elem_pos_attr", 6, 24, 2),
+]
+
+
+def _model(dataset, method, num_blocks, dropout=0.0, l2=1e-2, seed=0):
+    from flex_dm_b200.mfp import MFP
+
+    cols = make_input_columns(dataset)
+    m = MFP(cols, num_blocks=num_blocks, masking_method=method, latent_dim=256, dropout=dropout, l2=l2, seed=seed)
+    m.set_weights(H.perturbed_weights(m.engine, seed))
+    return cols, m
+
+
+# ----------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 1), (0, 0), (1, 1)], ids=["fwd", "dgrad", "wgrad"])
+@pytest.mark.parametrize("M,N,K,splits", [(128, 128, 32, 1), (256, 256, 256, 1), (200, 1380, 256, 1), (256, 512, 1000, 4), (132, 36, 72, 1)])
+def test_gemm_layouts(impl, a_mn, b_mn, M, N, K, splits):
+    from flex_dm_b200.engine import debug_gemm
+
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, generator=g)
+    Bm = torch.randn(N, K, generator=g)
+    bias = torch.randn(N, generator=g)
+    ref = A.double() @ Bm.double().T + bias.double()
+    Ad = (A.T.contiguous() if a_mn else A.contiguous()).cuda()
+    Bd = (Bm.T.contiguous() if b_mn else Bm.contiguous()).cuda()
+    out = torch.zeros(M, N, device="cuda")
+    debug_gemm(Ad, a_mn, Bd, b_mn, M, N, K, bias=bias.cuda(), splits=splits, impl=impl, out=out)
+    torch.cuda.synchronize()
+    err = (out.cpu().double() - ref).abs().max().item()
+    scale = (A.double().abs() @ Bm.double().abs().T).max().item()
+    tol = 1e-5 if impl == 1 else 2e-3
+    assert err <= tol * scale, (err, scale)
+
+
+# ----------------------------------------------------------------------------------------------- masking (bit-exact)
+@pytest.mark.parametrize("dataset,method,B,S,L", CONFIGS)
+def test_mask_corrupt_matches_oracle(dataset, method, B, S, L):
+    cols, m = _model(dataset, method, 1)
+    batch = make_synthetic_batch(cols, B, S, seed=3, lengths="ragged")
+    staged = m.stage(batch)
+    Bq, Sq, length, dcols = m._bind(staged)
+    for step in range(3):
+        tasks = m.engine.sample_tasks(m.task_ids, 11, step).clone()
+        m.engine.mask_corrupt(length, dcols, tasks, 11, step)
+        torch.cuda.synchronize()
+        draws = O.PhiloxDraws(11, step)
+        ot = draws.tasks(B, m.task_ids)
+        assert np.array_equal(tasks.cpu().numpy(), ot)
+        _, omod, omasks = H.oracle_train_inputs(cols, batch, ot, 11, step)
+        for f, key in enumerate(m.keys):
+            got = m.engine.modified[f].cpu()
+            assert np.array_equal(m.engine.masks[f].cpu().numpy().astype(bool), omasks[key].numpy()), key
+            if cols[key]["type"] == "categorical":
+                assert np.array_equal(got.numpy(), omod[key].numpy().astype(np.int32)), key
+            else:
+                assert np.allclose(got.numpy(), omod[key].numpy(), atol=1e-6, rtol=0), key
+
+
+def test_mask_for_test_matches_oracle():
+    cols, m = _model("crello", "random", 1)
+    B, S = 3, 10
+    batch = make_synthetic_batch(cols, B, S, seed=5, lengths="ragged")
+    t = H.to_torch(batch)
+    seq = O.get_seq_mask(t["length"], S)
+    masks = O.get_initial_masks(m.input_columns, seq)
+    for key in ("left", "color", "image_embedding"):
+        masks[key] = seq
+    omod = O.preprocess_for_test(t, m.input_columns, masks)
+    staged = m.stage(batch)
+    _, _, length, dcols = m._bind(staged)
+    m.engine.mask_for_test(length, dcols, [masks[k].to(torch.uint8).cuda() for k in m.keys])
+    for f, key in enumerate(m.keys):
+        assert np.allclose(m.engine.modified[f].cpu().numpy(), omod[key].numpy(), atol=0), key
+
+
+# ----------------------------------------------------------------------------------------------- forward / loss / backward
+def _oracle_run(cols, m, batch, tasks, seed, step, drop=None):
+    targets, omod, omasks = H.oracle_train_inputs(cols, batch, tasks, seed, step)
+    params = OrderedDict((k, v.requires_grad_(True)) for k, v in H.oracle_params_from_engine(m.engine).items())
+    L = m.engine.cfg.num_blocks
+    outputs = O.model_forward(params, omod, m.input_columns, L, drop, float(m.engine.cfg.dropout))
+    sort_flag = (torch.as_tensor(tasks) == m.task_names.index("pos")) if m.sort_pos else None
+    total, losses, scores, metrics = O.loss_layer(targets, outputs, omasks, cols, sort_flag)
+    total.backward()
+    grads = OrderedDict((k, (v.grad if v.grad is not None else torch.zeros_like(v)).numpy()) for k, v in params.items())
+    return outputs, float(total.detach()), losses, scores, metrics, grads, omod, omasks
+
+
+@pytest.mark.parametrize("dataset,method,B,S,L", CONFIGS)
+def test_forward_loss_backward_match_oracle(dataset, method, B, S, L):
+    cols, m = _model(dataset, method, L)
+    batch = make_synthetic_batch(cols, B, S, seed=1, lengths="ragged")
+    staged = m.stage(batch)
+    _, _, length, dcols = m._bind(staged)
+    eng = m.engine
+    seed, step = 5, 0
+    tasks = eng.sample_tasks(m.task_ids, seed, step).clone()
+    eng.mask_corrupt(length, dcols, tasks, seed, step)
+    logits = torch.empty((B * S, eng.logit_width), device="cuda")
+    eng.forward(length, None, False, seed, step, logits_out=logits)
+    row = torch.zeros(eng.metrics_width, device="cuda")
+    eng.loss(length, dcols, eng.masks, row, 1.0 / B, True, sort_tasks=tasks if m.sort_pos else None)
+    eng.backward(length, None, False, seed, step)
+    torch.cuda.synchronize()
+
+    outputs, total, losses, scores, metrics, grads, _, _ = _oracle_run(cols, m, batch, tasks.cpu().numpy(), seed, step)
+    got = m.split_logits(logits, B, S)
+    for key in m.keys:
+        ref = outputs[key].detach().numpy()
+        err = np.abs(got[key].cpu().numpy() - ref).max()
+        assert err <= H.LOGIT_ATOL and err <= H.LOGIT_RTOL * max(1.0, np.abs(ref).max()) * 4, (key, err)
+    r = row.cpu().numpy()
+    F = len(m.keys)
+    assert r[3 * F] == pytest.approx(total, rel=H.LOSS_RTOL)
+    for f, key in enumerate(m.keys):
+        assert r[3 * f] == pytest.approx(float(losses[key]), rel=H.LOSS_RTOL, abs=1e-5), key
+        assert r[3 * f + 2] == pytest.approx(float(scores[key + "_score_den"]), abs=1e-3), key
+        # the score numerator counts argmax hits: allow one flip per 200 from TF32 near-ties
+        assert abs(r[3 * f + 1] - float(scores[key + "_score_num"])) <= max(1.0, 0.005 * float(scores[key + "_score_den"])), key
+    got_grads = eng.get_weights(eng.grads)
+    for name, g in grads.items():
+        gn = np.linalg.norm(g)
+        if gn < 1e-9:
+            assert np.linalg.norm(got_grads[name]) < 1e-6, name
+        else:
+            assert H.rel_l2(got_grads[name], g) <= H.GRAD_REL_L2, (name, H.rel_l2(got_grads[name], g))
+
+
+def test_training_dropout_matches_oracle_keep_masks():
+    cols, m = _model("crello", "random", 2, dropout=0.1)
+    B, S = 4, 16
+    batch = make_synthetic_batch(cols, B, S, seed=2, lengths="ragged")
+    staged = m.stage(batch)
+    _, _, length, dcols = m._bind(staged)
+    eng = m.engine
+    seed, step = 9, 4
+    tasks = eng.sample_tasks(m.task_ids, seed, step).clone()
+    eng.mask_corrupt(length, dcols, tasks, seed, step)
+    logits = torch.empty((B * S, eng.logit_width), device="cuda")
+    eng.forward(length, None, True, seed, step, logits_out=logits)
+    row = torch.zeros(eng.metrics_width, device="cuda")
+    eng.loss(length, dcols, eng.masks, row, 1.0 / B, True)
+    eng.backward(length, None, True, seed, step)
+    torch.cuda.synchronize()
+    draws = O.PhiloxDraws(seed, step)
+    drop = {(i, j): torch.from_numpy(draws.dropout_keep(i, j, (B, S, 256), 0.1)) for i in range(2) for j in (0, 1)}
+    outputs, total, losses, scores, metrics, grads, _, _ = _oracle_run(cols, m, batch, tasks.cpu().numpy(), seed, step, drop)
+    got = m.split_logits(logits, B, S)
+    for key in m.keys:
+        assert np.abs(got[key].cpu().numpy() - outputs[key].detach().numpy()).max() <= H.LOGIT_ATOL, key
+    assert row.cpu().numpy()[3 * len(m.keys)] == pytest.approx(total, rel=H.LOSS_RTOL)
+    got_grads = eng.get_weights(eng.grads)
+    for name in ("model/blocks/seq2seq/seq2seq_0/attn/dense_query/kernel", "model/blocks/seq2seq/seq2seq_1/mlp/layer_with_weights-1/kernel",
+                 "model/encoder/input_layer/left/embeddings"):
+        assert H.rel_l2(got_grads[name], grads[name]) <= H.GRAD_REL_L2, name
+
+
+def test_optimizer_step_matches_oracle():
+    cols, m = _model("rico", "random", 1)
+    eng = m.engine
+    eng.bind(2, 8)
+    rng = np.random.Generator(np.random.PCG64(0))
+    names = list(eng.variables.keys())
+    grads = OrderedDict((n, (rng.standard_normal(eng.variable_shape(n)) * (3.0 if i % 3 == 0 else 0.01)).astype(np.float32)) for i, n in enumerate(names))
+    p = H.oracle_params_from_engine(eng)
+    specs = O.variable_specs(cols, 1, 256)
+    om = OrderedDict((k, torch.zeros_like(v)) for k, v in p.items())
+    ov = OrderedDict((k, torch.zeros_like(v)) for k, v in p.items())
+    l2 = float(eng.cfg.l2)
+    l2_out = torch.zeros(1, device="cuda")
+    for t in (1, 2, 3):
+        eng.grads.zero_()
+        for n in names:
+            eng.variable_view(n, eng.grads).copy_(torch.from_numpy(grads[n]).reshape(eng.variable_view(n).shape).cuda())
+        expect_l2 = float(O.l2_regulariser(p, specs, l2))
+        og = OrderedDict((n, torch.tensor(grads[n], dtype=torch.float64) + (2 * l2 * p[n] if specs[n][2] else 0.0)) for n in names)
+        O.adam_step(p, og, om, ov, t, lr=1e-3, clipnorm=1.0)
+        eng.optimizer_step(t, 1e-3, 1.0, l2_out)
+        torch.cuda.synchronize()
+        assert float(l2_out.cpu()) == pytest.approx(expect_l2, rel=1e-5)
+    got = eng.get_weights()
+    for n in names:
+        assert np.abs(got[n] - p[n].numpy()).max() <= H.WEIGHT_ATOL * 3, n
+    # padding between variables is never touched
+    used = torch.zeros(eng.param_count, dtype=torch.bool)
+    for n in names:
+        eng.variable_view(n, used).fill_(True)
+    assert float(eng.params.cpu()[~used].abs().max()) == 0.0
+
+
+def test_train_steps_track_oracle_loss():
+    """'loss match' (BASELINE.json metric): same weights, same Philox-defined masks and dropout -> same loss curve."""
+    cols, m = _model("crello", "random", 2, dropout=0.1, l2=1e-2, seed=3)
+    from flex_dm_b200.mfp import Adam
+
+    m.seed = 21
+    m.compile(optimizer=Adam(learning_rate=1e-3, clipnorm=1.0))
+    o = O.OracleMFP(cols, num_blocks=2, masking_method="random", dropout=0.1, l2=1e-2, dtype=torch.float64, learning_rate=1e-3, clipnorm=1.0)
+    o.params = H.oracle_params_from_engine(m.engine)
+    o.m = OrderedDict((k, torch.zeros_like(v)) for k, v in o.params.items())
+    o.v = OrderedDict((k, torch.zeros_like(v)) for k, v in o.params.items())
+    batch = make_synthetic_batch(cols, 4, 32, seed=0, lengths="ragged")
+    for step in range(4):
+        row = m.train_step(batch)
+        got = m.metrics_from_row(row)
+        ref = o.train_step(batch, seed=21, step=step)
+        assert got["loss"] == pytest.approx(ref["loss"], rel=H.LOSS_RTOL), step
+        assert got["total_score"] == pytest.approx(ref["metrics"]["total_score"], abs=2e-2)
+    w = m.get_weights()
+    for name in ("model/blocks/seq2seq/seq2seq_1/attn/combine_heads/kernel", "model/decoder/decoders/left/kernel"):
+        assert np.abs(w[name] - o.params[name].numpy()).max() < 2e-4, name
+
+
+def test_call_outputs_merge_ground_truth():
+    cols, m = _model("crello", "random", 1)
+    B, S = 3, 12
+    batch = make_synthetic_batch(cols, B, S, seed=8, lengths="ragged")
+    t = H.to_torch(batch)
+    seq = O.get_seq_mask(t["length"], S)
+    masks = O.get_initial_masks(m.input_columns, seq)
+    masks["top"] = seq
+    masks["text_embedding"] = seq
+    out = m(batch, training=False, demo_args={"masks": masks})
+    omod = O.preprocess_for_test(t, m.input_columns, masks)
+    ref = O.model_forward(H.oracle_params_from_engine(m.engine), omod, m.input_columns, 1)
+    merged = O.merge_inputs_and_prediction(t, m.input_columns, masks, ref)
+    for key in m.keys:
+        assert out[key].shape == merged[key].shape, key
+        assert np.abs(out[key].cpu().numpy() - merged[key].numpy()).max() <= H.LOGIT_ATOL, key
+    assert np.array_equal(out["left"].cpu().numpy(), np.eye(64, dtype=np.float32)[batch["left"]])  # unmasked -> one-hot GT
+    assert np.array_equal(out["canvas_width"].cpu().numpy(), batch["canvas_width"])
+    assert out["tasks"].shape == (B,)
+
+
+def test_loss_layer_standalone_with_sort():
+    from flex_dm_b200.metrics import LossLayer
+
+    cols = make_input_columns("rico")
+    B, S = 4, 9
+    batch = make_synthetic_batch(cols, B, S, seed=4, lengths="ragged")
+    t = H.to_torch(batch)
+    seq = O.get_seq_mask(t["length"], S)
+    icols = OrderedDict((k, v) for k, v in cols.items())
+    masks = O.get_initial_masks(icols, seq)
+    for key in ("left", "top", "width", "height"):
+        masks[key] = seq
+    g = torch.Generator().manual_seed(0)
+    pred = OrderedDict()
+    for key, c in O.get_valid_input_columns(cols).items():
+        pred[key] = torch.randn(B, S, c["shape"][-1], c["input_dim"], generator=g)
+    flag = torch.tensor([True, False, True, True])
+    _, losses, scores, _ = O.loss_layer(t, {k: v.double() for k, v in pred.items()}, masks, cols, flag)
+    layer = LossLayer(cols)
+    (got,) = layer((batch, pred, masks), False, flag)
+    for k, v in scores.items():
+        assert float(got[k]) == pytest.approx(float(v), abs=1e-4), k
+    for key in layer.keys:
+        assert layer.losses[key] == pytest.approx(float(losses[key]), rel=1e-4, abs=1e-5), key
+
+
+# ----------------------------------------------------------------------------------------------- full-size properties
+def test_full_size_step_properties():
+    """BASELINE.json configs[1] shape (B=256, S=128, L=4): size-independent properties instead of the oracle."""
+    from flex_dm_b200.mfp import Adam
+
+    cols, m = _model("crello", "random", 4, dropout=0.0, l2=1e-2)
+    B, S = 256, 128
+    batch = make_synthetic_batch(cols, B, S, seed=0, lengths="ragged")
+    staged = m.stage(batch)
+    _, _, length, dcols = m._bind(staged)
+    eng = m.engine
+    tasks = eng.sample_tasks(m.task_ids, 1, 0).clone()
+    eng.mask_corrupt(length, dcols, tasks, 1, 0)
+    logits = torch.empty((B * S, eng.logit_width), device="cuda")
+    eng.forward(length, None, False, 1, 0, logits_out=logits)
+    row = torch.zeros(eng.metrics_width, device="cuda")
+    eng.loss(length, dcols, eng.masks, row, 1.0 / B, True)
+    eng.backward(length, None, False, 1, 0)
+    g1 = eng.grads.clone()
+    r1 = row.clone()
+    assert torch.isfinite(logits).all() and torch.isfinite(g1).all()
+    # (1) padded elements never influence the loss or any gradient: garble them and repeat
+    valid = (torch.arange(S, device="cuda")[None, :] <= length[:, None])
+    for f, key in enumerate(m.keys):
+        if cols[key]["type"] == "numerical":
+            eng.modified[f][~valid] = 3.25
+    eng.forward(length, None, False, 1, 0)
+    eng.loss(length, dcols, eng.masks, row, 1.0 / B, True)
+    eng.backward(length, None, False, 1, 0)
+    assert torch.allclose(row[:-1], r1[:-1], rtol=1e-5, atol=1e-6)
+    assert H.rel_l2(eng.grads.cpu().numpy(), g1.cpu().numpy()) < 1e-3  # split-K atomics reorder fp32 sums
+    # (2) documents are independent: reversing the batch order gives the same loss
+    perm = torch.arange(B - 1, -1, -1, device="cuda")
+    length2 = length[perm].contiguous()
+    cols2 = [c[perm].contiguous() for c in dcols]
+    tasks2 = tasks[perm].contiguous()
+    eng.mask_corrupt(length, dcols, tasks, 1, 0)
+    mod2 = [c[perm].contiguous() for c in eng.modified]
+    masks2 = [c[perm].contiguous() for c in eng.masks]
+    eng.forward(length2, mod2, False, 1, 0)
+    eng.loss(length2, cols2, masks2, row, 1.0 / B, False)
+    assert torch.allclose(row[:-1], r1[:-1], rtol=2e-4, atol=1e-5)
+    # (3) a few Adam steps on one batch reduce its loss
+    m.compile(optimizer=Adam(learning_rate=1e-3, clipnorm=1.0))
+    first = m.metrics_from_row(m.train_step(batch))["loss"]
+    for _ in range(5):
+        last = m.metrics_from_row(m.train_step(batch))["loss"]
+    assert np.isfinite(last) and last < first
