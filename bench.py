@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""MFP train-step throughput on synthetic crello-shaped batches (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one full pass of the hot path over one batch: sample tasks -> mask/corrupt -> encoder -> L blocks ->
+heads -> loss -> backward -> [NCCL all-reduce of the flat gradients] -> L2 + per-variable clip + Adam.
+Workload at N GPUs: BASELINE.json configs[1] (crello Ours-IMP, masking_method=random, L=4, D=256, H=8, S=128,
+256 documents per GPU, every document full length) -- weak scaling over documents.
+Prints ONE JSON line on rank 0 (see the key list in DESIGN.md "Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "MFP train-step elements/sec (crello seq_len=128)"
+UNIT = "elements/s"
+B_PER_GPU, SEQ_LEN, NUM_BLOCKS, LATENT = 256, 128, 4, 256
+N_DEVICE_BATCHES = 4  # rotate distinct resident batches: 4 x 135 MB of inputs > the 126 MB L2
+
+
+def flops_per_element(cols, S, L, D=256):
+    """F_fwd = 2 D sum(d_num) + L (16 D^2 + 4 S D) + 2 D sum(W); train = 3 x."""
+    from flex_dm_b200.spec import get_valid_input_columns
+
+    d_num = sum(c["shape"][-1] for c in get_valid_input_columns(cols).values() if c["type"] == "numerical")
+    w = sum(c["shape"][-1] * c["input_dim"] if c["type"] == "categorical" else c["shape"][-1] for c in get_valid_input_columns(cols).values())
+    gemm_fwd = 2 * D * d_num + L * 16 * D * D + 2 * D * w
+    attn_fwd = L * 4 * S * D
+    return 3 * (gemm_fwd + attn_fwd), 3 * gemm_fwd
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for line in self.lines:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                smax.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_throughput(budget_s=20.0, docs=8, threads=None):
+    """The oracle's fp32 'port' of the reference train step (all masking variants, eager op sequence) on the host
+    cores, on a bounded sample of the workload: `docs` full-length documents of the same schema / depth."""
+    import torch
+
+    from flex_dm_b200.spec import make_input_columns, make_synthetic_batch
+    from oracle import mfp_oracle as O
+
+    if threads:
+        torch.set_num_threads(threads)
+    cols = make_input_columns("crello", max_length=SEQ_LEN)
+    batch = make_synthetic_batch(cols, docs, SEQ_LEN, seed=0, lengths="full")
+    o = O.OracleMFP(cols, num_blocks=NUM_BLOCKS, masking_method="random", dropout=0.1, l2=1e-2, dtype=torch.float32)
+    o.train_step(batch, seed=0, step=0)  # warm-up
+    steps, t0 = 0, time.perf_counter()
+    while True:
+        o.train_step(batch, seed=0, step=steps + 1)
+        steps += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or steps >= 50:
+            break
+    return {"value": docs * SEQ_LEN * steps / el, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d steps of %d full-length crello documents (S=%d, L=%d, D=%d), fp32 PyTorch-CPU restatement of the TF eager op sequence "
+                      "(TensorFlow is not installable here)" % (steps, docs, SEQ_LEN, NUM_BLOCKS, LATENT)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path.  TF 2.8 cannot be installed (no wheel, Python 3.12), so this is
+    the oracle port on all host threads, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    from flex_dm_b200.spec import make_input_columns, make_synthetic_batch
+    from oracle import mfp_oracle as O
+
+    docs = 8
+    cols = make_input_columns("crello", max_length=SEQ_LEN)
+    batch = make_synthetic_batch(cols, docs, SEQ_LEN, seed=0, lengths="full")
+    o = O.OracleMFP(cols, num_blocks=NUM_BLOCKS, masking_method="random", dropout=0.1, l2=1e-2, dtype=torch.float32)
+    for i in range(args.warmup):
+        o.train_step(batch, seed=0, step=i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        o.train_step(batch, seed=0, step=args.warmup + i)
+    el = time.perf_counter() - t0
+    value = docs * SEQ_LEN * args.steps / el
+    sample = "each step = %d full-length documents (S=%d) of the crello workload; fp32 PyTorch-CPU port of the reference op sequence" % (docs, SEQ_LEN)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "crello Ours-IMP (masking_method=random) L=4 D=256 H=8 seq_len=128, CPU sample of %d documents per step" % docs},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    from flex_dm_b200.mfp import MFP, Adam
+    from flex_dm_b200.spec import make_input_columns, make_synthetic_batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    cols = make_input_columns("crello", max_length=SEQ_LEN)
+    model = MFP(cols, num_blocks=NUM_BLOCKS, masking_method="random", latent_dim=LATENT, dropout=0.1, l2=1e-2, seed=0, device=dev)
+    model.compile(optimizer=Adam(learning_rate=1e-4, clipnorm=1.0))
+    if world > 1:
+        model.enable_data_parallel(dist, world)
+        dist.broadcast(model.engine.params, 0)
+
+    # synthetic data: distinct batches per rank (seed = rank), pinned on the host for the e2e leg
+    host = [make_synthetic_batch(cols, B_PER_GPU, SEQ_LEN, seed=1000 * rank + i, lengths="full") for i in range(N_DEVICE_BATCHES)]
+    needed = [k for k, c in model.input_columns.items() if k == "length" or c["is_sequence"]]
+    pinned = [{k: torch.from_numpy(b[k]).pin_memory() for k in needed} for b in host]
+    resident = [model.stage(b) for b in pinned]
+    torch.cuda.synchronize()
+    elements_per_step = B_PER_GPU * SEQ_LEN  # every document is full length: valid elements = B*S
+    h2d_bytes = sum(t.numel() * t.element_size() for t in pinned[0].values())
+    d2h_bytes = model.engine.metrics_width * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for i in range(steps):
+            fn(i)
+        stop.record()
+        barrier()
+        ms = torch.tensor([start.elapsed_time(stop)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident leg (value)
+    def step_resident(i):
+        model.train_step(resident[i % N_DEVICE_BATCHES], staged=True)
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = model.engine.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = model.engine.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * elements_per_step * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end leg: host (pinned) batches through the public API, metrics row read back every step
+    rows_host = torch.empty((args.steps, model.engine.metrics_width), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        row = model.train_step(pinned[i % N_DEVICE_BATCHES])
+        rows_host[i % args.steps].copy_(row, non_blocking=True)
+
+    for i in range(3):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = world * elements_per_step * args.steps / (ms_e2e * 1e-3)
+    last = model.metrics_from_row(rows_host[args.steps - 1])
+    assert np.isfinite(last["loss"]), last
+
+    # ---- roofline of the dominant kernel (the TF32 tcgen05 GEMM): separate instrumented pass, CUDA events per launch
+    train_flops, gemm_flops = flops_per_element(cols, SEQ_LEN, NUM_BLOCKS, LATENT)
+    prof_steps = 3
+    torch.cuda.synchronize()
+    model.engine.profile_begin()
+    for i in range(prof_steps):
+        step_resident(i)
+    prof = model.engine.profile_end()
+    gemm_ms, gemm_launches = prof["gemm"]
+    attn_ms, attn_launches = prof["attention"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    achieved = gemm_flops * elements_per_step * prof_steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "gemm_tf32_tcgen05", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None,
+                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback") + " (no TF32 peak was measured; TF32 dense is nominally half of bf16)",
+                "gemm_ms_per_step": gemm_ms / prof_steps, "gemm_launches_per_step": gemm_launches // prof_steps,
+                "attention_ms_per_step": attn_ms / prof_steps, "attention_launches_per_step": attn_launches // prof_steps,
+                "step_tensor_roofline_frac": train_flops * elements_per_step / (ms / args.steps * 1e-3) / 1e12 / peak}
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        cpu = None if args.no_cpu_baseline else cpu_port_throughput(args.cpu_budget)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+                "data": "synthetic",
+                "config": {"workload": "crello Ours-IMP (masking_method=random) full config: L=4 D=256 H=8 FFN=512 seq_len=128, %d documents per GPU, "
+                                       "all documents full length, dropout=0.1 l2=1e-2 Adam(1e-4, clipnorm=1.0)" % B_PER_GPU,
+                           "global_batch": B_PER_GPU * world, "seq_len": SEQ_LEN, "parallelism": "dp%d" % world,
+                           "l2_flush": "inputs larger than L2: %d distinct resident batches (%.0f MB) rotate; activations per step 1.6 GB" % (N_DEVICE_BATCHES, N_DEVICE_BATCHES * h2d_bytes / 1e6),
+                           "loss_last_step": last["loss"]},
+                "roofline": roofline, "cpu_baseline": cpu,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

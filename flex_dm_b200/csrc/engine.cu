@@ -51,6 +51,9 @@ struct mfp_engine {
   TensorMapCache* maps = nullptr;
   int gemm_impl = 0;
   int64_t launches = 0;
+  // optional per-kernel-class device timing (bench.py roofline): CUDA event pairs around each launch
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events[MFP_PROFILE_CLASSES];
 };
 
 namespace mfp {
@@ -198,6 +201,20 @@ static int check_bound(const mfp_engine* h) {
   return MFP_OK;
 }
 
+struct ProfScope {
+  mfp_engine* h; int cls; cudaStream_t st; cudaEvent_t stop = nullptr;
+  ProfScope(mfp_engine* h_, int cls_, cudaStream_t st_) : h(h_), cls(cls_), st(st_) {
+    if (!h->profiling) return;
+    cudaEvent_t start;
+    cudaEventCreate(&start);
+    cudaEventCreate(&stop);
+    cudaEventRecord(start, st);
+    h->prof_events[cls].push_back(start);
+    h->prof_events[cls].push_back(stop);
+  }
+  ~ProfScope() { if (stop) cudaEventRecord(stop, st); }
+};
+
 static int gemm(mfp_engine* h, const float* A, int a_mn, int lda, const float* Bp, int b_mn, int ldb, int M, int N, int K, const GemmEpilogue& ep,
                 int splits, cudaStream_t st) {
   GemmCall c{};
@@ -207,6 +224,7 @@ static int gemm(mfp_engine* h, const float* A, int a_mn, int lda, const float* B
   c.splits = splits;
   c.ep = ep;
   h->launches++;
+  ProfScope prof(h, MFP_PROFILE_GEMM, st);
   return launch_gemm(h->maps, c, h->gemm_impl, st);
 }
 
@@ -387,7 +405,7 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
     GemmEpilogue e1 = make_epilogue(qkv, 3 * D);
     e1.bias = P + b.bqkv;
     MFP_TRY(gemm(h, ln1, 0, D, P + b.wqkv, 1, 3 * D, T, 3 * D, D, e1, 1, st));
-    MFP_TRY(launch_attention_fwd(qkv, modified->length, h->B, h->S, attn, lse, st));
+    { ProfScope prof(h, MFP_PROFILE_ATTENTION, st); MFP_TRY(launch_attention_fwd(qkv, modified->length, h->B, h->S, attn, lse, st)); }
     GemmEpilogue e2 = make_epilogue(xmid, D);
     e2.bias = P + b.bo;
     e2.residual = xi; e2.ldr = D;
@@ -497,7 +515,7 @@ int mfp_backward(mfp_engine* h, const mfp_batch* modified, int32_t training, uin
     MFP_TRY(gemm(h, attn, 1, D, dy, 1, D, D, D, T, make_epilogue(G + b.wo, D), wgrad_splits(D, D, T), st));
     MFP_TRY(launch_colsum(dy, T, D, D, G + b.bo, st));
     MFP_TRY(gemm(h, dy, 0, D, P + b.wo, 0, D, T, D, D, make_epilogue(dattn, D), 1, st));
-    MFP_TRY(launch_attention_bwd(qkv, attn, lse, dattn, modified->length, h->B, h->S, dqkv, st));
+    { ProfScope prof(h, MFP_PROFILE_ATTENTION, st); MFP_TRY(launch_attention_bwd(qkv, attn, lse, dattn, modified->length, h->B, h->S, dqkv, st)); }
     MFP_TRY(gemm(h, ln1, 1, D, dqkv, 1, 3 * D, D, 3 * D, T, make_epilogue(G + b.wqkv, 3 * D), wgrad_splits(D, 3 * D, T), st));
     MFP_TRY(launch_colsum(dqkv, T, 3 * D, 3 * D, G + b.bqkv, st));
     MFP_TRY(gemm(h, dqkv, 0, 3 * D, P + b.wqkv, 0, 3 * D, T, D, 3 * D, make_epilogue(dtmp, D), 1, st));
@@ -543,6 +561,39 @@ int mfp_merge_prediction(mfp_engine* h, int32_t field, const void* input_col, co
 }
 
 int64_t mfp_launch_count(const mfp_engine* h) { return h ? h->launches : 0; }
+
+int mfp_set_gemm_impl(mfp_engine* h, int32_t impl) {
+  if (!h || impl < 0 || impl > 1) { set_error("mfp_set_gemm_impl: bad argument"); return MFP_ERR_ARG; }
+  h->gemm_impl = impl;
+  return MFP_OK;
+}
+
+int mfp_profile_begin(mfp_engine* h) {
+  if (!h) { set_error("null engine"); return MFP_ERR_ARG; }
+  for (auto& v : h->prof_events) { for (cudaEvent_t e : v) cudaEventDestroy(e); v.clear(); }
+  h->profiling = true;
+  return MFP_OK;
+}
+
+int mfp_profile_end(mfp_engine* h, float* ms_per_class_host, int32_t* launches_per_class_host) {
+  if (!h || !ms_per_class_host || !launches_per_class_host) { set_error("mfp_profile_end: null argument"); return MFP_ERR_ARG; }
+  h->profiling = false;
+  MFP_CUDA_OK(cudaDeviceSynchronize());
+  for (int c = 0; c < MFP_PROFILE_CLASSES; ++c) {
+    float total = 0.f;
+    auto& v = h->prof_events[c];
+    for (size_t i = 0; i + 1 < v.size(); i += 2) {
+      float ms = 0.f;
+      MFP_CUDA_OK(cudaEventElapsedTime(&ms, v[i], v[i + 1]));
+      total += ms;
+    }
+    ms_per_class_host[c] = total;
+    launches_per_class_host[c] = (int32_t)(v.size() / 2);
+    for (cudaEvent_t e : v) cudaEventDestroy(e);
+    v.clear();
+  }
+  return MFP_OK;
+}
 
 int mfp_debug_gemm(const float* A, int32_t a_mn, int32_t lda, const float* B, int32_t b_mn, int32_t ldb, float* D, int32_t ldd, int32_t M, int32_t N,
                    int32_t K, const float* bias, int32_t relu, int32_t splits, int32_t impl, void* stream) {

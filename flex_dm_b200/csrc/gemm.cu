@@ -108,13 +108,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // Shared-memory matrix descriptor (SWIZZLE_128B, Blackwell version bit) -- cute/arch/mma_sm100_desc.hpp layout.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (the only layout for MN-major tf32)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address, bits [0,14)
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;  // leading byte offset, bits [16,30)
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;  // stride byte offset, bits [32,46)
   d |= 1ull << 46;                                 // descriptor version (sm_100)
-  d |= 2ull << 61;                                 // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 
@@ -218,9 +219,10 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t sb = sa + L::kABytes;
 #pragma unroll
         for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
-          // K-major: 8 fp32 of K = 32 B inside the 128 B swizzle row.  MN-major: 8 K-rows = one 1024 B swizzle atom.
-          const uint64_t da = a_mn ? make_smem_desc(sa + kk * 1024, tune.mn_lbo, tune.mn_sbo) : make_smem_desc(sa + kk * 32, tune.k_lbo, tune.k_sbo);
-          const uint64_t db = b_mn ? make_smem_desc(sb + kk * 1024, tune.mn_lbo, tune.mn_sbo) : make_smem_desc(sb + kk * 32, tune.k_lbo, tune.k_sbo);
+          // K-major: 8 fp32 of K = 32 B inside the 128 B swizzle row (SWIZZLE_128B, 8-row atoms 1024 B apart).
+          // MN-major: 8 K-rows = two 4-row 512 B atoms of SWIZZLE_128B_BASE32B (SBO), 32-wide MN chunks kBK*128 B apart (LBO).
+          const uint64_t da = a_mn ? make_smem_desc(sa + kk * 1024, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(sa + kk * 32, tune.k_lbo, tune.k_sbo, 2);
+          const uint64_t db = b_mn ? make_smem_desc(sb + kk * 1024, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(sb + kk * 32, tune.k_lbo, tune.k_sbo, 2);
           umma_tf32(tmem_base, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
         }
         tcgen05_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
@@ -314,16 +316,16 @@ static EncodeTiledFn get_encode_fn() {
 struct MapKey {
   const void* ptr;
   uint64_t inner, outer, ld;
-  uint32_t box_inner, box_outer;
+  uint32_t box_inner, box_outer, swizzle;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer;
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer && swizzle == o.swizzle;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = std::hash<const void*>()(k.ptr);
     auto mix = [&](uint64_t v) { h ^= std::hash<uint64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-    mix(k.inner); mix(k.outer); mix(k.ld); mix(k.box_inner); mix(k.box_outer);
+    mix(k.inner); mix(k.outer); mix(k.ld); mix(k.box_inner); mix(k.box_outer); mix(k.swizzle);
     return h;
   }
 };
@@ -331,8 +333,8 @@ struct MapKeyHash {
 class TensorMapCache {
  public:
   // 2-D fp32 tensor [outer][inner] with row pitch ld (floats); box = [box_outer][box_inner], SWIZZLE_128B.
-  const CUtensorMap* get(const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
-    MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+  const CUtensorMap* get(const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer, bool atom32) {
+    MapKey key{ptr, inner, outer, ld, box_inner, box_outer, atom32 ? 1u : 0u};
     auto it = maps_.find(key);
     if (it != maps_.end()) return &it->second;
     EncodeTiledFn enc = get_encode_fn();
@@ -345,7 +347,7 @@ class TensorMapCache {
     cuuint32_t estr[2] = {1, 1};
     static const bool plain_f32 = getenv("FLEXDM_TMA_F32") != nullptr;  // default: round operands to TF32 (RN) in the TMA unit
     CUresult r = enc(&m, plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(ptr), dims, strides, box,
-                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d (inner=%llu outer=%llu ld=%llu)", (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld); return nullptr; }
     auto res = maps_.emplace(key, m);
@@ -372,10 +374,10 @@ static int launch_tcgen05(TensorMapCache* cache, const GemmCall& c, cudaStream_t
     MFP_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
-  const CUtensorMap* ma = c.a.mn_major ? cache->get(c.a.ptr, c.M, c.K, c.a.ld, 32, kBK) : cache->get(c.a.ptr, c.K, c.M, c.a.ld, kBK, kBM);
-  const CUtensorMap* mb = c.b.mn_major ? cache->get(c.b.ptr, c.N, c.K, c.b.ld, 32, kBK) : cache->get(c.b.ptr, c.K, c.N, c.b.ld, kBK, BN);
+  const CUtensorMap* ma = c.a.mn_major ? cache->get(c.a.ptr, c.M, c.K, c.a.ld, 32, kBK, true) : cache->get(c.a.ptr, c.K, c.M, c.a.ld, kBK, kBM, false);
+  const CUtensorMap* mb = c.b.mn_major ? cache->get(c.b.ptr, c.N, c.K, c.b.ld, 32, kBK, true) : cache->get(c.b.ptr, c.K, c.N, c.b.ld, kBK, BN, false);
   if (!ma || !mb) return MFP_ERR_CUDA;
-  static const GemmTune tune = {env_u32("FLEXDM_MN_LBO", kBK * 128), env_u32("FLEXDM_MN_SBO", 1024), env_u32("FLEXDM_K_LBO", 16), env_u32("FLEXDM_K_SBO", 1024)};
+  static const GemmTune tune = {env_u32("FLEXDM_MN_LBO", kBK * 128), env_u32("FLEXDM_MN_SBO", 512), env_u32("FLEXDM_K_LBO", 16), env_u32("FLEXDM_K_SBO", 1024)};
   const int num_kb = (c.K + kBK - 1) / kBK;
   int splits = c.splits < 1 ? 1 : c.splits;
   if (splits > num_kb) splits = num_kb;

@@ -73,6 +73,9 @@ _SIGNATURES = {
     "mfp_merge_prediction": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                             ctypes.c_void_p]),
     "mfp_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "mfp_set_gemm_impl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
+    "mfp_profile_begin": (ctypes.c_int, [ctypes.c_void_p]),
+    "mfp_profile_end": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)]),
     "mfp_debug_gemm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
                                       ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                                       ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
@@ -309,6 +312,20 @@ class Engine:
     def merge_prediction(self, field: int, input_col, mask, out, logits_in=None):
         _check(self.lib, self.lib.mfp_merge_prediction(self.handle, field, _ptr(input_col), _ptr(mask), _ptr(logits_in), _ptr(out), _stream()),
                "mfp_merge_prediction")
+
+    def profile_begin(self):
+        _check(self.lib, self.lib.mfp_profile_begin(self.handle), "mfp_profile_begin")
+
+    def profile_end(self):
+        """-> {"gemm": (ms, launches), "attention": (ms, launches)}"""
+        ms = (ctypes.c_float * 2)()
+        n = (ctypes.c_int32 * 2)()
+        _check(self.lib, self.lib.mfp_profile_end(self.handle, ms, n), "mfp_profile_end")
+        return {"gemm": (float(ms[0]), int(n[0])), "attention": (float(ms[1]), int(n[1]))}
+
+    def set_gemm_impl(self, impl: int):
+        """0 = tcgen05 TF32 (product path), 1 = fp32 SIMT bring-up GEMM (tests only)."""
+        _check(self.lib, self.lib.mfp_set_gemm_impl(self.handle, int(impl)), "mfp_set_gemm_impl")
 
     def launch_count(self) -> int:
         return int(self.lib.mfp_launch_count(self.handle))

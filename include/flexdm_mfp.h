@@ -138,6 +138,19 @@ int mfp_merge_prediction(mfp_engine* h, int32_t field, const void* input_col, co
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t mfp_launch_count(const mfp_engine* h);
 
+/* Bring-up / test hook: 0 = tcgen05 TF32 GEMM (default, the product path), 1 = fp32 SIMT GEMM with the same
+ * epilogue.  The parity tests use 1 to pin every other kernel at fp32 accuracy, independent of TF32 rounding. */
+int mfp_set_gemm_impl(mfp_engine* h, int32_t impl);
+
+/* Optional device timing of kernel classes (bench.py's roofline): between begin and end every launch of the class is
+ * bracketed by CUDA events on the launching stream; end synchronises and returns the summed milliseconds and the
+ * launch count per class (host arrays of MFP_PROFILE_CLASSES entries).  Not meant for the throughput-timed region. */
+#define MFP_PROFILE_CLASSES 2
+#define MFP_PROFILE_GEMM 0
+#define MFP_PROFILE_ATTENTION 1
+int mfp_profile_begin(mfp_engine* h);
+int mfp_profile_end(mfp_engine* h, float* ms_per_class_host, int32_t* launches_per_class_host);
+
 /* Bring-up hook: D[M,N] = A . B^T through the same tcgen05/TMA GEMM the engine uses.
  * a_mn / b_mn: 0 = operand is K-major ([rows=M|N][K] row-major, pitch ld), 1 = MN-major ([K][M|N] row-major).
  * impl: 0 = tcgen05, 1 = SIMT bring-up kernel. */

@@ -141,7 +141,7 @@ def test_forward_loss_backward_match_oracle(dataset, method, B, S, L):
     for name, g in grads.items():
         gn = np.linalg.norm(g)
         if gn < 1e-9:
-            assert np.linalg.norm(got_grads[name]) < 1e-6, name
+            assert np.linalg.norm(got_grads[name]) < 1e-4, name  # e.g. key bias: softmax is shift-invariant
         else:
             assert H.rel_l2(got_grads[name], g) <= H.GRAD_REL_L2, (name, H.rel_l2(got_grads[name], g))
 
