@@ -13,7 +13,11 @@ from oracle import mfp_oracle as O
 LOGIT_ATOL = 2e-2      # max |logit - oracle| (logits are O(1)-O(10))
 LOGIT_RTOL = 5e-3      # relative to the oracle's max |logit| of the field
 LOSS_RTOL = 2e-3       # total / per-key loss
-GRAD_REL_L2 = 2e-2     # ||g - g_oracle||_2 / ||g_oracle||_2 per variable
+GRAD_REL_L2 = 5e-2     # ||g - g_oracle||_2 / ||g_oracle||_2 per variable (TF32 product path; tiny batches average least)
+# With the fp32 SIMT GEMM (mfp_set_gemm_impl(1)) every other kernel is pinned at fp32 accuracy:
+F32_LOGIT_ATOL = 2e-4
+F32_LOSS_RTOL = 2e-5
+F32_GRAD_REL_L2 = 2e-3  # fp32 accumulation order vs the float64 oracle (measured up to 6.2e-4)
 WEIGHT_ATOL = 2e-6     # weights after one Adam step from identical gradients
 
 

@@ -106,9 +106,12 @@ def _oracle_run(cols, m, batch, tasks, seed, step, drop=None):
     return outputs, float(total.detach()), losses, scores, metrics, grads, omod, omasks
 
 
+@pytest.mark.parametrize("impl", [1, 0], ids=["fp32-simt", "tf32-tcgen05"])
 @pytest.mark.parametrize("dataset,method,B,S,L", CONFIGS)
-def test_forward_loss_backward_match_oracle(dataset, method, B, S, L):
+def test_forward_loss_backward_match_oracle(dataset, method, B, S, L, impl):
     cols, m = _model(dataset, method, L)
+    m.engine.set_gemm_impl(impl)
+    logit_atol, loss_rtol, grad_tol = (H.F32_LOGIT_ATOL, H.F32_LOSS_RTOL, H.F32_GRAD_REL_L2) if impl == 1 else (H.LOGIT_ATOL, H.LOSS_RTOL, H.GRAD_REL_L2)
     batch = make_synthetic_batch(cols, B, S, seed=1, lengths="ragged")
     staged = m.stage(batch)
     _, _, length, dcols = m._bind(staged)
@@ -128,12 +131,12 @@ def test_forward_loss_backward_match_oracle(dataset, method, B, S, L):
     for key in m.keys:
         ref = outputs[key].detach().numpy()
         err = np.abs(got[key].cpu().numpy() - ref).max()
-        assert err <= H.LOGIT_ATOL and err <= H.LOGIT_RTOL * max(1.0, np.abs(ref).max()) * 4, (key, err)
+        assert err <= logit_atol and err <= H.LOGIT_RTOL * max(1.0, np.abs(ref).max()) * 4, (key, err)
     r = row.cpu().numpy()
     F = len(m.keys)
-    assert r[3 * F] == pytest.approx(total, rel=H.LOSS_RTOL)
+    assert r[3 * F] == pytest.approx(total, rel=loss_rtol)
     for f, key in enumerate(m.keys):
-        assert r[3 * f] == pytest.approx(float(losses[key]), rel=H.LOSS_RTOL, abs=1e-5), key
+        assert r[3 * f] == pytest.approx(float(losses[key]), rel=loss_rtol, abs=1e-5), key
         assert r[3 * f + 2] == pytest.approx(float(scores[key + "_score_den"]), abs=1e-3), key
         # the score numerator counts argmax hits: allow one flip per 200 from TF32 near-ties
         assert abs(r[3 * f + 1] - float(scores[key + "_score_num"])) <= max(1.0, 0.005 * float(scores[key + "_score_den"])), key
@@ -143,7 +146,7 @@ def test_forward_loss_backward_match_oracle(dataset, method, B, S, L):
         if gn < 1e-9:
             assert np.linalg.norm(got_grads[name]) < 1e-4, name  # e.g. key bias: softmax is shift-invariant
         else:
-            assert H.rel_l2(got_grads[name], g) <= H.GRAD_REL_L2, (name, H.rel_l2(got_grads[name], g))
+            assert H.rel_l2(got_grads[name], g) <= grad_tol, (name, H.rel_l2(got_grads[name], g))
 
 
 def test_training_dropout_matches_oracle_keep_masks():
@@ -220,6 +223,7 @@ def test_train_steps_track_oracle_loss():
     o.m = OrderedDict((k, torch.zeros_like(v)) for k, v in o.params.items())
     o.v = OrderedDict((k, torch.zeros_like(v)) for k, v in o.params.items())
     batch = make_synthetic_batch(cols, 4, 32, seed=0, lengths="ragged")
+    w0 = m.get_weights()
     for step in range(4):
         row = m.train_step(batch)
         got = m.metrics_from_row(row)
@@ -228,7 +232,12 @@ def test_train_steps_track_oracle_loss():
         assert got["total_score"] == pytest.approx(ref["metrics"]["total_score"], abs=2e-2)
     w = m.get_weights()
     for name in ("model/blocks/seq2seq/seq2seq_1/attn/combine_heads/kernel", "model/decoder/decoders/left/kernel"):
-        assert np.abs(w[name] - o.params[name].numpy()).max() < 2e-4, name
+        # Adam moves every weight by ~lr per step whatever |g| is, so a TF32-sized gradient error on a near-zero
+        # gradient entry can flip a whole lr-sized update: compare the accumulated update in relative L2, and bound
+        # the worst entry by the 4 * lr a weight can travel in 4 steps.
+        delta_ref = o.params[name].numpy() - w0[name]
+        assert H.rel_l2(w[name] - w0[name], delta_ref) < 0.1, name
+        assert np.abs(w[name] - o.params[name].numpy()).max() < 4 * 1e-3, name
 
 
 def test_call_outputs_merge_ground_truth():
