@@ -215,15 +215,22 @@ struct ProfScope {
   ~ProfScope() { if (stop) cudaEventRecord(stop, st); }
 };
 
+// colsum (optional, [N]): += sum over K of the B operand's columns -- the bias gradient of a wgrad GEMM, taken from the
+// B tiles while they sit in shared memory (tcgen05 path) or by a separate kernel (SIMT bring-up path).
 static int gemm(mfp_engine* h, const float* A, int a_mn, int lda, const float* Bp, int b_mn, int ldb, int M, int N, int K, const GemmEpilogue& ep,
-                int splits, cudaStream_t st) {
+                int splits, cudaStream_t st, float* colsum = nullptr) {
   GemmCall c{};
   c.a = GemmOperand{A, a_mn, lda};
   c.b = GemmOperand{Bp, b_mn, ldb};
   c.M = M; c.N = N; c.K = K;
   c.splits = splits;
   c.ep = ep;
+  c.colsum = (h->gemm_impl == 0) ? colsum : nullptr;
   h->launches++;
+  if (colsum && h->gemm_impl != 0) {
+    MFP_TRY(launch_colsum(Bp, K, N, ldb, colsum, st));
+    h->launches++;
+  }
   ProfScope prof(h, MFP_PROFILE_GEMM, st);
   return launch_gemm(h->maps, c, h->gemm_impl, st);
 }
@@ -474,9 +481,7 @@ int mfp_backward(mfp_engine* h, const mfp_batch* modified, int32_t training, uin
   MFP_CUDA_OK(cudaMemsetAsync(G, 0, (size_t)h->param_count * sizeof(float), st));
   // ---- heads: dX = dlogits . Wh^T ; dWh = X^T . dlogits ; dbh = colsum(dlogits)
   MFP_TRY(gemm(h, dlogits, 0, sc.LW, P + h->wh, 0, sc.LW, T, D, sc.LW, make_epilogue(dx, D), 1, st));
-  MFP_TRY(gemm(h, x + L * TD, 1, D, dlogits, 1, sc.LW, D, sc.LW, T, make_epilogue(G + h->wh, sc.LW), wgrad_splits(D, sc.LW, T), st));
-  MFP_TRY(launch_colsum(dlogits, T, sc.LW, sc.LW, G + h->bh, st));
-  h->launches++;
+  MFP_TRY(gemm(h, x + L * TD, 1, D, dlogits, 1, sc.LW, D, sc.LW, T, make_epilogue(G + h->wh, sc.LW), wgrad_splits(D, sc.LW, T), st, G + h->bh));
   for (int i = L - 1; i >= 0; --i) {
     const BlockLayout& b = h->blocks[i];
     const float* xi = x + i * TD;
@@ -496,13 +501,11 @@ int mfp_backward(mfp_engine* h, const mfp_batch* modified, int32_t training, uin
       h->launches++;
       dy = dyb;
     }
-    MFP_TRY(gemm(h, hid, 1, kF, dy, 1, D, kF, D, T, make_epilogue(G + b.w2, D), wgrad_splits(kF, D, T), st));
-    MFP_TRY(launch_colsum(dy, T, D, D, G + b.b2, st));
+    MFP_TRY(gemm(h, hid, 1, kF, dy, 1, D, kF, D, T, make_epilogue(G + b.w2, D), wgrad_splits(kF, D, T), st, G + b.b2));
     GemmEpilogue eh = make_epilogue(dhid, kF);
     eh.relu_src = hid; eh.ld_relu = kF;
     MFP_TRY(gemm(h, dy, 0, D, P + b.w2, 0, D, T, kF, D, eh, 1, st));
-    MFP_TRY(gemm(h, ln2, 1, D, dhid, 1, kF, D, kF, T, make_epilogue(G + b.w1, kF), wgrad_splits(D, kF, T), st));
-    MFP_TRY(launch_colsum(dhid, T, kF, kF, G + b.b1, st));
+    MFP_TRY(gemm(h, ln2, 1, D, dhid, 1, kF, D, kF, T, make_epilogue(G + b.w1, kF), wgrad_splits(D, kF, T), st, G + b.b1));
     MFP_TRY(gemm(h, dhid, 0, kF, P + b.w1, 0, kF, T, D, kF, make_epilogue(dtmp, D), 1, st));
     MFP_TRY(launch_layernorm_bwd(xmid, dtmp, P + b.g2, stats + 2 * T, stats + 3 * T, dx, T, dx, G + b.g2, G + b.be2, st));
     // attention branch: xmid = x_in + drop(attn.Wo + bo)
@@ -512,15 +515,13 @@ int mfp_backward(mfp_engine* h, const mfp_batch* modified, int32_t training, uin
       h->launches++;
       dy = dyb;
     }
-    MFP_TRY(gemm(h, attn, 1, D, dy, 1, D, D, D, T, make_epilogue(G + b.wo, D), wgrad_splits(D, D, T), st));
-    MFP_TRY(launch_colsum(dy, T, D, D, G + b.bo, st));
+    MFP_TRY(gemm(h, attn, 1, D, dy, 1, D, D, D, T, make_epilogue(G + b.wo, D), wgrad_splits(D, D, T), st, G + b.bo));
     MFP_TRY(gemm(h, dy, 0, D, P + b.wo, 0, D, T, D, D, make_epilogue(dattn, D), 1, st));
     { ProfScope prof(h, MFP_PROFILE_ATTENTION, st); MFP_TRY(launch_attention_bwd(qkv, attn, lse, dattn, modified->length, h->B, h->S, dqkv, st)); }
-    MFP_TRY(gemm(h, ln1, 1, D, dqkv, 1, 3 * D, D, 3 * D, T, make_epilogue(G + b.wqkv, 3 * D), wgrad_splits(D, 3 * D, T), st));
-    MFP_TRY(launch_colsum(dqkv, T, 3 * D, 3 * D, G + b.bqkv, st));
+    MFP_TRY(gemm(h, ln1, 1, D, dqkv, 1, 3 * D, D, 3 * D, T, make_epilogue(G + b.wqkv, 3 * D), wgrad_splits(D, 3 * D, T), st, G + b.bqkv));
     MFP_TRY(gemm(h, dqkv, 0, 3 * D, P + b.wqkv, 0, 3 * D, T, D, 3 * D, make_epilogue(dtmp, D), 1, st));
     MFP_TRY(launch_layernorm_bwd(xi, dtmp, P + b.g1, stats, stats + T, dx, T, dx, G + b.g1, G + b.be1, st));
-    h->launches += 7;
+    h->launches += 3;
   }
   // ---- encoder: tables / special rows / bias by shared-memory scatter; Dense kernels by wgrad GEMM
   const unsigned char* flags = wsp<unsigned char>(h, h->off.flags);
@@ -596,7 +597,8 @@ int mfp_profile_end(mfp_engine* h, float* ms_per_class_host, int32_t* launches_p
 }
 
 int mfp_debug_gemm(const float* A, int32_t a_mn, int32_t lda, const float* B, int32_t b_mn, int32_t ldb, float* D, int32_t ldd, int32_t M, int32_t N,
-                   int32_t K, const float* bias, int32_t relu, int32_t splits, int32_t impl, void* stream) {
+                   int32_t K, const float* bias, int32_t relu, const float* residual, const float* relu_src, float* colsum, int32_t splits, int32_t impl,
+                   void* stream) {
   static TensorMapCache* cache = tensor_map_cache_create();
   GemmCall c{};
   c.a = GemmOperand{A, a_mn, lda};
@@ -606,6 +608,10 @@ int mfp_debug_gemm(const float* A, int32_t a_mn, int32_t lda, const float* B, in
   c.ep = make_epilogue(D, ldd);
   c.ep.bias = bias;
   c.ep.relu = relu;
+  c.ep.residual = residual; c.ep.ldr = ldd;
+  c.ep.relu_src = relu_src; c.ep.ld_relu = ldd;
+  c.colsum = (impl == 0) ? colsum : nullptr;
+  if (colsum && impl != 0) MFP_TRY(launch_colsum(B, K, N, ldb, colsum, (cudaStream_t)stream));
   return launch_gemm(cache, c, impl, (cudaStream_t)stream);
 }
 

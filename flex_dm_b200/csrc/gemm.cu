@@ -120,58 +120,113 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 
 // ------------------------------------------------------------------------------------------------- tcgen05 kernel
+// Persistent, warp-specialised: one CTA per SM loops over output tiles (n fastest, so CTAs running together share
+// A tiles through L2).  Roles (8 warps):
+//   warp 0      TMA producer: A/B operand tiles -> kStages-deep shared-memory ring (mbarrier full/empty)
+//   warp 1      MMA issuer: one thread issues tcgen05.mma kind::tf32 into one of two TMEM accumulators
+//   warp 2      TMEM allocator; with warp 3 the optional column-sum role (bias gradients of wgrad GEMMs: sums the
+//               MN-major B tiles while they sit in shared memory, so dY is never re-read from HBM)
+//   warps 4-7   epilogue: TMEM -> registers -> fused ops -> swizzled shared staging -> TMA store (or TMA reduce-add
+//               for split-K); the residual / ReLU-mask operand arrives by TMA as well, one 32x32 chunk ahead.
+// The epilogue of tile i overlaps the main loop of tile i+1 through the double-buffered accumulator.
 constexpr int kBM = 128;        // UMMA M (one TMEM lane per row)
 constexpr int kBK = 32;         // 32 fp32 = 128 B = one swizzle row
 constexpr int kUmmaK = 8;       // tf32: 32 B of K per instruction
-constexpr int kStages = 3;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 256;
+constexpr int kEpiWarp0 = 4;    // first epilogue warp (warp & 3 = TMEM lane quarter)
+constexpr int kChunkBytes = 32 * 32 * 4;  // one 32-row x 32-column fp32 staging chunk
 
 struct GemmTune {
   uint32_t mn_lbo, mn_sbo, k_lbo, k_sbo;
 };
 
-template <int BN>
-struct GemmSmem {
-  static constexpr int kABytes = kBM * kBK * 4;
-  static constexpr int kBBytes = BN * kBK * 4;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOff = kStages * kStageBytes;
-  static constexpr int kTotal = kBarOff + 128 + 1024;  // + barriers + alignment slack
+struct GemmTiles {
+  int tiles_m, tiles_n, splits, kb_per_split;
 };
 
 template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, (BN <= 128) ? 2 : 1)
-gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-                  int a_mn, int b_mn, int kb_per_split, GemmEpilogue ep, GemmTune tune) {
+struct GemmSmem {
+  static constexpr int kStages = (BN <= 128) ? 4 : 3;
+  static constexpr int kABytes = kBM * kBK * 4;
+  static constexpr int kBBytes = BN * kBK * 4;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kEpiOff = kStages * kStageBytes;          // 4 warps x {out[2], aux[2]} chunks
+  static constexpr int kBarOff = kEpiOff + 4 * 4 * kChunkBytes;
+  static constexpr int kNumBars = 2 * kStages + 4 + 8;           // full, empty, tmem full[2]/empty[2], aux[4 warps][2]
+  static constexpr int kTotal = kBarOff + 8 * kNumBars + 16 + 1024;  // + TMEM slot + alignment slack
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// Epilogue variants are compiled in (EPI bit mask), so each instantiation carries only the code it runs: the epilogue
+// warps are issue-bound (one warp per scheduler), every dead branch in their loop costs throughput.
+enum : int { kEpiBias = 1, kEpiRelu = 2, kEpiResidual = 4, kEpiReluMask = 8, kEpiDropout = 16, kEpiRowflag = 32 };
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                  const __grid_constant__ CUtensorMap tmAux, int M, int N, int K, int a_mn, int b_mn, GemmTiles tl, GemmEpilogue ep,
+                  float* __restrict__ colsum, GemmTune tune) {
+  constexpr int aux_mode = (EPI & kEpiResidual) ? 1 : ((EPI & kEpiReluMask) ? 2 : 0);
   using L = GemmSmem<BN>;
+  constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bar_base = base + L::kBarOff;
-  // barriers: full[kStages], empty[kStages], accum; then the TMEM base address slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  const uint32_t accum_bar = bar_base + 8u * (2 * kStages);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 1);
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  auto aux_bar = [&](int w, int b) { return bar_base + 8u * (2 * kStages + 4 + 2 * w + b); };
+  const uint32_t tmem_slot = bar_base + 8u * L::kNumBars;
+  const uint32_t* tmem_slot_ptr = reinterpret_cast<const uint32_t*>(base_ptr + L::kBarOff + 8 * L::kNumBars);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBM;
-  const int n0 = blockIdx.y * BN;
   const int num_kb = (K + kBK - 1) / kBK;
-  const int kb0 = blockIdx.z * kb_per_split;
-  const int kb1 = min(num_kb, kb0 + kb_per_split);
+  const int tiles_mn = tl.tiles_m * tl.tiles_n;
+  const int num_tiles = tiles_mn * tl.splits;
+  const bool do_colsum = (colsum != nullptr);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), do_colsum ? 3 : 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    for (int w = 0; w < 4; ++w) {
+      mbar_init(aux_bar(w, 0), 1);
+      mbar_init(aux_bar(w, 1), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    prefetch_tensormap(&tmOut);
+    if (aux_mode != 0) prefetch_tensormap(&tmAux);
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(2 * BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
@@ -184,24 +239,29 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t sa = base + stage * L::kStageBytes;
-        const uint32_t sb = sa + L::kABytes;
-        mbar_expect_tx(full_bar(stage), L::kStageBytes);
-        if (!a_mn) {
-          tma_load_2d(sa, &tmA, kb * kBK, m0, full_bar(stage));
-        } else {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile / tiles_mn, r = tile - split * tiles_mn;
+        const int m0 = (r / tl.tiles_n) * kBM, n0 = (r % tl.tiles_n) * BN;
+        const int kb0 = split * tl.kb_per_split, kb1 = min(num_kb, kb0 + tl.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = base + stage * L::kStageBytes;
+          const uint32_t sb = sa + L::kABytes;
+          mbar_expect_tx(full_bar(stage), L::kStageBytes);
+          if (!a_mn) {
+            tma_load_2d(sa, &tmA, kb * kBK, m0, full_bar(stage));
+          } else {
 #pragma unroll
-          for (int j = 0; j < kBM / 32; ++j) tma_load_2d(sa + j * (kBK * 128), &tmA, m0 + 32 * j, kb * kBK, full_bar(stage));
-        }
-        if (!b_mn) {
-          tma_load_2d(sb, &tmB, kb * kBK, n0, full_bar(stage));
-        } else {
+            for (int j = 0; j < kBM / 32; ++j) tma_load_2d(sa + j * (kBK * 128), &tmA, m0 + 32 * j, kb * kBK, full_bar(stage));
+          }
+          if (!b_mn) {
+            tma_load_2d(sb, &tmB, kb * kBK, n0, full_bar(stage));
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * (kBK * 128), &tmB, n0 + 32 * j, kb * kBK, full_bar(stage));
+            for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * (kBK * 128), &tmB, n0 + 32 * j, kb * kBK, full_bar(stage));
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -210,50 +270,170 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // instruction descriptor: c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13), a_major bit15, b_major bit16, N>>3 [17,23), M>>4 [24,29)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn ? 1 : 0) << 15) | ((uint32_t)(b_mn ? 1 : 0) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile / tiles_mn;
+        const int kb0 = split * tl.kb_per_split, kb1 = min(num_kb, kb0 + tl.kb_per_split);
+        mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = base + stage * L::kStageBytes;
+          const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+          for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
+            // K-major: 8 fp32 of K = 32 B inside the 128 B swizzle row (SWIZZLE_128B, 8-row atoms 1024 B apart).
+            // MN-major: 8 K-rows = two 4-row 512 B atoms of SWIZZLE_128B_BASE32B (SBO), 32-wide MN chunks kBK*128 B apart (LBO).
+            const uint64_t da = a_mn ? make_smem_desc(sa + kk * 1024, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(sa + kk * 32, tune.k_lbo, tune.k_sbo, 2);
+            const uint64_t db = b_mn ? make_smem_desc(sb + kk * 1024, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(sb + kk * 32, tune.k_lbo, tune.k_sbo, 2);
+            umma_tf32(tacc, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        tcgen05_commit(tfull_bar(as));  // accumulator complete
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
+    }
+  } else if (warp < kEpiWarp0) {
+    // ===== column sums of the MN-major B tiles (bias gradient), m-tile 0 only =====
+    if (do_colsum) {
+      const int tid = threadIdx.x - 64;  // 0..63
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(full_bar(stage), phase);
-        tcgen05_fence_after();
-        const uint32_t sa = base + stage * L::kStageBytes;
-        const uint32_t sb = sa + L::kABytes;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile / tiles_mn, r = tile - split * tiles_mn;
+        const bool active = (r / tl.tiles_n) == 0;
+        const int n0 = (r % tl.tiles_n) * BN;
+        const int kb0 = split * tl.kb_per_split, kb1 = min(num_kb, kb0 + tl.kb_per_split);
+        float acc[BN / 64];
 #pragma unroll
-        for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
-          // K-major: 8 fp32 of K = 32 B inside the 128 B swizzle row (SWIZZLE_128B, 8-row atoms 1024 B apart).
-          // MN-major: 8 K-rows = two 4-row 512 B atoms of SWIZZLE_128B_BASE32B (SBO), 32-wide MN chunks kBK*128 B apart (LBO).
-          const uint64_t da = a_mn ? make_smem_desc(sa + kk * 1024, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(sa + kk * 32, tune.k_lbo, tune.k_sbo, 2);
-          const uint64_t db = b_mn ? make_smem_desc(sb + kk * 1024, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(sb + kk * 32, tune.k_lbo, tune.k_sbo, 2);
-          umma_tf32(tmem_base, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+        for (int i = 0; i < BN / 64; ++i) acc[i] = 0.f;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          if (active) {
+            const uint8_t* sb = base_ptr + stage * L::kStageBytes + L::kABytes;
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) {
+              const int col = tid + 64 * i;
+              const uint8_t* cb = sb + (col >> 5) * (kBK * 128) + (col & 7) * 4;
+              const int u = (col & 31) >> 3;
+#pragma unroll 8
+              for (int k = 0; k < kBK; ++k) acc[i] += *reinterpret_cast<const float*>(cb + k * 128 + ((u ^ (k & 3)) << 5));
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty_bar(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        tcgen05_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        if (active) {
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i) {
+            const int col = n0 + tid + 64 * i;
+            if (col < N) atomicAdd(colsum + col, acc[i]);
+          }
+        }
       }
-      tcgen05_commit(accum_bar);  // accumulator complete
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> fused ops -> global =====
+    // ===== epilogue: TMEM -> registers -> fused ops -> swizzled staging -> TMA store =====
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    mbar_wait(accum_bar, 0);
-    tcgen05_fence_after();
-    const bool lead_split = (blockIdx.z == 0);
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-      if (row < M) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])};
-          epilogue_store4(v, row, n0 + c * 32 + j, N, ep, lead_split);
-        }
+    const uint32_t epi = base + L::kEpiOff + q * (4 * kChunkBytes);
+    uint8_t* epi_ptr = base_ptr + L::kEpiOff + q * (4 * kChunkBytes);
+    const uint32_t sw = (uint32_t)(lane & 7);
+    int as = 0, ob = 0;
+    uint32_t aphase = 0, auxphase0 = 0, auxphase1 = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int split = tile / tiles_mn, r = tile - split * tiles_mn;
+      const int m0 = (r / tl.tiles_n) * kBM, n0 = (r % tl.tiles_n) * BN;
+      const int row0 = m0 + q * 32;
+      const int row = row0 + lane;
+      const bool lead_split = (split == 0);
+      const bool use_aux = aux_mode != 0 && (aux_mode == 2 || lead_split);
+      const int nchunks = min(BN / 32, (N - n0 + 31) / 32);
+      if (use_aux && lane == 0) {
+        mbar_expect_tx(aux_bar(q, 0), kChunkBytes);
+        tma_load_2d(epi + 2 * kChunkBytes, &tmAux, n0, row0, aux_bar(q, 0));
       }
+      bool flagged = false;
+      if constexpr (EPI & kEpiRowflag) flagged = row < M && ep.rowflag[row];
+      mbar_wait(tfull_bar(as), aphase);
+      tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < nchunks; ++c) {
+        const int col0 = n0 + c * 32;
+        if (use_aux && c + 1 < nchunks && lane == 0) {
+          const int b = (c + 1) & 1;
+          mbar_expect_tx(aux_bar(q, b), kChunkBytes);
+          tma_load_2d(epi + (2 + b) * kChunkBytes, &tmAux, col0 + 32, row0, aux_bar(q, b));
+        }
+        // bias of this chunk's 32 columns: issued before the TMEM load so its latency hides behind it
+        float4 bv[8];
+        if constexpr (EPI & kEpiBias) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            bv[j] = (lead_split && col0 + 4 * j < N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        uint32_t rr[32];
+        tmem_ld32(tacc + (uint32_t)(c * 32), rr);
+        if (use_aux) {
+          if (c & 1) { mbar_wait(aux_bar(q, 1), auxphase1); auxphase1 ^= 1u; }
+          else { mbar_wait(aux_bar(q, 0), auxphase0); auxphase0 ^= 1u; }
+        }
+        if (lane == 0) tma_wait_group_read<1>();  // the staging buffer about to be overwritten has been read out
+        __syncwarp();
+        const uint8_t* auxp = epi_ptr + (2 + (c & 1)) * kChunkBytes + lane * 128;
+        uint8_t* outp = epi_ptr + ob * kChunkBytes + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v[4] = {__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3])};
+          if constexpr (EPI & kEpiBias) { v[0] += bv[j].x; v[1] += bv[j].y; v[2] += bv[j].z; v[3] += bv[j].w; }
+          if constexpr (EPI & kEpiRelu) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.0f);
+          }
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          if constexpr (aux_mode != 0) {
+            if (use_aux) a = *reinterpret_cast<const float4*>(auxp + ((j ^ sw) << 4));
+          }
+          if constexpr (aux_mode == 2) {
+            v[0] = a.x > 0.0f ? v[0] : 0.0f; v[1] = a.y > 0.0f ? v[1] : 0.0f;
+            v[2] = a.z > 0.0f ? v[2] : 0.0f; v[3] = a.w > 0.0f ? v[3] : 0.0f;
+          }
+          if constexpr (EPI & kEpiDropout)
+            dropout4(v, (uint32_t)row * (uint32_t)N + (uint32_t)(col0 + 4 * j), ep.drop_rate, ep.drop_seed, ep.drop_step, ep.drop_site);
+          if constexpr (EPI & kEpiRowflag) {
+            if (flagged) { v[0] = v[1] = v[2] = v[3] = 0.0f; }
+          }
+          if constexpr (aux_mode == 1) { v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; }
+          *reinterpret_cast<float4*>(outp + ((j ^ sw) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (ep.atomic) tma_reduce_add_2d(&tmOut, epi + ob * kChunkBytes, col0, row0);
+          else tma_store_2d(&tmOut, epi + ob * kChunkBytes, col0, row0);
+          tma_commit_group();
+        }
+        ob ^= 1;
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
     }
+    if (lane == 0) tma_wait_group_read<0>();
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
   }
 }
 
@@ -313,28 +493,33 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+enum MapKind : uint32_t { kMapOperandK = 0, kMapOperandMN = 1, kMapEpilogue = 2 };
+
 struct MapKey {
   const void* ptr;
   uint64_t inner, outer, ld;
-  uint32_t box_inner, box_outer, swizzle;
+  uint32_t box_inner, box_outer, kind;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer && swizzle == o.swizzle;
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer && kind == o.kind;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = std::hash<const void*>()(k.ptr);
     auto mix = [&](uint64_t v) { h ^= std::hash<uint64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-    mix(k.inner); mix(k.outer); mix(k.ld); mix(k.box_inner); mix(k.box_outer); mix(k.swizzle);
+    mix(k.inner); mix(k.outer); mix(k.ld); mix(k.box_inner); mix(k.box_outer); mix(k.kind);
     return h;
   }
 };
 
 class TensorMapCache {
  public:
-  // 2-D fp32 tensor [outer][inner] with row pitch ld (floats); box = [box_outer][box_inner], SWIZZLE_128B.
-  const CUtensorMap* get(const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer, bool atom32) {
-    MapKey key{ptr, inner, outer, ld, box_inner, box_outer, atom32 ? 1u : 0u};
+  // 2-D fp32 tensor [outer][inner] with row pitch ld (floats); box = [box_outer][box_inner].
+  //   kMapOperandK : MMA operand, K-major, SWIZZLE_128B, values rounded to TF32 (RN) by the TMA unit
+  //   kMapOperandMN: MMA operand, MN-major, SWIZZLE_128B_ATOM_32B (the only MN-major layout for 32-bit types), TF32
+  //   kMapEpilogue : epilogue staging chunks (store / reduce-add / residual load), SWIZZLE_128B, plain fp32
+  const CUtensorMap* get(const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer, MapKind kind) {
+    MapKey key{ptr, inner, outer, ld, box_inner, box_outer, (uint32_t)kind};
     auto it = maps_.find(key);
     if (it != maps_.end()) return &it->second;
     EncodeTiledFn enc = get_encode_fn();
@@ -346,8 +531,9 @@ class TensorMapCache {
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
     static const bool plain_f32 = getenv("FLEXDM_TMA_F32") != nullptr;  // default: round operands to TF32 (RN) in the TMA unit
-    CUresult r = enc(&m, plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(ptr), dims, strides, box,
-                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    const CUtensorMapDataType dt = (kind == kMapEpilogue || plain_f32) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+    const CUtensorMapSwizzle sw = (kind == kMapOperandMN) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+    CUresult r = enc(&m, dt, 2, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d (inner=%llu outer=%llu ld=%llu)", (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld); return nullptr; }
     auto res = maps_.emplace(key, m);
@@ -366,27 +552,47 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
   return s ? (uint32_t)strtoul(s, nullptr, 0) : dflt;
 }
 
-template <int BN>
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int EPI>
 static int launch_tcgen05(TensorMapCache* cache, const GemmCall& c, cudaStream_t stream) {
   using L = GemmSmem<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    MFP_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    MFP_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tcgen05<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
-  const CUtensorMap* ma = c.a.mn_major ? cache->get(c.a.ptr, c.M, c.K, c.a.ld, 32, kBK, true) : cache->get(c.a.ptr, c.K, c.M, c.a.ld, kBK, kBM, false);
-  const CUtensorMap* mb = c.b.mn_major ? cache->get(c.b.ptr, c.N, c.K, c.b.ld, 32, kBK, true) : cache->get(c.b.ptr, c.K, c.N, c.b.ld, kBK, BN, false);
-  if (!ma || !mb) return MFP_ERR_CUDA;
+  if (c.ep.residual && c.ep.relu_src) { set_error("gemm: residual and relu_src cannot be combined"); return MFP_ERR_ARG; }
+  if (c.colsum && !c.b.mn_major) { set_error("gemm: the fused column sum needs an MN-major B operand"); return MFP_ERR_ARG; }
+  const CUtensorMap* ma = c.a.mn_major ? cache->get(c.a.ptr, c.M, c.K, c.a.ld, 32, kBK, kMapOperandMN) : cache->get(c.a.ptr, c.K, c.M, c.a.ld, kBK, kBM, kMapOperandK);
+  const CUtensorMap* mb = c.b.mn_major ? cache->get(c.b.ptr, c.N, c.K, c.b.ld, 32, kBK, kMapOperandMN) : cache->get(c.b.ptr, c.K, c.N, c.b.ld, kBK, BN, kMapOperandK);
+  const CUtensorMap* mo = cache->get(c.ep.out, c.N, c.M, c.ep.ldo, 32, 32, kMapEpilogue);
+  const CUtensorMap* mx = mo;
+  if (c.ep.residual) mx = cache->get(c.ep.residual, c.N, c.M, c.ep.ldr, 32, 32, kMapEpilogue);
+  if (c.ep.relu_src) mx = cache->get(c.ep.relu_src, c.N, c.M, c.ep.ld_relu, 32, 32, kMapEpilogue);
+  if (!ma || !mb || !mo || !mx) return MFP_ERR_CUDA;
   static const GemmTune tune = {env_u32("FLEXDM_MN_LBO", kBK * 128), env_u32("FLEXDM_MN_SBO", 512), env_u32("FLEXDM_K_LBO", 16), env_u32("FLEXDM_K_SBO", 1024)};
   const int num_kb = (c.K + kBK - 1) / kBK;
   int splits = c.splits < 1 ? 1 : c.splits;
   if (splits > num_kb) splits = num_kb;
-  const int kb_per_split = (num_kb + splits - 1) / splits;
-  splits = (num_kb + kb_per_split - 1) / kb_per_split;  // no empty split
+  GemmTiles tl;
+  tl.kb_per_split = (num_kb + splits - 1) / splits;
+  tl.splits = (num_kb + tl.kb_per_split - 1) / tl.kb_per_split;  // no empty split
+  tl.tiles_m = (c.M + kBM - 1) / kBM;
+  tl.tiles_n = (c.N + BN - 1) / BN;
   GemmEpilogue ep = c.ep;
-  if (splits > 1) ep.atomic = 1;
-  dim3 grid((c.M + kBM - 1) / kBM, (c.N + BN - 1) / BN, splits);
-  gemm_tf32_tcgen05<BN><<<grid, kGemmThreads, L::kTotal, stream>>>(*ma, *mb, c.M, c.N, c.K, c.a.mn_major, c.b.mn_major, kb_per_split, ep, tune);
+  if (tl.splits > 1) ep.atomic = 1;
+  const int num_tiles = tl.tiles_m * tl.tiles_n * tl.splits;
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  gemm_tf32_tcgen05<BN, EPI><<<grid, kGemmThreads, L::kTotal, stream>>>(*ma, *mb, *mo, *mx, c.M, c.N, c.K, c.a.mn_major, c.b.mn_major, tl, ep, c.colsum,
+                                                                       tune);
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
@@ -395,6 +601,7 @@ int launch_gemm(TensorMapCache* cache, const GemmCall& c, int impl, cudaStream_t
   if (c.M <= 0 || c.N <= 0 || c.K <= 0) { set_error("gemm: empty problem %dx%dx%d", c.M, c.N, c.K); return MFP_ERR_ARG; }
   if ((c.N % 4) || (c.ep.ldo % 4)) { set_error("gemm: N and ldo must be multiples of 4 (N=%d ldo=%d)", c.N, c.ep.ldo); return MFP_ERR_ARG; }
   if (impl == 1) {
+    if (c.colsum) { set_error("gemm: the SIMT bring-up kernel has no fused column sum"); return MFP_ERR_ARG; }
     int splits = c.splits < 1 ? 1 : c.splits;
     int k_per_split = ((c.K + splits - 1) / splits + 15) / 16 * 16;
     splits = (c.K + k_per_split - 1) / k_per_split;
@@ -405,7 +612,23 @@ int launch_gemm(TensorMapCache* cache, const GemmCall& c, int impl, cudaStream_t
     MFP_CUDA_OK(cudaGetLastError());
     return MFP_OK;
   }
-  return launch_tcgen05<128>(cache, c, stream);
+  const int epi = (c.ep.bias ? kEpiBias : 0) | (c.ep.relu ? kEpiRelu : 0) | (c.ep.residual ? kEpiResidual : 0) | (c.ep.relu_src ? kEpiReluMask : 0) |
+                  (c.ep.drop_enabled ? kEpiDropout : 0) | (c.ep.rowflag ? kEpiRowflag : 0);
+#define MFP_GEMM_CASE(E) \
+  case (E): return (c.N <= 128) ? launch_tcgen05<128, (E)>(cache, c, stream) : launch_tcgen05<256, (E)>(cache, c, stream);
+  switch (epi) {
+    MFP_GEMM_CASE(0)                                           // dgrad / wgrad
+    MFP_GEMM_CASE(kEpiBias)                                    // QKV, heads
+    MFP_GEMM_CASE(kEpiBias | kEpiRelu)                         // FFN 1
+    MFP_GEMM_CASE(kEpiBias | kEpiResidual)                     // attention output / FFN 2, eval
+    MFP_GEMM_CASE(kEpiBias | kEpiResidual | kEpiDropout)       // attention output / FFN 2, training
+    MFP_GEMM_CASE(kEpiResidual | kEpiRowflag)                  // encoder Dense of a numerical field
+    MFP_GEMM_CASE(kEpiReluMask)                                // dgrad through the FFN ReLU
+    default:
+      set_error("gemm: epilogue combination 0x%x is not instantiated", epi);
+      return MFP_ERR_UNSUPPORTED;
+  }
+#undef MFP_GEMM_CASE
 }
 
 }  // namespace mfp

@@ -1,6 +1,7 @@
 // TF32 GEMM of the MFP engine: D[M,N] (+)= A[M,K] . B[N,K]^T with a fused epilogue.
-// tcgen05.mma (kind::tf32, cta_group::1) with TMEM accumulators, operands staged by TMA (SWIZZLE_128B)
-// through a 3-stage mbarrier ring; warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue.
+// Persistent tcgen05.mma kernel (kind::tf32, cta_group::1): operands staged by TMA (SWIZZLE_128B) through an mbarrier
+// ring, two TMEM accumulators so the epilogue of one tile overlaps the main loop of the next, epilogue through
+// swizzled shared staging and TMA store / reduce-add.  See gemm.cu for the warp roles.
 #pragma once
 #include "common.cuh"
 
@@ -45,6 +46,7 @@ struct GemmCall {
   int M, N, K;
   int splits;  // split-K factor (>1 forces atomic accumulation into a zeroed/pre-filled output)
   GemmEpilogue ep;
+  float* colsum;  // optional [N]: += column sums of the (MN-major) B operand over K, i.e. the bias gradient of a wgrad GEMM
 };
 
 class TensorMapCache;

@@ -78,7 +78,8 @@ _SIGNATURES = {
     "mfp_profile_end": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)]),
     "mfp_debug_gemm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
                                       ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
-                                      ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
+                                      ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                      ctypes.c_void_p]),
 }
 
 
@@ -332,10 +333,12 @@ class Engine:
 
 
 def debug_gemm(A: torch.Tensor, a_mn: bool, B: torch.Tensor, b_mn: bool, M: int, N: int, K: int, bias=None, relu=False, splits=1, impl=0,
-               out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """D[M,N] = A . B^T through the engine's GEMM (bring-up / unit tests)."""
+               out: Optional[torch.Tensor] = None, residual=None, relu_src=None, colsum=None) -> torch.Tensor:
+    """D[M,N] = epilogue(A . B^T) through the engine's GEMM (bring-up / unit tests); residual / relu_src share D's pitch."""
     lib = load_library()
     D = torch.zeros((M, N), dtype=torch.float32, device=A.device) if out is None else out
+    for t in (residual, relu_src):
+        assert t is None or t.stride(0) == D.stride(0)
     _check(lib, lib.mfp_debug_gemm(_ptr(A), int(a_mn), A.stride(0), _ptr(B), int(b_mn), B.stride(0), _ptr(D), D.stride(0), M, N, K, _ptr(bias),
-                                   int(relu), splits, impl, _stream()), "mfp_debug_gemm")
+                                   int(relu), _ptr(residual), _ptr(relu_src), _ptr(colsum), splits, impl, _stream()), "mfp_debug_gemm")
     return D

@@ -151,12 +151,14 @@ int mfp_set_gemm_impl(mfp_engine* h, int32_t impl);
 int mfp_profile_begin(mfp_engine* h);
 int mfp_profile_end(mfp_engine* h, float* ms_per_class_host, int32_t* launches_per_class_host);
 
-/* Bring-up hook: D[M,N] = A . B^T through the same tcgen05/TMA GEMM the engine uses.
+/* Bring-up hook: D[M,N] = epilogue(A . B^T) through the same tcgen05/TMA GEMM the engine uses.
  * a_mn / b_mn: 0 = operand is K-major ([rows=M|N][K] row-major, pitch ld), 1 = MN-major ([K][M|N] row-major).
- * impl: 0 = tcgen05, 1 = SIMT bring-up kernel. */
+ * Optional epilogue operands: bias [N]; relu != 0; residual [M,N] (pitch ldd) added last; relu_src [M,N] (pitch ldd):
+ * result zeroed where relu_src <= 0; colsum [N] += column sums of the MN-major B operand (bias gradient of a wgrad).
+ * splits > 1 accumulates into D (which must be pre-filled).  impl: 0 = tcgen05, 1 = SIMT bring-up kernel. */
 int mfp_debug_gemm(const float* A, int32_t a_mn, int32_t lda, const float* B, int32_t b_mn, int32_t ldb,
                    float* D, int32_t ldd, int32_t M, int32_t N, int32_t K, const float* bias, int32_t relu,
-                   int32_t splits, int32_t impl, void* stream);
+                   const float* residual, const float* relu_src, float* colsum, int32_t splits, int32_t impl, void* stream);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,45 @@ def test_gemm_layouts(impl, a_mn, b_mn, M, N, K, splits):
     assert err <= tol * scale, (err, scale)
 
 
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("M,N,K", [(300, 256, 256), (1000, 520, 64), (128, 36, 40)])
+def test_gemm_fused_epilogues(impl, M, N, K):
+    """bias + ReLU, residual add (in place), ReLU mask of a dgrad, and the fused bias-gradient column sum of a wgrad."""
+    from flex_dm_b200.engine import debug_gemm
+
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g)
+    bias = torch.randn(N, generator=g)
+    R = torch.randn(M, N, generator=g)
+    tol = 1e-5 if impl == 1 else 2e-3
+    scale = (A.double().abs() @ W.double().abs().T).max().item()
+    Ad, Wd, bd = A.cuda(), W.cuda(), bias.cuda()
+    # bias + relu
+    out = debug_gemm(Ad, 0, Wd, 0, M, N, K, bias=bd, relu=True, impl=impl)
+    ref = torch.relu(A.double() @ W.double().T + bias.double())
+    assert (out.cpu().double() - ref).abs().max().item() <= tol * scale
+    # residual, in place (out aliases the residual, as in the encoder)
+    x = R.cuda().clone()
+    debug_gemm(Ad, 0, Wd, 0, M, N, K, bias=bd, impl=impl, out=x, residual=x)
+    ref = A.double() @ W.double().T + bias.double() + R.double()
+    assert (x.cpu().double() - ref).abs().max().item() <= tol * scale
+    # relu mask
+    out = debug_gemm(Ad, 0, Wd, 0, M, N, K, impl=impl, relu_src=R.cuda())
+    ref = (A.double() @ W.double().T) * (R.double() > 0)
+    assert (out.cpu().double() - ref).abs().max().item() <= tol * scale
+    # wgrad with split-K and the fused column sum: D[K', N'] = X^T . dY, colsum = sum_rows dY   (rows = M tokens)
+    X = torch.randn(M, K, generator=g)
+    dY = torch.randn(M, N, generator=g)
+    out = torch.zeros(K, N, device="cuda")
+    cs = torch.zeros(N, device="cuda")
+    debug_gemm(X.cuda(), 1, dY.cuda(), 1, K, N, M, splits=3, impl=impl, out=out, colsum=cs)
+    ref = X.double().T @ dY.double()
+    wscale = (X.double().abs().T @ dY.double().abs()).max().item()
+    assert (out.cpu().double() - ref).abs().max().item() <= tol * wscale
+    assert (cs.cpu().double() - dY.double().sum(0)).abs().max().item() <= 1e-4 * dY.abs().sum(0).max().item()
+
+
 # ----------------------------------------------------------------------------------------------- masking (bit-exact)
 @pytest.mark.parametrize("dataset,method,B,S,L", CONFIGS)
 def test_mask_corrupt_matches_oracle(dataset, method, B, S, L):
@@ -144,7 +183,10 @@ def test_forward_loss_backward_match_oracle(dataset, method, B, S, L, impl):
     for name, g in grads.items():
         gn = np.linalg.norm(g)
         if gn < 1e-9:
-            assert np.linalg.norm(got_grads[name]) < 1e-4, name  # e.g. key bias: softmax is shift-invariant
+            # e.g. the key bias: softmax is shift-invariant, so its exact gradient is 0 and what is left is the rounding
+            # noise of the column sum of dK -- bound it relative to the gradient of the kernel it belongs to
+            sibling = np.linalg.norm(grads[name.replace("/bias", "/kernel")])
+            assert np.linalg.norm(got_grads[name]) <= grad_tol * max(sibling, 1e-6), name
         else:
             assert H.rel_l2(got_grads[name], g) <= grad_tol, (name, H.rel_l2(got_grads[name], g))
 
