@@ -1,0 +1,237 @@
+// Masked multi-head self-attention core on the 5th-generation tensor cores (reference: architecture/transformer.py:60-76).
+//
+// One "unit" = one (document, head): Q, K, V tiles of [S <= 128 elements][32] fp32 cut straight out of the [T, 3D] QKV
+// activation by 3-D TMA maps ([B][S][3D]: rows past the document end are out of bounds, so they load as zeros and are
+// clipped on store -- no padding copies, no cross-document reads).  Per unit:
+//   S = Q K^T          tcgen05.mma kind::tf32, both operands K-major in shared memory, accumulator [128 x 128] in TMEM
+//   P = softmax(S/sqrt(dh)) over the document's valid keys: one thread per query row reads its row from TMEM (no
+//       cross-thread reduction at all), writes the unnormalised probabilities (rounded to TF32) back IN PLACE
+//   O = P V            tcgen05.mma with the A operand read from TMEM and V (MN-major) from shared memory; only the
+//       ceil(n/8) key slabs that hold valid keys are issued
+//   O / rowsum -> swizzled staging -> TMA store into the head's 32 columns of the [T, D] output; lse for the backward.
+// Persistent CTAs loop over units; a 3-slot TMA ring, two score buffers and two output buffers in TMEM let the loads
+// and S = QK^T of unit i+1 run under the softmax of unit i, and the epilogue of unit i-1 run while P V of unit i is in
+// flight.  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4-7 = softmax + epilogue.
+#include "gemm.cuh"
+#include "kernels.cuh"
+#include "tc.cuh"
+
+namespace mfp {
+
+constexpr int kAtRows = 128;                    // queries / keys per unit tile
+constexpr int kAtTileBytes = kAtRows * kDh * 4;  // 16 KB: [128][32] fp32, 128 B rows
+constexpr int kAtThreads = 256;
+constexpr float kAtScale = 0.17677669529663687f;  // 1/sqrt(32), transformer.py:62-63
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ------------------------------------------------------------------------------------------------- forward
+constexpr int kFwdSlots = 3;
+struct AttnFwdSmem {
+  static constexpr int kSlotBytes = 3 * kAtTileBytes;                 // Q, K, V
+  static constexpr int kStageOff = kFwdSlots * kSlotBytes;            // 4 warps x 2 x [32][32] fp32 output staging
+  static constexpr int kBarOff = kStageOff + 4 * 2 * 4096;
+  static constexpr int kNumBars = 2 * kFwdSlots + 6;                  // full, empty, s_full[2], p_ready[2], o_full[2]
+  static constexpr int kTotal = kBarOff + 8 * kNumBars + 16 + 1024;
+};
+
+__global__ void __launch_bounds__(kAtThreads, 1)
+attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                        const int* __restrict__ length, int B, int S, float* __restrict__ lse) {
+  using L = AttnFwdSmem;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_base = base + L::kBarOff;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kFwdSlots + s); };
+  auto sfull_bar = [&](int a) { return bar_base + 8u * (2 * kFwdSlots + a); };
+  auto pready_bar = [&](int a) { return bar_base + 8u * (2 * kFwdSlots + 2 + a); };
+  auto ofull_bar = [&](int a) { return bar_base + 8u * (2 * kFwdSlots + 4 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * L::kNumBars;
+  const uint32_t* tmem_slot_ptr = reinterpret_cast<const uint32_t*>(base_ptr + L::kBarOff + 8 * L::kNumBars);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int units = B * kH;
+  const int n_local = (units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kFwdSlots; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(sfull_bar(a), 1); mbar_init(pready_bar(a), 4); mbar_init(ofull_bar(a), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tensormap(&tmQK);
+    prefetch_tensormap(&tmV);
+    prefetch_tensormap(&tmO);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  // TMEM columns: scores / probabilities [0,128) and [128,256); outputs [256,288) and [288,320)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < n_local; ++i) {
+        const int u = blockIdx.x + i * gridDim.x, b = u / kH, h = u % kH;
+        const int slot = i % kFwdSlots;
+        mbar_wait(empty_bar(slot), ((i / kFwdSlots) & 1) ^ 1u);
+        const uint32_t sq = base + slot * L::kSlotBytes;
+        mbar_expect_tx(full_bar(slot), L::kSlotBytes);
+        tma_load_3d(sq, &tmQK, h * kDh, 0, b, full_bar(slot));
+        tma_load_3d(sq + kAtTileBytes, &tmQK, kD + h * kDh, 0, b, full_bar(slot));
+        tma_load_3d(sq + 2 * kAtTileBytes, &tmV, 2 * kD + h * kDh, 0, b, full_bar(slot));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptors: c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13), a_major bit15, b_major bit16, N>>3 [17,23), M>>4 [24,29)
+      const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kAtRows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc_o = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(kDh >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int i = 0; i <= n_local; ++i) {
+        if (i < n_local) {
+          const int slot = i % kFwdSlots;
+          mbar_wait(full_bar(slot), (i / kFwdSlots) & 1);
+          tcgen05_fence_after();
+          const uint32_t sq = base + slot * L::kSlotBytes, sk = sq + kAtTileBytes;
+          const uint32_t sbuf = tmem_base + (uint32_t)((i & 1) * 128);
+#pragma unroll
+          for (int kk = 0; kk < kDh / 8; ++kk)
+            umma_tf32(sbuf, make_smem_desc(sq + kk * 32, 16, 1024, 2), make_smem_desc(sk + kk * 32, 16, 1024, 2), idesc_s, kk > 0 ? 1u : 0u);
+          tcgen05_commit(sfull_bar(i & 1));
+        }
+        if (i >= 1) {
+          const int j = i - 1;
+          const int u = blockIdx.x + j * gridDim.x, b = u / kH;
+          const int n = min(S, __ldg(length + b) + 1);
+          const int nk = (n + 7) >> 3;
+          mbar_wait(pready_bar(j & 1), (j >> 1) & 1);
+          tcgen05_fence_after();
+          const uint32_t sv = base + (j % kFwdSlots) * L::kSlotBytes + 2 * kAtTileBytes;
+          const uint32_t pbuf = tmem_base + (uint32_t)((j & 1) * 128);
+          const uint32_t obuf = tmem_base + 256u + (uint32_t)((j & 1) * 32);
+          for (int kk = 0; kk < nk; ++kk)
+            umma_tf32_ts(obuf, pbuf + (uint32_t)(kk * 8), make_smem_desc(sv + kk * 1024, kAtTileBytes, 512, 1), idesc_o, kk > 0 ? 1u : 0u);
+          tcgen05_commit(ofull_bar(j & 1));
+          tcgen05_commit(empty_bar(j % kFwdSlots));
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t stage = base + L::kStageOff + q * 8192;
+    uint8_t* stage_ptr = base_ptr + L::kStageOff + q * 8192;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    const float c2 = kAtScale * kLog2e;
+    float inv_l = 0.f, inv_l_prev = 0.f;
+    int ob = 0;
+    for (int i = 0; i <= n_local; ++i) {
+      if (i < n_local) {
+        const int u = blockIdx.x + i * gridDim.x, b = u / kH, h = u % kH;
+        const int n = min(S, __ldg(length + b) + 1);
+        mbar_wait(sfull_bar(i & 1), (i >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t sbuf = lane_base + (uint32_t)((i & 1) * 128);
+        const int nch = (n + 31) >> 5;
+        float m = -INFINITY;
+        for (int c = 0; c < nch; ++c) {
+          uint32_t r[32];
+          tmem_ld32(sbuf + (uint32_t)(c * 32), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j < n) m = fmaxf(m, __uint_as_float(r[j]));
+        }
+        float l = 0.f;
+        const float mc = m * c2;
+        for (int c = 0; c < nch; ++c) {
+          uint32_t r[32];
+          tmem_ld32(sbuf + (uint32_t)(c * 32), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float p = (c * 32 + j < n) ? fast_exp2(fmaf(__uint_as_float(r[j]), c2, -mc)) : 0.f;
+            l += p;
+            r[j] = to_tf32(p);
+          }
+          tmem_st32(sbuf + (uint32_t)(c * 32), r);
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pready_bar(i & 1));
+        inv_l = 1.0f / l;
+        if (row < S) lse[((size_t)b * kH + h) * S + row] = m * kAtScale + __logf(l);
+      }
+      if (i >= 1) {
+        const int j = i - 1;
+        const int u = blockIdx.x + j * gridDim.x, b = u / kH, h = u % kH;
+        mbar_wait(ofull_bar(j & 1), (j >> 1) & 1);
+        tcgen05_fence_after();
+        uint32_t r[32];
+        tmem_ld32(lane_base + 256u + (uint32_t)((j & 1) * 32), r);
+        if (lane == 0) tma_wait_group_read<1>();
+        __syncwarp();
+        uint8_t* outp = stage_ptr + ob * 4096 + lane * 128;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<float4*>(outp + ((k ^ sw) << 4)) =
+              make_float4(__uint_as_float(r[4 * k]) * inv_l_prev, __uint_as_float(r[4 * k + 1]) * inv_l_prev, __uint_as_float(r[4 * k + 2]) * inv_l_prev,
+                          __uint_as_float(r[4 * k + 3]) * inv_l_prev);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmO, stage + ob * 4096, h * kDh, q * 32, b);
+          tma_commit_group();
+        }
+        ob ^= 1;
+      }
+      inv_l_prev = inv_l;
+    }
+    if (lane == 0) tma_wait_group_read<0>();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+int launch_attention_fwd_tc(TensorMapCache* maps, const float* qkv, const int* length, int B, int S, float* out, float* lse, cudaStream_t st) {
+  if (S > kAtRows) { set_error("attention (tcgen05): S = %d exceeds the %d-row unit tile", S, kAtRows); return MFP_ERR_UNSUPPORTED; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    MFP_CUDA_OK(cudaFuncSetAttribute(attention_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdSmem::kTotal));
+    attr_set = true;
+  }
+  const uint64_t qdims[3] = {(uint64_t)(3 * kD), (uint64_t)S, (uint64_t)B}, qstr[2] = {(uint64_t)(3 * kD), (uint64_t)S * 3 * kD};
+  const uint32_t qbox[3] = {(uint32_t)kDh, (uint32_t)kAtRows, 1};
+  const uint64_t odims[3] = {(uint64_t)kD, (uint64_t)S, (uint64_t)B}, ostr[2] = {(uint64_t)kD, (uint64_t)S * kD};
+  const uint32_t obox[3] = {(uint32_t)kDh, 32, 1};
+  const CUtensorMap* mqk = tensor_map_get(maps, qkv, 3, qdims, qstr, qbox, kMapOperandK);
+  const CUtensorMap* mv = tensor_map_get(maps, qkv, 3, qdims, qstr, qbox, kMapOperandMN);
+  const CUtensorMap* mo = tensor_map_get(maps, out, 3, odims, ostr, obox, kMapEpilogue);
+  if (!mqk || !mv || !mo) return MFP_ERR_CUDA;
+  const int units = B * kH;
+  const int grid = units < sm_count() ? units : sm_count();
+  attention_fwd_tc_kernel<<<grid, kAtThreads, AttnFwdSmem::kTotal, st>>>(*mqk, *mv, *mo, length, B, S, lse);
+  MFP_CUDA_OK(cudaGetLastError());
+  return MFP_OK;
+}
+
+}  // namespace mfp

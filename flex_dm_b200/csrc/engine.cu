@@ -236,9 +236,11 @@ static int gemm(mfp_engine* h, const float* A, int a_mn, int lda, const float* B
 }
 
 // split-K factor of a weight-gradient GEMM (K = tokens): enough CTAs for ~2 per SM
+// The GEMM is persistent (one CTA per SM, 128 x 256 tiles): pick the largest split count that still fits one wave.
 static int wgrad_splits(int M, int N, int K) {
-  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
-  int s = (2 * 148 + tiles - 1) / tiles;
+  const int bn = (N <= 128) ? 128 : 256;
+  const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
+  int s = 148 / tiles;
   const int kb = (K + 31) / 32;
   if (s > kb / 4) s = kb / 4;
   return s < 1 ? 1 : s;
@@ -412,7 +414,11 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
     GemmEpilogue e1 = make_epilogue(qkv, 3 * D);
     e1.bias = P + b.bqkv;
     MFP_TRY(gemm(h, ln1, 0, D, P + b.wqkv, 1, 3 * D, T, 3 * D, D, e1, 1, st));
-    { ProfScope prof(h, MFP_PROFILE_ATTENTION, st); MFP_TRY(launch_attention_fwd(qkv, modified->length, h->B, h->S, attn, lse, st)); }
+    {
+      ProfScope prof(h, MFP_PROFILE_ATTENTION, st);
+      if (h->gemm_impl == 0 && h->S <= 128) MFP_TRY(launch_attention_fwd_tc(h->maps, qkv, modified->length, h->B, h->S, attn, lse, st));
+      else MFP_TRY(launch_attention_fwd(qkv, modified->length, h->B, h->S, attn, lse, st));
+    }
     GemmEpilogue e2 = make_epilogue(xmid, D);
     e2.bias = P + b.bo;
     e2.residual = xi; e2.ldr = D;
@@ -594,6 +600,13 @@ int mfp_profile_end(mfp_engine* h, float* ms_per_class_host, int32_t* launches_p
     v.clear();
   }
   return MFP_OK;
+}
+
+int mfp_debug_attention(const float* qkv, const int32_t* length, int32_t B, int32_t S, float* out, float* lse, int32_t impl, void* stream) {
+  static TensorMapCache* cache = tensor_map_cache_create();
+  if (!qkv || !length || !out || !lse || B < 1 || S < 1) { set_error("mfp_debug_attention: bad argument"); return MFP_ERR_ARG; }
+  if (impl == 0) return launch_attention_fwd_tc(cache, qkv, length, B, S, out, lse, (cudaStream_t)stream);
+  return launch_attention_fwd(qkv, length, B, S, out, lse, (cudaStream_t)stream);
 }
 
 int mfp_debug_gemm(const float* A, int32_t a_mn, int32_t lda, const float* B, int32_t b_mn, int32_t ldb, float* D, int32_t ldd, int32_t M, int32_t N,

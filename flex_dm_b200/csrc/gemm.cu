@@ -2,11 +2,13 @@
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 #include <unordered_map>
 
 #include "gemm.cuh"
+#include "tc.cuh"
 
 namespace mfp {
 
@@ -41,84 +43,6 @@ __device__ __forceinline__ void epilogue_store4(float (&v)[4], int row, int col,
   }
 }
 
-// ------------------------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return done != 0;
-}
-// Bounded wait: a protocol bug must trap, not hang the GPU box.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("mfp gemm: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// Shared-memory matrix descriptor (SWIZZLE_128B, Blackwell version bit) -- cute/arch/mma_sm100_desc.hpp layout.
-// layout_type: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (the only layout for MN-major tf32)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address, bits [0,14)
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;  // leading byte offset, bits [16,30)
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;  // stride byte offset, bits [32,46)
-  d |= 1ull << 46;                                 // descriptor version (sm_100)
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
-
 // ------------------------------------------------------------------------------------------------- tcgen05 kernel
 // Persistent, warp-specialised: one CTA per SM loops over output tiles (n fastest, so CTAs running together share
 // A tiles through L2).  Roles (8 warps):
@@ -138,6 +62,7 @@ constexpr int kChunkBytes = 32 * 32 * 4;  // one 32-row x 32-column fp32 staging
 
 struct GemmTune {
   uint32_t mn_lbo, mn_sbo, k_lbo, k_sbo;
+  uint32_t k_layout;  // descriptor layout type of K-major operands: 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B (experiment)
 };
 
 struct GemmTiles {
@@ -155,25 +80,6 @@ struct GemmSmem {
   static constexpr int kNumBars = 2 * kStages + 4 + 8;           // full, empty, tmem full[2]/empty[2], aux[4 warps][2]
   static constexpr int kTotal = kBarOff + 8 * kNumBars + 16 + 1024;  // + TMEM slot + alignment slack
 };
-
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src),
-               "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
-               "r"(src), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
 
 // Epilogue variants are compiled in (EPI bit mask), so each instantiation carries only the code it runs: the epilogue
 // warps are issue-bound (one warp per scheduler), every dead branch in their loop costs throughput.
@@ -287,8 +193,8 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
             // K-major: 8 fp32 of K = 32 B inside the 128 B swizzle row (SWIZZLE_128B, 8-row atoms 1024 B apart).
             // MN-major: 8 K-rows = two 4-row 512 B atoms of SWIZZLE_128B_BASE32B (SBO), 32-wide MN chunks kBK*128 B apart (LBO).
-            const uint64_t da = a_mn ? make_smem_desc(sa + kk * 1024, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(sa + kk * 32, tune.k_lbo, tune.k_sbo, 2);
-            const uint64_t db = b_mn ? make_smem_desc(sb + kk * 1024, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(sb + kk * 32, tune.k_lbo, tune.k_sbo, 2);
+            const uint64_t da = a_mn ? make_smem_desc(sa + kk * 1024, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(sa + kk * 32, tune.k_lbo, tune.k_sbo, tune.k_layout);
+            const uint64_t db = b_mn ? make_smem_desc(sb + kk * 1024, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(sb + kk * 32, tune.k_lbo, tune.k_sbo, tune.k_layout);
             umma_tf32(tacc, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
           tcgen05_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
@@ -493,56 +399,77 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-enum MapKind : uint32_t { kMapOperandK = 0, kMapOperandMN = 1, kMapEpilogue = 2 };
+static bool k_atom32() { static const bool v = getenv("FLEXDM_K_ATOM32") != nullptr; return v; }  // experiment: one smem image for both majors
 
 struct MapKey {
   const void* ptr;
-  uint64_t inner, outer, ld;
-  uint32_t box_inner, box_outer, kind;
-  bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer && kind == o.kind;
-  }
+  uint64_t dims[3], strides[2];
+  uint32_t box[3], rank, kind;
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = std::hash<const void*>()(k.ptr);
     auto mix = [&](uint64_t v) { h ^= std::hash<uint64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-    mix(k.inner); mix(k.outer); mix(k.ld); mix(k.box_inner); mix(k.box_outer); mix(k.kind);
+    for (int i = 0; i < 3; ++i) { mix(k.dims[i]); mix(k.box[i]); }
+    mix(k.strides[0]); mix(k.strides[1]); mix(k.rank); mix(k.kind);
     return h;
   }
 };
 
 class TensorMapCache {
  public:
-  // 2-D fp32 tensor [outer][inner] with row pitch ld (floats); box = [box_outer][box_inner].
+  // fp32 tensor of rank 2 or 3, dims[0] innermost (contiguous), strides (in floats) of dims 1.. ; box per dim.
   //   kMapOperandK : MMA operand, K-major, SWIZZLE_128B, values rounded to TF32 (RN) by the TMA unit
   //   kMapOperandMN: MMA operand, MN-major, SWIZZLE_128B_ATOM_32B (the only MN-major layout for 32-bit types), TF32
   //   kMapEpilogue : epilogue staging chunks (store / reduce-add / residual load), SWIZZLE_128B, plain fp32
-  const CUtensorMap* get(const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer, MapKind kind) {
-    MapKey key{ptr, inner, outer, ld, box_inner, box_outer, (uint32_t)kind};
+  const CUtensorMap* get(const float* ptr, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box, MapKind kind) {
+    MapKey key;
+    memset(&key, 0, sizeof(key));
+    key.ptr = ptr; key.rank = (uint32_t)rank; key.kind = (uint32_t)kind;
+    for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides[i];
     auto it = maps_.find(key);
     if (it != maps_.end()) return &it->second;
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)"); return nullptr; }
-    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 4)) { set_error("TMA operand must be 16-byte aligned with a pitch multiple of 4 floats"); return nullptr; }
+    if (reinterpret_cast<uintptr_t>(ptr) & 15) { set_error("TMA operand must be 16-byte aligned"); return nullptr; }
     CUtensorMap m;
-    cuuint64_t dims[2] = {inner, outer};
-    cuuint64_t strides[1] = {ld * sizeof(float)};
-    cuuint32_t box[2] = {box_inner, box_outer};
-    cuuint32_t estr[2] = {1, 1};
+    cuuint64_t gdims[3] = {1, 1, 1}, gstr[2] = {0, 0};
+    cuuint32_t gbox[3] = {1, 1, 1}, estr[3] = {1, 1, 1};
+    for (int i = 0; i < rank; ++i) { gdims[i] = dims[i]; gbox[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) {
+      if (strides[i] % 4) { set_error("TMA operand pitch must be a multiple of 4 floats"); return nullptr; }
+      gstr[i] = strides[i] * sizeof(float);
+    }
     static const bool plain_f32 = getenv("FLEXDM_TMA_F32") != nullptr;  // default: round operands to TF32 (RN) in the TMA unit
     const CUtensorMapDataType dt = (kind == kMapEpilogue || plain_f32) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
-    const CUtensorMapSwizzle sw = (kind == kMapOperandMN) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
-    CUresult r = enc(&m, dt, 2, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d (inner=%llu outer=%llu ld=%llu)", (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld); return nullptr; }
+    const CUtensorMapSwizzle sw = (kind == kMapOperandMN || (kind == kMapOperandK && k_atom32())) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+    CUresult r = enc(&m, dt, (cuuint32_t)rank, const_cast<float*>(ptr), gdims, gstr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled failed: %d (rank=%d dims=%llu,%llu,%llu)", (int)r, rank, (unsigned long long)gdims[0], (unsigned long long)gdims[1],
+                (unsigned long long)gdims[2]);
+      return nullptr;
+    }
     auto res = maps_.emplace(key, m);
     return &res.first->second;
+  }
+  // 2-D [outer][inner] with row pitch ld (floats); box = [box_outer][box_inner]
+  const CUtensorMap* get(const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer, MapKind kind) {
+    const uint64_t dims[2] = {inner, outer}, strides[1] = {ld};
+    const uint32_t box[2] = {box_inner, box_outer};
+    return get(ptr, 2, dims, strides, box, kind);
   }
 
  private:
   std::unordered_map<MapKey, CUtensorMap, MapKeyHash> maps_;
 };
+
+const CUtensorMap* tensor_map_get(TensorMapCache* cache, const float* ptr, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
+                                  MapKind kind) {
+  return cache->get(ptr, rank, dims, strides, box, kind);
+}
 
 TensorMapCache* tensor_map_cache_create() { return new TensorMapCache(); }
 void tensor_map_cache_destroy(TensorMapCache* c) { delete c; }
@@ -578,7 +505,8 @@ static int launch_tcgen05(TensorMapCache* cache, const GemmCall& c, cudaStream_t
   if (c.ep.residual) mx = cache->get(c.ep.residual, c.N, c.M, c.ep.ldr, 32, 32, kMapEpilogue);
   if (c.ep.relu_src) mx = cache->get(c.ep.relu_src, c.N, c.M, c.ep.ld_relu, 32, 32, kMapEpilogue);
   if (!ma || !mb || !mo || !mx) return MFP_ERR_CUDA;
-  static const GemmTune tune = {env_u32("FLEXDM_MN_LBO", kBK * 128), env_u32("FLEXDM_MN_SBO", 512), env_u32("FLEXDM_K_LBO", 16), env_u32("FLEXDM_K_SBO", 1024)};
+  static const GemmTune tune = {env_u32("FLEXDM_MN_LBO", kBK * 128), env_u32("FLEXDM_MN_SBO", 512), env_u32("FLEXDM_K_LBO", 16), env_u32("FLEXDM_K_SBO", 1024),
+                                k_atom32() ? 1u : 2u};
   const int num_kb = (c.K + kBK - 1) / kBK;
   int splits = c.splits < 1 ? 1 : c.splits;
   if (splits > num_kb) splits = num_kb;

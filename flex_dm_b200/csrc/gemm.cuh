@@ -3,6 +3,8 @@
 // ring, two TMEM accumulators so the epilogue of one tile overlaps the main loop of the next, epilogue through
 // swizzled shared staging and TMA store / reduce-add.  See gemm.cu for the warp roles.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace mfp {
@@ -49,9 +51,14 @@ struct GemmCall {
   float* colsum;  // optional [N]: += column sums of the (MN-major) B operand over K, i.e. the bias gradient of a wgrad GEMM
 };
 
+// TMA descriptors, cached per (pointer, geometry): building one costs a driver call.
+enum MapKind : uint32_t { kMapOperandK = 0, kMapOperandMN = 1, kMapEpilogue = 2 };
 class TensorMapCache;
 TensorMapCache* tensor_map_cache_create();
 void tensor_map_cache_destroy(TensorMapCache*);
+// fp32 tensor of rank 2 or 3: dims[0] innermost (contiguous), strides (floats) of dims 1.., box per dim; see gemm.cu for the kinds
+const CUtensorMap* tensor_map_get(TensorMapCache* cache, const float* ptr, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
+                                  MapKind kind);
 
 // impl: 0 = tcgen05, 1 = SIMT bring-up kernel.  Returns MFP_OK or an error (message via set_error).
 int launch_gemm(TensorMapCache* cache, const GemmCall& call, int impl, cudaStream_t stream);

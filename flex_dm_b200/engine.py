@@ -76,6 +76,8 @@ _SIGNATURES = {
     "mfp_set_gemm_impl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     "mfp_profile_begin": (ctypes.c_int, [ctypes.c_void_p]),
     "mfp_profile_end": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)]),
+    "mfp_debug_attention": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_int32, ctypes.c_void_p]),
     "mfp_debug_gemm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
                                       ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                                       ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
@@ -330,6 +332,15 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self.lib.mfp_launch_count(self.handle))
+
+
+def debug_attention(qkv: torch.Tensor, length: torch.Tensor, B: int, S: int, impl: int = 0):
+    """(out [B*S, 256], lse [B, 8, S]) of the attention core on a [B*S, 768] QKV activation (bring-up / unit tests)."""
+    lib = load_library()
+    out = torch.zeros((B * S, 256), dtype=torch.float32, device=qkv.device)
+    lse = torch.zeros((B, 8, S), dtype=torch.float32, device=qkv.device)
+    _check(lib, lib.mfp_debug_attention(_ptr(qkv), _ptr(length), B, S, _ptr(out), _ptr(lse), impl, _stream()), "mfp_debug_attention")
+    return out, lse
 
 
 def debug_gemm(A: torch.Tensor, a_mn: bool, B: torch.Tensor, b_mn: bool, M: int, N: int, K: int, bias=None, relu=False, splits=1, impl=0,

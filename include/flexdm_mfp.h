@@ -138,8 +138,9 @@ int mfp_merge_prediction(mfp_engine* h, int32_t field, const void* input_col, co
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t mfp_launch_count(const mfp_engine* h);
 
-/* Bring-up / test hook: 0 = tcgen05 TF32 GEMM (default, the product path), 1 = fp32 SIMT GEMM with the same
- * epilogue.  The parity tests use 1 to pin every other kernel at fp32 accuracy, independent of TF32 rounding. */
+/* Bring-up / test hook: 0 = tcgen05 TF32 GEMMs and attention (default, the product path), 1 = fp32 SIMT GEMM with the
+ * same epilogue and fp32 SIMT attention.  The parity tests use 1 to pin every other kernel at fp32 accuracy,
+ * independent of TF32 rounding. */
 int mfp_set_gemm_impl(mfp_engine* h, int32_t impl);
 
 /* Optional device timing of kernel classes (bench.py's roofline): between begin and end every launch of the class is
@@ -150,6 +151,12 @@ int mfp_set_gemm_impl(mfp_engine* h, int32_t impl);
 #define MFP_PROFILE_ATTENTION 1
 int mfp_profile_begin(mfp_engine* h);
 int mfp_profile_end(mfp_engine* h, float* ms_per_class_host, int32_t* launches_per_class_host);
+
+/* Bring-up hook: the attention core of MultiHeadSelfAttention (architecture/transformer.py:60-76) alone.
+ * qkv [B*S, 768] (q | k | v, head h = columns 32h..32h+31 of each third), length [B] zero-based;
+ * out [B*S, 256] heads merged, lse [B, 8, S].  impl: 0 = tcgen05 (S <= 128), 1 = SIMT. */
+int mfp_debug_attention(const float* qkv, const int32_t* length, int32_t B, int32_t S, float* out, float* lse,
+                        int32_t impl, void* stream);
 
 /* Bring-up hook: D[M,N] = epilogue(A . B^T) through the same tcgen05/TMA GEMM the engine uses.
  * a_mn / b_mn: 0 = operand is K-major ([rows=M|N][K] row-major, pitch ld), 1 = MN-major ([K][M|N] row-major).

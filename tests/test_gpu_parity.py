@@ -91,6 +91,38 @@ def test_gemm_fused_epilogues(impl, M, N, K):
     assert (cs.cpu().double() - dY.double().sum(0)).abs().max().item() <= 1e-4 * dY.abs().sum(0).max().item()
 
 
+# ----------------------------------------------------------------------------------------------- attention core
+def _attention_reference(qkv, length, B, S):
+    """transformer.py:60-76 in float64: softmax(QK^T/sqrt(dh) - 1e9 (1 - key mask)) V per head."""
+    x = qkv.double().reshape(B, S, 3, 8, 32)
+    q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))  # (B, H, S, dh)
+    score = q @ k.transpose(-1, -2) / np.sqrt(32.0)
+    mask = (torch.arange(S)[None, :] <= length[:, None]).double()  # (B, S)
+    score = score + (-1e9) * (1.0 - mask)[:, None, None, :]
+    lse = torch.logsumexp(score, dim=-1)
+    out = torch.softmax(score, dim=-1) @ v
+    return out.permute(0, 2, 1, 3).reshape(B * S, 256), lse
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("B,S", [(3, 128), (5, 50), (2, 7), (40, 128)])
+def test_attention_core(impl, B, S):
+    from flex_dm_b200.engine import debug_attention
+
+    g = torch.Generator().manual_seed(B * 1000 + S)
+    qkv = torch.randn(B * S, 768, generator=g) * 1.5
+    length = torch.randint(0, S, (B,), generator=g, dtype=torch.int32)
+    length[0] = S - 1
+    if B > 1:
+        length[1] = 0  # a single valid element: every query returns V[0]
+    ref_out, ref_lse = _attention_reference(qkv, length, B, S)
+    out, lse = debug_attention(qkv.cuda(), length.cuda(), B, S, impl=impl)
+    torch.cuda.synchronize()
+    tol = 2e-5 if impl == 1 else 4e-3
+    assert (out.cpu().double() - ref_out).abs().max().item() <= tol * max(1.0, ref_out.abs().max().item())
+    assert (lse.cpu().double() - ref_lse).abs().max().item() <= (1e-4 if impl == 1 else 2e-2)
+
+
 # ----------------------------------------------------------------------------------------------- masking (bit-exact)
 @pytest.mark.parametrize("dataset,method,B,S,L", CONFIGS)
 def test_mask_corrupt_matches_oracle(dataset, method, B, S, L):
