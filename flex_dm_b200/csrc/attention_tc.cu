@@ -203,6 +203,222 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------- backward
+// Works in the TRANSPOSED domain (keys on the 128 TMEM lanes) so that both probability-shaped operands of the
+// gradient GEMMs are already where tcgen05 wants an A operand -- in tensor memory, one key per lane:
+//   S^T  = K Q^T,   dP^T = V dO^T                (both operands K-major in shared memory)
+//   P^T  = exp(S^T/sqrt(dh) - lse_i),  dS^T = P^T o (dP^T - D_i)   thread j owns key j; lse_i, D_i = dO_i.O_i from smem
+//   dV   = P^T dO,  dK = dS^T Q                   (A = TMEM in place of S^T / dP^T, B = MN-major shared tiles)
+//   dQ   = dS K                                   (A = dS^T written once to shared memory in the MN-major layout)
+// K-major and MN-major tf32 operands need different 128-byte swizzles, so Q, K and dO are fetched twice by TMA (the
+// second fetch hits L2).  Two independent single-slot rings: the K-major set is released as soon as S^T / dP^T are
+// done, the MN-major set after the three gradient GEMMs, so the next unit's loads fly under this unit's math.
+struct AttnBwdSmem {
+  static constexpr int kKmajOff = 0;                       // K, Q, V, dO   (K-major, SWIZZLE_128B)
+  static constexpr int kMnOff = 4 * kAtTileBytes;          // dO, Q, K      (MN-major, SWIZZLE_128B_ATOM_32B)
+  static constexpr int kDsOff = 7 * kAtTileBytes;          // dS^T as the MN-major A operand of dQ: 4 chunks x [128 keys][32 q]
+  static constexpr int kStageOff = kDsOff + 4 * kAtTileBytes;  // 4 warps x 2 x [32][32] fp32
+  static constexpr int kVecOff = kStageOff + 4 * 2 * 4096;     // lse[128], D[128]
+  static constexpr int kBarOff = kVecOff + 1024;
+  static constexpr int kNumBars = 7;                       // kfull, kempty, mnfull, mnempty, s_full, p_ready, o_full
+  static constexpr int kTotal = kBarOff + 8 * kNumBars + 16 + 1024;
+};
+
+__global__ void __launch_bounds__(kAtThreads, 1)
+attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid_constant__ CUtensorMap tmQkvMN, const __grid_constant__ CUtensorMap tmDoK,
+                        const __grid_constant__ CUtensorMap tmDoMN, const __grid_constant__ CUtensorMap tmDqkv, const float* __restrict__ out,
+                        const float* __restrict__ lse, const int* __restrict__ length, int B, int S) {
+  using L = AttnBwdSmem;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_base = base + L::kBarOff;
+  const uint32_t kfull = bar_base, kempty = bar_base + 8, mnfull = bar_base + 16, mnempty = bar_base + 24, sfull = bar_base + 32,
+                 pready = bar_base + 40, ofull = bar_base + 48;
+  const uint32_t tmem_slot = bar_base + 8u * L::kNumBars;
+  const uint32_t* tmem_slot_ptr = reinterpret_cast<const uint32_t*>(base_ptr + L::kBarOff + 8 * L::kNumBars);
+  float* lse_s = reinterpret_cast<float*>(base_ptr + L::kVecOff);
+  float* d_s = lse_s + kAtRows;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int units = B * kH;
+  const int n_local = (units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (threadIdx.x == 0) {
+    mbar_init(kfull, 1); mbar_init(kempty, 5); mbar_init(mnfull, 1); mbar_init(mnempty, 1);  // kempty: MMA commit + the 4 warps that read dO
+    mbar_init(sfull, 1); mbar_init(pready, 4); mbar_init(ofull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tensormap(&tmQkvK); prefetch_tensormap(&tmQkvMN); prefetch_tensormap(&tmDoK); prefetch_tensormap(&tmDoMN); prefetch_tensormap(&tmDqkv);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  // TMEM columns: S^T / P^T [0,128), dP^T / dS^T [128,256), dV [256,288), dK [288,320), dQ [320,352)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < n_local; ++i) {
+        const int u = blockIdx.x + i * gridDim.x, b = u / kH, h = u % kH;
+        const uint32_t ph = (uint32_t)(i & 1);
+        mbar_wait(kempty, ph ^ 1u);
+        mbar_expect_tx(kfull, 4 * kAtTileBytes);
+        const uint32_t sk = base + L::kKmajOff;
+        tma_load_3d(sk, &tmQkvK, kD + h * kDh, 0, b, kfull);                          // K
+        tma_load_3d(sk + kAtTileBytes, &tmQkvK, h * kDh, 0, b, kfull);                // Q
+        tma_load_3d(sk + 2 * kAtTileBytes, &tmQkvK, 2 * kD + h * kDh, 0, b, kfull);   // V
+        tma_load_3d(sk + 3 * kAtTileBytes, &tmDoK, h * kDh, 0, b, kfull);             // dO
+        mbar_wait(mnempty, ph ^ 1u);
+        mbar_expect_tx(mnfull, 3 * kAtTileBytes);
+        const uint32_t sm = base + L::kMnOff;
+        tma_load_3d(sm, &tmDoMN, h * kDh, 0, b, mnfull);                              // dO
+        tma_load_3d(sm + kAtTileBytes, &tmQkvMN, h * kDh, 0, b, mnfull);              // Q
+        tma_load_3d(sm + 2 * kAtTileBytes, &tmQkvMN, kD + h * kDh, 0, b, mnfull);     // K
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kAtRows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc_g = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(kDh >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // B MN-major
+      const uint32_t idesc_q = idesc_g | (1u << 15);                                                                                       // A MN-major too
+      const uint32_t sk = base + L::kKmajOff, sq = sk + kAtTileBytes, sv = sk + 2 * kAtTileBytes, sdo = sk + 3 * kAtTileBytes;
+      const uint32_t mdo = base + L::kMnOff, mq = mdo + kAtTileBytes, mk = mdo + 2 * kAtTileBytes;
+      const uint32_t sds = base + L::kDsOff;
+      for (int i = 0; i < n_local; ++i) {
+        const int u = blockIdx.x + i * gridDim.x, b = u / kH;
+        const int n = min(S, __ldg(length + b) + 1);
+        const int nk = (n + 7) >> 3;
+        const uint32_t ph = (uint32_t)(i & 1);
+        mbar_wait(kfull, ph);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < kDh / 8; ++kk)
+          umma_tf32(tmem_base, make_smem_desc(sk + kk * 32, 16, 1024, 2), make_smem_desc(sq + kk * 32, 16, 1024, 2), idesc_s, kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < kDh / 8; ++kk)
+          umma_tf32(tmem_base + 128u, make_smem_desc(sv + kk * 32, 16, 1024, 2), make_smem_desc(sdo + kk * 32, 16, 1024, 2), idesc_s, kk > 0 ? 1u : 0u);
+        tcgen05_commit(sfull);
+        tcgen05_commit(kempty);
+        mbar_wait(pready, ph);
+        mbar_wait(mnfull, ph);
+        tcgen05_fence_after();
+        for (int kk = 0; kk < nk; ++kk)  // dV = P^T dO
+          umma_tf32_ts(tmem_base + 256u, tmem_base + (uint32_t)(kk * 8), make_smem_desc(mdo + kk * 1024, kAtTileBytes, 512, 1), idesc_g, kk > 0 ? 1u : 0u);
+        for (int kk = 0; kk < nk; ++kk)  // dK = dS^T Q
+          umma_tf32_ts(tmem_base + 288u, tmem_base + 128u + (uint32_t)(kk * 8), make_smem_desc(mq + kk * 1024, kAtTileBytes, 512, 1), idesc_g, kk > 0 ? 1u : 0u);
+        for (int kk = 0; kk < nk; ++kk)  // dQ = dS K
+          umma_tf32(tmem_base + 320u, make_smem_desc(sds + kk * 1024, kAtTileBytes, 512, 1), make_smem_desc(mk + kk * 1024, kAtTileBytes, 512, 1), idesc_q,
+                    kk > 0 ? 1u : 0u);
+        tcgen05_commit(ofull);
+        tcgen05_commit(mnempty);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;  // key index in softmax / dS; query index in the D preparation; output row in the epilogue
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t stage = base + L::kStageOff + q * 8192;
+    uint8_t* stage_ptr = base_ptr + L::kStageOff + q * 8192;
+    uint8_t* ds_ptr = base_ptr + L::kDsOff;
+    const uint8_t* do_ptr = base_ptr + L::kKmajOff + 3 * kAtTileBytes;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    const float c2 = kAtScale * kLog2e;
+    int ob = 0;
+
+    auto prepare = [&](int i) {  // lse_i and D_i = dO_i . O_i of unit i -> shared memory (all 128 threads, one query row each)
+      const int u = blockIdx.x + i * gridDim.x, b = u / kH, h = u % kH;
+      mbar_wait(kfull, (uint32_t)(i & 1));
+      float dsum = 0.f, l = INFINITY;
+      if (row < S) {
+        const float4* op = reinterpret_cast<const float4*>(out + ((size_t)b * S + row) * kD + h * kDh);
+        const uint8_t* dp = do_ptr + row * 128;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 o = __ldg(op + k);
+          const float4 g = *reinterpret_cast<const float4*>(dp + ((k ^ sw) << 4));
+          dsum += o.x * g.x + o.y * g.y + o.z * g.z + o.w * g.w;
+        }
+        l = __ldg(lse + ((size_t)b * kH + h) * S + row);
+      }
+      lse_s[row] = l * kLog2e;
+      d_s[row] = dsum;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(kempty);  // this warp no longer reads the K-major dO tile
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    auto epilogue = [&](int i) {
+      const int u = blockIdx.x + i * gridDim.x, b = u / kH, h = u % kH;
+      mbar_wait(ofull, (uint32_t)(i & 1));
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < 3; ++t) {  // dV, dK, dQ
+        uint32_t r[32];
+        tmem_ld32(lane_base + 256u + (uint32_t)(t * 32), r);
+        const float sc = (t == 0) ? 1.0f : kAtScale;
+        if (lane == 0) tma_wait_group_read<1>();
+        __syncwarp();
+        uint8_t* outp = stage_ptr + ob * 4096 + lane * 128;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<float4*>(outp + ((k ^ sw) << 4)) = make_float4(__uint_as_float(r[4 * k]) * sc, __uint_as_float(r[4 * k + 1]) * sc,
+                                                                           __uint_as_float(r[4 * k + 2]) * sc, __uint_as_float(r[4 * k + 3]) * sc);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmDqkv, stage + ob * 4096, (2 - t) * kD + h * kDh, q * 32, b);
+          tma_commit_group();
+        }
+        ob ^= 1;
+      }
+    };
+
+    if (n_local > 0) prepare(0);
+    for (int i = 0; i < n_local; ++i) {
+      const int u = blockIdx.x + i * gridDim.x, b = u / kH;
+      const int n = min(S, __ldg(length + b) + 1);
+      const bool key_valid = row < n;
+      mbar_wait(sfull, (uint32_t)(i & 1));
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {  // 32 queries at a time
+        uint32_t rs[32], rd[32];
+        tmem_ld32(lane_base + (uint32_t)(c * 32), rs);
+        tmem_ld32(lane_base + 128u + (uint32_t)(c * 32), rd);
+        uint8_t* dsp = ds_ptr + c * kAtTileBytes + row * 128;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int qi = c * 32 + j;
+          const float p = key_valid ? fast_exp2(fmaf(__uint_as_float(rs[j]), c2, -lse_s[qi])) : 0.f;
+          const float ds = p * (__uint_as_float(rd[j]) - d_s[qi]);
+          rs[j] = to_tf32(p);
+          rd[j] = to_tf32(ds);
+        }
+        tmem_st32(lane_base + (uint32_t)(c * 32), rs);
+        tmem_st32(lane_base + 128u + (uint32_t)(c * 32), rd);
+#pragma unroll
+        for (int f = 0; f < 8; ++f)
+          *reinterpret_cast<uint4*>(dsp + ((((f >> 1) ^ (row & 3)) << 5) | ((f & 1) << 4))) = make_uint4(rd[4 * f], rd[4 * f + 1], rd[4 * f + 2], rd[4 * f + 3]);
+      }
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pready);
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done with lse_s / d_s before the next unit overwrites them
+      if (i + 1 < n_local) prepare(i + 1);
+      epilogue(i);
+    }
+    if (lane == 0) tma_wait_group_read<0>();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+}
+
 static int sm_count() {
   static int n = 0;
   if (!n) {
@@ -234,4 +450,30 @@ int launch_attention_fwd_tc(TensorMapCache* maps, const float* qkv, const int* l
   return MFP_OK;
 }
 
+int launch_attention_bwd_tc(TensorMapCache* maps, const float* qkv, const float* out, const float* lse, const float* dout, const int* length, int B, int S,
+                            float* dqkv, cudaStream_t st) {
+  if (S > kAtRows) { set_error("attention backward (tcgen05): S = %d exceeds the %d-row unit tile", S, kAtRows); return MFP_ERR_UNSUPPORTED; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    MFP_CUDA_OK(cudaFuncSetAttribute(attention_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnBwdSmem::kTotal));
+    attr_set = true;
+  }
+  const uint64_t qdims[3] = {(uint64_t)(3 * kD), (uint64_t)S, (uint64_t)B}, qstr[2] = {(uint64_t)(3 * kD), (uint64_t)S * 3 * kD};
+  const uint64_t odims[3] = {(uint64_t)kD, (uint64_t)S, (uint64_t)B}, ostr[2] = {(uint64_t)kD, (uint64_t)S * kD};
+  const uint32_t tbox[3] = {(uint32_t)kDh, (uint32_t)kAtRows, 1};
+  const uint32_t sbox[3] = {(uint32_t)kDh, 32, 1};
+  const CUtensorMap* mqk = tensor_map_get(maps, qkv, 3, qdims, qstr, tbox, kMapOperandK);
+  const CUtensorMap* mqm = tensor_map_get(maps, qkv, 3, qdims, qstr, tbox, kMapOperandMN);
+  const CUtensorMap* mdk = tensor_map_get(maps, dout, 3, odims, ostr, tbox, kMapOperandK);
+  const CUtensorMap* mdm = tensor_map_get(maps, dout, 3, odims, ostr, tbox, kMapOperandMN);
+  const CUtensorMap* mg = tensor_map_get(maps, dqkv, 3, qdims, qstr, sbox, kMapEpilogue);
+  if (!mqk || !mqm || !mdk || !mdm || !mg) return MFP_ERR_CUDA;
+  const int units = B * kH;
+  const int grid = units < sm_count() ? units : sm_count();
+  attention_bwd_tc_kernel<<<grid, kAtThreads, AttnBwdSmem::kTotal, st>>>(*mqk, *mqm, *mdk, *mdm, *mg, out, lse, length, B, S);
+  MFP_CUDA_OK(cudaGetLastError());
+  return MFP_OK;
+}
+
 }  // namespace mfp
+

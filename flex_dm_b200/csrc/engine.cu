@@ -523,7 +523,11 @@ int mfp_backward(mfp_engine* h, const mfp_batch* modified, int32_t training, uin
     }
     MFP_TRY(gemm(h, attn, 1, D, dy, 1, D, D, D, T, make_epilogue(G + b.wo, D), wgrad_splits(D, D, T), st, G + b.bo));
     MFP_TRY(gemm(h, dy, 0, D, P + b.wo, 0, D, T, D, D, make_epilogue(dattn, D), 1, st));
-    { ProfScope prof(h, MFP_PROFILE_ATTENTION, st); MFP_TRY(launch_attention_bwd(qkv, attn, lse, dattn, modified->length, h->B, h->S, dqkv, st)); }
+    {
+      ProfScope prof(h, MFP_PROFILE_ATTENTION, st);
+      if (h->gemm_impl == 0 && h->S <= 128) MFP_TRY(launch_attention_bwd_tc(h->maps, qkv, attn, lse, dattn, modified->length, h->B, h->S, dqkv, st));
+      else MFP_TRY(launch_attention_bwd(qkv, attn, lse, dattn, modified->length, h->B, h->S, dqkv, st));
+    }
     MFP_TRY(gemm(h, ln1, 1, D, dqkv, 1, 3 * D, D, 3 * D, T, make_epilogue(G + b.wqkv, 3 * D), wgrad_splits(D, 3 * D, T), st, G + b.bqkv));
     MFP_TRY(gemm(h, dqkv, 0, 3 * D, P + b.wqkv, 0, 3 * D, T, D, 3 * D, make_epilogue(dtmp, D), 1, st));
     MFP_TRY(launch_layernorm_bwd(xi, dtmp, P + b.g1, stats, stats + T, dx, T, dx, G + b.g1, G + b.be1, st));
@@ -607,6 +611,14 @@ int mfp_debug_attention(const float* qkv, const int32_t* length, int32_t B, int3
   if (!qkv || !length || !out || !lse || B < 1 || S < 1) { set_error("mfp_debug_attention: bad argument"); return MFP_ERR_ARG; }
   if (impl == 0) return launch_attention_fwd_tc(cache, qkv, length, B, S, out, lse, (cudaStream_t)stream);
   return launch_attention_fwd(qkv, length, B, S, out, lse, (cudaStream_t)stream);
+}
+
+int mfp_debug_attention_bwd(const float* qkv, const int32_t* length, int32_t B, int32_t S, const float* out, const float* lse, const float* dout,
+                            float* dqkv, int32_t impl, void* stream) {
+  static TensorMapCache* cache = tensor_map_cache_create();
+  if (!qkv || !length || !out || !lse || !dout || !dqkv || B < 1 || S < 1) { set_error("mfp_debug_attention_bwd: bad argument"); return MFP_ERR_ARG; }
+  if (impl == 0) return launch_attention_bwd_tc(cache, qkv, out, lse, dout, length, B, S, dqkv, (cudaStream_t)stream);
+  return launch_attention_bwd(qkv, out, lse, dout, length, B, S, dqkv, (cudaStream_t)stream);
 }
 
 int mfp_debug_gemm(const float* A, int32_t a_mn, int32_t lda, const float* B, int32_t b_mn, int32_t ldb, float* D, int32_t ldd, int32_t M, int32_t N,

@@ -35,6 +35,8 @@ int launch_attention_bwd(const float* qkv, const float* out, const float* lse, c
 // attention_tc.cu: the same attention core on tcgen05 tensor cores (S <= 128)
 class TensorMapCache;
 int launch_attention_fwd_tc(TensorMapCache* maps, const float* qkv, const int* length, int B, int S, float* out, float* lse, cudaStream_t st);
+int launch_attention_bwd_tc(TensorMapCache* maps, const float* qkv, const float* out, const float* lse, const float* dout, const int* length, int B, int S,
+                            float* dqkv, cudaStream_t st);
 int launch_dropout_bwd(const float* dx, int T, float rate, uint32_t seed, uint32_t step, uint32_t site, float* dy, cudaStream_t st);
 int launch_colsum(const float* x, int rows, int cols, int ld, float* out /*atomic accumulate*/, cudaStream_t st);
 

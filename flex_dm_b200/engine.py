@@ -78,6 +78,8 @@ _SIGNATURES = {
     "mfp_profile_end": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)]),
     "mfp_debug_attention": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_int32, ctypes.c_void_p]),
+    "mfp_debug_attention_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
     "mfp_debug_gemm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
                                       ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                                       ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
@@ -341,6 +343,15 @@ def debug_attention(qkv: torch.Tensor, length: torch.Tensor, B: int, S: int, imp
     lse = torch.zeros((B, 8, S), dtype=torch.float32, device=qkv.device)
     _check(lib, lib.mfp_debug_attention(_ptr(qkv), _ptr(length), B, S, _ptr(out), _ptr(lse), impl, _stream()), "mfp_debug_attention")
     return out, lse
+
+
+def debug_attention_bwd(qkv, length, B: int, S: int, out, lse, dout, impl: int = 0):
+    """dqkv [B*S, 768] of the attention core (bring-up / unit tests)."""
+    lib = load_library()
+    dqkv = torch.full((B * S, 768), float("nan"), dtype=torch.float32, device=qkv.device)
+    _check(lib, lib.mfp_debug_attention_bwd(_ptr(qkv), _ptr(length), B, S, _ptr(out), _ptr(lse), _ptr(dout), _ptr(dqkv), impl, _stream()),
+           "mfp_debug_attention_bwd")
+    return dqkv
 
 
 def debug_gemm(A: torch.Tensor, a_mn: bool, B: torch.Tensor, b_mn: bool, M: int, N: int, K: int, bias=None, relu=False, splits=1, impl=0,

@@ -158,6 +158,10 @@ int mfp_profile_end(mfp_engine* h, float* ms_per_class_host, int32_t* launches_p
 int mfp_debug_attention(const float* qkv, const int32_t* length, int32_t B, int32_t S, float* out, float* lse,
                         int32_t impl, void* stream);
 
+/* Bring-up hook: backward of the attention core: dqkv [B*S, 768] from qkv, the forward's out / lse and dout [B*S, 256]. */
+int mfp_debug_attention_bwd(const float* qkv, const int32_t* length, int32_t B, int32_t S, const float* out, const float* lse,
+                            const float* dout, float* dqkv, int32_t impl, void* stream);
+
 /* Bring-up hook: D[M,N] = epilogue(A . B^T) through the same tcgen05/TMA GEMM the engine uses.
  * a_mn / b_mn: 0 = operand is K-major ([rows=M|N][K] row-major, pitch ld), 1 = MN-major ([K][M|N] row-major).
  * Optional epilogue operands: bias [N]; relu != 0; residual [M,N] (pitch ldd) added last; relu_src [M,N] (pitch ldd):

@@ -123,6 +123,31 @@ def test_attention_core(impl, B, S):
     assert (lse.cpu().double() - ref_lse).abs().max().item() <= (1e-4 if impl == 1 else 2e-2)
 
 
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("B,S", [(3, 128), (5, 50), (2, 7), (40, 128)])
+def test_attention_core_backward(impl, B, S):
+    from flex_dm_b200.engine import debug_attention, debug_attention_bwd
+
+    g = torch.Generator().manual_seed(B * 77 + S)
+    qkv = torch.randn(B * S, 768, generator=g) * 1.2
+    length = torch.randint(0, S, (B,), generator=g, dtype=torch.int32)
+    length[0] = S - 1
+    valid = (torch.arange(S)[None, :] <= length[:, None]).reshape(B * S, 1)
+    dout = torch.randn(B * S, 256, generator=g) * valid  # padded elements carry no upstream gradient (metrics.py:263-267)
+    x = qkv.double().clone().requires_grad_(True)
+    ref_out, _ = _attention_reference(x, length, B, S)
+    (ref_out * dout.double()).sum().backward()
+    ref = x.grad
+    out, lse = debug_attention(qkv.cuda(), length.cuda(), B, S, impl=impl)
+    dqkv = debug_attention_bwd(qkv.cuda(), length.cuda(), B, S, out, lse, dout.cuda(), impl=impl)
+    torch.cuda.synchronize()
+    got = dqkv.cpu().double()
+    assert torch.isfinite(got).all()
+    for name, sl in (("dq", slice(0, 256)), ("dk", slice(256, 512)), ("dv", slice(512, 768))):
+        err = (got[:, sl] - ref[:, sl]).norm().item() / max(ref[:, sl].norm().item(), 1e-30)
+        assert err <= (1e-5 if impl == 1 else 3e-3), (name, err)
+
+
 # ----------------------------------------------------------------------------------------------- masking (bit-exact)
 @pytest.mark.parametrize("dataset,method,B,S,L", CONFIGS)
 def test_mask_corrupt_matches_oracle(dataset, method, B, S, L):
