@@ -12,6 +12,7 @@ constexpr int kH = 8;          // transformer.py:43
 constexpr int kDh = 32;        // kD / kH
 constexpr int kF = 512;        // FFN hidden = 2*emb_size (transformer.py:164)
 constexpr int kMaxFields = MFP_MAX_FIELDS;
+constexpr int kMaxLookups = 96;
 
 // masking.py:8-15
 constexpr float kMaskValue = 10.0f;
@@ -41,6 +42,7 @@ struct FieldDev {
   int task_id;     // task index of the attribute group holding this field (spec.py:364-377)
   int has_cond;    // loss_condition present (crello-spec.yml:88-121)
   int num_slot;    // index among numerical fields, -1 otherwise
+  int grow_off;    // first row of this field in the encoder's gradient-row space (encoder.cu, embed_onehot_kernel)
   unsigned long long cond_mask;  // bit i: elements of type i carry this field
   long long table_off;   // params offset: embedding table (categorical) or 2-row special table (numerical)
   long long kernel_off;  // numerical Dense kernel [C, D]
@@ -53,6 +55,9 @@ struct Schema {
   int LW;          // padded logits width
   int n_num;       // numerical fields
   int sort_field[5];  // indices of type,left,top,width,height (tensor_utils.py:11)
+  int R, Rp;          // gradient rows of the encoder (tables + {<MASK>, <UNUSED>, bias} per numerical field); Rp = R padded to 4
+  int n_lookups;      // embedding rows summed per element: one per categorical sub-target + one per numerical field
+  unsigned char lk_field[kMaxLookups], lk_sub[kMaxLookups];
   FieldDev f[kMaxFields];
 };
 

@@ -1,107 +1,117 @@
 // Per-element multi-attribute embedding + additive fusion (reference: architecture/encoder.py:147-199) and its
 // backward.  The numerical fields' Dense (512 -> D) runs on the tensor cores (gemm.cu); this file produces
 // everything else of h0 in one pass: categorical gather-sum over sub-targets, <MASK>/<UNUSED> special rows
-// and the Dense bias of unflagged rows.
+// and the Dense bias of unflagged rows.  The backward is a one-hot GEMM (see below).
 #include "kernels.cuh"
 
 namespace mfp {
 
 constexpr int kTokPerCta = 8;
 
-// thread d owns column d of every row it touches: coalesced 1 KB table-row reads, no cross-thread reduction
-__global__ void __launch_bounds__(kD) embed_fwd_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs mod,
-                                                       const unsigned char* __restrict__ flags, const float* __restrict__ params, int T,
-                                                       float* __restrict__ h0) {
-  const int d = threadIdx.x;
-  const int t0 = blockIdx.x * kTokPerCta;
-#pragma unroll 1
-  for (int t = t0; t < min(T, t0 + kTokPerCta); ++t) {
-    float acc = 0.0f;
-    for (int f = 0; f < sc.F; ++f) {
+// One warp per element: lane l first resolves lookup l (a categorical sub-target's table row, or a numerical field's
+// <MASK> / <UNUSED> / bias row) to a parameter offset, then the warp streams the rows -- independent 1 KB reads, two
+// float4 per lane -- and accumulates them in the reference's order (fields in column order, sub-targets in order).
+__global__ void __launch_bounds__(32 * kTokPerCta) embed_fwd_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs mod,
+                                                                    const unsigned char* __restrict__ flags, const float* __restrict__ params, int T,
+                                                                    float* __restrict__ h0) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * kTokPerCta + (threadIdx.x >> 5);
+  if (t >= T) return;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+  for (int base = 0; base < sc.n_lookups; base += 32) {
+    long long my_off = 0;
+    const int l = base + lane;
+    if (l < sc.n_lookups) {
+      const int f = sc.lk_field[l], c = sc.lk_sub[l];
       const FieldDev& fd = sc.f[f];
       if (fd.kind == 0) {
-        const int* idx = reinterpret_cast<const int*>(mod.cols[f]) + (size_t)t * fd.C;
-        for (int c = 0; c < fd.C; ++c) {
-          int i = __ldg(idx + c);
-          i = min(max(i, 0), fd.input_dim + 1);
-          acc += __ldg(params + fd.table_off + (size_t)i * kD + d);  // encoder.py:157-160
-        }
+        int i = __ldg(reinterpret_cast<const int*>(mod.cols[f]) + (size_t)t * fd.C + c);
+        i = min(max(i, 0), fd.input_dim + 1);
+        my_off = fd.table_off + (long long)i * kD;  // encoder.py:157-160
       } else {
         const int flag = flags[(size_t)fd.num_slot * T + t];
-        acc += flag ? __ldg(params + fd.table_off + (size_t)(flag - 1) * kD + d)  // encoder.py:167-175
-                    : __ldg(params + fd.bias_off + d);                            // Dense bias; x.W is added by the GEMM
+        my_off = flag ? fd.table_off + (long long)(flag - 1) * kD  // encoder.py:167-175
+                      : fd.bias_off;                               // Dense bias; x.W is added by the GEMM
       }
     }
-    h0[(size_t)t * kD + d] = acc;
+    const int cnt = min(32, sc.n_lookups - base);
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) {
+      const long long off = __shfl_sync(0xffffffffu, my_off, j);
+      const float4* row = reinterpret_cast<const float4*>(params + off);
+      const float4 r0 = __ldg(row + lane), r1 = __ldg(row + 32 + lane);
+      a0.x += r0.x; a0.y += r0.y; a0.z += r0.z; a0.w += r0.w;
+      a1.x += r1.x; a1.y += r1.y; a1.z += r1.z; a1.w += r1.w;
+    }
+  }
+  float4* out = reinterpret_cast<float4*>(h0 + (size_t)t * kD);
+  out[lane] = a0;
+  out[32 + lane] = a1;
+}
+
+// Backward of the above as a tensor-core contraction.  Every element selects a handful of "gradient rows" (one per
+// categorical sub-target; for a numerical field the <MASK> row, the <UNUSED> row or the Dense bias), so
+//     d(table rows)[R, D] = OneHot[T, R]^T . dh0[T, D]
+// is a wgrad-shaped GEMM with an MN-major multi-hot A operand.  embed_onehot_kernel writes that operand (small integer
+// counts, exact in TF32); the engine runs the GEMM into a scratch [R, D] block and embed_scatter_kernel moves the rows
+// to their variables.  The Dense kernels' gradients are X^T . dh0m GEMMs, dh0m = dh0 with the rows of special-token
+// elements zeroed (written by the last LayerNorm-backward launch, transformer.cu).
+__global__ void __launch_bounds__(32 * kTokPerCta) embed_onehot_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs mod,
+                                                                       const unsigned char* __restrict__ flags, int T, float* __restrict__ onehot) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * kTokPerCta + (threadIdx.x >> 5);
+  if (t >= T) return;
+  float4* out = reinterpret_cast<float4*>(onehot + (size_t)t * sc.Rp);
+  const int n4 = sc.Rp >> 2;
+  for (int j = lane; j < n4; j += 32) out[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+  for (int l = lane; l < sc.n_lookups; l += 32) {
+    const int f = sc.lk_field[l], c = sc.lk_sub[l];
+    const FieldDev& fd = sc.f[f];
+    int r;
+    if (fd.kind == 0) {
+      const int i = __ldg(reinterpret_cast<const int*>(mod.cols[f]) + (size_t)t * fd.C + c);
+      r = fd.grow_off + min(max(i, 0), fd.input_dim + 1);
+    } else {
+      const int flag = flags[(size_t)fd.num_slot * T + t];
+      r = fd.grow_off + (flag ? flag - 1 : 2);
+    }
+    atomicAdd(onehot + (size_t)t * sc.Rp + r, 1.0f);  // sub-targets of one field may pick the same row (color): counts, not flags
   }
 }
 
-// Backward of the above.  grid = (chunks, F).  Each CTA accumulates its token chunk into a shared-memory copy
-// of the field's table (thread d owns column d -> no conflicts, no atomics), then flushes once with atomics.
-// Numerical fields use a 3-row table {<MASK> row, <UNUSED> row, bias} and also emit dh0 masked by flag == 0,
-// which is the B operand of the Dense kernel's wgrad GEMM.
-__global__ void __launch_bounds__(kD) embed_bwd_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs mod,
-                                                       const unsigned char* __restrict__ flags, const float* __restrict__ dh0, int T,
-                                                       int tok_per_chunk, float* __restrict__ grads, float* __restrict__ dh0_masked) {
-  extern __shared__ float tab[];
+// grid = rows of the scratch block, block = D
+__global__ void __launch_bounds__(kD) embed_scatter_kernel(const __grid_constant__ Schema sc, const float* __restrict__ scratch, float* __restrict__ grads) {
   const int d = threadIdx.x;
-  const int f = blockIdx.y;
-  const FieldDev& fd = sc.f[f];
-  const int rows = (fd.kind == 0) ? fd.input_dim + 2 : 3;
-  for (int r = 0; r < rows; ++r) tab[r * kD + d] = 0.0f;
-  const int t0 = blockIdx.x * tok_per_chunk;
-  const int t1 = min(T, t0 + tok_per_chunk);
-  if (fd.kind == 0) {
-    const int* idx = reinterpret_cast<const int*>(mod.cols[f]);
-#pragma unroll 1
-    for (int t = t0; t < t1; ++t) {
-      const float g = dh0[(size_t)t * kD + d];
-      for (int c = 0; c < fd.C; ++c) {
-        int i = __ldg(idx + (size_t)t * fd.C + c);
-        i = min(max(i, 0), fd.input_dim + 1);
-        tab[i * kD + d] += g;
+  const int r = blockIdx.x;
+  {
+    for (int f = 0; f < sc.F; ++f) {
+      const FieldDev& fd = sc.f[f];
+      const int rows = (fd.kind == 0) ? fd.input_dim + 2 : 3;
+      if (r >= fd.grow_off && r < fd.grow_off + rows) {
+        const int k = r - fd.grow_off;
+        const long long dst = (fd.kind == 0 || k < 2) ? fd.table_off + (long long)k * kD : fd.bias_off;
+        grads[dst + d] = scratch[(size_t)r * kD + d];
+        return;
       }
     }
-    for (int r = 0; r < rows; ++r) {
-      const float v = tab[r * kD + d];
-      if (v != 0.0f) atomicAdd(grads + fd.table_off + (size_t)r * kD + d, v);
-    }
-  } else {
-    float* masked = dh0_masked + (size_t)fd.num_slot * T * kD;
-#pragma unroll 1
-    for (int t = t0; t < t1; ++t) {
-      const float g = dh0[(size_t)t * kD + d];
-      const int flag = flags[(size_t)fd.num_slot * T + t];
-      tab[(flag ? flag - 1 : 2) * kD + d] += g;
-      masked[(size_t)t * kD + d] = flag ? 0.0f : g;
-    }
-    atomicAdd(grads + fd.table_off + d, tab[d]);
-    atomicAdd(grads + fd.table_off + kD + d, tab[kD + d]);
-    atomicAdd(grads + fd.bias_off + d, tab[2 * kD + d]);
   }
 }
 
 int launch_embed_fwd(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, const float* params, int T, float* h0, cudaStream_t st) {
-  embed_fwd_kernel<<<(T + kTokPerCta - 1) / kTokPerCta, kD, 0, st>>>(sc, mod, flags, params, T, h0);
+  embed_fwd_kernel<<<(T + kTokPerCta - 1) / kTokPerCta, 32 * kTokPerCta, 0, st>>>(sc, mod, flags, params, T, h0);
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
 
-int launch_embed_bwd(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, const float* dh0, int T, float* grads, float* dh0_masked,
-                     cudaStream_t st) {
-  int max_rows = 3;
-  for (int f = 0; f < sc.F; ++f)
-    if (sc.f[f].kind == 0) max_rows = max(max_rows, sc.f[f].input_dim + 2);
-  const size_t smem = (size_t)max_rows * kD * sizeof(float);
-  if (smem > 200 * 1024) { set_error("embed_bwd: vocabulary of %d rows does not fit the shared-memory table", max_rows); return MFP_ERR_UNSUPPORTED; }
-  static size_t configured = 0;
-  if (smem > configured) {
-    MFP_CUDA_OK(cudaFuncSetAttribute(embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  const int chunks = min(64, (T + 63) / 64);
-  const int tok_per_chunk = (T + chunks - 1) / chunks;
-  embed_bwd_kernel<<<dim3(chunks, sc.F), kD, smem, st>>>(sc, mod, flags, dh0, T, tok_per_chunk, grads, dh0_masked);
+int launch_embed_onehot(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, int T, float* onehot, cudaStream_t st) {
+  embed_onehot_kernel<<<(T + kTokPerCta - 1) / kTokPerCta, 32 * kTokPerCta, 0, st>>>(sc, mod, flags, T, onehot);
+  MFP_CUDA_OK(cudaGetLastError());
+  return MFP_OK;
+}
+
+int launch_embed_scatter(const Schema& sc, const float* scratch, float* grads, cudaStream_t st) {
+  embed_scatter_kernel<<<sc.R, kD, 0, st>>>(sc, scratch, grads);
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }

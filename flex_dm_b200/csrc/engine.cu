@@ -28,7 +28,7 @@ struct BlockLayout {
 
 struct Workspace {
   // byte offsets into the caller's workspace
-  size_t vars, flags, x, ln1, qkv, attn, xmid, ln2, hid, stats, lse, logits, dlogits, dx, dtmp, dy, dqkv, dhid, dattn, dh0m, part, idx_true, idx_pred,
+  size_t vars, flags, x, ln1, qkv, attn, xmid, ln2, hid, stats, lse, logits, dlogits, dx, dtmp, dy, dqkv, dhid, dattn, dh0m, onehot, rowgrad, part, idx_true, idx_pred,
       norms, total;
 };
 
@@ -177,10 +177,12 @@ static Workspace plan_workspace(const mfp_engine* h, int B, int S) {
   w.dhid = take(T * kF * fl);
   w.dattn = take(T * D * fl);
   w.dh0m = take((size_t)(h->sc.n_num > 0 ? h->sc.n_num : 1) * T * D * fl);
+  w.onehot = take(T * (size_t)h->sc.Rp * fl);
+  w.rowgrad = take((size_t)h->sc.Rp * D * fl);
   w.part = take(3 * F * T * fl);
   w.idx_true = take(T * sizeof(int));
   w.idx_pred = take(T * sizeof(int));
-  w.norms = take(2 * h->vars.size() * fl);
+  w.norms = take(2 * 16 * h->vars.size() * fl);
   w.total = cur;
   return w;
 }
@@ -289,6 +291,20 @@ int mfp_create(const mfp_config* cfg, const mfp_field_desc* fields, mfp_engine**
     h->field_names.push_back(std::string(d.name, strnlen(d.name, sizeof(d.name))));
   }
   h->sc.n_num = n_num;
+  int n_lk = 0;
+  for (int f = 0; f < cfg->num_fields; ++f) {
+    const int subs = (h->sc.f[f].kind == 0) ? h->sc.f[f].C : 1;
+    if (n_lk + subs > kMaxLookups) { set_error("mfp_create: more than %d embedding lookups per element", kMaxLookups); delete h; return MFP_ERR_UNSUPPORTED; }
+    for (int c = 0; c < subs; ++c) { h->sc.lk_field[n_lk] = (unsigned char)f; h->sc.lk_sub[n_lk] = (unsigned char)c; ++n_lk; }
+  }
+  h->sc.n_lookups = n_lk;
+  int grow = 0;
+  for (int f = 0; f < cfg->num_fields; ++f) {
+    h->sc.f[f].grow_off = grow;
+    grow += (h->sc.f[f].kind == 0) ? h->sc.f[f].input_dim + 2 : 3;
+  }
+  h->sc.R = grow;
+  h->sc.Rp = (grow + 3) & ~3;
   if (cfg->type_field < 0 || cfg->type_field >= cfg->num_fields || h->sc.f[cfg->type_field].kind != 0) {
     set_error("mfp_create: type_field must index a categorical field");
     delete h;
@@ -530,20 +546,28 @@ int mfp_backward(mfp_engine* h, const mfp_batch* modified, int32_t training, uin
     }
     MFP_TRY(gemm(h, ln1, 1, D, dqkv, 1, 3 * D, D, 3 * D, T, make_epilogue(G + b.wqkv, 3 * D), wgrad_splits(D, 3 * D, T), st, G + b.bqkv));
     MFP_TRY(gemm(h, dqkv, 0, 3 * D, P + b.wqkv, 0, 3 * D, T, D, 3 * D, make_epilogue(dtmp, D), 1, st));
-    MFP_TRY(launch_layernorm_bwd(xi, dtmp, P + b.g1, stats, stats + T, dx, T, dx, G + b.g1, G + b.be1, st));
+    if (i == 0 && sc.n_num > 0)
+      MFP_TRY(launch_layernorm_bwd(xi, dtmp, P + b.g1, stats, stats + T, dx, T, dx, G + b.g1, G + b.be1, st, wsp<unsigned char>(h, h->off.flags), sc.n_num,
+                                   wsp<float>(h, h->off.dh0m)));
+    else
+      MFP_TRY(launch_layernorm_bwd(xi, dtmp, P + b.g1, stats, stats + T, dx, T, dx, G + b.g1, G + b.be1, st));
     h->launches += 3;
   }
-  // ---- encoder: tables / special rows / bias by shared-memory scatter; Dense kernels by wgrad GEMM
+  // ---- encoder: table / special / bias rows by a one-hot wgrad GEMM; Dense kernels by X^T . (dh0 with special-token rows zeroed) (encoder.cu)
   const unsigned char* flags = wsp<unsigned char>(h, h->off.flags);
-  float* dh0m = wsp<float>(h, h->off.dh0m);
-  MFP_TRY(launch_embed_bwd(sc, mod, flags, dx, T, G, dh0m, st));
-  h->launches++;
+  float* onehot = wsp<float>(h, h->off.onehot);
+  float* rowgrad = wsp<float>(h, h->off.rowgrad);
+  MFP_TRY(launch_embed_onehot(sc, mod, flags, T, onehot, st));
+  MFP_CUDA_OK(cudaMemsetAsync(rowgrad, 0, (size_t)sc.Rp * D * sizeof(float), st));
+  MFP_TRY(gemm(h, onehot, 1, sc.Rp, dx, 1, D, sc.R, D, T, make_epilogue(rowgrad, D), wgrad_splits(sc.R, D, T), st));
   for (int f = 0; f < sc.F; ++f) {
     const FieldDev& fd = sc.f[f];
     if (fd.kind != 1) continue;
-    MFP_TRY(gemm(h, reinterpret_cast<const float*>(mod.cols[f]), 1, fd.C, dh0m + (size_t)fd.num_slot * TD, 1, D, fd.C, D, T,
+    MFP_TRY(gemm(h, reinterpret_cast<const float*>(mod.cols[f]), 1, fd.C, wsp<float>(h, h->off.dh0m) + (size_t)fd.num_slot * TD, 1, D, fd.C, D, T,
                  make_epilogue(G + fd.kernel_off, D), wgrad_splits(fd.C, D, T), st));
   }
+  MFP_TRY(launch_embed_scatter(sc, rowgrad, G, st));
+  h->launches += 2;
   return MFP_OK;
 }
 

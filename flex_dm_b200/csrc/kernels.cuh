@@ -22,13 +22,15 @@ int launch_row_flags(const Schema& sc, const BatchPtrs& mod, int T, unsigned cha
 
 // encoder.cu
 int launch_embed_fwd(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, const float* params, int T, float* h0, cudaStream_t st);
-int launch_embed_bwd(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, const float* dh0, int T, float* grads,
-                     float* dh0_masked /*[n_num][T*D]*/, cudaStream_t st);
+int launch_embed_onehot(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, int T, float* onehot /*[T][Rp]*/, cudaStream_t st);
+int launch_embed_scatter(const Schema& sc, const float* scratch /*[R][D]*/, float* grads, cudaStream_t st);
 
 // transformer.cu
 int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, int T, float* y, float* mean, float* rstd, cudaStream_t st);
+// rowflags / n_masked / dx_masked (optional): also write n_masked copies of dx with the rows whose flag != 0 zeroed (encoder Dense wgrads)
 int launch_layernorm_bwd(const float* x, const float* dy, const float* gamma, const float* mean, const float* rstd, const float* dres, int T,
-                         float* dx, float* dgamma, float* dbeta, cudaStream_t st);
+                         float* dx, float* dgamma, float* dbeta, cudaStream_t st, const unsigned char* rowflags = nullptr, int n_masked = 0,
+                         float* dx_masked = nullptr);
 int launch_attention_fwd(const float* qkv, const int* length, int B, int S, float* out, float* lse, cudaStream_t st);
 int launch_attention_bwd(const float* qkv, const float* out, const float* lse, const float* dout, const int* length, int B, int S, float* dqkv,
                          cudaStream_t st);
@@ -59,8 +61,8 @@ struct VarDev {
   long long off;
   int rows, cols, ld, l2;
 };
-int launch_regularization_loss(const VarDev* vars, int V, const float* params, float* norms /*[2][V]*/, float l2, float* out, cudaStream_t st);
-int launch_optimizer(const VarDev* vars, int V, float* params, const float* grads, float* m, float* v, float* norms /*[2][V]*/, int t, float lr,
+int launch_regularization_loss(const VarDev* vars, int V, const float* params, float* norms /*[V][16][2] partial sums*/, float l2, float* out, cudaStream_t st);
+int launch_optimizer(const VarDev* vars, int V, float* params, const float* grads, float* m, float* v, float* norms /*[V][16][2] partial sums*/, int t, float lr,
                      float clipnorm, float l2, float* l2_loss_out, cudaStream_t st);
 
 }  // namespace mfp

@@ -5,44 +5,44 @@
 
 namespace mfp {
 
-// one CTA per variable: ||g + 2 l2 w||_2 and sum w^2 (fixed-order reduction -> deterministic)
+constexpr int kNormChunks = 16;  // CTAs per variable in the norm pass; partials are summed in a fixed order (deterministic)
+
+// grid = (V, kNormChunks): partial sums of (g + 2 l2 w)^2 and w^2 over one slice of one variable
 __global__ void __launch_bounds__(256) var_norms_kernel(const VarDev* __restrict__ vars, const float* __restrict__ params,
-                                                        const float* __restrict__ grads, float l2, int V, float* __restrict__ norms) {
-  __shared__ float red[2][256];
+                                                        const float* __restrict__ grads, float l2, int V, float* __restrict__ part) {
+  __shared__ float red[2][8];
   const VarDev v = vars[blockIdx.x];
   const int n = v.rows * v.cols;
   const float k = (v.l2 && l2 > 0.f) ? 2.0f * l2 : 0.f;
+  const int per = (n + kNormChunks - 1) / kNormChunks;
+  const int i0 = blockIdx.y * per, i1 = min(n, i0 + per);
   float sg = 0.f, sw = 0.f;
-  for (int i = threadIdx.x; i < n; i += 256) {
+  for (int i = i0 + threadIdx.x; i < i1; i += 256) {
     const int r = i / v.cols, c = i - r * v.cols;
     const size_t idx = (size_t)v.off + (size_t)r * v.ld + c;
     const float w = params[idx];
-    const float g = grads[idx] + k * w;
+    const float g = (grads ? grads[idx] : 0.f) + k * w;
     sg += g * g;
     sw += w * w;
   }
-  red[0][threadIdx.x] = sg;
-  red[1][threadIdx.x] = sw;
+  sg = warp_sum(sg);
+  sw = warp_sum(sw);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sg; red[1][threadIdx.x >> 5] = sw; }
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      red[0][threadIdx.x] += red[0][threadIdx.x + o];
-      red[1][threadIdx.x] += red[1][threadIdx.x + o];
-    }
-    __syncthreads();
-  }
   if (threadIdx.x == 0) {
-    norms[blockIdx.x] = sqrtf(red[0][0]);
-    norms[V + blockIdx.x] = (v.l2 && l2 > 0.f) ? red[1][0] : 0.f;
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; b += red[1][w]; }
+    part[(blockIdx.x * kNormChunks + blockIdx.y) * 2] = a;
+    part[(blockIdx.x * kNormChunks + blockIdx.y) * 2 + 1] = (v.l2 && l2 > 0.f) ? b : 0.f;
   }
 }
 
-__global__ void l2_loss_kernel(const float* __restrict__ norms, int V, float l2, float* __restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    float s = 0.f;
-    for (int i = 0; i < V; ++i) s += norms[V + i];
-    *out = (l2 > 0.f) ? l2 * s : 0.f;  // A3: l2 * sum(w^2), no 1/2
-  }
+// one warp: l2 * sum over regularised variables of sum w^2 (fixed order)
+__global__ void l2_loss_kernel(const float* __restrict__ part, int V, float l2, float* __restrict__ out) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < V * kNormChunks; i += 32) s += part[2 * i + 1];
+  s = warp_sum(s);
+  if (threadIdx.x == 0) *out = (l2 > 0.f) ? l2 * s : 0.f;  // A3: l2 * sum(w^2), no 1/2
 }
 
 // grid = (V, chunks)
@@ -52,7 +52,10 @@ __global__ void __launch_bounds__(256) adam_kernel(const VarDev* __restrict__ va
   const VarDev v = vars[blockIdx.x];
   const int n = v.rows * v.cols;
   const float k = (v.l2 && l2 > 0.f) ? 2.0f * l2 : 0.f;
-  const float scale = (clipnorm > 0.f) ? clipnorm / fmaxf(norms[blockIdx.x], clipnorm) : 1.0f;  // tf.clip_by_norm (A4)
+  float nsq = 0.f;
+#pragma unroll
+  for (int c = 0; c < kNormChunks; ++c) nsq += norms[(blockIdx.x * kNormChunks + c) * 2];
+  const float scale = (clipnorm > 0.f) ? clipnorm / fmaxf(sqrtf(nsq), clipnorm) : 1.0f;  // tf.clip_by_norm (A4)
   for (int i = blockIdx.y * 256 + threadIdx.x; i < n; i += gridDim.y * 256) {
     const int r = i / v.cols, c = i - r * v.cols;
     const size_t idx = (size_t)v.off + (size_t)r * v.ld + c;
@@ -66,30 +69,8 @@ __global__ void __launch_bounds__(256) adam_kernel(const VarDev* __restrict__ va
   }
 }
 
-// l2 * sum w^2 only (Keras test_step adds the regularisation losses to the reported loss as well)
-__global__ void __launch_bounds__(256) var_w2_kernel(const VarDev* __restrict__ vars, const float* __restrict__ params, float l2, int V,
-                                                     float* __restrict__ norms) {
-  __shared__ float red[256];
-  const VarDev v = vars[blockIdx.x];
-  const int n = v.rows * v.cols;
-  float sw = 0.f;
-  if (v.l2 && l2 > 0.f)
-    for (int i = threadIdx.x; i < n; i += 256) {
-      const int r = i / v.cols, c = i - r * v.cols;
-      const float w = params[(size_t)v.off + (size_t)r * v.ld + c];
-      sw += w * w;
-    }
-  red[threadIdx.x] = sw;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) norms[V + blockIdx.x] = red[0];
-}
-
 int launch_regularization_loss(const VarDev* vars, int V, const float* params, float* norms, float l2, float* out, cudaStream_t st) {
-  var_w2_kernel<<<V, 256, 0, st>>>(vars, params, l2, V, norms);
+  var_norms_kernel<<<dim3(V, kNormChunks), 256, 0, st>>>(vars, params, nullptr, l2, V, norms);
   MFP_CUDA_OK(cudaGetLastError());
   l2_loss_kernel<<<1, 32, 0, st>>>(norms, V, l2, out);
   MFP_CUDA_OK(cudaGetLastError());
@@ -98,7 +79,7 @@ int launch_regularization_loss(const VarDev* vars, int V, const float* params, f
 
 int launch_optimizer(const VarDev* vars, int V, float* params, const float* grads, float* m, float* v, float* norms, int t, float lr, float clipnorm,
                      float l2, float* l2_loss_out, cudaStream_t st) {
-  var_norms_kernel<<<V, 256, 0, st>>>(vars, params, grads, l2, V, norms);
+  var_norms_kernel<<<dim3(V, kNormChunks), 256, 0, st>>>(vars, params, grads, l2, V, norms);
   MFP_CUDA_OK(cudaGetLastError());
   if (l2_loss_out) {
     l2_loss_kernel<<<1, 32, 0, st>>>(norms, V, l2, l2_loss_out);

@@ -33,7 +33,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ dres, int T, float* __restrict__ dx,
-                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            const unsigned char* __restrict__ rowflags, int n_masked, float* __restrict__ dx_masked) {
   __shared__ float red[2][8][kD];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + lane), gb = __ldg(reinterpret_cast<const float4*>(gamma) + 32 + lane);
@@ -68,6 +69,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     float4* out = reinterpret_cast<float4*>(dx + (size_t)t * kD);
     out[lane] = make_float4(o[0], o[1], o[2], o[3]);
     out[32 + lane] = make_float4(o[4], o[5], o[6], o[7]);
+    // encoder: copies of dx with the rows of special-token elements zeroed, one per numerical field (B operand of its Dense wgrad)
+    for (int s = 0; s < n_masked; ++s) {
+      const bool keep = rowflags[(size_t)s * T + t] == 0;
+      float4* mo = reinterpret_cast<float4*>(dx_masked + ((size_t)s * T + t) * kD);
+      mo[lane] = keep ? make_float4(o[0], o[1], o[2], o[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      mo[32 + lane] = keep ? make_float4(o[4], o[5], o[6], o[7]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -272,9 +280,9 @@ int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, 
 }
 
 int launch_layernorm_bwd(const float* x, const float* dy, const float* gamma, const float* mean, const float* rstd, const float* dres, int T,
-                         float* dx, float* dgamma, float* dbeta, cudaStream_t st) {
+                         float* dx, float* dgamma, float* dbeta, cudaStream_t st, const unsigned char* rowflags, int n_masked, float* dx_masked) {
   const int grid = min((T + 7) / 8, 148 * 4);
-  layernorm_bwd_kernel<<<grid, 256, 0, st>>>(x, dy, gamma, mean, rstd, dres, T, dx, dgamma, dbeta);
+  layernorm_bwd_kernel<<<grid, 256, 0, st>>>(x, dy, gamma, mean, rstd, dres, T, dx, dgamma, dbeta, rowflags, n_masked, dx_masked);
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }

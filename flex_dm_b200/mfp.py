@@ -162,6 +162,21 @@ class MFP:
             out[key] = x.contiguous()
         return out
 
+    def host_columns(self, inputs: Dict) -> Dict[str, torch.Tensor]:
+        """The columns the path reads, as host tensors of the engine's dtypes (int32 / float32), ready for an H2D copy."""
+        out = {}
+        for key, column in self.input_columns.items():
+            if key not in inputs:
+                if key == "length" or column["is_sequence"]:
+                    raise KeyError("missing input column %s" % key)
+                continue
+            x = inputs[key]
+            if isinstance(x, np.ndarray):
+                x = torch.from_numpy(x)
+            want = torch.float32 if column.get("type") == "numerical" else torch.int32
+            out[key] = (x if x.dtype == want else x.to(want)).contiguous()
+        return out
+
     def _bind(self, staged: Dict[str, torch.Tensor]):
         B, S = staged[self.keys[0]].shape[:2]
         self.engine.bind(int(B), int(S))
@@ -235,14 +250,14 @@ class MFP:
             rows[:, -1] = l2
         return rows
 
-    def _run_epoch(self, iterator, steps: int, train: bool) -> "OrderedDict[str, float]":
+    def _run_epoch(self, iterator, steps: int, train: bool, staged: bool = False) -> "OrderedDict[str, float]":
         if steps > self._ring.shape[0] if self._ring is not None else False:
             self._ring = torch.zeros((steps, self.engine.metrics_width), dtype=torch.float32, device=self.device)
             self._ring_pos = 0
         rows = []
         for _ in range(steps):
             batch = next(iterator)
-            rows.append(self.train_step(batch) if train else self.test_step(batch))
+            rows.append(self.train_step(batch, staged=staged) if train else self.test_step(batch, staged=staged))
             if len(rows) == self._ring.shape[0]:
                 break
         stacked = self._reduce_rows(torch.stack(rows)).cpu().numpy()
@@ -252,9 +267,11 @@ class MFP:
     def fit(self, dataset: Iterable, steps_per_epoch: int, epochs: int = 1, validation_data: Optional[Iterable] = None,
             validation_steps: Optional[int] = None, validation_freq: int = 1, callbacks=None, verbose: int = 2):
         """train.py:79-88.  ``dataset`` yields batch dicts and repeats (train.py:44-46 ``repeat=True``)."""
-        iterator = iter(dataset)
+        from .data import DevicePrefetcher
+
+        iterator = DevicePrefetcher(self, dataset)  # H2D copies of step i+1 run under the compute of step i
         for epoch in range(epochs):
-            logs = self._run_epoch(iterator, steps_per_epoch, True)
+            logs = self._run_epoch(iterator, steps_per_epoch, True, staged=True)
             if validation_data is not None and (epoch + 1) % max(1, validation_freq) == 0:
                 val = self._run_epoch(iter(validation_data), validation_steps or 1, False)
                 logs.update(("val_" + k, v) for k, v in val.items())
