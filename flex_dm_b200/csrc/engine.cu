@@ -54,6 +54,7 @@ struct mfp_engine {
   // optional per-kernel-class device timing (bench.py roofline): CUDA event pairs around each launch
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events[MFP_PROFILE_CLASSES];
+  double prof_bytes[MFP_PROFILE_CLASSES] = {0, 0};  // algorithmic HBM bytes of the profiled launches
 };
 
 namespace mfp {
@@ -205,8 +206,9 @@ static int check_bound(const mfp_engine* h) {
 
 struct ProfScope {
   mfp_engine* h; int cls; cudaStream_t st; cudaEvent_t stop = nullptr;
-  ProfScope(mfp_engine* h_, int cls_, cudaStream_t st_) : h(h_), cls(cls_), st(st_) {
+  ProfScope(mfp_engine* h_, int cls_, cudaStream_t st_, double bytes = 0.0) : h(h_), cls(cls_), st(st_) {
     if (!h->profiling) return;
+    h->prof_bytes[cls] += bytes;
     cudaEvent_t start;
     cudaEventCreate(&start);
     cudaEventCreate(&stop);
@@ -233,7 +235,9 @@ static int gemm(mfp_engine* h, const float* A, int a_mn, int lda, const float* B
     MFP_TRY(launch_colsum(Bp, K, N, ldb, colsum, st));
     h->launches++;
   }
-  ProfScope prof(h, MFP_PROFILE_GEMM, st);
+  // algorithmic bytes: each operand and the output once, plus the residual / ReLU-mask operand
+  const double bytes = 4.0 * ((double)M * K + (double)N * K + (double)M * N * ((ep.residual || ep.relu_src) ? 2.0 : 1.0));
+  ProfScope prof(h, MFP_PROFILE_GEMM, st, bytes);
   return launch_gemm(h->maps, c, h->gemm_impl, st);
 }
 
@@ -431,7 +435,7 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
     e1.bias = P + b.bqkv;
     MFP_TRY(gemm(h, ln1, 0, D, P + b.wqkv, 1, 3 * D, T, 3 * D, D, e1, 1, st));
     {
-      ProfScope prof(h, MFP_PROFILE_ATTENTION, st);
+      ProfScope prof(h, MFP_PROFILE_ATTENTION, st, 4.0 * T * (3.0 * D + D) + 4.0 * h->B * kH * h->S);  // qkv in, out + lse
       if (h->gemm_impl == 0 && h->S <= 128) MFP_TRY(launch_attention_fwd_tc(h->maps, qkv, modified->length, h->B, h->S, attn, lse, st));
       else MFP_TRY(launch_attention_fwd(qkv, modified->length, h->B, h->S, attn, lse, st));
     }
@@ -540,7 +544,7 @@ int mfp_backward(mfp_engine* h, const mfp_batch* modified, int32_t training, uin
     MFP_TRY(gemm(h, attn, 1, D, dy, 1, D, D, D, T, make_epilogue(G + b.wo, D), wgrad_splits(D, D, T), st, G + b.bo));
     MFP_TRY(gemm(h, dy, 0, D, P + b.wo, 0, D, T, D, D, make_epilogue(dattn, D), 1, st));
     {
-      ProfScope prof(h, MFP_PROFILE_ATTENTION, st);
+      ProfScope prof(h, MFP_PROFILE_ATTENTION, st, 4.0 * T * (3.0 * D + D + D + 3.0 * D) + 4.0 * h->B * kH * h->S);  // qkv, out, dout in; dqkv out
       if (h->gemm_impl == 0 && h->S <= 128) MFP_TRY(launch_attention_bwd_tc(h->maps, qkv, attn, lse, dattn, modified->length, h->B, h->S, dqkv, st));
       else MFP_TRY(launch_attention_bwd(qkv, attn, lse, dattn, modified->length, h->B, h->S, dqkv, st));
     }
@@ -606,12 +610,13 @@ int mfp_set_gemm_impl(mfp_engine* h, int32_t impl) {
 int mfp_profile_begin(mfp_engine* h) {
   if (!h) { set_error("null engine"); return MFP_ERR_ARG; }
   for (auto& v : h->prof_events) { for (cudaEvent_t e : v) cudaEventDestroy(e); v.clear(); }
+  for (double& b : h->prof_bytes) b = 0.0;
   h->profiling = true;
   return MFP_OK;
 }
 
-int mfp_profile_end(mfp_engine* h, float* ms_per_class_host, int32_t* launches_per_class_host) {
-  if (!h || !ms_per_class_host || !launches_per_class_host) { set_error("mfp_profile_end: null argument"); return MFP_ERR_ARG; }
+int mfp_profile_end(mfp_engine* h, float* ms_per_class_host, int32_t* launches_per_class_host, double* bytes_per_class_host) {
+  if (!h || !ms_per_class_host || !launches_per_class_host || !bytes_per_class_host) { set_error("mfp_profile_end: null argument"); return MFP_ERR_ARG; }
   h->profiling = false;
   MFP_CUDA_OK(cudaDeviceSynchronize());
   for (int c = 0; c < MFP_PROFILE_CLASSES; ++c) {
@@ -624,6 +629,7 @@ int mfp_profile_end(mfp_engine* h, float* ms_per_class_host, int32_t* launches_p
     }
     ms_per_class_host[c] = total;
     launches_per_class_host[c] = (int32_t)(v.size() / 2);
+    bytes_per_class_host[c] = h->prof_bytes[c];
     for (cudaEvent_t e : v) cudaEventDestroy(e);
     v.clear();
   }

@@ -75,7 +75,7 @@ _SIGNATURES = {
     "mfp_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "mfp_set_gemm_impl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     "mfp_profile_begin": (ctypes.c_int, [ctypes.c_void_p]),
-    "mfp_profile_end": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)]),
+    "mfp_profile_end": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double)]),
     "mfp_debug_attention": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_int32, ctypes.c_void_p]),
     "mfp_debug_attention_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
@@ -322,11 +322,12 @@ class Engine:
         _check(self.lib, self.lib.mfp_profile_begin(self.handle), "mfp_profile_begin")
 
     def profile_end(self):
-        """-> {"gemm": (ms, launches), "attention": (ms, launches)}"""
+        """-> {"gemm": (ms, launches, algorithmic bytes), "attention": (...)}"""
         ms = (ctypes.c_float * 2)()
         n = (ctypes.c_int32 * 2)()
-        _check(self.lib, self.lib.mfp_profile_end(self.handle, ms, n), "mfp_profile_end")
-        return {"gemm": (float(ms[0]), int(n[0])), "attention": (float(ms[1]), int(n[1]))}
+        nbytes = (ctypes.c_double * 2)()
+        _check(self.lib, self.lib.mfp_profile_end(self.handle, ms, n, nbytes), "mfp_profile_end")
+        return {"gemm": (float(ms[0]), int(n[0]), float(nbytes[0])), "attention": (float(ms[1]), int(n[1]), float(nbytes[1]))}
 
     def set_gemm_impl(self, impl: int):
         """0 = tcgen05 TF32 (product path), 1 = fp32 SIMT bring-up GEMM (tests only)."""

@@ -22,6 +22,7 @@ import torch
 
 from .engine import Engine
 from .masking import get_task_names
+from .parallel import all_reduce_gradients, broadcast_parameters, reduce_metric_rows
 from .spec import get_dataset_name, get_valid_input_columns
 
 logger = logging.getLogger(__name__)
@@ -125,6 +126,7 @@ class MFP:
         """Shard batches over documents; one all-reduce of the flat gradient buffer per step."""
         self._dist = dist_module
         self._world = int(world_size)
+        broadcast_parameters(dist_module, self.engine.params, 0)  # every rank starts from rank 0's initialisation
 
     # ------------------------------------------------------------------ Keras surface
     def compile(self, optimizer=None, run_eagerly=None, **_):
@@ -205,7 +207,7 @@ class MFP:
         eng.loss(length, cols, eng.masks, row, 1.0 / (B * self._world), True, sort_tasks=tasks if self.sort_pos else None)
         eng.backward(length, None, True, seed, step)
         if self._world > 1:
-            self._dist.all_reduce(eng.grads)
+            all_reduce_gradients(self._dist, eng.grads)
         self.optimizer.iterations += 1
         eng.optimizer_step(self.optimizer.iterations, self.optimizer.learning_rate, self.optimizer.clipnorm, row[-1:])
         self._step += 1
@@ -244,10 +246,7 @@ class MFP:
 
     def _reduce_rows(self, rows: torch.Tensor) -> torch.Tensor:
         if self._world > 1:
-            rows = rows.clone()
-            l2 = rows[:, -1].clone()
-            self._dist.all_reduce(rows)
-            rows[:, -1] = l2
+            rows = reduce_metric_rows(self._dist, rows)
         return rows
 
     def _run_epoch(self, iterator, steps: int, train: bool, staged: bool = False) -> "OrderedDict[str, float]":

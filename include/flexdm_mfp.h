@@ -144,13 +144,14 @@ int64_t mfp_launch_count(const mfp_engine* h);
 int mfp_set_gemm_impl(mfp_engine* h, int32_t impl);
 
 /* Optional device timing of kernel classes (bench.py's roofline): between begin and end every launch of the class is
- * bracketed by CUDA events on the launching stream; end synchronises and returns the summed milliseconds and the
- * launch count per class (host arrays of MFP_PROFILE_CLASSES entries).  Not meant for the throughput-timed region. */
+ * bracketed by CUDA events on the launching stream; end synchronises and returns the summed milliseconds, the launch
+ * count and the algorithmic HBM bytes (every operand and output once) per class (host arrays of MFP_PROFILE_CLASSES
+ * entries).  Not meant for the throughput-timed region. */
 #define MFP_PROFILE_CLASSES 2
 #define MFP_PROFILE_GEMM 0
 #define MFP_PROFILE_ATTENTION 1
 int mfp_profile_begin(mfp_engine* h);
-int mfp_profile_end(mfp_engine* h, float* ms_per_class_host, int32_t* launches_per_class_host);
+int mfp_profile_end(mfp_engine* h, float* ms_per_class_host, int32_t* launches_per_class_host, double* bytes_per_class_host);
 
 /* Bring-up hook: the attention core of MultiHeadSelfAttention (architecture/transformer.py:60-76) alone.
  * qkv [B*S, 768] (q | k | v, head h = columns 32h..32h+31 of each third), length [B] zero-based;
