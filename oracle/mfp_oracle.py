@@ -1,12 +1,17 @@
 """TEST INFRASTRUCTURE (oracle) -- not product code.  Only tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs may import this package; the product path never does.
 
-PARITY UNPINNED: the reference (CyberAgentAILab/flex-dm @ f2bcc9f) has no tests, golden vectors or fixtures,
-and its arithmetic lives in tensorflow-gpu / tensorflow_probability (unpinned in requirements.txt:1,8; README.md:10
-says TF 2.8) which cannot be installed here (no wheel, Python 3.12, no network).  This file is therefore a CPU
-restatement, op for op, of the reference's Python plus the Keras/TF 2.8 semantics it relies on (SURVEY.md
-Appendix A, each one a named constant/function below so it can be flipped in one place).  It is pinned only by
-the hand-derived known-answer tests in tests/test_oracle_known_answers.py.
+PARITY STATUS: pinned against the reference's own Python, NOT against TensorFlow itself.  The reference
+(CyberAgentAILab/flex-dm @ f2bcc9f) has no tests, golden vectors or fixtures, and its arithmetic lives in
+tensorflow-gpu / tensorflow_probability (unpinned in requirements.txt:1,8; README.md:10 says TF 2.8) which cannot be
+installed here (no wheel, Python 3.12, no network).  tests/golden/make_golden.py therefore imports the reference's
+unmodified Python (mfp.models.mfp.MFP and everything under it) on top of a torch-backed stand-in for the slice of
+the TF/Keras API it touches (oracle/tf_standin/) and records its outputs; tests/test_golden_reference.py checks this
+file against those vectors: masking path bit-exact, logits / losses / scores / gradients / Adam update to 1e-10.
+What remains unpinned ("parity unpinned" in the strict sense): the semantics of the TF/Keras primitives themselves
+(each one a named constant/function below so it can be flipped in one place) -- the stand-in
+restates them from the same recall as this file -- and TensorFlow's RNG streams.  The hand-derived known-answer tests
+in tests/test_oracle_known_answers.py cover those primitives independently.
 
 Everything is plain PyTorch-CPU tensor code in the dtype of the parameters (float64 = parity oracle,
 float32 = the timed "port" CPU baseline).  All ``file:line`` citations are relative to

@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""Generate the golden vectors under tests/golden/ by executing the REFERENCE'S OWN PYTHON
+(/root/reference/src/mfp/mfp: MFP.call, preprocess_for_train, Model.call, LossLayer.call, sort_inputs, ...)
+on top of the torch-backed TensorFlow stand-in in oracle/tf_standin/ (TensorFlow cannot be installed here).
+
+    python tests/golden/make_golden.py            # needs /root/reference; runs in the build container only
+
+The vectors travel to the GPU box as committed .npz fixtures; nothing at test / bench time reads /root/reference.
+
+What the vectors pin: the reference's Python logic end to end, at the precision of float64 for the network/loss
+and bit-exactly for the masking path.  What they do not pin: the TF/Keras primitive semantics the stand-in restates
+from recall and TensorFlow's own RNG streams (random draws are scripted from the B200 path's
+Philox contract, in the reference's call order, so that masks are comparable bit for bit).
+
+Per case (file <case>.npz):
+  in/<column>            the batch (DataSpec.parse_fn layout)
+  tasks                  scripted task ids
+  mod/<column>, mask/<column>     outputs of the reference's preprocess_for_train, captured at Model.call / LossLayer.call
+  logits/<column>        float64 raw logits of Model.call(modified_inputs, training=True) with the scripted dropout masks
+  loss/<column>, score_num/<column>, score_den/<column>, metric/<name>, data_loss, total_loss
+  merged/<column>        MFP.call's return value (merge_inputs_and_prediction), float32 run
+  gradnorm/<variable>, gradproj/<variable>, gradhead/<variable>   per-variable summaries of d total_loss / d variable
+  newproj/<variable>, newhead/<variable>                           the same summaries of the variables after Adam(1e-4, clipnorm=1)
+Weights are not stored: they are oracle.mfp_oracle.init_params(cols, L, 256, seed=WEIGHT_SEED, bias_scale=0.05).
+"""
+import os
+import sys
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.dont_write_bytecode = True
+sys.path.insert(0, os.path.join(ROOT, "oracle", "tf_standin"))
+sys.path.insert(1, "/root/reference/src/mfp")
+sys.path.insert(2, ROOT)
+
+import tensorflow as tf  # noqa: E402  (the stand-in)
+from tensorflow import config as tfc  # noqa: E402
+from mfp.models.mfp import MFP as RefMFP  # noqa: E402  (the reference)
+
+from flex_dm_b200.spec import get_valid_input_columns, make_input_columns, make_synthetic_batch  # noqa: E402
+from oracle import mfp_oracle as O  # noqa: E402
+
+WEIGHT_SEED = 11
+D = 256
+RATE = 0.1
+L2 = 1e-2
+HEAD = 8  # leading entries of each gradient kept verbatim
+
+
+def projection_vector(name, n):
+    """Deterministic +-1 vector per variable (Philox-free, numpy PCG64 keyed by a stable hash of the name)."""
+    h = int.from_bytes(name.encode()[-8:].rjust(8, b"\0"), "little") ^ (len(name) * 0x9E3779B97F4A7C15 & (2**63 - 1))
+    rng = np.random.Generator(np.random.PCG64(h))
+    return rng.integers(0, 2, size=n).astype(np.float64) * 2.0 - 1.0
+
+
+CASES = OrderedDict([
+    # name: (dataset, masking_method, B, S, num_blocks, seed, step, lengths, tasks)
+    ("crello_random", ("crello", "random", 4, 16, 2, 7, 0, [16, 1, 9, 5], None)),
+    ("crello_multi", ("crello", "elem_pos_attr_img_txt", 6, 12, 2, 3, 2, [12, 7, 1, 12, 4, 10], [1, 3, 4, 5, 6, 3])),
+    ("rico_pos", ("rico", "elem_pos_attr", 5, 10, 2, 5, 1, [10, 3, 8, 1, 6], [3, 1, 4, 3, 3])),
+])
+
+
+def rng_script(cols, B, S, tasks, draws, num_blocks, training):
+    """The reference's RNG call order for one MFP.call(training): mfp.py:301 -> masking.py filter_padding :24-53
+    -> random_masking :227-269 -> elem_masking :136-155 -> feat_masking per group :116-133 -> Dropout x2 per block."""
+    icols = OrderedDict((k, v) for k, v in cols.items() if not v.get("demo_only", False))
+    seq = get_valid_input_columns(icols)
+    fidx = {k: i for i, k in enumerate(seq)}
+
+    def discard(c):
+        C = c["shape"][-1]
+        return ("randint", None) if c["type"] == "categorical" else ("normal", None)
+
+    s = [("categorical", np.asarray(tasks, dtype=np.int32))]
+    for k, c in seq.items():  # filter_padding: apply_token(..., "unused") evaluates the "random" dict entry eagerly
+        s.append(discard(c))
+    for k, c in seq.items():  # random_masking
+        u1, u2, u3 = draws.uniforms(fidx[k], B, S)
+        s += [("uniform", u1), ("uniform", u2), ("uniform", u3), discard(c)]
+        C = c["shape"][-1]
+        if c["type"] == "categorical":
+            s.append(("randint", draws.rand_cat(fidx[k], B, S, C, c["input_dim"])))
+        else:
+            s.append(("normal", draws.rand_num(fidx[k], B, S, C)))
+    s.append(("uniform", draws.elem_u(B)))  # select_single_element
+    for k, c in seq.items():
+        s.append(discard(c))
+    for group in O.get_attribute_groups(icols.keys()).values():  # feat_masking
+        for k in group:
+            s.append(discard(seq[k]))
+    if training:
+        for i in range(num_blocks):
+            for j in (0, 1):
+                s.append(("dropout", draws.dropout_keep(i, j, (B, S, D), RATE)))
+    return s
+
+
+def set_weights(model, params, dtype):
+    variables = model.named_variables()
+    assert set(variables) == set(params), (sorted(set(variables) ^ set(params)))
+    with torch.no_grad():
+        for name, w in variables.items():
+            assert tuple(w.shape) == tuple(params[name].shape), (name, w.shape, params[name].shape)
+            w.data = params[name].detach().to(dtype).clone()
+    return variables
+
+
+def run_case(name, spec):
+    dataset, method, B, S, L, seed, step, lengths, tasks = spec
+    cols = make_input_columns(dataset, max_length=max(S, 50))
+    batch = make_synthetic_batch(cols, B, S, seed=seed, fixed_lengths=np.asarray(lengths))
+    draws = O.PhiloxDraws(seed, step)
+    oracle = O.OracleMFP(cols, num_blocks=L, masking_method=method, dropout=RATE, l2=L2)
+    if tasks is None:
+        tasks = draws.tasks(B, oracle.allowed_tasks)
+    tasks = np.asarray(tasks, dtype=np.int32)
+    params = O.init_params(cols, L, D, WEIGHT_SEED, torch.float64, bias_scale=0.05)
+    out = {"tasks": tasks}
+    for k, v in batch.items():
+        out["in/" + k] = v
+
+    # ---------------- phase A: the whole MFP.call in float32 (bit-faithful dtypes for the masking path)
+    tfc.FLOAT = torch.float32
+    model = RefMFP(cols, num_blocks=L, block_type="deepsvg", masking_method=method, seq_type="default", arch_type="oneshot",
+                   context=None, input_dtype="set", latent_dim=D, dropout=RATE, l2=L2)
+    inputs32 = {k: torch.as_tensor(v).as_subclass(tf.Tensor) for k, v in batch.items()}
+    captured = {}
+    inner_call, loss_call = model.model.call, model.loss_layer.call
+
+    def model_spy(mod, training):
+        captured["mod"] = {k: v.clone() for k, v in mod.items()}
+        y = inner_call(mod, training)
+        captured["logits"] = {k: v for k, v in y.items()}
+        return y
+
+    def loss_spy(inputs, training=False, sort_flag=None, ignore_sort=None):
+        captured["targets"], _, captured["masks"] = inputs
+        captured["targets"] = dict(captured["targets"])
+        captured["masks"] = dict(captured["masks"])
+        captured["sort_flag"] = sort_flag
+        return loss_call(inputs, training, sort_flag, ignore_sort)
+
+    model.model.call, model.loss_layer.call = model_spy, loss_spy
+    tfc.rng = tfc.ScriptedRNG(rng_script(cols, B, S, tasks, draws, L, True))
+    model({k: v.clone() for k, v in inputs32.items()}, training=True)  # builds the lazily-created variables
+    set_weights(model, params, torch.float32)
+    model.reset_step_state()
+    tfc.rng = tfc.ScriptedRNG(rng_script(cols, B, S, tasks, draws, L, True))
+    merged = model({k: v.clone() for k, v in inputs32.items()}, training=True)
+    assert tfc.rng.done(), "the reference asked for fewer draws than scripted"
+    loss32 = float(sum(model.losses))
+    assert torch.equal(merged["tasks"].to(torch.int32), torch.as_tensor(tasks))
+    for k, v in captured["mod"].items():
+        out["mod/" + k] = v.detach().numpy()
+    for k, v in captured["masks"].items():
+        out["mask/" + k] = v.numpy()
+    for k, v in merged.items():
+        if k != "tasks":
+            out["merged/" + k] = v.detach().numpy().astype(np.float32) if v.is_floating_point() else v.numpy()
+    out["total_loss_f32_run"] = np.float64(loss32)
+
+    # ---------------- phase B: Model.call + LossLayer.call in float64 on the captured modified inputs
+    tfc.FLOAT = torch.float64
+    model.model.call, model.loss_layer.call = inner_call, loss_call
+    variables = set_weights(model, params, torch.float64)
+    model.reset_step_state()
+    mod64 = {k: (v.to(torch.float64) if v.is_floating_point() else v) for k, v in captured["mod"].items()}
+    targets64 = {k: (v.to(torch.float64) if v.is_floating_point() else v.clone()) for k, v in captured["targets"].items()}
+    tfc.rng = tfc.ScriptedRNG([("dropout", draws.dropout_keep(i, j, (B, S, D), RATE)) for i in range(L) for j in (0, 1)])
+    logits = model.model(mod64, True)
+    for k, v in logits.items():
+        out["logits/" + k] = v.detach().numpy()
+    if model.sort_pos:  # mfp.py:335-338
+        (scores,) = model.loss_layer((targets64, dict(logits), captured["masks"]), True, torch.as_tensor(tasks) == model.task_names.index("pos"))
+    else:
+        (scores,) = model.loss_layer((targets64, dict(logits), captured["masks"]), True)
+    assert tfc.rng.done()
+    data_loss = sum(model.loss_layer._losses)
+    total = sum(model.losses)
+    for k, v in scores.items():
+        key, what = k.rsplit("_score_", 1)
+        out["score_%s/%s" % (what, key)] = np.float64(v.detach())
+    for mname, v in model.loss_layer.step_metrics:
+        if mname.endswith("_loss"):
+            out["loss/" + mname[:-5]] = np.float64(torch.as_tensor(v).detach())
+        else:
+            out["metric/" + mname] = np.float64(torch.as_tensor(v).detach())
+    out["data_loss"] = np.float64(data_loss.detach())
+    out["total_loss"] = np.float64(total.detach())
+    assert abs(loss32 - float(total)) <= 2e-4 * abs(float(total)), (loss32, float(total))
+
+    names = list(variables.keys())
+    grads = torch.autograd.grad(total, [variables[n] for n in names], allow_unused=True)
+    grads = [g if g is not None else torch.zeros_like(variables[n]) for g, n in zip(grads, names)]
+    opt = tf.keras.optimizers.Adam(learning_rate=1e-4, clipnorm=1.0)  # train.py:71-77
+    opt.apply_gradients(zip(grads, [variables[n] for n in names]))
+    for n, g in zip(names, grads):
+        g = g.detach().numpy().reshape(-1)
+        w = variables[n].detach().numpy().reshape(-1)
+        pv = projection_vector(n, g.size)
+        out["gradnorm/" + n] = np.float64(np.linalg.norm(g))
+        out["gradproj/" + n] = np.float64(g @ pv)
+        out["gradhead/" + n] = g[:HEAD].copy()
+        out["newproj/" + n] = np.float64(w @ pv)
+        out["newhead/" + n] = w[:HEAD].copy()
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("%-16s tasks=%s total_loss=%.6f data_loss=%.6f -> %s (%.0f kB)" % (name, tasks.tolist(), float(total), float(data_loss),
+                                                                            os.path.relpath(path, ROOT), os.path.getsize(path) / 1e3))
+
+
+def run_demo_case(name="crello_demo", B=3, S=10, L=2, seed=5, lengths=(10, 1, 6), masked_keys=("left", "color", "image_embedding")):
+    """The eval.py / notebook entry: model(example, training=False, demo_args={"masks": ...}) (mfp.py:298-347 with
+    preprocess_for_test :72-92); forward only, no loss layer."""
+    cols = make_input_columns("crello", max_length=50)
+    batch = make_synthetic_batch(cols, B, S, seed=seed, fixed_lengths=np.asarray(lengths))
+    params = O.init_params(cols, L, D, WEIGHT_SEED, torch.float64, bias_scale=0.05)
+    icols = OrderedDict((k, v) for k, v in cols.items() if not v.get("demo_only", False))
+    seq = get_valid_input_columns(icols)
+    seq_mask = np.arange(S)[None, :] < np.asarray(lengths)[:, None]
+    masks = {}
+    for k, c in icols.items():
+        masks[k] = np.ones((B,), bool) if not c["is_sequence"] else (seq_mask.copy() if k in masked_keys else np.zeros((B, S), bool))
+    out = {"tasks": np.zeros((B,), np.int32)}
+    for k, v in batch.items():
+        out["in/" + k] = v
+    for k, v in masks.items():
+        out["mask/" + k] = v
+
+    def script():
+        d = [("randint", None) if c["type"] == "categorical" else ("normal", None) for c in seq.values()]
+        return [("categorical", out["tasks"])] + d + d  # task sampler, filter_padding, apply_token(..., "masked")
+
+    tfc.FLOAT = torch.float32
+    model = RefMFP(cols, num_blocks=L, block_type="deepsvg", masking_method="random", seq_type="default", arch_type="oneshot",
+                   context=None, input_dtype="set", latent_dim=D, dropout=RATE, l2=L2)
+    captured = {}
+    inner_call = model.model.call
+
+    def model_spy(mod, training):
+        assert not training
+        captured["mod"] = {k: v.clone() for k, v in mod.items()}
+        return inner_call(mod, training)
+
+    model.model.call = model_spy
+    inputs32 = {k: torch.as_tensor(v).as_subclass(tf.Tensor) for k, v in batch.items()}
+    tmasks = {k: torch.as_tensor(v).as_subclass(tf.Tensor) for k, v in masks.items()}
+    tfc.rng = tfc.ScriptedRNG(script())
+    model(dict(inputs32), training=False, demo_args={"masks": dict(tmasks)})
+    set_weights(model, params, torch.float32)
+    tfc.rng = tfc.ScriptedRNG(script())
+    merged = model(dict(inputs32), training=False, demo_args={"masks": dict(tmasks)})
+    assert tfc.rng.done()
+    for k, v in captured["mod"].items():
+        out["mod/" + k] = v.detach().numpy()
+    for k, v in merged.items():
+        if k != "tasks":
+            out["merged/" + k] = v.detach().numpy().astype(np.float32) if v.is_floating_point() else v.numpy()
+    tfc.FLOAT = torch.float64
+    model.model.call = inner_call
+    set_weights(model, params, torch.float64)
+    mod64 = {k: (v.to(torch.float64) if v.is_floating_point() else v) for k, v in captured["mod"].items()}
+    tfc.rng = tfc.ScriptedRNG([])
+    for k, v in model.model(mod64, False).items():
+        out["logits/" + k] = v.detach().numpy()
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("%-16s demo forward -> %s (%.0f kB)" % (name, os.path.relpath(path, ROOT), os.path.getsize(path) / 1e3))
+
+
+if __name__ == "__main__":
+    for case, spec in CASES.items():
+        run_case(case, spec)
+    run_demo_case()

@@ -1,0 +1,247 @@
+"""Golden vectors produced by the REFERENCE'S OWN PYTHON (tests/golden/make_golden.py runs /root/reference's
+MFP.call / preprocess_for_train / Model.call / LossLayer.call on the torch-backed TensorFlow stand-in,
+oracle/tf_standin/) against (a) the CPU oracle -- CPU tests, this is what pins the oracle -- and (b) the CUDA
+engine through the C ABI -- GPU tests.  The .npz fixtures are committed; nothing here reads /root/reference.
+
+Masking outputs (task selection, <MASK>/<UNUSED>/random tokens, per-field masks) are compared bit-exactly; floating
+point within the tolerances of tests/helpers.py."""
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from flex_dm_b200.spec import make_input_columns
+from oracle import mfp_oracle as O
+from tests import helpers as H
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+WEIGHT_SEED, RATE, L2, LR = 11, 0.1, 1e-2, 1e-4  # as in make_golden.py
+CASES = {  # name: (dataset, masking_method, num_blocks, seed, step)
+    "crello_random": ("crello", "random", 2, 7, 0),
+    "crello_multi": ("crello", "elem_pos_attr_img_txt", 2, 3, 2),
+    "rico_pos": ("rico", "elem_pos_attr", 2, 5, 1),
+}
+
+
+def projection_vector(name, n):  # same as make_golden.py
+    h = int.from_bytes(name.encode()[-8:].rjust(8, b"\0"), "little") ^ (len(name) * 0x9E3779B97F4A7C15 & (2**63 - 1))
+    rng = np.random.Generator(np.random.PCG64(h))
+    return rng.integers(0, 2, size=n).astype(np.float64) * 2.0 - 1.0
+
+
+def load(case):
+    g = np.load(os.path.join(GOLDEN, case + ".npz"))
+    dataset, method, L, seed, step = CASES[case]
+    batch = OrderedDict((k[3:], g[k]) for k in g.files if k.startswith("in/"))
+    cols = make_input_columns(dataset, max_length=50)
+    return g, cols, batch, method, L, seed, step
+
+
+def test_golden_files_cover_every_task_and_edge_case():
+    """The fixtures exercise what the reference's masking/loss code branches on: every task id of both datasets,
+    a single-element document, full-length documents, the rico sort branch."""
+    seen = set()
+    for case in CASES:
+        g = np.load(os.path.join(GOLDEN, case + ".npz"))
+        seen |= {(CASES[case][0], int(t)) for t in g["tasks"]}
+        assert int(g["in/length"].min()) == 0 and int(g["in/length"].max()) == g["in/left"].shape[1] - 1
+    assert {t for d, t in seen if d == "crello"} == {0, 1, 3, 4, 5, 6}
+    assert {t for d, t in seen if d == "rico"} >= {1, 3, 4}
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_oracle_matches_reference_python(case):
+    g, cols, batch, method, L, seed, step = load(case)
+    o = O.OracleMFP(cols, num_blocks=L, masking_method=method, dropout=RATE, l2=L2, learning_rate=LR, clipnorm=1.0)
+    o.params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float64, bias_scale=0.05)
+    draws = O.PhiloxDraws(seed, step)
+    tasks = torch.as_tensor(g["tasks"])
+    assert set(g["tasks"].tolist()) <= set(o.allowed_tasks)
+    inputs = o.to_torch(batch)
+    targets, mod, masks = O.preprocess_for_train(inputs, o.input_columns, tasks, draws)
+    # ---- masking path: bit-exact against the reference's preprocess_for_train (mfp.py:95-138)
+    for key in o.input_columns:
+        assert np.array_equal(mod[key].numpy(), g["mod/" + key]), key
+        assert np.array_equal(masks[key].numpy(), g["mask/" + key]), key
+    assert np.array_equal(mod["task"].numpy(), g["mod/task"])
+    B, S = batch["left"].shape[:2]
+    r = o.step_from(targets, mod, masks, tasks, o.dropout_masks(draws, B, S))
+    # ---- Model.call (model.py:26-30): raw logits
+    for key, v in r["outputs"].items():
+        assert np.abs(v.detach().numpy() - g["logits/" + key]).max() <= 1e-10, key
+    # ---- LossLayer.call (metrics.py:173-299) + regularisers
+    assert r["loss"] == pytest.approx(float(g["total_loss"]), rel=1e-12)
+    assert r["data_loss"] == pytest.approx(float(g["data_loss"]), rel=1e-12)
+    for key, v in r["losses"].items():
+        assert v == pytest.approx(float(g["loss/" + key]), rel=1e-11, abs=1e-12), key
+    for key, v in r["scores"].items():
+        k, what = key.rsplit("_score_", 1)
+        assert v == pytest.approx(float(g["score_%s/%s" % (what, k)]), rel=1e-11, abs=1e-12), key
+    for key, v in r["metrics"].items():
+        if not key.endswith("_loss"):
+            assert v == pytest.approx(float(g["metric/" + key]), rel=1e-11, abs=1e-12), key
+    # ---- gradients of the total loss and the variables after Adam(1e-4, clipnorm=1) (train.py:71-77)
+    for name, gr in r["grads"].items():
+        gr = gr.numpy().reshape(-1)
+        scale = max(float(g["gradnorm/" + name]), 1e-12)
+        assert abs(np.linalg.norm(gr) - float(g["gradnorm/" + name])) <= 1e-9 * scale, name
+        assert abs(gr @ projection_vector(name, gr.size) - float(g["gradproj/" + name])) <= 1e-9 * scale * np.sqrt(gr.size), name
+        assert np.abs(gr[:8] - g["gradhead/" + name]).max() <= 1e-9 * scale, name
+        w = o.params[name].numpy().reshape(-1)
+        assert np.abs(w[:8] - g["newhead/" + name]).max() <= 1e-12, name
+        assert abs(w @ projection_vector(name, w.size) - float(g["newproj/" + name])) <= 1e-10 * np.sqrt(w.size), name
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_oracle_merge_matches_reference_python(case):
+    """MFP.call's return value (mfp.py:46-69,342-347) from the float32 run of the reference."""
+    g, cols, batch, method, L, seed, step = load(case)
+    o = O.OracleMFP(cols, num_blocks=L, masking_method=method, dropout=RATE, l2=L2, dtype=torch.float32)
+    o.params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float32, bias_scale=0.05)
+    draws = O.PhiloxDraws(seed, step)
+    tasks = torch.as_tensor(g["tasks"])
+    inputs = o.to_torch(batch)
+    targets, mod, masks = O.preprocess_for_train(inputs, o.input_columns, tasks, draws)
+    B, S = batch["left"].shape[:2]
+    outputs = O.model_forward(o.params, mod, o.input_columns, L, o.dropout_masks(draws, B, S), RATE)
+    merged = O.merge_inputs_and_prediction(inputs, o.input_columns, masks, outputs)
+    keys = [k[7:] for k in g.files if k.startswith("merged/")]
+    assert set(keys) == set(o.input_columns)
+    for key in keys:
+        ref = g["merged/" + key]
+        got = merged[key].detach().numpy()
+        assert got.shape == ref.shape, key
+        if o.input_columns[key]["is_sequence"]:
+            assert np.abs(got - ref).max() <= 2e-4, key
+        else:
+            assert np.array_equal(got, ref), key
+
+
+# ================================================================================================= GPU (C ABI)
+@pytest.mark.gpu
+@pytest.mark.parametrize("impl", [1, 0], ids=["fp32-simt", "tf32-tcgen05"])
+@pytest.mark.parametrize("case", list(CASES))
+def test_engine_matches_reference_python(case, impl):
+    from flex_dm_b200.mfp import MFP
+
+    g, cols, batch, method, L, seed, step = load(case)
+    m = MFP(cols, num_blocks=L, masking_method=method, latent_dim=256, dropout=RATE, l2=L2, seed=0)
+    params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float64, bias_scale=0.05)
+    m.set_weights({k: v.numpy().astype(np.float32) for k, v in params.items()})
+    eng = m.engine
+    eng.set_gemm_impl(impl)
+    logit_atol, loss_rtol, grad_tol = (H.F32_LOGIT_ATOL, H.F32_LOSS_RTOL, H.F32_GRAD_REL_L2) if impl == 1 else (H.LOGIT_ATOL, H.LOSS_RTOL, H.GRAD_REL_L2)
+    B, S = batch["left"].shape[:2]
+    staged = m.stage(batch)
+    _, _, length, dcols = m._bind(staged)
+    tasks = torch.as_tensor(g["tasks"]).cuda()
+    eng.mask_corrupt(length, dcols, tasks, seed, step)
+    torch.cuda.synchronize()
+    # ---- masking: bit-exact against the reference's preprocess_for_train
+    for f, key in enumerate(m.keys):
+        assert np.array_equal(eng.masks[f].cpu().numpy().astype(bool), g["mask/" + key]), key
+        got = eng.modified[f].cpu().numpy()
+        if cols[key]["type"] == "categorical":
+            assert np.array_equal(got, g["mod/" + key]), key
+        else:
+            assert np.array_equal(got, g["mod/" + key].astype(np.float32)), key
+    # ---- forward (training, Philox dropout) / loss / backward
+    logits = torch.empty((B * S, eng.logit_width), device="cuda")
+    eng.forward(length, None, True, seed, step, logits_out=logits)
+    row = torch.zeros(eng.metrics_width, device="cuda")
+    eng.loss(length, dcols, eng.masks, row, 1.0 / B, True, sort_tasks=tasks if m.sort_pos else None)
+    eng.backward(length, None, True, seed, step)
+    torch.cuda.synchronize()
+    got = m.split_logits(logits, B, S)
+    for key in m.keys:
+        assert np.abs(got[key].cpu().numpy() - g["logits/" + key]).max() <= logit_atol, key
+    r = row.cpu().numpy()
+    F = len(m.keys)
+    assert r[3 * F] == pytest.approx(float(g["data_loss"]), rel=loss_rtol)
+    for f, key in enumerate(m.keys):
+        assert r[3 * f] == pytest.approx(float(g["loss/" + key]), rel=loss_rtol, abs=1e-5), key
+        den = float(g["score_den/" + key])
+        assert r[3 * f + 2] == pytest.approx(den, abs=1e-3), key
+        assert abs(r[3 * f + 1] - float(g["score_num/" + key])) <= max(1.0, 0.005 * den), key
+    # ---- gradients (the engine adds the L2 term inside the optimiser pass: d(l2 sum w^2)/dw = 2 l2 w)
+    specs = O.variable_specs(cols, L, 256)
+    got_grads = eng.get_weights(eng.grads)
+    w0 = eng.get_weights()
+    for name in specs:
+        gg = got_grads[name].astype(np.float64).reshape(-1)
+        if specs[name][2]:
+            gg = gg + 2.0 * L2 * w0[name].astype(np.float64).reshape(-1)
+        scale = max(float(g["gradnorm/" + name]), 1e-9)
+        assert abs(np.linalg.norm(gg) - float(g["gradnorm/" + name])) <= grad_tol * scale, name
+        assert abs(gg @ projection_vector(name, gg.size) - float(g["gradproj/" + name])) <= grad_tol * scale * 4, name
+        assert np.abs(gg[:8] - g["gradhead/" + name]).max() <= grad_tol * scale, name
+    # ---- L2 + per-variable clipnorm + Adam, one step
+    l2_out = torch.zeros(1, device="cuda")
+    eng.optimizer_step(1, LR, 1.0, l2_out)
+    torch.cuda.synchronize()
+    assert float(l2_out.cpu()) == pytest.approx(float(g["total_loss"]) - float(g["data_loss"]), rel=1e-5)
+    w1 = eng.get_weights()
+    for name in specs:
+        w = w1[name].astype(np.float64).reshape(-1)
+        # one Adam step moves every entry by about lr * sign(g): compare the moved weights, and the movement itself
+        assert np.abs(w[:8] - g["newhead/" + name]).max() <= 5e-6, name
+        moved = (w - w0[name].astype(np.float64).reshape(-1))[:8]
+        ref_moved = g["newhead/" + name] - params[name].numpy().reshape(-1)[:8]
+        big = np.abs(g["gradhead/" + name]) > 10 * grad_tol * max(float(g["gradnorm/" + name]), 1e-9)
+        assert np.all(np.sign(moved[big]) == np.sign(ref_moved[big])), name
+
+
+# ================================================================================================= demo / eval entry
+def _load_demo():
+    g = np.load(os.path.join(GOLDEN, "crello_demo.npz"))
+    cols = make_input_columns("crello", max_length=50)
+    batch = OrderedDict((k[3:], g[k]) for k in g.files if k.startswith("in/"))
+    masks = OrderedDict((k[5:], g[k]) for k in g.files if k.startswith("mask/"))
+    return g, cols, batch, masks
+
+
+def test_oracle_demo_call_matches_reference_python():
+    """model(example, training=False, demo_args={"masks": ...}) (eval.py:103, notebooks): preprocess_for_test,
+    Model.call without dropout, merge_inputs_and_prediction."""
+    g, cols, batch, masks = _load_demo()
+    icols = OrderedDict((k, v) for k, v in cols.items() if not v.get("demo_only", False))
+    inputs = {k: torch.as_tensor(v) for k, v in batch.items()}
+    tmasks = {k: torch.as_tensor(v) for k, v in masks.items()}
+    mod = O.preprocess_for_test(inputs, icols, tmasks)
+    for key in icols:
+        assert np.array_equal(mod[key].numpy(), g["mod/" + key]), key
+    params = O.init_params(cols, 2, 256, WEIGHT_SEED, torch.float64, bias_scale=0.05)
+    mod64 = {k: (v.double() if v.is_floating_point() else v) for k, v in mod.items()}
+    outputs = O.model_forward(params, mod64, icols, 2)
+    for key, v in outputs.items():
+        assert np.abs(v.numpy() - g["logits/" + key]).max() <= 1e-10, key
+    merged = O.merge_inputs_and_prediction(inputs, icols, tmasks, outputs)
+    for key in icols:
+        ref = g["merged/" + key]
+        assert merged[key].shape == ref.shape, key
+        assert np.abs(merged[key].numpy() - ref).max() <= 2e-4, key
+
+
+@pytest.mark.gpu
+def test_engine_demo_call_matches_reference_python():
+    from flex_dm_b200.mfp import MFP
+
+    g, cols, batch, masks = _load_demo()
+    m = MFP(cols, num_blocks=2, masking_method="random", latent_dim=256, dropout=RATE, l2=L2, seed=0)
+    params = O.init_params(cols, 2, 256, WEIGHT_SEED, torch.float64, bias_scale=0.05)
+    m.set_weights({k: v.numpy().astype(np.float32) for k, v in params.items()})
+    out = m(batch, training=False, demo_args={"masks": {k: torch.as_tensor(v) for k, v in masks.items()}})
+    torch.cuda.synchronize()
+    for f, key in enumerate(m.keys):
+        got = m.engine.modified[f].cpu().numpy()
+        assert np.array_equal(got, g["mod/" + key].astype(got.dtype)), key
+    for key, column in m.input_columns.items():
+        ref = g["merged/" + key]
+        got = out[key].cpu().numpy()
+        assert got.shape == ref.shape, key
+        if column["is_sequence"]:
+            assert np.abs(got - ref).max() <= H.LOGIT_ATOL, key
+        else:
+            assert np.array_equal(got, ref), key
