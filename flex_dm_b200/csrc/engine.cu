@@ -521,10 +521,14 @@ int mfp_backward(mfp_engine* h, const mfp_batch* modified, int32_t training, uin
     const float* lse = wsp<float>(h, h->off.lse) + (size_t)i * h->B * kH * h->S;
 
     // FFN branch: x_out = xmid + drop(relu(ln2.W1 + b1).W2 + b2)
+    // dy = dx under the FFN branch's dropout mask: written by the LayerNorm backward of the block above (below: by the
+    // separate kernel for the topmost block, whose dx comes out of the heads' dgrad GEMM)
     const float* dy = dx;
     if (drop) {
-      MFP_TRY(launch_dropout_bwd(dx, T, h->cfg.dropout, seed, step, kSiteDropout + 2 * i + 1, dyb, st));
-      h->launches++;
+      if (i == L - 1) {
+        MFP_TRY(launch_dropout_bwd(dx, T, h->cfg.dropout, seed, step, kSiteDropout + 2 * i + 1, dyb, st));
+        h->launches++;
+      }
       dy = dyb;
     }
     MFP_TRY(gemm(h, hid, 1, kF, dy, 1, D, kF, D, T, make_epilogue(G + b.w2, D), wgrad_splits(kF, D, T), st, G + b.b2));
@@ -533,14 +537,10 @@ int mfp_backward(mfp_engine* h, const mfp_batch* modified, int32_t training, uin
     MFP_TRY(gemm(h, dy, 0, D, P + b.w2, 0, D, T, kF, D, eh, 1, st));
     MFP_TRY(gemm(h, ln2, 1, D, dhid, 1, kF, D, kF, T, make_epilogue(G + b.w1, kF), wgrad_splits(D, kF, T), st, G + b.b1));
     MFP_TRY(gemm(h, dhid, 0, kF, P + b.w1, 0, kF, T, D, kF, make_epilogue(dtmp, D), 1, st));
-    MFP_TRY(launch_layernorm_bwd(xmid, dtmp, P + b.g2, stats + 2 * T, stats + 3 * T, dx, T, dx, G + b.g2, G + b.be2, st));
+    MFP_TRY(launch_layernorm_bwd(xmid, dtmp, P + b.g2, stats + 2 * T, stats + 3 * T, dx, T, dx, G + b.g2, G + b.be2, st, nullptr, 0, nullptr,
+                                 drop ? dyb : nullptr, h->cfg.dropout, seed, step, kSiteDropout + 2 * i));
     // attention branch: xmid = x_in + drop(attn.Wo + bo)
-    dy = dx;
-    if (drop) {
-      MFP_TRY(launch_dropout_bwd(dx, T, h->cfg.dropout, seed, step, kSiteDropout + 2 * i, dyb, st));
-      h->launches++;
-      dy = dyb;
-    }
+    dy = drop ? dyb : dx;
     MFP_TRY(gemm(h, attn, 1, D, dy, 1, D, D, D, T, make_epilogue(G + b.wo, D), wgrad_splits(D, D, T), st, G + b.bo));
     MFP_TRY(gemm(h, dy, 0, D, P + b.wo, 0, D, T, D, D, make_epilogue(dattn, D), 1, st));
     {
@@ -550,11 +550,12 @@ int mfp_backward(mfp_engine* h, const mfp_batch* modified, int32_t training, uin
     }
     MFP_TRY(gemm(h, ln1, 1, D, dqkv, 1, 3 * D, D, 3 * D, T, make_epilogue(G + b.wqkv, 3 * D), wgrad_splits(D, 3 * D, T), st, G + b.bqkv));
     MFP_TRY(gemm(h, dqkv, 0, 3 * D, P + b.wqkv, 0, 3 * D, T, D, 3 * D, make_epilogue(dtmp, D), 1, st));
-    if (i == 0 && sc.n_num > 0)
+    if (i == 0)
       MFP_TRY(launch_layernorm_bwd(xi, dtmp, P + b.g1, stats, stats + T, dx, T, dx, G + b.g1, G + b.be1, st, wsp<unsigned char>(h, h->off.flags), sc.n_num,
-                                   wsp<float>(h, h->off.dh0m)));
+                                   sc.n_num > 0 ? wsp<float>(h, h->off.dh0m) : nullptr));
     else
-      MFP_TRY(launch_layernorm_bwd(xi, dtmp, P + b.g1, stats, stats + T, dx, T, dx, G + b.g1, G + b.be1, st));
+      MFP_TRY(launch_layernorm_bwd(xi, dtmp, P + b.g1, stats, stats + T, dx, T, dx, G + b.g1, G + b.be1, st, nullptr, 0, nullptr, drop ? dyb : nullptr,
+                                   h->cfg.dropout, seed, step, kSiteDropout + 2 * (i - 1) + 1));
     h->launches += 3;
   }
   // ---- encoder: table / special / bias rows by a one-hot wgrad GEMM; Dense kernels by X^T . (dh0 with special-token rows zeroed) (encoder.cu)

@@ -206,30 +206,34 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp < kEpiWarp0) {
-    // ===== column sums of the MN-major B tiles (bias gradient), m-tile 0 only =====
+    // ===== column sums of the MN-major B tiles (bias gradient) =====
+    // Every CTA of an n-tile sees the same B tiles; the 32 K-rows of each are shared out over the m-tiles (tiles_m = 2 or 4
+    // for the Dense layers: 16 or 8 rows per CTA; otherwise m-tile 0 takes them all), so that no CTA's ring is held up by
+    // this role.  Thread t owns 4 consecutive columns: chunk t>>3 (32 columns, 4 KB apart), 32-byte atom (t>>1)&3, half t&1;
+    // a quarter-warp reads one contiguous 128-byte row per LDS.128 (conflict-free under the 32-byte-atom swizzle).
     if (do_colsum) {
       const int tid = threadIdx.x - 64;  // 0..63
+      const int chunk = tid >> 3, atom = (tid >> 1) & 3, half = tid & 1;
+      const bool share = (32 % tl.tiles_m) == 0;
+      const int rows_per = share ? 32 / tl.tiles_m : 32;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int split = tile / tiles_mn, r = tile - split * tiles_mn;
-        const bool active = (r / tl.tiles_n) == 0;
+        const int mt = r / tl.tiles_n;
+        const bool active = (share || mt == 0) && chunk < BN / 32;
+        const int k_first = share ? mt * rows_per : 0;
         const int n0 = (r % tl.tiles_n) * BN;
         const int kb0 = split * tl.kb_per_split, kb1 = min(num_kb, kb0 + tl.kb_per_split);
-        float acc[BN / 64];
-#pragma unroll
-        for (int i = 0; i < BN / 64; ++i) acc[i] = 0.f;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           if (active) {
-            const uint8_t* sb = base_ptr + stage * L::kStageBytes + L::kABytes;
-#pragma unroll
-            for (int i = 0; i < BN / 64; ++i) {
-              const int col = tid + 64 * i;
-              const uint8_t* cb = sb + (col >> 5) * (kBK * 128) + (col & 7) * 4;
-              const int u = (col & 31) >> 3;
+            const uint8_t* cb = base_ptr + stage * L::kStageBytes + L::kABytes + chunk * (kBK * 128) + half * 16;
 #pragma unroll 8
-              for (int k = 0; k < kBK; ++k) acc[i] += *reinterpret_cast<const float*>(cb + k * 128 + ((u ^ (k & 3)) << 5));
+            for (int k = k_first; k < k_first + rows_per; ++k) {
+              const float4 v = *reinterpret_cast<const float4*>(cb + k * 128 + ((atom ^ (k & 3)) << 5));
+              acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
             }
           }
           __syncwarp();
@@ -237,10 +241,10 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         if (active) {
-#pragma unroll
-          for (int i = 0; i < BN / 64; ++i) {
-            const int col = n0 + tid + 64 * i;
-            if (col < N) atomicAdd(colsum + col, acc[i]);
+          const int col = n0 + chunk * 32 + atom * 8 + half * 4;
+          if (col < N) {  // N is a multiple of 4
+            atomicAdd(colsum + col, acc.x); atomicAdd(colsum + col + 1, acc.y);
+            atomicAdd(colsum + col + 2, acc.z); atomicAdd(colsum + col + 3, acc.w);
           }
         }
       }
@@ -270,23 +274,20 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(tfull_bar(as), aphase);
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-#pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
+      // One 32-column chunk: fused ops on the accumulator registers -> swizzled staging -> TMA store / reduce-add.
+      auto process = [&](const int c, uint32_t (&rr)[32]) {
         const int col0 = n0 + c * 32;
         if (use_aux && c + 1 < nchunks && lane == 0) {
           const int b = (c + 1) & 1;
           mbar_expect_tx(aux_bar(q, b), kChunkBytes);
           tma_load_2d(epi + (2 + b) * kChunkBytes, &tmAux, col0 + 32, row0, aux_bar(q, b));
         }
-        // bias of this chunk's 32 columns: issued before the TMEM load so its latency hides behind it
         float4 bv[8];
         if constexpr (EPI & kEpiBias) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             bv[j] = (lead_split && col0 + 4 * j < N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        uint32_t rr[32];
-        tmem_ld32(tacc + (uint32_t)(c * 32), rr);
         if (use_aux) {
           if (c & 1) { mbar_wait(aux_bar(q, 1), auxphase1); auxphase1 ^= 1u; }
           else { mbar_wait(aux_bar(q, 0), auxphase0); auxphase0 ^= 1u; }
@@ -327,10 +328,30 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tma_commit_group();
         }
         ob ^= 1;
+      };
+      // Software pipeline over the chunks: the TMEM load of chunk c+1 is in flight while chunk c is processed (the
+      // tcgen05.ld -> first-use latency was the top stall of the serial loop).  The accumulator is handed back to the
+      // MMA warp as soon as its last chunk sits in registers.
+      auto release_acc = [&]() {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+      };
+      uint32_t rr0[32], rr1[32];
+      tmem_ld32_issue(tacc, rr0);
+#pragma unroll 1
+      for (int c = 0; c < nchunks; c += 2) {
+        tmem_ld32_wait(rr0);
+        if (c + 1 < nchunks) tmem_ld32_issue(tacc + (uint32_t)((c + 1) * 32), rr1);
+        else release_acc();
+        process(c, rr0);
+        if (c + 1 < nchunks) {
+          tmem_ld32_wait(rr1);
+          if (c + 2 < nchunks) tmem_ld32_issue(tacc + (uint32_t)((c + 2) * 32), rr0);
+          else release_acc();
+          process(c + 1, rr1);
+        }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }

@@ -30,7 +30,8 @@ int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, 
 // rowflags / n_masked / dx_masked (optional): also write n_masked copies of dx with the rows whose flag != 0 zeroed (encoder Dense wgrads)
 int launch_layernorm_bwd(const float* x, const float* dy, const float* gamma, const float* mean, const float* rstd, const float* dres, int T,
                          float* dx, float* dgamma, float* dbeta, cudaStream_t st, const unsigned char* rowflags = nullptr, int n_masked = 0,
-                         float* dx_masked = nullptr);
+                         float* dx_masked = nullptr, float* dx_drop = nullptr, float drop_rate = 0.f, uint32_t drop_seed = 0, uint32_t drop_step = 0,
+                         uint32_t drop_site = 0);
 int launch_attention_fwd(const float* qkv, const int* length, int B, int S, float* out, float* lse, cudaStream_t st);
 int launch_attention_bwd(const float* qkv, const float* out, const float* lse, const float* dout, const int* length, int B, int S, float* dqkv,
                          cudaStream_t st);

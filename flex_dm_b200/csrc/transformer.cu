@@ -34,7 +34,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ dres, int T, float* __restrict__ dx,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            const unsigned char* __restrict__ rowflags, int n_masked, float* __restrict__ dx_masked) {
+                                                            const unsigned char* __restrict__ rowflags, int n_masked, float* __restrict__ dx_masked,
+                                                            float* __restrict__ dx_drop, float drop_rate, uint32_t drop_seed, uint32_t drop_step,
+                                                            uint32_t drop_site) {
   __shared__ float red[2][8][kD];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + lane), gb = __ldg(reinterpret_cast<const float4*>(gamma) + 32 + lane);
@@ -69,6 +71,16 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     float4* out = reinterpret_cast<float4*>(dx + (size_t)t * kD);
     out[lane] = make_float4(o[0], o[1], o[2], o[3]);
     out[32 + lane] = make_float4(o[4], o[5], o[6], o[7]);
+    // the gradient entering the next (earlier) sub-layer's branch is dx under that branch's dropout mask: written here so
+    // that no separate dropout-backward pass re-reads dx
+    if (dx_drop) {
+      float va[4] = {o[0], o[1], o[2], o[3]}, vb[4] = {o[4], o[5], o[6], o[7]};
+      dropout4(va, (uint32_t)t * kD + 4u * lane, drop_rate, drop_seed, drop_step, drop_site);
+      dropout4(vb, (uint32_t)t * kD + 128u + 4u * lane, drop_rate, drop_seed, drop_step, drop_site);
+      float4* po = reinterpret_cast<float4*>(dx_drop + (size_t)t * kD);
+      po[lane] = make_float4(va[0], va[1], va[2], va[3]);
+      po[32 + lane] = make_float4(vb[0], vb[1], vb[2], vb[3]);
+    }
     // encoder: copies of dx with the rows of special-token elements zeroed, one per numerical field (B operand of its Dense wgrad)
     for (int s = 0; s < n_masked; ++s) {
       const bool keep = rowflags[(size_t)s * T + t] == 0;
@@ -280,9 +292,11 @@ int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, 
 }
 
 int launch_layernorm_bwd(const float* x, const float* dy, const float* gamma, const float* mean, const float* rstd, const float* dres, int T,
-                         float* dx, float* dgamma, float* dbeta, cudaStream_t st, const unsigned char* rowflags, int n_masked, float* dx_masked) {
+                         float* dx, float* dgamma, float* dbeta, cudaStream_t st, const unsigned char* rowflags, int n_masked, float* dx_masked,
+                         float* dx_drop, float drop_rate, uint32_t drop_seed, uint32_t drop_step, uint32_t drop_site) {
   const int grid = min((T + 7) / 8, 148 * 4);
-  layernorm_bwd_kernel<<<grid, 256, 0, st>>>(x, dy, gamma, mean, rstd, dres, T, dx, dgamma, dbeta, rowflags, n_masked, dx_masked);
+  layernorm_bwd_kernel<<<grid, 256, 0, st>>>(x, dy, gamma, mean, rstd, dres, T, dx, dgamma, dbeta, rowflags, n_masked, dx_masked, dx_drop, drop_rate,
+                                             drop_seed, drop_step, drop_site);
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }

@@ -146,7 +146,11 @@ def test_engine_matches_reference_python(case, impl):
         if cols[key]["type"] == "categorical":
             assert np.array_equal(got, g["mod/" + key]), key
         else:
-            assert np.array_equal(got, g["mod/" + key].astype(np.float32)), key
+            # <MASK> (10.0) / <UNUSED> (0.0) rows exactly; random replacements are Box-Muller normals whose device
+            # logf/cosf differ from numpy's in the last bits
+            ref = g["mod/" + key].astype(np.float32)
+            assert np.array_equal(got == 10.0, ref == 10.0) and np.array_equal(got == 0.0, ref == 0.0), key
+            assert np.allclose(got, ref, atol=1e-6, rtol=0), key
     # ---- forward (training, Philox dropout) / loss / backward
     logits = torch.empty((B * S, eng.logit_width), device="cuda")
     eng.forward(length, None, True, seed, step, logits_out=logits)
@@ -174,6 +178,10 @@ def test_engine_matches_reference_python(case, impl):
         if specs[name][2]:
             gg = gg + 2.0 * L2 * w0[name].astype(np.float64).reshape(-1)
         scale = max(float(g["gradnorm/" + name]), 1e-9)
+        if name.endswith("dense_key/bias"):
+            # softmax is shift-invariant: the exact data gradient of the key bias is 0 (what is left in the golden value is
+            # the L2 term); the engine's is the rounding noise of the column sum of dK -- bound it by the kernel's gradient
+            scale = max(scale, float(g["gradnorm/" + name.replace("/bias", "/kernel")]))
         assert abs(np.linalg.norm(gg) - float(g["gradnorm/" + name])) <= grad_tol * scale, name
         assert abs(gg @ projection_vector(name, gg.size) - float(g["gradproj/" + name])) <= grad_tol * scale * 4, name
         assert np.abs(gg[:8] - g["gradhead/" + name]).max() <= grad_tol * scale, name
