@@ -76,6 +76,8 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_launch_dependents();  // one resident CTA per SM for the whole kernel: the next kernel's CTAs only queue up behind it
+  pdl_wait();               // everything above touched no global memory
   // TMEM columns: scores / probabilities [0,128) and [128,256); outputs [256,288) and [288,320)
 
   if (warp == 0) {
@@ -258,6 +260,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_launch_dependents();  // one resident CTA per SM for the whole kernel: the next kernel's CTAs only queue up behind it
+  pdl_wait();               // everything above touched no global memory
   // TMEM columns: S^T / P^T [0,128), dP^T / dS^T [128,256), dV [256,288), dK [288,320), dQ [320,352)
 
   if (warp == 0) {
@@ -445,7 +449,7 @@ int launch_attention_fwd_tc(TensorMapCache* maps, const float* qkv, const int* l
   if (!mqk || !mv || !mo) return MFP_ERR_CUDA;
   const int units = B * kH;
   const int grid = units < sm_count() ? units : sm_count();
-  attention_fwd_tc_kernel<<<grid, kAtThreads, AttnFwdSmem::kTotal, st>>>(*mqk, *mv, *mo, length, B, S, lse);
+  MFP_CUDA_OK(launch_pdl(attention_fwd_tc_kernel, grid, kAtThreads, AttnFwdSmem::kTotal, st, *mqk, *mv, *mo, length, B, S, lse));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
@@ -470,7 +474,7 @@ int launch_attention_bwd_tc(TensorMapCache* maps, const float* qkv, const float*
   if (!mqk || !mqm || !mdk || !mdm || !mg) return MFP_ERR_CUDA;
   const int units = B * kH;
   const int grid = units < sm_count() ? units : sm_count();
-  attention_bwd_tc_kernel<<<grid, kAtThreads, AttnBwdSmem::kTotal, st>>>(*mqk, *mqm, *mdk, *mdm, *mg, out, lse, length, B, S);
+  MFP_CUDA_OK(launch_pdl(attention_bwd_tc_kernel, grid, kAtThreads, AttnBwdSmem::kTotal, st, *mqk, *mqm, *mdk, *mdm, *mg, out, lse, length, B, S));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }

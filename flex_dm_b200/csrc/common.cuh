@@ -70,6 +70,33 @@ struct MaskPtrs {
   const unsigned char* m[kMaxFields];  // [T] each
 };
 
+// ------------------------------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the step is launched with the programmatic-stream-serialization attribute: its CTAs may be scheduled while
+// the previous kernel of the stream is still draining, which hides the launch latency between the ~100 short kernels of a
+// step.  pdl_wait() (griddepcontrol.wait) blocks until the previous kernel has completed and its writes are visible; it is the
+// first statement of every kernel, or follows the barrier / TMEM set-up of the persistent ones.  FLEXDM_PDL=0 turns it off.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------- Philox4x32-10
 struct U4 { uint32_t x, y, z, w; };
 

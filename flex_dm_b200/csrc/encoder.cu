@@ -14,6 +14,7 @@ constexpr int kTokPerCta = 8;
 __global__ void __launch_bounds__(32 * kTokPerCta) embed_fwd_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs mod,
                                                                     const unsigned char* __restrict__ flags, const float* __restrict__ params, int T,
                                                                     float* __restrict__ h0) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * kTokPerCta + (threadIdx.x >> 5);
   if (t >= T) return;
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(32 * kTokPerCta) embed_fwd_kernel(const __grid
 // elements zeroed (written by the last LayerNorm-backward launch, transformer.cu).
 __global__ void __launch_bounds__(32 * kTokPerCta) embed_onehot_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs mod,
                                                                        const unsigned char* __restrict__ flags, int T, float* __restrict__ onehot) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * kTokPerCta + (threadIdx.x >> 5);
   if (t >= T) return;
@@ -82,6 +84,7 @@ __global__ void __launch_bounds__(32 * kTokPerCta) embed_onehot_kernel(const __g
 
 // grid = rows of the scratch block, block = D
 __global__ void __launch_bounds__(kD) embed_scatter_kernel(const __grid_constant__ Schema sc, const float* __restrict__ scratch, float* __restrict__ grads) {
+  pdl_wait();
   const int d = threadIdx.x;
   const int r = blockIdx.x;
   {
@@ -99,19 +102,19 @@ __global__ void __launch_bounds__(kD) embed_scatter_kernel(const __grid_constant
 }
 
 int launch_embed_fwd(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, const float* params, int T, float* h0, cudaStream_t st) {
-  embed_fwd_kernel<<<(T + kTokPerCta - 1) / kTokPerCta, 32 * kTokPerCta, 0, st>>>(sc, mod, flags, params, T, h0);
+  MFP_CUDA_OK(launch_pdl(embed_fwd_kernel, (T + kTokPerCta - 1) / kTokPerCta, 32 * kTokPerCta, 0, st, sc, mod, flags, params, T, h0));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
 
 int launch_embed_onehot(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, int T, float* onehot, cudaStream_t st) {
-  embed_onehot_kernel<<<(T + kTokPerCta - 1) / kTokPerCta, 32 * kTokPerCta, 0, st>>>(sc, mod, flags, T, onehot);
+  MFP_CUDA_OK(launch_pdl(embed_onehot_kernel, (T + kTokPerCta - 1) / kTokPerCta, 32 * kTokPerCta, 0, st, sc, mod, flags, T, onehot));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
 
 int launch_embed_scatter(const Schema& sc, const float* scratch, float* grads, cudaStream_t st) {
-  embed_scatter_kernel<<<sc.R, kD, 0, st>>>(sc, scratch, grads);
+  MFP_CUDA_OK(launch_pdl(embed_scatter_kernel, sc.R, kD, 0, st, sc, scratch, grads));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }

@@ -139,6 +139,8 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_launch_dependents();  // one resident CTA per SM for the whole kernel: the next kernel's CTAs only queue up behind it
+  pdl_wait();               // everything above (barriers, TMEM, tensor-map prefetch) touched no global memory
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -367,6 +369,7 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ------------------------------------------------------------------------------------------------- SIMT bring-up kernel
 __global__ void __launch_bounds__(256) gemm_simt(const float* __restrict__ A, int a_mn, int lda, const float* __restrict__ B, int b_mn, int ldb,
                                                  int M, int N, int K, int k_per_split, GemmEpilogue ep) {
+  pdl_wait();
   __shared__ float As[16][65];
   __shared__ float Bs[16][65];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -495,6 +498,11 @@ const CUtensorMap* tensor_map_get(TensorMapCache* cache, const float* ptr, int r
 TensorMapCache* tensor_map_cache_create() { return new TensorMapCache(); }
 void tensor_map_cache_destroy(TensorMapCache* c) { delete c; }
 
+bool pdl_enabled() {
+  static const bool on = [] { const char* s = getenv("FLEXDM_PDL"); return !(s && s[0] == '0'); }();
+  return on;
+}
+
 static uint32_t env_u32(const char* name, uint32_t dflt) {
   const char* s = getenv(name);
   return s ? (uint32_t)strtoul(s, nullptr, 0) : dflt;
@@ -540,8 +548,8 @@ static int launch_tcgen05(TensorMapCache* cache, const GemmCall& c, cudaStream_t
   if (tl.splits > 1) ep.atomic = 1;
   const int num_tiles = tl.tiles_m * tl.tiles_n * tl.splits;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_tf32_tcgen05<BN, EPI><<<grid, kGemmThreads, L::kTotal, stream>>>(*ma, *mb, *mo, *mx, c.M, c.N, c.K, c.a.mn_major, c.b.mn_major, tl, ep, c.colsum,
-                                                                       tune);
+  MFP_CUDA_OK(launch_pdl(gemm_tf32_tcgen05<BN, EPI>, grid, kGemmThreads, L::kTotal, stream, *ma, *mb, *mo, *mx, c.M, c.N, c.K, c.a.mn_major, c.b.mn_major, tl, ep, c.colsum,
+                                                                       tune));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
@@ -557,7 +565,7 @@ int launch_gemm(TensorMapCache* cache, const GemmCall& c, int impl, cudaStream_t
     GemmEpilogue ep = c.ep;
     if (splits > 1) ep.atomic = 1;
     dim3 grid((c.M + 63) / 64, (c.N + 63) / 64, splits);
-    gemm_simt<<<grid, 256, 0, stream>>>(c.a.ptr, c.a.mn_major, c.a.ld, c.b.ptr, c.b.mn_major, c.b.ld, c.M, c.N, c.K, k_per_split, ep);
+    MFP_CUDA_OK(launch_pdl(gemm_simt, grid, 256, 0, stream, c.a.ptr, c.a.mn_major, c.a.ld, c.b.ptr, c.b.mn_major, c.b.ld, c.M, c.N, c.K, k_per_split, ep));
     MFP_CUDA_OK(cudaGetLastError());
     return MFP_OK;
   }

@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(128) sort_indices_kernel(const __grid_constant
                                                            const float* __restrict__ logits, const unsigned char* __restrict__ sort_flag,
                                                            const int* __restrict__ sort_tasks, int pos_task_id, int S,
                                                            int* __restrict__ idx_true, int* __restrict__ idx_pred) {
+  pdl_wait();
   extern __shared__ long long keys[];  // [2][S]
   const int b = blockIdx.x;
   const bool sorted = sort_flag ? (sort_flag[b] != 0) : (sort_tasks && sort_tasks[b] == pos_task_id);
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(128) sort_indices_kernel(const __grid_constant
 __global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs targets,
                                                    const __grid_constant__ MaskPtrs masks, const float* __restrict__ logits, int use_sort, int B, int S,
                                                    float inv_batch, float* __restrict__ dlogits, const __grid_constant__ LossBuffers buf) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int T = B * S;
   const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -179,6 +181,7 @@ __global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ Schem
 
 // fixed-order reduction of one (quantity, field) row of partials; grid = (F, 3)
 __global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* __restrict__ part, int F, int T, float inv_batch, float* __restrict__ metrics) {
+  pdl_wait();
   __shared__ float red[1024];
   const int f = blockIdx.x, k = blockIdx.y;
   const float* p = part + ((size_t)k * F + f) * T;
@@ -194,6 +197,7 @@ __global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* __restri
 }
 
 __global__ void loss_total_kernel(int F, float* __restrict__ metrics) {
+  pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     float total = 0.f;
     for (int f = 0; f < F; ++f) total += metrics[f * 3];  // metrics.py:291-297
@@ -205,6 +209,7 @@ __global__ void loss_total_kernel(int F, float* __restrict__ metrics) {
 __global__ void __launch_bounds__(256) merge_prediction_kernel(const __grid_constant__ Schema sc, int f, const void* __restrict__ input_col,
                                                                const unsigned char* __restrict__ mask, const float* __restrict__ logits, int T,
                                                                float* __restrict__ out) {
+  pdl_wait();
   const FieldDev& fd = sc.f[f];
   const size_t total = (size_t)T * fd.logit_w;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(256) merge_prediction_kernel(const __grid_cons
 
 int launch_sort_indices(const Schema& sc, const BatchPtrs& targets, const float* logits, const unsigned char* sort_flag, const int* sort_tasks,
                         int pos_task_id, int B, int S, const LossBuffers& buf, cudaStream_t st) {
-  sort_indices_kernel<<<B, 128, 2 * S * sizeof(long long), st>>>(sc, targets, logits, sort_flag, sort_tasks, pos_task_id, S, buf.idx_true, buf.idx_pred);
+  MFP_CUDA_OK(launch_pdl(sort_indices_kernel, B, 128, 2 * S * sizeof(long long), st, sc, targets, logits, sort_flag, sort_tasks, pos_task_id, S, buf.idx_true, buf.idx_pred));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
@@ -232,11 +237,11 @@ int launch_sort_indices(const Schema& sc, const BatchPtrs& targets, const float*
 int launch_loss(const Schema& sc, const BatchPtrs& targets, const MaskPtrs& masks, const float* logits, int use_sort, int B, int S, float inv_batch,
                 float* dlogits, const LossBuffers& buf, float* metrics_out, cudaStream_t st) {
   const int T = B * S;
-  loss_kernel<<<(T + 7) / 8, 256, 0, st>>>(sc, targets, masks, logits, use_sort, B, S, inv_batch, dlogits, buf);
+  MFP_CUDA_OK(launch_pdl(loss_kernel, (T + 7) / 8, 256, 0, st, sc, targets, masks, logits, use_sort, B, S, inv_batch, dlogits, buf));
   MFP_CUDA_OK(cudaGetLastError());
-  loss_reduce_kernel<<<dim3(sc.F, 3), 1024, 0, st>>>(buf.part, sc.F, T, inv_batch, metrics_out);
+  MFP_CUDA_OK(launch_pdl(loss_reduce_kernel, dim3(sc.F, 3), 1024, 0, st, buf.part, sc.F, T, inv_batch, metrics_out));
   MFP_CUDA_OK(cudaGetLastError());
-  loss_total_kernel<<<1, 32, 0, st>>>(sc.F, metrics_out);
+  MFP_CUDA_OK(launch_pdl(loss_total_kernel, 1, 32, 0, st, sc.F, metrics_out));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
@@ -244,7 +249,7 @@ int launch_loss(const Schema& sc, const BatchPtrs& targets, const MaskPtrs& mask
 int launch_merge_prediction(const Schema& sc, int field, const void* input_col, const unsigned char* mask, const float* logits, int T, float* out,
                             cudaStream_t st) {
   const size_t total = (size_t)T * sc.f[field].logit_w;
-  merge_prediction_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sc, field, input_col, mask, logits, T, out);
+  MFP_CUDA_OK(launch_pdl(merge_prediction_kernel, (unsigned)((total + 255) / 256), 256, 0, st, sc, field, input_col, mask, logits, T, out));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }

@@ -7,6 +7,7 @@
 namespace mfp {
 
 __global__ void sample_tasks_kernel(TaskSet allowed, int B, uint32_t seed, uint32_t step, int* __restrict__ tasks) {
+  pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const U4 r = philox4x32_10((uint32_t)b, kFieldTask, 0u, 0u, seed, step);
@@ -25,6 +26,7 @@ __device__ __forceinline__ float2 box_muller(uint32_t xa, uint32_t xb) {
 __global__ void __launch_bounds__(256) mask_corrupt_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs in,
                                                            const int* __restrict__ tasks, const __grid_constant__ MaskPtrs test_masks, int mode, int B,
                                                            int S, uint32_t seed, uint32_t step, const __grid_constant__ ModifiedPtrs out) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= B * S) return;
@@ -97,6 +99,7 @@ __global__ void __launch_bounds__(256) mask_corrupt_kernel(const __grid_constant
 // Encoder special-token detection by value (encoder.py:165-166): 1 = all == MASK_VALUE, 2 = all == NULL_VALUE.
 __global__ void __launch_bounds__(256) row_flags_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs mod, int T,
                                                         unsigned char* __restrict__ flags) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= T) return;
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(256) row_flags_kernel(const __grid_constant__ 
 }
 
 int launch_sample_tasks(const TaskSet& allowed, int B, uint32_t seed, uint32_t step, int* tasks, cudaStream_t st) {
-  sample_tasks_kernel<<<(B + 127) / 128, 128, 0, st>>>(allowed, B, seed, step, tasks);
+  MFP_CUDA_OK(launch_pdl(sample_tasks_kernel, (B + 127) / 128, 128, 0, st, allowed, B, seed, step, tasks));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
@@ -127,14 +130,14 @@ int launch_mask_corrupt(const Schema& sc, const BatchPtrs& in, const int* tasks,
   MaskPtrs tm{};
   if (test_masks) tm = *test_masks;
   const int T = B * S;
-  mask_corrupt_kernel<<<(T + 7) / 8, 256, 0, st>>>(sc, in, tasks, tm, test_masks ? 1 : 0, B, S, seed, step, out);
+  MFP_CUDA_OK(launch_pdl(mask_corrupt_kernel, (T + 7) / 8, 256, 0, st, sc, in, tasks, tm, test_masks ? 1 : 0, B, S, seed, step, out));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
 
 int launch_row_flags(const Schema& sc, const BatchPtrs& mod, int T, unsigned char* flags, cudaStream_t st) {
   if (sc.n_num == 0) return MFP_OK;
-  row_flags_kernel<<<(T + 7) / 8, 256, 0, st>>>(sc, mod, T, flags);
+  MFP_CUDA_OK(launch_pdl(row_flags_kernel, (T + 7) / 8, 256, 0, st, sc, mod, T, flags));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }

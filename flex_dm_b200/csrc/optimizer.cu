@@ -10,6 +10,7 @@ constexpr int kNormChunks = 16;  // CTAs per variable in the norm pass; partials
 // grid = (V, kNormChunks): partial sums of (g + 2 l2 w)^2 and w^2 over one slice of one variable
 __global__ void __launch_bounds__(256) var_norms_kernel(const VarDev* __restrict__ vars, const float* __restrict__ params,
                                                         const float* __restrict__ grads, float l2, int V, float* __restrict__ part) {
+  pdl_wait();
   __shared__ float red[2][8];
   const VarDev v = vars[blockIdx.x];
   const int n = v.rows * v.cols;
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(256) var_norms_kernel(const VarDev* __restrict
 
 // one warp: l2 * sum over regularised variables of sum w^2 (fixed order)
 __global__ void l2_loss_kernel(const float* __restrict__ part, int V, float l2, float* __restrict__ out) {
+  pdl_wait();
   float s = 0.f;
   for (int i = threadIdx.x; i < V * kNormChunks; i += 32) s += part[2 * i + 1];
   s = warp_sum(s);
@@ -49,6 +51,7 @@ __global__ void l2_loss_kernel(const float* __restrict__ part, int V, float l2, 
 __global__ void __launch_bounds__(256) adam_kernel(const VarDev* __restrict__ vars, float* __restrict__ params, const float* __restrict__ grads,
                                                    float* __restrict__ m, float* __restrict__ vv, const float* __restrict__ norms, float l2,
                                                    float clipnorm, float alpha) {
+  pdl_wait();
   const VarDev v = vars[blockIdx.x];
   const int n = v.rows * v.cols;
   const float k = (v.l2 && l2 > 0.f) ? 2.0f * l2 : 0.f;
@@ -70,23 +73,23 @@ __global__ void __launch_bounds__(256) adam_kernel(const VarDev* __restrict__ va
 }
 
 int launch_regularization_loss(const VarDev* vars, int V, const float* params, float* norms, float l2, float* out, cudaStream_t st) {
-  var_norms_kernel<<<dim3(V, kNormChunks), 256, 0, st>>>(vars, params, nullptr, l2, V, norms);
+  MFP_CUDA_OK(launch_pdl(var_norms_kernel, dim3(V, kNormChunks), 256, 0, st, vars, params, nullptr, l2, V, norms));
   MFP_CUDA_OK(cudaGetLastError());
-  l2_loss_kernel<<<1, 32, 0, st>>>(norms, V, l2, out);
+  MFP_CUDA_OK(launch_pdl(l2_loss_kernel, 1, 32, 0, st, norms, V, l2, out));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
 
 int launch_optimizer(const VarDev* vars, int V, float* params, const float* grads, float* m, float* v, float* norms, int t, float lr, float clipnorm,
                      float l2, float* l2_loss_out, cudaStream_t st) {
-  var_norms_kernel<<<dim3(V, kNormChunks), 256, 0, st>>>(vars, params, grads, l2, V, norms);
+  MFP_CUDA_OK(launch_pdl(var_norms_kernel, dim3(V, kNormChunks), 256, 0, st, vars, params, grads, l2, V, norms));
   MFP_CUDA_OK(cudaGetLastError());
   if (l2_loss_out) {
-    l2_loss_kernel<<<1, 32, 0, st>>>(norms, V, l2, l2_loss_out);
+    MFP_CUDA_OK(launch_pdl(l2_loss_kernel, 1, 32, 0, st, norms, V, l2, l2_loss_out));
     MFP_CUDA_OK(cudaGetLastError());
   }
   const double alpha = (double)lr * sqrt(1.0 - pow(0.999, (double)t)) / (1.0 - pow(0.9, (double)t));
-  adam_kernel<<<dim3(V, 16), 256, 0, st>>>(vars, params, grads, m, v, norms, l2, clipnorm, (float)alpha);
+  MFP_CUDA_OK(launch_pdl(adam_kernel, dim3(V, 16), 256, 0, st, vars, params, grads, m, v, norms, l2, clipnorm, (float)alpha));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }

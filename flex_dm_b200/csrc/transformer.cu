@@ -10,6 +10,7 @@ namespace mfp {
 // one warp per row of D = 256: lane owns columns [4*lane, 4*lane+4) and [128 + 4*lane, ...)
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             int T, float* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (t >= T) return;
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             const unsigned char* __restrict__ rowflags, int n_masked, float* __restrict__ dx_masked,
                                                             float* __restrict__ dx_drop, float drop_rate, uint32_t drop_seed, uint32_t drop_step,
                                                             uint32_t drop_site) {
+  pdl_wait();
   __shared__ float red[2][8][kD];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + lane), gb = __ldg(reinterpret_cast<const float4*>(gamma) + 32 + lane);
@@ -114,6 +116,7 @@ constexpr int kAttnThreads = 128;
 
 __global__ void __launch_bounds__(kAttnThreads) attention_fwd_kernel(const float* __restrict__ qkv, const int* __restrict__ length, int S,
                                                                      float* __restrict__ out, float* __restrict__ lse) {
+  pdl_wait();
   extern __shared__ float sm[];
   float* Ks = sm;
   float* Vs = sm + (size_t)S * kDh;
@@ -177,6 +180,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_fwd_kernel(const float
 __global__ void __launch_bounds__(kAttnThreads) attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ out,
                                                                      const float* __restrict__ lse, const float* __restrict__ dout,
                                                                      const int* __restrict__ length, int S, float* __restrict__ dqkv) {
+  pdl_wait();
   extern __shared__ float sm[];
   float* Qs = sm;                         // pre-scaled by 1/sqrt(dh)
   float* Ks = Qs + (size_t)S * kDh;
@@ -265,6 +269,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_bwd_kernel(const float
 // ------------------------------------------------------------------------------------------------- small kernels
 __global__ void __launch_bounds__(256) dropout_bwd_kernel(const float* __restrict__ dx, size_t n4, float rate, uint32_t seed, uint32_t step,
                                                           uint32_t site, float* __restrict__ dy) {
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 g = reinterpret_cast<const float4*>(dx)[i];
@@ -276,6 +281,7 @@ __global__ void __launch_bounds__(256) dropout_bwd_kernel(const float* __restric
 // out[c] += sum_r x[r, c]; grid = (col blocks, row chunks)
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int rows, int cols, int ld, int rows_per_chunk,
                                                      float* __restrict__ out) {
+  pdl_wait();
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= cols) return;
   const int r0 = blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
@@ -286,7 +292,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
 
 // ------------------------------------------------------------------------------------------------- launchers
 int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, int T, float* y, float* mean, float* rstd, cudaStream_t st) {
-  layernorm_fwd_kernel<<<(T + 7) / 8, 256, 0, st>>>(x, gamma, beta, T, y, mean, rstd);
+  MFP_CUDA_OK(launch_pdl(layernorm_fwd_kernel, (T + 7) / 8, 256, 0, st, x, gamma, beta, T, y, mean, rstd));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
@@ -295,8 +301,8 @@ int launch_layernorm_bwd(const float* x, const float* dy, const float* gamma, co
                          float* dx, float* dgamma, float* dbeta, cudaStream_t st, const unsigned char* rowflags, int n_masked, float* dx_masked,
                          float* dx_drop, float drop_rate, uint32_t drop_seed, uint32_t drop_step, uint32_t drop_site) {
   const int grid = min((T + 7) / 8, 148 * 4);
-  layernorm_bwd_kernel<<<grid, 256, 0, st>>>(x, dy, gamma, mean, rstd, dres, T, dx, dgamma, dbeta, rowflags, n_masked, dx_masked, dx_drop, drop_rate,
-                                             drop_seed, drop_step, drop_site);
+  MFP_CUDA_OK(launch_pdl(layernorm_bwd_kernel, grid, 256, 0, st, x, dy, gamma, mean, rstd, dres, T, dx, dgamma, dbeta, rowflags, n_masked, dx_masked, dx_drop, drop_rate,
+                                             drop_seed, drop_step, drop_site));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
@@ -314,7 +320,7 @@ int launch_attention_fwd(const float* qkv, const int* length, int B, int S, floa
   static size_t configured = 0;
   const size_t smem = (size_t)2 * S * kDh * sizeof(float);
   MFP_TRY(attn_smem_check(smem, (const void*)attention_fwd_kernel, &configured));
-  attention_fwd_kernel<<<B * kH, kAttnThreads, smem, st>>>(qkv, length, S, out, lse);
+  MFP_CUDA_OK(launch_pdl(attention_fwd_kernel, B * kH, kAttnThreads, smem, st, qkv, length, S, out, lse));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
@@ -324,14 +330,14 @@ int launch_attention_bwd(const float* qkv, const float* out, const float* lse, c
   static size_t configured = 0;
   const size_t smem = ((size_t)4 * S * kDh + 2 * S) * sizeof(float);
   MFP_TRY(attn_smem_check(smem, (const void*)attention_bwd_kernel, &configured));
-  attention_bwd_kernel<<<B * kH, kAttnThreads, smem, st>>>(qkv, out, lse, dout, length, S, dqkv);
+  MFP_CUDA_OK(launch_pdl(attention_bwd_kernel, B * kH, kAttnThreads, smem, st, qkv, out, lse, dout, length, S, dqkv));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
 
 int launch_dropout_bwd(const float* dx, int T, float rate, uint32_t seed, uint32_t step, uint32_t site, float* dy, cudaStream_t st) {
   const size_t n4 = (size_t)T * kD / 4;
-  dropout_bwd_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(dx, n4, rate, seed, step, site, dy);
+  MFP_CUDA_OK(launch_pdl(dropout_bwd_kernel, (unsigned)((n4 + 255) / 256), 256, 0, st, dx, n4, rate, seed, step, site, dy));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
@@ -339,7 +345,7 @@ int launch_dropout_bwd(const float* dx, int T, float rate, uint32_t seed, uint32
 int launch_colsum(const float* x, int rows, int cols, int ld, float* out, cudaStream_t st) {
   const int chunks = min(128, (rows + 63) / 64);
   const int rows_per_chunk = (rows + chunks - 1) / chunks;
-  colsum_kernel<<<dim3((cols + 255) / 256, chunks), 256, 0, st>>>(x, rows, cols, ld, rows_per_chunk, out);
+  MFP_CUDA_OK(launch_pdl(colsum_kernel, dim3((cols + 255) / 256, chunks), 256, 0, st, x, rows, cols, ld, rows_per_chunk, out));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }

@@ -193,12 +193,14 @@ def test_engine_matches_reference_python(case, impl):
     w1 = eng.get_weights()
     for name in specs:
         w = w1[name].astype(np.float64).reshape(-1)
-        # one Adam step moves every entry by about lr * sign(g): compare the moved weights, and the movement itself
-        assert np.abs(w[:8] - g["newhead/" + name]).max() <= 5e-6, name
-        moved = (w - w0[name].astype(np.float64).reshape(-1))[:8]
-        ref_moved = g["newhead/" + name] - params[name].numpy().reshape(-1)[:8]
-        big = np.abs(g["gradhead/" + name]) > 10 * grad_tol * max(float(g["gradnorm/" + name]), 1e-9)
-        assert np.all(np.sign(moved[big]) == np.sign(ref_moved[big])), name
+        # The first Adam step is lr * g / (|g| + 3.2e-6) on the clipped gradient: entries far above that scale move by
+        # exactly +-lr (compared strictly); entries whose exact gradient is ~0 move by up to lr in the direction of the
+        # rounding noise, in the engine and in a float32 TensorFlow run alike (bounded by 2 lr).
+        gref = g["gradhead/" + name] * min(1.0, 1.0 / max(float(g["gradnorm/" + name]), 1e-12))
+        strict = np.abs(gref) > 1e-3
+        diff = np.abs(w[:8] - g["newhead/" + name])
+        assert diff[strict].max(initial=0.0) <= 5e-6, name
+        assert diff.max() <= 2.0 * LR + 5e-6, name
 
 
 # ================================================================================================= demo / eval entry
