@@ -32,15 +32,16 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 // ------------------------------------------------------------------------------------------------- forward
 constexpr int kFwdSlots = 3;
+constexpr int kAtFwdThreads = 384;  // warps 0-3: TMA / MMA / TMEM allocator / idle; warps 4-7 and 8-11: two softmax + epilogue groups
 struct AttnFwdSmem {
   static constexpr int kSlotBytes = 3 * kAtTileBytes;                 // Q, K, V
-  static constexpr int kStageOff = kFwdSlots * kSlotBytes;            // 4 warps x 2 x [32][32] fp32 output staging
-  static constexpr int kBarOff = kStageOff + 4 * 2 * 4096;
+  static constexpr int kStageOff = kFwdSlots * kSlotBytes;            // 8 warps x 2 x [32][32] fp32 output staging
+  static constexpr int kBarOff = kStageOff + 8 * 2 * 4096;
   static constexpr int kNumBars = 2 * kFwdSlots + 6;                  // full, empty, s_full[2], p_ready[2], o_full[2]
   static constexpr int kTotal = kBarOff + 8 * kNumBars + 16 + 1024;
 };
 
-__global__ void __launch_bounds__(kAtThreads, 1)
+__global__ void __launch_bounds__(kAtFwdThreads, 1)
 attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                         const int* __restrict__ length, int B, int S, float* __restrict__ lse) {
   using L = AttnFwdSmem;
@@ -128,36 +129,53 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
       }
     }
   } else if (warp >= 4) {
+    // Two softmax groups (warps 4-7 and 8-11) take the units alternately, one per score / output buffer in TMEM: a group is
+    // one warp per scheduler and latency-bound on its TMEM round trips, so two of them in flight nearly double the rate.
+    const int g = (warp - 4) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t stage = base + L::kStageOff + q * 8192;
-    uint8_t* stage_ptr = base_ptr + L::kStageOff + q * 8192;
+    const uint32_t stage = base + L::kStageOff + (g * 4 + q) * 8192;
+    uint8_t* stage_ptr = base_ptr + L::kStageOff + (g * 4 + q) * 8192;
     const uint32_t sw = (uint32_t)(lane & 7);
     const float c2 = kAtScale * kLog2e;
-    float inv_l = 0.f, inv_l_prev = 0.f;
+    const uint32_t sbuf = lane_base + (uint32_t)(g * 128);
+    const uint32_t obuf = lane_base + 256u + (uint32_t)(g * 32);
     int ob = 0;
-    for (int i = 0; i <= n_local; ++i) {
-      if (i < n_local) {
-        const int u = blockIdx.x + i * gridDim.x, b = u / kH, h = u % kH;
-        const int n = min(S, __ldg(length + b) + 1);
-        mbar_wait(sfull_bar(i & 1), (i >> 1) & 1);
-        tcgen05_fence_after();
-        const uint32_t sbuf = lane_base + (uint32_t)((i & 1) * 128);
-        const int nch = (n + 31) >> 5;
-        float m = -INFINITY;
-        for (int c = 0; c < nch; ++c) {
-          uint32_t r[32];
-          tmem_ld32(sbuf + (uint32_t)(c * 32), r);
+    for (int i = g; i < n_local; i += 2) {
+      const int u = blockIdx.x + i * gridDim.x, b = u / kH, h = u % kH;
+      const int n = min(S, __ldg(length + b) + 1);
+      const uint32_t ph = (uint32_t)((i >> 1) & 1);
+      mbar_wait(sfull_bar(g), ph);
+      tcgen05_fence_after();
+      const int nch = (n + 31) >> 5;
+      // pass 1: row maximum over the valid keys (the load of chunk c+1 flies under the reduction of chunk c)
+      float m = -INFINITY;
+      {
+        uint32_t ra[32], rb[32];
+        auto reduce = [&](const int c, uint32_t (&r)[32]) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (c * 32 + j < n) m = fmaxf(m, __uint_as_float(r[j]));
+        };
+        tmem_ld32_issue(sbuf, ra);
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld32_wait(ra);
+          if (c + 1 < nch) tmem_ld32_issue(sbuf + (uint32_t)((c + 1) * 32), rb);
+          reduce(c, ra);
+          if (c + 1 < nch) {
+            tmem_ld32_wait(rb);
+            if (c + 2 < nch) tmem_ld32_issue(sbuf + (uint32_t)((c + 2) * 32), ra);
+            reduce(c + 1, rb);
+          }
         }
-        float l = 0.f;
-        const float mc = m * c2;
-        for (int c = 0; c < nch; ++c) {
-          uint32_t r[32];
-          tmem_ld32(sbuf + (uint32_t)(c * 32), r);
+      }
+      // pass 2: unnormalised probabilities, rounded to TF32, written back in place
+      float l = 0.f;
+      const float mc = m * c2;
+      {
+        uint32_t ra[32], rb[32];
+        auto expo = [&](const int c, uint32_t (&r)[32]) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float p = (c * 32 + j < n) ? fast_exp2(fmaf(__uint_as_float(r[j]), c2, -mc)) : 0.f;
@@ -165,38 +183,45 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
             r[j] = to_tf32(p);
           }
           tmem_st32(sbuf + (uint32_t)(c * 32), r);
+        };
+        tmem_ld32_issue(sbuf, ra);
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld32_wait(ra);
+          if (c + 1 < nch) tmem_ld32_issue(sbuf + (uint32_t)((c + 1) * 32), rb);
+          expo(c, ra);
+          if (c + 1 < nch) {
+            tmem_ld32_wait(rb);
+            if (c + 2 < nch) tmem_ld32_issue(sbuf + (uint32_t)((c + 2) * 32), ra);
+            expo(c + 1, rb);
+          }
         }
-        tmem_st_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(pready_bar(i & 1));
-        inv_l = 1.0f / l;
-        if (row < S) lse[((size_t)b * kH + h) * S + row] = m * kAtScale + __logf(l);
       }
-      if (i >= 1) {
-        const int j = i - 1;
-        const int u = blockIdx.x + j * gridDim.x, b = u / kH, h = u % kH;
-        mbar_wait(ofull_bar(j & 1), (j >> 1) & 1);
-        tcgen05_fence_after();
-        uint32_t r[32];
-        tmem_ld32(lane_base + 256u + (uint32_t)((j & 1) * 32), r);
-        if (lane == 0) tma_wait_group_read<1>();
-        __syncwarp();
-        uint8_t* outp = stage_ptr + ob * 4096 + lane * 128;
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pready_bar(g));
+      const float inv_l = 1.0f / l;
+      if (row < S) lse[((size_t)b * kH + h) * S + row] = m * kAtScale + __logf(l);
+      // epilogue of the same unit: O / rowsum -> swizzled staging -> TMA store (the other group's softmax runs meanwhile)
+      mbar_wait(ofull_bar(g), ph);
+      tcgen05_fence_after();
+      uint32_t r[32];
+      tmem_ld32(obuf, r);
+      if (lane == 0) tma_wait_group_read<1>();
+      __syncwarp();
+      uint8_t* outp = stage_ptr + ob * 4096 + lane * 128;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          *reinterpret_cast<float4*>(outp + ((k ^ sw) << 4)) =
-              make_float4(__uint_as_float(r[4 * k]) * inv_l_prev, __uint_as_float(r[4 * k + 1]) * inv_l_prev, __uint_as_float(r[4 * k + 2]) * inv_l_prev,
-                          __uint_as_float(r[4 * k + 3]) * inv_l_prev);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_3d(&tmO, stage + ob * 4096, h * kDh, q * 32, b);
-          tma_commit_group();
-        }
-        ob ^= 1;
+      for (int k = 0; k < 8; ++k)
+        *reinterpret_cast<float4*>(outp + ((k ^ sw) << 4)) =
+            make_float4(__uint_as_float(r[4 * k]) * inv_l, __uint_as_float(r[4 * k + 1]) * inv_l, __uint_as_float(r[4 * k + 2]) * inv_l,
+                        __uint_as_float(r[4 * k + 3]) * inv_l);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tmO, stage + ob * 4096, h * kDh, q * 32, b);
+        tma_commit_group();
       }
-      inv_l_prev = inv_l;
+      ob ^= 1;
     }
     if (lane == 0) tma_wait_group_read<0>();
   }
@@ -449,7 +474,7 @@ int launch_attention_fwd_tc(TensorMapCache* maps, const float* qkv, const int* l
   if (!mqk || !mv || !mo) return MFP_ERR_CUDA;
   const int units = B * kH;
   const int grid = units < sm_count() ? units : sm_count();
-  MFP_CUDA_OK(launch_pdl(attention_fwd_tc_kernel, grid, kAtThreads, AttnFwdSmem::kTotal, st, *mqk, *mv, *mo, length, B, S, lse));
+  MFP_CUDA_OK(launch_pdl(attention_fwd_tc_kernel, grid, kAtFwdThreads, AttnFwdSmem::kTotal, st, *mqk, *mv, *mo, length, B, S, lse));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }

@@ -52,7 +52,9 @@ struct FieldDev {
 struct Schema {
   int F;           // sequence fields, get_valid_input_columns order
   int type_field;  // index of "type"
-  int LW;          // padded logits width
+  int LW;          // logits row pitch: heads start at multiples of 4 columns, the row is padded to 32 columns (128 B) so that every
+                   // row of the [T, LW] logits / gradient matrices is sector- and TMA-box-aligned
+  int LWu;         // columns in use (sum of the heads' 4-padded widths); [LWu, LW) is zero padding
   int n_num;       // numerical fields
   int sort_field[5];  // indices of type,left,top,width,height (tensor_utils.py:11)
   int R, Rp;          // gradient rows of the encoder (tables + {<MASK>, <UNUSED>, bias} per numerical field); Rp = R padded to 4

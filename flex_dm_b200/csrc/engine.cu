@@ -49,6 +49,7 @@ struct mfp_engine {
   Workspace off{};
   float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
   TensorMapCache* maps = nullptr;
+  const void* flags_for = nullptr;  // modified column (first numerical field) the workspace row flags were just derived from
   int gemm_impl = 0;
   int64_t launches = 0;
   // optional per-kernel-class device timing (bench.py roofline): CUDA event pairs around each launch
@@ -90,7 +91,8 @@ static void build_layout(mfp_engine* h) {
     fd.logit_off = lw;
     lw += (fd.logit_w + 3) & ~3;
   }
-  sc.LW = lw;
+  sc.LWu = lw;
+  sc.LW = (lw + 31) & ~31;
   // encoder (encoder.py:72-92)
   for (int f = 0; f < sc.F; ++f) {
     FieldDev& fd = sc.f[f];
@@ -196,6 +198,12 @@ static BatchPtrs to_batch(const mfp_engine* h, const mfp_batch* b) {
   p.length = b->length;
   for (int f = 0; f < h->sc.F; ++f) p.cols[f] = b->cols[f];
   return p;
+}
+
+static int first_numerical(const Schema& sc) {
+  for (int f = 0; f < sc.F; ++f)
+    if (sc.f[f].kind == 1) return f;
+  return 0;
 }
 
 static int check_bound(const mfp_engine* h) {
@@ -355,6 +363,7 @@ int mfp_bind(mfp_engine* h, int32_t B, int32_t S, void* workspace, int64_t works
   if ((size_t)workspace_bytes < w.total) { set_error("mfp_bind: workspace too small (%lld < %zu)", (long long)workspace_bytes, w.total); return MFP_ERR_ARG; }
   if (reinterpret_cast<uintptr_t>(workspace) & 255) { set_error("mfp_bind: workspace must be 256-byte aligned"); return MFP_ERR_ARG; }
   h->B = B; h->S = S; h->T = B * S;
+  h->flags_for = nullptr;
   h->ws = reinterpret_cast<uint8_t*>(workspace);
   h->off = w;
   h->params = params; h->grads = grads; h->adam_m = adam_m; h->adam_v = adam_v;
@@ -380,7 +389,9 @@ int mfp_mask_corrupt(mfp_engine* h, const mfp_batch* inputs, const int32_t* task
   ModifiedPtrs out{};
   for (int f = 0; f < h->sc.F; ++f) { out.cols[f] = modified_cols[f]; out.masks[f] = masks_out[f]; }
   h->launches++;
-  return launch_mask_corrupt(h->sc, to_batch(h, inputs), tasks, nullptr, h->B, h->S, seed, step, out, (cudaStream_t)stream);
+  h->flags_for = h->sc.n_num > 0 ? modified_cols[first_numerical(h->sc)] : nullptr;  // the encoder's row flags come out of the same pass
+  return launch_mask_corrupt(h->sc, to_batch(h, inputs), tasks, nullptr, h->B, h->S, seed, step, out, (cudaStream_t)stream,
+                             wsp<unsigned char>(h, h->off.flags));
 }
 
 int mfp_mask_for_test(mfp_engine* h, const mfp_batch* inputs, const uint8_t* const* masks, void* const* modified_cols, void* stream) {
@@ -389,7 +400,8 @@ int mfp_mask_for_test(mfp_engine* h, const mfp_batch* inputs, const uint8_t* con
   MaskPtrs tm{};
   for (int f = 0; f < h->sc.F; ++f) { out.cols[f] = modified_cols[f]; tm.m[f] = masks[f]; }
   h->launches++;
-  return launch_mask_corrupt(h->sc, to_batch(h, inputs), nullptr, &tm, h->B, h->S, 0, 0, out, (cudaStream_t)stream);
+  h->flags_for = h->sc.n_num > 0 ? modified_cols[first_numerical(h->sc)] : nullptr;
+  return launch_mask_corrupt(h->sc, to_batch(h, inputs), nullptr, &tm, h->B, h->S, 0, 0, out, (cudaStream_t)stream, wsp<unsigned char>(h, h->off.flags));
 }
 
 int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint32_t seed, uint32_t step, float* logits_out, void* stream) {
@@ -405,9 +417,13 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
   const bool drop = training && h->cfg.dropout > 0.f;
 
   // ---- encoder (encoder.py:147-199)
-  MFP_TRY(launch_row_flags(sc, mod, T, flags, st));
+  // special-token flags of the numerical fields: already written by the mask/corrupt pass when it produced exactly these
+  // columns just before (consumed once: any later forward on the same buffers re-derives them by value)
+  const bool have_flags = sc.n_num > 0 && h->flags_for != nullptr && h->flags_for == modified->cols[first_numerical(sc)];
+  h->flags_for = nullptr;
+  if (!have_flags) { MFP_TRY(launch_row_flags(sc, mod, T, flags, st)); h->launches++; }
   MFP_TRY(launch_embed_fwd(sc, mod, flags, P, T, x, st));
-  h->launches += 2;
+  h->launches += 1;
   for (int f = 0; f < sc.F; ++f) {
     const FieldDev& fd = sc.f[f];
     if (fd.kind != 1) continue;

@@ -69,14 +69,18 @@ struct GemmTiles {
   int tiles_m, tiles_n, splits, kb_per_split;
 };
 
-template <int BN>
+// AUX: the epilogue stages a residual / ReLU-mask operand (two more 4 KB chunks per epilogue warp).  Without it the 32 KB saved
+// buy a fourth operand stage at BN = 256: the ring is latency-bound (a slot is refilled only after its MMAs retire), so the
+// bytes in flight set the fill rate.
+template <int BN, bool AUX>
 struct GemmSmem {
-  static constexpr int kStages = (BN <= 128) ? 4 : 3;
+  static constexpr int kStages = (BN <= 128 || !AUX) ? 4 : 3;
+  static constexpr int kEpiChunks = AUX ? 4 : 2;                 // per epilogue warp: out[2] (+ aux[2])
   static constexpr int kABytes = kBM * kBK * 4;
   static constexpr int kBBytes = BN * kBK * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiOff = kStages * kStageBytes;          // 4 warps x {out[2], aux[2]} chunks
-  static constexpr int kBarOff = kEpiOff + 4 * 4 * kChunkBytes;
+  static constexpr int kBarOff = kEpiOff + 4 * kEpiChunks * kChunkBytes;
   static constexpr int kNumBars = 2 * kStages + 4 + 8;           // full, empty, tmem full[2]/empty[2], aux[4 warps][2]
   static constexpr int kTotal = kBarOff + 8 * kNumBars + 16 + 1024;  // + TMEM slot + alignment slack
 };
@@ -91,7 +95,7 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const __grid_constant__ CUtensorMap tmAux, int M, int N, int K, int a_mn, int b_mn, GemmTiles tl, GemmEpilogue ep,
                   float* __restrict__ colsum, GemmTune tune) {
   constexpr int aux_mode = (EPI & kEpiResidual) ? 1 : ((EPI & kEpiReluMask) ? 2 : 0);
-  using L = GemmSmem<BN>;
+  using L = GemmSmem<BN, aux_mode != 0>;
   constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -254,8 +258,8 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ===== epilogue: TMEM -> registers -> fused ops -> swizzled staging -> TMA store =====
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const uint32_t epi = base + L::kEpiOff + q * (4 * kChunkBytes);
-    uint8_t* epi_ptr = base_ptr + L::kEpiOff + q * (4 * kChunkBytes);
+    const uint32_t epi = base + L::kEpiOff + q * (L::kEpiChunks * kChunkBytes);
+    uint8_t* epi_ptr = base_ptr + L::kEpiOff + q * (L::kEpiChunks * kChunkBytes);
     const uint32_t sw = (uint32_t)(lane & 7);
     int as = 0, ob = 0;
     uint32_t aphase = 0, auxphase0 = 0, auxphase1 = 0;
@@ -519,7 +523,8 @@ static int num_sms() {
 
 template <int BN, int EPI>
 static int launch_tcgen05(TensorMapCache* cache, const GemmCall& c, cudaStream_t stream) {
-  using L = GemmSmem<BN>;
+  using L = GemmSmem<BN, (EPI & (kEpiResidual | kEpiReluMask)) != 0>;
+  static_assert(L::kTotal <= 227 * 1024, "GEMM shared memory exceeds the 227 KB per-CTA limit");
   static bool attr_set = false;
   if (!attr_set) {
     MFP_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tcgen05<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));

@@ -17,7 +17,7 @@ struct ModifiedPtrs {
 // masking.cu
 int launch_sample_tasks(const TaskSet& allowed, int B, uint32_t seed, uint32_t step, int* tasks, cudaStream_t st);
 int launch_mask_corrupt(const Schema& sc, const BatchPtrs& in, const int* tasks, const MaskPtrs* test_masks, int B, int S, uint32_t seed,
-                        uint32_t step, const ModifiedPtrs& out, cudaStream_t st);
+                        uint32_t step, const ModifiedPtrs& out, cudaStream_t st, unsigned char* flags /*[n_num][T], optional*/ = nullptr);
 int launch_row_flags(const Schema& sc, const BatchPtrs& mod, int T, unsigned char* flags /*[n_num][T]*/, cudaStream_t st);
 
 // encoder.cu

@@ -70,6 +70,8 @@ __global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ Schem
   const int type_true = reinterpret_cast<const int*>(targets.cols[sc.type_field])[tt * sc.f[sc.type_field].C];
   const float* lrow = logits + tp * sc.LW;
   float* drow = dlogits ? dlogits + tp * sc.LW : nullptr;
+  if (drow)
+    for (int c = sc.LWu + lane; c < sc.LW; c += 32) drow[c] = 0.f;  // row padding
   for (int f = 0; f < sc.F; ++f) {
     const FieldDev& fd = sc.f[f];
     // metrics.py:251-267: mfp mask (unsorted position) x type gate (sorted target) x seq mask

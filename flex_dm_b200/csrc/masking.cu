@@ -25,7 +25,8 @@ __device__ __forceinline__ float2 box_muller(uint32_t xa, uint32_t xb) {
 // mode 0: train (tasks != null), mode 1: test (test_masks given)
 __global__ void __launch_bounds__(256) mask_corrupt_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs in,
                                                            const int* __restrict__ tasks, const __grid_constant__ MaskPtrs test_masks, int mode, int B,
-                                                           int S, uint32_t seed, uint32_t step, const __grid_constant__ ModifiedPtrs out) {
+                                                           int S, uint32_t seed, uint32_t step, const __grid_constant__ ModifiedPtrs out,
+                                                           unsigned char* __restrict__ flags) {
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(256) mask_corrupt_kernel(const __grid_constant
     } else {
       const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in.cols[f]) + (size_t)t * fd.C);
       float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out.cols[f]) + (size_t)t * fd.C);
+      bool all_mask = true, all_null = true;  // the encoder's by-value special-token test (row_flags_kernel), on what is written
       for (int q = lane; q < fd.C / 4; q += 32) {
         float4 v;
         if (action == 1) {
@@ -91,6 +93,13 @@ __global__ void __launch_bounds__(256) mask_corrupt_kernel(const __grid_constant
           v = src[q];
         }
         dst[q] = v;
+        all_mask = all_mask && v.x == kMaskValue && v.y == kMaskValue && v.z == kMaskValue && v.w == kMaskValue;
+        all_null = all_null && v.x == kNullValue && v.y == kNullValue && v.z == kNullValue && v.w == kNullValue;
+      }
+      if (flags) {
+        all_mask = __all_sync(0xffffffffu, all_mask);
+        all_null = __all_sync(0xffffffffu, all_null);
+        if (lane == 0) flags[(size_t)fd.num_slot * B * S + t] = all_null ? 2 : (all_mask ? 1 : 0);
       }
     }
   }
@@ -126,11 +135,11 @@ int launch_sample_tasks(const TaskSet& allowed, int B, uint32_t seed, uint32_t s
 }
 
 int launch_mask_corrupt(const Schema& sc, const BatchPtrs& in, const int* tasks, const MaskPtrs* test_masks, int B, int S, uint32_t seed,
-                        uint32_t step, const ModifiedPtrs& out, cudaStream_t st) {
+                        uint32_t step, const ModifiedPtrs& out, cudaStream_t st, unsigned char* flags) {
   MaskPtrs tm{};
   if (test_masks) tm = *test_masks;
   const int T = B * S;
-  MFP_CUDA_OK(launch_pdl(mask_corrupt_kernel, (T + 7) / 8, 256, 0, st, sc, in, tasks, tm, test_masks ? 1 : 0, B, S, seed, step, out));
+  MFP_CUDA_OK(launch_pdl(mask_corrupt_kernel, (T + 7) / 8, 256, 0, st, sc, in, tasks, tm, test_masks ? 1 : 0, B, S, seed, step, out, flags));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
