@@ -277,6 +277,16 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       bool flagged = false;
       if constexpr (EPI & kEpiRowflag) flagged = row < M && ep.rowflag[row];
+      // The tile's bias row (BN columns) is fetched once, 8 columns per lane, while the accumulator is still being computed,
+      // and handed out by warp shuffles: a global load per chunk would put its L2 latency on the epilogue's critical path.
+      float bt[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if constexpr (EPI & kEpiBias) {
+        if (lead_split && lane < BN / 8) {
+          const int bc = n0 + lane * 8;
+          if (bc < N) { const float4 t = __ldg(reinterpret_cast<const float4*>(ep.bias + bc)); bt[0] = t.x; bt[1] = t.y; bt[2] = t.z; bt[3] = t.w; }
+          if (bc + 4 < N) { const float4 t = __ldg(reinterpret_cast<const float4*>(ep.bias + bc + 4)); bt[4] = t.x; bt[5] = t.y; bt[6] = t.z; bt[7] = t.w; }
+        }
+      }
       mbar_wait(tfull_bar(as), aphase);
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
@@ -287,12 +297,6 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int b = (c + 1) & 1;
           mbar_expect_tx(aux_bar(q, b), kChunkBytes);
           tma_load_2d(epi + (2 + b) * kChunkBytes, &tmAux, col0 + 32, row0, aux_bar(q, b));
-        }
-        float4 bv[8];
-        if constexpr (EPI & kEpiBias) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            bv[j] = (lead_split && col0 + 4 * j < N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (use_aux) {
           if (c & 1) { mbar_wait(aux_bar(q, 1), auxphase1); auxphase1 ^= 1u; }
@@ -305,7 +309,10 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float v[4] = {__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3])};
-          if constexpr (EPI & kEpiBias) { v[0] += bv[j].x; v[1] += bv[j].y; v[2] += bv[j].z; v[3] += bv[j].w; }
+          if constexpr (EPI & kEpiBias) {  // bias of columns col0 + 4j .. +3 sits in lane 4c + j/2, registers 4(j&1) .. +3
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] += __shfl_sync(0xffffffffu, bt[(j & 1) * 4 + e], c * 4 + (j >> 1));
+          }
           if constexpr (EPI & kEpiRelu) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.0f);
