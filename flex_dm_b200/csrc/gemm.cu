@@ -74,7 +74,7 @@ struct GemmTiles {
 // bytes in flight set the fill rate.
 template <int BN, bool AUX>
 struct GemmSmem {
-  static constexpr int kStages = (BN <= 128 || !AUX) ? 4 : 3;
+  static constexpr int kStages = (BN <= 128) ? (AUX ? 5 : 6) : (AUX ? 3 : 4);
   static constexpr int kEpiChunks = AUX ? 4 : 2;                 // per epilogue warp: out[2] (+ aux[2])
   static constexpr int kABytes = kBM * kBK * 4;
   static constexpr int kBBytes = BN * kBK * 4;
@@ -93,7 +93,7 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                   const __grid_constant__ CUtensorMap tmAux, int M, int N, int K, int a_mn, int b_mn, GemmTiles tl, GemmEpilogue ep,
-                  float* __restrict__ colsum, GemmTune tune) {
+                  float* __restrict__ colsum, GemmTune tune, unsigned long long* __restrict__ trace) {
   constexpr int aux_mode = (EPI & kEpiResidual) ? 1 : ((EPI & kEpiReluMask) ? 2 : 0);
   using L = GemmSmem<BN, aux_mode != 0>;
   constexpr int kStages = L::kStages;
@@ -145,29 +145,48 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_launch_dependents();  // one resident CTA per SM for the whole kernel: the next kernel's CTAs only queue up behind it
   pdl_wait();               // everything above (barriers, TMEM, tensor-map prefetch) touched no global memory
+  // FLEXDM_GEMM_TRACE: per-role wait cycles (which stage of the pipeline starves which), written to trace[blockIdx.x * 8 + k]
+  const long long t_start = trace ? clock64() : 0;
+  unsigned long long w0 = 0, w1 = 0, w2 = 0;
+  auto wait_t = [&](uint32_t bar, uint32_t parity, unsigned long long& acc) {
+    if (trace) {
+      const long long t0 = clock64();
+      mbar_wait(bar, parity);
+      acc += (unsigned long long)(clock64() - t0);
+    } else {
+      mbar_wait(bar, parity);
+    }
+  };
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int split = tile / tiles_mn, r = tile - split * tiles_mn;
-        const int m0 = (r / tl.tiles_n) * kBM, n0 = (r % tl.tiles_n) * BN;
+    // Lane 0 feeds the operand ring.  MN-major operands whose MN extent is whole 32-column blocks come in ONE 3-D box per stage
+    // ([block][k][32]: the same shared-memory image as separate 32-column boxes; a_mn / b_mn == 2) -- the per-instruction cost
+    // of eight 4 KB boxes had made this thread the bottleneck of every forward and weight-gradient GEMM.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int split = tile / tiles_mn, r = tile - split * tiles_mn;
+      const int m0 = (r / tl.tiles_n) * kBM, n0 = (r % tl.tiles_n) * BN;
+      if (lane == 0) {
         const int kb0 = split * tl.kb_per_split, kb1 = min(num_kb, kb0 + tl.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+          wait_t(empty_bar(stage), phase ^ 1u, w0);
           const uint32_t sa = base + stage * L::kStageBytes;
           const uint32_t sb = sa + L::kABytes;
           mbar_expect_tx(full_bar(stage), L::kStageBytes);
-          if (!a_mn) {
+          if (a_mn == 0) {
             tma_load_2d(sa, &tmA, kb * kBK, m0, full_bar(stage));
+          } else if (a_mn == 2) {
+            tma_load_3d(sa, &tmA, 0, kb * kBK, m0 >> 5, full_bar(stage));
           } else {
 #pragma unroll
             for (int j = 0; j < kBM / 32; ++j) tma_load_2d(sa + j * (kBK * 128), &tmA, m0 + 32 * j, kb * kBK, full_bar(stage));
           }
-          if (!b_mn) {
+          if (b_mn == 0) {
             tma_load_2d(sb, &tmB, kb * kBK, n0, full_bar(stage));
+          } else if (b_mn == 2) {
+            tma_load_3d(sb, &tmB, 0, kb * kBK, n0 >> 5, full_bar(stage));
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * (kBK * 128), &tmB, n0 + 32 * j, kb * kBK, full_bar(stage));
@@ -176,6 +195,7 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
+    if (trace && lane == 0) { trace[blockIdx.x * 8 + 0] = w0; trace[blockIdx.x * 8 + 7] = (unsigned long long)(clock64() - t_start); }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
@@ -187,11 +207,11 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int split = tile / tiles_mn;
         const int kb0 = split * tl.kb_per_split, kb1 = min(num_kb, kb0 + tl.kb_per_split);
-        mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator
+        wait_t(tempty_bar(as), aphase ^ 1u, w1);  // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          wait_t(full_bar(stage), phase, w0);
           tcgen05_fence_after();
           const uint32_t sa = base + stage * L::kStageBytes;
           const uint32_t sb = sa + L::kABytes;
@@ -210,6 +230,7 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         as ^= 1;
         if (as == 0) aphase ^= 1u;
       }
+      if (trace) { trace[blockIdx.x * 8 + 1] = w0; trace[blockIdx.x * 8 + 2] = w1; }
     }
   } else if (warp < kEpiWarp0) {
     // ===== column sums of the MN-major B tiles (bias gradient) =====
@@ -287,7 +308,7 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (bc + 4 < N) { const float4 t = __ldg(reinterpret_cast<const float4*>(ep.bias + bc + 4)); bt[4] = t.x; bt[5] = t.y; bt[6] = t.z; bt[7] = t.w; }
         }
       }
-      mbar_wait(tfull_bar(as), aphase);
+      wait_t(tfull_bar(as), aphase, w0);
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
       // One 32-column chunk: fused ops on the accumulator registers -> swizzled staging -> TMA store / reduce-add.
@@ -302,7 +323,10 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (c & 1) { mbar_wait(aux_bar(q, 1), auxphase1); auxphase1 ^= 1u; }
           else { mbar_wait(aux_bar(q, 0), auxphase0); auxphase0 ^= 1u; }
         }
-        if (lane == 0) tma_wait_group_read<1>();  // the staging buffer about to be overwritten has been read out
+        if (lane == 0) {  // the staging buffer about to be overwritten has been read out
+          if (trace) { const long long t0 = clock64(); tma_wait_group_read<1>(); w1 += (unsigned long long)(clock64() - t0); }
+          else tma_wait_group_read<1>();
+        }
         __syncwarp();
         const uint8_t* auxp = epi_ptr + (2 + (c & 1)) * kChunkBytes + lane * 128;
         uint8_t* outp = epi_ptr + ob * kChunkBytes + lane * 128;
@@ -354,7 +378,8 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tmem_ld32_issue(tacc, rr0);
 #pragma unroll 1
       for (int c = 0; c < nchunks; c += 2) {
-        tmem_ld32_wait(rr0);
+        if (trace) { const long long t0 = clock64(); tmem_ld32_wait(rr0); w2 += (unsigned long long)(clock64() - t0); }
+        else tmem_ld32_wait(rr0);
         if (c + 1 < nchunks) tmem_ld32_issue(tacc + (uint32_t)((c + 1) * 32), rr1);
         else release_acc();
         process(c, rr0);
@@ -369,6 +394,10 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (as == 0) aphase ^= 1u;
     }
     if (lane == 0) tma_wait_group_read<0>();
+    if (trace && warp == kEpiWarp0 && lane == 0) {
+      trace[blockIdx.x * 8 + 3] = w0; trace[blockIdx.x * 8 + 4] = w1; trace[blockIdx.x * 8 + 5] = w2;
+      trace[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - t_start);
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -539,8 +568,21 @@ static int launch_tcgen05(TensorMapCache* cache, const GemmCall& c, cudaStream_t
   }
   if (c.ep.residual && c.ep.relu_src) { set_error("gemm: residual and relu_src cannot be combined"); return MFP_ERR_ARG; }
   if (c.colsum && !c.b.mn_major) { set_error("gemm: the fused column sum needs an MN-major B operand"); return MFP_ERR_ARG; }
-  const CUtensorMap* ma = c.a.mn_major ? cache->get(c.a.ptr, c.M, c.K, c.a.ld, 32, kBK, kMapOperandMN) : cache->get(c.a.ptr, c.K, c.M, c.a.ld, kBK, kBM, kMapOperandK);
-  const CUtensorMap* mb = c.b.mn_major ? cache->get(c.b.ptr, c.N, c.K, c.b.ld, 32, kBK, kMapOperandMN) : cache->get(c.b.ptr, c.K, c.N, c.b.ld, kBK, BN, kMapOperandK);
+  // MN-major operand [K][MN] with pitch ld: 2-D boxes of 32 columns x kBK rows, or -- when MN is whole 32-column blocks -- a 3-D
+  // view [MN / 32][K][32] whose box (32, kBK, tile / 32) brings a whole stage in one instruction (mode 2 in the kernel)
+  auto mn_map = [&](const GemmOperand& o, int mn, int tile_mn, int* mode) -> const CUtensorMap* {
+    if (mn % 32 == 0 && o.ld % 32 == 0) {
+      const uint64_t d3[3] = {32, (uint64_t)c.K, (uint64_t)mn / 32}, s3[2] = {(uint64_t)o.ld, 32};
+      const uint32_t b3[3] = {32, (uint32_t)kBK, (uint32_t)(tile_mn / 32)};
+      *mode = 2;
+      return cache->get(o.ptr, 3, d3, s3, b3, kMapOperandMN);
+    }
+    *mode = 1;
+    return cache->get(o.ptr, mn, c.K, o.ld, 32, kBK, kMapOperandMN);
+  };
+  int a_mode = 0, b_mode = 0;
+  const CUtensorMap* ma = c.a.mn_major ? mn_map(c.a, c.M, kBM, &a_mode) : cache->get(c.a.ptr, c.K, c.M, c.a.ld, kBK, kBM, kMapOperandK);
+  const CUtensorMap* mb = c.b.mn_major ? mn_map(c.b, c.N, BN, &b_mode) : cache->get(c.b.ptr, c.K, c.N, c.b.ld, kBK, BN, kMapOperandK);
   const CUtensorMap* mo = cache->get(c.ep.out, c.N, c.M, c.ep.ldo, 32, 32, kMapEpilogue);
   const CUtensorMap* mx = mo;
   if (c.ep.residual) mx = cache->get(c.ep.residual, c.N, c.M, c.ep.ldr, 32, 32, kMapEpilogue);
@@ -560,8 +602,23 @@ static int launch_tcgen05(TensorMapCache* cache, const GemmCall& c, cudaStream_t
   if (tl.splits > 1) ep.atomic = 1;
   const int num_tiles = tl.tiles_m * tl.tiles_n * tl.splits;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  MFP_CUDA_OK(launch_pdl(gemm_tf32_tcgen05<BN, EPI>, grid, kGemmThreads, L::kTotal, stream, *ma, *mb, *mo, *mx, c.M, c.N, c.K, c.a.mn_major, c.b.mn_major, tl, ep, c.colsum,
-                                                                       tune));
+  static const bool trace_on = getenv("FLEXDM_GEMM_TRACE") != nullptr;  // debugging aid: prints per-role wait cycles of every launch
+  static unsigned long long* trace = nullptr;
+  if (trace_on && !trace) { MFP_CUDA_OK(cudaMalloc(&trace, 148 * 8 * sizeof(unsigned long long))); }
+  if (trace_on) MFP_CUDA_OK(cudaMemsetAsync(trace, 0, 148 * 8 * sizeof(unsigned long long), stream));
+  MFP_CUDA_OK(launch_pdl(gemm_tf32_tcgen05<BN, EPI>, grid, kGemmThreads, L::kTotal, stream, *ma, *mb, *mo, *mx, c.M, c.N, c.K, a_mode, b_mode, tl, ep, c.colsum,
+                         tune, trace_on ? trace : nullptr));
+  if (trace_on) {
+    unsigned long long hbuf[148 * 8];
+    MFP_CUDA_OK(cudaStreamSynchronize(stream));
+    MFP_CUDA_OK(cudaMemcpy(hbuf, trace, sizeof(hbuf), cudaMemcpyDeviceToHost));
+    double acc[8] = {};
+    for (int b = 0; b < grid && b < 148; ++b)
+      for (int k = 0; k < 8; ++k) acc[k] += (double)hbuf[b * 8 + k] / grid;
+    fprintf(stderr, "gemm trace M=%d N=%d K=%d a_mn=%d b_mn=%d epi=%d splits=%d tiles/cta=%.2f | producer: wait_empty %.0f of %.0f | mma: wait_full %.0f wait_tempty %.0f | "
+            "epilogue(w4): wait_tfull %.0f wait_store %.0f wait_tmem_ld %.0f of %.0f cycles\n", c.M, c.N, c.K, c.a.mn_major, c.b.mn_major, EPI, tl.splits,
+            (double)num_tiles / grid, acc[0], acc[7], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6]);
+  }
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
@@ -583,8 +640,9 @@ int launch_gemm(TensorMapCache* cache, const GemmCall& c, int impl, cudaStream_t
   }
   const int epi = (c.ep.bias ? kEpiBias : 0) | (c.ep.relu ? kEpiRelu : 0) | (c.ep.residual ? kEpiResidual : 0) | (c.ep.relu_src ? kEpiReluMask : 0) |
                   (c.ep.drop_enabled ? kEpiDropout : 0) | (c.ep.rowflag ? kEpiRowflag : 0);
+  static const bool bn128 = getenv("FLEXDM_GEMM_BN128") != nullptr;  // experiment: 128 x 128 tiles everywhere (deeper ring, more A bytes in flight)
 #define MFP_GEMM_CASE(E) \
-  case (E): return (c.N <= 128) ? launch_tcgen05<128, (E)>(cache, c, stream) : launch_tcgen05<256, (E)>(cache, c, stream);
+  case (E): return (c.N <= 128 || bn128) ? launch_tcgen05<128, (E)>(cache, c, stream) : launch_tcgen05<256, (E)>(cache, c, stream);
   switch (epi) {
     MFP_GEMM_CASE(0)                                           // dgrad / wgrad
     MFP_GEMM_CASE(kEpiBias)                                    // QKV, heads
