@@ -202,29 +202,36 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // instruction descriptor: c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13), a_major bit15, b_major bit16, N>>3 [17,23), M>>4 [24,29)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn ? 1 : 0) << 15) | ((uint32_t)(b_mn ? 1 : 0) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+      // Shared-memory descriptors: built once for stage 0 / k-step 0; the address field (bits [0,14), units of 16 B) is all that
+      // changes, so a stage or k-step is one 64-bit add.  This thread's instruction stream is serial and sits on the critical path
+      // (measured: ~1000 cycles per k-block against 512 of tensor time), so nothing is recomputed inside the loop.
+      // K-major: 8 fp32 of K = 32 B inside the 128 B swizzle row (SWIZZLE_128B, 8-row atoms 1024 B apart).
+      // MN-major: 8 K-rows = two 4-row 512 B atoms of SWIZZLE_128B_BASE32B (SBO), 32-wide MN chunks kBK*128 B apart (LBO).
+      const uint64_t da0 = a_mn ? make_smem_desc(base, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(base, tune.k_lbo, tune.k_sbo, tune.k_layout);
+      const uint64_t db0 = b_mn ? make_smem_desc(base + L::kABytes, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(base + L::kABytes, tune.k_lbo, tune.k_sbo, tune.k_layout);
+      const uint64_t a_step = a_mn ? (1024u >> 4) : (32u >> 4), b_step = b_mn ? (1024u >> 4) : (32u >> 4);
+      constexpr uint64_t kStageStep = (uint64_t)(L::kStageBytes >> 4);
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
+      uint64_t da = da0, db = db0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int split = tile / tiles_mn;
         const int kb0 = split * tl.kb_per_split, kb1 = min(num_kb, kb0 + tl.kb_per_split);
         wait_t(tempty_bar(as), aphase ^ 1u, w1);  // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+        uint32_t accumulate = 0u;
         for (int kb = kb0; kb < kb1; ++kb) {
           wait_t(full_bar(stage), phase, w0);
           tcgen05_fence_after();
-          const uint32_t sa = base + stage * L::kStageBytes;
-          const uint32_t sb = sa + L::kABytes;
 #pragma unroll
           for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
-            // K-major: 8 fp32 of K = 32 B inside the 128 B swizzle row (SWIZZLE_128B, 8-row atoms 1024 B apart).
-            // MN-major: 8 K-rows = two 4-row 512 B atoms of SWIZZLE_128B_BASE32B (SBO), 32-wide MN chunks kBK*128 B apart (LBO).
-            const uint64_t da = a_mn ? make_smem_desc(sa + kk * 1024, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(sa + kk * 32, tune.k_lbo, tune.k_sbo, tune.k_layout);
-            const uint64_t db = b_mn ? make_smem_desc(sb + kk * 1024, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(sb + kk * 32, tune.k_lbo, tune.k_sbo, tune.k_layout);
-            umma_tf32(tacc, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            umma_tf32(tacc, da + kk * a_step, db + kk * b_step, idesc, accumulate);
+            accumulate = 1u;
           }
           tcgen05_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          da += kStageStep; db += kStageStep;
+          if (++stage == kStages) { stage = 0; phase ^= 1u; da = da0; db = db0; }
         }
         tcgen05_commit(tfull_bar(as));  // accumulator complete
         as ^= 1;
