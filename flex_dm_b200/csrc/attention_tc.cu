@@ -99,16 +99,20 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
       // instruction descriptors: c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13), a_major bit15, b_major bit16, N>>3 [17,23), M>>4 [24,29)
       const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kAtRows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t idesc_o = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(kDh >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // shared-memory descriptors built once (this thread's serial instruction stream is on the critical path): only the address
+      // field (bits [0,14), units of 16 B) changes with the slot, the operand tile and the k-step
+      const uint64_t dq0 = make_smem_desc(base, 16, 1024, 2);                                   // Q (K-major); K is one tile further
+      const uint64_t dv0 = make_smem_desc(base + 2 * kAtTileBytes, kAtTileBytes, 512, 1);       // V (MN-major)
+      constexpr uint64_t kTileStep = (uint64_t)(kAtTileBytes >> 4), kSlotStep = (uint64_t)(L::kSlotBytes >> 4);
       for (int i = 0; i <= n_local; ++i) {
         if (i < n_local) {
           const int slot = i % kFwdSlots;
           mbar_wait(full_bar(slot), (i / kFwdSlots) & 1);
           tcgen05_fence_after();
-          const uint32_t sq = base + slot * L::kSlotBytes, sk = sq + kAtTileBytes;
+          const uint64_t dq = dq0 + (uint64_t)slot * kSlotStep, dk = dq + kTileStep;
           const uint32_t sbuf = tmem_base + (uint32_t)((i & 1) * 128);
 #pragma unroll
-          for (int kk = 0; kk < kDh / 8; ++kk)
-            umma_tf32(sbuf, make_smem_desc(sq + kk * 32, 16, 1024, 2), make_smem_desc(sk + kk * 32, 16, 1024, 2), idesc_s, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < kDh / 8; ++kk) umma_tf32(sbuf, dq + (uint64_t)(kk * 2), dk + (uint64_t)(kk * 2), idesc_s, kk > 0 ? 1u : 0u);
           tcgen05_commit(sfull_bar(i & 1));
         }
         if (i >= 1) {
@@ -118,11 +122,10 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
           const int nk = (n + 7) >> 3;
           mbar_wait(pready_bar(j & 1), (j >> 1) & 1);
           tcgen05_fence_after();
-          const uint32_t sv = base + (j % kFwdSlots) * L::kSlotBytes + 2 * kAtTileBytes;
+          const uint64_t dv = dv0 + (uint64_t)(j % kFwdSlots) * kSlotStep;
           const uint32_t pbuf = tmem_base + (uint32_t)((j & 1) * 128);
           const uint32_t obuf = tmem_base + 256u + (uint32_t)((j & 1) * 32);
-          for (int kk = 0; kk < nk; ++kk)
-            umma_tf32_ts(obuf, pbuf + (uint32_t)(kk * 8), make_smem_desc(sv + kk * 1024, kAtTileBytes, 512, 1), idesc_o, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < nk; ++kk) umma_tf32_ts(obuf, pbuf + (uint32_t)(kk * 8), dv + (uint64_t)(kk * 64), idesc_o, kk > 0 ? 1u : 0u);
           tcgen05_commit(ofull_bar(j & 1));
           tcgen05_commit(empty_bar(j % kFwdSlots));
         }
@@ -331,9 +334,13 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid
       const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kAtRows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t idesc_g = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(kDh >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // B MN-major
       const uint32_t idesc_q = idesc_g | (1u << 15);                                                                                       // A MN-major too
+      // descriptors built once; a k-step is one add on the address field (units of 16 B)
       const uint32_t sk = base + L::kKmajOff, sq = sk + kAtTileBytes, sv = sk + 2 * kAtTileBytes, sdo = sk + 3 * kAtTileBytes;
       const uint32_t mdo = base + L::kMnOff, mq = mdo + kAtTileBytes, mk = mdo + 2 * kAtTileBytes;
-      const uint32_t sds = base + L::kDsOff;
+      const uint64_t dk_k = make_smem_desc(sk, 16, 1024, 2), dq_k = make_smem_desc(sq, 16, 1024, 2), dv_k = make_smem_desc(sv, 16, 1024, 2),
+                     ddo_k = make_smem_desc(sdo, 16, 1024, 2);
+      const uint64_t ddo_m = make_smem_desc(mdo, kAtTileBytes, 512, 1), dq_m = make_smem_desc(mq, kAtTileBytes, 512, 1),
+                     dk_m = make_smem_desc(mk, kAtTileBytes, 512, 1), dds_m = make_smem_desc(base + L::kDsOff, kAtTileBytes, 512, 1);
       for (int i = 0; i < n_local; ++i) {
         const int u = blockIdx.x + i * gridDim.x, b = u / kH;
         const int n = min(S, __ldg(length + b) + 1);
@@ -342,23 +349,20 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid
         mbar_wait(kfull, ph);
         tcgen05_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < kDh / 8; ++kk)
-          umma_tf32(tmem_base, make_smem_desc(sk + kk * 32, 16, 1024, 2), make_smem_desc(sq + kk * 32, 16, 1024, 2), idesc_s, kk > 0 ? 1u : 0u);
+        for (int kk = 0; kk < kDh / 8; ++kk) umma_tf32(tmem_base, dk_k + (uint64_t)(kk * 2), dq_k + (uint64_t)(kk * 2), idesc_s, kk > 0 ? 1u : 0u);
 #pragma unroll
-        for (int kk = 0; kk < kDh / 8; ++kk)
-          umma_tf32(tmem_base + 128u, make_smem_desc(sv + kk * 32, 16, 1024, 2), make_smem_desc(sdo + kk * 32, 16, 1024, 2), idesc_s, kk > 0 ? 1u : 0u);
+        for (int kk = 0; kk < kDh / 8; ++kk) umma_tf32(tmem_base + 128u, dv_k + (uint64_t)(kk * 2), ddo_k + (uint64_t)(kk * 2), idesc_s, kk > 0 ? 1u : 0u);
         tcgen05_commit(sfull);
         tcgen05_commit(kempty);
         mbar_wait(pready, ph);
         mbar_wait(mnfull, ph);
         tcgen05_fence_after();
         for (int kk = 0; kk < nk; ++kk)  // dV = P^T dO
-          umma_tf32_ts(tmem_base + 256u, tmem_base + (uint32_t)(kk * 8), make_smem_desc(mdo + kk * 1024, kAtTileBytes, 512, 1), idesc_g, kk > 0 ? 1u : 0u);
+          umma_tf32_ts(tmem_base + 256u, tmem_base + (uint32_t)(kk * 8), ddo_m + (uint64_t)(kk * 64), idesc_g, kk > 0 ? 1u : 0u);
         for (int kk = 0; kk < nk; ++kk)  // dK = dS^T Q
-          umma_tf32_ts(tmem_base + 288u, tmem_base + 128u + (uint32_t)(kk * 8), make_smem_desc(mq + kk * 1024, kAtTileBytes, 512, 1), idesc_g, kk > 0 ? 1u : 0u);
+          umma_tf32_ts(tmem_base + 288u, tmem_base + 128u + (uint32_t)(kk * 8), dq_m + (uint64_t)(kk * 64), idesc_g, kk > 0 ? 1u : 0u);
         for (int kk = 0; kk < nk; ++kk)  // dQ = dS K
-          umma_tf32(tmem_base + 320u, make_smem_desc(sds + kk * 1024, kAtTileBytes, 512, 1), make_smem_desc(mk + kk * 1024, kAtTileBytes, 512, 1), idesc_q,
-                    kk > 0 ? 1u : 0u);
+          umma_tf32(tmem_base + 320u, dds_m + (uint64_t)(kk * 64), dk_m + (uint64_t)(kk * 64), idesc_q, kk > 0 ? 1u : 0u);
         tcgen05_commit(ofull);
         tcgen05_commit(mnempty);
       }
@@ -432,8 +436,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {  // 32 queries at a time
         uint32_t rs[32], rd[32];
-        tmem_ld32(lane_base + (uint32_t)(c * 32), rs);
-        tmem_ld32(lane_base + 128u + (uint32_t)(c * 32), rd);
+        tmem_ld32_issue(lane_base + (uint32_t)(c * 32), rs);  // both loads in flight before the single wait
+        tmem_ld32_issue(lane_base + 128u + (uint32_t)(c * 32), rd);
+        tmem_ld32_wait(rs);
+        tmem_ld32_wait(rd);
         uint8_t* dsp = ds_ptr + c * kAtTileBytes + row * 128;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {

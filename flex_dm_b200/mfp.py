@@ -307,10 +307,13 @@ class MFP:
                 m = demo_args["masks"][key]
                 m = torch.as_tensor(m) if not isinstance(m, torch.Tensor) else m
                 masks.append(m.to(self.device).to(torch.uint8).contiguous())
-            if int(demo_args.get("num_iter", 1)) > 1:
-                raise NotImplementedError("iterative_decode (mfp.py:141-207) is a 'next' row of SURVEY.md section 8f")
-            eng.mask_for_test(length, cols, masks)  # mfp.py:72-92
-            eng.forward(length, None, training, seed, step)
+            num_iter = int(demo_args.get("num_iter", 1))
+            final_logits = None
+            if num_iter > 1:
+                final_logits = self._iterative_decode(B, S, length, cols, masks, num_iter, seed, step)  # mfp.py:141-207
+            else:
+                eng.mask_for_test(length, cols, masks)  # mfp.py:72-92
+                eng.forward(length, None, training, seed, step)
             if "tasks" in demo_args:
                 t = demo_args["tasks"]
                 tasks = (torch.as_tensor(t) if not isinstance(t, torch.Tensor) else t).to(self.device)
@@ -333,13 +336,65 @@ class MFP:
             c = self.engine.columns[key]
             shape = (B, S, c["shape"][-1], c["input_dim"]) if c["type"] == "categorical" else (B, S, c["shape"][-1])
             out = torch.empty(shape, dtype=torch.float32, device=self.device)
-            eng.merge_prediction(f, cols[f], masks[f], out)
+            eng.merge_prediction(f, cols[f], masks[f], out, logits_in=final_logits if is_demo else None)
             outputs[key] = out
         for key, column in self.all_columns.items():  # copy unpredicted items for visualization (mfp.py:66-68)
             if column.get("demo_only", False) and key in inputs:
                 outputs[key] = inputs[key]
         outputs["tasks"] = tasks.clone()
         return outputs
+
+    def _iterative_decode(self, B: int, S: int, length, cols, masks_u8, num_iter: int, seed: int, step: int) -> torch.Tensor:
+        """``iterative_decode`` (mfp.py:141-207), MaskGIT-like: ``num_iter`` forward passes of the engine; after each one the
+        categorical predictions whose confidence reaches the document's top-k threshold are written back into the inputs and
+        unmasked.  The selection itself is a few small device-tensor operations per pass (control logic around the forward
+        passes, which is where the time goes).  Returns the flat ``[B*S, logit_width]`` matrix of final outputs.
+        The reference compares a (B, S) confidence with a (B,) threshold (:184), which broadcasts only for B = 1; the threshold
+        is applied per document here, which is identical for B = 1."""
+        eng = self.engine
+        columns = [eng.columns[k] for k in self.keys]
+        cat = [f for f, c in enumerate(columns) if c["type"] == "categorical"]
+        eng.mask_for_test(length, cols, [torch.zeros_like(m) for m in masks_u8])  # filter_padding alone (:146)
+        filtered = [t.clone() for t in eng.modified]
+        eng.mask_for_test(length, cols, masks_u8)  # modified_inputs of preprocess_for_test
+        masks = [m.reshape(B, S).bool().clone() for m in masks_u8]
+        num_masked = sum(masks[f].sum(dim=-1) for f in cat).cpu().numpy()
+        num_update = torch.from_numpy(np.round(num_masked / num_iter).astype(np.int64)).to(self.device)  # numpy rounding, as in :152-153
+        logits = torch.empty((B * S, eng.logit_width), dtype=torch.float32, device=self.device)
+        final = None
+        rows = torch.arange(B, device=self.device)
+        for i in range(num_iter):
+            eng.forward(length, None, False, seed, step, logits_out=logits)
+            out = self.split_logits(logits, B, S)
+            if i == 0:
+                final = logits.clone()
+            fin = self.split_logits(final, B, S)
+            conf = {}
+            for f in cat:
+                p = torch.softmax(out[self.keys[f]], dim=-1).max(dim=-1).values.mean(dim=-1)  # mean over sub-targets (e.g. RGB) of the max probability
+                conf[f] = torch.where(masks[f], p, torch.zeros((), dtype=p.dtype, device=self.device))
+            conf_sorted = torch.sort(torch.cat([conf[f] for f in cat], dim=-1), dim=-1, descending=True).values
+            threshold = conf_sorted[rows, num_update.clamp(max=conf_sorted.shape[1] - 1)]
+            for f in cat:
+                key = self.keys[f]
+                pred = out[key].argmax(dim=-1).to(torch.int32)
+                update = (conf[f] >= threshold[:, None]) & (conf[f] > 0)
+                filtered[f] = torch.where(update[:, :, None], pred.reshape(filtered[f].shape), filtered[f])
+                masks[f] = torch.where(masks[f] == update, torch.zeros_like(masks[f]), masks[f])
+                if i > 0:
+                    fin[key].copy_(torch.where(update[:, :, None, None], out[key], fin[key]))
+            for f, c in enumerate(columns):  # apply_token(filtered, masks, "masked") (masking.py:68-95) -> the next pass's inputs
+                m = masks[f].reshape(B, S, 1)
+                if c["type"] == "categorical":
+                    eng.modified[f].copy_(torch.where(m, torch.full_like(filtered[f], c["input_dim"]), filtered[f]).reshape(eng.modified[f].shape))
+                else:
+                    eng.modified[f].copy_(torch.where(m, torch.full_like(filtered[f], 10.0), filtered[f]).reshape(eng.modified[f].shape))
+        fin = self.split_logits(final, B, S)
+        out = self.split_logits(logits, B, S)
+        for f, c in enumerate(columns):  # "use last prediction for numerical fields" (:202-204)
+            if c["type"] == "numerical":
+                fin[self.keys[f]].copy_(out[self.keys[f]])
+        return final
 
     def model(self, modified_inputs: Dict, training: bool = False, seed: Optional[int] = None, step: int = 0) -> Dict[str, torch.Tensor]:
         """The inner boundary ``self.model(modified_inputs, training)`` = ``Model.call`` (model.py:26-30):

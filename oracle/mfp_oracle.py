@@ -584,6 +584,44 @@ def merge_inputs_and_prediction(inputs, input_columns, masks, prediction):
     return out
 
 
+def iterative_decode(params, masks, inputs, input_columns, modified_inputs, num_iter, num_blocks):
+    """mfp.py:141-207 -- MaskGIT-like decoding: ``num_iter`` forward passes; after each, the categorical predictions whose
+    confidence (mean over sub-targets of the max softmax probability) reaches the document's top-k threshold are written
+    back into the inputs and unmasked.  The reference compares a (B, S) confidence with a (B,) threshold (:184), which only
+    broadcasts for B = 1; per-document thresholds (``threshold[:, None]``) are the same thing there and defined for any B."""
+    masks = dict(masks)
+    S = inputs[next(iter(get_valid_input_columns(input_columns)))].shape[1]
+    seq_mask = get_seq_mask(inputs["length"], S)
+    filtered = filter_padding(inputs, input_columns, seq_mask)
+    cat_keys = [k for k, v in input_columns.items() if v["is_sequence"] and v.get("type", None) == "categorical"]
+    num_masked = sum(masks[k].numpy().astype("int").sum(-1) for k in cat_keys)
+    num_update = (num_masked / num_iter).round().astype("int")  # numpy: round half to even
+    modified = dict(modified_inputs)
+    final = None
+    for i in range(num_iter):
+        outputs = model_forward(params, modified, input_columns, num_blocks)
+        if i == 0:
+            final = OrderedDict(outputs)
+        conf = {k: torch.where(masks[k], torch.softmax(outputs[k], dim=-1).max(dim=-1).values.mean(dim=-1), torch.zeros((), dtype=outputs[k].dtype))
+                for k in cat_keys}
+        conf_sorted = torch.sort(torch.cat([conf[k] for k in cat_keys], dim=-1), dim=-1, descending=True).values
+        threshold = torch.stack([conf_sorted[b, k] for b, k in enumerate(num_update)])
+        for key in cat_keys:
+            pred = outputs[key].argmax(dim=-1).to(filtered[key].dtype)
+            update = (conf[key] >= threshold[:, None]) & (conf[key] > 0)
+            filtered[key] = torch.where(update[:, :, None], pred, filtered[key])
+            masks[key] = torch.where(masks[key] == update, torch.zeros_like(masks[key]), masks[key])
+            if i > 0:
+                final[key] = torch.where(update[:, :, None, None], outputs[key], final[key])
+        for key, column in input_columns.items():
+            if column["is_sequence"]:
+                modified[key] = apply_token(filtered[key], column, masks[key], "masked")
+    for key, column in input_columns.items():  # the reference names image_embedding / text_embedding (:203-204)
+        if column["is_sequence"] and column["type"] == "numerical":
+            final[key] = outputs[key]
+    return final
+
+
 # ----------------------------------------------------------------------------------------------- optimiser
 def clip_by_norm(g, clipnorm):
     """A4: tf.clip_by_norm per variable: g * c / max(||g||, c)."""

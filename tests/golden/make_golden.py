@@ -274,7 +274,61 @@ def run_demo_case(name="crello_demo", B=3, S=10, L=2, seed=5, lengths=(10, 1, 6)
     print("%-16s demo forward -> %s (%.0f kB)" % (name, os.path.relpath(path, ROOT), os.path.getsize(path) / 1e3))
 
 
+def decode_weights(cols, L):
+    """Weights of the iterative-decoding case: decoder kernels scaled up so that the per-field confidences (max softmax
+    probability) are well separated and the top-k selection does not hinge on the last bits of a logit."""
+    params = O.init_params(cols, L, D, WEIGHT_SEED, torch.float64, bias_scale=0.05)
+    for name in params:
+        if name.startswith("model/decoder/") and name.endswith("/kernel"):
+            params[name] = params[name] * 30.0
+    return params
+
+
+def run_decode_case(name="crello_decode", B=1, S=12, L=2, seed=6, lengths=(12,), num_iter=3,
+                    masked_keys=("type", "left", "top", "width", "height", "color", "image_embedding")):
+    """eval.py --num_iter > 1: MaskGIT-like iterative decoding (mfp.py:141-207), whole MFP.call in float64.  B = 1: the reference
+    compares a (B, S) confidence with a (B,) threshold (mfp.py:184), which only broadcasts for a single document."""
+    cols = make_input_columns("crello", max_length=50)
+    batch = make_synthetic_batch(cols, B, S, seed=seed, fixed_lengths=np.asarray(lengths))
+    params = decode_weights(cols, L)
+    icols = OrderedDict((k, v) for k, v in cols.items() if not v.get("demo_only", False))
+    seq = get_valid_input_columns(icols)
+    seq_mask = np.arange(S)[None, :] < np.asarray(lengths)[:, None]
+    masks = {}
+    for k, c in icols.items():
+        masks[k] = np.ones((B,), bool) if not c["is_sequence"] else (seq_mask.copy() if k in masked_keys else np.zeros((B, S), bool))
+    out = {"tasks": np.zeros((B,), np.int32), "num_iter": np.int32(num_iter)}
+    for k, v in batch.items():
+        out["in/" + k] = v
+    for k, v in masks.items():
+        out["mask/" + k] = v
+    d = [("randint", None) if c["type"] == "categorical" else ("normal", None) for c in seq.values()]
+    # task sampler; preprocess_for_test: filter_padding + apply_token; iterative_decode: filter_padding, then apply_token per iteration
+    script = [("categorical", out["tasks"])] + d + d + d + d * num_iter
+    tfc.FLOAT = torch.float64
+    model = RefMFP(cols, num_blocks=L, block_type="deepsvg", masking_method="random", seq_type="default", arch_type="oneshot",
+                   context=None, input_dtype="set", latent_dim=D, dropout=RATE, l2=L2)
+
+    def inputs64():
+        return {k: (torch.as_tensor(v).double() if v.dtype.kind == "f" else torch.as_tensor(v)).as_subclass(tf.Tensor) for k, v in batch.items()}
+
+    tmasks = {k: torch.as_tensor(v).as_subclass(tf.Tensor) for k, v in masks.items()}
+    tfc.rng = tfc.ScriptedRNG(script)
+    model(inputs64(), training=False, demo_args={"masks": dict(tmasks), "num_iter": num_iter})
+    set_weights(model, params, torch.float64)
+    tfc.rng = tfc.ScriptedRNG(script)
+    merged = model(inputs64(), training=False, demo_args={"masks": dict(tmasks), "num_iter": num_iter})
+    assert tfc.rng.done()
+    for k, v in merged.items():
+        if k != "tasks":
+            out["merged/" + k] = v.detach().numpy()
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("%-16s iterative decode (%d iterations) -> %s (%.0f kB)" % (name, num_iter, os.path.relpath(path, ROOT), os.path.getsize(path) / 1e3))
+
+
 if __name__ == "__main__":
     for case, spec in CASES.items():
         run_case(case, spec)
     run_demo_case()
+    run_decode_case()

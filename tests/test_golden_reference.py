@@ -255,3 +255,64 @@ def test_engine_demo_call_matches_reference_python():
             assert np.abs(got - ref).max() <= H.LOGIT_ATOL, key
         else:
             assert np.array_equal(got, ref), key
+
+
+# ================================================================================================= iterative decoding
+def _load_decode():
+    g = np.load(os.path.join(GOLDEN, "crello_decode.npz"))
+    cols = make_input_columns("crello", max_length=50)
+    batch = OrderedDict((k[3:], g[k]) for k in g.files if k.startswith("in/"))
+    masks = OrderedDict((k[5:], g[k]) for k in g.files if k.startswith("mask/"))
+    params = O.init_params(cols, 2, 256, WEIGHT_SEED, torch.float64, bias_scale=0.05)
+    for name in params:  # decode_weights() of make_golden.py
+        if name.startswith("model/decoder/") and name.endswith("/kernel"):
+            params[name] = params[name] * 30.0
+    return g, cols, batch, masks, params, int(g["num_iter"])
+
+
+def test_oracle_iterative_decode_matches_reference_python():
+    """model(example, training=False, demo_args={"masks": ..., "num_iter": 3}): mfp.py:141-207 run by the reference itself."""
+    g, cols, batch, masks, params, num_iter = _load_decode()
+    icols = OrderedDict((k, v) for k, v in cols.items() if not v.get("demo_only", False))
+    inputs = {k: (torch.as_tensor(v).double() if v.dtype.kind == "f" else torch.as_tensor(v)) for k, v in batch.items()}
+    tmasks = {k: torch.as_tensor(v) for k, v in masks.items()}
+    mod = O.preprocess_for_test(inputs, icols, tmasks)
+    outputs = O.iterative_decode(params, tmasks, inputs, icols, mod, num_iter, 2)
+    merged = O.merge_inputs_and_prediction(inputs, icols, tmasks, outputs)
+    for key in icols:
+        ref = g["merged/" + key]
+        assert merged[key].shape == ref.shape, key
+        assert np.abs(merged[key].numpy() - ref).max() <= 1e-9, key
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("impl", [1, 0], ids=["fp32-simt", "tf32-tcgen05"])
+def test_engine_iterative_decode_matches_reference_python(impl):
+    from flex_dm_b200.mfp import MFP
+
+    g, cols, batch, masks, params, num_iter = _load_decode()
+    m = MFP(cols, num_blocks=2, masking_method="random", latent_dim=256, dropout=RATE, l2=L2, seed=0)
+    m.set_weights({k: v.numpy().astype(np.float32) for k, v in params.items()})
+    m.engine.set_gemm_impl(impl)
+    out = m(batch, training=False, demo_args={"masks": {k: torch.as_tensor(v) for k, v in masks.items()}, "num_iter": num_iter})
+    torch.cuda.synchronize()
+    # the decoder kernels are scaled by 30, so are the logits (O(100)): the tolerance is relative to each field's largest logit
+    rtol = 1e-4 if impl == 1 else 5e-3
+    agree, total = 0, 0
+    for key, column in m.input_columns.items():
+        ref = g["merged/" + key]
+        got = out[key].cpu().numpy()
+        assert got.shape == ref.shape, key
+        if not column["is_sequence"]:
+            assert np.array_equal(got, ref), key
+        elif column["type"] == "categorical":
+            # which pass a prediction was frozen in depends on a ranking of confidences: compare the decoded labels, and the
+            # logits wherever both runs froze the element in the same pass (identical inputs up to rounding)
+            atol = rtol * np.abs(ref).max()
+            same = np.abs(got - ref).max(axis=(-1, -2)) <= atol
+            agree += int((got.argmax(-1) == ref.argmax(-1)).all(axis=-1).sum())
+            total += got.shape[0] * got.shape[1]
+            assert same.mean() >= 0.9, (key, same.mean(), float(np.abs(got - ref).max()), atol)
+        else:
+            assert np.abs(got - ref).max() <= rtol * np.abs(ref).max(), (key, float(np.abs(got - ref).max()), float(np.abs(ref).max()))
+    assert agree >= 0.97 * total, (agree, total)
