@@ -271,7 +271,8 @@ struct AttnBwdSmem {
   static constexpr int kTotal = kBarOff + 8 * kNumBars + 16 + 1024;
 };
 
-__global__ void __launch_bounds__(kAtThreads, 1)
+constexpr int kAtBwdThreads = 384;  // warps 0-3: TMA / MMA / TMEM allocator / idle; warps 4-7 and 8-11: two compute groups
+__global__ void __launch_bounds__(kAtBwdThreads, 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid_constant__ CUtensorMap tmQkvMN, const __grid_constant__ CUtensorMap tmDoK,
                         const __grid_constant__ CUtensorMap tmDoMN, const __grid_constant__ CUtensorMap tmDqkv, const float* __restrict__ out,
                         const float* __restrict__ lse, const int* __restrict__ length, int B, int S) {
@@ -293,7 +294,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid
 
   if (threadIdx.x == 0) {
     mbar_init(kfull, 1); mbar_init(kempty, 5); mbar_init(mnfull, 1); mbar_init(mnempty, 1);  // kempty: MMA commit + the 4 warps that read dO
-    mbar_init(sfull, 1); mbar_init(pready, 4); mbar_init(ofull, 1);
+    mbar_init(sfull, 1); mbar_init(pready, 8); mbar_init(ofull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tensormap(&tmQkvK); prefetch_tensormap(&tmQkvMN); prefetch_tensormap(&tmDoK); prefetch_tensormap(&tmDoMN); prefetch_tensormap(&tmDqkv);
   }
@@ -368,18 +369,21 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid
       }
     }
   } else if (warp >= 4) {
+    // Two compute groups of four warps (one warp per TMEM lane quarter each).  Both own all 128 keys (lanes); group g takes the
+    // query chunks 2g, 2g+1 of P^T / dS^T.  Afterwards group 0 stores dV and dK while group 1 prepares lse / D of the next unit
+    // and stores dQ.  Named barriers 1 and 2 (256 threads) order the writes and reads of lse_s / d_s between the groups.
+    const int g = (warp - 4) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;  // key index in softmax / dS; query index in the D preparation; output row in the epilogue
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t stage = base + L::kStageOff + q * 8192;
-    uint8_t* stage_ptr = base_ptr + L::kStageOff + q * 8192;
+    const uint32_t stage = base + L::kStageOff + (g * 4 + q) * 4096;  // one [32][32] fp32 staging chunk per warp
+    uint8_t* stage_ptr = base_ptr + L::kStageOff + (g * 4 + q) * 4096;
     uint8_t* ds_ptr = base_ptr + L::kDsOff;
     const uint8_t* do_ptr = base_ptr + L::kKmajOff + 3 * kAtTileBytes;
     const uint32_t sw = (uint32_t)(lane & 7);
     const float c2 = kAtScale * kLog2e;
-    int ob = 0;
 
-    auto prepare = [&](int i) {  // lse_i and D_i = dO_i . O_i of unit i -> shared memory (all 128 threads, one query row each)
+    auto prepare = [&](int i) {  // lse_i and D_i = dO_i . O_i of unit i -> shared memory (group 1: one query row per thread)
       const int u = blockIdx.x + i * gridDim.x, b = u / kH, h = u % kH;
       mbar_wait(kfull, (uint32_t)(i & 1));
       float dsum = 0.f, l = INFINITY;
@@ -389,8 +393,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float4 o = __ldg(op + k);
-          const float4 g = *reinterpret_cast<const float4*>(dp + ((k ^ sw) << 4));
-          dsum += o.x * g.x + o.y * g.y + o.z * g.z + o.w * g.w;
+          const float4 gv = *reinterpret_cast<const float4*>(dp + ((k ^ sw) << 4));
+          dsum += o.x * gv.x + o.y * gv.y + o.z * gv.z + o.w * gv.w;
         }
         l = __ldg(lse + ((size_t)b * kH + h) * S + row);
       }
@@ -398,43 +402,37 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid
       d_s[row] = dsum;
       __syncwarp();
       if (lane == 0) mbar_arrive(kempty);  // this warp no longer reads the K-major dO tile
-      asm volatile("bar.sync 1, 128;" ::: "memory");
     };
-    auto epilogue = [&](int i) {
+    auto store_tile = [&](int i, int t) {  // t = 0 dV, 1 dK, 2 dQ: TMEM -> registers -> swizzled staging -> TMA store
       const int u = blockIdx.x + i * gridDim.x, b = u / kH, h = u % kH;
-      mbar_wait(ofull, (uint32_t)(i & 1));
-      tcgen05_fence_after();
-#pragma unroll 1
-      for (int t = 0; t < 3; ++t) {  // dV, dK, dQ
-        uint32_t r[32];
-        tmem_ld32(lane_base + 256u + (uint32_t)(t * 32), r);
-        const float sc = (t == 0) ? 1.0f : kAtScale;
-        if (lane == 0) tma_wait_group_read<1>();
-        __syncwarp();
-        uint8_t* outp = stage_ptr + ob * 4096 + lane * 128;
+      uint32_t r[32];
+      tmem_ld32(lane_base + 256u + (uint32_t)(t * 32), r);
+      const float sc = (t == 0) ? 1.0f : kAtScale;
+      if (lane == 0) tma_wait_group_read<0>();  // the staging chunk has been read out by the previous store
+      __syncwarp();
+      uint8_t* outp = stage_ptr + lane * 128;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          *reinterpret_cast<float4*>(outp + ((k ^ sw) << 4)) = make_float4(__uint_as_float(r[4 * k]) * sc, __uint_as_float(r[4 * k + 1]) * sc,
-                                                                           __uint_as_float(r[4 * k + 2]) * sc, __uint_as_float(r[4 * k + 3]) * sc);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_3d(&tmDqkv, stage + ob * 4096, (2 - t) * kD + h * kDh, q * 32, b);
-          tma_commit_group();
-        }
-        ob ^= 1;
+      for (int k = 0; k < 8; ++k)
+        *reinterpret_cast<float4*>(outp + ((k ^ sw) << 4)) = make_float4(__uint_as_float(r[4 * k]) * sc, __uint_as_float(r[4 * k + 1]) * sc,
+                                                                         __uint_as_float(r[4 * k + 2]) * sc, __uint_as_float(r[4 * k + 3]) * sc);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tmDqkv, stage, (2 - t) * kD + h * kDh, q * 32, b);
+        tma_commit_group();
       }
     };
 
-    if (n_local > 0) prepare(0);
+    if (n_local > 0 && g == 1) prepare(0);
     for (int i = 0; i < n_local; ++i) {
       const int u = blockIdx.x + i * gridDim.x, b = u / kH;
       const int n = min(S, __ldg(length + b) + 1);
       const bool key_valid = row < n;
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // lse_s / d_s of this unit are in place
       mbar_wait(sfull, (uint32_t)(i & 1));
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {  // 32 queries at a time
+      for (int c = 2 * g; c < 2 * g + 2; ++c) {  // 32 queries at a time
         uint32_t rs[32], rd[32];
         tmem_ld32_issue(lane_base + (uint32_t)(c * 32), rs);  // both loads in flight before the single wait
         tmem_ld32_issue(lane_base + 128u + (uint32_t)(c * 32), rd);
@@ -460,9 +458,12 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pready);
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done with lse_s / d_s before the next unit overwrites them
-      if (i + 1 < n_local) prepare(i + 1);
-      epilogue(i);
+      asm volatile("bar.sync 2, 256;" ::: "memory");  // everyone is done with lse_s / d_s before the next unit overwrites them
+      if (g == 1 && i + 1 < n_local) prepare(i + 1);
+      mbar_wait(ofull, (uint32_t)(i & 1));
+      tcgen05_fence_after();
+      if (g == 0) { store_tile(i, 0); store_tile(i, 1); }
+      else store_tile(i, 2);
     }
     if (lane == 0) tma_wait_group_read<0>();
   }
@@ -522,7 +523,7 @@ int launch_attention_bwd_tc(TensorMapCache* maps, const float* qkv, const float*
   if (!mqk || !mqm || !mdk || !mdm || !mg) return MFP_ERR_CUDA;
   const int units = B * kH;
   const int grid = units < sm_count() ? units : sm_count();
-  MFP_CUDA_OK(launch_pdl(attention_bwd_tc_kernel, grid, kAtThreads, AttnBwdSmem::kTotal, st, *mqk, *mqm, *mdk, *mdm, *mg, out, lse, length, B, S));
+  MFP_CUDA_OK(launch_pdl(attention_bwd_tc_kernel, grid, kAtBwdThreads, AttnBwdSmem::kTotal, st, *mqk, *mqm, *mdk, *mdm, *mg, out, lse, length, B, S));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
