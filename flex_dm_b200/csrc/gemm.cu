@@ -118,8 +118,8 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), do_colsum ? 3 : 1);
+      mbar_init(full_bar(s), 2);                   // the A producer and the B producer each arrive with their own byte count
+      mbar_init(empty_bar(s), do_colsum ? 2 : 1);  // MMA commit (+ the column-sum warp)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -158,44 +158,51 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   };
 
-  if (warp == 0) {
-    // ===== TMA producer =====
-    // Lane 0 feeds the operand ring.  MN-major operands whose MN extent is whole 32-column blocks come in ONE 3-D box per stage
-    // ([block][k][32]: the same shared-memory image as separate 32-column boxes; a_mn / b_mn == 2) -- the per-instruction cost
-    // of eight 4 KB boxes had made this thread the bottleneck of every forward and weight-gradient GEMM.
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int split = tile / tiles_mn, r = tile - split * tiles_mn;
-      const int m0 = (r / tl.tiles_n) * kBM, n0 = (r % tl.tiles_n) * BN;
-      if (lane == 0) {
+  if (warp == 0 || warp == 3) {
+    // ===== TMA producers: warp 0 feeds the A half of every stage, warp 3 the B half =====
+    // One thread can issue a tensor box only every ~600 cycles whatever its size (tools/microbench/rowrate.cu: 16 KB boxes from one
+    // thread top out at 55 GB/s per SM, from four threads at 135 GB/s); with one producer issuing both operands a k-block took
+    // ~1100 cycles against 512 of tensor time.  Two issuing warps, one box each per k-block.
+    // MN-major operands whose MN extent is whole 32-column blocks come in ONE 3-D box per stage ([block][k][32]: the same
+    // shared-memory image as separate 32-column boxes; a_mn / b_mn == 2).
+    if (lane == 0) {
+      const bool is_a = (warp == 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile / tiles_mn, r = tile - split * tiles_mn;
+        const int m0 = (r / tl.tiles_n) * kBM, n0 = (r % tl.tiles_n) * BN;
         const int kb0 = split * tl.kb_per_split, kb1 = min(num_kb, kb0 + tl.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           wait_t(empty_bar(stage), phase ^ 1u, w0);
           const uint32_t sa = base + stage * L::kStageBytes;
           const uint32_t sb = sa + L::kABytes;
-          mbar_expect_tx(full_bar(stage), L::kStageBytes);
-          if (a_mn == 0) {
-            tma_load_2d(sa, &tmA, kb * kBK, m0, full_bar(stage));
-          } else if (a_mn == 2) {
-            tma_load_3d(sa, &tmA, 0, kb * kBK, m0 >> 5, full_bar(stage));
-          } else {
+          if (is_a) {
+            mbar_expect_tx(full_bar(stage), L::kABytes);
+            if (a_mn == 0) {
+              tma_load_2d(sa, &tmA, kb * kBK, m0, full_bar(stage));
+            } else if (a_mn == 2) {
+              tma_load_3d(sa, &tmA, 0, kb * kBK, m0 >> 5, full_bar(stage));
+            } else {
 #pragma unroll
-            for (int j = 0; j < kBM / 32; ++j) tma_load_2d(sa + j * (kBK * 128), &tmA, m0 + 32 * j, kb * kBK, full_bar(stage));
-          }
-          if (b_mn == 0) {
-            tma_load_2d(sb, &tmB, kb * kBK, n0, full_bar(stage));
-          } else if (b_mn == 2) {
-            tma_load_3d(sb, &tmB, 0, kb * kBK, n0 >> 5, full_bar(stage));
+              for (int j = 0; j < kBM / 32; ++j) tma_load_2d(sa + j * (kBK * 128), &tmA, m0 + 32 * j, kb * kBK, full_bar(stage));
+            }
           } else {
+            mbar_expect_tx(full_bar(stage), L::kBBytes);
+            if (b_mn == 0) {
+              tma_load_2d(sb, &tmB, kb * kBK, n0, full_bar(stage));
+            } else if (b_mn == 2) {
+              tma_load_3d(sb, &tmB, 0, kb * kBK, n0 >> 5, full_bar(stage));
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * (kBK * 128), &tmB, n0 + 32 * j, kb * kBK, full_bar(stage));
+              for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * (kBK * 128), &tmB, n0 + 32 * j, kb * kBK, full_bar(stage));
+            }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
+      if (trace && is_a) { trace[blockIdx.x * 8 + 0] = w0; trace[blockIdx.x * 8 + 7] = (unsigned long long)(clock64() - t_start); }
     }
-    if (trace && lane == 0) { trace[blockIdx.x * 8 + 0] = w0; trace[blockIdx.x * 8 + 7] = (unsigned long long)(clock64() - t_start); }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
@@ -239,15 +246,15 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       if (trace) { trace[blockIdx.x * 8 + 1] = w0; trace[blockIdx.x * 8 + 2] = w1; }
     }
-  } else if (warp < kEpiWarp0) {
+  } else if (warp == 2) {
     // ===== column sums of the MN-major B tiles (bias gradient) =====
     // Every CTA of an n-tile sees the same B tiles; the 32 K-rows of each are shared out over the m-tiles (tiles_m = 2 or 4
     // for the Dense layers: 16 or 8 rows per CTA; otherwise m-tile 0 takes them all), so that no CTA's ring is held up by
-    // this role.  Thread t owns 4 consecutive columns: chunk t>>3 (32 columns, 4 KB apart), 32-byte atom (t>>1)&3, half t&1;
-    // a quarter-warp reads one contiguous 128-byte row per LDS.128 (conflict-free under the 32-byte-atom swizzle).
+    // this role.  Thread t owns two groups of 4 consecutive columns, 128 columns apart: chunk (t>>3) + 4i (32 columns, 4 KB
+    // apart), 32-byte atom (t>>1)&3, half t&1; a quarter-warp reads one contiguous 128-byte row per LDS.128 (conflict-free under
+    // the 32-byte-atom swizzle).
     if (do_colsum) {
-      const int tid = threadIdx.x - 64;  // 0..63
-      const int chunk = tid >> 3, atom = (tid >> 1) & 3, half = tid & 1;
+      const int chunk0 = lane >> 3, atom = (lane >> 1) & 3, half = lane & 1;
       const bool share = (32 % tl.tiles_m) == 0;
       const int rows_per = share ? 32 / tl.tiles_m : 32;
       int stage = 0;
@@ -255,19 +262,24 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int split = tile / tiles_mn, r = tile - split * tiles_mn;
         const int mt = r / tl.tiles_n;
-        const bool active = (share || mt == 0) && chunk < BN / 32;
+        const bool active = share || mt == 0;
         const int k_first = share ? mt * rows_per : 0;
         const int n0 = (r % tl.tiles_n) * BN;
         const int kb0 = split * tl.kb_per_split, kb1 = min(num_kb, kb0 + tl.kb_per_split);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 acc[BN / 128];
+#pragma unroll
+        for (int i = 0; i < BN / 128; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           if (active) {
-            const uint8_t* cb = base_ptr + stage * L::kStageBytes + L::kABytes + chunk * (kBK * 128) + half * 16;
-#pragma unroll 8
+            const uint8_t* cb = base_ptr + stage * L::kStageBytes + L::kABytes + chunk0 * (kBK * 128) + half * 16;
+#pragma unroll 4
             for (int k = k_first; k < k_first + rows_per; ++k) {
-              const float4 v = *reinterpret_cast<const float4*>(cb + k * 128 + ((atom ^ (k & 3)) << 5));
-              acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+#pragma unroll
+              for (int i = 0; i < BN / 128; ++i) {
+                const float4 v = *reinterpret_cast<const float4*>(cb + i * 4 * (kBK * 128) + k * 128 + ((atom ^ (k & 3)) << 5));
+                acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
+              }
             }
           }
           __syncwarp();
@@ -275,10 +287,13 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         if (active) {
-          const int col = n0 + chunk * 32 + atom * 8 + half * 4;
-          if (col < N) {  // N is a multiple of 4
-            atomicAdd(colsum + col, acc.x); atomicAdd(colsum + col + 1, acc.y);
-            atomicAdd(colsum + col + 2, acc.z); atomicAdd(colsum + col + 3, acc.w);
+#pragma unroll
+          for (int i = 0; i < BN / 128; ++i) {
+            const int col = n0 + (chunk0 + 4 * i) * 32 + atom * 8 + half * 4;
+            if (col < N) {  // N is a multiple of 4
+              atomicAdd(colsum + col, acc[i].x); atomicAdd(colsum + col + 1, acc[i].y);
+              atomicAdd(colsum + col + 2, acc[i].z); atomicAdd(colsum + col + 3, acc[i].w);
+            }
           }
         }
       }

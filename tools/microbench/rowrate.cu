@@ -36,26 +36,32 @@ __global__ void __launch_bounds__(128, 1) stg_kernel(float* out, int rows, int c
 }
 
 __global__ void __launch_bounds__(128, 1) tload_kernel(const __grid_constant__ CUtensorMap tm, int rows, int cols, int box_rows, int stages, int iters,
-                                                       unsigned long long* sink) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) unsigned long long bars[8];
+                                                       unsigned long long* sink, int poll, int issuers) {
+  extern __shared__ __align__(1024) uint8_t smem_all[];
+  __shared__ __align__(8) unsigned long long bars_all[32];
+  const int wid = threadIdx.x >> 5;
+  uint8_t* smem = smem_all + (size_t)wid * stages * (32 * box_rows * 4);
+  unsigned long long* bars = bars_all + wid * 8;
   const int chunk = 32 * box_rows * 4;
-  if (threadIdx.x == 0) {
+  if ((threadIdx.x & 31) == 0 && wid < issuers) {
     for (int s = 0; s < stages; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[s])) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if ((threadIdx.x & 31) == 0 && wid < issuers) {
     const int tiles_c = cols / 32, tiles_r = rows / box_rows;
     const long long ntiles = (long long)tiles_c * tiles_r;
-    long long pos = ((long long)blockIdx.x * 977) % ntiles;
+    long long pos = ((long long)(blockIdx.x * issuers + wid) * 977) % ntiles;
     uint32_t phase = 0;
     for (int it = 0; it <= iters; ++it) {
       for (int s = 0; s < stages; ++s) {
         const uint32_t bar = smem_u32(&bars[s]);
         if (it > 0) {
           uint32_t done = 0;
-          while (!done) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+          if (poll)  // non-blocking test in a spin loop instead of the (potentially suspending) try_wait
+            while (!done) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+          else
+            while (!done) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(phase) : "memory");
         }
         if (it < iters) {
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(chunk) : "memory");
@@ -64,7 +70,7 @@ __global__ void __launch_bounds__(128, 1) tload_kernel(const __grid_constant__ C
                            smem_u32(smem + (size_t)s * chunk)),
                        "l"(reinterpret_cast<uint64_t>(&tm)), "r"(c0), "r"(r0), "r"(bar)
                        : "memory");
-          pos = (pos + gridDim.x) % ntiles;
+          pos = (pos + (long long)gridDim.x * issuers) % ntiles;
         }
       }
       if (it > 0) phase ^= 1u;
@@ -91,7 +97,7 @@ int main(int argc, char** argv) {
     printf("stg.v4 coalesced 32x32 chunks, cols %d, 4 warps: %.1f GB/s aggregate, %.1f GB/s per SM (%.3f ms) %s\n", cols, total / ms / 1e6, total / ms / 1e6 / sms, ms,
            cudaGetErrorString(cudaGetLastError()));
   } else {
-    const int box_rows = argc > 3 ? atoi(argv[3]) : 128, stages = argc > 4 ? atoi(argv[4]) : 4;
+    const int box_rows = argc > 3 ? atoi(argv[3]) : 128, stages = argc > 4 ? atoi(argv[4]) : 4, poll = argc > 5 ? atoi(argv[5]) : 0, issuers = argc > 6 ? atoi(argv[6]) : 1;
     void* p = nullptr; cudaDriverEntryPointQueryResult q;
     cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
     CUtensorMap tm;
@@ -102,14 +108,14 @@ int main(int argc, char** argv) {
     if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); return 1; }
     unsigned long long* sink; cudaMalloc(&sink, 148 * 8);
     const int chunk = 32 * box_rows * 4;
-    cudaFuncSetAttribute(tload_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stages * chunk);
+    cudaFuncSetAttribute(tload_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, issuers * stages * chunk);
     const int iters = 600;
     for (int rep = 0; rep < 3; ++rep) {
-      cudaEventRecord(a); tload_kernel<<<sms, 128, stages * chunk>>>(tm, rows, cols, box_rows, stages, iters, sink); cudaEventRecord(b); cudaEventSynchronize(b);
+      cudaEventRecord(a); tload_kernel<<<sms, 128, issuers * stages * chunk>>>(tm, rows, cols, box_rows, stages, iters, sink, poll, issuers); cudaEventRecord(b); cudaEventSynchronize(b);
       cudaEventElapsedTime(&ms, a, b);
     }
-    const double total = (double)sms * iters * stages * chunk;
-    printf("tensor load 32 x %d boxes (%d KB) x %d stages, cols %d: %.1f GB/s aggregate, %.1f GB/s per SM (%.3f ms) %s\n", box_rows, chunk / 1024, stages, cols,
+    const double total = (double)sms * iters * stages * chunk * issuers;
+    printf("tensor load%s 32 x %d boxes (%d KB) x %d stages, cols %d: %.1f GB/s aggregate, %.1f GB/s per SM (%.3f ms) %s\n", issuers > 1 ? " [several issuing warps]" : (poll ? " [test_wait polling]" : ""), box_rows, chunk / 1024, stages, cols,
            total / ms / 1e6, total / ms / 1e6 / sms, ms, cudaGetErrorString(cudaGetLastError()));
   }
   return 0;
