@@ -46,10 +46,11 @@ __device__ __forceinline__ void epilogue_store4(float (&v)[4], int row, int col,
 // ------------------------------------------------------------------------------------------------- tcgen05 kernel
 // Persistent, warp-specialised: one CTA per SM loops over output tiles (n fastest, so CTAs running together share
 // A tiles through L2).  Roles (8 warps):
-//   warp 0      TMA producer: A/B operand tiles -> kStages-deep shared-memory ring (mbarrier full/empty)
+//   warp 0      TMA producer of the A half of every stage of the kStages-deep shared-memory ring (mbarrier full/empty)
+//   warp 3      TMA producer of the B half (one issuing thread gets a box out only every ~600 cycles: two issuers, one box each)
 //   warp 1      MMA issuer: one thread issues tcgen05.mma kind::tf32 into one of two TMEM accumulators
-//   warp 2      TMEM allocator; with warp 3 the optional column-sum role (bias gradients of wgrad GEMMs: sums the
-//               MN-major B tiles while they sit in shared memory, so dY is never re-read from HBM)
+//   warp 2      TMEM allocator; optional column-sum role (bias gradients of wgrad GEMMs: sums the MN-major B tiles while they
+//               sit in shared memory, so dY is never re-read from HBM)
 //   warps 4-7   epilogue: TMEM -> registers -> fused ops -> swizzled shared staging -> TMA store (or TMA reduce-add
 //               for split-K); the residual / ReLU-mask operand arrives by TMA as well, one 32x32 chunk ahead.
 // The epilogue of tile i overlaps the main loop of tile i+1 through the double-buffered accumulator.
