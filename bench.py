@@ -280,8 +280,18 @@ def main():
     # activations and K = 256..512 these GEMMs sit below the ridge point, so the binding roofline is HBM: achieved =
     # algorithmic bytes of the step's GEMM launches (each operand and output once, counted by the engine) / their summed
     # CUDA-event time on the launching stream.  The tensor-pipe view of the same launches is given beside it.
+    # measured DRAM bytes per launch of the same kernel class, from the committed ncu pass over one step of this workload
+    # (profiles/kernel_traffic.json, written by tools/summarize_launches.py); null when that capture is absent
+    traffic, traffic_src = None, None
+    try:
+        kt = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
+        traffic = kt["classes"]["gemm"]["dram_bytes_per_launch"]
+        traffic_src = "profiles/kernel_traffic.json: " + kt["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "gemm_tf32_tcgen05", "achieved": gemm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gemm_gbs / hbm_peak,
-                "traffic": None, "peak_source": src + " hbm_gbs",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": gemm_bytes / max(gemm_launches, 1), "peak_source": src + " hbm_gbs",
                 "gemm_ms_per_step": gemm_ms / prof_steps, "gemm_launches_per_step": gemm_launches // prof_steps,
                 "gemm_algorithmic_bytes_per_step": gemm_bytes / prof_steps,
                 "tensor": {"achieved": gemm_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": gemm_tflops / tensor_peak,
