@@ -252,8 +252,7 @@ static int gemm(mfp_engine* h, const float* A, int a_mn, int lda, const float* B
 // split-K factor of a weight-gradient GEMM (K = tokens): enough CTAs for ~2 per SM
 // The GEMM is persistent (one CTA per SM, 128 x 256 tiles): pick the largest split count that still fits one wave.
 static int wgrad_splits(int M, int N, int K) {
-  static const bool bn128 = getenv("FLEXDM_GEMM_BN128") != nullptr;
-  const int bn = (N <= 128 || bn128) ? 128 : 256;
+  const int bn = (N <= 128) ? 128 : 256;
   const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
   int s = 148 / tiles;
   const int kb = (K + 31) / 32;

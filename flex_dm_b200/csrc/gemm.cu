@@ -663,9 +663,8 @@ int launch_gemm(TensorMapCache* cache, const GemmCall& c, int impl, cudaStream_t
   }
   const int epi = (c.ep.bias ? kEpiBias : 0) | (c.ep.relu ? kEpiRelu : 0) | (c.ep.residual ? kEpiResidual : 0) | (c.ep.relu_src ? kEpiReluMask : 0) |
                   (c.ep.drop_enabled ? kEpiDropout : 0) | (c.ep.rowflag ? kEpiRowflag : 0);
-  static const bool bn128 = getenv("FLEXDM_GEMM_BN128") != nullptr;  // experiment: 128 x 128 tiles everywhere (deeper ring, more A bytes in flight)
 #define MFP_GEMM_CASE(E) \
-  case (E): return (c.N <= 128 || bn128) ? launch_tcgen05<128, (E)>(cache, c, stream) : launch_tcgen05<256, (E)>(cache, c, stream);
+  case (E): return (c.N <= 128) ? launch_tcgen05<128, (E)>(cache, c, stream) : launch_tcgen05<256, (E)>(cache, c, stream);
   switch (epi) {
     MFP_GEMM_CASE(0)                                           // dgrad / wgrad
     MFP_GEMM_CASE(kEpiBias)                                    // QKV, heads
