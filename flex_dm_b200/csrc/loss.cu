@@ -70,17 +70,20 @@ __global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ Schem
   const int type_true = reinterpret_cast<const int*>(targets.cols[sc.type_field])[tt * sc.f[sc.type_field].C];
   const float* lrow = logits + tp * sc.LW;
   float* drow = dlogits ? dlogits + tp * sc.LW : nullptr;
-  if (drow)
-    for (int c = sc.LWu + lane; c < sc.LW; c += 32) drow[c] = 0.f;  // row padding
+  if (drow) {
+    // The gradient row is zero except under the (15 % or so of) fields this element is masked in: clear it once with 16-byte
+    // stores (LW is a multiple of 32 floats), then only the active fields write their entries.
+    float4* d4 = reinterpret_cast<float4*>(drow);
+    for (int c = lane; c < sc.LW / 4; c += 32) d4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+  }
   for (int f = 0; f < sc.F; ++f) {
     const FieldDev& fd = sc.f[f];
     // metrics.py:251-267: mfp mask (unsorted position) x type gate (sorted target) x seq mask
     const bool w = valid && masks.m[f][t] && (!fd.has_cond || ((fd.cond_mask >> type_true) & 1ull));
-    const int padded_w = (fd.logit_w + 3) & ~3;
     float loss = 0.f, score = 0.f, den = 0.f;
     if (!w) {
-      if (drow)
-        for (int c = lane; c < padded_w; c += 32) drow[fd.logit_off + c] = 0.f;
+      // nothing to add: the row was cleared above
     } else if (fd.kind == 0) {
       const int V = fd.input_dim;
       for (int c = 0; c < fd.C; ++c) {
@@ -151,8 +154,6 @@ __global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ Schem
         }
         (void)py;
       }
-      if (drow)
-        for (int c = fd.logit_w + lane; c < padded_w; c += 32) drow[fd.logit_off + c] = 0.f;
     } else {
       // metrics.py:52-57,246-248: sum_d (yhat - y)^2; score = 0.5 cos + 0.5 (l2_normalize eps 1e-12)
       const float* y = reinterpret_cast<const float*>(targets.cols[f]) + tt * fd.C;
@@ -170,8 +171,6 @@ __global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ Schem
       loss = sq;
       score = 0.5f * xy * rsqrtf(fmaxf(yy, 1e-12f)) * rsqrtf(fmaxf(xx, 1e-12f)) + 0.5f;
       den = 1.f;
-      if (drow)
-        for (int c = fd.C + lane; c < padded_w; c += 32) drow[fd.logit_off + c] = 0.f;
     }
     if (lane == 0) {
       buf.part[((size_t)0 * sc.F + f) * T + t] = loss;

@@ -18,13 +18,28 @@ __global__ void __launch_bounds__(256) var_norms_kernel(const VarDev* __restrict
   const int per = (n + kNormChunks - 1) / kNormChunks;
   const int i0 = blockIdx.y * per, i1 = min(n, i0 + per);
   float sg = 0.f, sw = 0.f;
-  for (int i = i0 + threadIdx.x; i < i1; i += 256) {
-    const int r = i / v.cols, c = i - r * v.cols;
-    const size_t idx = (size_t)v.off + (size_t)r * v.ld + c;
-    const float w = params[idx];
-    const float g = (grads ? grads[idx] : 0.f) + k * w;
-    sg += g * g;
-    sw += w * w;
+  if (((v.cols | v.ld) & 3) == 0 && (v.off & 3) == 0) {  // 16-byte path: whole float4s of a row (all Dense kernels, tables, biases of width % 4 == 0)
+    const int c4 = v.cols >> 2, n4 = v.rows * c4;
+    const int per4 = (n4 + kNormChunks - 1) / kNormChunks;
+    const int j0 = blockIdx.y * per4, j1 = min(n4, j0 + per4);
+    for (int j = j0 + threadIdx.x; j < j1; j += 256) {
+      const int r = j / c4, c = (j - r * c4) << 2;
+      const size_t idx = (size_t)v.off + (size_t)r * v.ld + c;
+      const float4 w = *reinterpret_cast<const float4*>(params + idx);
+      float4 g = grads ? *reinterpret_cast<const float4*>(grads + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      g.x += k * w.x; g.y += k * w.y; g.z += k * w.z; g.w += k * w.w;
+      sg += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
+      sw += w.x * w.x + w.y * w.y + w.z * w.z + w.w * w.w;
+    }
+  } else {
+    for (int i = i0 + threadIdx.x; i < i1; i += 256) {
+      const int r = i / v.cols, c = i - r * v.cols;
+      const size_t idx = (size_t)v.off + (size_t)r * v.ld + c;
+      const float w = params[idx];
+      const float g = (grads ? grads[idx] : 0.f) + k * w;
+      sg += g * g;
+      sw += w * w;
+    }
   }
   sg = warp_sum(sg);
   sw = warp_sum(sw);
@@ -59,16 +74,35 @@ __global__ void __launch_bounds__(256) adam_kernel(const VarDev* __restrict__ va
 #pragma unroll
   for (int c = 0; c < kNormChunks; ++c) nsq += norms[(blockIdx.x * kNormChunks + c) * 2];
   const float scale = (clipnorm > 0.f) ? clipnorm / fmaxf(sqrtf(nsq), clipnorm) : 1.0f;  // tf.clip_by_norm (A4)
-  for (int i = blockIdx.y * 256 + threadIdx.x; i < n; i += gridDim.y * 256) {
-    const int r = i / v.cols, c = i - r * v.cols;
-    const size_t idx = (size_t)v.off + (size_t)r * v.ld + c;
-    const float w = params[idx];
-    const float g = (grads[idx] + k * w) * scale;
-    const float mi = kAdamB1 * m[idx] + (1.0f - kAdamB1) * g;
-    const float vi = kAdamB2 * vv[idx] + (1.0f - kAdamB2) * g * g;
-    m[idx] = mi;
-    vv[idx] = vi;
-    params[idx] = w - alpha * mi / (sqrtf(vi) + kAdamEps);  // A5
+  auto update = [&](float w, float g, float& mi, float& vi) {
+    g = (g + k * w) * scale;
+    mi = kAdamB1 * mi + (1.0f - kAdamB1) * g;
+    vi = kAdamB2 * vi + (1.0f - kAdamB2) * g * g;
+    return w - alpha * mi / (sqrtf(vi) + kAdamEps);  // A5
+  };
+  if (((v.cols | v.ld) & 3) == 0 && (v.off & 3) == 0) {  // 16-byte path (same element-wise arithmetic)
+    const int c4 = v.cols >> 2, n4 = v.rows * c4;
+    for (int j = blockIdx.y * 256 + threadIdx.x; j < n4; j += gridDim.y * 256) {
+      const int r = j / c4, c = (j - r * c4) << 2;
+      const size_t idx = (size_t)v.off + (size_t)r * v.ld + c;
+      float4 w = *reinterpret_cast<const float4*>(params + idx);
+      const float4 g = *reinterpret_cast<const float4*>(grads + idx);
+      float4 mi = *reinterpret_cast<const float4*>(m + idx), vi = *reinterpret_cast<const float4*>(vv + idx);
+      w.x = update(w.x, g.x, mi.x, vi.x); w.y = update(w.y, g.y, mi.y, vi.y);
+      w.z = update(w.z, g.z, mi.z, vi.z); w.w = update(w.w, g.w, mi.w, vi.w);
+      *reinterpret_cast<float4*>(m + idx) = mi;
+      *reinterpret_cast<float4*>(vv + idx) = vi;
+      *reinterpret_cast<float4*>(params + idx) = w;
+    }
+  } else {
+    for (int i = blockIdx.y * 256 + threadIdx.x; i < n; i += gridDim.y * 256) {
+      const int r = i / v.cols, c = i - r * v.cols;
+      const size_t idx = (size_t)v.off + (size_t)r * v.ld + c;
+      float mi = m[idx], vi = vv[idx];
+      params[idx] = update(params[idx], grads[idx], mi, vi);
+      m[idx] = mi;
+      vv[idx] = vi;
+    }
   }
 }
 
