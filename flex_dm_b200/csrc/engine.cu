@@ -49,6 +49,7 @@ struct mfp_engine {
   Workspace off{};
   float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
   TensorMapCache* maps = nullptr;
+  std::vector<long long> stage_lo, stage_hi;  // flat-buffer range whose gradients are final after backward stage s (see mfp_backward_stages)
   const void* flags_for = nullptr;  // modified column (first numerical field) the workspace row flags were just derived from
   int gemm_impl = 0;
   int64_t launches = 0;
@@ -110,10 +111,16 @@ static void build_layout(mfp_engine* h) {
       add_var(h, base + "/bias", fd.bias_off, 1, D, D, 1);
     }
   }
+  // backward stages: 0 = heads, 1..L = blocks L-1..0, L+1 = encoder; the layout is encoder | blocks | heads, each contiguous
+  h->stage_lo.assign(L + 2, 0);
+  h->stage_hi.assign(L + 2, 0);
+  h->stage_lo[L + 1] = 0;
+  h->stage_hi[L + 1] = cur;
   // blocks (transformer.py:54-57,161-173); Q|K|V kernels share one [D, 3D] matrix so the projection is one GEMM
   h->blocks.resize(L);
   for (int i = 0; i < L; ++i) {
     BlockLayout& b = h->blocks[i];
+    h->stage_lo[L - i] = cur;
     b.wqkv = alloc(3LL * D * D); b.bqkv = alloc(3 * D);
     b.wo = alloc((long long)D * D); b.bo = alloc(D);
     b.w1 = alloc((long long)D * kF); b.b1 = alloc(kF);
@@ -137,7 +144,9 @@ static void build_layout(mfp_engine* h) {
     add_var(h, s + "/norm1/beta", b.be1, 1, D, D, 0);
     add_var(h, s + "/norm2/gamma", b.g2, 1, D, D, 0);
     add_var(h, s + "/norm2/beta", b.be2, 1, D, D, 0);
+    h->stage_hi[L - i] = cur;
   }
+  h->stage_lo[0] = cur;
   // decoder heads (decoder.py:32-43), concatenated into one [D, LW] matrix
   h->wh = alloc((long long)D * sc.LW);
   h->bh = alloc(sc.LW);
@@ -148,6 +157,7 @@ static void build_layout(mfp_engine* h) {
     add_var(h, base + "/bias", h->bh + fd.logit_off, 1, fd.logit_w, sc.LW, 1);
   }
   h->param_count = cur;
+  h->stage_hi[0] = cur;
 }
 
 static Workspace plan_workspace(const mfp_engine* h, int B, int S) {
@@ -500,9 +510,24 @@ int mfp_loss(mfp_engine* h, const mfp_batch* targets, const uint8_t* const* mask
   return launch_loss(h->sc, tg, mp, logits, use_sort, h->B, h->S, inv_batch, compute_grad ? wsp<float>(h, h->off.dlogits) : nullptr, buf, metrics_out, st);
 }
 
+int32_t mfp_backward_num_stages(const mfp_engine* h) { return h ? h->cfg.num_blocks + 2 : 0; }
+
+int mfp_backward_stage_range(const mfp_engine* h, int32_t stage, int64_t* lo, int64_t* hi) {
+  if (!h || !lo || !hi || stage < 0 || stage >= h->cfg.num_blocks + 2) { set_error("mfp_backward_stage_range: bad argument"); return MFP_ERR_ARG; }
+  *lo = h->stage_lo[stage];
+  *hi = h->stage_hi[stage];
+  return MFP_OK;
+}
+
 int mfp_backward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint32_t seed, uint32_t step, void* stream) {
+  return mfp_backward_stages(h, modified, training, seed, step, 0, h ? h->cfg.num_blocks + 1 : 0, stream);
+}
+
+int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t training, uint32_t seed, uint32_t step, int32_t first_stage,
+                        int32_t last_stage, void* stream) {
   MFP_TRY(check_bound(h));
   if (!h->grads) { set_error("mfp_backward: no gradient buffer bound"); return MFP_ERR_STATE; }
+  if (first_stage < 0 || last_stage > h->cfg.num_blocks + 1 || first_stage > last_stage) { set_error("mfp_backward_stages: bad stage range"); return MFP_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   const Schema& sc = h->sc;
   const int T = h->T, D = kD, L = h->cfg.num_blocks;
@@ -520,11 +545,14 @@ int mfp_backward(mfp_engine* h, const mfp_batch* modified, int32_t training, uin
   float* dhid = wsp<float>(h, h->off.dhid);
   float* dattn = wsp<float>(h, h->off.dattn);
 
-  MFP_CUDA_OK(cudaMemsetAsync(G, 0, (size_t)h->param_count * sizeof(float), st));
-  // ---- heads: dX = dlogits . Wh^T ; dWh = X^T . dlogits ; dbh = colsum(dlogits)
-  MFP_TRY(gemm(h, dlogits, 0, sc.LW, P + h->wh, 0, sc.LW, T, D, sc.LW, make_epilogue(dx, D), 1, st));
-  MFP_TRY(gemm(h, x + L * TD, 1, D, dlogits, 1, sc.LW, D, sc.LW, T, make_epilogue(G + h->wh, sc.LW), wgrad_splits(D, sc.LW, T), st, G + h->bh));
+  if (first_stage == 0) {
+    MFP_CUDA_OK(cudaMemsetAsync(G, 0, (size_t)h->param_count * sizeof(float), st));
+    // ---- heads: dX = dlogits . Wh^T ; dWh = X^T . dlogits ; dbh = colsum(dlogits)
+    MFP_TRY(gemm(h, dlogits, 0, sc.LW, P + h->wh, 0, sc.LW, T, D, sc.LW, make_epilogue(dx, D), 1, st));
+    MFP_TRY(gemm(h, x + L * TD, 1, D, dlogits, 1, sc.LW, D, sc.LW, T, make_epilogue(G + h->wh, sc.LW), wgrad_splits(D, sc.LW, T), st, G + h->bh));
+  }
   for (int i = L - 1; i >= 0; --i) {
+    if (L - i < first_stage || L - i > last_stage) continue;  // stage L - i
     const BlockLayout& b = h->blocks[i];
     const float* xi = x + i * TD;
     const float* ln1 = wsp<float>(h, h->off.ln1) + i * TD;
@@ -574,6 +602,7 @@ int mfp_backward(mfp_engine* h, const mfp_batch* modified, int32_t training, uin
                                    h->cfg.dropout, seed, step, kSiteDropout + 2 * (i - 1) + 1));
     h->launches += 3;
   }
+  if (last_stage < L + 1) return MFP_OK;
   // ---- encoder: table / special / bias rows by a one-hot wgrad GEMM; Dense kernels by X^T . (dh0 with special-token rows zeroed) (encoder.cu)
   const unsigned char* flags = wsp<unsigned char>(h, h->off.flags);
   float* onehot = wsp<float>(h, h->off.onehot);

@@ -42,6 +42,10 @@ __global__ void __launch_bounds__(256) mask_corrupt_kernel(const __grid_constant
     const U4 r = philox4x32_10((uint32_t)b, kFieldElem, 0u, 0u, seed, step);
     elem_sel = (int)(u01(r.x) * (float)n_valid);
   }
+  // random_masking draws three uniforms per (element, field): lane f computes the Philox block of field f once and the field
+  // loop broadcasts it (every lane recomputing every field's block was a third of this kernel's time)
+  U4 rf = {0u, 0u, 0u, 0u};
+  if (task == 0 && lane < sc.F) rf = philox4x32_10((uint32_t)t, (uint32_t)lane, kStreamRandomU, 0u, seed, step);
   for (int f = 0; f < sc.F; ++f) {
     const FieldDev fd = sc.f[f];
     // filter_padding (masking.py:24-53)
@@ -51,11 +55,11 @@ __global__ void __launch_bounds__(256) mask_corrupt_kernel(const __grid_constant
     if (mode == 1) {
       mfp = test_masks.m[f][t] != 0;
       action = mfp ? 1 : 0;
-    } else if (task == 0) {  // random_masking (masking.py:227-269)
-      const U4 r = philox4x32_10((uint32_t)t, (uint32_t)f, kStreamRandomU, 0u, seed, step);
-      mfp = valid && (u01(r.x) < kMaskProb);
-      const bool chg = mfp && (u01(r.y) < kChangeProb);
-      if (chg) action = (u01(r.z) >= kThresh) ? 1 : 2;
+    } else if (task == 0) {  // random_masking (masking.py:227-269); task is uniform over the warp (one document)
+      const uint32_t rx = __shfl_sync(0xffffffffu, rf.x, f), ry = __shfl_sync(0xffffffffu, rf.y, f), rz = __shfl_sync(0xffffffffu, rf.z, f);
+      mfp = valid && (u01(rx) < kMaskProb);
+      const bool chg = mfp && (u01(ry) < kChangeProb);
+      if (chg) action = (u01(rz) >= kThresh) ? 1 : 2;
     } else if (task == 1) {  // elem_masking (masking.py:136-155)
       mfp = (s == elem_sel);
       action = mfp ? 1 : 0;

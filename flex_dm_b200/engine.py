@@ -7,7 +7,7 @@ call fails this module raises.
 import ctypes
 import os
 from collections import OrderedDict
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -68,6 +68,10 @@ _SIGNATURES = {
     "mfp_loss": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Batch), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_void_p,
                                 ctypes.c_void_p, ctypes.c_float, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
     "mfp_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Batch), ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]),
+    "mfp_backward_num_stages": (ctypes.c_int32, [ctypes.c_void_p]),
+    "mfp_backward_stage_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
+    "mfp_backward_stages": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Batch), ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int32,
+                                           ctypes.c_int32, ctypes.c_void_p]),
     "mfp_optimizer_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
     "mfp_regularization_loss": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "mfp_merge_prediction": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -306,6 +310,22 @@ class Engine:
         b = self._batch(length, self.modified if cols is None else cols)
         _check(self.lib, self.lib.mfp_backward(self.handle, ctypes.byref(b), 1 if training else 0, seed & 0xFFFFFFFF, step & 0xFFFFFFFF, _stream()),
                "mfp_backward")
+
+    def backward_stages(self, length, first_stage: int, last_stage: int, cols: Optional[List[torch.Tensor]] = None, training: bool = True, seed: int = 0,
+                        step: int = 0):
+        """Stages ``first_stage..last_stage`` of the backward pass (0 = heads, 1..L = blocks L-1..0, L+1 = encoder), ascending, once per step."""
+        b = self._batch(length, self.modified if cols is None else cols)
+        _check(self.lib, self.lib.mfp_backward_stages(self.handle, ctypes.byref(b), 1 if training else 0, seed & 0xFFFFFFFF, step & 0xFFFFFFFF,
+                                                      int(first_stage), int(last_stage), _stream()), "mfp_backward_stages")
+
+    def backward_stage_ranges(self) -> List[Tuple[int, int]]:
+        """``[lo, hi)`` of the flat gradient buffer that is final after each backward stage."""
+        out = []
+        for s in range(int(self.lib.mfp_backward_num_stages(self.handle))):
+            lo, hi = ctypes.c_int64(), ctypes.c_int64()
+            _check(self.lib, self.lib.mfp_backward_stage_range(self.handle, s, ctypes.byref(lo), ctypes.byref(hi)), "mfp_backward_stage_range")
+            out.append((int(lo.value), int(hi.value)))
+        return out
 
     def optimizer_step(self, t: int, learning_rate: float, clipnorm: Optional[float], l2_out: Optional[torch.Tensor] = None):
         _check(self.lib, self.lib.mfp_optimizer_step(self.handle, int(t), float(learning_rate), float(clipnorm) if clipnorm else 0.0, _ptr(l2_out),

@@ -22,7 +22,7 @@ import torch
 
 from .engine import Engine
 from .masking import get_task_names
-from .parallel import all_reduce_gradients, broadcast_parameters, reduce_metric_rows
+from .parallel import all_reduce_gradient_slice, broadcast_parameters, reduce_metric_rows
 from .spec import get_dataset_name, get_valid_input_columns
 
 logger = logging.getLogger(__name__)
@@ -126,6 +126,7 @@ class MFP:
         """Shard batches over documents; one all-reduce of the flat gradient buffer per step."""
         self._dist = dist_module
         self._world = int(world_size)
+        self._stage_ranges = self.engine.backward_stage_ranges()
         broadcast_parameters(dist_module, self.engine.params, 0)  # every rank starts from rank 0's initialisation
 
     # ------------------------------------------------------------------ Keras surface
@@ -205,9 +206,17 @@ class MFP:
         eng.mask_corrupt(length, cols, tasks, seed, step)
         eng.forward(length, None, True, seed, step)
         eng.loss(length, cols, eng.masks, row, 1.0 / (B * self._world), True, sort_tasks=tasks if self.sort_pos else None)
-        eng.backward(length, None, True, seed, step)
         if self._world > 1:
-            all_reduce_gradients(self._dist, eng.grads)
+            # staged backward: each stage's gradient slice starts its all-reduce as soon as it is final (heads first, encoder last)
+            works = []
+            for s, (lo, hi) in enumerate(self._stage_ranges):
+                eng.backward_stages(length, s, s, None, True, seed, step)
+                works.append(all_reduce_gradient_slice(self._dist, eng.grads, lo, hi))
+            for w in works:
+                if w is not None:
+                    w.wait()
+        else:
+            eng.backward(length, None, True, seed, step)
         self.optimizer.iterations += 1
         eng.optimizer_step(self.optimizer.iterations, self.optimizer.learning_rate, self.optimizer.clipnorm, row[-1:])
         self._step += 1

@@ -6,7 +6,9 @@ mean of per-document sums (metrics.py:265-277), so:
 
 * every rank takes a contiguous slice of the global batch (``shard_documents``),
 * computes gradients of ``(1 / B_global) * sum over its documents`` (``inv_batch`` of ``mfp_loss``),
-* ONE ``all_reduce(sum)`` of the flat fp32 gradient buffer gives the global-batch gradient (``all_reduce_gradients``),
+* ``all_reduce(sum)`` of the flat fp32 gradient buffer gives the global-batch gradient: in one piece (``all_reduce_gradients``) or,
+  as the train step does, one contiguous slice per backward stage started as soon as that stage's gradients are final
+  (``all_reduce_gradient_slice``), so that the exchange runs under the rest of the backward pass,
 * L2, per-variable clipnorm and Adam run after the reduce on every rank (replicated state), exactly the
   single-process semantics because clipping sees the reduced gradient,
 * loss / score numerators / denominators are additive, so metric rows are all-reduced too (``reduce_metric_rows``);
@@ -40,6 +42,15 @@ def all_reduce_gradients(dist, flat_grads: torch.Tensor) -> torch.Tensor:
     """One collective per step over the flat gradient buffer (11.25 MB for crello): sum of the ranks' partial gradients."""
     dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
     return flat_grads
+
+
+def all_reduce_gradient_slice(dist, flat_grads: torch.Tensor, lo: int, hi: int):
+    """Start the all-reduce of one finished slice of the flat gradient buffer (a backward stage's variables) without waiting: on
+    NCCL it runs on the communicator's stream under the backward of the layers below.  Returns the work handle; ``wait()`` it (a
+    stream dependency, not a host block) before the optimiser reads the buffer."""
+    if hi <= lo:
+        return None
+    return dist.all_reduce(flat_grads[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
 
 
 def reduce_metric_rows(dist, rows: torch.Tensor) -> torch.Tensor:

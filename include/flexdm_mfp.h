@@ -121,6 +121,16 @@ int mfp_loss(mfp_engine* h, const mfp_batch* targets, const uint8_t* const* mask
  * Writes the flat gradient buffer bound in mfp_bind (overwrites; the L2 term is added in the optimiser). */
 int mfp_backward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint32_t seed, uint32_t step, void* stream);
 
+/* The same backward pass in stages, so that a data-parallel host can start the all-reduce of a layer's gradients while the
+ * layers below are still being differentiated (the reference has no distributed code).
+ * Stage 0 = decoder heads (also clears the gradient buffer), stages 1..L = blocks L-1..0, stage L+1 = encoder.
+ * Stages must run in ascending order, each exactly once per step; mfp_backward == stages 0..L+1.
+ * mfp_backward_stage_range: the half-open range [lo, hi) of the flat gradient buffer that is final once `stage` has run. */
+int32_t mfp_backward_num_stages(const mfp_engine* h);
+int mfp_backward_stage_range(const mfp_engine* h, int32_t stage, int64_t* lo, int64_t* hi);
+int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t training, uint32_t seed, uint32_t step,
+                        int32_t first_stage, int32_t last_stage, void* stream);
+
 /* Adam(learning_rate, clipnorm) apply_gradients (train.py:71-77) + the L2 regularisers' gradient and loss term
  * (architecture/utils.py:8-22): g += 2*l2*w; per-variable clip_by_norm; TF-form Adam.  t = 1-based step.
  * l2_loss_out (device float, optional) receives l2 * sum w^2 evaluated BEFORE the update. */

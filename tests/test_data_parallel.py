@@ -80,7 +80,15 @@ def _worker(rank, world, port, out):
         for k in keys:
             row += [float(losses[k]) * (hi - lo) / B, float(scores[k + "_score_num"]), float(scores[k + "_score_den"])]
         row = torch.tensor([row + [float(total) * (hi - lo) / B, 123.0]], dtype=torch.float64)
-        parallel.all_reduce_gradients(dist, g)
+        # the train step reduces one slice per backward stage, asynchronously; the pieces must add up to the one-shot all-reduce
+        g_once = parallel.all_reduce_gradients(dist, g.clone())
+        n = g.numel()
+        cuts = [0, n // 5, n // 2, n]
+        works = [parallel.all_reduce_gradient_slice(dist, g, cuts[i], cuts[i + 1]) for i in range(3)]
+        assert parallel.all_reduce_gradient_slice(dist, g, 7, 7) is None  # an empty stage has nothing to exchange
+        for w in works:
+            w.wait()
+        assert torch.equal(g, g_once)
         row = parallel.reduce_metric_rows(dist, row)
         out[rank] = (shard["length"].shape[0], float((g - g_full).abs().max() / g_full.abs().max()), float((row - row_full).abs().max()),
                      float(row[0, -1]))

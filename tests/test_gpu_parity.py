@@ -277,6 +277,39 @@ def test_training_dropout_matches_oracle_keep_masks():
         assert H.rel_l2(got_grads[name], grads[name]) <= H.GRAD_REL_L2, name
 
 
+def test_backward_stages_equal_the_monolithic_pass():
+    """mfp_backward_stages (what the data-parallel step runs, one all-reduce slice per stage) == mfp_backward; the stage ranges
+    tile the flat gradient buffer."""
+    cols, m = _model("crello", "random", 2, dropout=0.1)
+    B, S = 4, 16
+    batch = make_synthetic_batch(cols, B, S, seed=2, lengths="ragged")
+    staged = m.stage(batch)
+    _, _, length, dcols = m._bind(staged)
+    eng = m.engine
+    seed, step = 9, 4
+    tasks = eng.sample_tasks(m.task_ids, seed, step).clone()
+    eng.mask_corrupt(length, dcols, tasks, seed, step)
+    eng.forward(length, None, True, seed, step)
+    row = torch.zeros(eng.metrics_width, device="cuda")
+    eng.loss(length, dcols, eng.masks, row, 1.0 / B, True)
+    eng.backward(length, None, True, seed, step)
+    ref = eng.grads.clone()
+    ranges = eng.backward_stage_ranges()
+    assert len(ranges) == 2 + 2
+    spans = sorted(ranges)
+    assert spans[0][0] == 0 and spans[-1][1] == eng.param_count and all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))
+    eng.grads.fill_(float("nan"))
+    final = torch.zeros_like(ref, dtype=torch.bool)
+    for s, (lo, hi) in enumerate(ranges):
+        eng.backward_stages(length, s, s, None, True, seed, step)
+        torch.cuda.synchronize()
+        final[lo:hi] = True
+        got = eng.grads[final]  # everything declared final so far already equals the monolithic result (split-K summation order aside)
+        assert torch.isfinite(got).all()
+        assert float((got - ref[final]).abs().max()) <= 1e-5 * float(ref.abs().max()), s
+    assert bool(final.all())
+
+
 def test_optimizer_step_matches_oracle():
     cols, m = _model("rico", "random", 1)
     eng = m.engine
