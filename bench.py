@@ -96,8 +96,7 @@ def cpu_port_throughput(budget_s=20.0, docs=8, threads=None):
     from flex_dm_b200.spec import make_input_columns, make_synthetic_batch
     from oracle import mfp_oracle as O
 
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     cols = make_input_columns("crello", max_length=SEQ_LEN)
     batch = make_synthetic_batch(cols, docs, SEQ_LEN, seed=0, lengths="full")
     o = O.OracleMFP(cols, num_blocks=NUM_BLOCKS, masking_method="random", dropout=0.1, l2=1e-2, dtype=torch.float32)
@@ -125,6 +124,7 @@ def run_reference(args):
     from flex_dm_b200.spec import make_input_columns, make_synthetic_batch
     from oracle import mfp_oracle as O
 
+    torch.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: take every host core back
     docs = 8
     cols = make_input_columns("crello", max_length=SEQ_LEN)
     batch = make_synthetic_batch(cols, docs, SEQ_LEN, seed=0, lengths="full")

@@ -6,9 +6,9 @@ mean of per-document sums (metrics.py:265-277), so:
 
 * every rank takes a contiguous slice of the global batch (``shard_documents``),
 * computes gradients of ``(1 / B_global) * sum over its documents`` (``inv_batch`` of ``mfp_loss``),
-* ``all_reduce(sum)`` of the flat fp32 gradient buffer gives the global-batch gradient: in one piece (``all_reduce_gradients``) or,
-  as the train step does, one contiguous slice per backward stage started as soon as that stage's gradients are final
-  (``all_reduce_gradient_slice``), so that the exchange runs under the rest of the backward pass,
+* ``all_reduce(sum)`` of the flat fp32 gradient buffer gives the global-batch gradient: in one piece after the backward pass
+  (``all_reduce_gradients``, the default of the train step) or one contiguous slice per backward stage started as soon as that
+  stage's gradients are final (``all_reduce_gradient_slice``, ``MFP.enable_data_parallel(..., overlap=True)``),
 * L2, per-variable clipnorm and Adam run after the reduce on every rank (replicated state), exactly the
   single-process semantics because clipping sees the reduced gradient,
 * loss / score numerators / denominators are additive, so metric rows are all-reduced too (``reduce_metric_rows``);
