@@ -283,6 +283,7 @@ int mfp_create(const mfp_config* cfg, const mfp_field_desc* fields, mfp_engine**
   if (cfg->latent_dim != kD) { set_error("mfp_create: latent_dim must be %d in this build (got %d)", kD, cfg->latent_dim); return MFP_ERR_UNSUPPORTED; }
   if (cfg->num_fields < 1 || cfg->num_fields > kMaxFields) { set_error("mfp_create: num_fields out of range"); return MFP_ERR_ARG; }
   if (cfg->num_blocks < 1 || cfg->num_blocks > 64) { set_error("mfp_create: num_blocks out of range"); return MFP_ERR_ARG; }
+  if (cfg->block_type != 0 && cfg->block_type != 1) { set_error("mfp_create: block_type must be 0 (deepsvg) or 1 (transformer)"); return MFP_ERR_ARG; }
   mfp_engine* h = new mfp_engine();
   h->cfg = *cfg;
   memset(&h->sc, 0, sizeof(h->sc));
@@ -456,6 +457,36 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
     float* stats = wsp<float>(h, h->off.stats) + (size_t)i * 4 * T;
     float* lse = wsp<float>(h, h->off.lse) + (size_t)i * h->B * kH * h->S;
 
+    if (h->cfg.block_type == 1) {
+      // post-LayerNorm TransformerBlock (transformer.py:187-205): z1 = x + drop(attn(x)); x1 = LN1(z1); z2 = x1 + drop(mlp(x1));
+      // out = LN2(z2).  Same buffers under other roles: xmid holds z1, ln2 holds x1, ln1 holds z2.
+      GemmEpilogue q1 = make_epilogue(qkv, 3 * D);
+      q1.bias = P + b.bqkv;
+      MFP_TRY(gemm(h, xi, 0, D, P + b.wqkv, 1, 3 * D, T, 3 * D, D, q1, 1, st));
+      {
+        ProfScope prof(h, MFP_PROFILE_ATTENTION, st, 4.0 * T * (3.0 * D + D) + 4.0 * h->B * kH * h->S);
+        if (h->gemm_impl == 0 && h->S <= 128) MFP_TRY(launch_attention_fwd_tc(h->maps, qkv, modified->length, h->B, h->S, attn, lse, st));
+        else MFP_TRY(launch_attention_fwd(qkv, modified->length, h->B, h->S, attn, lse, st));
+      }
+      GemmEpilogue q2 = make_epilogue(xmid, D);
+      q2.bias = P + b.bo;
+      q2.residual = xi; q2.ldr = D;
+      if (drop) { q2.drop_enabled = 1; q2.drop_rate = h->cfg.dropout; q2.drop_seed = seed; q2.drop_step = step; q2.drop_site = kSiteDropout + 2 * i; }
+      MFP_TRY(gemm(h, attn, 0, D, P + b.wo, 1, D, T, D, D, q2, 1, st));
+      MFP_TRY(launch_layernorm_fwd(xmid, P + b.g1, P + b.be1, T, ln2, stats, stats + T, st));
+      GemmEpilogue q3 = make_epilogue(hid, kF);
+      q3.bias = P + b.b1;
+      q3.relu = 1;
+      MFP_TRY(gemm(h, ln2, 0, D, P + b.w1, 1, kF, T, kF, D, q3, 1, st));
+      GemmEpilogue q4 = make_epilogue(ln1, D);
+      q4.bias = P + b.b2;
+      q4.residual = ln2; q4.ldr = D;
+      if (drop) { q4.drop_enabled = 1; q4.drop_rate = h->cfg.dropout; q4.drop_seed = seed; q4.drop_step = step; q4.drop_site = kSiteDropout + 2 * i + 1; }
+      MFP_TRY(gemm(h, hid, 0, kF, P + b.w2, 1, D, T, D, kF, q4, 1, st));
+      MFP_TRY(launch_layernorm_fwd(ln1, P + b.g2, P + b.be2, T, xo, stats + 2 * T, stats + 3 * T, st));
+      h->launches += 3;
+      continue;
+    }
     MFP_TRY(launch_layernorm_fwd(xi, P + b.g1, P + b.be1, T, ln1, stats, stats + T, st));
     GemmEpilogue e1 = make_epilogue(qkv, 3 * D);
     e1.bias = P + b.bqkv;
@@ -564,6 +595,45 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
     const float* stats = wsp<float>(h, h->off.stats) + (size_t)i * 4 * T;
     const float* lse = wsp<float>(h, h->off.lse) + (size_t)i * h->B * kH * h->S;
 
+    if (h->cfg.block_type == 1) {
+      // post-LayerNorm block, backward of the wiring above.  dx = d(out).
+      //   dz2 = LN2'(dx);  FFN branch on drop2(dz2);  dx1 = dz2 + d(mlp input);  dz1 = LN1'(dx1);  attention branch on drop1(dz1);
+      //   d(block input) = dz1 + d(QKV input)
+      const float* z2 = ln1;
+      const float* x1 = ln2;
+      MFP_TRY(launch_layernorm_bwd(z2, dx, P + b.g2, stats + 2 * T, stats + 3 * T, nullptr, T, dx, G + b.g2, G + b.be2, st, nullptr, 0, nullptr,
+                                   drop ? dyb : nullptr, h->cfg.dropout, seed, step, kSiteDropout + 2 * i + 1));
+      const float* dy2 = drop ? dyb : dx;
+      MFP_TRY(gemm(h, hid, 1, kF, dy2, 1, D, kF, D, T, make_epilogue(G + b.w2, D), wgrad_splits(kF, D, T), st, G + b.b2));
+      GemmEpilogue ph = make_epilogue(dhid, kF);
+      ph.relu_src = hid; ph.ld_relu = kF;
+      MFP_TRY(gemm(h, dy2, 0, D, P + b.w2, 0, D, T, kF, D, ph, 1, st));
+      MFP_TRY(gemm(h, x1, 1, D, dhid, 1, kF, D, kF, T, make_epilogue(G + b.w1, kF), wgrad_splits(D, kF, T), st, G + b.b1));
+      GemmEpilogue p1 = make_epilogue(dx, D);  // dx1 = dz2 (in dx) + dhid . W1^T, in place
+      p1.residual = dx; p1.ldr = D;
+      MFP_TRY(gemm(h, dhid, 0, kF, P + b.w1, 0, kF, T, D, kF, p1, 1, st));
+      MFP_TRY(launch_layernorm_bwd(xmid, dx, P + b.g1, stats, stats + T, nullptr, T, dx, G + b.g1, G + b.be1, st, nullptr, 0, nullptr,
+                                   drop ? dyb : nullptr, h->cfg.dropout, seed, step, kSiteDropout + 2 * i));
+      const float* dy1 = drop ? dyb : dx;
+      MFP_TRY(gemm(h, attn, 1, D, dy1, 1, D, D, D, T, make_epilogue(G + b.wo, D), wgrad_splits(D, D, T), st, G + b.bo));
+      MFP_TRY(gemm(h, dy1, 0, D, P + b.wo, 0, D, T, D, D, make_epilogue(dattn, D), 1, st));
+      {
+        ProfScope prof(h, MFP_PROFILE_ATTENTION, st, 4.0 * T * (3.0 * D + D + D + 3.0 * D) + 4.0 * h->B * kH * h->S);
+        if (h->gemm_impl == 0 && h->S <= 128) MFP_TRY(launch_attention_bwd_tc(h->maps, qkv, attn, lse, dattn, modified->length, h->B, h->S, dqkv, st));
+        else MFP_TRY(launch_attention_bwd(qkv, attn, lse, dattn, modified->length, h->B, h->S, dqkv, st));
+      }
+      MFP_TRY(gemm(h, xi, 1, D, dqkv, 1, 3 * D, D, 3 * D, T, make_epilogue(G + b.wqkv, 3 * D), wgrad_splits(D, 3 * D, T), st, G + b.bqkv));
+      GemmEpilogue p2 = make_epilogue(dx, D);  // d(block input) = dz1 (in dx) + dqkv . Wqkv^T, in place
+      p2.residual = dx; p2.ldr = D;
+      MFP_TRY(gemm(h, dqkv, 0, 3 * D, P + b.wqkv, 0, 3 * D, T, D, 3 * D, p2, 1, st));
+      if (i == 0 && sc.n_num > 0) {
+        // the encoder's Dense wgrads want dh0 with the rows of special-token elements zeroed, one copy per numerical field
+        MFP_TRY(launch_masked_copies(dx, wsp<unsigned char>(h, h->off.flags), sc.n_num, T, wsp<float>(h, h->off.dh0m), st));
+        h->launches++;
+      }
+      h->launches += 3;
+      continue;
+    }
     // FFN branch: x_out = xmid + drop(relu(ln2.W1 + b1).W2 + b2)
     // dy = dx under the FFN branch's dropout mask: written by the LayerNorm backward of the block above (below: by the
     // separate kernel for the topmost block, whose dx comes out of the heads' dgrad GEMM)

@@ -673,6 +673,7 @@ int launch_gemm(TensorMapCache* cache, const GemmCall& c, int impl, cudaStream_t
     MFP_GEMM_CASE(kEpiBias | kEpiResidual | kEpiDropout)       // attention output / FFN 2, training
     MFP_GEMM_CASE(kEpiResidual | kEpiRowflag)                  // encoder Dense of a numerical field
     MFP_GEMM_CASE(kEpiReluMask)                                // dgrad through the FFN ReLU
+    MFP_GEMM_CASE(kEpiResidual)                                // dgrad + the gradient of the skip path (post-LayerNorm block)
     default:
       set_error("gemm: epilogue combination 0x%x is not instantiated", epi);
       return MFP_ERR_UNSUPPORTED;

@@ -32,6 +32,7 @@ int launch_layernorm_bwd(const float* x, const float* dy, const float* gamma, co
                          float* dx, float* dgamma, float* dbeta, cudaStream_t st, const unsigned char* rowflags = nullptr, int n_masked = 0,
                          float* dx_masked = nullptr, float* dx_drop = nullptr, float drop_rate = 0.f, uint32_t drop_seed = 0, uint32_t drop_step = 0,
                          uint32_t drop_site = 0);
+int launch_masked_copies(const float* src, const unsigned char* flags /*[n_copies][T]*/, int n_copies, int T, float* dst /*[n_copies][T][D]*/, cudaStream_t st);
 int launch_attention_fwd(const float* qkv, const int* length, int B, int S, float* out, float* lse, cudaStream_t st);
 int launch_attention_bwd(const float* qkv, const float* out, const float* lse, const float* dout, const int* length, int B, int S, float* dqkv,
                          cudaStream_t st);

@@ -278,6 +278,19 @@ __global__ void __launch_bounds__(256) dropout_bwd_kernel(const float* __restric
   reinterpret_cast<float4*>(dy)[i] = make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// dst[s][t][:] = flags[s][t] ? 0 : src[t][:] -- the encoder's Dense weight gradients take dh0 with the rows of special-token elements
+// zeroed, one copy per numerical field (the pre-LayerNorm path gets these copies out of its last LayerNorm backward)
+__global__ void __launch_bounds__(256) masked_copies_kernel(const float* __restrict__ src, const unsigned char* __restrict__ flags, int n_copies, int T,
+                                                            float* __restrict__ dst) {
+  pdl_wait();
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index into [T, kD]
+  if (i >= (size_t)T * kD / 4) return;
+  const int t = (int)(i / (kD / 4));
+  const float4 v = reinterpret_cast<const float4*>(src)[i];
+  for (int s = 0; s < n_copies; ++s)
+    reinterpret_cast<float4*>(dst + (size_t)s * T * kD)[i] = flags[(size_t)s * T + t] ? make_float4(0.f, 0.f, 0.f, 0.f) : v;
+}
+
 // out[c] += sum_r x[r, c]; grid = (col blocks, row chunks)
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int rows, int cols, int ld, int rows_per_chunk,
                                                      float* __restrict__ out) {
@@ -338,6 +351,13 @@ int launch_attention_bwd(const float* qkv, const float* out, const float* lse, c
 int launch_dropout_bwd(const float* dx, int T, float rate, uint32_t seed, uint32_t step, uint32_t site, float* dy, cudaStream_t st) {
   const size_t n4 = (size_t)T * kD / 4;
   MFP_CUDA_OK(launch_pdl(dropout_bwd_kernel, (unsigned)((n4 + 255) / 256), 256, 0, st, dx, n4, rate, seed, step, site, dy));
+  MFP_CUDA_OK(cudaGetLastError());
+  return MFP_OK;
+}
+
+int launch_masked_copies(const float* src, const unsigned char* flags, int n_copies, int T, float* dst, cudaStream_t st) {
+  const size_t n4 = (size_t)T * kD / 4;
+  MFP_CUDA_OK(launch_pdl(masked_copies_kernel, (unsigned)((n4 + 255) / 256), 256, 0, st, src, flags, n_copies, T, dst));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }

@@ -30,7 +30,7 @@ class FieldDesc(ctypes.Structure):
 class Config(ctypes.Structure):
     _fields_ = [("num_fields", ctypes.c_int32), ("type_field", ctypes.c_int32), ("latent_dim", ctypes.c_int32), ("num_blocks", ctypes.c_int32),
                 ("sort_pos", ctypes.c_int32), ("pos_task_id", ctypes.c_int32), ("total_columns", ctypes.c_int32),
-                ("sort_fields", ctypes.c_int32 * 5), ("dropout", ctypes.c_float), ("l2", ctypes.c_float)]
+                ("sort_fields", ctypes.c_int32 * 5), ("dropout", ctypes.c_float), ("l2", ctypes.c_float), ("block_type", ctypes.c_int32)]
 
 
 class Variable(ctypes.Structure):
@@ -132,7 +132,7 @@ class Engine:
     """One ``mfp_engine`` handle plus the device buffers it is bound to."""
 
     def __init__(self, input_columns: Dict, num_blocks: int = 4, latent_dim: int = 256, dropout: float = 0.1, l2: Optional[float] = 1e-2,
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, block_type: str = "deepsvg"):
         self.lib = load_library()
         if not torch.cuda.is_available():
             raise RuntimeError("flex_dm_b200: a CUDA device is required (there is no CPU fallback)")
@@ -180,6 +180,7 @@ class Engine:
             cfg.sort_fields[i] = self.keys.index(k)
         cfg.dropout = float(dropout)
         cfg.l2 = -1.0 if l2 is None else float(l2)
+        cfg.block_type = {"deepsvg": 0, "transformer": 1}[block_type]  # transformer.py:232-236
         self.cfg = cfg
         handle = ctypes.c_void_p()
         _check(self.lib, self.lib.mfp_create(ctypes.byref(cfg), fields, ctypes.byref(handle)), "mfp_create")

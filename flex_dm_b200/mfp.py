@@ -88,7 +88,9 @@ class MFP:
         **kwargs,  # keys are latent_dim, dropout, l2
     ):
         assert arch_type == "oneshot"  # mfp.py:230
-        for flag, value, supported in (("block_type", block_type, "deepsvg"), ("seq_type", seq_type, "default"),
+        if block_type not in ("deepsvg", "transformer"):  # get_seq_block, transformer.py:232-236
+            raise KeyError(block_type)
+        for flag, value, supported in (("seq_type", seq_type, "default"),
                                        ("context", context, None), ("input_dtype", input_dtype, "set"),
                                        ("use_elemwise_noise", use_elemwise_noise, False)):
             if value != supported:
@@ -105,7 +107,8 @@ class MFP:
         l2 = kwargs.pop("l2", None)
         if kwargs:
             raise TypeError("unexpected arguments: %s" % sorted(kwargs))
-        self.engine = Engine(input_columns, num_blocks=num_blocks, latent_dim=latent_dim, dropout=dropout, l2=l2, device=device)
+        self.block_type = block_type
+        self.engine = Engine(input_columns, num_blocks=num_blocks, latent_dim=latent_dim, dropout=dropout, l2=l2, device=device, block_type=block_type)
         self.device = self.engine.device
         self.keys = self.engine.keys
         self.task_names = get_task_names(input_columns)

@@ -50,6 +50,8 @@ typedef struct {
   int32_t sort_fields[5]; /* indices of type,left,top,width,height (tensor_utils.py:11) */
   float dropout;       /* rate of the two residual-branch Dropouts (transformer.py:174-175) */
   float l2;            /* make_dense_options / make_emb_options coefficient (architecture/utils.py:8-22); <0 = None */
+  int32_t block_type;  /* 0 = "deepsvg" (pre-LayerNorm block, transformer.py:208-229; the default), 1 = "transformer"
+                        * (post-LayerNorm TransformerBlock, transformer.py:187-205): same variables, same kernels, other wiring */
 } mfp_config;
 
 /* One trainable variable of the reference model as a strided view of the flat

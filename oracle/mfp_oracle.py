@@ -394,10 +394,20 @@ def dropout(x, keep, rate):
     return x * keep.to(x.dtype) * (1.0 / (1.0 - rate))
 
 
-def blocks_forward(p, x, mask, num_blocks, drop=None, rate=0.0):
-    """architecture/transformer.py:208-229 (DeepSVGBlock) stacked by Blocks.__call__ :272-280; no final norm."""
+def blocks_forward(p, x, mask, num_blocks, drop=None, rate=0.0, block_type="deepsvg"):
+    """architecture/transformer.py:208-229 (DeepSVGBlock, pre-LayerNorm) or :187-205 (TransformerBlock, post-LayerNorm: --block_type
+    transformer) stacked by Blocks.__call__ :272-280; no final norm."""
     for i in range(num_blocks):
         b = "model/blocks/seq2seq/seq2seq_%d" % i
+        if block_type == "transformer":
+            y = mhsa_forward(p, b + "/attn", x, mask)
+            y = dropout(y, None if drop is None else drop[(i, 0)], rate)
+            x = layer_norm(x + y, p[b + "/norm1/gamma"], p[b + "/norm1/beta"])
+            y = torch.relu(dense(x, p, b + "/mlp/layer_with_weights-0"))
+            y = dense(y, p, b + "/mlp/layer_with_weights-1")
+            y = dropout(y, None if drop is None else drop[(i, 1)], rate)
+            x = layer_norm(x + y, p[b + "/norm2/gamma"], p[b + "/norm2/beta"])
+            continue
         y = layer_norm(x, p[b + "/norm1/gamma"], p[b + "/norm1/beta"])
         y = mhsa_forward(p, b + "/attn", y, mask)
         y = dropout(y, None if drop is None else drop[(i, 0)], rate)
@@ -423,10 +433,10 @@ def decoder_forward(p, h, input_columns):
     return out
 
 
-def model_forward(p, modified_inputs, input_columns, num_blocks, drop=None, rate=0.0, return_hidden=False):
+def model_forward(p, modified_inputs, input_columns, num_blocks, drop=None, rate=0.0, return_hidden=False, block_type="deepsvg"):
     """models/model.py:26-30."""
     h0, mask = encoder_forward(p, modified_inputs, input_columns)
-    h = blocks_forward(p, h0, mask, num_blocks, drop, rate)
+    h = blocks_forward(p, h0, mask, num_blocks, drop, rate, block_type)
     out = decoder_forward(p, h, input_columns)
     if return_hidden:
         return out, h0, h
@@ -643,7 +653,8 @@ class OracleMFP:
     """The reference's MFP train/eval step (mfp.py:210-347 + Keras default train_step) on CPU."""
 
     def __init__(self, input_columns, num_blocks=4, masking_method="random", latent_dim=256, dropout=0.1, l2=1e-2,
-                 seed=0, dtype=torch.float64, learning_rate=1e-4, clipnorm=1.0, bias_scale=0.0):
+                 seed=0, dtype=torch.float64, learning_rate=1e-4, clipnorm=1.0, bias_scale=0.0, block_type="deepsvg"):
+        self.block_type = block_type
         self.input_columns = OrderedDict((k, v) for k, v in input_columns.items() if not v.get("demo_only", False))
         self.all_columns = input_columns
         self.num_blocks, self.latent_dim, self.rate, self.l2 = num_blocks, latent_dim, dropout, l2
@@ -669,7 +680,7 @@ class OracleMFP:
                 for i in range(self.num_blocks) for j in (0, 1)}
 
     def loss_from(self, params, targets, modified, masks, tasks, drop):
-        outputs = model_forward(params, modified, self.input_columns, self.num_blocks, drop, self.rate)
+        outputs = model_forward(params, modified, self.input_columns, self.num_blocks, drop, self.rate, block_type=self.block_type)
         sort_flag = (tasks == self.task_names.index("pos")) if self.sort_pos else None  # mfp.py:335-340
         data_loss, losses, scores, metrics = loss_layer(targets, outputs, masks, self.all_columns, sort_flag)
         reg = l2_regulariser(params, self.specs, self.l2) if self.l2 is not None else 0.0

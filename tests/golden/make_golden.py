@@ -63,7 +63,10 @@ CASES = OrderedDict([
     ("crello_random", ("crello", "random", 4, 16, 2, 7, 0, [16, 1, 9, 5], None)),
     ("crello_multi", ("crello", "elem_pos_attr_img_txt", 6, 12, 2, 3, 2, [12, 7, 1, 12, 4, 10], [1, 3, 4, 5, 6, 3])),
     ("rico_pos", ("rico", "elem_pos_attr", 5, 10, 2, 5, 1, [10, 3, 8, 1, 6], [3, 1, 4, 3, 3])),
+    # --block_type transformer: the post-LayerNorm TransformerBlock (transformer.py:187-205)
+    ("crello_postln", ("crello", "random", 3, 12, 2, 9, 3, [12, 1, 7], None)),
 ])
+BLOCK_TYPE = {"crello_postln": "transformer"}
 
 
 def rng_script(cols, B, S, tasks, draws, num_blocks, training):
@@ -116,6 +119,7 @@ def run_case(name, spec):
     cols = make_input_columns(dataset, max_length=max(S, 50))
     batch = make_synthetic_batch(cols, B, S, seed=seed, fixed_lengths=np.asarray(lengths))
     draws = O.PhiloxDraws(seed, step)
+    block_type = BLOCK_TYPE.get(name, "deepsvg")
     oracle = O.OracleMFP(cols, num_blocks=L, masking_method=method, dropout=RATE, l2=L2)
     if tasks is None:
         tasks = draws.tasks(B, oracle.allowed_tasks)
@@ -127,7 +131,7 @@ def run_case(name, spec):
 
     # ---------------- phase A: the whole MFP.call in float32 (bit-faithful dtypes for the masking path)
     tfc.FLOAT = torch.float32
-    model = RefMFP(cols, num_blocks=L, block_type="deepsvg", masking_method=method, seq_type="default", arch_type="oneshot",
+    model = RefMFP(cols, num_blocks=L, block_type=block_type, masking_method=method, seq_type="default", arch_type="oneshot",
                    context=None, input_dtype="set", latent_dim=D, dropout=RATE, l2=L2)
     inputs32 = {k: torch.as_tensor(v).as_subclass(tf.Tensor) for k, v in batch.items()}
     captured = {}

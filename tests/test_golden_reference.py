@@ -22,7 +22,9 @@ CASES = {  # name: (dataset, masking_method, num_blocks, seed, step)
     "crello_random": ("crello", "random", 2, 7, 0),
     "crello_multi": ("crello", "elem_pos_attr_img_txt", 2, 3, 2),
     "rico_pos": ("rico", "elem_pos_attr", 2, 5, 1),
+    "crello_postln": ("crello", "random", 2, 9, 3),  # --block_type transformer (post-LayerNorm block)
 }
+BLOCK_TYPE = {"crello_postln": "transformer"}
 
 
 def projection_vector(name, n):  # same as make_golden.py
@@ -48,13 +50,15 @@ def test_golden_files_cover_every_task_and_edge_case():
         seen |= {(CASES[case][0], int(t)) for t in g["tasks"]}
         assert int(g["in/length"].min()) == 0 and int(g["in/length"].max()) == g["in/left"].shape[1] - 1
     assert {t for d, t in seen if d == "crello"} == {0, 1, 3, 4, 5, 6}
+    assert "crello_postln" in CASES  # the post-LayerNorm block of --block_type transformer
     assert {t for d, t in seen if d == "rico"} >= {1, 3, 4}
 
 
 @pytest.mark.parametrize("case", list(CASES))
 def test_oracle_matches_reference_python(case):
     g, cols, batch, method, L, seed, step = load(case)
-    o = O.OracleMFP(cols, num_blocks=L, masking_method=method, dropout=RATE, l2=L2, learning_rate=LR, clipnorm=1.0)
+    o = O.OracleMFP(cols, num_blocks=L, masking_method=method, dropout=RATE, l2=L2, learning_rate=LR, clipnorm=1.0,
+                    block_type=BLOCK_TYPE.get(case, "deepsvg"))
     o.params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float64, bias_scale=0.05)
     draws = O.PhiloxDraws(seed, step)
     tasks = torch.as_tensor(g["tasks"])
@@ -105,7 +109,7 @@ def test_oracle_merge_matches_reference_python(case):
     inputs = o.to_torch(batch)
     targets, mod, masks = O.preprocess_for_train(inputs, o.input_columns, tasks, draws)
     B, S = batch["left"].shape[:2]
-    outputs = O.model_forward(o.params, mod, o.input_columns, L, o.dropout_masks(draws, B, S), RATE)
+    outputs = O.model_forward(o.params, mod, o.input_columns, L, o.dropout_masks(draws, B, S), RATE, block_type=BLOCK_TYPE.get(case, "deepsvg"))
     merged = O.merge_inputs_and_prediction(inputs, o.input_columns, masks, outputs)
     keys = [k[7:] for k in g.files if k.startswith("merged/")]
     assert set(keys) == set(o.input_columns)
@@ -127,7 +131,7 @@ def test_engine_matches_reference_python(case, impl):
     from flex_dm_b200.mfp import MFP
 
     g, cols, batch, method, L, seed, step = load(case)
-    m = MFP(cols, num_blocks=L, masking_method=method, latent_dim=256, dropout=RATE, l2=L2, seed=0)
+    m = MFP(cols, num_blocks=L, block_type=BLOCK_TYPE.get(case, "deepsvg"), masking_method=method, latent_dim=256, dropout=RATE, l2=L2, seed=0)
     params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float64, bias_scale=0.05)
     m.set_weights({k: v.numpy().astype(np.float32) for k, v in params.items()})
     eng = m.engine
