@@ -518,6 +518,9 @@ class TensorMapCache {
     for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides[i];
     auto it = maps_.find(key);
     if (it != maps_.end()) return &it->second;
+    // Descriptors are copied into kernel parameters at launch, so nothing outlives a call: when a caller keeps feeding fresh
+    // buffers (Model.call on user tensors, debug entry points) the cache is simply restarted instead of growing without bound.
+    if (maps_.size() >= 4096) maps_.clear();
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)"); return nullptr; }
     if (reinterpret_cast<uintptr_t>(ptr) & 15) { set_error("TMA operand must be 16-byte aligned"); return nullptr; }
