@@ -482,6 +482,7 @@ static int sm_count() {
 }
 
 int launch_attention_fwd_tc(TensorMapCache* maps, const float* qkv, const int* length, int B, int S, float* out, float* lse, cudaStream_t st) {
+  tensor_map_cache_trim(maps);
   if (S > kAtRows) { set_error("attention (tcgen05): S = %d exceeds the %d-row unit tile", S, kAtRows); return MFP_ERR_UNSUPPORTED; }
   static bool attr_set = false;
   if (!attr_set) {
@@ -505,6 +506,7 @@ int launch_attention_fwd_tc(TensorMapCache* maps, const float* qkv, const int* l
 
 int launch_attention_bwd_tc(TensorMapCache* maps, const float* qkv, const float* out, const float* lse, const float* dout, const int* length, int B, int S,
                             float* dqkv, cudaStream_t st) {
+  tensor_map_cache_trim(maps);
   if (S > kAtRows) { set_error("attention backward (tcgen05): S = %d exceeds the %d-row unit tile", S, kAtRows); return MFP_ERR_UNSUPPORTED; }
   static bool attr_set = false;
   if (!attr_set) {

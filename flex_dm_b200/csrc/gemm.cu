@@ -518,9 +518,7 @@ class TensorMapCache {
     for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides[i];
     auto it = maps_.find(key);
     if (it != maps_.end()) return &it->second;
-    // Descriptors are copied into kernel parameters at launch, so nothing outlives a call: when a caller keeps feeding fresh
-    // buffers (Model.call on user tensors, debug entry points) the cache is simply restarted instead of growing without bound.
-    if (maps_.size() >= 4096) maps_.clear();
+
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)"); return nullptr; }
     if (reinterpret_cast<uintptr_t>(ptr) & 15) { set_error("TMA operand must be 16-byte aligned"); return nullptr; }
@@ -545,6 +543,12 @@ class TensorMapCache {
     auto res = maps_.emplace(key, m);
     return &res.first->second;
   }
+  // Descriptors are copied into kernel parameters at launch, so none outlives a launcher call: when a caller keeps feeding fresh
+  // buffers (Model.call on user tensors, debug entry points) the cache is restarted -- by the launchers, before their first get()
+  // -- instead of growing without bound.
+  void trim() {
+    if (maps_.size() >= 4096) maps_.clear();
+  }
   // 2-D [outer][inner] with row pitch ld (floats); box = [box_outer][box_inner]
   const CUtensorMap* get(const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer, MapKind kind) {
     const uint64_t dims[2] = {inner, outer}, strides[1] = {ld};
@@ -561,6 +565,7 @@ const CUtensorMap* tensor_map_get(TensorMapCache* cache, const float* ptr, int r
   return cache->get(ptr, rank, dims, strides, box, kind);
 }
 
+void tensor_map_cache_trim(TensorMapCache* cache) { cache->trim(); }
 TensorMapCache* tensor_map_cache_create() { return new TensorMapCache(); }
 void tensor_map_cache_destroy(TensorMapCache* c) { delete c; }
 
@@ -592,6 +597,7 @@ static int launch_tcgen05(TensorMapCache* cache, const GemmCall& c, cudaStream_t
     MFP_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tcgen05<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
+  cache->trim();
   if (c.ep.residual && c.ep.relu_src) { set_error("gemm: residual and relu_src cannot be combined"); return MFP_ERR_ARG; }
   if (c.colsum && !c.b.mn_major) { set_error("gemm: the fused column sum needs an MN-major B operand"); return MFP_ERR_ARG; }
   // MN-major operand [K][MN] with pitch ld: 2-D boxes of 32 columns x kBK rows, or -- when MN is whole 32-column blocks -- a 3-D

@@ -56,6 +56,7 @@ enum MapKind : uint32_t { kMapOperandK = 0, kMapOperandMN = 1, kMapEpilogue = 2 
 class TensorMapCache;
 TensorMapCache* tensor_map_cache_create();
 void tensor_map_cache_destroy(TensorMapCache*);
+void tensor_map_cache_trim(TensorMapCache*);  // call at the start of a launcher, before its first tensor_map_get (pointers from earlier calls die)
 // fp32 tensor of rank 2 or 3: dims[0] innermost (contiguous), strides (floats) of dims 1.., box per dim; see gemm.cu for the kinds
 const CUtensorMap* tensor_map_get(TensorMapCache* cache, const float* ptr, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
                                   MapKind kind);
