@@ -31,6 +31,8 @@ constexpr uint32_t kStreamRandomCat = 1;
 constexpr uint32_t kStreamRandomNum = 16;
 constexpr uint32_t kFieldElem = 1000;
 constexpr uint32_t kFieldTask = 1001;
+constexpr uint32_t kFieldShuffle = 1002;   // shuffle_inputs: per-element sort key
+constexpr uint32_t kSitePosDropout = 1999;  // Dropout of the PositionEmbedding (input_dtype != "set")
 constexpr uint32_t kSiteDropout = 2000;
 
 struct FieldDev {

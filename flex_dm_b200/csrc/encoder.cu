@@ -2,6 +2,7 @@
 // backward.  The numerical fields' Dense (512 -> D) runs on the tensor cores (gemm.cu); this file produces
 // everything else of h0 in one pass: categorical gather-sum over sub-targets, <MASK>/<UNUSED> special rows
 // and the Dense bias of unflagged rows.  The backward is a one-hot GEMM (see below).
+#include "gemm.cuh"
 #include "kernels.cuh"
 
 namespace mfp {
@@ -13,7 +14,7 @@ constexpr int kTokPerCta = 8;
 // float4 per lane -- and accumulates them in the reference's order (fields in column order, sub-targets in order).
 __global__ void __launch_bounds__(32 * kTokPerCta) embed_fwd_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs mod,
                                                                     const unsigned char* __restrict__ flags, const float* __restrict__ params, int T,
-                                                                    float* __restrict__ h0) {
+                                                                    float* __restrict__ h0, const PosEmbed pos) {
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * kTokPerCta + (threadIdx.x >> 5);
@@ -45,9 +46,36 @@ __global__ void __launch_bounds__(32 * kTokPerCta) embed_fwd_kernel(const __grid
       a1.x += r1.x; a1.y += r1.y; a1.z += r1.z; a1.w += r1.w;
     }
   }
+  if (pos.table) {  // seq += PositionEmbedding(...): row of position s, under its own dropout site when training (transformer.py:24-30)
+    const float4* row = reinterpret_cast<const float4*>(pos.table + (size_t)(t % pos.S) * kD);
+    const float4 p0 = __ldg(row + lane), p1 = __ldg(row + 32 + lane);
+    float va[4] = {p0.x, p0.y, p0.z, p0.w}, vb[4] = {p1.x, p1.y, p1.z, p1.w};
+    if (pos.rate > 0.f) {
+      dropout4(va, (uint32_t)t * kD + 4u * lane, pos.rate, pos.seed, pos.step, kSitePosDropout);
+      dropout4(vb, (uint32_t)t * kD + 128u + 4u * lane, pos.rate, pos.seed, pos.step, kSitePosDropout);
+    }
+    a0.x += va[0]; a0.y += va[1]; a0.z += va[2]; a0.w += va[3];
+    a1.x += vb[0]; a1.y += vb[1]; a1.z += vb[2]; a1.w += vb[3];
+  }
   float4* out = reinterpret_cast<float4*>(h0 + (size_t)t * kD);
   out[lane] = a0;
   out[32 + lane] = a1;
+}
+
+// d(PositionEmbedding table)[s] = sum over documents of dh0[b, s] under the same dropout mask.  grid = S, block = D/4 threads.
+__global__ void __launch_bounds__(kD / 4) pos_embed_bwd_kernel(const float* __restrict__ dh0, int B, int S, float rate, uint32_t seed, uint32_t step,
+                                                               float* __restrict__ dtable) {
+  pdl_wait();
+  const int s = blockIdx.x, q = threadIdx.x;  // float4 index within the row
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b = 0; b < B; ++b) {
+    const size_t t = (size_t)b * S + s;
+    const float4 g = reinterpret_cast<const float4*>(dh0 + t * kD)[q];
+    float v[4] = {g.x, g.y, g.z, g.w};
+    if (rate > 0.f) dropout4(v, (uint32_t)t * kD + 4u * q, rate, seed, step, kSitePosDropout);
+    acc.x += v[0]; acc.y += v[1]; acc.z += v[2]; acc.w += v[3];
+  }
+  reinterpret_cast<float4*>(dtable + (size_t)s * kD)[q] = acc;
 }
 
 // Backward of the above as a tensor-core contraction.  Every element selects a handful of "gradient rows" (one per
@@ -101,8 +129,15 @@ __global__ void __launch_bounds__(kD) embed_scatter_kernel(const __grid_constant
   }
 }
 
-int launch_embed_fwd(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, const float* params, int T, float* h0, cudaStream_t st) {
-  MFP_CUDA_OK(launch_pdl(embed_fwd_kernel, (T + kTokPerCta - 1) / kTokPerCta, 32 * kTokPerCta, 0, st, sc, mod, flags, params, T, h0));
+int launch_embed_fwd(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, const float* params, int T, float* h0, cudaStream_t st,
+                     const PosEmbed& pos) {
+  MFP_CUDA_OK(launch_pdl(embed_fwd_kernel, (T + kTokPerCta - 1) / kTokPerCta, 32 * kTokPerCta, 0, st, sc, mod, flags, params, T, h0, pos));
+  MFP_CUDA_OK(cudaGetLastError());
+  return MFP_OK;
+}
+
+int launch_pos_embed_bwd(const float* dh0, int B, int S, float rate, uint32_t seed, uint32_t step, float* dtable, cudaStream_t st) {
+  MFP_CUDA_OK(launch_pdl(pos_embed_bwd_kernel, S, kD / 4, 0, st, dh0, B, S, rate, seed, step, dtable));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }

@@ -28,7 +28,7 @@ struct BlockLayout {
 
 struct Workspace {
   // byte offsets into the caller's workspace
-  size_t vars, flags, x, ln1, qkv, attn, xmid, ln2, hid, stats, lse, logits, dlogits, dx, dtmp, dy, dqkv, dhid, dattn, dh0m, onehot, rowgrad, part, idx_true, idx_pred,
+  size_t vars, flags, perm, x, ln1, qkv, attn, xmid, ln2, hid, stats, lse, logits, dlogits, dx, dtmp, dy, dqkv, dhid, dattn, dh0m, onehot, rowgrad, part, idx_true, idx_pred,
       norms, total;
 };
 
@@ -43,6 +43,7 @@ struct mfp_engine {
   std::vector<mfp_variable> vars;
   std::vector<BlockLayout> blocks;
   long long wh = 0, bh = 0, param_count = 0;
+  long long pos_off = -1;  // PositionEmbedding table (input_dtype != "set"), rows = length_input_dim + 1
   // bound state
   int B = 0, S = 0, T = 0;
   uint8_t* ws = nullptr;
@@ -111,6 +112,10 @@ static void build_layout(mfp_engine* h) {
       add_var(h, base + "/bias", fd.bias_off, 1, D, D, 1);
     }
   }
+  if (h->cfg.input_dtype != 0) {  // PositionEmbedding(latent_dim, maxlen = length input_dim) -> Embedding(maxlen + 1, D): encoder.py:48-55, transformer.py:17-21
+    h->pos_off = alloc((long long)(h->cfg.length_input_dim + 1) * D);
+    add_var(h, "model/encoder/input_layer/const/embeddings/embeddings", h->pos_off, h->cfg.length_input_dim + 1, D, D, 1);
+  }
   // backward stages: 0 = heads, 1..L = blocks L-1..0, L+1 = encoder; the layout is encoder | blocks | heads, each contiguous
   h->stage_lo.assign(L + 2, 0);
   h->stage_hi.assign(L + 2, 0);
@@ -172,6 +177,7 @@ static Workspace plan_workspace(const mfp_engine* h, int B, int S) {
   const size_t fl = sizeof(float);
   w.vars = take(h->vars.size() * sizeof(VarDev));
   w.flags = take((size_t)(h->sc.n_num > 0 ? h->sc.n_num : 1) * T);
+  w.perm = take(T * sizeof(int));
   w.x = take((L + 1) * T * D * fl);
   w.ln1 = take(L * T * D * fl);
   w.qkv = take(L * T * 3 * D * fl);
@@ -283,6 +289,8 @@ int mfp_create(const mfp_config* cfg, const mfp_field_desc* fields, mfp_engine**
   if (cfg->latent_dim != kD) { set_error("mfp_create: latent_dim must be %d in this build (got %d)", kD, cfg->latent_dim); return MFP_ERR_UNSUPPORTED; }
   if (cfg->num_fields < 1 || cfg->num_fields > kMaxFields) { set_error("mfp_create: num_fields out of range"); return MFP_ERR_ARG; }
   if (cfg->num_blocks < 1 || cfg->num_blocks > 64) { set_error("mfp_create: num_blocks out of range"); return MFP_ERR_ARG; }
+  if (cfg->input_dtype != 0 && cfg->input_dtype != 1) { set_error("mfp_create: input_dtype must be 0 (set) or 1 (shuffled_set)"); return MFP_ERR_ARG; }
+  if (cfg->input_dtype != 0 && cfg->length_input_dim < 1) { set_error("mfp_create: shuffled_set needs length_input_dim"); return MFP_ERR_ARG; }
   if (cfg->block_type != 0 && cfg->block_type != 1) { set_error("mfp_create: block_type must be 0 (deepsvg) or 1 (transformer)"); return MFP_ERR_ARG; }
   mfp_engine* h = new mfp_engine();
   h->cfg = *cfg;
@@ -370,6 +378,10 @@ int mfp_bind(mfp_engine* h, int32_t B, int32_t S, void* workspace, int64_t works
   if (!h || !workspace || !params) { set_error("mfp_bind: null argument"); return MFP_ERR_ARG; }
   if (B < 1 || S < 1) { set_error("mfp_bind: bad shape"); return MFP_ERR_ARG; }
   if (S > 384) { set_error("mfp_bind: S = %d exceeds the attention kernels' shared-memory plan (max 384)", S); return MFP_ERR_UNSUPPORTED; }
+  if (h->cfg.input_dtype != 0 && S > h->cfg.length_input_dim + 1) {
+    set_error("mfp_bind: S = %d exceeds the PositionEmbedding table (%d rows)", S, h->cfg.length_input_dim + 1);
+    return MFP_ERR_ARG;
+  }
   const Workspace w = plan_workspace(h, B, S);
   if ((size_t)workspace_bytes < w.total) { set_error("mfp_bind: workspace too small (%lld < %zu)", (long long)workspace_bytes, w.total); return MFP_ERR_ARG; }
   if (reinterpret_cast<uintptr_t>(workspace) & 255) { set_error("mfp_bind: workspace must be 256-byte aligned"); return MFP_ERR_ARG; }
@@ -405,6 +417,21 @@ int mfp_mask_corrupt(mfp_engine* h, const mfp_batch* inputs, const int32_t* task
                              wsp<unsigned char>(h, h->off.flags));
 }
 
+int mfp_shuffle_inputs(mfp_engine* h, const mfp_batch* inputs, uint32_t seed, uint32_t step, void* const* shuffled_cols, int32_t* perm_out, void* stream) {
+  MFP_TRY(check_bound(h));
+  if (!inputs || !shuffled_cols) { set_error("mfp_shuffle_inputs: null argument"); return MFP_ERR_ARG; }
+  ModifiedPtrs out{};
+  for (int f = 0; f < h->sc.F; ++f) {
+    if (!shuffled_cols[f] || shuffled_cols[f] == inputs->cols[f]) { set_error("mfp_shuffle_inputs: output columns must be distinct buffers"); return MFP_ERR_ARG; }
+    out.cols[f] = shuffled_cols[f];
+  }
+  int* perm = wsp<int>(h, h->off.perm);
+  h->launches += 2;
+  MFP_TRY(launch_shuffle_inputs(h->sc, to_batch(h, inputs), h->B, h->S, seed, step, perm, out, (cudaStream_t)stream));
+  if (perm_out) MFP_CUDA_OK(cudaMemcpyAsync(perm_out, perm, (size_t)h->T * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return MFP_OK;
+}
+
 int mfp_mask_for_test(mfp_engine* h, const mfp_batch* inputs, const uint8_t* const* masks, void* const* modified_cols, void* stream) {
   MFP_TRY(check_bound(h));
   ModifiedPtrs out{};
@@ -433,7 +460,9 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
   const bool have_flags = sc.n_num > 0 && h->flags_for != nullptr && h->flags_for == modified->cols[first_numerical(sc)];
   h->flags_for = nullptr;
   if (!have_flags) { MFP_TRY(launch_row_flags(sc, mod, T, flags, st)); h->launches++; }
-  MFP_TRY(launch_embed_fwd(sc, mod, flags, P, T, x, st));
+  PosEmbed pos{nullptr, 0, 0.f, 0u, 0u};
+  if (h->pos_off >= 0) pos = PosEmbed{P + h->pos_off, h->S, drop ? h->cfg.dropout : 0.f, seed, step};
+  MFP_TRY(launch_embed_fwd(sc, mod, flags, P, T, x, st, pos));
   h->launches += 1;
   for (int f = 0; f < sc.F; ++f) {
     const FieldDev& fd = sc.f[f];
@@ -688,6 +717,10 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
   }
   MFP_TRY(launch_embed_scatter(sc, rowgrad, G, st));
   h->launches += 2;
+  if (h->pos_off >= 0) {  // rows >= S of the table get no gradient (G was cleared in stage 0)
+    MFP_TRY(launch_pos_embed_bwd(dx, h->B, h->S, drop ? h->cfg.dropout : 0.f, seed, step, G + h->pos_off, st));
+    h->launches++;
+  }
   return MFP_OK;
 }
 

@@ -18,10 +18,21 @@ struct ModifiedPtrs {
 int launch_sample_tasks(const TaskSet& allowed, int B, uint32_t seed, uint32_t step, int* tasks, cudaStream_t st);
 int launch_mask_corrupt(const Schema& sc, const BatchPtrs& in, const int* tasks, const MaskPtrs* test_masks, int B, int S, uint32_t seed,
                         uint32_t step, const ModifiedPtrs& out, cudaStream_t st, unsigned char* flags /*[n_num][T], optional*/ = nullptr);
+int launch_shuffle_inputs(const Schema& sc, const BatchPtrs& in, int B, int S, uint32_t seed, uint32_t step, int* perm /*[B][S]*/, const ModifiedPtrs& out,
+                          cudaStream_t st);
 int launch_row_flags(const Schema& sc, const BatchPtrs& mod, int T, unsigned char* flags /*[n_num][T]*/, cudaStream_t st);
 
 // encoder.cu
-int launch_embed_fwd(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, const float* params, int T, float* h0, cudaStream_t st);
+// pos: optional PositionEmbedding table [>= S][D] added per position (input_dtype != "set"), under dropout when pos_rate > 0
+struct PosEmbed {
+  const float* table;
+  int S;
+  float rate;  // 0 = inference
+  uint32_t seed, step;
+};
+int launch_embed_fwd(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, const float* params, int T, float* h0, cudaStream_t st,
+                     const PosEmbed& pos = PosEmbed{nullptr, 0, 0.f, 0u, 0u});
+int launch_pos_embed_bwd(const float* dh0, int B, int S, float rate, uint32_t seed, uint32_t step, float* dtable /*[S][D], overwritten*/, cudaStream_t st);
 int launch_embed_onehot(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, int T, float* onehot /*[T][Rp]*/, cudaStream_t st);
 int launch_embed_scatter(const Schema& sc, const float* scratch /*[R][D]*/, float* grads, cudaStream_t st);
 

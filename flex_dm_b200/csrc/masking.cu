@@ -147,6 +147,55 @@ __global__ void __launch_bounds__(256) row_flags_kernel(const __grid_constant__ 
   }
 }
 
+// shuffle_inputs (tensor_utils.py:47-76): grid = documents.  perm[b][r] = source position of output position r: the valid positions
+// ordered by their Philox key (ties by position), padding in place.
+__global__ void __launch_bounds__(128) shuffle_perm_kernel(const int* __restrict__ length, int S, uint32_t seed, uint32_t step, int* __restrict__ perm) {
+  pdl_wait();
+  extern __shared__ uint32_t skeys[];  // [S]
+  const int b = blockIdx.x;
+  const int n = min(S, length[b] + 1);
+  for (int s = threadIdx.x; s < n; s += blockDim.x) skeys[s] = philox4x32_10((uint32_t)(b * S + s), kFieldShuffle, 0u, 0u, seed, step).x;
+  __syncthreads();
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    if (s >= n) { perm[b * S + s] = s; continue; }
+    const uint32_t k = skeys[s];
+    int r = 0;
+    for (int j = 0; j < n; ++j) r += (skeys[j] < k) || (skeys[j] == k && j < s);
+    perm[b * S + r] = s;
+  }
+}
+
+// one warp per output element: every sequence column gathered through the permutation
+__global__ void __launch_bounds__(256) gather_columns_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs in,
+                                                             const int* __restrict__ perm, int B, int S, const __grid_constant__ ModifiedPtrs out) {
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= B * S) return;
+  const int b = t / S;
+  const size_t src_t = (size_t)b * S + perm[t];
+  for (int f = 0; f < sc.F; ++f) {
+    const FieldDev& fd = sc.f[f];
+    if (fd.kind == 0) {
+      if (lane < fd.C) reinterpret_cast<int*>(out.cols[f])[(size_t)t * fd.C + lane] = reinterpret_cast<const int*>(in.cols[f])[src_t * fd.C + lane];
+    } else {
+      const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in.cols[f]) + src_t * fd.C);
+      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out.cols[f]) + (size_t)t * fd.C);
+      for (int q = lane; q < fd.C / 4; q += 32) dst[q] = src[q];
+    }
+  }
+}
+
+int launch_shuffle_inputs(const Schema& sc, const BatchPtrs& in, int B, int S, uint32_t seed, uint32_t step, int* perm, const ModifiedPtrs& out,
+                          cudaStream_t st) {
+  MFP_CUDA_OK(launch_pdl(shuffle_perm_kernel, B, 128, S * sizeof(uint32_t), st, in.length, S, seed, step, perm));
+  MFP_CUDA_OK(cudaGetLastError());
+  const int T = B * S;
+  MFP_CUDA_OK(launch_pdl(gather_columns_kernel, (T + 7) / 8, 256, 0, st, sc, in, perm, B, S, out));
+  MFP_CUDA_OK(cudaGetLastError());
+  return MFP_OK;
+}
+
 int launch_sample_tasks(const TaskSet& allowed, int B, uint32_t seed, uint32_t step, int* tasks, cudaStream_t st) {
   MFP_CUDA_OK(launch_pdl(sample_tasks_kernel, (B + 127) / 128, 128, 0, st, allowed, B, seed, step, tasks));
   MFP_CUDA_OK(cudaGetLastError());

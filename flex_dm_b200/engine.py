@@ -30,7 +30,8 @@ class FieldDesc(ctypes.Structure):
 class Config(ctypes.Structure):
     _fields_ = [("num_fields", ctypes.c_int32), ("type_field", ctypes.c_int32), ("latent_dim", ctypes.c_int32), ("num_blocks", ctypes.c_int32),
                 ("sort_pos", ctypes.c_int32), ("pos_task_id", ctypes.c_int32), ("total_columns", ctypes.c_int32),
-                ("sort_fields", ctypes.c_int32 * 5), ("dropout", ctypes.c_float), ("l2", ctypes.c_float), ("block_type", ctypes.c_int32)]
+                ("sort_fields", ctypes.c_int32 * 5), ("dropout", ctypes.c_float), ("l2", ctypes.c_float), ("input_dtype", ctypes.c_int32),
+                ("length_input_dim", ctypes.c_int32), ("block_type", ctypes.c_int32)]
 
 
 class Variable(ctypes.Structure):
@@ -61,6 +62,8 @@ _SIGNATURES = {
                                         ctypes.c_void_p, ctypes.c_void_p]),
     "mfp_mask_corrupt": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Batch), ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
+    "mfp_shuffle_inputs": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Batch), ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_void_p),
+                                          ctypes.c_void_p, ctypes.c_void_p]),
     "mfp_mask_for_test": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Batch), ctypes.POINTER(ctypes.c_void_p),
                                          ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
     "mfp_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Batch), ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p,
@@ -132,7 +135,7 @@ class Engine:
     """One ``mfp_engine`` handle plus the device buffers it is bound to."""
 
     def __init__(self, input_columns: Dict, num_blocks: int = 4, latent_dim: int = 256, dropout: float = 0.1, l2: Optional[float] = 1e-2,
-                 device: Optional[torch.device] = None, block_type: str = "deepsvg"):
+                 device: Optional[torch.device] = None, block_type: str = "deepsvg", input_dtype: str = "set"):
         self.lib = load_library()
         if not torch.cuda.is_available():
             raise RuntimeError("flex_dm_b200: a CUDA device is required (there is no CPU fallback)")
@@ -181,6 +184,9 @@ class Engine:
         cfg.dropout = float(dropout)
         cfg.l2 = -1.0 if l2 is None else float(l2)
         cfg.block_type = {"deepsvg": 0, "transformer": 1}[block_type]  # transformer.py:232-236
+        cfg.input_dtype = {"set": 0, "shuffled_set": 1}[input_dtype]  # mfp.py:104-105, encoder.py:41
+        cfg.length_input_dim = int(input_columns["length"]["input_dim"])
+        self.input_dtype = input_dtype
         self.cfg = cfg
         handle = ctypes.c_void_p()
         _check(self.lib, self.lib.mfp_create(ctypes.byref(cfg), fields, ctypes.byref(handle)), "mfp_create")
@@ -258,6 +264,8 @@ class Engine:
                 self.masks.append(torch.zeros((B, S), dtype=torch.uint8, device=self.device))
             self.tasks = torch.zeros((B,), dtype=torch.int32, device=self.device)
             self.logits = None
+            # shuffled copies of the sequence columns (--input_dtype shuffled_set): targets and corruption source of the step
+            self.shuffled = [torch.zeros_like(t) for t in self.modified] if self.input_dtype == "shuffled_set" else None
         _check(self.lib, self.lib.mfp_bind(self.handle, B, S, ctypes.c_void_p(self._ws_ptr), nbytes, _ptr(self.params), _ptr(self.grads),
                                            _ptr(self.adam_m), _ptr(self.adam_v)), "mfp_bind")
         self.B, self.S = B, S
@@ -286,6 +294,14 @@ class Engine:
         _check(self.lib, self.lib.mfp_mask_corrupt(self.handle, ctypes.byref(b), _ptr(tasks), seed & 0xFFFFFFFF, step & 0xFFFFFFFF,
                                                    ctypes.cast(self._mod_ptrs, ctypes.POINTER(ctypes.c_void_p)),
                                                    ctypes.cast(self._mask_ptrs, ctypes.POINTER(ctypes.c_void_p)), _stream()), "mfp_mask_corrupt")
+
+    def shuffle_inputs(self, length, cols, seed: int, step: int, perm_out: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+        """shuffle_inputs (tensor_utils.py:47-76): returns the shuffled sequence columns (engine-owned buffers)."""
+        b = self._batch(length, cols)
+        sp = _PTR_ARRAY(*[t.data_ptr() for t in self.shuffled])
+        _check(self.lib, self.lib.mfp_shuffle_inputs(self.handle, ctypes.byref(b), seed & 0xFFFFFFFF, step & 0xFFFFFFFF,
+                                                     ctypes.cast(sp, ctypes.POINTER(ctypes.c_void_p)), _ptr(perm_out), _stream()), "mfp_shuffle_inputs")
+        return self.shuffled
 
     def mask_for_test(self, length, cols, masks: List[torch.Tensor]):
         b = self._batch(length, cols)

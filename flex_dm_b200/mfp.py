@@ -90,8 +90,10 @@ class MFP:
         assert arch_type == "oneshot"  # mfp.py:230
         if block_type not in ("deepsvg", "transformer"):  # get_seq_block, transformer.py:232-236
             raise KeyError(block_type)
+        if input_dtype not in ("set", "shuffled_set"):
+            raise NotImplementedError("input_dtype=%r is outside the B200 hot path (SURVEY.md section 8f); supported: 'set', 'shuffled_set'" % (input_dtype,))
         for flag, value, supported in (("seq_type", seq_type, "default"),
-                                       ("context", context, None), ("input_dtype", input_dtype, "set"),
+                                       ("context", context, None),
                                        ("use_elemwise_noise", use_elemwise_noise, False)):
             if value != supported:
                 raise NotImplementedError("%s=%r is outside the B200 hot path (SURVEY.md section 8f); supported: %r" % (flag, value, supported))
@@ -108,7 +110,8 @@ class MFP:
         if kwargs:
             raise TypeError("unexpected arguments: %s" % sorted(kwargs))
         self.block_type = block_type
-        self.engine = Engine(input_columns, num_blocks=num_blocks, latent_dim=latent_dim, dropout=dropout, l2=l2, device=device, block_type=block_type)
+        self.engine = Engine(input_columns, num_blocks=num_blocks, latent_dim=latent_dim, dropout=dropout, l2=l2, device=device, block_type=block_type,
+                             input_dtype=input_dtype)
         self.device = self.engine.device
         self.keys = self.engine.keys
         self.task_names = get_task_names(input_columns)
@@ -211,6 +214,8 @@ class MFP:
         eng, seed, step = self.engine, self.seed, self._step
         row = self._next_row()
         tasks = eng.sample_tasks(self.task_ids, seed, step)
+        if self.input_dtype == "shuffled_set":  # mfp.py:104-105: the shuffled batch is what gets corrupted and what the loss targets
+            cols = eng.shuffle_inputs(length, cols, seed, step)
         eng.mask_corrupt(length, cols, tasks, seed, step)
         eng.forward(length, None, True, seed, step)
         eng.loss(length, cols, eng.masks, row, 1.0 / (B * self._world), True, sort_tasks=tasks if self.sort_pos else None)
@@ -239,6 +244,8 @@ class MFP:
         eng, seed, step = self.engine, self.seed, self._step
         row = self._next_row()
         tasks = eng.sample_tasks(self.task_ids, seed, step)
+        if self.input_dtype == "shuffled_set":
+            cols = eng.shuffle_inputs(length, cols, seed, step)
         eng.mask_corrupt(length, cols, tasks, seed, step)
         eng.forward(length, None, False, seed, step)
         eng.loss(length, cols, eng.masks, row, 1.0 / (B * self._world), False, sort_tasks=tasks if self.sort_pos else None)
@@ -337,6 +344,9 @@ class MFP:
                 t = demo_args["tasks"]
                 tasks = (torch.as_tensor(t) if not isinstance(t, torch.Tensor) else t).to(self.device)
         else:
+            merge_cols = cols  # merge_inputs_and_prediction receives the caller's (unshuffled) inputs: mfp.py:342-344
+            if self.input_dtype == "shuffled_set":
+                cols = eng.shuffle_inputs(length, cols, seed, step)
             eng.mask_corrupt(length, cols, tasks, seed, step)  # mfp.py:95-138
             eng.forward(length, None, training, seed, step)
             row = self._next_row()
@@ -344,6 +354,7 @@ class MFP:
             eng.regularization_loss(row[-1:])
             self.last_metrics_row = row
             masks = eng.masks
+            cols = merge_cols
         self._step += 1
         # merge_inputs_and_prediction (mfp.py:46-69)
         outputs = {}

@@ -129,6 +129,20 @@ class PhiloxDraws:
         x0, _, _, _ = philox.philox4x32_10(np.arange(B), philox.FIELD_ELEM, 0, 0, self.seed, self.step)
         return philox.u01(x0)
 
+    def shuffle_perm(self, lengths: np.ndarray, S: int) -> np.ndarray:
+        """(B,S) source position of every output position: valid positions ordered by their Philox key (ties by position), padding in place."""
+        B = len(lengths)
+        perm = np.tile(np.arange(S, dtype=np.int64), (B, 1))
+        x0, _, _, _ = philox.philox4x32_10(np.arange(B * S), philox.FIELD_SHUFFLE, 0, 0, self.seed, self.step)
+        keys = x0.reshape(B, S).astype(np.int64)
+        for b in range(B):
+            n = int(lengths[b])
+            perm[b, :n] = np.lexsort((np.arange(n), keys[b, :n]))
+        return perm
+
+    def pos_dropout_keep(self, shape, rate: float) -> np.ndarray:
+        return philox.dropout_keep(int(np.prod(shape)), philox.SITE_POS_DROPOUT, rate, self.seed, self.step).reshape(shape)
+
     def dropout_keep(self, block: int, branch: int, shape, rate: float) -> np.ndarray:
         n = int(np.prod(shape))
         return philox.dropout_keep(n, philox.SITE_DROPOUT + 2 * block + branch, rate, self.seed, self.step).reshape(shape)
@@ -238,8 +252,25 @@ def feat_masking(inputs, input_columns, mask, feat_group):  # masking.py:116-133
     return modified, masks
 
 
-def preprocess_for_train(inputs, input_columns, tasks: torch.Tensor, draws: PhiloxDraws):
-    """mfp.py:95-138 (is_autoreg=False, input_dtype="set"): all variants are computed, then selected per document."""
+def shuffle_inputs(inputs, perm: np.ndarray):
+    """tensor_utils.py:47-76 with the permutation given: every tensor whose second axis is S is gathered along it."""
+    S = perm.shape[1]
+    idx = torch.as_tensor(perm, dtype=torch.int64)
+    out = {}
+    for key, val in inputs.items():
+        if val.dim() >= 2 and val.shape[1] == S:
+            full = idx.reshape(idx.shape + (1,) * (val.dim() - 2)).expand(-1, -1, *val.shape[2:])
+            out[key] = torch.gather(val, 1, full)
+        else:
+            out[key] = val
+    return out
+
+
+def preprocess_for_train(inputs, input_columns, tasks: torch.Tensor, draws: PhiloxDraws, input_dtype: str = "set"):
+    """mfp.py:95-138 (is_autoreg=False): optional shuffle; all masking variants are computed, then selected per document."""
+    if input_dtype == "shuffled_set":  # mfp.py:104-105
+        S_ = inputs[next(iter(get_valid_input_columns(input_columns)))].shape[1]
+        inputs = shuffle_inputs(inputs, draws.shuffle_perm(inputs["length"].reshape(-1).numpy() + 1, S_))
     groups = get_attribute_groups(input_columns.keys())
     S = inputs[next(iter(get_valid_input_columns(input_columns)))].shape[1]
     seq_mask = get_seq_mask(inputs["length"], S)
@@ -279,7 +310,7 @@ def preprocess_for_test(inputs, input_columns, masks, tasks=None):
 
 
 # ----------------------------------------------------------------------------------------------- parameters
-def variable_specs(input_columns, num_blocks=4, latent_dim=256) -> "OrderedDict[str, Tuple[tuple, str, bool]]":
+def variable_specs(input_columns, num_blocks=4, latent_dim=256, input_dtype="set") -> "OrderedDict[str, Tuple[tuple, str, bool]]":
     """name -> (shape, init, l2-regularised).  SURVEY.md Appendix B; names follow the reference's attribute
     paths (mfp.py:249, model.py:20,45,52, encoder.py:74-92, transformer.py:54-57,161-173,263, decoder.py:39)."""
     D = latent_dim
@@ -293,6 +324,8 @@ def variable_specs(input_columns, num_blocks=4, latent_dim=256) -> "OrderedDict[
             v[base + "_special/embeddings"] = ((2, D), "uniform", True)  # encoder.py:82-87
             v[base + "/kernel"] = ((c["shape"][-1], D), "glorot", True)  # encoder.py:88-92
             v[base + "/bias"] = ((D,), "zeros", True)
+    if input_dtype != "set":  # PositionEmbedding(latent_dim, maxlen=length input_dim): Embedding(maxlen + 1, D) (encoder.py:48-55, transformer.py:17-21)
+        v["model/encoder/input_layer/const/embeddings/embeddings"] = ((input_columns["length"]["input_dim"] + 1, D), "uniform", True)
     for i in range(num_blocks):
         b = "model/blocks/seq2seq/seq2seq_%d" % i
         for d in ("dense_query", "dense_key", "dense_value", "combine_heads"):  # transformer.py:54-57
@@ -312,12 +345,12 @@ def variable_specs(input_columns, num_blocks=4, latent_dim=256) -> "OrderedDict[
     return v
 
 
-def init_params(input_columns, num_blocks=4, latent_dim=256, seed=0, dtype=torch.float64, bias_scale=0.0):
+def init_params(input_columns, num_blocks=4, latent_dim=256, seed=0, dtype=torch.float64, bias_scale=0.0, input_dtype="set"):
     """Keras default initialisers (Appendix A9): Dense glorot-uniform / zero bias, Embedding U(-0.05, 0.05), LN ones/zeros.
     ``bias_scale`` > 0 perturbs biases / LN parameters so that parity tests exercise them."""
     rng = np.random.Generator(np.random.PCG64(seed))
     params = OrderedDict()
-    for name, (shape, init, _) in variable_specs(input_columns, num_blocks, latent_dim).items():
+    for name, (shape, init, _) in variable_specs(input_columns, num_blocks, latent_dim, input_dtype).items():
         if init == "uniform":
             w = rng.uniform(-0.05, 0.05, size=shape)
         elif init == "glorot":
@@ -343,7 +376,7 @@ def dense(x, p, name):
     return x @ p[name + "/kernel"] + p[name + "/bias"]  # A12
 
 
-def encoder_forward(p, inputs, input_columns):
+def encoder_forward(p, inputs, input_columns, pos_keep=None, pos_rate=0.0):
     """architecture/encoder.py:147-265 with fusion="add", context=None, input_dtype="set"."""
     cols = get_valid_input_columns(input_columns)
     dtype = next(iter(p.values())).dtype
@@ -364,6 +397,11 @@ def encoder_forward(p, inputs, input_columns):
             x = torch.where(is_masked[..., None], special[0], x)  # encoder.py:174
             x = torch.where(is_unused[..., None], special[1], x)  # encoder.py:175
         seq = seq + x  # encoder.py:194-197
+    pos_name = "model/encoder/input_layer/const/embeddings/embeddings"
+    if pos_name in p:  # use_pos_token (encoder.py:251-252): PositionEmbedding tiled over the batch, under its own Dropout
+        B = seq.shape[0]
+        emb = p[pos_name][:S][None].expand(B, -1, -1)
+        seq = seq + dropout(emb, pos_keep, pos_rate)
     return seq, seq_mask
 
 
@@ -435,7 +473,7 @@ def decoder_forward(p, h, input_columns):
 
 def model_forward(p, modified_inputs, input_columns, num_blocks, drop=None, rate=0.0, return_hidden=False, block_type="deepsvg"):
     """models/model.py:26-30."""
-    h0, mask = encoder_forward(p, modified_inputs, input_columns)
+    h0, mask = encoder_forward(p, modified_inputs, input_columns, None if drop is None else drop.get("pos"), rate)
     h = blocks_forward(p, h0, mask, num_blocks, drop, rate, block_type)
     out = decoder_forward(p, h, input_columns)
     if return_hidden:
@@ -653,14 +691,15 @@ class OracleMFP:
     """The reference's MFP train/eval step (mfp.py:210-347 + Keras default train_step) on CPU."""
 
     def __init__(self, input_columns, num_blocks=4, masking_method="random", latent_dim=256, dropout=0.1, l2=1e-2,
-                 seed=0, dtype=torch.float64, learning_rate=1e-4, clipnorm=1.0, bias_scale=0.0, block_type="deepsvg"):
+                 seed=0, dtype=torch.float64, learning_rate=1e-4, clipnorm=1.0, bias_scale=0.0, block_type="deepsvg", input_dtype="set"):
         self.block_type = block_type
+        self.input_dtype = input_dtype
         self.input_columns = OrderedDict((k, v) for k, v in input_columns.items() if not v.get("demo_only", False))
         self.all_columns = input_columns
         self.num_blocks, self.latent_dim, self.rate, self.l2 = num_blocks, latent_dim, dropout, l2
         self.dtype = dtype
-        self.specs = variable_specs(input_columns, num_blocks, latent_dim)
-        self.params = init_params(input_columns, num_blocks, latent_dim, seed, dtype, bias_scale)
+        self.specs = variable_specs(input_columns, num_blocks, latent_dim, input_dtype)
+        self.params = init_params(input_columns, num_blocks, latent_dim, seed, dtype, bias_scale, input_dtype)
         self.m = OrderedDict((k, torch.zeros_like(v)) for k, v in self.params.items())
         self.v = OrderedDict((k, torch.zeros_like(v)) for k, v in self.params.items())
         self.t = 0
@@ -676,8 +715,11 @@ class OracleMFP:
     def dropout_masks(self, draws: Optional[PhiloxDraws], B, S):
         if draws is None or self.rate == 0.0:
             return None
-        return {(i, j): torch.from_numpy(draws.dropout_keep(i, j, (B, S, self.latent_dim), self.rate))
+        keep = {(i, j): torch.from_numpy(draws.dropout_keep(i, j, (B, S, self.latent_dim), self.rate))
                 for i in range(self.num_blocks) for j in (0, 1)}
+        if self.input_dtype != "set":
+            keep["pos"] = torch.from_numpy(draws.pos_dropout_keep((B, S, self.latent_dim), self.rate))
+        return keep
 
     def loss_from(self, params, targets, modified, masks, tasks, drop):
         outputs = model_forward(params, modified, self.input_columns, self.num_blocks, drop, self.rate, block_type=self.block_type)
@@ -692,7 +734,7 @@ class OracleMFP:
         draws = PhiloxDraws(seed, step)
         B = inputs["length"].shape[0]
         tasks = torch.from_numpy(draws.tasks(B, self.allowed_tasks))
-        targets, modified, masks = preprocess_for_train(inputs, self.input_columns, tasks, draws)
+        targets, modified, masks = preprocess_for_train(inputs, self.input_columns, tasks, draws, self.input_dtype)
         S = masks[next(iter(get_valid_input_columns(self.input_columns)))].shape[1]
         drop = self.dropout_masks(draws, B, S) if training_dropout else None
         return self.step_from(targets, modified, masks, tasks, drop)

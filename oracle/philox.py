@@ -22,6 +22,8 @@ STREAM_RANDOM_CAT = 1  # + c : random replacement token of sub-target c
 STREAM_RANDOM_NUM = 16  # + (j >> 2): Box-Muller normals for numerical dims 4*(j>>2) .. +3
 FIELD_ELEM = 1000  # elem_masking: per-document uniform
 FIELD_TASK = 1001  # task sampler: per-document draw
+FIELD_SHUFFLE = 1002  # shuffle_inputs: per-element sort key (x0)
+SITE_POS_DROPOUT = 1999  # Dropout of the PositionEmbedding (input_dtype != "set")
 SITE_DROPOUT = 2000  # + 2*block + {0: attention branch, 1: FFN branch}
 
 

@@ -65,11 +65,14 @@ CASES = OrderedDict([
     ("rico_pos", ("rico", "elem_pos_attr", 5, 10, 2, 5, 1, [10, 3, 8, 1, 6], [3, 1, 4, 3, 3])),
     # --block_type transformer: the post-LayerNorm TransformerBlock (transformer.py:187-205)
     ("crello_postln", ("crello", "random", 3, 12, 2, 9, 3, [12, 1, 7], None)),
+    # --input_dtype shuffled_set: elements shuffled per document (tensor_utils.py:47-76) + PositionEmbedding with dropout (encoder.py:48-55,251-252)
+    ("rico_shuffled", ("rico", "elem_pos_attr", 4, 9, 2, 13, 5, [9, 4, 1, 6], [0, 3, 1, 4])),
 ])
 BLOCK_TYPE = {"crello_postln": "transformer"}
+INPUT_DTYPE = {"rico_shuffled": "shuffled_set"}
 
 
-def rng_script(cols, B, S, tasks, draws, num_blocks, training):
+def rng_script(cols, B, S, tasks, draws, num_blocks, training, pos_dropout=False):
     """The reference's RNG call order for one MFP.call(training): mfp.py:301 -> masking.py filter_padding :24-53
     -> random_masking :227-269 -> elem_masking :136-155 -> feat_masking per group :116-133 -> Dropout x2 per block."""
     icols = OrderedDict((k, v) for k, v in cols.items() if not v.get("demo_only", False))
@@ -98,6 +101,8 @@ def rng_script(cols, B, S, tasks, draws, num_blocks, training):
         for k in group:
             s.append(discard(seq[k]))
     if training:
+        if pos_dropout:  # the encoder's PositionEmbedding dropout comes before the blocks'
+            s.append(("dropout", draws.pos_dropout_keep((B, S, D), RATE)))
         for i in range(num_blocks):
             for j in (0, 1):
                 s.append(("dropout", draws.dropout_keep(i, j, (B, S, D), RATE)))
@@ -120,19 +125,40 @@ def run_case(name, spec):
     batch = make_synthetic_batch(cols, B, S, seed=seed, fixed_lengths=np.asarray(lengths))
     draws = O.PhiloxDraws(seed, step)
     block_type = BLOCK_TYPE.get(name, "deepsvg")
-    oracle = O.OracleMFP(cols, num_blocks=L, masking_method=method, dropout=RATE, l2=L2)
+    input_dtype = INPUT_DTYPE.get(name, "set")
+    if input_dtype == "shuffled_set":
+        method = method if "random" in method else "random_" + method  # keep task 0 reachable for the scripted task ids
+    oracle = O.OracleMFP(cols, num_blocks=L, masking_method=method, dropout=RATE, l2=L2, input_dtype=input_dtype)
     if tasks is None:
         tasks = draws.tasks(B, oracle.allowed_tasks)
     tasks = np.asarray(tasks, dtype=np.int32)
-    params = O.init_params(cols, L, D, WEIGHT_SEED, torch.float64, bias_scale=0.05)
+    params = O.init_params(cols, L, D, WEIGHT_SEED, torch.float64, bias_scale=0.05, input_dtype=input_dtype)
     out = {"tasks": tasks}
     for k, v in batch.items():
         out["in/" + k] = v
+    perm = None
+    if input_dtype == "shuffled_set":
+        # the reference shuffles with Python's `random` (tensor_utils.py:60-62); its draws are scripted with the Philox permutation
+        perm = draws.shuffle_perm(np.asarray(lengths), S)
+        out["perm"] = perm.astype(np.int32)
+        import mfp.models.tensor_utils as ref_tu
+
+        class _ScriptedRandom:
+            calls = 0
+
+            @staticmethod
+            def shuffle(x):
+                b = _ScriptedRandom.calls % B
+                _ScriptedRandom.calls += 1
+                n = len(x)
+                x[:] = [int(perm[b, i]) for i in range(n)]
+
+        ref_tu.random = _ScriptedRandom
 
     # ---------------- phase A: the whole MFP.call in float32 (bit-faithful dtypes for the masking path)
     tfc.FLOAT = torch.float32
     model = RefMFP(cols, num_blocks=L, block_type=block_type, masking_method=method, seq_type="default", arch_type="oneshot",
-                   context=None, input_dtype="set", latent_dim=D, dropout=RATE, l2=L2)
+                   context=None, input_dtype=input_dtype, latent_dim=D, dropout=RATE, l2=L2)
     inputs32 = {k: torch.as_tensor(v).as_subclass(tf.Tensor) for k, v in batch.items()}
     captured = {}
     inner_call, loss_call = model.model.call, model.loss_layer.call
@@ -151,11 +177,11 @@ def run_case(name, spec):
         return loss_call(inputs, training, sort_flag, ignore_sort)
 
     model.model.call, model.loss_layer.call = model_spy, loss_spy
-    tfc.rng = tfc.ScriptedRNG(rng_script(cols, B, S, tasks, draws, L, True))
+    tfc.rng = tfc.ScriptedRNG(rng_script(cols, B, S, tasks, draws, L, True, input_dtype != "set"))
     model({k: v.clone() for k, v in inputs32.items()}, training=True)  # builds the lazily-created variables
     set_weights(model, params, torch.float32)
     model.reset_step_state()
-    tfc.rng = tfc.ScriptedRNG(rng_script(cols, B, S, tasks, draws, L, True))
+    tfc.rng = tfc.ScriptedRNG(rng_script(cols, B, S, tasks, draws, L, True, input_dtype != "set"))
     merged = model({k: v.clone() for k, v in inputs32.items()}, training=True)
     assert tfc.rng.done(), "the reference asked for fewer draws than scripted"
     loss32 = float(sum(model.losses))
@@ -164,6 +190,9 @@ def run_case(name, spec):
         out["mod/" + k] = v.detach().numpy()
     for k, v in captured["masks"].items():
         out["mask/" + k] = v.numpy()
+    if input_dtype == "shuffled_set":
+        for k, v in captured["targets"].items():  # the shuffled batch: what the loss is computed against
+            out["tgt/" + k] = v.detach().numpy()
     for k, v in merged.items():
         if k != "tasks":
             out["merged/" + k] = v.detach().numpy().astype(np.float32) if v.is_floating_point() else v.numpy()
@@ -176,7 +205,8 @@ def run_case(name, spec):
     model.reset_step_state()
     mod64 = {k: (v.to(torch.float64) if v.is_floating_point() else v) for k, v in captured["mod"].items()}
     targets64 = {k: (v.to(torch.float64) if v.is_floating_point() else v.clone()) for k, v in captured["targets"].items()}
-    tfc.rng = tfc.ScriptedRNG([("dropout", draws.dropout_keep(i, j, (B, S, D), RATE)) for i in range(L) for j in (0, 1)])
+    tfc.rng = tfc.ScriptedRNG(([("dropout", draws.pos_dropout_keep((B, S, D), RATE))] if input_dtype != "set" else []) +
+                              [("dropout", draws.dropout_keep(i, j, (B, S, D), RATE)) for i in range(L) for j in (0, 1)])
     logits = model.model(mod64, True)
     for k, v in logits.items():
         out["logits/" + k] = v.detach().numpy()

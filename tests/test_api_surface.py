@@ -13,7 +13,7 @@ from oracle import mfp_oracle as O
 from tests import helpers as H
 
 
-@pytest.mark.parametrize("kwargs", [{"context": "id"}, {"input_dtype": "shuffled_set"}, {"seq_type": "flat"},
+@pytest.mark.parametrize("kwargs", [{"context": "id"}, {"input_dtype": "sorted_set"}, {"seq_type": "flat"},
                                     {"use_elemwise_noise": True}])
 def test_unsupported_switches_raise_instead_of_being_ignored(kwargs):
     from flex_dm_b200.mfp import MFP
@@ -66,6 +66,30 @@ def test_sequences_longer_than_the_tensor_core_tile():
     ref = O.model_forward(params, {k: torch.as_tensor(v) for k, v in batch.items()}, m.input_columns, 1)
     for key in m.keys:
         assert np.abs(got[key].cpu().numpy() - ref[key].numpy()).max() <= H.LOGIT_ATOL, key
+
+
+@pytest.mark.gpu
+def test_shuffled_set_train_steps_track_the_oracle():
+    """--input_dtype shuffled_set through the public train_step: shuffle -> corrupt -> PositionEmbedding encoder -> ... -> Adam,
+    against the oracle replaying the same Philox streams."""
+    from collections import OrderedDict
+
+    from flex_dm_b200.mfp import MFP, Adam
+
+    cols = make_input_columns("crello")
+    m = MFP(cols, num_blocks=1, masking_method="random", input_dtype="shuffled_set", latent_dim=256, dropout=0.1, l2=1e-2, seed=17)
+    m.set_weights(H.perturbed_weights(m.engine, 3))
+    m.compile(optimizer=Adam(learning_rate=1e-3, clipnorm=1.0))
+    assert "model/encoder/input_layer/const/embeddings/embeddings" in m.get_weights()
+    o = O.OracleMFP(cols, num_blocks=1, masking_method="random", dropout=0.1, l2=1e-2, learning_rate=1e-3, clipnorm=1.0, input_dtype="shuffled_set")
+    o.params = H.oracle_params_from_engine(m.engine)
+    o.m = OrderedDict((k, torch.zeros_like(v)) for k, v in o.params.items())
+    o.v = OrderedDict((k, torch.zeros_like(v)) for k, v in o.params.items())
+    batch = make_synthetic_batch(cols, 4, 20, seed=6, lengths="ragged")
+    for step in range(3):
+        got = m.metrics_from_row(m.train_step(batch))
+        ref = o.train_step(batch, seed=17, step=step)
+        assert got["loss"] == pytest.approx(ref["loss"], rel=H.LOSS_RTOL), step
 
 
 # ------------------------------------------------------------------------------------------------- eval.py::evaluate

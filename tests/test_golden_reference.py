@@ -23,8 +23,10 @@ CASES = {  # name: (dataset, masking_method, num_blocks, seed, step)
     "crello_multi": ("crello", "elem_pos_attr_img_txt", 2, 3, 2),
     "rico_pos": ("rico", "elem_pos_attr", 2, 5, 1),
     "crello_postln": ("crello", "random", 2, 9, 3),  # --block_type transformer (post-LayerNorm block)
+    "rico_shuffled": ("rico", "random_elem_pos_attr", 2, 13, 5),  # --input_dtype shuffled_set (shuffle + PositionEmbedding)
 }
 BLOCK_TYPE = {"crello_postln": "transformer"}
+INPUT_DTYPE = {"rico_shuffled": "shuffled_set"}
 
 
 def projection_vector(name, n):  # same as make_golden.py
@@ -57,14 +59,18 @@ def test_golden_files_cover_every_task_and_edge_case():
 @pytest.mark.parametrize("case", list(CASES))
 def test_oracle_matches_reference_python(case):
     g, cols, batch, method, L, seed, step = load(case)
+    input_dtype = INPUT_DTYPE.get(case, "set")
     o = O.OracleMFP(cols, num_blocks=L, masking_method=method, dropout=RATE, l2=L2, learning_rate=LR, clipnorm=1.0,
-                    block_type=BLOCK_TYPE.get(case, "deepsvg"))
-    o.params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float64, bias_scale=0.05)
+                    block_type=BLOCK_TYPE.get(case, "deepsvg"), input_dtype=input_dtype)
+    o.params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float64, bias_scale=0.05, input_dtype=input_dtype)
     draws = O.PhiloxDraws(seed, step)
     tasks = torch.as_tensor(g["tasks"])
     assert set(g["tasks"].tolist()) <= set(o.allowed_tasks)
     inputs = o.to_torch(batch)
-    targets, mod, masks = O.preprocess_for_train(inputs, o.input_columns, tasks, draws)
+    targets, mod, masks = O.preprocess_for_train(inputs, o.input_columns, tasks, draws, input_dtype)
+    if input_dtype == "shuffled_set":  # the shuffled batch the reference's shuffle_inputs produced (tensor_utils.py:47-76)
+        for key in o.input_columns:
+            assert np.array_equal(targets[key].numpy(), g["tgt/" + key]), key
     # ---- masking path: bit-exact against the reference's preprocess_for_train (mfp.py:95-138)
     for key in o.input_columns:
         assert np.array_equal(mod[key].numpy(), g["mod/" + key]), key
@@ -102,12 +108,13 @@ def test_oracle_matches_reference_python(case):
 def test_oracle_merge_matches_reference_python(case):
     """MFP.call's return value (mfp.py:46-69,342-347) from the float32 run of the reference."""
     g, cols, batch, method, L, seed, step = load(case)
-    o = O.OracleMFP(cols, num_blocks=L, masking_method=method, dropout=RATE, l2=L2, dtype=torch.float32)
-    o.params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float32, bias_scale=0.05)
+    input_dtype = INPUT_DTYPE.get(case, "set")
+    o = O.OracleMFP(cols, num_blocks=L, masking_method=method, dropout=RATE, l2=L2, dtype=torch.float32, input_dtype=input_dtype)
+    o.params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float32, bias_scale=0.05, input_dtype=input_dtype)
     draws = O.PhiloxDraws(seed, step)
     tasks = torch.as_tensor(g["tasks"])
     inputs = o.to_torch(batch)
-    targets, mod, masks = O.preprocess_for_train(inputs, o.input_columns, tasks, draws)
+    targets, mod, masks = O.preprocess_for_train(inputs, o.input_columns, tasks, draws, input_dtype)
     B, S = batch["left"].shape[:2]
     outputs = O.model_forward(o.params, mod, o.input_columns, L, o.dropout_masks(draws, B, S), RATE, block_type=BLOCK_TYPE.get(case, "deepsvg"))
     merged = O.merge_inputs_and_prediction(inputs, o.input_columns, masks, outputs)
@@ -131,8 +138,10 @@ def test_engine_matches_reference_python(case, impl):
     from flex_dm_b200.mfp import MFP
 
     g, cols, batch, method, L, seed, step = load(case)
-    m = MFP(cols, num_blocks=L, block_type=BLOCK_TYPE.get(case, "deepsvg"), masking_method=method, latent_dim=256, dropout=RATE, l2=L2, seed=0)
-    params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float64, bias_scale=0.05)
+    input_dtype = INPUT_DTYPE.get(case, "set")
+    m = MFP(cols, num_blocks=L, block_type=BLOCK_TYPE.get(case, "deepsvg"), masking_method=method, input_dtype=input_dtype, latent_dim=256,
+            dropout=RATE, l2=L2, seed=0)
+    params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float64, bias_scale=0.05, input_dtype=input_dtype)
     m.set_weights({k: v.numpy().astype(np.float32) for k, v in params.items()})
     eng = m.engine
     eng.set_gemm_impl(impl)
@@ -141,6 +150,13 @@ def test_engine_matches_reference_python(case, impl):
     staged = m.stage(batch)
     _, _, length, dcols = m._bind(staged)
     tasks = torch.as_tensor(g["tasks"]).cuda()
+    if input_dtype == "shuffled_set":  # shuffle_inputs: permutation and shuffled columns bit-exact against the reference's
+        perm = torch.zeros((B, S), dtype=torch.int32, device="cuda")
+        dcols = eng.shuffle_inputs(length, dcols, seed, step, perm_out=perm)
+        torch.cuda.synchronize()
+        assert np.array_equal(perm.cpu().numpy(), g["perm"])
+        for f, key in enumerate(m.keys):
+            assert np.array_equal(dcols[f].cpu().numpy(), g["tgt/" + key]), key
     eng.mask_corrupt(length, dcols, tasks, seed, step)
     torch.cuda.synchronize()
     # ---- masking: bit-exact against the reference's preprocess_for_train
@@ -174,7 +190,7 @@ def test_engine_matches_reference_python(case, impl):
         assert r[3 * f + 2] == pytest.approx(den, abs=1e-3), key
         assert abs(r[3 * f + 1] - float(g["score_num/" + key])) <= max(1.0, 0.005 * den), key
     # ---- gradients (the engine adds the L2 term inside the optimiser pass: d(l2 sum w^2)/dw = 2 l2 w)
-    specs = O.variable_specs(cols, L, 256)
+    specs = O.variable_specs(cols, L, 256, input_dtype)
     got_grads = eng.get_weights(eng.grads)
     w0 = eng.get_weights()
     for name in specs:
