@@ -9,7 +9,6 @@ synchronises with the host.
 """
 from typing import Dict, Iterable, Iterator, List, Optional
 
-import numpy as np
 import torch
 
 

@@ -9,7 +9,6 @@ works as in eval.py:109-110).  The arithmetic is ``csrc/loss.cu`` reached throug
 from collections import OrderedDict
 from typing import Dict, Optional
 
-import numpy as np
 import torch
 
 from .engine import Engine

@@ -23,7 +23,7 @@ import torch
 from .engine import Engine
 from .masking import get_task_names
 from .parallel import all_reduce_gradient_slice, all_reduce_gradients, broadcast_parameters, reduce_metric_rows
-from .spec import get_dataset_name, get_valid_input_columns
+from .spec import get_dataset_name
 
 logger = logging.getLogger(__name__)
 

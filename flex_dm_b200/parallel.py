@@ -18,7 +18,6 @@ Everything here is backend-agnostic ``torch.distributed`` (NCCL on the GPUs, glo
 """
 from typing import Dict, Tuple
 
-import numpy as np
 import torch
 
 

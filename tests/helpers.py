@@ -4,7 +4,6 @@ from collections import OrderedDict
 import numpy as np
 import torch
 
-from flex_dm_b200.spec import make_input_columns, make_synthetic_batch
 from oracle import mfp_oracle as O
 
 # Stated tolerances (BASELINE.json north_star: "within a stated fp32 tolerance"):
