@@ -289,8 +289,8 @@ int mfp_create(const mfp_config* cfg, const mfp_field_desc* fields, mfp_engine**
   if (cfg->latent_dim != kD) { set_error("mfp_create: latent_dim must be %d in this build (got %d)", kD, cfg->latent_dim); return MFP_ERR_UNSUPPORTED; }
   if (cfg->num_fields < 1 || cfg->num_fields > kMaxFields) { set_error("mfp_create: num_fields out of range"); return MFP_ERR_ARG; }
   if (cfg->num_blocks < 1 || cfg->num_blocks > 64) { set_error("mfp_create: num_blocks out of range"); return MFP_ERR_ARG; }
-  if (cfg->input_dtype != 0 && cfg->input_dtype != 1) { set_error("mfp_create: input_dtype must be 0 (set) or 1 (shuffled_set)"); return MFP_ERR_ARG; }
-  if (cfg->input_dtype != 0 && cfg->length_input_dim < 1) { set_error("mfp_create: shuffled_set needs length_input_dim"); return MFP_ERR_ARG; }
+  if (cfg->input_dtype < 0 || cfg->input_dtype > 2) { set_error("mfp_create: input_dtype must be 0 (set), 1 (shuffled_set) or 2 (sorted_set)"); return MFP_ERR_ARG; }
+  if (cfg->input_dtype != 0 && cfg->length_input_dim < 1) { set_error("mfp_create: shuffled_set / sorted_set need length_input_dim"); return MFP_ERR_ARG; }
   if (cfg->block_type != 0 && cfg->block_type != 1) { set_error("mfp_create: block_type must be 0 (deepsvg) or 1 (transformer)"); return MFP_ERR_ARG; }
   mfp_engine* h = new mfp_engine();
   h->cfg = *cfg;
@@ -427,7 +427,7 @@ int mfp_shuffle_inputs(mfp_engine* h, const mfp_batch* inputs, uint32_t seed, ui
   }
   int* perm = wsp<int>(h, h->off.perm);
   h->launches += 2;
-  MFP_TRY(launch_shuffle_inputs(h->sc, to_batch(h, inputs), h->B, h->S, seed, step, perm, out, (cudaStream_t)stream));
+  MFP_TRY(launch_shuffle_inputs(h->sc, to_batch(h, inputs), h->B, h->S, seed, step, perm, out, (cudaStream_t)stream, h->cfg.input_dtype == 2));
   if (perm_out) MFP_CUDA_OK(cudaMemcpyAsync(perm_out, perm, (size_t)h->T * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return MFP_OK;
 }

@@ -18,8 +18,9 @@ struct ModifiedPtrs {
 int launch_sample_tasks(const TaskSet& allowed, int B, uint32_t seed, uint32_t step, int* tasks, cudaStream_t st);
 int launch_mask_corrupt(const Schema& sc, const BatchPtrs& in, const int* tasks, const MaskPtrs* test_masks, int B, int S, uint32_t seed,
                         uint32_t step, const ModifiedPtrs& out, cudaStream_t st, unsigned char* flags /*[n_num][T], optional*/ = nullptr);
+// reorders every sequence column: random permutation of the valid elements (shuffled_set) or lexicographic sort (sorted_set)
 int launch_shuffle_inputs(const Schema& sc, const BatchPtrs& in, int B, int S, uint32_t seed, uint32_t step, int* perm /*[B][S]*/, const ModifiedPtrs& out,
-                          cudaStream_t st);
+                          cudaStream_t st, bool sorted = false);
 int launch_row_flags(const Schema& sc, const BatchPtrs& mod, int T, unsigned char* flags /*[n_num][T]*/, cudaStream_t st);
 
 // encoder.cu

@@ -165,6 +165,28 @@ __global__ void __launch_bounds__(128) shuffle_perm_kernel(const int* __restrict
   }
 }
 
+// sort_inputs (tensor_utils.py:14-44, --input_dtype sorted_set): elements ordered by the base-100 digits of (type, left, top, width, height)[..., 0],
+// padding last (key + 100^5), stable.  grid = documents.
+__global__ void __launch_bounds__(128) sort_perm_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs in, int S, int* __restrict__ perm) {
+  pdl_wait();
+  extern __shared__ long long lkeys[];  // [S]
+  const int b = blockIdx.x;
+  const int n = in.length[b] + 1;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const size_t t = (size_t)b * S + s;
+    long long k = 0;
+    for (int i = 0; i < 5; ++i) k = k * 100 + reinterpret_cast<const int*>(in.cols[sc.sort_field[i]])[t * sc.f[sc.sort_field[i]].C];
+    lkeys[s] = k + ((s >= n) ? 10000000000LL : 0LL);
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const long long k = lkeys[s];
+    int r = 0;
+    for (int j = 0; j < S; ++j) r += (lkeys[j] < k) || (lkeys[j] == k && j < s);
+    perm[b * S + r] = s;
+  }
+}
+
 // one warp per output element: every sequence column gathered through the permutation
 __global__ void __launch_bounds__(256) gather_columns_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs in,
                                                              const int* __restrict__ perm, int B, int S, const __grid_constant__ ModifiedPtrs out) {
@@ -187,8 +209,9 @@ __global__ void __launch_bounds__(256) gather_columns_kernel(const __grid_consta
 }
 
 int launch_shuffle_inputs(const Schema& sc, const BatchPtrs& in, int B, int S, uint32_t seed, uint32_t step, int* perm, const ModifiedPtrs& out,
-                          cudaStream_t st) {
-  MFP_CUDA_OK(launch_pdl(shuffle_perm_kernel, B, 128, S * sizeof(uint32_t), st, in.length, S, seed, step, perm));
+                          cudaStream_t st, bool sorted) {
+  if (sorted) MFP_CUDA_OK(launch_pdl(sort_perm_kernel, B, 128, S * sizeof(long long), st, sc, in, S, perm));
+  else MFP_CUDA_OK(launch_pdl(shuffle_perm_kernel, B, 128, S * sizeof(uint32_t), st, in.length, S, seed, step, perm));
   MFP_CUDA_OK(cudaGetLastError());
   const int T = B * S;
   MFP_CUDA_OK(launch_pdl(gather_columns_kernel, (T + 7) / 8, 256, 0, st, sc, in, perm, B, S, out));

@@ -184,7 +184,7 @@ class Engine:
         cfg.dropout = float(dropout)
         cfg.l2 = -1.0 if l2 is None else float(l2)
         cfg.block_type = {"deepsvg": 0, "transformer": 1}[block_type]  # transformer.py:232-236
-        cfg.input_dtype = {"set": 0, "shuffled_set": 1}[input_dtype]  # mfp.py:104-105, encoder.py:41
+        cfg.input_dtype = {"set": 0, "shuffled_set": 1, "sorted_set": 2}[input_dtype]  # mfp.py:104-105, encoder.py:41
         cfg.length_input_dim = int(input_columns["length"]["input_dim"])
         self.input_dtype = input_dtype
         self.cfg = cfg
@@ -265,7 +265,7 @@ class Engine:
             self.tasks = torch.zeros((B,), dtype=torch.int32, device=self.device)
             self.logits = None
             # shuffled copies of the sequence columns (--input_dtype shuffled_set): targets and corruption source of the step
-            self.shuffled = [torch.zeros_like(t) for t in self.modified] if self.input_dtype == "shuffled_set" else None
+            self.shuffled = [torch.zeros_like(t) for t in self.modified] if self.input_dtype != "set" else None
         _check(self.lib, self.lib.mfp_bind(self.handle, B, S, ctypes.c_void_p(self._ws_ptr), nbytes, _ptr(self.params), _ptr(self.grads),
                                            _ptr(self.adam_m), _ptr(self.adam_v)), "mfp_bind")
         self.B, self.S = B, S

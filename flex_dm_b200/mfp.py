@@ -90,8 +90,8 @@ class MFP:
         assert arch_type == "oneshot"  # mfp.py:230
         if block_type not in ("deepsvg", "transformer"):  # get_seq_block, transformer.py:232-236
             raise KeyError(block_type)
-        if input_dtype not in ("set", "shuffled_set"):
-            raise NotImplementedError("input_dtype=%r is outside the B200 hot path (SURVEY.md section 8f); supported: 'set', 'shuffled_set'" % (input_dtype,))
+        if input_dtype not in ("set", "shuffled_set", "sorted_set"):
+            raise ValueError("input_dtype=%r (args.py: set | shuffled_set | sorted_set)" % (input_dtype,))
         for flag, value, supported in (("seq_type", seq_type, "default"),
                                        ("context", context, None),
                                        ("use_elemwise_noise", use_elemwise_noise, False)):
@@ -214,7 +214,7 @@ class MFP:
         eng, seed, step = self.engine, self.seed, self._step
         row = self._next_row()
         tasks = eng.sample_tasks(self.task_ids, seed, step)
-        if self.input_dtype == "shuffled_set":  # mfp.py:104-105: the shuffled batch is what gets corrupted and what the loss targets
+        if self.input_dtype != "set":  # mfp.py:104-105: the shuffled batch is what gets corrupted and what the loss targets
             cols = eng.shuffle_inputs(length, cols, seed, step)
         eng.mask_corrupt(length, cols, tasks, seed, step)
         eng.forward(length, None, True, seed, step)
@@ -244,7 +244,7 @@ class MFP:
         eng, seed, step = self.engine, self.seed, self._step
         row = self._next_row()
         tasks = eng.sample_tasks(self.task_ids, seed, step)
-        if self.input_dtype == "shuffled_set":
+        if self.input_dtype != "set":
             cols = eng.shuffle_inputs(length, cols, seed, step)
         eng.mask_corrupt(length, cols, tasks, seed, step)
         eng.forward(length, None, False, seed, step)
@@ -345,7 +345,7 @@ class MFP:
                 tasks = (torch.as_tensor(t) if not isinstance(t, torch.Tensor) else t).to(self.device)
         else:
             merge_cols = cols  # merge_inputs_and_prediction receives the caller's (unshuffled) inputs: mfp.py:342-344
-            if self.input_dtype == "shuffled_set":
+            if self.input_dtype != "set":
                 cols = eng.shuffle_inputs(length, cols, seed, step)
             eng.mask_corrupt(length, cols, tasks, seed, step)  # mfp.py:95-138
             eng.forward(length, None, training, seed, step)

@@ -50,9 +50,10 @@ typedef struct {
   int32_t sort_fields[5]; /* indices of type,left,top,width,height (tensor_utils.py:11) */
   float dropout;       /* rate of the two residual-branch Dropouts (transformer.py:174-175) */
   float l2;            /* make_dense_options / make_emb_options coefficient (architecture/utils.py:8-22); <0 = None */
-  int32_t input_dtype; /* 0 = "set" (default); 1 = "shuffled_set": the elements of every document are shuffled before the corruption
-                        * (mfp.py:104-105, tensor_utils.py:47-76; mfp_shuffle_inputs) and the encoder adds a learned
-                        * PositionEmbedding with dropout (encoder.py:48-55,251-252; transformer.py:5-30) */
+  int32_t input_dtype; /* 0 = "set" (default); 1 = "shuffled_set" / 2 = "sorted_set": the elements of every document are shuffled
+                        * (tensor_utils.py:47-76) / sorted by (type,left,top,width,height) (tensor_utils.py:14-44) before the
+                        * corruption (mfp.py:104-107; mfp_shuffle_inputs) and the encoder adds a learned PositionEmbedding with
+                        * dropout (encoder.py:48-55,251-252; transformer.py:5-30) */
   int32_t length_input_dim; /* input_columns["length"]["input_dim"]: the PositionEmbedding table has this + 1 rows (>= S needed) */
   int32_t block_type;  /* 0 = "deepsvg" (pre-LayerNorm block, transformer.py:208-229; the default), 1 = "transformer"
                         * (post-LayerNorm TransformerBlock, transformer.py:187-205): same variables, same kernels, other wiring */
@@ -110,7 +111,7 @@ int mfp_mask_for_test(mfp_engine* h, const mfp_batch* inputs, const uint8_t* con
 /* shuffle_inputs (models/tensor_utils.py:47-76; mfp.py:104-105, --input_dtype shuffled_set): a random permutation of the valid
  * elements of every document, applied to every sequence column (padding stays in place).  The reference draws it with Python's
  * `random`; here element (b, s) gets a Philox key (counter = (b*S+s, 1002), key = (seed, step)) and the valid elements are
- * ordered by it.  shuffled_cols: one output column per field, same shapes as the inputs; perm_out (optional, int32 [B,S]):
+ * ordered by it.  With input_dtype = "sorted_set" the same call applies sort_inputs (tensor_utils.py:14-44) instead.  shuffled_cols: one output column per field, same shapes as the inputs; perm_out (optional, int32 [B,S]):
  * source position of every output position. */
 int mfp_shuffle_inputs(mfp_engine* h, const mfp_batch* inputs, uint32_t seed, uint32_t step, void* const* shuffled_cols,
                        int32_t* perm_out, void* stream);

@@ -271,6 +271,8 @@ def preprocess_for_train(inputs, input_columns, tasks: torch.Tensor, draws: Phil
     if input_dtype == "shuffled_set":  # mfp.py:104-105
         S_ = inputs[next(iter(get_valid_input_columns(input_columns)))].shape[1]
         inputs = shuffle_inputs(inputs, draws.shuffle_perm(inputs["length"].reshape(-1).numpy() + 1, S_))
+    elif input_dtype == "sorted_set":  # mfp.py:106-107
+        inputs, _ = sort_inputs(inputs, input_columns)
     groups = get_attribute_groups(input_columns.keys())
     S = inputs[next(iter(get_valid_input_columns(input_columns)))].shape[1]
     seq_mask = get_seq_mask(inputs["length"], S)

@@ -67,9 +67,11 @@ CASES = OrderedDict([
     ("crello_postln", ("crello", "random", 3, 12, 2, 9, 3, [12, 1, 7], None)),
     # --input_dtype shuffled_set: elements shuffled per document (tensor_utils.py:47-76) + PositionEmbedding with dropout (encoder.py:48-55,251-252)
     ("rico_shuffled", ("rico", "elem_pos_attr", 4, 9, 2, 13, 5, [9, 4, 1, 6], [0, 3, 1, 4])),
+    # --input_dtype sorted_set: elements sorted by (type, left, top, width, height) (tensor_utils.py:14-44) + PositionEmbedding
+    ("crello_sorted", ("crello", "random", 3, 10, 2, 15, 1, [10, 6, 1], None)),
 ])
 BLOCK_TYPE = {"crello_postln": "transformer"}
-INPUT_DTYPE = {"rico_shuffled": "shuffled_set"}
+INPUT_DTYPE = {"rico_shuffled": "shuffled_set", "crello_sorted": "sorted_set"}
 
 
 def rng_script(cols, B, S, tasks, draws, num_blocks, training, pos_dropout=False):
@@ -128,6 +130,9 @@ def run_case(name, spec):
     input_dtype = INPUT_DTYPE.get(name, "set")
     if input_dtype == "shuffled_set":
         method = method if "random" in method else "random_" + method  # keep task 0 reachable for the scripted task ids
+    if input_dtype == "sorted_set":
+        icols_ = OrderedDict((k, v) for k, v in cols.items() if not v.get("demo_only", False))
+        out_perm = O.sort_inputs({k: torch.as_tensor(v) for k, v in batch.items()}, icols_)[1].numpy().astype(np.int32)
     oracle = O.OracleMFP(cols, num_blocks=L, masking_method=method, dropout=RATE, l2=L2, input_dtype=input_dtype)
     if tasks is None:
         tasks = draws.tasks(B, oracle.allowed_tasks)
@@ -137,6 +142,8 @@ def run_case(name, spec):
     for k, v in batch.items():
         out["in/" + k] = v
     perm = None
+    if input_dtype == "sorted_set":
+        out["perm"] = out_perm  # (from the oracle's sort; the sorted columns themselves come from the reference run below)
     if input_dtype == "shuffled_set":
         # the reference shuffles with Python's `random` (tensor_utils.py:60-62); its draws are scripted with the Philox permutation
         perm = draws.shuffle_perm(np.asarray(lengths), S)
@@ -190,8 +197,8 @@ def run_case(name, spec):
         out["mod/" + k] = v.detach().numpy()
     for k, v in captured["masks"].items():
         out["mask/" + k] = v.numpy()
-    if input_dtype == "shuffled_set":
-        for k, v in captured["targets"].items():  # the shuffled batch: what the loss is computed against
+    if input_dtype != "set":
+        for k, v in captured["targets"].items():  # the shuffled / sorted batch: what the loss is computed against
             out["tgt/" + k] = v.detach().numpy()
     for k, v in merged.items():
         if k != "tasks":

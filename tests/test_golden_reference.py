@@ -24,9 +24,10 @@ CASES = {  # name: (dataset, masking_method, num_blocks, seed, step)
     "rico_pos": ("rico", "elem_pos_attr", 2, 5, 1),
     "crello_postln": ("crello", "random", 2, 9, 3),  # --block_type transformer (post-LayerNorm block)
     "rico_shuffled": ("rico", "random_elem_pos_attr", 2, 13, 5),  # --input_dtype shuffled_set (shuffle + PositionEmbedding)
+    "crello_sorted": ("crello", "random", 2, 15, 1),  # --input_dtype sorted_set (sort_inputs + PositionEmbedding)
 }
 BLOCK_TYPE = {"crello_postln": "transformer"}
-INPUT_DTYPE = {"rico_shuffled": "shuffled_set"}
+INPUT_DTYPE = {"rico_shuffled": "shuffled_set", "crello_sorted": "sorted_set"}
 
 
 def projection_vector(name, n):  # same as make_golden.py
@@ -68,7 +69,7 @@ def test_oracle_matches_reference_python(case):
     assert set(g["tasks"].tolist()) <= set(o.allowed_tasks)
     inputs = o.to_torch(batch)
     targets, mod, masks = O.preprocess_for_train(inputs, o.input_columns, tasks, draws, input_dtype)
-    if input_dtype == "shuffled_set":  # the shuffled batch the reference's shuffle_inputs produced (tensor_utils.py:47-76)
+    if input_dtype != "set":  # the batch the reference's shuffle_inputs / sort_inputs produced (tensor_utils.py:14-76)
         for key in o.input_columns:
             assert np.array_equal(targets[key].numpy(), g["tgt/" + key]), key
     # ---- masking path: bit-exact against the reference's preprocess_for_train (mfp.py:95-138)
@@ -150,7 +151,7 @@ def test_engine_matches_reference_python(case, impl):
     staged = m.stage(batch)
     _, _, length, dcols = m._bind(staged)
     tasks = torch.as_tensor(g["tasks"]).cuda()
-    if input_dtype == "shuffled_set":  # shuffle_inputs: permutation and shuffled columns bit-exact against the reference's
+    if input_dtype != "set":  # shuffle_inputs / sort_inputs: permutation and reordered columns bit-exact against the reference's
         perm = torch.zeros((B, S), dtype=torch.int32, device="cuda")
         dcols = eng.shuffle_inputs(length, dcols, seed, step, perm_out=perm)
         torch.cuda.synchronize()
