@@ -1,0 +1,414 @@
+// tf.train.SequenceExample -> padded batch columns: the native side of DataSpec.parse_fn
+// (src/mfp/mfp/data/spec.py:255-287) with the preprocessors of DataSpec._init_preprocessor (spec.py:90-134) and
+// SequenceDiscretizer (data/discretizer.py:6-31) applied while the values are written.
+//
+// Published schema (tensorflow/core/example/{example,feature}.proto):
+//   SequenceExample { Features context = 1; FeatureLists feature_lists = 2; }
+//   Features        { map<string, Feature> feature = 1; }          FeatureLists { map<string, FeatureList> feature_list = 1; }
+//   FeatureList     { repeated Feature feature = 1; }
+//   Feature         { oneof kind { BytesList bytes_list = 1; FloatList float_list = 2; Int64List int64_list = 3; } }
+//   BytesList { repeated bytes value = 1; }  FloatList { repeated float value = 1 [packed]; }  Int64List { repeated int64 value = 1 [packed]; }
+// Semantics restated from tf.io.parse_sequence_example with FixedLenFeature / FixedLenSequenceFeature (no defaults, allow_missing
+// False): a missing key, a wrong kind or a value count != prod(shape) is an error; sequence features are padded to the longest of the
+// batch with 0 / 0.0 / "".
+#include <algorithm>
+#include <atomic>
+#include <memory>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "util.hpp"
+
+namespace {
+
+using fdio::Wire;
+
+struct Column {
+  std::string name;
+  int is_sequence, dtype, width, transform, output;
+  int num_oov, has_mask;
+  std::string mask_str;
+  int64_t mask_int;
+  std::unordered_map<std::string, int32_t> str_index;
+  std::unordered_map<int64_t, int32_t> int_index;
+  std::vector<float> boundaries;
+  int32_t first_vocab_index;  // [mask] + [oov] come first
+  // value a padded step holds after preprocessing; pad_code != OK when the parse default is not representable (OOV without OOV index)
+  int32_t pad_i32 = 0;
+  int pad_code = FDIO_OK;
+};
+
+struct Span { const uint8_t* p = nullptr; size_t n = 0; bool present = false; };
+
+static const char* kDtypeName[] = {"int64", "float", "string"};
+
+struct Value {  // one scalar as it sits in the record
+  int64_t i = 0;
+  float f = 0.f;
+  const uint8_t* s = nullptr;
+  size_t n = 0;
+};
+
+}  // namespace
+
+struct fdio_schema {
+  std::vector<Column> cols;
+  std::unordered_map<std::string, int> context_index, sequence_index;
+};
+
+namespace {
+
+// ---- preprocessors ----------------------------------------------------------------------------------------------------------------
+int lookup_str(const Column& c, const uint8_t* s, size_t n, int32_t* out) {
+  if (c.has_mask && n == c.mask_str.size() && memcmp(s, c.mask_str.data(), n) == 0) { *out = 0; return FDIO_OK; }
+  auto it = c.str_index.find(std::string(reinterpret_cast<const char*>(s), n));
+  if (it != c.str_index.end()) { *out = it->second; return FDIO_OK; }
+  if (c.num_oov == 1) { *out = c.has_mask ? 1 : 0; return FDIO_OK; }
+  return FDIO_ERR_OOV;
+}
+int lookup_int(const Column& c, int64_t v, int32_t* out) {
+  if (c.has_mask && v == c.mask_int) { *out = 0; return FDIO_OK; }
+  auto it = c.int_index.find(v);
+  if (it != c.int_index.end()) { *out = it->second; return FDIO_OK; }
+  if (c.num_oov == 1) { *out = c.has_mask ? 1 : 0; return FDIO_OK; }
+  return FDIO_ERR_OOV;
+}
+inline int32_t bucketize(const Column& c, float x) {  // Bucketize: number of boundaries <= x
+  return int32_t(std::upper_bound(c.boundaries.begin(), c.boundaries.end(), x) - c.boundaries.begin());
+}
+
+// One value -> its place in the output buffer.  `slot` counts scalars from the start of the column buffer.
+int emit(const Column& c, const Value& v, void* out, size_t slot, const uint8_t* record) {
+  if (c.output == FDIO_OUT_SKIP) {
+    if (c.transform != FDIO_LOOKUP) return FDIO_OK;  // still validate lookups so that errors do not depend on the output kind
+  }
+  int32_t r = 0;
+  switch (c.transform) {
+    case FDIO_LOOKUP: {
+      int code = c.dtype == FDIO_STRING ? lookup_str(c, v.s, v.n, &r) : lookup_int(c, v.i, &r);
+      if (code != FDIO_OK) return code;
+      break;
+    }
+    case FDIO_DISCRETIZE:
+      r = bucketize(c, c.dtype == FDIO_INT64 ? float(v.i) : v.f);
+      break;
+    default:
+      if (c.dtype == FDIO_FLOAT32) {
+        if (c.output == FDIO_OUT_FLOAT32) static_cast<float*>(out)[slot] = v.f;
+        return FDIO_OK;
+      }
+      if (c.dtype == FDIO_STRING) {
+        if (c.output == FDIO_OUT_SPAN) {
+          int64_t* o = static_cast<int64_t*>(out) + 2 * slot;
+          o[0] = v.s ? int64_t(v.s - record) : 0;
+          o[1] = int64_t(v.n);
+        }
+        return FDIO_OK;
+      }
+      r = int32_t(v.i);  // tf.cast(int64 -> int32), spec.py:281-285
+  }
+  if (c.output == FDIO_OUT_INT32) static_cast<int32_t*>(out)[slot] = r;
+  return FDIO_OK;
+}
+
+// ---- Feature decoding -----------------------------------------------------------------------------------------------------------
+// Walks the values of one Feature message; calls fn(Value) per scalar.  Returns the count or a negative code.
+// `bulk` (optional): destination of `bulk_n` untransformed floats -- a packed FloatList of exactly that many values is copied in one go.
+template <class Fn>
+int64_t for_each_value(const Column& c, const uint8_t* p, size_t n, Fn&& fn, float* bulk = nullptr, size_t bulk_n = 0) {
+  Wire w(p, n);
+  int64_t count = 0;
+  bool kind_seen = false;
+  while (!w.done()) {
+    uint32_t field, type;
+    if (!w.tag(&field, &type)) return FDIO_ERR_CORRUPT;
+    if (type != 2 || field < 1 || field > 3) { if (!w.skip(type)) return FDIO_ERR_CORRUPT; continue; }
+    const uint8_t* lp; size_t ln;
+    if (!w.bytes(&lp, &ln)) return FDIO_ERR_CORRUPT;
+    const int kind = field == 1 ? FDIO_STRING : field == 2 ? FDIO_FLOAT32 : FDIO_INT64;
+    if (kind != c.dtype) return FDIO_ERR_INVALID;
+    if (kind_seen) count = 0;  // oneof: the last kind on the wire wins; the callers below only see the final pass
+    kind_seen = true;
+    Wire l(lp, ln);
+    while (!l.done()) {
+      uint32_t f2, t2;
+      if (!l.tag(&f2, &t2)) return FDIO_ERR_CORRUPT;
+      if (f2 != 1) { if (!l.skip(t2)) return FDIO_ERR_CORRUPT; continue; }
+      Value v;
+      if (kind == FDIO_STRING) {
+        if (t2 != 2 || !l.bytes(&v.s, &v.n)) return FDIO_ERR_CORRUPT;
+        int code = fn(v, count); if (code != FDIO_OK) return code;
+        ++count;
+      } else if (kind == FDIO_FLOAT32) {
+        if (t2 == 2) {  // packed
+          const uint8_t* fp; size_t fn_;
+          if (!l.bytes(&fp, &fn_) || (fn_ & 3)) return FDIO_ERR_CORRUPT;
+          if (bulk && count == 0 && fn_ == 4 * bulk_n) { memcpy(bulk, fp, fn_); count += int64_t(bulk_n); continue; }
+          for (size_t k = 0; k < fn_; k += 4) { memcpy(&v.f, fp + k, 4); int code = fn(v, count); if (code != FDIO_OK) return code; ++count; }
+        } else if (t2 == 5) {
+          uint32_t bits; if (!l.fixed32(&bits)) return FDIO_ERR_CORRUPT;
+          memcpy(&v.f, &bits, 4);
+          int code = fn(v, count); if (code != FDIO_OK) return code;
+          ++count;
+        } else return FDIO_ERR_CORRUPT;
+      } else {
+        if (t2 == 2) {  // packed varints
+          const uint8_t* ip; size_t in_;
+          if (!l.bytes(&ip, &in_)) return FDIO_ERR_CORRUPT;
+          Wire iv(ip, in_);
+          while (!iv.done()) { uint64_t u; if (!iv.varint(&u)) return FDIO_ERR_CORRUPT; v.i = int64_t(u); int code = fn(v, count); if (code != FDIO_OK) return code; ++count; }
+        } else if (t2 == 0) {
+          uint64_t u; if (!l.varint(&u)) return FDIO_ERR_CORRUPT;
+          v.i = int64_t(u);
+          int code = fn(v, count); if (code != FDIO_OK) return code;
+          ++count;
+        } else return FDIO_ERR_CORRUPT;
+      }
+    }
+  }
+  return kind_seen ? count : int64_t(FDIO_ERR_NOT_FOUND);  // a Feature with no kind set holds no values
+}
+
+// Collects the (key -> message bytes) entries of a Features / FeatureLists map; last occurrence of a key wins (protobuf map rule).
+int collect_map(const uint8_t* p, size_t n, const std::unordered_map<std::string, int>& index, std::vector<Span>* found) {
+  Wire w(p, n);
+  std::string key;
+  while (!w.done()) {
+    uint32_t field, type;
+    if (!w.tag(&field, &type)) return FDIO_ERR_CORRUPT;
+    if (field != 1 || type != 2) { if (!w.skip(type)) return FDIO_ERR_CORRUPT; continue; }
+    const uint8_t* ep; size_t en;
+    if (!w.bytes(&ep, &en)) return FDIO_ERR_CORRUPT;
+    Wire e(ep, en);
+    const uint8_t* kp = nullptr; size_t kn = 0;
+    Span val; val.present = true;  // an entry without a value field is an empty message
+    while (!e.done()) {
+      uint32_t f2, t2;
+      if (!e.tag(&f2, &t2)) return FDIO_ERR_CORRUPT;
+      if (f2 == 1 && t2 == 2) { if (!e.bytes(&kp, &kn)) return FDIO_ERR_CORRUPT; }
+      else if (f2 == 2 && t2 == 2) { if (!e.bytes(&val.p, &val.n)) return FDIO_ERR_CORRUPT; }
+      else if (!e.skip(t2)) return FDIO_ERR_CORRUPT;
+    }
+    key.assign(reinterpret_cast<const char*>(kp), kn);
+    auto it = index.find(key);
+    if (it != index.end()) (*found)[size_t(it->second)] = val;
+  }
+  return FDIO_OK;
+}
+
+int split_example(const uint8_t* rec, size_t len, const fdio_schema& s, std::vector<Span>* found) {
+  std::fill(found->begin(), found->end(), Span());
+  Wire w(rec, len);
+  while (!w.done()) {
+    uint32_t field, type;
+    if (!w.tag(&field, &type)) return FDIO_ERR_CORRUPT;
+    if (type == 2 && (field == 1 || field == 2)) {
+      const uint8_t* p; size_t n;
+      if (!w.bytes(&p, &n)) return FDIO_ERR_CORRUPT;
+      int code = collect_map(p, n, field == 1 ? s.context_index : s.sequence_index, found);
+      if (code != FDIO_OK) return code;
+    } else if (!w.skip(type)) return FDIO_ERR_CORRUPT;
+  }
+  return FDIO_OK;
+}
+
+// Number of Feature entries of a FeatureList.
+int64_t count_steps(const Span& fl) {
+  Wire w(fl.p, fl.n);
+  int64_t steps = 0;
+  while (!w.done()) {
+    uint32_t field, type;
+    if (!w.tag(&field, &type)) return FDIO_ERR_CORRUPT;
+    if (field == 1 && type == 2) { const uint8_t* p; size_t n; if (!w.bytes(&p, &n)) return FDIO_ERR_CORRUPT; ++steps; }
+    else if (!w.skip(type)) return FDIO_ERR_CORRUPT;
+  }
+  return steps;
+}
+
+struct RecordError { int code = FDIO_OK; std::string text; };
+
+void describe(RecordError* e, int code, int32_t b, const Column& c, int64_t step, const char* what) {
+  char buf[400];
+  if (step >= 0) snprintf(buf, sizeof(buf), "record %d, key '%s', index %lld: %s", b, c.name.c_str(), (long long)step, what);
+  else snprintf(buf, sizeof(buf), "record %d, key '%s': %s", b, c.name.c_str(), what);
+  e->code = code;
+  e->text = buf;
+}
+
+const char* what_for(int code, const Column& c, char* scratch, size_t n) {
+  switch (code) {
+    case FDIO_ERR_CORRUPT: return "malformed protobuf";
+    case FDIO_ERR_INVALID: snprintf(scratch, n, "feature kind does not match the column dtype (%s)", kDtypeName[c.dtype]); return scratch;
+    case FDIO_ERR_OOV: return "value is not in the lookup vocabulary and num_oov_indices is 0";
+    case FDIO_ERR_NOT_FOUND: return "feature holds no values";
+    default: return "error";
+  }
+}
+
+void parse_record(const fdio_schema& s, const uint8_t* rec, size_t len, int32_t b, int32_t S, void* const* out, std::vector<Span>* found,
+                  RecordError* err) {
+  char scratch[160];
+  int code = split_example(rec, len, s, found);
+  if (code != FDIO_OK) { err->code = code; err->text = "record " + std::to_string(b) + ": malformed SequenceExample"; return; }
+  for (size_t ci = 0; ci < s.cols.size(); ++ci) {
+    const Column& c = s.cols[ci];
+    const Span& sp = (*found)[ci];
+    void* o = out ? out[ci] : nullptr;
+    const size_t W = size_t(c.width);
+    if (!c.is_sequence) {
+      if (!sp.present) { describe(err, FDIO_ERR_INVALID, b, c, -1, "feature is required but could not be found"); return; }
+      const size_t base = size_t(b) * W;
+      int64_t n = for_each_value(c, sp.p, sp.n, [&](const Value& v, int64_t k) { return k < int64_t(W) ? emit(c, v, o, base + size_t(k), rec) : FDIO_OK; });
+      if (n < 0) { describe(err, n == FDIO_ERR_NOT_FOUND ? int(FDIO_ERR_INVALID) : int(n), b, c, -1, what_for(int(n), c, scratch, sizeof(scratch))); return; }
+      if (n != int64_t(W)) {
+        snprintf(scratch, sizeof(scratch), "number of %s values != expected: values size %lld but output shape holds %zu", kDtypeName[c.dtype], (long long)n, W);
+        describe(err, FDIO_ERR_INVALID, b, c, -1, scratch);
+        return;
+      }
+      continue;
+    }
+    if (!sp.present) { describe(err, FDIO_ERR_INVALID, b, c, -1, "feature list is required but could not be found"); return; }
+    // steps of this document
+    Wire w(sp.p, sp.n);
+    int64_t t = 0;
+    while (!w.done()) {
+      uint32_t field, type;
+      if (!w.tag(&field, &type)) { describe(err, FDIO_ERR_CORRUPT, b, c, t, "malformed protobuf"); return; }
+      if (field != 1 || type != 2) { if (!w.skip(type)) { describe(err, FDIO_ERR_CORRUPT, b, c, t, "malformed protobuf"); return; } continue; }
+      const uint8_t* fp; size_t fn;
+      if (!w.bytes(&fp, &fn)) { describe(err, FDIO_ERR_CORRUPT, b, c, t, "malformed protobuf"); return; }
+      if (t >= S) { describe(err, FDIO_ERR_ARG, b, c, t, "more steps than the batch was sized for"); return; }
+      const size_t base = (size_t(b) * size_t(S) + size_t(t)) * W;
+      float* bulk = (c.transform == FDIO_NONE && c.output == FDIO_OUT_FLOAT32) ? static_cast<float*>(o) + base : nullptr;
+      int64_t n = for_each_value(c, fp, fn, [&](const Value& v, int64_t k) { return k < int64_t(W) ? emit(c, v, o, base + size_t(k), rec) : FDIO_OK; }, bulk, W);
+      if (n < 0) { describe(err, n == FDIO_ERR_NOT_FOUND ? int(FDIO_ERR_INVALID) : int(n), b, c, t, what_for(int(n), c, scratch, sizeof(scratch))); return; }
+      if (n != int64_t(W)) {
+        snprintf(scratch, sizeof(scratch), "number of %s values != expected: values size %lld but output shape holds %zu", kDtypeName[c.dtype], (long long)n, W);
+        describe(err, FDIO_ERR_INVALID, b, c, t, scratch);
+        return;
+      }
+      ++t;
+    }
+    // padding: the parse default put through the preprocessor
+    if (t < S && c.output != FDIO_OUT_SKIP) {
+      if (c.pad_code != FDIO_OK) { describe(err, c.pad_code, b, c, t, "the padding value is not in the lookup vocabulary and num_oov_indices is 0"); return; }
+      const size_t base = (size_t(b) * size_t(S) + size_t(t)) * W, cnt = size_t(S - t) * W;
+      if (c.output == FDIO_OUT_INT32) std::fill_n(static_cast<int32_t*>(o) + base, cnt, c.pad_i32);
+      else if (c.output == FDIO_OUT_FLOAT32) std::fill_n(static_cast<float*>(o) + base, cnt, 0.f);
+      else std::fill_n(static_cast<int64_t*>(o) + 2 * base, 2 * cnt, int64_t(0));
+    }
+  }
+}
+
+template <class Fn>
+int run_threads(int32_t B, int32_t n_threads, Fn&& fn) {  // fn(first, last, RecordError*)
+  int T = std::max(1, std::min<int>(n_threads, B));
+  std::vector<RecordError> errs;
+  errs.resize(size_t(T));
+  if (T == 1) fn(0, B, &errs[0]);
+  else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t) {
+      int32_t lo = int32_t(int64_t(B) * t / T), hi = int32_t(int64_t(B) * (t + 1) / T);
+      th.emplace_back([&, lo, hi, t] { fn(lo, hi, &errs[size_t(t)]); });
+    }
+    for (auto& x : th) x.join();
+  }
+  for (auto& e : errs)  // chunks are in record order: the first failing chunk holds the lowest failing record
+    if (e.code != FDIO_OK) return fdio::fail(e.code, "%s", e.text.c_str());
+  return FDIO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+fdio_schema* fdio_schema_create(const fdio_column* columns, int32_t n) {
+  if (!columns || n <= 0) { fdio::fail(FDIO_ERR_ARG, "fdio_schema_create: no columns"); return nullptr; }
+  auto s = std::make_unique<fdio_schema>();
+  for (int32_t i = 0; i < n; ++i) {
+    const fdio_column& in = columns[i];
+    Column c;
+    if (!in.name) { fdio::fail(FDIO_ERR_ARG, "column %d has no name", i); return nullptr; }
+    c.name = in.name;
+    c.is_sequence = in.is_sequence != 0;
+    c.dtype = in.dtype; c.width = in.width; c.transform = in.transform; c.output = in.output;
+    c.num_oov = in.num_oov_indices; c.has_mask = in.has_mask != 0;
+    c.mask_int = in.mask_int;
+    if (in.mask_str) c.mask_str = in.mask_str;
+    if (c.dtype < FDIO_INT64 || c.dtype > FDIO_STRING || c.width <= 0 || c.transform < FDIO_NONE || c.transform > FDIO_DISCRETIZE ||
+        c.output < FDIO_OUT_INT32 || c.output > FDIO_OUT_SKIP) {
+      fdio::fail(FDIO_ERR_ARG, "column '%s': invalid dtype / width / transform / output", in.name);
+      return nullptr;
+    }
+    const bool yields_int = c.transform != FDIO_NONE || c.dtype == FDIO_INT64;
+    const bool ok = c.output == FDIO_OUT_SKIP || (yields_int && c.output == FDIO_OUT_INT32) ||
+                    (c.transform == FDIO_NONE && c.dtype == FDIO_FLOAT32 && c.output == FDIO_OUT_FLOAT32) ||
+                    (c.transform == FDIO_NONE && c.dtype == FDIO_STRING && c.output == FDIO_OUT_SPAN);
+    if (!ok) { fdio::fail(FDIO_ERR_ARG, "column '%s': output kind does not fit dtype and transform", in.name); return nullptr; }
+    if (c.transform == FDIO_LOOKUP) {
+      if (c.dtype == FDIO_FLOAT32) { fdio::fail(FDIO_ERR_ARG, "column '%s': lookup needs a string or int64 column", in.name); return nullptr; }
+      if (c.num_oov < 0 || c.num_oov > 1) {
+        fdio::fail(FDIO_ERR_UNSUPPORTED, "column '%s': num_oov_indices = %d (hashed OOV buckets) is not supported", in.name, c.num_oov);
+        return nullptr;
+      }
+      c.first_vocab_index = (c.has_mask ? 1 : 0) + c.num_oov;
+      for (int32_t k = 0; k < in.vocab_size; ++k) {
+        bool fresh = c.dtype == FDIO_STRING ? c.str_index.emplace(in.vocab_str[k], c.first_vocab_index + k).second
+                                            : c.int_index.emplace(in.vocab_int[k], c.first_vocab_index + k).second;
+        if (!fresh) { fdio::fail(FDIO_ERR_ARG, "column '%s': repeated vocabulary term at position %d", in.name, k); return nullptr; }
+      }
+      c.pad_code = c.dtype == FDIO_STRING ? lookup_str(c, reinterpret_cast<const uint8_t*>(""), 0, &c.pad_i32) : lookup_int(c, 0, &c.pad_i32);
+    } else if (c.transform == FDIO_DISCRETIZE) {
+      if (c.dtype == FDIO_STRING || in.n_boundaries < 0 || (in.n_boundaries && !in.boundaries)) {
+        fdio::fail(FDIO_ERR_ARG, "column '%s': discretize needs a numeric column and boundaries", in.name);
+        return nullptr;
+      }
+      c.boundaries.assign(in.boundaries, in.boundaries + in.n_boundaries);
+      if (!std::is_sorted(c.boundaries.begin(), c.boundaries.end())) { fdio::fail(FDIO_ERR_ARG, "column '%s': boundaries must ascend", in.name); return nullptr; }
+      c.pad_i32 = bucketize(c, 0.f);
+    }
+    auto& index = c.is_sequence ? s->sequence_index : s->context_index;
+    if (!index.emplace(c.name, int(i)).second) { fdio::fail(FDIO_ERR_ARG, "column '%s' appears twice", in.name); return nullptr; }
+    s->cols.push_back(std::move(c));
+  }
+  return s.release();
+}
+
+void fdio_schema_destroy(fdio_schema* s) { delete s; }
+
+int fdio_batch_steps(const fdio_schema* s, const uint8_t* const* records, const uint64_t* lens, int32_t B, int32_t* max_steps, int32_t n_threads) {
+  if (!s || !records || !lens || !max_steps || B < 0) return fdio::fail(FDIO_ERR_ARG, "fdio_batch_steps: bad argument");
+  return run_threads(B, n_threads, [&](int32_t lo, int32_t hi, RecordError* err) {
+    std::vector<Span> found(s->cols.size());
+    for (int32_t b = lo; b < hi; ++b) {
+      if (split_example(records[b], lens[b], *s, &found) != FDIO_OK) {
+        err->code = FDIO_ERR_CORRUPT; err->text = "record " + std::to_string(b) + ": malformed SequenceExample"; return;
+      }
+      int64_t m = 0;
+      for (size_t ci = 0; ci < s->cols.size(); ++ci) {
+        if (!s->cols[ci].is_sequence || !found[ci].present) continue;
+        int64_t n = count_steps(found[ci]);
+        if (n < 0) { describe(err, FDIO_ERR_CORRUPT, b, s->cols[ci], -1, "malformed protobuf"); return; }
+        m = std::max(m, n);
+      }
+      max_steps[b] = int32_t(m);
+    }
+  });
+}
+
+int fdio_parse_batch(const fdio_schema* s, const uint8_t* const* records, const uint64_t* lens, int32_t B, int32_t S, void* const* out,
+                     int32_t n_threads) {
+  if (!s || !records || !lens || !out || B < 0 || S < 0) return fdio::fail(FDIO_ERR_ARG, "fdio_parse_batch: bad argument");
+  for (size_t ci = 0; ci < s->cols.size(); ++ci)
+    if (s->cols[ci].output != FDIO_OUT_SKIP && !out[ci] && B > 0 && (S > 0 || !s->cols[ci].is_sequence))
+      return fdio::fail(FDIO_ERR_ARG, "fdio_parse_batch: no output buffer for column '%s'", s->cols[ci].name.c_str());
+  return run_threads(B, n_threads, [&](int32_t lo, int32_t hi, RecordError* err) {
+    std::vector<Span> found(s->cols.size());
+    for (int32_t b = lo; b < hi && err->code == FDIO_OK; ++b) parse_record(*s, records[b], lens[b], b, S, out, &found, err);
+  });
+}
+
+}  // extern "C"

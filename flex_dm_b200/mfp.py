@@ -20,6 +20,7 @@ from typing import Dict, Iterable, List, Optional
 import numpy as np
 import torch
 
+from . import checkpoint
 from .engine import Engine
 from .masking import get_task_names
 from .parallel import all_reduce_gradient_slice, all_reduce_gradients, broadcast_parameters, reduce_metric_rows
@@ -457,12 +458,25 @@ class MFP:
         self.engine.set_weights(weights)
 
     def save_weights(self, path: str):
-        """train.py:94-97.  Stored as ``<path>.npz`` keyed by the reference's variable paths."""
+        """train.py:94-97, helpers/callbacks.py:49-56.  Like Keras, the file format follows the path: anything that is not ``.npz`` is a
+        TensorFlow object-based checkpoint (``<path>.index`` + ``<path>.data-00000-of-00001``, variables keyed by the reference's
+        attribute paths; written by ``libflexdm_io.so``); ``.npz`` keeps the flat numpy archive."""
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-        np.savez(path if path.endswith(".npz") else path + ".npz", **self.engine.get_weights())
+        if path.endswith((".h5", ".hdf5", ".keras")):
+            raise NotImplementedError("HDF5 weight files are not supported; the reference writes TensorFlow checkpoints (best.ckpt / final.ckpt)")
+        if path.endswith(".npz"):
+            np.savez(path, **self.engine.get_weights())
+        else:
+            checkpoint.save_variables(path, self.engine.get_weights())
 
     def load_weights(self, path: str):
-        """train.py:67-69, eval.py:169-172."""
-        path = path if path.endswith(".npz") else path + ".npz"
-        with np.load(path) as data:
+        """train.py:67-69, eval.py:169-172: a TensorFlow checkpoint prefix (``.../best.ckpt``) or an ``.npz`` archive of ``save_weights``."""
+        if checkpoint.is_tf_checkpoint(path):
+            wanted = OrderedDict((name, self.engine.variable_shape(name)) for name in self.engine.variables)
+            self.engine.set_weights(checkpoint.load_variables(path, wanted))
+            return
+        npz = path if path.endswith(".npz") else path + ".npz"
+        if not os.path.exists(npz):
+            raise FileNotFoundError("Neither a TensorFlow checkpoint (%s.index) nor %s exists" % (path, npz))
+        with np.load(npz) as data:
             self.engine.set_weights({k: data[k] for k in data.files})
