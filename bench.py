@@ -145,6 +145,50 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def tfrecord_leg(model, timed, steps):
+    """Trains from a TFRecord export of one synthetic batch (256 full-length crello documents, reshuffled every pass): every step the
+    native reader parses 256 SequenceExamples (135 MB of columns) on the host threads into pinned memory."""
+    import shutil
+    import tempfile
+    import time
+
+    import torch
+
+    from flex_dm_b200.data import DevicePrefetcher
+    from flex_dm_b200.dataspec import DataSpec
+    from flex_dm_b200.synthetic import write_synthetic_dataset
+
+    root = tempfile.mkdtemp(prefix="flexdm_tfrecord_")
+    try:
+        write_synthetic_dataset(root, "crello", {"train": B_PER_GPU}, seq_len=SEQ_LEN, lengths="full", shards=2, seed=123)
+        spec = DataSpec(os.path.join(root, "crello-spec.yml"), root, batch_size=B_PER_GPU)
+        dataset = spec.make_dataset("train", shuffle=True, repeat=True, prefetch=3, pad_to=SEQ_LEN)
+        # host-only rate of the parser (no GPU work in flight)
+        it = iter(spec.make_dataset("train", shuffle=True, repeat=True, prefetch=0, pad_to=SEQ_LEN))
+        for _ in range(3):
+            next(it)
+        t0 = time.perf_counter()
+        n_host = 10
+        for _ in range(n_host):
+            next(it)
+        host_ms = (time.perf_counter() - t0) * 1e3 / n_host
+        feeder = DevicePrefetcher(model, iter(dataset))
+        row_host = torch.empty((model.engine.metrics_width,), dtype=torch.float32).pin_memory()
+
+        def step(i):
+            row_host.copy_(model.train_step(next(feeder), staged=True), non_blocking=True)
+
+        for i in range(3):
+            step(i)
+        ms = timed(step, steps)
+        return {"value": B_PER_GPU * SEQ_LEN * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+                "host_parse_ms_per_batch": host_ms, "host_threads": spec._threads,
+                "source": "TFRecord shards of tf.train.SequenceExample (256 synthetic crello documents, S=128) -> DataSpec.make_dataset(shuffle, repeat, "
+                          "prefetch=3) -> libflexdm_io parse_batch into pinned memory -> DevicePrefetcher -> MFP.train_step"}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -154,6 +198,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end and roofline legs (ncu launch-list runs)")
+    ap.add_argument("--no-tfrecord", action="store_true", help="skip the TFRecord input-pipeline leg (N=1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -256,6 +301,12 @@ def main():
     last = model.metrics_from_row(rows_host[args.steps - 1])
     assert np.isfinite(last["loss"]), last
 
+    # ---- input-side leg (N = 1): the same step fed from TFRecord files through DataSpec.make_dataset (native SequenceExample parser on
+    # host threads -> pinned batches -> DevicePrefetcher), i.e. train.py's own data path; reported beside e2e, not instead of it.
+    input_pipeline = None
+    if world == 1 and not args.no_tfrecord:
+        input_pipeline = tfrecord_leg(model, timed, min(args.steps, 40))
+
     # ---- roofline of the dominant kernel (the TF32 tcgen05 GEMM): separate instrumented pass, CUDA events per launch
     train_flops, gemm_flops = flops_per_element(cols, SEQ_LEN, NUM_BLOCKS, LATENT)
     prof_steps = 3
@@ -316,6 +367,8 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks}
+        if input_pipeline is not None:
+            line["input_pipeline"] = input_pipeline
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
