@@ -433,3 +433,16 @@ from . import keras  # noqa: E402,F401
 data = _module(__name__ + ".data")
 data.experimental = _module(__name__ + ".data.experimental", AUTOTUNE=-1)
 io = _module(__name__ + ".io")
+__version__ = "2.8.0"  # README.md:10 of the reference; selects the non-2.3/2.4 branches of data/spec.py and data/discretizer.py
+
+# input side (data/spec.py, data/discretizer.py): see data_io.py
+from . import data_io as _data_io  # noqa: E402
+
+io.FixedLenFeature = _data_io.FixedLenFeature
+io.FixedLenSequenceFeature = _data_io.FixedLenSequenceFeature
+io.parse_sequence_example = _data_io.parse_sequence_example
+io.gfile = _module(__name__ + ".io.gfile", GFile=_data_io._GFile)
+_experimental = keras._mod(keras.__name__ + ".layers.experimental")
+_experimental.preprocessing = keras._mod(keras.__name__ + ".layers.experimental.preprocessing", StringLookup=_data_io.StringLookup,
+                                         IntegerLookup=_data_io.IntegerLookup, Discretization=_data_io.Discretization)
+keras.layers.experimental = _experimental

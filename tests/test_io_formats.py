@@ -589,3 +589,67 @@ def test_checkpoint_corruption_is_detected(tmp_path):
         checkpoint.Bundle(prefix)
     with pytest.raises(FileNotFoundError):
         checkpoint.Bundle(str(tmp_path / "missing.ckpt"))
+
+
+# ------------------------------------------------------------------------------------------------------------------------ reference-run goldens
+def _normalise(x):
+    """Tuples -> lists, numpy / torch scalars -> Python, bytes -> str: the shape the golden JSON has."""
+    if isinstance(x, dict):
+        return {k: _normalise(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_normalise(v) for v in x]
+    if isinstance(x, bytes):
+        return x.decode("utf-8")
+    if isinstance(x, np.ndarray):
+        return _normalise(x.tolist())
+    if isinstance(x, np.generic):
+        return _normalise(x.item())
+    return x
+
+
+def _approx_equal(a, b, path=""):
+    if isinstance(b, dict):
+        assert isinstance(a, dict) and sorted(a) == sorted(b), path
+        for k in b:
+            _approx_equal(a[k], b[k], path + "/" + str(k))
+    elif isinstance(b, list):
+        assert isinstance(a, list) and len(a) == len(b), path
+        for i, (x, y) in enumerate(zip(a, b)):
+            _approx_equal(x, y, "%s[%d]" % (path, i))
+    elif isinstance(b, float):
+        assert a == pytest.approx(b, rel=1e-12, abs=1e-12), path
+    else:
+        assert a == b, (path, a, b)
+
+
+@pytest.mark.parametrize("name", ["crello", "rico"])
+def test_dataspec_matches_the_reference_run_golden(name):
+    """``tests/golden/make_dataspec_golden.py`` ran the reference's own ``DataSpec`` (its YAML specs, ``_create_lookup``,
+    ``make_input_columns``, ``parse_fn``, ``unbatch``) on the committed TFRecord fixture; this class must reproduce every output."""
+    import json
+
+    golden_dir = os.path.join(ROOT, "tests", "golden")
+    meta = json.load(open(os.path.join(golden_dir, "dataspec_%s.json" % name)))
+    arrays = np.load(os.path.join(golden_dir, "dataspec_%s.npz" % name))
+    root = os.path.join(golden_dir, "dataspec_" + name)
+    spec = DataSpec(name, root, batch_size=4)
+    # the schema restated in BUILTIN_SPECS is the reference's YAML
+    assert list(spec.columns.keys()) == meta["column_order"]
+    _approx_equal(_normalise(json.loads(json.dumps(spec.columns))), meta["spec_columns"])
+    _approx_equal(_normalise(spec.make_input_columns()), meta["input_columns"])
+    assert spec.size("train") == meta["size"] and spec.steps_per_epoch("train") == meta["steps_per_epoch"]
+    shard = TFRecordFile(os.path.join(root, "train-00000-of-00001.tfrecord"), verify_crc=2)
+    records = [shard.record(i) for i in range(len(shard))]
+    assert records == DO.read_tfrecord(shard.path)
+    batch = spec.parse_fn(records)
+    assert sorted(k for k in batch if not isinstance(batch[k], np.ndarray)) == sorted(arrays.files)
+    for k in arrays.files:
+        got = batch[k].numpy()
+        assert str(got.dtype) == meta["dtypes"][k] and got.shape == arrays[k].shape and np.array_equal(got, arrays[k]), k
+    for k, v in meta["strings"].items():
+        assert _normalise(batch[k]) == v, k
+    _approx_equal(_normalise(spec.unbatch(batch)), meta["unbatch"])
+    # the same batch through the dataset iterator
+    first = next(iter(spec.make_dataset("train", batch_size=len(records), shuffle=False)))
+    for k in arrays.files:
+        assert np.array_equal(first[k].numpy(), arrays[k]), k
