@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(kD / 4) pos_embed_bwd_kernel(const float* __re
 // to their variables.  The Dense kernels' gradients are X^T . dh0m GEMMs, dh0m = dh0 with the rows of special-token
 // elements zeroed (written by the last LayerNorm-backward launch, transformer.cu).
 __global__ void __launch_bounds__(32 * kTokPerCta) embed_onehot_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs mod,
-                                                                       const unsigned char* __restrict__ flags, int T, float* __restrict__ onehot) {
+                                                                       const unsigned char* __restrict__ flags, int T, float* __restrict__ onehot,
+                                                                       const int* __restrict__ ctx_row, int S) {
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * kTokPerCta + (threadIdx.x >> 5);
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(32 * kTokPerCta) embed_onehot_kernel(const __g
   float4* out = reinterpret_cast<float4*>(onehot + (size_t)t * sc.Rp);
   const int n4 = sc.Rp >> 2;
   for (int j = lane; j < n4; j += 32) out[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ctx_row && (t % S) == __ldg(ctx_row + t / S)) return;  // the context token's row: its gradient belongs to the context table only
   __syncwarp();
   for (int l = lane; l < sc.n_lookups; l += 32) {
     const int f = sc.lk_field[l], c = sc.lk_sub[l];
@@ -142,8 +144,52 @@ int launch_pos_embed_bwd(const float* dh0, int B, int S, float rate, uint32_t se
   return MFP_OK;
 }
 
-int launch_embed_onehot(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, int T, float* onehot, cudaStream_t st) {
-  MFP_CUDA_OK(launch_pdl(embed_onehot_kernel, (T + kTokPerCta - 1) / kTokPerCta, 32 * kTokPerCta, 0, st, sc, mod, flags, T, onehot));
+// h0[b, length[b] + 1, :] = table[ids[b]] and ctx_row[b] = length[b] + 1.  grid = B, block = D/4.  A document that fills all S rows has
+// no room for the token (the host pads the batch by one row): it is left without one and ctx_row[b] = S (matches no row; the attention
+// kernels clamp their length to S).
+__global__ void __launch_bounds__(kD / 4) context_token_kernel(const float* __restrict__ table, int rows, const int* __restrict__ ids,
+                                                               const int* __restrict__ length, int S, float* __restrict__ h0, int* __restrict__ ctx_row) {
+  pdl_wait();
+  const int b = blockIdx.x, q = threadIdx.x;
+  const int n = __ldg(length + b) + 1;
+  if (n >= S) {
+    if (q == 0) ctx_row[b] = S;
+    return;
+  }
+  const int id = min(max(__ldg(ids + b), 0), rows - 1);
+  reinterpret_cast<float4*>(h0 + ((size_t)b * S + n) * kD)[q] = __ldg(reinterpret_cast<const float4*>(table + (size_t)id * kD) + q);
+  if (q == 0) ctx_row[b] = n;
+}
+
+// d(context table)[r] = sum over the documents whose id is r of dh0[b, ctx_row[b]] (fixed order: deterministic).  grid = rows, block = D/4.
+__global__ void __launch_bounds__(kD / 4) context_token_bwd_kernel(const float* __restrict__ dh0, const int* __restrict__ ids, const int* __restrict__ ctx_row,
+                                                                   int rows, int B, int S, float* __restrict__ dtable) {
+  pdl_wait();
+  const int r = blockIdx.x, q = threadIdx.x;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b = 0; b < B; ++b) {
+    const int row = __ldg(ctx_row + b);
+    if (row >= S || min(max(__ldg(ids + b), 0), rows - 1) != r) continue;
+    const float4 g = reinterpret_cast<const float4*>(dh0 + ((size_t)b * S + row) * kD)[q];
+    acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+  }
+  reinterpret_cast<float4*>(dtable + (size_t)r * kD)[q] = acc;
+}
+
+int launch_context_token(const float* table, int rows, const int* ids, const int* length, int B, int S, float* h0, int* ctx_row, cudaStream_t st) {
+  MFP_CUDA_OK(launch_pdl(context_token_kernel, B, kD / 4, 0, st, table, rows, ids, length, S, h0, ctx_row));
+  MFP_CUDA_OK(cudaGetLastError());
+  return MFP_OK;
+}
+
+int launch_context_token_bwd(const float* dh0, const int* ids, const int* ctx_row, int rows, int B, int S, float* dtable, cudaStream_t st) {
+  MFP_CUDA_OK(launch_pdl(context_token_bwd_kernel, rows, kD / 4, 0, st, dh0, ids, ctx_row, rows, B, S, dtable));
+  MFP_CUDA_OK(cudaGetLastError());
+  return MFP_OK;
+}
+
+int launch_embed_onehot(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, int T, float* onehot, cudaStream_t st, const int* ctx_row, int S) {
+  MFP_CUDA_OK(launch_pdl(embed_onehot_kernel, (T + kTokPerCta - 1) / kTokPerCta, 32 * kTokPerCta, 0, st, sc, mod, flags, T, onehot, ctx_row, S));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }

@@ -29,7 +29,7 @@ struct BlockLayout {
 struct Workspace {
   // byte offsets into the caller's workspace
   size_t vars, flags, perm, x, ln1, qkv, attn, xmid, ln2, hid, stats, lse, logits, dlogits, dx, dtmp, dy, dqkv, dhid, dattn, dh0m, onehot, rowgrad, part, idx_true, idx_pred,
-      norms, total;
+      norms, ctx_row, total;
 };
 
 }  // namespace mfp
@@ -44,6 +44,8 @@ struct mfp_engine {
   std::vector<BlockLayout> blocks;
   long long wh = 0, bh = 0, param_count = 0;
   long long pos_off = -1;  // PositionEmbedding table (input_dtype != "set"), rows = length_input_dim + 1
+  long long ctx_off = -1;  // --context id / length: embedding table of the context token, rows = cfg.context_rows
+  const int32_t* ctx_ids = nullptr;  // --context id: device task ids of the current batch (mfp_set_context_ids)
   // bound state
   int B = 0, S = 0, T = 0;
   uint8_t* ws = nullptr;
@@ -115,6 +117,10 @@ static void build_layout(mfp_engine* h) {
   if (h->cfg.input_dtype != 0) {  // PositionEmbedding(latent_dim, maxlen = length input_dim) -> Embedding(maxlen + 1, D): encoder.py:48-55, transformer.py:17-21
     h->pos_off = alloc((long long)(h->cfg.length_input_dim + 1) * D);
     add_var(h, "model/encoder/input_layer/const/embeddings/embeddings", h->pos_off, h->cfg.length_input_dim + 1, D, D, 1);
+  }
+  if (h->cfg.context != 0) {  // encoder.py:96-110: input_layer["task"] / input_layer["length"]
+    h->ctx_off = alloc((long long)h->cfg.context_rows * D);
+    add_var(h, std::string("model/encoder/input_layer/") + (h->cfg.context == 1 ? "task" : "length") + "/embeddings", h->ctx_off, h->cfg.context_rows, D, D, 1);
   }
   // backward stages: 0 = heads, 1..L = blocks L-1..0, L+1 = encoder; the layout is encoder | blocks | heads, each contiguous
   h->stage_lo.assign(L + 2, 0);
@@ -202,6 +208,7 @@ static Workspace plan_workspace(const mfp_engine* h, int B, int S) {
   w.idx_true = take(T * sizeof(int));
   w.idx_pred = take(T * sizeof(int));
   w.norms = take(2 * 16 * h->vars.size() * fl);
+  w.ctx_row = take((size_t)B * sizeof(int));
   w.total = cur;
   return w;
 }
@@ -291,6 +298,9 @@ int mfp_create(const mfp_config* cfg, const mfp_field_desc* fields, mfp_engine**
   if (cfg->num_blocks < 1 || cfg->num_blocks > 64) { set_error("mfp_create: num_blocks out of range"); return MFP_ERR_ARG; }
   if (cfg->input_dtype < 0 || cfg->input_dtype > 2) { set_error("mfp_create: input_dtype must be 0 (set), 1 (shuffled_set) or 2 (sorted_set)"); return MFP_ERR_ARG; }
   if (cfg->input_dtype != 0 && cfg->length_input_dim < 1) { set_error("mfp_create: shuffled_set / sorted_set need length_input_dim"); return MFP_ERR_ARG; }
+  if (cfg->context < 0 || cfg->context > 2) { set_error("mfp_create: context must be 0 (None), 1 (id) or 2 (length)"); return MFP_ERR_ARG; }
+  if (cfg->context != 0 && cfg->context_rows < 1) { set_error("mfp_create: context needs context_rows >= 1"); return MFP_ERR_ARG; }
+  if (cfg->context != 0 && cfg->input_dtype != 0) { set_error("mfp_create: context with shuffled_set / sorted_set is not supported"); return MFP_ERR_UNSUPPORTED; }
   if (cfg->block_type != 0 && cfg->block_type != 1) { set_error("mfp_create: block_type must be 0 (deepsvg) or 1 (transformer)"); return MFP_ERR_ARG; }
   mfp_engine* h = new mfp_engine();
   h->cfg = *cfg;
@@ -382,6 +392,7 @@ int mfp_bind(mfp_engine* h, int32_t B, int32_t S, void* workspace, int64_t works
     set_error("mfp_bind: S = %d exceeds the PositionEmbedding table (%d rows)", S, h->cfg.length_input_dim + 1);
     return MFP_ERR_ARG;
   }
+  if (h->cfg.context != 0 && S < 2) { set_error("mfp_bind: a context token needs S >= 2 (one row beyond the longest document)"); return MFP_ERR_ARG; }
   const Workspace w = plan_workspace(h, B, S);
   if ((size_t)workspace_bytes < w.total) { set_error("mfp_bind: workspace too small (%lld < %zu)", (long long)workspace_bytes, w.total); return MFP_ERR_ARG; }
   if (reinterpret_cast<uintptr_t>(workspace) & 255) { set_error("mfp_bind: workspace must be 256-byte aligned"); return MFP_ERR_ARG; }
@@ -442,6 +453,13 @@ int mfp_mask_for_test(mfp_engine* h, const mfp_batch* inputs, const uint8_t* con
   return launch_mask_corrupt(h->sc, to_batch(h, inputs), nullptr, &tm, h->B, h->S, 0, 0, out, (cudaStream_t)stream, wsp<unsigned char>(h, h->off.flags));
 }
 
+int mfp_set_context_ids(mfp_engine* h, const int32_t* task_ids) {
+  if (!h) { set_error("mfp_set_context_ids: null engine"); return MFP_ERR_ARG; }
+  if (h->cfg.context != 1) { set_error("mfp_set_context_ids: the engine was not created with context = id"); return MFP_ERR_STATE; }
+  h->ctx_ids = task_ids;
+  return MFP_OK;
+}
+
 int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint32_t seed, uint32_t step, float* logits_out, void* stream) {
   MFP_TRY(check_bound(h));
   cudaStream_t st = (cudaStream_t)stream;
@@ -472,6 +490,16 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
     ep.rowflag = flags + (size_t)fd.num_slot * T;
     MFP_TRY(gemm(h, reinterpret_cast<const float*>(mod.cols[f]), 0, fd.C, P + fd.kernel_off, 1, D, T, D, fd.C, ep, 1, st));
   }
+  // ---- context token (encoder.py:231-249): one more row per document, attended to by every element
+  const int* attn_len = modified->length;
+  if (h->cfg.context != 0) {
+    const int* ids = h->cfg.context == 1 ? h->ctx_ids : modified->length;
+    if (!ids) { set_error("mfp_forward: context = id needs mfp_set_context_ids first"); return MFP_ERR_STATE; }
+    int* ctx_row = wsp<int>(h, h->off.ctx_row);
+    MFP_TRY(launch_context_token(P + h->ctx_off, h->cfg.context_rows, ids, modified->length, h->B, h->S, x, ctx_row, st));
+    h->launches++;
+    attn_len = ctx_row;
+  }
   // ---- blocks (transformer.py:208-229)
   for (int i = 0; i < L; ++i) {
     const BlockLayout& b = h->blocks[i];
@@ -494,8 +522,8 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
       MFP_TRY(gemm(h, xi, 0, D, P + b.wqkv, 1, 3 * D, T, 3 * D, D, q1, 1, st));
       {
         ProfScope prof(h, MFP_PROFILE_ATTENTION, st, 4.0 * T * (3.0 * D + D) + 4.0 * h->B * kH * h->S);
-        if (h->gemm_impl == 0 && h->S <= 128) MFP_TRY(launch_attention_fwd_tc(h->maps, qkv, modified->length, h->B, h->S, attn, lse, st));
-        else MFP_TRY(launch_attention_fwd(qkv, modified->length, h->B, h->S, attn, lse, st));
+        if (h->gemm_impl == 0 && h->S <= 128) MFP_TRY(launch_attention_fwd_tc(h->maps, qkv, attn_len, h->B, h->S, attn, lse, st));
+        else MFP_TRY(launch_attention_fwd(qkv, attn_len, h->B, h->S, attn, lse, st));
       }
       GemmEpilogue q2 = make_epilogue(xmid, D);
       q2.bias = P + b.bo;
@@ -522,8 +550,8 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
     MFP_TRY(gemm(h, ln1, 0, D, P + b.wqkv, 1, 3 * D, T, 3 * D, D, e1, 1, st));
     {
       ProfScope prof(h, MFP_PROFILE_ATTENTION, st, 4.0 * T * (3.0 * D + D) + 4.0 * h->B * kH * h->S);  // qkv in, out + lse
-      if (h->gemm_impl == 0 && h->S <= 128) MFP_TRY(launch_attention_fwd_tc(h->maps, qkv, modified->length, h->B, h->S, attn, lse, st));
-      else MFP_TRY(launch_attention_fwd(qkv, modified->length, h->B, h->S, attn, lse, st));
+      if (h->gemm_impl == 0 && h->S <= 128) MFP_TRY(launch_attention_fwd_tc(h->maps, qkv, attn_len, h->B, h->S, attn, lse, st));
+      else MFP_TRY(launch_attention_fwd(qkv, attn_len, h->B, h->S, attn, lse, st));
     }
     GemmEpilogue e2 = make_epilogue(xmid, D);
     e2.bias = P + b.bo;
@@ -597,6 +625,9 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
   const size_t TD = (size_t)T * D;
   const bool drop = training && h->cfg.dropout > 0.f;
   float* x = wsp<float>(h, h->off.x);
+  // --context: the forward pass left every document's context-token row in the workspace; it is also the attention length array
+  const int* ctx_row = h->cfg.context != 0 ? wsp<int>(h, h->off.ctx_row) : nullptr;
+  const int* attn_len = ctx_row ? ctx_row : modified->length;
   float* dlogits = wsp<float>(h, h->off.dlogits);
   float* dx = wsp<float>(h, h->off.dx);
   float* dtmp = wsp<float>(h, h->off.dtmp);
@@ -648,8 +679,8 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
       MFP_TRY(gemm(h, dy1, 0, D, P + b.wo, 0, D, T, D, D, make_epilogue(dattn, D), 1, st));
       {
         ProfScope prof(h, MFP_PROFILE_ATTENTION, st, 4.0 * T * (3.0 * D + D + D + 3.0 * D) + 4.0 * h->B * kH * h->S);
-        if (h->gemm_impl == 0 && h->S <= 128) MFP_TRY(launch_attention_bwd_tc(h->maps, qkv, attn, lse, dattn, modified->length, h->B, h->S, dqkv, st));
-        else MFP_TRY(launch_attention_bwd(qkv, attn, lse, dattn, modified->length, h->B, h->S, dqkv, st));
+        if (h->gemm_impl == 0 && h->S <= 128) MFP_TRY(launch_attention_bwd_tc(h->maps, qkv, attn, lse, dattn, attn_len, h->B, h->S, dqkv, st));
+        else MFP_TRY(launch_attention_bwd(qkv, attn, lse, dattn, attn_len, h->B, h->S, dqkv, st));
       }
       MFP_TRY(gemm(h, xi, 1, D, dqkv, 1, 3 * D, D, 3 * D, T, make_epilogue(G + b.wqkv, 3 * D), wgrad_splits(D, 3 * D, T), st, G + b.bqkv));
       GemmEpilogue p2 = make_epilogue(dx, D);  // d(block input) = dz1 (in dx) + dqkv . Wqkv^T, in place
@@ -688,8 +719,8 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
     MFP_TRY(gemm(h, dy, 0, D, P + b.wo, 0, D, T, D, D, make_epilogue(dattn, D), 1, st));
     {
       ProfScope prof(h, MFP_PROFILE_ATTENTION, st, 4.0 * T * (3.0 * D + D + D + 3.0 * D) + 4.0 * h->B * kH * h->S);  // qkv, out, dout in; dqkv out
-      if (h->gemm_impl == 0 && h->S <= 128) MFP_TRY(launch_attention_bwd_tc(h->maps, qkv, attn, lse, dattn, modified->length, h->B, h->S, dqkv, st));
-      else MFP_TRY(launch_attention_bwd(qkv, attn, lse, dattn, modified->length, h->B, h->S, dqkv, st));
+      if (h->gemm_impl == 0 && h->S <= 128) MFP_TRY(launch_attention_bwd_tc(h->maps, qkv, attn, lse, dattn, attn_len, h->B, h->S, dqkv, st));
+      else MFP_TRY(launch_attention_bwd(qkv, attn, lse, dattn, attn_len, h->B, h->S, dqkv, st));
     }
     MFP_TRY(gemm(h, ln1, 1, D, dqkv, 1, 3 * D, D, 3 * D, T, make_epilogue(G + b.wqkv, 3 * D), wgrad_splits(D, 3 * D, T), st, G + b.bqkv));
     MFP_TRY(gemm(h, dqkv, 0, 3 * D, P + b.wqkv, 0, 3 * D, T, D, 3 * D, make_epilogue(dtmp, D), 1, st));
@@ -706,7 +737,7 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
   const unsigned char* flags = wsp<unsigned char>(h, h->off.flags);
   float* onehot = wsp<float>(h, h->off.onehot);
   float* rowgrad = wsp<float>(h, h->off.rowgrad);
-  MFP_TRY(launch_embed_onehot(sc, mod, flags, T, onehot, st));
+  MFP_TRY(launch_embed_onehot(sc, mod, flags, T, onehot, st, ctx_row, h->S));
   MFP_CUDA_OK(cudaMemsetAsync(rowgrad, 0, (size_t)sc.Rp * D * sizeof(float), st));
   MFP_TRY(gemm(h, onehot, 1, sc.Rp, dx, 1, D, sc.R, D, T, make_epilogue(rowgrad, D), wgrad_splits(sc.R, D, T), st));
   for (int f = 0; f < sc.F; ++f) {
@@ -717,6 +748,12 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
   }
   MFP_TRY(launch_embed_scatter(sc, rowgrad, G, st));
   h->launches += 2;
+  if (ctx_row) {  // d(context table): the token rows of dh0, summed per id (the one-hot rows of those positions are zero)
+    const int* ids = h->cfg.context == 1 ? h->ctx_ids : modified->length;
+    if (!ids) { set_error("mfp_backward: context = id needs mfp_set_context_ids first"); return MFP_ERR_STATE; }
+    MFP_TRY(launch_context_token_bwd(dx, ids, ctx_row, h->cfg.context_rows, h->B, h->S, G + h->ctx_off, st));
+    h->launches++;
+  }
   if (h->pos_off >= 0) {  // rows >= S of the table get no gradient (G was cleared in stage 0)
     MFP_TRY(launch_pos_embed_bwd(dx, h->B, h->S, drop ? h->cfg.dropout : 0.f, seed, step, G + h->pos_off, st));
     h->launches++;

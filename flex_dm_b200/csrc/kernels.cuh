@@ -34,7 +34,14 @@ struct PosEmbed {
 int launch_embed_fwd(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, const float* params, int T, float* h0, cudaStream_t st,
                      const PosEmbed& pos = PosEmbed{nullptr, 0, 0.f, 0u, 0u});
 int launch_pos_embed_bwd(const float* dh0, int B, int S, float rate, uint32_t seed, uint32_t step, float* dtable /*[S][D], overwritten*/, cudaStream_t st);
-int launch_embed_onehot(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, int T, float* onehot /*[T][Rp]*/, cudaStream_t st);
+int launch_embed_onehot(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, int T, float* onehot /*[T][Rp]*/, cudaStream_t st,
+                        const int* ctx_row = nullptr /*[B]: row of each document that holds the context token (all-zero one-hot row)*/, int S = 0);
+// --context id / length (encoder.py:96-110,231-249): the special token of document b sits in row ctx_row[b] = length[b] + 1 of its S rows
+// (self-attention without positions is order-free, so "after the last element" equals the reference's "prepended"); ctx_row doubles as
+// the attention kernels' length array (zero-based: covers the elements and the token).
+int launch_context_token(const float* table, int rows, const int* ids, const int* length, int B, int S, float* h0, int* ctx_row, cudaStream_t st);
+int launch_context_token_bwd(const float* dh0, const int* ids, const int* ctx_row, int rows, int B, int S, float* dtable /*[rows][D], overwritten*/,
+                             cudaStream_t st);
 int launch_embed_scatter(const Schema& sc, const float* scratch /*[R][D]*/, float* grads, cudaStream_t st);
 
 // transformer.cu

@@ -31,7 +31,7 @@ class Config(ctypes.Structure):
     _fields_ = [("num_fields", ctypes.c_int32), ("type_field", ctypes.c_int32), ("latent_dim", ctypes.c_int32), ("num_blocks", ctypes.c_int32),
                 ("sort_pos", ctypes.c_int32), ("pos_task_id", ctypes.c_int32), ("total_columns", ctypes.c_int32),
                 ("sort_fields", ctypes.c_int32 * 5), ("dropout", ctypes.c_float), ("l2", ctypes.c_float), ("input_dtype", ctypes.c_int32),
-                ("length_input_dim", ctypes.c_int32), ("block_type", ctypes.c_int32)]
+                ("length_input_dim", ctypes.c_int32), ("block_type", ctypes.c_int32), ("context", ctypes.c_int32), ("context_rows", ctypes.c_int32)]
 
 
 class Variable(ctypes.Structure):
@@ -66,6 +66,7 @@ _SIGNATURES = {
                                           ctypes.c_void_p, ctypes.c_void_p]),
     "mfp_mask_for_test": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Batch), ctypes.POINTER(ctypes.c_void_p),
                                          ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
+    "mfp_set_context_ids": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "mfp_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Batch), ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p,
                                    ctypes.c_void_p]),
     "mfp_loss": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Batch), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_void_p,
@@ -135,7 +136,7 @@ class Engine:
     """One ``mfp_engine`` handle plus the device buffers it is bound to."""
 
     def __init__(self, input_columns: Dict, num_blocks: int = 4, latent_dim: int = 256, dropout: float = 0.1, l2: Optional[float] = 1e-2,
-                 device: Optional[torch.device] = None, block_type: str = "deepsvg", input_dtype: str = "set"):
+                 device: Optional[torch.device] = None, block_type: str = "deepsvg", input_dtype: str = "set", context: Optional[str] = None):
         self.lib = load_library()
         if not torch.cuda.is_available():
             raise RuntimeError("flex_dm_b200: a CUDA device is required (there is no CPU fallback)")
@@ -186,6 +187,10 @@ class Engine:
         cfg.block_type = {"deepsvg": 0, "transformer": 1}[block_type]  # transformer.py:232-236
         cfg.input_dtype = {"set": 0, "shuffled_set": 1, "sorted_set": 2}[input_dtype]  # mfp.py:104-105, encoder.py:41
         cfg.length_input_dim = int(input_columns["length"]["input_dim"])
+        cfg.context = {None: 0, "id": 1, "length": 2}[context]  # encoder.py:96-110
+        cfg.context_rows = {None: 0, "id": len(self.task_names), "length": int(input_columns["length"]["input_dim"])}[context]
+        self.context = context
+        self._context_ids = None  # keeps the tensor alive while the engine holds its pointer
         self.input_dtype = input_dtype
         self.cfg = cfg
         handle = ctypes.c_void_p()
@@ -308,6 +313,14 @@ class Engine:
         mp = _PTR_ARRAY(*[m.data_ptr() for m in masks])
         _check(self.lib, self.lib.mfp_mask_for_test(self.handle, ctypes.byref(b), ctypes.cast(mp, ctypes.POINTER(ctypes.c_void_p)),
                                                     ctypes.cast(self._mod_ptrs, ctypes.POINTER(ctypes.c_void_p)), _stream()), "mfp_mask_for_test")
+
+    def set_context_ids(self, task_ids: torch.Tensor):
+        """--context id: the per-document task ids the context token embeds (mfp.py:137; eval.py:100-101)."""
+        ids = task_ids.to(device=self.device, dtype=torch.int32).reshape(-1).contiguous()
+        if ids.numel() != self.B:
+            raise ValueError("expected %d task ids, got %d" % (self.B, ids.numel()))
+        self._context_ids = ids
+        _check(self.lib, self.lib.mfp_set_context_ids(self.handle, _ptr(ids)), "mfp_set_context_ids")
 
     def forward(self, length, cols: Optional[List[torch.Tensor]] = None, training: bool = False, seed: int = 0, step: int = 0,
                 logits_out: Optional[torch.Tensor] = None):

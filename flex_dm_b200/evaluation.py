@@ -67,7 +67,11 @@ def evaluate(model, dataset: Iterable[Dict], input_columns: Dict, task_mode: str
             continue
         batch, masks = build_masks(example, input_columns, task_mode, group_keys)
         B = batch["left"].shape[0]
-        prediction = model(batch, training=False, demo_args={"masks": masks, "num_iter": num_iter})
+        demo_args = {"masks": masks, "num_iter": num_iter}
+        if getattr(model, "context", None) == "id":  # eval.py:99-101
+            task_id = model.task_names.index(group_name)
+            demo_args["tasks"] = torch.full((B,), task_id, dtype=torch.int32)
+        prediction = model(batch, training=False, demo_args=demo_args)
         if sort_pos and task_mode == "pos":
             (scores,) = loss_layer((batch, prediction, masks), False, torch.ones((B,), dtype=torch.bool))
         else:

@@ -93,14 +93,18 @@ class MFP:
             raise KeyError(block_type)
         if input_dtype not in ("set", "shuffled_set", "sorted_set"):
             raise ValueError("input_dtype=%r (args.py: set | shuffled_set | sorted_set)" % (input_dtype,))
+        if context not in (None, "id", "length"):  # encoder.py:11 CONTEXT_NAMES; the canvas variants embed and predict canvas columns
+            raise NotImplementedError("context=%r is outside the B200 hot path (SURVEY.md section 8f); supported: None, 'id', 'length'" % (context,))
+        if context is not None and input_dtype != "set":
+            raise NotImplementedError("context=%r with input_dtype=%r is not supported" % (context, input_dtype))
         for flag, value, supported in (("seq_type", seq_type, "default"),
-                                       ("context", context, None),
                                        ("use_elemwise_noise", use_elemwise_noise, False)):
             if value != supported:
                 raise NotImplementedError("%s=%r is outside the B200 hot path (SURVEY.md section 8f); supported: %r" % (flag, value, supported))
         self.name = name
         self.arch_type = arch_type
         self.context = context
+        self._pad_context = True  # False: the caller guarantees length + 1 < S for every document (one free row for the context token)
         self.input_dtype = input_dtype
         self.all_columns = input_columns
         self.input_columns = OrderedDict((k, v) for (k, v) in input_columns.items() if not v.get("demo_only", False))  # mfp.py:235-237
@@ -112,7 +116,7 @@ class MFP:
             raise TypeError("unexpected arguments: %s" % sorted(kwargs))
         self.block_type = block_type
         self.engine = Engine(input_columns, num_blocks=num_blocks, latent_dim=latent_dim, dropout=dropout, l2=l2, device=device, block_type=block_type,
-                             input_dtype=input_dtype)
+                             input_dtype=input_dtype, context=context)
         self.device = self.engine.device
         self.keys = self.engine.keys
         self.task_names = get_task_names(input_columns)
@@ -193,11 +197,24 @@ class MFP:
         return out
 
     def _bind(self, staged: Dict[str, torch.Tensor]):
-        B, S = staged[self.keys[0]].shape[:2]
+        cols = [staged[k] for k in self.keys]
+        if self.context is not None and self._pad_context:
+            # the context token (encoder.py:231-249) takes the row after each document's last element: one more (padding) row so
+            # that full-length documents have one too; callers see the caller's S again (``_crop``)
+            cols = [torch.nn.functional.pad(c, (0, 0, 0, 1)) for c in cols]
+        B, S = cols[0].shape[:2]
         self.engine.bind(int(B), int(S))
         if self._ring is None:
             self._ring = torch.zeros((256, self.engine.metrics_width), dtype=torch.float32, device=self.device)
-        return int(B), int(S), staged["length"].reshape(-1), [staged[k] for k in self.keys]
+        return int(B), int(S), staged["length"].reshape(-1), cols
+
+    def _set_context(self, tasks: torch.Tensor):
+        if self.context == "id":  # modified_inputs["task"] (mfp.py:137) -> Encoder input_layer["task"] (encoder.py:234-237)
+            self.engine.set_context_ids(tasks)
+
+    def _crop(self, x: torch.Tensor) -> torch.Tensor:
+        """Drops the extra row ``_bind`` added for the context token."""
+        return x if (self.context is None or not self._pad_context) else x[:, :-1]
 
     def _next_row(self) -> torch.Tensor:
         row = self._ring[self._ring_pos % self._ring.shape[0]]
@@ -215,6 +232,7 @@ class MFP:
         eng, seed, step = self.engine, self.seed, self._step
         row = self._next_row()
         tasks = eng.sample_tasks(self.task_ids, seed, step)
+        self._set_context(tasks)
         if self.input_dtype != "set":  # mfp.py:104-105: the shuffled batch is what gets corrupted and what the loss targets
             cols = eng.shuffle_inputs(length, cols, seed, step)
         eng.mask_corrupt(length, cols, tasks, seed, step)
@@ -245,6 +263,7 @@ class MFP:
         eng, seed, step = self.engine, self.seed, self._step
         row = self._next_row()
         tasks = eng.sample_tasks(self.task_ids, seed, step)
+        self._set_context(tasks)
         if self.input_dtype != "set":
             cols = eng.shuffle_inputs(length, cols, seed, step)
         eng.mask_corrupt(length, cols, tasks, seed, step)
@@ -328,12 +347,20 @@ class MFP:
         B, S, length, cols = self._bind(staged)
         eng, seed, step = self.engine, self.seed, self._step
         tasks = eng.sample_tasks(self.task_ids, seed, step)  # mfp.py:301
+        if is_demo and "tasks" in demo_args:  # preprocess_for_test(..., demo_args.get("tasks", tasks)) (mfp.py:307-312)
+            t = demo_args["tasks"]
+            self._set_context((torch.as_tensor(t) if not isinstance(t, torch.Tensor) else t).to(self.device))
+        else:
+            self._set_context(tasks)
         if is_demo:
             masks = []
             for key in self.keys:
                 m = demo_args["masks"][key]
                 m = torch.as_tensor(m) if not isinstance(m, torch.Tensor) else m
-                masks.append(m.to(self.device).to(torch.uint8).contiguous())
+                m = m.to(self.device).to(torch.uint8)
+                if self.context is not None and self._pad_context:
+                    m = torch.nn.functional.pad(m, (0, 1))  # the context token's row is never masked
+                masks.append(m.contiguous())
             num_iter = int(demo_args.get("num_iter", 1))
             final_logits = None
             if num_iter > 1:
@@ -368,7 +395,7 @@ class MFP:
             shape = (B, S, c["shape"][-1], c["input_dim"]) if c["type"] == "categorical" else (B, S, c["shape"][-1])
             out = torch.empty(shape, dtype=torch.float32, device=self.device)
             eng.merge_prediction(f, cols[f], masks[f], out, logits_in=final_logits if is_demo else None)
-            outputs[key] = out
+            outputs[key] = self._crop(out)
         for key, column in self.all_columns.items():  # copy unpredicted items for visualization (mfp.py:66-68)
             if column.get("demo_only", False) and key in inputs:
                 outputs[key] = inputs[key]
@@ -434,9 +461,12 @@ class MFP:
         staged = self.stage(modified_inputs)
         B, S, length, cols = self._bind(staged)
         eng = self.engine
+        if self.context == "id":
+            t = modified_inputs["task"]  # added by preprocess_for_train / preprocess_for_test (mfp.py:91,137)
+            self._set_context((torch.as_tensor(np.asarray(t)) if not isinstance(t, torch.Tensor) else t).to(self.device))
         logits = torch.empty((B * S, eng.logit_width), dtype=torch.float32, device=self.device)
         eng.forward(length, cols, training, self.seed if seed is None else seed, step, logits_out=logits)
-        return self.split_logits(logits, B, S)
+        return OrderedDict((k, self._crop(v)) for k, v in self.split_logits(logits, B, S).items())
 
     def split_logits(self, logits: torch.Tensor, B: int, S: int) -> Dict[str, torch.Tensor]:
         out = OrderedDict()

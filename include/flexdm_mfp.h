@@ -57,6 +57,12 @@ typedef struct {
   int32_t length_input_dim; /* input_columns["length"]["input_dim"]: the PositionEmbedding table has this + 1 rows (>= S needed) */
   int32_t block_type;  /* 0 = "deepsvg" (pre-LayerNorm block, transformer.py:208-229; the default), 1 = "transformer"
                         * (post-LayerNorm TransformerBlock, transformer.py:187-205): same variables, same kernels, other wiring */
+  int32_t context;     /* --context (encoder.py:96-110,231-249; decoder.py:74-78): 0 = None, 1 = "id" (a learned embedding of the document's task
+                        * id), 2 = "length" (of its zero-based length) joins the sequence as one more token that every element attends to and
+                        * that the heads ignore.  The engine keeps the token in row length[b] + 1 of the document's S rows (attention without
+                        * positions is order-free, so this equals the reference's prepended token up to summation order): every document
+                        * needs length[b] + 1 < S -- the host mirror pads the batch by one row.  Not combined with input_dtype != 0. */
+  int32_t context_rows; /* rows of that embedding table: len(get_task_names(...)) for "id", input_columns["length"]["input_dim"] for "length" */
 } mfp_config;
 
 /* One trainable variable of the reference model as a strided view of the flat
@@ -118,6 +124,10 @@ int mfp_shuffle_inputs(mfp_engine* h, const mfp_batch* inputs, uint32_t seed, ui
 
 /* Model.call(modified_inputs, training) (models/model.py:26-30): encoder -> blocks -> decoder.
  * Logits land in the workspace; `logits_out` (optional, [B*S, logit_width]) receives a copy. */
+/* --context id: the per-document ids the context token embeds (device int32 [B]; MFP.call's `tasks`, mfp.py:137,301; eval.py:100-101).
+ * The pointer is kept and read by every following mfp_forward / mfp_backward*; "length" contexts read the batch's own length array. */
+int mfp_set_context_ids(mfp_engine* h, const int32_t* task_ids);
+
 int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint32_t seed, uint32_t step,
                 float* logits_out, void* stream);
 

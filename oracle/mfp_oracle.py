@@ -312,7 +312,7 @@ def preprocess_for_test(inputs, input_columns, masks, tasks=None):
 
 
 # ----------------------------------------------------------------------------------------------- parameters
-def variable_specs(input_columns, num_blocks=4, latent_dim=256, input_dtype="set") -> "OrderedDict[str, Tuple[tuple, str, bool]]":
+def variable_specs(input_columns, num_blocks=4, latent_dim=256, input_dtype="set", context=None) -> "OrderedDict[str, Tuple[tuple, str, bool]]":
     """name -> (shape, init, l2-regularised).  SURVEY.md Appendix B; names follow the reference's attribute
     paths (mfp.py:249, model.py:20,45,52, encoder.py:74-92, transformer.py:54-57,161-173,263, decoder.py:39)."""
     D = latent_dim
@@ -328,6 +328,10 @@ def variable_specs(input_columns, num_blocks=4, latent_dim=256, input_dtype="set
             v[base + "/bias"] = ((D,), "zeros", True)
     if input_dtype != "set":  # PositionEmbedding(latent_dim, maxlen=length input_dim): Embedding(maxlen + 1, D) (encoder.py:48-55, transformer.py:17-21)
         v["model/encoder/input_layer/const/embeddings/embeddings"] = ((input_columns["length"]["input_dim"] + 1, D), "uniform", True)
+    if context == "id":  # encoder.py:96-103
+        v["model/encoder/input_layer/task/embeddings"] = ((len(get_task_names(input_columns)), D), "uniform", True)
+    elif context == "length":  # encoder.py:104-110
+        v["model/encoder/input_layer/length/embeddings"] = ((input_columns["length"]["input_dim"], D), "uniform", True)
     for i in range(num_blocks):
         b = "model/blocks/seq2seq/seq2seq_%d" % i
         for d in ("dense_query", "dense_key", "dense_value", "combine_heads"):  # transformer.py:54-57
@@ -347,12 +351,12 @@ def variable_specs(input_columns, num_blocks=4, latent_dim=256, input_dtype="set
     return v
 
 
-def init_params(input_columns, num_blocks=4, latent_dim=256, seed=0, dtype=torch.float64, bias_scale=0.0, input_dtype="set"):
+def init_params(input_columns, num_blocks=4, latent_dim=256, seed=0, dtype=torch.float64, bias_scale=0.0, input_dtype="set", context=None):
     """Keras default initialisers (Appendix A9): Dense glorot-uniform / zero bias, Embedding U(-0.05, 0.05), LN ones/zeros.
     ``bias_scale`` > 0 perturbs biases / LN parameters so that parity tests exercise them."""
     rng = np.random.Generator(np.random.PCG64(seed))
     params = OrderedDict()
-    for name, (shape, init, _) in variable_specs(input_columns, num_blocks, latent_dim, input_dtype).items():
+    for name, (shape, init, _) in variable_specs(input_columns, num_blocks, latent_dim, input_dtype, context).items():
         if init == "uniform":
             w = rng.uniform(-0.05, 0.05, size=shape)
         elif init == "glorot":
@@ -378,8 +382,8 @@ def dense(x, p, name):
     return x @ p[name + "/kernel"] + p[name + "/bias"]  # A12
 
 
-def encoder_forward(p, inputs, input_columns, pos_keep=None, pos_rate=0.0):
-    """architecture/encoder.py:147-265 with fusion="add", context=None, input_dtype="set"."""
+def encoder_forward(p, inputs, input_columns, pos_keep=None, pos_rate=0.0, context=None):
+    """architecture/encoder.py:147-265 with fusion="add"; context None / "id" / "length"."""
     cols = get_valid_input_columns(input_columns)
     dtype = next(iter(p.values())).dtype
     S = inputs[next(iter(cols))].shape[1]
@@ -404,6 +408,12 @@ def encoder_forward(p, inputs, input_columns, pos_keep=None, pos_rate=0.0):
         B = seq.shape[0]
         emb = p[pos_name][:S][None].expand(B, -1, -1)
         seq = seq + dropout(emb, pos_keep, pos_rate)
+    if context is not None:  # encoder.py:231-249: a special token in front of the sequence, one more valid position per document
+        ids = inputs["task"] if context == "id" else inputs["length"]  # :234-242
+        ids = ids[:, 0] if ids.dim() == 2 else ids
+        canvas = p["model/encoder/input_layer/%s/embeddings" % ("task" if context == "id" else "length")][ids.to(torch.int64)]
+        seq = torch.cat([canvas[:, None, :], seq], dim=1)  # :247-248
+        seq_mask = get_seq_mask(inputs["length"] + 1, S + 1)  # :249
     return seq, seq_mask
 
 
@@ -473,10 +483,32 @@ def decoder_forward(p, h, input_columns):
     return out
 
 
-def model_forward(p, modified_inputs, input_columns, num_blocks, drop=None, rate=0.0, return_hidden=False, block_type="deepsvg"):
+def context_dropout_layout(drop, length):
+    """Dropout keep-masks are drawn per row of the B200 engine's ``[B, S, D]`` activations, where the context token of document b
+    sits in row ``n_b = length[b] + 1`` (the first padding row) and element s in row s.  The reference puts the token in front
+    (position 0) and element s at position s + 1: gather the masks into that order.  The padding positions behind the token have no
+    engine row of their own and no effect on any result; they reuse the rows at their own index."""
+    if drop is None:
+        return None
+    n = (length.reshape(-1) + 1).to(torch.int64)
+    out = {}
+    for key, keep in drop.items():
+        B, S, _ = keep.shape
+        src = torch.arange(-1, S).repeat(B, 1)  # position p >= 1 reads row p - 1
+        src[:, 0] = n.clamp(max=S - 1)  # the token's row
+        src = src.clamp(min=0)
+        out[key] = torch.gather(keep, 1, src[:, :, None].expand(-1, -1, keep.shape[2]))
+    return out
+
+
+def model_forward(p, modified_inputs, input_columns, num_blocks, drop=None, rate=0.0, return_hidden=False, block_type="deepsvg", context=None):
     """models/model.py:26-30."""
-    h0, mask = encoder_forward(p, modified_inputs, input_columns, None if drop is None else drop.get("pos"), rate)
+    if context is not None:
+        drop = context_dropout_layout(drop, modified_inputs["length"])
+    h0, mask = encoder_forward(p, modified_inputs, input_columns, None if drop is None else drop.get("pos"), rate, context)
     h = blocks_forward(p, h0, mask, num_blocks, drop, rate, block_type)
+    if context is not None:  # decoder.py:74-78: the heads read the element positions only
+        h = h[:, 1:]
     out = decoder_forward(p, h, input_columns)
     if return_hidden:
         return out, h0, h
@@ -693,15 +725,17 @@ class OracleMFP:
     """The reference's MFP train/eval step (mfp.py:210-347 + Keras default train_step) on CPU."""
 
     def __init__(self, input_columns, num_blocks=4, masking_method="random", latent_dim=256, dropout=0.1, l2=1e-2,
-                 seed=0, dtype=torch.float64, learning_rate=1e-4, clipnorm=1.0, bias_scale=0.0, block_type="deepsvg", input_dtype="set"):
+                 seed=0, dtype=torch.float64, learning_rate=1e-4, clipnorm=1.0, bias_scale=0.0, block_type="deepsvg", input_dtype="set",
+                 context=None):
         self.block_type = block_type
+        self.context = context
         self.input_dtype = input_dtype
         self.input_columns = OrderedDict((k, v) for k, v in input_columns.items() if not v.get("demo_only", False))
         self.all_columns = input_columns
         self.num_blocks, self.latent_dim, self.rate, self.l2 = num_blocks, latent_dim, dropout, l2
         self.dtype = dtype
-        self.specs = variable_specs(input_columns, num_blocks, latent_dim, input_dtype)
-        self.params = init_params(input_columns, num_blocks, latent_dim, seed, dtype, bias_scale, input_dtype)
+        self.specs = variable_specs(input_columns, num_blocks, latent_dim, input_dtype, context)
+        self.params = init_params(input_columns, num_blocks, latent_dim, seed, dtype, bias_scale, input_dtype, context)
         self.m = OrderedDict((k, torch.zeros_like(v)) for k, v in self.params.items())
         self.v = OrderedDict((k, torch.zeros_like(v)) for k, v in self.params.items())
         self.t = 0
@@ -724,7 +758,8 @@ class OracleMFP:
         return keep
 
     def loss_from(self, params, targets, modified, masks, tasks, drop):
-        outputs = model_forward(params, modified, self.input_columns, self.num_blocks, drop, self.rate, block_type=self.block_type)
+        outputs = model_forward(params, modified, self.input_columns, self.num_blocks, drop, self.rate, block_type=self.block_type,
+                                context=self.context)
         sort_flag = (tasks == self.task_names.index("pos")) if self.sort_pos else None  # mfp.py:335-340
         data_loss, losses, scores, metrics = loss_layer(targets, outputs, masks, self.all_columns, sort_flag)
         reg = l2_regulariser(params, self.specs, self.l2) if self.l2 is not None else 0.0

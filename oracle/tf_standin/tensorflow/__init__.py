@@ -446,3 +446,12 @@ _experimental = keras._mod(keras.__name__ + ".layers.experimental")
 _experimental.preprocessing = keras._mod(keras.__name__ + ".layers.experimental.preprocessing", StringLookup=_data_io.StringLookup,
                                          IntegerLookup=_data_io.IntegerLookup, Discretization=_data_io.Discretization)
 keras.layers.experimental = _experimental
+
+# einops (encoder.py uses rearrange on the context token) picks its backend by the tensor's type and would try a TensorFlow backend
+# because a module named "tensorflow" is loaded: register the torch backend first -- stand-in tensors are torch tensors.
+try:
+    from einops import _backends as _einops_backends
+
+    _einops_backends._loaded_backends.setdefault("torch", _einops_backends.TorchBackend())
+except Exception:  # einops absent: nothing on the path needs it then
+    pass

@@ -69,12 +69,27 @@ CASES = OrderedDict([
     ("rico_shuffled", ("rico", "elem_pos_attr", 4, 9, 2, 13, 5, [9, 4, 1, 6], [0, 3, 1, 4])),
     # --input_dtype sorted_set: elements sorted by (type, left, top, width, height) (tensor_utils.py:14-44) + PositionEmbedding
     ("crello_sorted", ("crello", "random", 3, 10, 2, 15, 1, [10, 6, 1], None)),
+    # --context id / length: a learned special token (task id / document length) joins the sequence (encoder.py:96-110,231-249; decoder.py:74-78).
+    # Every document leaves the last row free: the engine keeps the token in the row after a document's last element.
+    ("crello_ctx_id", ("crello", "elem_pos_attr_img_txt", 4, 11, 2, 21, 2, [10, 4, 1, 7], [1, 3, 5, 6])),
+    ("rico_ctx_length", ("rico", "elem_pos_attr", 4, 9, 2, 23, 1, [8, 3, 1, 5], [3, 1, 4, 3])),
 ])
+CONTEXT = {"crello_ctx_id": "id", "rico_ctx_length": "length"}
 BLOCK_TYPE = {"crello_postln": "transformer"}
 INPUT_DTYPE = {"rico_shuffled": "shuffled_set", "crello_sorted": "sorted_set"}
 
 
-def rng_script(cols, B, S, tasks, draws, num_blocks, training, pos_dropout=False):
+def block_dropout_script(draws, B, S, num_blocks, lengths=None):
+    """Keep-masks of the two Dropout sites per block, in the engine's row layout ``(B, S, D)``; with a context token (lengths given) the
+    engine batch has one padding row more than the reference's (which is cut to the longest document): the masks are gathered into
+    the reference's order (token first, oracle.context_dropout_layout) and cut to its S positions (token + S - 1 elements)."""
+    keep = {(i, j): torch.from_numpy(draws.dropout_keep(i, j, (B, S, D), RATE)) for i in range(num_blocks) for j in (0, 1)}
+    if lengths is not None:
+        keep = {k: v[:, :S] for k, v in O.context_dropout_layout(keep, torch.as_tensor(np.asarray(lengths)) - 1).items()}
+    return [("dropout", keep[(i, j)].numpy()) for i in range(num_blocks) for j in (0, 1)]
+
+
+def rng_script(cols, B, S, tasks, draws, num_blocks, training, pos_dropout=False, ctx_lengths=None):
     """The reference's RNG call order for one MFP.call(training): mfp.py:301 -> masking.py filter_padding :24-53
     -> random_masking :227-269 -> elem_masking :136-155 -> feat_masking per group :116-133 -> Dropout x2 per block."""
     icols = OrderedDict((k, v) for k, v in cols.items() if not v.get("demo_only", False))
@@ -85,17 +100,18 @@ def rng_script(cols, B, S, tasks, draws, num_blocks, training, pos_dropout=False
         C = c["shape"][-1]
         return ("randint", None) if c["type"] == "categorical" else ("normal", None)
 
+    Sr = S - 1 if ctx_lengths is not None else S  # columns the reference sees (see run_case)
     s = [("categorical", np.asarray(tasks, dtype=np.int32))]
     for k, c in seq.items():  # filter_padding: apply_token(..., "unused") evaluates the "random" dict entry eagerly
         s.append(discard(c))
     for k, c in seq.items():  # random_masking
-        u1, u2, u3 = draws.uniforms(fidx[k], B, S)
+        u1, u2, u3 = (u[:, :Sr] for u in draws.uniforms(fidx[k], B, S))
         s += [("uniform", u1), ("uniform", u2), ("uniform", u3), discard(c)]
         C = c["shape"][-1]
         if c["type"] == "categorical":
-            s.append(("randint", draws.rand_cat(fidx[k], B, S, C, c["input_dim"])))
+            s.append(("randint", draws.rand_cat(fidx[k], B, S, C, c["input_dim"])[:, :Sr]))
         else:
-            s.append(("normal", draws.rand_num(fidx[k], B, S, C)))
+            s.append(("normal", draws.rand_num(fidx[k], B, S, C)[:, :Sr]))
     s.append(("uniform", draws.elem_u(B)))  # select_single_element
     for k, c in seq.items():
         s.append(discard(c))
@@ -105,9 +121,7 @@ def rng_script(cols, B, S, tasks, draws, num_blocks, training, pos_dropout=False
     if training:
         if pos_dropout:  # the encoder's PositionEmbedding dropout comes before the blocks'
             s.append(("dropout", draws.pos_dropout_keep((B, S, D), RATE)))
-        for i in range(num_blocks):
-            for j in (0, 1):
-                s.append(("dropout", draws.dropout_keep(i, j, (B, S, D), RATE)))
+        s += block_dropout_script(draws, B, S, num_blocks, ctx_lengths)
     return s
 
 
@@ -128,16 +142,18 @@ def run_case(name, spec):
     draws = O.PhiloxDraws(seed, step)
     block_type = BLOCK_TYPE.get(name, "deepsvg")
     input_dtype = INPUT_DTYPE.get(name, "set")
+    context = CONTEXT.get(name)
+    ctx_lengths = lengths if context is not None else None
     if input_dtype == "shuffled_set":
         method = method if "random" in method else "random_" + method  # keep task 0 reachable for the scripted task ids
     if input_dtype == "sorted_set":
         icols_ = OrderedDict((k, v) for k, v in cols.items() if not v.get("demo_only", False))
         out_perm = O.sort_inputs({k: torch.as_tensor(v) for k, v in batch.items()}, icols_)[1].numpy().astype(np.int32)
-    oracle = O.OracleMFP(cols, num_blocks=L, masking_method=method, dropout=RATE, l2=L2, input_dtype=input_dtype)
+    oracle = O.OracleMFP(cols, num_blocks=L, masking_method=method, dropout=RATE, l2=L2, input_dtype=input_dtype, context=context)
     if tasks is None:
         tasks = draws.tasks(B, oracle.allowed_tasks)
     tasks = np.asarray(tasks, dtype=np.int32)
-    params = O.init_params(cols, L, D, WEIGHT_SEED, torch.float64, bias_scale=0.05, input_dtype=input_dtype)
+    params = O.init_params(cols, L, D, WEIGHT_SEED, torch.float64, bias_scale=0.05, input_dtype=input_dtype, context=context)
     out = {"tasks": tasks}
     for k, v in batch.items():
         out["in/" + k] = v
@@ -165,8 +181,10 @@ def run_case(name, spec):
     # ---------------- phase A: the whole MFP.call in float32 (bit-faithful dtypes for the masking path)
     tfc.FLOAT = torch.float32
     model = RefMFP(cols, num_blocks=L, block_type=block_type, masking_method=method, seq_type="default", arch_type="oneshot",
-                   context=None, input_dtype=input_dtype, latent_dim=D, dropout=RATE, l2=L2)
-    inputs32 = {k: torch.as_tensor(v).as_subclass(tf.Tensor) for k, v in batch.items()}
+                   context=context, input_dtype=input_dtype, latent_dim=D, dropout=RATE, l2=L2)
+    # with a context token the engine's batch keeps one free row per document; the reference wants S = the longest document
+    ref_batch = {k: (v[:, :S - 1] if (context is not None and v.ndim == 3) else v) for k, v in batch.items()}
+    inputs32 = {k: torch.as_tensor(v).as_subclass(tf.Tensor) for k, v in ref_batch.items()}
     captured = {}
     inner_call, loss_call = model.model.call, model.loss_layer.call
 
@@ -184,11 +202,11 @@ def run_case(name, spec):
         return loss_call(inputs, training, sort_flag, ignore_sort)
 
     model.model.call, model.loss_layer.call = model_spy, loss_spy
-    tfc.rng = tfc.ScriptedRNG(rng_script(cols, B, S, tasks, draws, L, True, input_dtype != "set"))
+    tfc.rng = tfc.ScriptedRNG(rng_script(cols, B, S, tasks, draws, L, True, input_dtype != "set", ctx_lengths))
     model({k: v.clone() for k, v in inputs32.items()}, training=True)  # builds the lazily-created variables
     set_weights(model, params, torch.float32)
     model.reset_step_state()
-    tfc.rng = tfc.ScriptedRNG(rng_script(cols, B, S, tasks, draws, L, True, input_dtype != "set"))
+    tfc.rng = tfc.ScriptedRNG(rng_script(cols, B, S, tasks, draws, L, True, input_dtype != "set", ctx_lengths))
     merged = model({k: v.clone() for k, v in inputs32.items()}, training=True)
     assert tfc.rng.done(), "the reference asked for fewer draws than scripted"
     loss32 = float(sum(model.losses))
@@ -213,7 +231,7 @@ def run_case(name, spec):
     mod64 = {k: (v.to(torch.float64) if v.is_floating_point() else v) for k, v in captured["mod"].items()}
     targets64 = {k: (v.to(torch.float64) if v.is_floating_point() else v.clone()) for k, v in captured["targets"].items()}
     tfc.rng = tfc.ScriptedRNG(([("dropout", draws.pos_dropout_keep((B, S, D), RATE))] if input_dtype != "set" else []) +
-                              [("dropout", draws.dropout_keep(i, j, (B, S, D), RATE)) for i in range(L) for j in (0, 1)])
+                              block_dropout_script(draws, B, S, L, ctx_lengths))
     logits = model.model(mod64, True)
     for k, v in logits.items():
         out["logits/" + k] = v.detach().numpy()
@@ -369,7 +387,11 @@ def run_decode_case(name="crello_decode", B=1, S=12, L=2, seed=6, lengths=(12,),
 
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])  # optional: regenerate just the named cases
     for case, spec in CASES.items():
-        run_case(case, spec)
-    run_demo_case()
-    run_decode_case()
+        if not only or case in only:
+            run_case(case, spec)
+    if not only or "crello_demo" in only:
+        run_demo_case()
+    if not only or "crello_decode" in only:
+        run_decode_case()

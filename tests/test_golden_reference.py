@@ -25,9 +25,19 @@ CASES = {  # name: (dataset, masking_method, num_blocks, seed, step)
     "crello_postln": ("crello", "random", 2, 9, 3),  # --block_type transformer (post-LayerNorm block)
     "rico_shuffled": ("rico", "random_elem_pos_attr", 2, 13, 5),  # --input_dtype shuffled_set (shuffle + PositionEmbedding)
     "crello_sorted": ("crello", "random", 2, 15, 1),  # --input_dtype sorted_set (sort_inputs + PositionEmbedding)
+    # --context id / length (encoder.py:96-110,231-249): the batch keeps one free row per document for the context token; the
+    # reference ran on the same batch cut to its longest document, so its arrays have one column less (``cut``)
+    "crello_ctx_id": ("crello", "elem_pos_attr_img_txt", 2, 21, 2),
+    "rico_ctx_length": ("rico", "elem_pos_attr", 2, 23, 1),
 }
 BLOCK_TYPE = {"crello_postln": "transformer"}
 INPUT_DTYPE = {"rico_shuffled": "shuffled_set", "crello_sorted": "sorted_set"}
+CONTEXT = {"crello_ctx_id": "id", "rico_ctx_length": "length"}
+
+
+def cut(x, case):
+    """Sequence arrays of a context case without the engine batch's free last row (what the reference saw)."""
+    return x[:, :-1] if case in CONTEXT else x
 
 
 def projection_vector(name, n):  # same as make_golden.py
@@ -51,7 +61,7 @@ def test_golden_files_cover_every_task_and_edge_case():
     for case in CASES:
         g = np.load(os.path.join(GOLDEN, case + ".npz"))
         seen |= {(CASES[case][0], int(t)) for t in g["tasks"]}
-        assert int(g["in/length"].min()) == 0 and int(g["in/length"].max()) == g["in/left"].shape[1] - 1
+        assert int(g["in/length"].min()) == 0 and int(g["in/length"].max()) == g["in/left"].shape[1] - (2 if case in CONTEXT else 1)
     assert {t for d, t in seen if d == "crello"} == {0, 1, 3, 4, 5, 6}
     assert "crello_postln" in CASES  # the post-LayerNorm block of --block_type transformer
     assert {t for d, t in seen if d == "rico"} >= {1, 3, 4}
@@ -62,8 +72,8 @@ def test_oracle_matches_reference_python(case):
     g, cols, batch, method, L, seed, step = load(case)
     input_dtype = INPUT_DTYPE.get(case, "set")
     o = O.OracleMFP(cols, num_blocks=L, masking_method=method, dropout=RATE, l2=L2, learning_rate=LR, clipnorm=1.0,
-                    block_type=BLOCK_TYPE.get(case, "deepsvg"), input_dtype=input_dtype)
-    o.params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float64, bias_scale=0.05, input_dtype=input_dtype)
+                    block_type=BLOCK_TYPE.get(case, "deepsvg"), input_dtype=input_dtype, context=CONTEXT.get(case))
+    o.params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float64, bias_scale=0.05, input_dtype=input_dtype, context=CONTEXT.get(case))
     draws = O.PhiloxDraws(seed, step)
     tasks = torch.as_tensor(g["tasks"])
     assert set(g["tasks"].tolist()) <= set(o.allowed_tasks)
@@ -73,15 +83,18 @@ def test_oracle_matches_reference_python(case):
         for key in o.input_columns:
             assert np.array_equal(targets[key].numpy(), g["tgt/" + key]), key
     # ---- masking path: bit-exact against the reference's preprocess_for_train (mfp.py:95-138)
-    for key in o.input_columns:
-        assert np.array_equal(mod[key].numpy(), g["mod/" + key]), key
-        assert np.array_equal(masks[key].numpy(), g["mask/" + key]), key
+    for key, column in o.input_columns.items():
+        seq = column["is_sequence"]
+        assert np.array_equal(cut(mod[key].numpy(), case) if seq else mod[key].numpy(), g["mod/" + key]), key
+        assert np.array_equal(cut(masks[key].numpy(), case) if seq else masks[key].numpy(), g["mask/" + key]), key
+        if seq and case in CONTEXT:
+            assert not masks[key][:, -1].any(), key  # the free row is padding
     assert np.array_equal(mod["task"].numpy(), g["mod/task"])
     B, S = batch["left"].shape[:2]
     r = o.step_from(targets, mod, masks, tasks, o.dropout_masks(draws, B, S))
     # ---- Model.call (model.py:26-30): raw logits
     for key, v in r["outputs"].items():
-        assert np.abs(v.detach().numpy() - g["logits/" + key]).max() <= 1e-10, key
+        assert np.abs(cut(v.detach().numpy(), case) - g["logits/" + key]).max() <= 1e-10, key
     # ---- LossLayer.call (metrics.py:173-299) + regularisers
     assert r["loss"] == pytest.approx(float(g["total_loss"]), rel=1e-12)
     assert r["data_loss"] == pytest.approx(float(g["data_loss"]), rel=1e-12)
@@ -110,20 +123,23 @@ def test_oracle_merge_matches_reference_python(case):
     """MFP.call's return value (mfp.py:46-69,342-347) from the float32 run of the reference."""
     g, cols, batch, method, L, seed, step = load(case)
     input_dtype = INPUT_DTYPE.get(case, "set")
-    o = O.OracleMFP(cols, num_blocks=L, masking_method=method, dropout=RATE, l2=L2, dtype=torch.float32, input_dtype=input_dtype)
-    o.params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float32, bias_scale=0.05, input_dtype=input_dtype)
+    o = O.OracleMFP(cols, num_blocks=L, masking_method=method, dropout=RATE, l2=L2, dtype=torch.float32, input_dtype=input_dtype, context=CONTEXT.get(case))
+    o.params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float32, bias_scale=0.05, input_dtype=input_dtype, context=CONTEXT.get(case))
     draws = O.PhiloxDraws(seed, step)
     tasks = torch.as_tensor(g["tasks"])
     inputs = o.to_torch(batch)
     targets, mod, masks = O.preprocess_for_train(inputs, o.input_columns, tasks, draws, input_dtype)
     B, S = batch["left"].shape[:2]
-    outputs = O.model_forward(o.params, mod, o.input_columns, L, o.dropout_masks(draws, B, S), RATE, block_type=BLOCK_TYPE.get(case, "deepsvg"))
+    outputs = O.model_forward(o.params, mod, o.input_columns, L, o.dropout_masks(draws, B, S), RATE, block_type=BLOCK_TYPE.get(case, "deepsvg"),
+                              context=CONTEXT.get(case))
     merged = O.merge_inputs_and_prediction(inputs, o.input_columns, masks, outputs)
     keys = [k[7:] for k in g.files if k.startswith("merged/")]
     assert set(keys) == set(o.input_columns)
     for key in keys:
         ref = g["merged/" + key]
         got = merged[key].detach().numpy()
+        if o.input_columns[key]["is_sequence"]:
+            got = cut(got, case)
         assert got.shape == ref.shape, key
         if o.input_columns[key]["is_sequence"]:
             assert np.abs(got - ref).max() <= 2e-4, key
@@ -141,8 +157,9 @@ def test_engine_matches_reference_python(case, impl):
     g, cols, batch, method, L, seed, step = load(case)
     input_dtype = INPUT_DTYPE.get(case, "set")
     m = MFP(cols, num_blocks=L, block_type=BLOCK_TYPE.get(case, "deepsvg"), masking_method=method, input_dtype=input_dtype, latent_dim=256,
-            dropout=RATE, l2=L2, seed=0)
-    params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float64, bias_scale=0.05, input_dtype=input_dtype)
+            dropout=RATE, l2=L2, seed=0, context=CONTEXT.get(case))
+    m._pad_context = False  # the golden batches already keep one free row per document (see CASES)
+    params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float64, bias_scale=0.05, input_dtype=input_dtype, context=CONTEXT.get(case))
     m.set_weights({k: v.numpy().astype(np.float32) for k, v in params.items()})
     eng = m.engine
     eng.set_gemm_impl(impl)
@@ -151,6 +168,7 @@ def test_engine_matches_reference_python(case, impl):
     staged = m.stage(batch)
     _, _, length, dcols = m._bind(staged)
     tasks = torch.as_tensor(g["tasks"]).cuda()
+    m._set_context(tasks)
     if input_dtype != "set":  # shuffle_inputs / sort_inputs: permutation and reordered columns bit-exact against the reference's
         perm = torch.zeros((B, S), dtype=torch.int32, device="cuda")
         dcols = eng.shuffle_inputs(length, dcols, seed, step, perm_out=perm)
@@ -162,8 +180,8 @@ def test_engine_matches_reference_python(case, impl):
     torch.cuda.synchronize()
     # ---- masking: bit-exact against the reference's preprocess_for_train
     for f, key in enumerate(m.keys):
-        assert np.array_equal(eng.masks[f].cpu().numpy().astype(bool), g["mask/" + key]), key
-        got = eng.modified[f].cpu().numpy()
+        assert np.array_equal(cut(eng.masks[f].cpu().numpy().astype(bool), case), g["mask/" + key]), key
+        got = cut(eng.modified[f].cpu().numpy(), case)
         if cols[key]["type"] == "categorical":
             assert np.array_equal(got, g["mod/" + key]), key
         else:
@@ -181,7 +199,7 @@ def test_engine_matches_reference_python(case, impl):
     torch.cuda.synchronize()
     got = m.split_logits(logits, B, S)
     for key in m.keys:
-        assert np.abs(got[key].cpu().numpy() - g["logits/" + key]).max() <= logit_atol, key
+        assert np.abs(cut(got[key].cpu().numpy(), case) - g["logits/" + key]).max() <= logit_atol, key
     r = row.cpu().numpy()
     F = len(m.keys)
     assert r[3 * F] == pytest.approx(float(g["data_loss"]), rel=loss_rtol)
@@ -191,7 +209,7 @@ def test_engine_matches_reference_python(case, impl):
         assert r[3 * f + 2] == pytest.approx(den, abs=1e-3), key
         assert abs(r[3 * f + 1] - float(g["score_num/" + key])) <= max(1.0, 0.005 * den), key
     # ---- gradients (the engine adds the L2 term inside the optimiser pass: d(l2 sum w^2)/dw = 2 l2 w)
-    specs = O.variable_specs(cols, L, 256, input_dtype)
+    specs = O.variable_specs(cols, L, 256, input_dtype, CONTEXT.get(case))
     got_grads = eng.get_weights(eng.grads)
     w0 = eng.get_weights()
     for name in specs:
