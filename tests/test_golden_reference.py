@@ -198,8 +198,14 @@ def test_engine_matches_reference_python(case, impl):
     eng.backward(length, None, True, seed, step)
     torch.cuda.synchronize()
     got = m.split_logits(logits, B, S)
+    valid = np.ones((B, S), dtype=bool)
+    if case in CONTEXT:
+        # the engine keeps the context token in the first padding row of each document, where the reference computes a (never used)
+        # prediction for a padded element: raw logits are comparable on the documents' own elements
+        valid = np.arange(S)[None, :] <= batch["length"].reshape(B, 1)
     for key in m.keys:
-        assert np.abs(cut(got[key].cpu().numpy(), case) - g["logits/" + key]).max() <= logit_atol, key
+        diff = np.abs(cut(got[key].cpu().numpy(), case) - g["logits/" + key])
+        assert diff[cut(valid, case)].max() <= logit_atol, key
     r = row.cpu().numpy()
     F = len(m.keys)
     assert r[3 * F] == pytest.approx(float(g["data_loss"]), rel=loss_rtol)
@@ -236,7 +242,8 @@ def test_engine_matches_reference_python(case, impl):
         # exactly +-lr (compared strictly); entries whose exact gradient is ~0 move by up to lr in the direction of the
         # rounding noise, in the engine and in a float32 TensorFlow run alike (bounded by 2 lr).
         gref = g["gradhead/" + name] * min(1.0, 1.0 / max(float(g["gradnorm/" + name]), 1e-12))
-        strict = np.abs(gref) > 1e-3
+        # (TF32: a clipped entry of 1e-3 is 1e-3 of the gradient's norm, the size of the product path's own rounding error)
+        strict = np.abs(gref) > (1e-3 if impl == 1 else 5e-3)
         diff = np.abs(w[:8] - g["newhead/" + name])
         assert diff[strict].max(initial=0.0) <= 5e-6, name
         assert diff.max() <= 2.0 * LR + 5e-6, name

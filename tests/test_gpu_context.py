@@ -124,9 +124,15 @@ def test_context_demo_call_and_evaluation():
     # inner boundary: Model.call on already-modified inputs reads modified_inputs["task"]
     inner = m.model({k: v.numpy() for k, v in omod.items() if k in m.input_columns or k == "task"}, training=False)
     oref = O.model_forward(p, omod, m.input_columns, 1, context="id")
+    valid = seq.numpy()  # raw outputs at padded positions are never used; the row after a document's last element holds the token here
     for key in m.keys:
-        assert np.abs(inner[key].cpu().numpy()[:, :S] - oref[key][:, :S].numpy()).max() <= H.LOGIT_ATOL, key
+        assert np.abs(inner[key].cpu().numpy()[:, :S] - oref[key][:, :S].numpy())[valid].max() <= H.LOGIT_ATOL, key
     # eval.py loop
     group = ("pos", get_attribute_groups(cols.keys())["pos"])
     scores = evaluate(m, [batch], m.input_columns, "pos", group=group)
-    assert set(scores) >= {"left", "top", "width", "height"} and all(0.0 <= v <= 1.0 for v in scores.values())
+    assert all(0.0 <= scores[k] <= 1.0 for k in ("left", "top", "width", "height"))  # the other fields are 0/0 = nan, as in the reference
+    # same numbers from the oracle's predictions pushed through the oracle's loss layer
+    _, _, oscores, _ = O.loss_layer(pt, O.model_forward(p, omod, m.input_columns, 1, context="id"), pmasks, m.all_columns, torch.ones((B,), dtype=torch.bool))
+    for k in ("left", "top", "width", "height"):
+        want = float(oscores[k + "_score_num"]) / float(oscores[k + "_score_den"])
+        assert scores[k] == pytest.approx(want, abs=0.08), k  # argmax ties under TF32 may flip single elements
