@@ -444,6 +444,25 @@ class DataSpec:
             output[name] = arr
         return output
 
+    def record_steps(self, pointers: np.ndarray, lengths: np.ndarray) -> np.ndarray:
+        """Number of elements (sequence steps) of each record."""
+        B = len(pointers)
+        schema, _ = self._schema(False)
+        ptrs = (ctypes.c_void_p * max(B, 1))(*[int(p) for p in pointers])
+        lens = (ctypes.c_uint64 * max(B, 1))(*[int(n) for n in lengths])
+        steps = (ctypes.c_int32 * max(B, 1))()
+        io_lib.check(self._lib.fdio_batch_steps(schema, ptrs, lens, B, steps, self._threads))
+        return np.asarray(steps[:B], dtype=np.int64)
+
+    def pad_word(self, name: str) -> int:
+        """The 32-bit pattern a padded step of a sequence column holds: the parse default (0 / 0.0 / "") through its preprocessor."""
+        column = self.columns[name]
+        layer = self._preprocessor.get(name)
+        if layer is None:
+            return 0
+        default = "" if column["dtype"] == "string" else 0
+        return int(np.asarray(layer([default] if isinstance(layer, SequenceDiscretizer) else default)).reshape(-1)[0])
+
     def parse_fn(self, serialized: Sequence[bytes], pad_to: Optional[int] = None) -> Dict:
         """``DataSpec.parse_fn`` over a batch of serialized SequenceExample byte strings (spec.py:255-287)."""
         bufs = [ctypes.create_string_buffer(s, len(s)) for s in serialized]
@@ -454,11 +473,12 @@ class DataSpec:
     # ---------------------------------------------------------------------------------------------------------------- datasets
     def make_dataset(self, split: str, batch_size: Optional[int] = None, shuffle=None, repeat: bool = False, prefetch: Optional[int] = 2,
                      parallel=None, cache=None, seed: int = 0, pad_to: Optional[int] = None, pin_memory: Optional[bool] = None,
-                     strings: bool = False, verify_crc: int = 1) -> "RecordDataset":
+                     strings: bool = False, verify_crc: int = 1, device=None) -> "RecordDataset":
         """spec.py:213-253: list ``<split>-*.tfrecord``, read, [shuffle], [repeat], batch, parse, prefetch.
 
-        ``parallel`` and ``cache`` are accepted for signature compatibility: shards are always mmapped (the page cache is the cache) and
-        parsing always uses the spec's host threads.  ``shuffle=True`` shuffles over the whole split like the reference
+        ``parallel`` and ``cache=True`` are accepted for signature compatibility: shards are always mmapped (the page cache is the cache)
+        and parsing always uses the spec's host threads.  ``cache="device"`` parses the split once into HBM and cuts every batch out of
+        it on the GPU (``device_cache.DeviceCachedDataset``; same batches for the same ``seed``).  ``shuffle=True`` shuffles over the whole split like the reference
         (``shuffle = self.size(split)``); an integer is a shuffle-buffer size.  ``strings=False`` leaves the demo-only byte-string
         columns (``id``, ``uuid``) out of the batches -- ``MFP`` drops them anyway (mfp.py:235-237)."""
         assert split in self._splits, "split must be one of (%s)" % ", ".join(self._splits.keys())
@@ -470,6 +490,11 @@ class DataSpec:
             raise FileNotFoundError("No TFRecord matches %s" % pattern)
         if pin_memory is None:
             pin_memory = torch.cuda.is_available()
+        if cache == "device":  # the parsed split resident in HBM, batches gathered on the GPU (device_cache.py)
+            from .device_cache import DeviceCachedDataset
+
+            return DeviceCachedDataset(RecordDataset(self, files, batch_size or self._batch_size, int(shuffle or 0), repeat, 0, seed, pad_to, pin_memory,
+                                                     False, verify_crc), device=device)
         return RecordDataset(self, files, batch_size or self._batch_size, int(shuffle or 0), repeat, prefetch or 0, seed, pad_to, pin_memory,
                              strings, verify_crc)
 

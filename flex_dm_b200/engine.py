@@ -44,6 +44,13 @@ class Batch(ctypes.Structure):
 
 
 _PTR_ARRAY = ctypes.c_void_p * MAX_FIELDS
+GATHER_MAX_COLUMNS = 24
+
+
+class GatherDesc(ctypes.Structure):
+    _fields_ = [("n_columns", ctypes.c_int32), ("words", ctypes.c_int32 * GATHER_MAX_COLUMNS), ("pad_word", ctypes.c_uint32 * GATHER_MAX_COLUMNS),
+                ("src", ctypes.c_void_p * GATHER_MAX_COLUMNS), ("dst", ctypes.c_void_p * GATHER_MAX_COLUMNS)]
+
 
 _SIGNATURES = {
     "mfp_last_error": (ctypes.c_char_p, []),
@@ -79,6 +86,8 @@ _SIGNATURES = {
     "mfp_optimizer_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
     "mfp_regularization_loss": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "mfp_merge_prediction": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p]),
+    "mfp_gather_documents": (ctypes.c_int, [ctypes.POINTER(GatherDesc), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
                                             ctypes.c_void_p]),
     "mfp_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "mfp_set_gemm_impl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
@@ -385,6 +394,25 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self.lib.mfp_launch_count(self.handle))
+
+
+def gather_documents(sources: List[torch.Tensor], pads: List[int], doc_start: torch.Tensor, doc_len: torch.Tensor, idx: torch.Tensor, S: int) -> List[torch.Tensor]:
+    """``mfp_gather_documents``: padded ``[B, S, C]`` batch columns cut out of ragged ``[total_elements, C]`` device arrays."""
+    lib = load_library()
+    B = int(idx.numel())
+    d = GatherDesc()
+    d.n_columns = len(sources)
+    outs = []
+    for c, (src, pad) in enumerate(zip(sources, pads)):
+        assert src.is_cuda and src.dim() == 2 and src.element_size() == 4 and src.is_contiguous()
+        out = torch.empty((B, S, src.shape[1]), dtype=src.dtype, device=src.device)
+        d.words[c] = int(src.shape[1])
+        d.pad_word[c] = int(pad) & 0xFFFFFFFF
+        d.src[c] = src.data_ptr()
+        d.dst[c] = out.data_ptr()
+        outs.append(out)
+    _check(lib, lib.mfp_gather_documents(ctypes.byref(d), _ptr(doc_start), _ptr(doc_len), _ptr(idx), B, int(S), _stream()), "mfp_gather_documents")
+    return outs
 
 
 def debug_attention(qkv: torch.Tensor, length: torch.Tensor, B: int, S: int, impl: int = 0):

@@ -314,7 +314,10 @@ class MFP:
         """train.py:79-88.  ``dataset`` yields batch dicts and repeats (train.py:44-46 ``repeat=True``)."""
         from .data import DevicePrefetcher
 
-        iterator = DevicePrefetcher(self, dataset)  # H2D copies of step i+1 run under the compute of step i
+        if getattr(dataset, "yields_device_batches", False):  # DataSpec.make_dataset(cache="device"): batches are cut out of HBM
+            iterator = iter(dataset)
+        else:
+            iterator = DevicePrefetcher(self, dataset)  # H2D copies of step i+1 run under the compute of step i
         for epoch in range(epochs):
             logs = self._run_epoch(iterator, steps_per_epoch, True, staged=True)
             if validation_data is not None and (epoch + 1) % max(1, validation_freq) == 0:

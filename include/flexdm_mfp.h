@@ -188,6 +188,22 @@ int mfp_set_gemm_impl(mfp_engine* h, int32_t impl);
 int mfp_profile_begin(mfp_engine* h);
 int mfp_profile_end(mfp_engine* h, float* ms_per_class_host, int32_t* launches_per_class_host, double* bytes_per_class_host);
 
+/* Device-resident dataset cache (the B200 answer to dataset.cache() of DataSpec.make_dataset, data/spec.py:238-239): a parsed split is
+ * kept ragged in HBM -- per sequence column one [total_elements, C] array of 32-bit words, documents back to back -- and a batch is
+ * cut out of it on the device.  For every column c and every b < B, s < S:
+ *     dst[c][b, s, :] = s < doc_len[idx[b]] ? src[c][doc_start[idx[b]] + s, :] : pad_word[c]
+ * (pad_word = the parse default put through the column's preprocessor, like parse_sequence_example's padding).  Engine-independent. */
+#define MFP_GATHER_MAX_COLUMNS 24
+typedef struct {
+  int32_t n_columns;
+  int32_t words[MFP_GATHER_MAX_COLUMNS];       /* 32-bit words per element of the column (C for int32 / float32 columns) */
+  uint32_t pad_word[MFP_GATHER_MAX_COLUMNS];
+  const void* src[MFP_GATHER_MAX_COLUMNS];     /* device, [total_elements, words] */
+  void* dst[MFP_GATHER_MAX_COLUMNS];           /* device, [B, S, words] */
+} mfp_gather_desc;
+int mfp_gather_documents(const mfp_gather_desc* desc, const int64_t* doc_start, const int32_t* doc_len, const int32_t* idx, int32_t B,
+                         int32_t S, void* stream);
+
 /* Bring-up hook: the attention core of MultiHeadSelfAttention (architecture/transformer.py:60-76) alone.
  * qkv [B*S, 768] (q | k | v, head h = columns 32h..32h+31 of each third), length [B] zero-based;
  * out [B*S, 256] heads merged, lse [B, 8, S].  impl: 0 = tcgen05 (S <= 128), 1 = SIMT. */
