@@ -103,5 +103,6 @@ def test_device_cached_dataset_matches_streaming(tmp_path, name):
     # ... and it is the same training run as from the streamed batches
     other = MFP(dataspec.make_input_columns(), num_blocks=1, masking_method="random", latent_dim=256, dropout=0.1, l2=1e-2, seed=2)
     other.compile(optimizer=Adam(learning_rate=1e-3, clipnorm=1.0))
-    h2 = other.fit(dataspec.make_dataset("train", shuffle=True, repeat=True, seed=4), steps_per_epoch=dataspec.steps_per_epoch("train"), epochs=3, verbose=0)
+    h2 = other.fit(dataspec.make_dataset("train", shuffle=True, repeat=True, seed=4), steps_per_epoch=dataspec.steps_per_epoch("train"), epochs=3,
+                   validation_data=dataspec.make_dataset("val"), validation_steps=1, verbose=0)  # (validation advances the RNG step counter too)
     assert [h["loss"] for h in h2] == pytest.approx([h["loss"] for h in history], rel=1e-4)  # split-K reduce-adds are unordered
