@@ -412,12 +412,11 @@ class DataSpec:
         schema, out_kind = self._schema(bool(strings))
         ptrs = (ctypes.c_void_p * max(B, 1))(*[int(p) for p in pointers])
         lens = (ctypes.c_uint64 * max(B, 1))(*[int(n) for n in lengths])
-        steps = (ctypes.c_int32 * max(B, 1))()
-        io_lib.check(self._lib.fdio_batch_steps(schema, ptrs, lens, B, steps, self._threads))
-        S = max(steps[:B]) if B else 0
-        if pad_to is not None:
-            if S > pad_to:
-                raise ValueError("A document has %d elements, more than pad_to=%d" % (S, pad_to))
+        if pad_to is None:  # parse_sequence_example pads to the longest document of the batch: one cheap pass over the record structure
+            steps = (ctypes.c_int32 * max(B, 1))()
+            io_lib.check(self._lib.fdio_batch_steps(schema, ptrs, lens, B, steps, self._threads))
+            S = max(steps[:B]) if B else 0
+        else:  # fixed shape: the fill pass itself reports a document that does not fit
             S = int(pad_to)
         out_ptrs = (ctypes.c_void_p * len(self._order))()
         output, spans = OrderedDict(), {}
@@ -434,7 +433,10 @@ class DataSpec:
                 t = torch.empty(full, dtype=torch.int32 if kind == io_lib.OUT_INT32 else torch.float32, pin_memory=pin_memory)  # every slot is written
             output[name] = t
             out_ptrs[i] = t.data_ptr()
-        io_lib.check(self._lib.fdio_parse_batch(schema, ptrs, lens, B, S, out_ptrs, self._threads))
+        code = self._lib.fdio_parse_batch(schema, ptrs, lens, B, S, out_ptrs, self._threads)
+        if code == io_lib.ERR_ARG and pad_to is not None and "more steps" in io_lib.last_error():
+            raise ValueError("A document has more than pad_to=%d elements (%s)" % (pad_to, io_lib.last_error()))
+        io_lib.check(code)
         for name, t in spans.items():  # (offset, length) pairs -> byte strings
             sp = t.numpy()
             arr = np.empty(sp.shape[:-1], dtype=object)
@@ -473,12 +475,14 @@ class DataSpec:
     # ---------------------------------------------------------------------------------------------------------------- datasets
     def make_dataset(self, split: str, batch_size: Optional[int] = None, shuffle=None, repeat: bool = False, prefetch: Optional[int] = 2,
                      parallel=None, cache=None, seed: int = 0, pad_to: Optional[int] = None, pin_memory: Optional[bool] = None,
-                     strings: bool = False, verify_crc: int = 1, device=None) -> "RecordDataset":
+                     strings: bool = False, verify_crc: int = 1, device=None, shard=None) -> "RecordDataset":
         """spec.py:213-253: list ``<split>-*.tfrecord``, read, [shuffle], [repeat], batch, parse, prefetch.
 
         ``parallel`` and ``cache=True`` are accepted for signature compatibility: shards are always mmapped (the page cache is the cache)
         and parsing always uses the spec's host threads.  ``cache="device"`` parses the split once into HBM and cuts every batch out of
-        it on the GPU (``device_cache.DeviceCachedDataset``; same batches for the same ``seed``).  ``shuffle=True`` shuffles over the whole split like the reference
+        it on the GPU (``device_cache.DeviceCachedDataset``; same batches for the same ``seed``).  ``shard=(rank, world_size)`` is the
+        document-sharded data-parallel split (``tf.data``'s ``shard``): every rank draws the same (seeded) document
+        order and keeps every ``world_size``-th document starting at ``rank``, so ranks see disjoint documents and equally many batches.  ``shuffle=True`` shuffles over the whole split like the reference
         (``shuffle = self.size(split)``); an integer is a shuffle-buffer size.  ``strings=False`` leaves the demo-only byte-string
         columns (``id``, ``uuid``) out of the batches -- ``MFP`` drops them anyway (mfp.py:235-237)."""
         assert split in self._splits, "split must be one of (%s)" % ", ".join(self._splits.keys())
@@ -494,9 +498,9 @@ class DataSpec:
             from .device_cache import DeviceCachedDataset
 
             return DeviceCachedDataset(RecordDataset(self, files, batch_size or self._batch_size, int(shuffle or 0), repeat, 0, seed, pad_to, pin_memory,
-                                                     False, verify_crc), device=device)
+                                                     False, verify_crc, shard), device=device)
         return RecordDataset(self, files, batch_size or self._batch_size, int(shuffle or 0), repeat, prefetch or 0, seed, pad_to, pin_memory,
-                             strings, verify_crc)
+                             strings, verify_crc, shard)
 
     # ---------------------------------------------------------------------------------------------------------------- post-processing
     def logit_to_label(self, example: Dict) -> Dict:
@@ -554,7 +558,7 @@ class RecordDataset:
     torch's caching host allocator, which recycles them safely under asynchronous device copies."""
 
     def __init__(self, spec: DataSpec, files: List[str], batch_size: int, shuffle: int, repeat: bool, prefetch: int, seed: int,
-                 pad_to: Optional[int], pin_memory: bool, strings: bool, verify_crc: int):
+                 pad_to: Optional[int], pin_memory: bool, strings: bool, verify_crc: int, shard=None):
         self.spec = spec
         self.shards = [TFRecordFile(f, verify_crc) for f in files]
         self.pointers = np.concatenate([s.pointers for s in self.shards]) if self.shards else np.empty(0, np.uint64)
@@ -562,11 +566,26 @@ class RecordDataset:
         self.batch_size, self.shuffle, self.repeat, self.prefetch = int(batch_size), int(shuffle), bool(repeat), int(prefetch)
         self.seed, self.pad_to, self.pin_memory, self.strings = seed, pad_to, pin_memory, strings
         self._epoch = 0
+        self.shard = None
+        if shard is not None:
+            rank, world = int(shard[0]), int(shard[1])
+            if not 0 <= rank < world:
+                raise ValueError("shard=(rank, world_size) with 0 <= rank < world_size, got %r" % (shard,))
+            self.shard = (rank, world)
 
     def __len__(self):
         return len(self.pointers)
 
     def _index_stream(self, rng: np.random.Generator) -> Iterator[int]:
+        if self.shard is None:
+            yield from self._global_stream(rng)
+            return
+        rank, world = self.shard
+        for k, i in enumerate(self._global_stream(rng)):  # identical on every rank (same seed): keep every world-th document
+            if k % world == rank:
+                yield i
+
+    def _global_stream(self, rng: np.random.Generator) -> Iterator[int]:
         n = len(self.pointers)
         while True:
             order = np.arange(n)

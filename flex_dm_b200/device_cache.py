@@ -68,7 +68,7 @@ class DeviceCachedDataset:
         S = int(self.doc_len_host[idx_host].max()) if len(picked) else 0
         if self.source.pad_to is not None:
             if S > self.source.pad_to:
-                raise ValueError("A document has %d elements, more than pad_to=%d" % (S, self.source.pad_to))
+                raise ValueError("A document has more than pad_to=%d elements (%d)" % (self.source.pad_to, S))
             S = int(self.source.pad_to)
         idx = torch.from_numpy(idx_host).to(self.device, non_blocking=True)
         out = OrderedDict()

@@ -653,3 +653,18 @@ def test_dataspec_matches_the_reference_run_golden(name):
     first = next(iter(spec.make_dataset("train", batch_size=len(records), shuffle=False)))
     for k in arrays.files:
         assert np.array_equal(first[k].numpy(), arrays[k]), k
+
+
+def test_sharded_datasets_partition_the_documents(crello_dir):
+    """``shard=(rank, world)``: the data-parallel ranks draw one seeded document order and split it document by document."""
+    root, _ = crello_dir
+    spec = DataSpec("crello", root, batch_size=4)
+    ids = lambda ds, n=None: [bytes(x) for i, b in zip(range(n or 10 ** 9), ds) for x in b["id"][:, 0]]
+    whole = ids(spec.make_dataset("train", shuffle=True, seed=6, strings=True))
+    parts = [ids(spec.make_dataset("train", shuffle=True, seed=6, strings=True, shard=(r, 3))) for r in range(3)]
+    assert [len(p) for p in parts] == [13, 12, 12] and sorted(sum(parts, [])) == sorted(whole)
+    assert all(parts[r] == whole[r::3] for r in range(3))
+    rep = [ids(spec.make_dataset("train", shuffle=True, seed=6, strings=True, repeat=True, shard=(r, 2)), n=20) for r in range(2)]
+    assert len(rep[0]) == len(rep[1]) == 80 and not set(rep[0][:18]) & set(rep[1][:18])
+    with pytest.raises(ValueError):
+        spec.make_dataset("train", shard=(3, 3))
