@@ -191,9 +191,32 @@ def tfrecord_leg(model, timed, steps):
         for i in range(3):
             step_cached(i)
         ms_cached = timed(step_cached, steps)
+        # the gather alone (kernel + the small index / context-column operations around it), against the HBM roofline: it reads and writes
+        # every column of the batch once
+        order = list(range(B_PER_GPU))
+        for _ in range(3):
+            cached.batch(order)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record()
+        n_gather = 20
+        for k in range(n_gather):
+            order = order[7:] + order[:7]
+            got = cached.batch(order)
+        ev1.record()
+        torch.cuda.synchronize()
+        gather_ms = ev0.elapsed_time(ev1) / n_gather
+        gather_bytes = 2 * sum(t.numel() * t.element_size() for k, t in got.items() if t.dim() == 3)
+        peak = 6650.0
+        try:
+            peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", peak)
+        except Exception:
+            pass
         return {"value": B_PER_GPU * SEQ_LEN * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
                 "device_cached": {"value": B_PER_GPU * SEQ_LEN * steps / (ms_cached * 1e-3), "unit": UNIT, "ms_per_step": ms_cached / steps,
                                   "resident_bytes": cached.nbytes(),
+                                  "gather": {"ms": gather_ms, "algorithmic_bytes": gather_bytes, "achieved": gather_bytes / (gather_ms * 1e-3) / 1e9,
+                                             "unit": "GB/s", "peak": peak, "frac": gather_bytes / (gather_ms * 1e-3) / 1e9 / peak},
                                   "source": "the parsed split kept ragged in HBM, batches cut out by mfp_gather_documents (DataSpec.make_dataset(cache='device'))"},
                 "host_parse_ms_per_batch": host_ms, "host_threads": spec._threads,
                 "source": "TFRecord shards of tf.train.SequenceExample (256 synthetic crello documents, S=128) -> DataSpec.make_dataset(shuffle, repeat, "
