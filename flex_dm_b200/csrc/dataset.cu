@@ -5,8 +5,9 @@
 // and B indices over PCIe.
 //
 // Layout: per column a [total_elements, W] array of 32-bit words with the documents back to back, so the W * n words of one document
-// are contiguous and a warp reads them coalesced.  blockIdx.y = column; the x-blocks of a column grid-stride over its B * S * W output
-// words in 16-byte groups when W is a multiple of 4 (the 512-float embeddings), word by word otherwise (C = 1 or 3 categorical columns).
+// are contiguous and a warp reads them coalesced.  blockIdx.y = column; the x-blocks of a column grid-stride over (document, chunk)
+// items of its B * S * W output words, in 16-byte units when W is a multiple of 4 (the 512-float embeddings), word by word otherwise
+// (C = 1 or 3 categorical columns).
 #include <cstdint>
 
 #include "common.cuh"
@@ -23,38 +24,37 @@ struct GatherArgs {
   uint32_t* dst[MFP_GATHER_MAX_COLUMNS];
 };
 
+// Work item = (document b, chunk of kChunk units of its S * W output words); unit = 16 bytes when W % 4 == 0, one word otherwise.
+// Items are grid-strided with 32-bit arithmetic (one division per item, none per load).
+constexpr int kChunk = 2048;  // units per item: 8 per thread
+
+template <typename Unit>
+__device__ __forceinline__ void gather_column(const Unit* __restrict__ src, Unit* __restrict__ dst, Unit padv, int units_per_elem, const long long* __restrict__ doc_start,
+                                              const int* __restrict__ doc_len, const int* __restrict__ idx, int B, int S) {
+  const unsigned per_doc = (unsigned)S * (unsigned)units_per_elem;
+  const unsigned chunks = (per_doc + kChunk - 1) / kChunk;
+  const unsigned items = (unsigned)B * chunks;
+  for (unsigned item = blockIdx.x; item < items; item += gridDim.x) {
+    const unsigned b = item / chunks, ch = item - b * chunks;
+    const int d = __ldg(idx + b);
+    const unsigned valid = (unsigned)__ldg(doc_len + d) * (unsigned)units_per_elem;
+    const Unit* from = src + (size_t)__ldg(doc_start + d) * units_per_elem;
+    Unit* to = dst + (size_t)b * per_doc;
+    const unsigned hi = min(per_doc, (ch + 1) * kChunk);
+#pragma unroll 4
+    for (unsigned r = ch * kChunk + threadIdx.x; r < hi; r += blockDim.x) to[r] = r < valid ? __ldg(from + r) : padv;
+  }
+}
+
 __global__ void __launch_bounds__(256) gather_documents_kernel(const __grid_constant__ GatherArgs a, const long long* __restrict__ doc_start,
                                                                const int* __restrict__ doc_len, const int* __restrict__ idx, int B, int S) {
   const int c = blockIdx.y;
   const int W = a.words[c];
   const uint32_t pad = a.pad[c];
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const size_t first = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if ((W & 3) == 0) {
-    const int W4 = W >> 2;
-    const size_t per_doc = (size_t)S * W4, total = (size_t)B * per_doc;
-    const uint4* src = reinterpret_cast<const uint4*>(a.src[c]);
-    uint4* dst = reinterpret_cast<uint4*>(a.dst[c]);
-    const uint4 padv = make_uint4(pad, pad, pad, pad);
-    for (size_t i = first; i < total; i += stride) {
-      const int b = (int)(i / per_doc);
-      const size_t r = i - (size_t)b * per_doc;  // (s, word group) within the document
-      const int d = __ldg(idx + b);
-      const size_t valid = (size_t)__ldg(doc_len + d) * W4;
-      dst[i] = r < valid ? __ldg(src + (size_t)__ldg(doc_start + d) * W4 + r) : padv;
-    }
-  } else {
-    const size_t per_doc = (size_t)S * W, total = (size_t)B * per_doc;
-    const uint32_t* src = a.src[c];
-    uint32_t* dst = a.dst[c];
-    for (size_t i = first; i < total; i += stride) {
-      const int b = (int)(i / per_doc);
-      const size_t r = i - (size_t)b * per_doc;
-      const int d = __ldg(idx + b);
-      const size_t valid = (size_t)__ldg(doc_len + d) * W;
-      dst[i] = r < valid ? __ldg(src + (size_t)__ldg(doc_start + d) * W + r) : pad;
-    }
-  }
+  if ((W & 3) == 0)
+    gather_column<uint4>(reinterpret_cast<const uint4*>(a.src[c]), reinterpret_cast<uint4*>(a.dst[c]), make_uint4(pad, pad, pad, pad), W >> 2, doc_start, doc_len, idx, B, S);
+  else
+    gather_column<uint32_t>(a.src[c], a.dst[c], pad, W, doc_start, doc_len, idx, B, S);
 }
 
 }  // namespace mfp
@@ -78,11 +78,13 @@ extern "C" int mfp_gather_documents(const mfp_gather_desc* desc, const int64_t* 
     a.pad[c] = desc->pad_word[c];
     a.src[c] = static_cast<const uint32_t*>(desc->src[c]);
     a.dst[c] = static_cast<uint32_t*>(desc->dst[c]);
-    const size_t units = (size_t)B * S * ((desc->words[c] & 3) == 0 ? desc->words[c] >> 2 : desc->words[c]);
-    most = units > most ? units : most;
+    const size_t per_doc = (size_t)S * ((desc->words[c] & 3) == 0 ? desc->words[c] >> 2 : desc->words[c]);
+    if (per_doc * (size_t)B >= (1ull << 31)) { set_error("mfp_gather_documents: column %d is too large for 32-bit indexing", c); return MFP_ERR_UNSUPPORTED; }
+    const size_t items = (size_t)B * ((per_doc + kChunk - 1) / kChunk);
+    most = items > most ? items : most;
   }
-  // enough x-blocks for the widest column to fill the machine (148 SMs x 8 resident 256-thread blocks), no more than its work
-  size_t bx = (most + 255) / 256;
+  // x-blocks: the items of the widest column, at most one full wave of 8 resident 256-thread blocks per SM
+  size_t bx = most;
   if (bx > 148 * 8) bx = 148 * 8;
   if (bx < 1) bx = 1;
   dim3 grid((unsigned)bx, (unsigned)desc->n_columns);

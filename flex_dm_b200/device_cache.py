@@ -49,7 +49,13 @@ class DeviceCachedDataset:
         self.doc_len_host = np.concatenate(lens).astype(np.int32) if lens else np.zeros(0, np.int32)
         starts = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(self.doc_len_host, out=starts[1:])
-        self.elements = OrderedDict((k, torch.cat(v).contiguous() if v else torch.empty((0, 1), device=self.device)) for k, v in pieces.items())
+        self.elements = OrderedDict()
+        for k, v in pieces.items():
+            width = int(np.prod(spec.columns[k].get("shape", (1,))))
+            t = torch.cat(v).reshape(-1, width).contiguous() if v else None
+            if t is None or t.numel() == 0:  # a split of empty documents: keep one dummy row so that the column has an address
+                t = torch.zeros((1, width), dtype=torch.float32 if out_kind[k] == io_lib.OUT_FLOAT32 else torch.int32, device=self.device)
+            self.elements[k] = t
         self.context = OrderedDict((k, torch.cat(v).contiguous()) for k, v in ctx.items())
         self.doc_start = torch.from_numpy(starts[:-1].copy()).to(self.device)
         self.doc_len = torch.from_numpy(self.doc_len_host).to(self.device)
@@ -70,7 +76,7 @@ class DeviceCachedDataset:
             if S > self.source.pad_to:
                 raise ValueError("A document has more than pad_to=%d elements (%d)" % (self.source.pad_to, S))
             S = int(self.source.pad_to)
-        idx = torch.from_numpy(idx_host).to(self.device, non_blocking=True)
+        idx = torch.from_numpy(idx_host).pin_memory().to(self.device, non_blocking=True)  # pinned staging: the copy does not block the host
         out = OrderedDict()
         long_idx = idx.long()
         for k, t in self.context.items():
