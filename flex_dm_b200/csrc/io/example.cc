@@ -25,13 +25,53 @@ namespace {
 
 using fdio::Wire;
 
+// Vocabulary of a string lookup: open addressing over FNV-1a, probed with the record's bytes in place (no temporary std::string).
+struct StringTable {
+  std::vector<int32_t> slot;  // index into keys, -1 = empty; size = power of two >= 2 * keys
+  std::vector<std::string> keys;
+  std::vector<int32_t> values;
+  static uint64_t hash(const uint8_t* p, size_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h ^ (h >> 29);
+  }
+  bool insert(const std::string& key, int32_t value) {
+    if (find(reinterpret_cast<const uint8_t*>(key.data()), key.size()) != nullptr) return false;
+    keys.push_back(key);
+    values.push_back(value);
+    if (slot.size() < 2 * keys.size() + 2) {
+      size_t cap = 16;
+      while (cap < 4 * keys.size()) cap <<= 1;
+      slot.assign(cap, -1);
+      for (size_t k = 0; k < keys.size(); ++k) place(int32_t(k));
+    } else {
+      place(int32_t(keys.size() - 1));
+    }
+    return true;
+  }
+  void place(int32_t k) {
+    size_t i = hash(reinterpret_cast<const uint8_t*>(keys[size_t(k)].data()), keys[size_t(k)].size()) & (slot.size() - 1);
+    while (slot[i] >= 0) i = (i + 1) & (slot.size() - 1);
+    slot[i] = k;
+  }
+  const int32_t* find(const uint8_t* p, size_t n) const {
+    if (slot.empty()) return nullptr;
+    size_t i = hash(p, n) & (slot.size() - 1);
+    for (int32_t k; (k = slot[i]) >= 0; i = (i + 1) & (slot.size() - 1)) {
+      const std::string& key = keys[size_t(k)];
+      if (key.size() == n && memcmp(key.data(), p, n) == 0) return &values[size_t(k)];
+    }
+    return nullptr;
+  }
+};
+
 struct Column {
   std::string name;
   int is_sequence, dtype, width, transform, output;
   int num_oov, has_mask;
   std::string mask_str;
   int64_t mask_int;
-  std::unordered_map<std::string, int32_t> str_index;
+  StringTable str_index;
   std::unordered_map<int64_t, int32_t> int_index;
   std::vector<float> boundaries;
   int32_t first_vocab_index;  // [mask] + [oov] come first
@@ -63,8 +103,7 @@ namespace {
 // ---- preprocessors ----------------------------------------------------------------------------------------------------------------
 int lookup_str(const Column& c, const uint8_t* s, size_t n, int32_t* out) {
   if (c.has_mask && n == c.mask_str.size() && memcmp(s, c.mask_str.data(), n) == 0) { *out = 0; return FDIO_OK; }
-  auto it = c.str_index.find(std::string(reinterpret_cast<const char*>(s), n));
-  if (it != c.str_index.end()) { *out = it->second; return FDIO_OK; }
+  if (const int32_t* hit = c.str_index.find(s, n)) { *out = *hit; return FDIO_OK; }
   if (c.num_oov == 1) { *out = c.has_mask ? 1 : 0; return FDIO_OK; }
   return FDIO_ERR_OOV;
 }
@@ -169,6 +208,39 @@ int64_t for_each_value(const Column& c, const uint8_t* p, size_t n, Fn&& fn, flo
     }
   }
   return kind_seen ? count : int64_t(FDIO_ERR_NOT_FOUND);  // a Feature with no kind set holds no values
+}
+
+// The canonical encodings of a Feature holding exactly one value (what every scalar column of a step looks like; all lengths < 128):
+//   bytes : 0a L+2 0a L <bytes>        float : 12 06 0a 04 <f32> (packed) or 12 05 0d <f32>        int64 : 1a L+2 0a L <varint> or 1a L+1 08 <varint>
+// Returns true and fills v when the bytes have exactly that shape and the kind is the column's; anything else goes through
+// for_each_value, which handles every legal encoding and reports the errors.
+inline bool single_value(const Column& c, const uint8_t* p, size_t n, Value* v) {
+  if (n < 3 || n > 129 || p[1] != n - 2) return false;
+  if (p[0] == 0x0a && c.dtype == FDIO_STRING) {
+    if (n < 4 || p[2] != 0x0a || p[3] != n - 4) return false;
+    v->s = p + 4; v->n = n - 4;
+    return true;
+  }
+  if (p[0] == 0x12 && c.dtype == FDIO_FLOAT32) {
+    if (n == 8 && p[2] == 0x0a && p[3] == 0x04) { memcpy(&v->f, p + 4, 4); return true; }
+    if (n == 7 && p[2] == 0x0d) { memcpy(&v->f, p + 3, 4); return true; }
+    return false;
+  }
+  if (p[0] == 0x1a && c.dtype == FDIO_INT64) {
+    size_t at;
+    if (p[2] == 0x0a) { if (n < 5 || p[3] != n - 4) return false; at = 4; }
+    else if (p[2] == 0x08) at = 3;
+    else return false;
+    uint64_t u = 0;
+    int shift = 0;
+    for (; at < n && shift < 64; shift += 7) {
+      const uint8_t byte = p[at++];
+      u |= uint64_t(byte & 0x7f) << shift;
+      if (!(byte & 0x80)) { if (at != n) return false; v->i = int64_t(u); return true; }
+    }
+    return false;
+  }
+  return false;
 }
 
 // Collects the (key -> message bytes) entries of a Features / FeatureLists map; last occurrence of a key wins (protobuf map rule).
@@ -281,6 +353,13 @@ void parse_record(const fdio_schema& s, const uint8_t* rec, size_t len, int32_t 
       if (!w.bytes(&fp, &fn)) { describe(err, FDIO_ERR_CORRUPT, b, c, t, "malformed protobuf"); return; }
       if (t >= S) { describe(err, FDIO_ERR_ARG, b, c, t, "more steps than the batch was sized for"); return; }
       const size_t base = (size_t(b) * size_t(S) + size_t(t)) * W;
+      Value one;
+      if (W == 1 && single_value(c, fp, fn, &one)) {
+        const int code = emit(c, one, o, base, rec);
+        if (code != FDIO_OK) { describe(err, code, b, c, t, what_for(code, c, scratch, sizeof(scratch))); return; }
+        ++t;
+        continue;
+      }
       float* bulk = (c.transform == FDIO_NONE && c.output == FDIO_OUT_FLOAT32) ? static_cast<float*>(o) + base : nullptr;
       int64_t n = for_each_value(c, fp, fn, [&](const Value& v, int64_t k) { return k < int64_t(W) ? emit(c, v, o, base + size_t(k), rec) : FDIO_OK; }, bulk, W);
       if (n < 0) { describe(err, n == FDIO_ERR_NOT_FOUND ? int(FDIO_ERR_INVALID) : int(n), b, c, t, what_for(int(n), c, scratch, sizeof(scratch))); return; }
@@ -356,7 +435,7 @@ fdio_schema* fdio_schema_create(const fdio_column* columns, int32_t n) {
       }
       c.first_vocab_index = (c.has_mask ? 1 : 0) + c.num_oov;
       for (int32_t k = 0; k < in.vocab_size; ++k) {
-        bool fresh = c.dtype == FDIO_STRING ? c.str_index.emplace(in.vocab_str[k], c.first_vocab_index + k).second
+        bool fresh = c.dtype == FDIO_STRING ? c.str_index.insert(in.vocab_str[k], c.first_vocab_index + k)
                                             : c.int_index.emplace(in.vocab_int[k], c.first_vocab_index + k).second;
         if (!fresh) { fdio::fail(FDIO_ERR_ARG, "column '%s': repeated vocabulary term at position %d", in.name, k); return nullptr; }
       }
