@@ -668,3 +668,109 @@ def test_sharded_datasets_partition_the_documents(crello_dir):
     assert len(rep[0]) == len(rep[1]) == 80 and not set(rep[0][:18]) & set(rep[1][:18])
     with pytest.raises(ValueError):
         spec.make_dataset("train", shard=(3, 3))
+
+
+# ------------------------------------------------------------------------------------------------------------------------ property test
+def _random_spec_and_records(rng):
+    """A random column spec in the YAML grammar of the reference (dtype / shape / is_sequence / lookup / discretize / max) with a
+    vocabulary, and random documents for it -- including empty documents, out-of-vocabulary tokens where the lookup has an OOV index,
+    mask tokens, values on and beyond the discretiser's boundaries, negative integers, and unpacked repeated fields."""
+    columns, vocabulary = {}, {}
+    n_cols = int(rng.integers(1, 7))
+    for ci in range(n_cols):
+        name = "c%d" % ci
+        dtype = ["int64", "float32", "string"][int(rng.integers(3))]
+        col = {"dtype": dtype}
+        if rng.random() < 0.7:
+            col["is_sequence"] = True
+        width = int(rng.integers(1, 5)) if rng.random() < 0.4 else 1
+        if width > 1:
+            col["shape"] = [width]
+        kind = rng.random()
+        if dtype == "string" or (dtype == "int64" and kind < 0.4):
+            size = int(rng.integers(1, 9))
+            mask = rng.random() < 0.5
+            oov = int(rng.random() < 0.6)
+            if dtype == "string":
+                tokens = ["tok%d" % k for k in range(size)]
+                col["lookup"] = {"num_oov_indices": oov, "mask_token": "" if mask else None}
+                if not mask and not oov:
+                    col["lookup"]["mask_token"] = ""  # padding "" must stay representable
+            else:
+                tokens = [int(x) for x in rng.choice(np.arange(-20, 40), size=size, replace=False)]
+                tokens = [t for t in tokens if t != 0] or [7]
+                col["lookup"] = {"num_oov_indices": oov, "mask_token": 0 if (mask or not oov) else None}
+            if rng.random() < 0.5:
+                col["min_freq"] = 5
+                vocabulary[name] = {str(t): int(rng.integers(1, 10)) for t in tokens}
+                if all(f < 5 for f in vocabulary[name].values()):
+                    vocabulary[name][str(tokens[0])] = 9
+            else:
+                vocabulary[name] = tokens
+        elif dtype != "string" and kind < 0.75:
+            lo = float(rng.integers(-3, 1))
+            col["discretize"] = {"min": lo, "max": lo + float(rng.integers(1, 300)), "bins": int(rng.integers(2, 70))}
+        elif dtype == "int64":
+            col["max"] = 9
+        columns[name] = col
+    pre = DO.make_preprocessors(columns, vocabulary)
+    records = []
+    for _ in range(int(rng.integers(1, 6))):
+        steps = int(rng.integers(0, 6))
+        context, lists = {}, {}
+        for name, col in columns.items():
+            width = int(np.prod(col.get("shape", (1,))))
+
+            def draw():
+                lk = pre.get(name) if "lookup" in col else None
+                if lk is not None:
+                    first = (0 if lk.mask is None else 1) + lk.num_oov
+                    pool = list(lk.tokens[first:]) + ([lk.mask] if lk.mask is not None else []) + (["zz unseen" if lk.is_string else 12345] if lk.num_oov else [])
+                    return [pool[int(rng.integers(len(pool)))] for _ in range(width)]
+                if col["dtype"] == "string":
+                    return ["s%d" % rng.integers(100) for _ in range(width)]
+                if col["dtype"] == "float32":
+                    d = col.get("discretize")
+                    if d and rng.random() < 0.4:  # exactly on a boundary, or outside the range
+                        edges = list(np.linspace(d["min"], d["max"], d["bins"])) + [d["min"] - 1.0, d["max"] + 1.0]
+                        return [float(edges[int(rng.integers(len(edges)))]) for _ in range(width)]
+                    return [float(np.float32(rng.normal() * 50)) for _ in range(width)]
+                return [int(rng.integers(-5, 300)) for _ in range(width)]
+
+            def feature(values):
+                if col["dtype"] == "string" or rng.random() < 0.7:
+                    return encode_feature(values, col["dtype"])
+                if col["dtype"] == "float32":  # unpacked: one fixed32 field per value
+                    return _ld(2, b"".join(b"\x0d" + struct.pack("<f", v) for v in values))
+                return _ld(3, b"".join(b"\x08" + _varint(v & ((1 << 64) - 1)) for v in values))
+
+            if col.get("is_sequence"):
+                lists[name] = [feature(draw()) for _ in range(steps)]
+            else:
+                context[name] = feature(draw())
+        records.append(encode_sequence_example(context, lists))
+    return columns, vocabulary, records
+
+
+def test_random_specs_and_documents_match_the_oracle(tmp_path):
+    """Property test over random schemas and documents: the native parser and the pure-Python restatement agree bit for bit."""
+    rng = np.random.default_rng(2024)
+    checked = 0
+    for trial in range(60):
+        columns, vocabulary, records = _random_spec_and_records(rng)
+        d = tmp_path / ("t%d" % trial)
+        d.mkdir()
+        spec = _tiny_spec(d, columns, vocabulary)
+        want = DO.parse_fn(columns, vocabulary, records)
+        got = spec.parse_fn(records)
+        _assert_batches_equal(got, want)
+        # the input columns the model is sized from follow the same vocabulary arithmetic
+        cols = spec.make_input_columns()
+        pre = DO.make_preprocessors(columns, vocabulary)
+        for name, col in columns.items():
+            if "lookup" in col:
+                assert cols[name]["input_dim"] == len(pre[name].tokens), name
+            elif "discretize" in col:
+                assert cols[name]["input_dim"] == col["discretize"]["bins"], name
+        checked += sum(v.size for v in want.values())
+    assert checked > 500
