@@ -341,7 +341,10 @@ def main():
     # host threads -> pinned batches -> DevicePrefetcher), i.e. train.py's own data path; reported beside e2e, not instead of it.
     input_pipeline = None
     if world == 1 and not args.no_tfrecord:
-        input_pipeline = tfrecord_leg(model, timed, min(args.steps, 40))
+        try:
+            input_pipeline = tfrecord_leg(model, timed, min(args.steps, 40))
+        except Exception as e:  # an auxiliary leg must never cost the headline line (e.g. no writable temp directory on the box)
+            input_pipeline = {"error": "%s: %s" % (type(e).__name__, e)}
 
     # ---- roofline of the dominant kernel (the TF32 tcgen05 GEMM): separate instrumented pass, CUDA events per launch
     train_flops, gemm_flops = flops_per_element(cols, SEQ_LEN, NUM_BLOCKS, LATENT)
