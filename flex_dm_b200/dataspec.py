@@ -410,8 +410,7 @@ class DataSpec:
         ``(B, S, *shape)`` with ``S`` = the longest document of the batch (``parse_sequence_example`` semantics) or ``pad_to``."""
         B = len(pointers)
         schema, out_kind = self._schema(bool(strings))
-        ptrs = (ctypes.c_void_p * max(B, 1))(*[int(p) for p in pointers])
-        lens = (ctypes.c_uint64 * max(B, 1))(*[int(n) for n in lengths])
+        ptrs, lens, _keep = self._record_arrays(pointers, lengths)
         if pad_to is None:  # parse_sequence_example pads to the longest document of the batch: one cheap pass over the record structure
             steps = (ctypes.c_int32 * max(B, 1))()
             io_lib.check(self._lib.fdio_batch_steps(schema, ptrs, lens, B, steps, self._threads))
@@ -446,12 +445,20 @@ class DataSpec:
             output[name] = arr
         return output
 
+    @staticmethod
+    def _record_arrays(pointers: np.ndarray, lengths: np.ndarray):
+        """The native call's (record pointers, record lengths) arguments straight from the numpy index arrays (no per-record Python)."""
+        p = np.ascontiguousarray(pointers, dtype=np.uint64)
+        n = np.ascontiguousarray(lengths, dtype=np.uint64)
+        if p.size == 0:
+            p, n = np.zeros(1, np.uint64), np.zeros(1, np.uint64)
+        return p.ctypes.data_as(ctypes.POINTER(ctypes.c_void_p)), n.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), (p, n)
+
     def record_steps(self, pointers: np.ndarray, lengths: np.ndarray) -> np.ndarray:
         """Number of elements (sequence steps) of each record."""
         B = len(pointers)
         schema, _ = self._schema(False)
-        ptrs = (ctypes.c_void_p * max(B, 1))(*[int(p) for p in pointers])
-        lens = (ctypes.c_uint64 * max(B, 1))(*[int(n) for n in lengths])
+        ptrs, lens, _keep = self._record_arrays(pointers, lengths)
         steps = (ctypes.c_int32 * max(B, 1))()
         io_lib.check(self._lib.fdio_batch_steps(schema, ptrs, lens, B, steps, self._threads))
         return np.asarray(steps[:B], dtype=np.int64)
