@@ -774,3 +774,40 @@ def test_random_specs_and_documents_match_the_oracle(tmp_path):
                 assert cols[name]["input_dim"] == col["discretize"]["bins"], name
         checked += sum(v.size for v in want.values())
     assert checked > 500
+
+
+def test_reference_style_checkpoint_with_optimizer_slots_restores_the_model_variables(tmp_path):
+    """A bundle shaped like the reference's ``best.ckpt`` (Keras ``save_weights`` of the compiled model: every model variable of SURVEY.md
+    Appendix B, Adam's ``iter`` / hyper-parameters / ``m`` and ``v`` slots, metric variables, no object graph) written by the independent
+    oracle writer: ``load_variables`` picks exactly the model variables, for every architecture switch that adds variables."""
+    from oracle import mfp_oracle as O
+
+    rng = np.random.default_rng(8)
+    for kwargs in ({}, {"input_dtype": "shuffled_set"}, {"context": "id"}, {"context": "length"}):
+        specs = O.variable_specs(make_input_columns("rico"), 2, 8, kwargs.get("input_dtype", "set"), kwargs.get("context"))  # small D: names matter here
+        weights = {name: rng.standard_normal(shape).astype(np.float32) for name, (shape, _, _) in specs.items()}
+        tensors = {name + checkpoint.VARIABLE_SUFFIX: w for name, w in weights.items()}
+        for name, w in weights.items():  # Adam slots sit next to their variables
+            for slot in ("m", "v"):
+                tensors["%s/.OPTIMIZER_SLOT/optimizer/%s%s" % (name, slot, checkpoint.VARIABLE_SUFFIX)] = np.zeros_like(w)
+        tensors["optimizer/iter" + checkpoint.VARIABLE_SUFFIX] = np.asarray(1234, dtype=np.int64)
+        for hp in ("beta_1", "beta_2", "decay", "learning_rate"):
+            tensors["optimizer/%s%s" % (hp, checkpoint.VARIABLE_SUFFIX)] = np.asarray(0.5, dtype=np.float32)
+        tensors["keras_api/metrics/0/total" + checkpoint.VARIABLE_SUFFIX] = np.asarray(1.0, dtype=np.float32)
+        prefix = str(tmp_path / ("best_%s.ckpt" % "_".join(map(str, kwargs.values()))))
+        bundle_oracle.write_bundle(prefix, tensors, entries_per_block=7, restart_interval=4)
+        got = checkpoint.load_variables(prefix, {k: v.shape for k, v in weights.items()})
+        assert list(got) == list(weights)
+        for k in weights:
+            assert np.array_equal(got[k], weights[k]), k
+    # keys spelled with an extra wrapper edge are still found when the match is unique and the shape agrees ...
+    tensors = {"root/model/decoder/decoders/left/kernel" + checkpoint.VARIABLE_SUFFIX: np.ones((8, 64), np.float32)}
+    prefix = str(tmp_path / "wrapped.ckpt")
+    bundle_oracle.write_bundle(prefix, tensors)
+    got = checkpoint.load_variables(prefix, {"model/decoder/decoders/left/kernel": (8, 64)})
+    assert got["model/decoder/decoders/left/kernel"].shape == (8, 64)
+    # ... and refused when it is ambiguous
+    tensors["other/model/decoder/decoders/left/kernel" + checkpoint.VARIABLE_SUFFIX] = np.zeros((8, 64), np.float32)
+    bundle_oracle.write_bundle(prefix, tensors)
+    with pytest.raises(KeyError):
+        checkpoint.load_variables(prefix, {"model/decoder/decoders/left/kernel": (8, 64)})
