@@ -176,6 +176,72 @@ __global__ void __launch_bounds__(kD / 4) context_token_bwd_kernel(const float* 
   reinterpret_cast<float4*>(dtable + (size_t)r * kD)[q] = acc;
 }
 
+// vec[b, :] = sum_c params[off_c + clamp(ids_c[b]) * D ...] in column order (encoder.py:156-160,194-199).  grid = B, block = D/4.
+__global__ void __launch_bounds__(kD / 4) canvas_vector_kernel(const __grid_constant__ CanvasArgs a, const float* __restrict__ params, float* __restrict__ vec) {
+  pdl_wait();
+  const int b = blockIdx.x, q = threadIdx.x;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = 0; c < a.n; ++c) {
+    const int id = min(max(__ldg(a.ids[c] + b), 0), a.rows[c] - 1);
+    const float4 r = __ldg(reinterpret_cast<const float4*>(params + a.off[c] + (long long)id * kD) + q);
+    acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
+  }
+  reinterpret_cast<float4*>(vec + (size_t)b * kD)[q] = acc;
+}
+
+// x[b, s, :] += vec[b, :] for every row (seq += canvas, encoder.py:228-230).  grid = B * S, block = D/4.
+__global__ void __launch_bounds__(kD / 4) add_doc_vector_kernel(float* __restrict__ x, const float* __restrict__ vec, int S) {
+  pdl_wait();
+  const int t = blockIdx.x, q = threadIdx.x;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(vec + (size_t)(t / S) * kD) + q);
+  float4* row = reinterpret_cast<float4*>(x + (size_t)t * kD) + q;
+  float4 r = *row;
+  r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
+  *row = r;
+}
+
+// dvec[b, :] = sum_s dx[b, s, :] (fixed order).  grid = B, block = D/4.
+__global__ void __launch_bounds__(kD / 4) sum_doc_rows_kernel(const float* __restrict__ dx, int S, float* __restrict__ dvec) {
+  pdl_wait();
+  const int b = blockIdx.x, q = threadIdx.x;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < S; ++s) {
+    const float4 g = reinterpret_cast<const float4*>(dx + ((size_t)b * S + s) * kD)[q];
+    acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+  }
+  reinterpret_cast<float4*>(dvec + (size_t)b * kD)[q] = acc;
+}
+
+__global__ void iota_kernel(int* __restrict__ iota, int* __restrict__ zeros, int n) {
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { iota[i] = i; zeros[i] = 0; }
+}
+
+int launch_canvas_vector(const CanvasArgs& a, const float* params, int B, float* vec, cudaStream_t st) {
+  MFP_CUDA_OK(launch_pdl(canvas_vector_kernel, B, kD / 4, 0, st, a, params, vec));
+  MFP_CUDA_OK(cudaGetLastError());
+  return MFP_OK;
+}
+
+int launch_add_doc_vector(float* x, const float* vec, int B, int S, cudaStream_t st) {
+  MFP_CUDA_OK(launch_pdl(add_doc_vector_kernel, B * S, kD / 4, 0, st, x, vec, S));
+  MFP_CUDA_OK(cudaGetLastError());
+  return MFP_OK;
+}
+
+int launch_sum_doc_rows(const float* dx, int B, int S, float* dvec, cudaStream_t st) {
+  MFP_CUDA_OK(launch_pdl(sum_doc_rows_kernel, B, kD / 4, 0, st, dx, S, dvec));
+  MFP_CUDA_OK(cudaGetLastError());
+  return MFP_OK;
+}
+
+int launch_iota(int* iota, int* zeros, int n, cudaStream_t st) {
+  MFP_CUDA_OK(launch_pdl(iota_kernel, (n + 255) / 256, 256, 0, st, iota, zeros, n));
+  MFP_CUDA_OK(cudaGetLastError());
+  return MFP_OK;
+}
+
 int launch_context_token(const float* table, int rows, const int* ids, const int* length, int B, int S, float* h0, int* ctx_row, cudaStream_t st) {
   MFP_CUDA_OK(launch_pdl(context_token_kernel, B, kD / 4, 0, st, table, rows, ids, length, S, h0, ctx_row));
   MFP_CUDA_OK(cudaGetLastError());

@@ -29,7 +29,7 @@ struct BlockLayout {
 struct Workspace {
   // byte offsets into the caller's workspace
   size_t vars, flags, perm, x, ln1, qkv, attn, xmid, ln2, hid, stats, lse, logits, dlogits, dx, dtmp, dy, dqkv, dhid, dattn, dh0m, onehot, rowgrad, part, idx_true, idx_pred,
-      norms, ctx_row, total;
+      norms, ctx_row, canvas_vec, dcanvas, iota, zeros, total;
 };
 
 }  // namespace mfp
@@ -46,6 +46,8 @@ struct mfp_engine {
   long long pos_off = -1;  // PositionEmbedding table (input_dtype != "set"), rows = length_input_dim + 1
   long long ctx_off = -1;  // --context id / length: embedding table of the context token, rows = cfg.context_rows
   const int32_t* ctx_ids = nullptr;  // --context id: device task ids of the current batch (mfp_set_context_ids)
+  long long canvas_off[MFP_MAX_CANVAS] = {0};  // --context canvas / canvas_add: embedding tables of the canvas columns
+  const int32_t* canvas_ids[MFP_MAX_CANVAS] = {nullptr};  // device columns of the current batch (mfp_set_canvas_columns)
   // bound state
   int B = 0, S = 0, T = 0;
   uint8_t* ws = nullptr;
@@ -118,9 +120,17 @@ static void build_layout(mfp_engine* h) {
     h->pos_off = alloc((long long)(h->cfg.length_input_dim + 1) * D);
     add_var(h, "model/encoder/input_layer/const/embeddings/embeddings", h->pos_off, h->cfg.length_input_dim + 1, D, D, 1);
   }
-  if (h->cfg.context != 0) {  // encoder.py:96-110: input_layer["task"] / input_layer["length"]
+  if (h->cfg.context == 1 || h->cfg.context == 2) {  // encoder.py:96-110: input_layer["task"] / input_layer["length"]
     h->ctx_off = alloc((long long)h->cfg.context_rows * D);
     add_var(h, std::string("model/encoder/input_layer/") + (h->cfg.context == 1 ? "task" : "length") + "/embeddings", h->ctx_off, h->cfg.context_rows, D, D, 1);
+  }
+  if (h->cfg.context >= 3) {  // canvas columns are embedded like categorical sequence columns (encoder.py:72-79 over valid_input_columns with use_canvas)
+    for (int c = 0; c < h->cfg.n_canvas; ++c) {
+      const int rows = h->cfg.canvas_input_dim[c] + 2;
+      h->canvas_off[c] = alloc((long long)rows * D);
+      const std::string name(h->cfg.canvas_names[c], strnlen(h->cfg.canvas_names[c], sizeof(h->cfg.canvas_names[c])));
+      add_var(h, "model/encoder/input_layer/" + name + "/embeddings", h->canvas_off[c], rows, D, D, 1);
+    }
   }
   // backward stages: 0 = heads, 1..L = blocks L-1..0, L+1 = encoder; the layout is encoder | blocks | heads, each contiguous
   h->stage_lo.assign(L + 2, 0);
@@ -167,6 +177,15 @@ static void build_layout(mfp_engine* h) {
     add_var(h, base + "/kernel", h->wh + fd.logit_off, D, fd.logit_w, sc.LW, 1);
     add_var(h, base + "/bias", h->bh + fd.logit_off, 1, fd.logit_w, sc.LW, 1);
   }
+  if (h->cfg.context == 3) {  // decoder.py:25-43: with use_canvas the decoder owns a head per canvas column; nothing reads them on this path
+    for (int c = 0; c < h->cfg.n_canvas; ++c) {  // (LossLayer skips non-sequence columns, metrics.py:226): variables with an L2 term only
+      const int w = h->cfg.canvas_input_dim[c];
+      const long long wk = alloc((long long)D * w), wb = alloc(w);
+      const std::string name(h->cfg.canvas_names[c], strnlen(h->cfg.canvas_names[c], sizeof(h->cfg.canvas_names[c])));
+      add_var(h, "model/decoder/decoders/" + name + "/kernel", wk, D, w, w, 1);
+      add_var(h, "model/decoder/decoders/" + name + "/bias", wb, 1, w, w, 1);
+    }
+  }
   h->param_count = cur;
   h->stage_hi[0] = cur;
 }
@@ -209,6 +228,10 @@ static Workspace plan_workspace(const mfp_engine* h, int B, int S) {
   w.idx_pred = take(T * sizeof(int));
   w.norms = take(2 * 16 * h->vars.size() * fl);
   w.ctx_row = take((size_t)B * sizeof(int));
+  w.canvas_vec = take((size_t)B * D * fl);
+  w.dcanvas = take((size_t)B * D * fl);
+  w.iota = take((size_t)B * sizeof(int));
+  w.zeros = take((size_t)B * sizeof(int));
   w.total = cur;
   return w;
 }
@@ -221,6 +244,17 @@ static BatchPtrs to_batch(const mfp_engine* h, const mfp_batch* b) {
   p.length = b->length;
   for (int f = 0; f < h->sc.F; ++f) p.cols[f] = b->cols[f];
   return p;
+}
+
+static int canvas_args(const mfp_engine* h, CanvasArgs* ca) {
+  ca->n = h->cfg.n_canvas;
+  for (int c = 0; c < ca->n; ++c) {
+    if (!h->canvas_ids[c]) { set_error("context = canvas / canvas_add needs mfp_set_canvas_columns first"); return MFP_ERR_STATE; }
+    ca->ids[c] = h->canvas_ids[c];
+    ca->off[c] = h->canvas_off[c];
+    ca->rows[c] = h->cfg.canvas_input_dim[c] + 2;
+  }
+  return MFP_OK;
 }
 
 static int first_numerical(const Schema& sc) {
@@ -298,8 +332,13 @@ int mfp_create(const mfp_config* cfg, const mfp_field_desc* fields, mfp_engine**
   if (cfg->num_blocks < 1 || cfg->num_blocks > 64) { set_error("mfp_create: num_blocks out of range"); return MFP_ERR_ARG; }
   if (cfg->input_dtype < 0 || cfg->input_dtype > 2) { set_error("mfp_create: input_dtype must be 0 (set), 1 (shuffled_set) or 2 (sorted_set)"); return MFP_ERR_ARG; }
   if (cfg->input_dtype != 0 && cfg->length_input_dim < 1) { set_error("mfp_create: shuffled_set / sorted_set need length_input_dim"); return MFP_ERR_ARG; }
-  if (cfg->context < 0 || cfg->context > 2) { set_error("mfp_create: context must be 0 (None), 1 (id) or 2 (length)"); return MFP_ERR_ARG; }
-  if (cfg->context != 0 && cfg->context_rows < 1) { set_error("mfp_create: context needs context_rows >= 1"); return MFP_ERR_ARG; }
+  if (cfg->context < 0 || cfg->context > 4) { set_error("mfp_create: context must be 0 (None), 1 (id), 2 (length), 3 (canvas) or 4 (canvas_add)"); return MFP_ERR_ARG; }
+  if ((cfg->context == 1 || cfg->context == 2) && cfg->context_rows < 1) { set_error("mfp_create: context needs context_rows >= 1"); return MFP_ERR_ARG; }
+  if (cfg->context >= 3) {
+    if (cfg->n_canvas < 1 || cfg->n_canvas > MFP_MAX_CANVAS) { set_error("mfp_create: canvas contexts need 1..%d canvas columns (encoder.py:205-206)", MFP_MAX_CANVAS); return MFP_ERR_ARG; }
+    for (int c = 0; c < cfg->n_canvas; ++c)
+      if (cfg->canvas_input_dim[c] < 1) { set_error("mfp_create: canvas column %d has no input_dim", c); return MFP_ERR_ARG; }
+  }
   if (cfg->context != 0 && cfg->input_dtype != 0) { set_error("mfp_create: context with shuffled_set / sorted_set is not supported"); return MFP_ERR_UNSUPPORTED; }
   if (cfg->block_type != 0 && cfg->block_type != 1) { set_error("mfp_create: block_type must be 0 (deepsvg) or 1 (transformer)"); return MFP_ERR_ARG; }
   mfp_engine* h = new mfp_engine();
@@ -392,7 +431,7 @@ int mfp_bind(mfp_engine* h, int32_t B, int32_t S, void* workspace, int64_t works
     set_error("mfp_bind: S = %d exceeds the PositionEmbedding table (%d rows)", S, h->cfg.length_input_dim + 1);
     return MFP_ERR_ARG;
   }
-  if (h->cfg.context != 0 && S < 2) { set_error("mfp_bind: a context token needs S >= 2 (one row beyond the longest document)"); return MFP_ERR_ARG; }
+  if (h->cfg.context >= 1 && h->cfg.context <= 3 && S < 2) { set_error("mfp_bind: a context token needs S >= 2 (one row beyond the longest document)"); return MFP_ERR_ARG; }
   const Workspace w = plan_workspace(h, B, S);
   if ((size_t)workspace_bytes < w.total) { set_error("mfp_bind: workspace too small (%lld < %zu)", (long long)workspace_bytes, w.total); return MFP_ERR_ARG; }
   if (reinterpret_cast<uintptr_t>(workspace) & 255) { set_error("mfp_bind: workspace must be 256-byte aligned"); return MFP_ERR_ARG; }
@@ -460,6 +499,16 @@ int mfp_set_context_ids(mfp_engine* h, const int32_t* task_ids) {
   return MFP_OK;
 }
 
+int mfp_set_canvas_columns(mfp_engine* h, const int32_t* const* columns) {
+  if (!h || !columns) { set_error("mfp_set_canvas_columns: null argument"); return MFP_ERR_ARG; }
+  if (h->cfg.context < 3) { set_error("mfp_set_canvas_columns: the engine was not created with context = canvas / canvas_add"); return MFP_ERR_STATE; }
+  for (int c = 0; c < h->cfg.n_canvas; ++c) {
+    if (!columns[c]) { set_error("mfp_set_canvas_columns: column %d is null", c); return MFP_ERR_ARG; }
+    h->canvas_ids[c] = columns[c];
+  }
+  return MFP_OK;
+}
+
 int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint32_t seed, uint32_t step, float* logits_out, void* stream) {
   MFP_TRY(check_bound(h));
   cudaStream_t st = (cudaStream_t)stream;
@@ -492,13 +541,29 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
   }
   // ---- context token (encoder.py:231-249): one more row per document, attended to by every element
   const int* attn_len = modified->length;
-  if (h->cfg.context != 0) {
+  if (h->cfg.context == 1 || h->cfg.context == 2) {
     const int* ids = h->cfg.context == 1 ? h->ctx_ids : modified->length;
     if (!ids) { set_error("mfp_forward: context = id needs mfp_set_context_ids first"); return MFP_ERR_STATE; }
     int* ctx_row = wsp<int>(h, h->off.ctx_row);
     MFP_TRY(launch_context_token(P + h->ctx_off, h->cfg.context_rows, ids, modified->length, h->B, h->S, x, ctx_row, st));
     h->launches++;
     attn_len = ctx_row;
+  } else if (h->cfg.context >= 3) {  // canvas (the token is the sum of the canvas columns' embeddings) / canvas_add (added to every element)
+    CanvasArgs ca{};
+    MFP_TRY(canvas_args(h, &ca));
+    float* vec = wsp<float>(h, h->off.canvas_vec);
+    MFP_TRY(launch_canvas_vector(ca, P, h->B, vec, st));
+    h->launches++;
+    if (h->cfg.context == 3) {
+      int* ctx_row = wsp<int>(h, h->off.ctx_row);
+      MFP_TRY(launch_iota(wsp<int>(h, h->off.iota), wsp<int>(h, h->off.zeros), h->B, st));
+      MFP_TRY(launch_context_token(vec, h->B, wsp<int>(h, h->off.iota), modified->length, h->B, h->S, x, ctx_row, st));  // "table" row b = document b's vector
+      h->launches += 2;
+      attn_len = ctx_row;
+    } else {
+      MFP_TRY(launch_add_doc_vector(x, vec, h->B, h->S, st));
+      h->launches++;
+    }
   }
   // ---- blocks (transformer.py:208-229)
   for (int i = 0; i < L; ++i) {
@@ -626,7 +691,7 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
   const bool drop = training && h->cfg.dropout > 0.f;
   float* x = wsp<float>(h, h->off.x);
   // --context: the forward pass left every document's context-token row in the workspace; it is also the attention length array
-  const int* ctx_row = h->cfg.context != 0 ? wsp<int>(h, h->off.ctx_row) : nullptr;
+  const int* ctx_row = (h->cfg.context >= 1 && h->cfg.context <= 3) ? wsp<int>(h, h->off.ctx_row) : nullptr;
   const int* attn_len = ctx_row ? ctx_row : modified->length;
   float* dlogits = wsp<float>(h, h->off.dlogits);
   float* dx = wsp<float>(h, h->off.dx);
@@ -748,11 +813,28 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
   }
   MFP_TRY(launch_embed_scatter(sc, rowgrad, G, st));
   h->launches += 2;
-  if (ctx_row) {  // d(context table): the token rows of dh0, summed per id (the one-hot rows of those positions are zero)
+  if (h->cfg.context == 1 || h->cfg.context == 2) {  // d(context table): the token rows of dh0, summed per id (the one-hot rows of those positions are zero)
     const int* ids = h->cfg.context == 1 ? h->ctx_ids : modified->length;
     if (!ids) { set_error("mfp_backward: context = id needs mfp_set_context_ids first"); return MFP_ERR_STATE; }
     MFP_TRY(launch_context_token_bwd(dx, ids, ctx_row, h->cfg.context_rows, h->B, h->S, G + h->ctx_off, st));
     h->launches++;
+  } else if (h->cfg.context >= 3) {
+    // d(canvas vector)[b] = the token's row of dh0 (canvas) or the sum of the document's rows (canvas_add); then every canvas table gets
+    // the vectors of the documents that picked each of its rows
+    CanvasArgs ca{};
+    MFP_TRY(canvas_args(h, &ca));
+    float* dvec = wsp<float>(h, h->off.dcanvas);
+    const int* iota = wsp<int>(h, h->off.iota);
+    const int* zeros = wsp<int>(h, h->off.zeros);
+    if (h->cfg.context == 3) {
+      MFP_TRY(launch_context_token_bwd(dx, iota, ctx_row, h->B, h->B, h->S, dvec, st));
+    } else {
+      MFP_TRY(launch_iota(wsp<int>(h, h->off.iota), wsp<int>(h, h->off.zeros), h->B, st));
+      MFP_TRY(launch_sum_doc_rows(dx, h->B, h->S, dvec, st));
+      h->launches++;
+    }
+    for (int c = 0; c < ca.n; ++c) MFP_TRY(launch_context_token_bwd(dvec, ca.ids[c], zeros, ca.rows[c], h->B, 1, G + ca.off[c], st));
+    h->launches += 1 + ca.n;
   }
   if (h->pos_off >= 0) {  // rows >= S of the table get no gradient (G was cleared in stage 0)
     MFP_TRY(launch_pos_embed_bwd(dx, h->B, h->S, drop ? h->cfg.dropout : 0.f, seed, step, G + h->pos_off, st));

@@ -40,6 +40,17 @@ int launch_embed_onehot(const Schema& sc, const BatchPtrs& mod, const unsigned c
 // (self-attention without positions is order-free, so "after the last element" equals the reference's "prepended"); ctx_row doubles as
 // the attention kernels' length array (zero-based: covers the elements and the token).
 int launch_context_token(const float* table, int rows, const int* ids, const int* length, int B, int S, float* h0, int* ctx_row, cudaStream_t st);
+// --context canvas / canvas_add (encoder.py:177-199,228-230): vec[b, :] = sum over the canvas columns c of table_c[ids_c[b]]
+struct CanvasArgs {
+  int n;
+  const int* ids[8];    // device [B]
+  long long off[8];     // table offsets in the flat parameter buffer
+  int rows[8];          // input_dim + 2
+};
+int launch_canvas_vector(const CanvasArgs& a, const float* params, int B, float* vec /*[B][D]*/, cudaStream_t st);
+int launch_add_doc_vector(float* x /*[B*S][D], += vec[b]*/, const float* vec, int B, int S, cudaStream_t st);
+int launch_sum_doc_rows(const float* dx /*[B*S][D]*/, int B, int S, float* dvec /*[B][D], overwritten*/, cudaStream_t st);
+int launch_iota(int* iota /*[n] = 0..n-1*/, int* zeros /*[n] = 0*/, int n, cudaStream_t st);
 int launch_context_token_bwd(const float* dh0, const int* ids, const int* ctx_row, int rows, int B, int S, float* dtable /*[rows][D], overwritten*/,
                              cudaStream_t st);
 int launch_embed_scatter(const Schema& sc, const float* scratch /*[R][D]*/, float* grads, cudaStream_t st);

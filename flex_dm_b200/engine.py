@@ -22,6 +22,9 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libflexdm_
 _lib = None
 
 
+MAX_CANVAS = 8
+
+
 class FieldDesc(ctypes.Structure):
     _fields_ = [("name", ctypes.c_char * 48), ("kind", ctypes.c_int32), ("C", ctypes.c_int32), ("input_dim", ctypes.c_int32),
                 ("task_id", ctypes.c_int32), ("has_cond", ctypes.c_int32), ("reserved", ctypes.c_int32), ("cond_mask", ctypes.c_uint64)]
@@ -31,7 +34,8 @@ class Config(ctypes.Structure):
     _fields_ = [("num_fields", ctypes.c_int32), ("type_field", ctypes.c_int32), ("latent_dim", ctypes.c_int32), ("num_blocks", ctypes.c_int32),
                 ("sort_pos", ctypes.c_int32), ("pos_task_id", ctypes.c_int32), ("total_columns", ctypes.c_int32),
                 ("sort_fields", ctypes.c_int32 * 5), ("dropout", ctypes.c_float), ("l2", ctypes.c_float), ("input_dtype", ctypes.c_int32),
-                ("length_input_dim", ctypes.c_int32), ("block_type", ctypes.c_int32), ("context", ctypes.c_int32), ("context_rows", ctypes.c_int32)]
+                ("length_input_dim", ctypes.c_int32), ("block_type", ctypes.c_int32), ("context", ctypes.c_int32), ("context_rows", ctypes.c_int32),
+                ("n_canvas", ctypes.c_int32), ("canvas_input_dim", ctypes.c_int32 * MAX_CANVAS), ("canvas_names", (ctypes.c_char * 48) * MAX_CANVAS)]
 
 
 class Variable(ctypes.Structure):
@@ -74,6 +78,7 @@ _SIGNATURES = {
     "mfp_mask_for_test": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Batch), ctypes.POINTER(ctypes.c_void_p),
                                          ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
     "mfp_set_context_ids": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "mfp_set_canvas_columns": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     "mfp_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Batch), ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p,
                                    ctypes.c_void_p]),
     "mfp_loss": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Batch), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_void_p,
@@ -196,10 +201,23 @@ class Engine:
         cfg.block_type = {"deepsvg": 0, "transformer": 1}[block_type]  # transformer.py:232-236
         cfg.input_dtype = {"set": 0, "shuffled_set": 1, "sorted_set": 2}[input_dtype]  # mfp.py:104-105, encoder.py:41
         cfg.length_input_dim = int(input_columns["length"]["input_dim"])
-        cfg.context = {None: 0, "id": 1, "length": 2}[context]  # encoder.py:96-110
-        cfg.context_rows = {None: 0, "id": len(self.task_names), "length": int(input_columns["length"]["input_dim"])}[context]
+        cfg.context = {None: 0, "id": 1, "length": 2, "canvas": 3, "canvas_add": 4}[context]  # encoder.py:11,96-110,228-249
+        cfg.context_rows = {"id": len(self.task_names), "length": int(input_columns["length"]["input_dim"])}.get(context, 0)
+        # canvas contexts: the non-sequence columns of get_valid_input_columns(input_columns, use_canvas=True) (encoder.py:34-37)
+        self.canvas_keys = [k for k, c in get_valid_input_columns(input_columns, True).items() if not c["is_sequence"]] if context in ("canvas", "canvas_add") else []
+        if context in ("canvas", "canvas_add"):
+            assert len(self.canvas_keys) > 0, (self.keys, self.canvas_keys)  # encoder.py:205-206
+            if len(self.canvas_keys) > MAX_CANVAS:
+                raise ValueError("too many canvas columns")
+            cfg.n_canvas = len(self.canvas_keys)
+            for i, k in enumerate(self.canvas_keys):
+                if input_columns[k]["type"] != "categorical" or tuple(input_columns[k]["shape"]) != (1,):
+                    raise NotImplementedError("canvas column %s: only categorical columns of shape (1,) are supported" % k)
+                cfg.canvas_input_dim[i] = int(input_columns[k]["input_dim"])
+                cfg.canvas_names[i].value = k.encode()
         self.context = context
-        self._context_ids = None  # keeps the tensor alive while the engine holds its pointer
+        self._context_ids = None  # keeps the tensors alive while the engine holds their pointers
+        self._canvas_cols = None
         self.input_dtype = input_dtype
         self.cfg = cfg
         handle = ctypes.c_void_p()
@@ -330,6 +348,15 @@ class Engine:
             raise ValueError("expected %d task ids, got %d" % (self.B, ids.numel()))
         self._context_ids = ids
         _check(self.lib, self.lib.mfp_set_context_ids(self.handle, _ptr(ids)), "mfp_set_context_ids")
+
+    def set_canvas_columns(self, columns: List[torch.Tensor]):
+        """--context canvas / canvas_add: the batch's canvas columns ``(B, 1)`` int32, in ``canvas_keys`` order."""
+        cols = [c.to(device=self.device, dtype=torch.int32).reshape(-1).contiguous() for c in columns]
+        if len(cols) != len(self.canvas_keys) or any(c.numel() != self.B for c in cols):
+            raise ValueError("expected %d canvas columns of %d documents" % (len(self.canvas_keys), self.B))
+        self._canvas_cols = cols
+        ptrs = (ctypes.c_void_p * MAX_CANVAS)(*[c.data_ptr() for c in cols])
+        _check(self.lib, self.lib.mfp_set_canvas_columns(self.handle, ptrs), "mfp_set_canvas_columns")
 
     def forward(self, length, cols: Optional[List[torch.Tensor]] = None, training: bool = False, seed: int = 0, step: int = 0,
                 logits_out: Optional[torch.Tensor] = None):

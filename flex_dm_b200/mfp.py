@@ -93,8 +93,8 @@ class MFP:
             raise KeyError(block_type)
         if input_dtype not in ("set", "shuffled_set", "sorted_set"):
             raise ValueError("input_dtype=%r (args.py: set | shuffled_set | sorted_set)" % (input_dtype,))
-        if context not in (None, "id", "length"):  # encoder.py:11 CONTEXT_NAMES; the canvas variants embed and predict canvas columns
-            raise NotImplementedError("context=%r is outside the B200 hot path (SURVEY.md section 8f); supported: None, 'id', 'length'" % (context,))
+        if context not in (None, "id", "length", "canvas", "canvas_add"):  # encoder.py:11 CONTEXT_NAMES
+            raise AssertionError("context=%r (encoder.py:28: one of None, 'id', 'canvas', 'length', 'canvas_add')" % (context,))
         if context is not None and input_dtype != "set":
             raise NotImplementedError("context=%r with input_dtype=%r is not supported" % (context, input_dtype))
         for flag, value, supported in (("seq_type", seq_type, "default"),
@@ -198,7 +198,8 @@ class MFP:
 
     def _bind(self, staged: Dict[str, torch.Tensor]):
         cols = [staged[k] for k in self.keys]
-        if self.context is not None and self._pad_context:
+        self._staged = staged
+        if self.context in ("id", "length", "canvas") and self._pad_context:
             # the context token (encoder.py:231-249) takes the row after each document's last element: one more (padding) row so
             # that full-length documents have one too; callers see the caller's S again (``_crop``)
             cols = [torch.nn.functional.pad(c, (0, 0, 0, 1)) for c in cols]
@@ -211,10 +212,15 @@ class MFP:
     def _set_context(self, tasks: torch.Tensor):
         if self.context == "id":  # modified_inputs["task"] (mfp.py:137) -> Encoder input_layer["task"] (encoder.py:234-237)
             self.engine.set_context_ids(tasks)
+        elif self.context in ("canvas", "canvas_add"):  # the canvas columns pass through the masking untouched (masking.py:246-248)
+            missing = [k for k in self.engine.canvas_keys if k not in self._staged]
+            if missing:
+                raise KeyError("missing canvas columns %s" % missing)
+            self.engine.set_canvas_columns([self._staged[k] for k in self.engine.canvas_keys])
 
     def _crop(self, x: torch.Tensor) -> torch.Tensor:
         """Drops the extra row ``_bind`` added for the context token."""
-        return x if (self.context is None or not self._pad_context) else x[:, :-1]
+        return x[:, :-1] if (self.context in ("id", "length", "canvas") and self._pad_context) else x
 
     def _next_row(self) -> torch.Tensor:
         row = self._ring[self._ring_pos % self._ring.shape[0]]
@@ -361,7 +367,7 @@ class MFP:
                 m = demo_args["masks"][key]
                 m = torch.as_tensor(m) if not isinstance(m, torch.Tensor) else m
                 m = m.to(self.device).to(torch.uint8)
-                if self.context is not None and self._pad_context:
+                if self.context in ("id", "length", "canvas") and self._pad_context:
                     m = torch.nn.functional.pad(m, (0, 1))  # the context token's row is never masked
                 masks.append(m.contiguous())
             num_iter = int(demo_args.get("num_iter", 1))
@@ -467,6 +473,8 @@ class MFP:
         if self.context == "id":
             t = modified_inputs["task"]  # added by preprocess_for_train / preprocess_for_test (mfp.py:91,137)
             self._set_context((torch.as_tensor(np.asarray(t)) if not isinstance(t, torch.Tensor) else t).to(self.device))
+        elif self.context is not None:
+            self._set_context(None)
         logits = torch.empty((B * S, eng.logit_width), dtype=torch.float32, device=self.device)
         eng.forward(length, cols, training, self.seed if seed is None else seed, step, logits_out=logits)
         return OrderedDict((k, self._crop(v)) for k, v in self.split_logits(logits, B, S).items())

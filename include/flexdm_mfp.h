@@ -21,6 +21,7 @@ extern "C" {
 #endif
 
 #define MFP_MAX_FIELDS 16
+#define MFP_MAX_CANVAS 8
 #define MFP_NAME_LEN 96
 
 enum { MFP_OK = 0, MFP_ERR_ARG = -1, MFP_ERR_CUDA = -2, MFP_ERR_STATE = -3, MFP_ERR_UNSUPPORTED = -4 };
@@ -63,6 +64,14 @@ typedef struct {
                         * positions is order-free, so this equals the reference's prepended token up to summation order): every document
                         * needs length[b] + 1 < S -- the host mirror pads the batch by one row.  Not combined with input_dtype != 0. */
   int32_t context_rows; /* rows of that embedding table: len(get_task_names(...)) for "id", input_columns["length"]["input_dim"] for "length" */
+  /* context = 3 ("canvas") / 4 ("canvas_add") (encoder.py:34-37,177-199,228-249; decoder.py:25-43): the canvas-level categorical columns
+   * (valid_input_columns with use_canvas: every non-sequence column but "length") are embedded (tables of input_dim + 2 rows) and
+   * summed into one vector per document, which becomes the context token (3; its row as for id / length) or is added to every
+   * element of the document (4).  With 3 the decoder also owns a Dense head per canvas column (decoder.py:32-43); LossLayer skips
+   * non-sequence columns (metrics.py:226), so those heads only see their L2 term. */
+  int32_t n_canvas;
+  int32_t canvas_input_dim[MFP_MAX_CANVAS];
+  char canvas_names[MFP_MAX_CANVAS][48];
 } mfp_config;
 
 /* One trainable variable of the reference model as a strided view of the flat
@@ -127,6 +136,8 @@ int mfp_shuffle_inputs(mfp_engine* h, const mfp_batch* inputs, uint32_t seed, ui
 /* --context id: the per-document ids the context token embeds (device int32 [B]; MFP.call's `tasks`, mfp.py:137,301; eval.py:100-101).
  * The pointer is kept and read by every following mfp_forward / mfp_backward*; "length" contexts read the batch's own length array. */
 int mfp_set_context_ids(mfp_engine* h, const int32_t* task_ids);
+/* --context canvas / canvas_add: the canvas columns of the current batch (n_canvas device int32 [B] arrays, config order); kept like the ids. */
+int mfp_set_canvas_columns(mfp_engine* h, const int32_t* const* columns);
 
 int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint32_t seed, uint32_t step,
                 float* logits_out, void* stream);

@@ -312,12 +312,26 @@ def preprocess_for_test(inputs, input_columns, masks, tasks=None):
 
 
 # ----------------------------------------------------------------------------------------------- parameters
+def canvas_columns(input_columns, context):
+    """The canvas-level columns the encoder embeds when ``"canvas" in context`` (encoder.py:34-37): the non-sequence entries of
+    get_valid_input_columns(input_columns, use_canvas=True), i.e. everything but ``length`` and the demo-only columns."""
+    if context not in ("canvas", "canvas_add"):
+        return OrderedDict()
+    icols = OrderedDict((k, c) for k, c in input_columns.items() if not c.get("demo_only", False))
+    out = OrderedDict((k, c) for k, c in get_valid_input_columns(icols, True).items() if not c["is_sequence"])
+    assert len(out) > 0  # encoder.py:205-206
+    return out
+
+
 def variable_specs(input_columns, num_blocks=4, latent_dim=256, input_dtype="set", context=None) -> "OrderedDict[str, Tuple[tuple, str, bool]]":
     """name -> (shape, init, l2-regularised).  SURVEY.md Appendix B; names follow the reference's attribute
     paths (mfp.py:249, model.py:20,45,52, encoder.py:74-92, transformer.py:54-57,161-173,263, decoder.py:39)."""
     D = latent_dim
     v = OrderedDict()
     cols = get_valid_input_columns(input_columns)
+    canvas_cols = canvas_columns(input_columns, context)
+    for key, c in canvas_cols.items():  # encoder.py:34-37,72-79: with use_canvas the canvas-level columns are embedded like any categorical column
+        v["model/encoder/input_layer/%s/embeddings" % key] = ((c["input_dim"] + 2, D), "uniform", True)
     for key, c in cols.items():
         base = "model/encoder/input_layer/%s" % key
         if c["type"] == "categorical":
@@ -344,6 +358,10 @@ def variable_specs(input_columns, num_blocks=4, latent_dim=256, input_dtype="set
         for n in ("norm1", "norm2"):  # transformer.py:172-173; LN gamma/beta are not regularised
             v["%s/%s/gamma" % (b, n)] = ((D,), "ones", False)
             v["%s/%s/beta" % (b, n)] = ((D,), "zeros", False)
+    if context == "canvas":  # decoder.py:25-43: use_canvas = (context == "canvas") adds a head per canvas column (never in the loss: metrics.py:226)
+        for key, c in canvas_cols.items():
+            v["model/decoder/decoders/%s/kernel" % key] = ((D, c["shape"][-1] * c["input_dim"]), "glorot", True)
+            v["model/decoder/decoders/%s/bias" % key] = ((c["shape"][-1] * c["input_dim"],), "zeros", True)
     for key, c in cols.items():
         units = c["shape"][-1] * c["input_dim"] if c["type"] == "categorical" else c["shape"][-1]  # decoder.py:33-37
         v["model/decoder/decoders/%s/kernel" % key] = ((D, units), "glorot", True)
@@ -408,10 +426,16 @@ def encoder_forward(p, inputs, input_columns, pos_keep=None, pos_rate=0.0, conte
         B = seq.shape[0]
         emb = p[pos_name][:S][None].expand(B, -1, -1)
         seq = seq + dropout(emb, pos_keep, pos_rate)
-    if context is not None:  # encoder.py:231-249: a special token in front of the sequence, one more valid position per document
-        ids = inputs["task"] if context == "id" else inputs["length"]  # :234-242
-        ids = ids[:, 0] if ids.dim() == 2 else ids
-        canvas = p["model/encoder/input_layer/%s/embeddings" % ("task" if context == "id" else "length")][ids.to(torch.int64)]
+    canvas = 0.0
+    for key in canvas_columns(input_columns, context):  # encoder.py:156-160,182-183,198-199: embed, sum over the sub-target axis, add up
+        canvas = canvas + p["model/encoder/input_layer/%s/embeddings" % key][inputs[key].to(torch.int64)].sum(dim=1)
+    if context == "canvas_add":  # encoder.py:228-230
+        seq = seq + canvas[:, None, :]
+    elif context is not None:  # encoder.py:231-249: a special token in front of the sequence, one more valid position per document
+        if context != "canvas":
+            ids = inputs["task"] if context == "id" else inputs["length"]  # :234-242
+            ids = ids[:, 0] if ids.dim() == 2 else ids
+            canvas = p["model/encoder/input_layer/%s/embeddings" % ("task" if context == "id" else "length")][ids.to(torch.int64)]
         seq = torch.cat([canvas[:, None, :], seq], dim=1)  # :247-248
         seq_mask = get_seq_mask(inputs["length"] + 1, S + 1)  # :249
     return seq, seq_mask
@@ -503,12 +527,12 @@ def context_dropout_layout(drop, length):
 
 def model_forward(p, modified_inputs, input_columns, num_blocks, drop=None, rate=0.0, return_hidden=False, block_type="deepsvg", context=None):
     """models/model.py:26-30."""
-    if context is not None:
+    if context in ("id", "length", "canvas"):
         drop = context_dropout_layout(drop, modified_inputs["length"])
     h0, mask = encoder_forward(p, modified_inputs, input_columns, None if drop is None else drop.get("pos"), rate, context)
     h = blocks_forward(p, h0, mask, num_blocks, drop, rate, block_type)
-    if context is not None:  # decoder.py:74-78: the heads read the element positions only
-        h = h[:, 1:]
+    if context in ("id", "length", "canvas"):  # decoder.py:74-78: the heads read the element positions only
+        h = h[:, 1:]  # (with "canvas" the decoder also predicts the canvas columns from the token; nothing on this path reads them)
     out = decoder_forward(p, h, input_columns)
     if return_hidden:
         return out, h0, h

@@ -73,8 +73,13 @@ CASES = OrderedDict([
     # Every document leaves the last row free: the engine keeps the token in the row after a document's last element.
     ("crello_ctx_id", ("crello", "elem_pos_attr_img_txt", 4, 11, 2, 21, 2, [10, 4, 1, 7], [1, 3, 5, 6])),
     ("rico_ctx_length", ("rico", "elem_pos_attr", 4, 9, 2, 23, 1, [8, 3, 1, 5], [3, 1, 4, 3])),
+    # --context canvas (token = sum of the canvas columns' embeddings; the decoder gains never-read canvas heads) and canvas_add (that
+    # sum added to every element; no token, so the batch may be full length): encoder.py:34-37,177-199,228-249, decoder.py:25-43
+    ("crello_ctx_canvas", ("crello", "random", 3, 9, 2, 25, 0, [8, 1, 5], None)),
+    ("crello_ctx_canvas_add", ("crello", "elem_pos_attr_img_txt", 3, 8, 2, 27, 1, [8, 1, 6], [4, 1, 6])),
 ])
-CONTEXT = {"crello_ctx_id": "id", "rico_ctx_length": "length"}
+CONTEXT = {"crello_ctx_id": "id", "rico_ctx_length": "length", "crello_ctx_canvas": "canvas", "crello_ctx_canvas_add": "canvas_add"}
+TOKEN_CONTEXTS = ("id", "length", "canvas")  # contexts that put a token into the sequence
 BLOCK_TYPE = {"crello_postln": "transformer"}
 INPUT_DTYPE = {"rico_shuffled": "shuffled_set", "crello_sorted": "sorted_set"}
 
@@ -143,7 +148,7 @@ def run_case(name, spec):
     block_type = BLOCK_TYPE.get(name, "deepsvg")
     input_dtype = INPUT_DTYPE.get(name, "set")
     context = CONTEXT.get(name)
-    ctx_lengths = lengths if context is not None else None
+    ctx_lengths = lengths if context in TOKEN_CONTEXTS else None
     if input_dtype == "shuffled_set":
         method = method if "random" in method else "random_" + method  # keep task 0 reachable for the scripted task ids
     if input_dtype == "sorted_set":
@@ -183,7 +188,7 @@ def run_case(name, spec):
     model = RefMFP(cols, num_blocks=L, block_type=block_type, masking_method=method, seq_type="default", arch_type="oneshot",
                    context=context, input_dtype=input_dtype, latent_dim=D, dropout=RATE, l2=L2)
     # with a context token the engine's batch keeps one free row per document; the reference wants S = the longest document
-    ref_batch = {k: (v[:, :S - 1] if (context is not None and v.ndim == 3) else v) for k, v in batch.items()}
+    ref_batch = {k: (v[:, :S - 1] if (context in TOKEN_CONTEXTS and v.ndim == 3) else v) for k, v in batch.items()}
     inputs32 = {k: torch.as_tensor(v).as_subclass(tf.Tensor) for k, v in ref_batch.items()}
     captured = {}
     inner_call, loss_call = model.model.call, model.loss_layer.call

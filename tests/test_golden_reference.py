@@ -29,15 +29,19 @@ CASES = {  # name: (dataset, masking_method, num_blocks, seed, step)
     # reference ran on the same batch cut to its longest document, so its arrays have one column less (``cut``)
     "crello_ctx_id": ("crello", "elem_pos_attr_img_txt", 2, 21, 2),
     "rico_ctx_length": ("rico", "elem_pos_attr", 2, 23, 1),
+    # --context canvas (token = sum of the canvas columns' embeddings) / canvas_add (that sum added to every element; no token)
+    "crello_ctx_canvas": ("crello", "random", 2, 25, 0),
+    "crello_ctx_canvas_add": ("crello", "elem_pos_attr_img_txt", 2, 27, 1),
 }
 BLOCK_TYPE = {"crello_postln": "transformer"}
 INPUT_DTYPE = {"rico_shuffled": "shuffled_set", "crello_sorted": "sorted_set"}
-CONTEXT = {"crello_ctx_id": "id", "rico_ctx_length": "length"}
+CONTEXT = {"crello_ctx_id": "id", "rico_ctx_length": "length", "crello_ctx_canvas": "canvas", "crello_ctx_canvas_add": "canvas_add"}
+TOKEN_CASES = {c for c, ctx in CONTEXT.items() if ctx != "canvas_add"}  # cases whose batch keeps a free row for the context token
 
 
 def cut(x, case):
     """Sequence arrays of a context case without the engine batch's free last row (what the reference saw)."""
-    return x[:, :-1] if case in CONTEXT else x
+    return x[:, :-1] if case in TOKEN_CASES else x
 
 
 def projection_vector(name, n):  # same as make_golden.py
@@ -61,7 +65,7 @@ def test_golden_files_cover_every_task_and_edge_case():
     for case in CASES:
         g = np.load(os.path.join(GOLDEN, case + ".npz"))
         seen |= {(CASES[case][0], int(t)) for t in g["tasks"]}
-        assert int(g["in/length"].min()) == 0 and int(g["in/length"].max()) == g["in/left"].shape[1] - (2 if case in CONTEXT else 1)
+        assert int(g["in/length"].min()) == 0 and int(g["in/length"].max()) == g["in/left"].shape[1] - (2 if case in TOKEN_CASES else 1)
     assert {t for d, t in seen if d == "crello"} == {0, 1, 3, 4, 5, 6}
     assert "crello_postln" in CASES  # the post-LayerNorm block of --block_type transformer
     assert {t for d, t in seen if d == "rico"} >= {1, 3, 4}
@@ -87,7 +91,7 @@ def test_oracle_matches_reference_python(case):
         seq = column["is_sequence"]
         assert np.array_equal(cut(mod[key].numpy(), case) if seq else mod[key].numpy(), g["mod/" + key]), key
         assert np.array_equal(cut(masks[key].numpy(), case) if seq else masks[key].numpy(), g["mask/" + key]), key
-        if seq and case in CONTEXT:
+        if seq and case in TOKEN_CASES:
             assert not masks[key][:, -1].any(), key  # the free row is padding
     assert np.array_equal(mod["task"].numpy(), g["mod/task"])
     B, S = batch["left"].shape[:2]
@@ -199,7 +203,7 @@ def test_engine_matches_reference_python(case, impl):
     torch.cuda.synchronize()
     got = m.split_logits(logits, B, S)
     valid = np.ones((B, S), dtype=bool)
-    if case in CONTEXT:
+    if case in TOKEN_CASES:
         # the engine keeps the context token in the first padding row of each document, where the reference computes a (never used)
         # prediction for a padded element: raw logits are comparable on the documents' own elements
         valid = np.arange(S)[None, :] <= batch["length"].reshape(B, 1)

@@ -21,7 +21,8 @@ def _padded(batch):
     return {k: (np.pad(v, ((0, 0), (0, 1), (0, 0))) if v.ndim == 3 else v) for k, v in batch.items()}
 
 
-@pytest.mark.parametrize("dataset,method,context", [("rico", "elem_pos_attr", "id"), ("crello", "random", "length"), ("crello", "elem_pos_attr_img_txt", "id")])
+@pytest.mark.parametrize("dataset,method,context", [("rico", "elem_pos_attr", "id"), ("crello", "random", "length"), ("crello", "elem_pos_attr_img_txt", "id"),
+                                                    ("crello", "random", "canvas"), ("crello", "elem_pos_attr_img_txt", "canvas_add")])
 def test_context_train_steps_track_the_oracle(dataset, method, context):
     from flex_dm_b200.mfp import MFP, Adam
 
@@ -30,8 +31,10 @@ def test_context_train_steps_track_the_oracle(dataset, method, context):
     m.set_weights(H.perturbed_weights(m.engine, seed=2))
     m.seed = 33
     m.compile(optimizer=Adam(learning_rate=1e-3, clipnorm=1.0))
-    table = "model/encoder/input_layer/%s/embeddings" % ("task" if context == "id" else "length")
-    assert table in m.get_weights() and m.get_weights()[table].shape == ((len(m.task_names) if context == "id" else 50), 256)
+    table = "model/encoder/input_layer/%s/embeddings" % {"id": "task", "length": "length"}.get(context, "format")
+    rows = {"id": len(m.task_names), "length": 50}.get(context, cols["format"]["input_dim"] + 2)
+    assert table in m.get_weights() and m.get_weights()[table].shape == (rows, 256)
+    assert ("model/decoder/decoders/format/kernel" in m.get_weights()) == (context == "canvas")  # decoder.py:25 use_canvas
     o = O.OracleMFP(cols, num_blocks=2, masking_method=method, dropout=0.1, l2=1e-2, dtype=torch.float64, learning_rate=1e-3, clipnorm=1.0, context=context)
     o.params = H.oracle_params_from_engine(m.engine)
     batch = make_synthetic_batch(cols, 5, 12, seed=1, lengths="ragged")  # holds a full-length document: exercises the extra row
@@ -39,14 +42,14 @@ def test_context_train_steps_track_the_oracle(dataset, method, context):
     w0 = m.get_weights()
     for step in range(3):
         got = m.metrics_from_row(m.train_step(batch))
-        ref = o.train_step(_padded(batch), seed=33, step=step)
+        ref = o.train_step(batch if context == "canvas_add" else _padded(batch), seed=33, step=step)
         assert got["loss"] == pytest.approx(ref["loss"], rel=H.LOSS_RTOL), step
         assert got["total_score"] == pytest.approx(ref["metrics"]["total_score"], abs=2e-2)
     w = m.get_weights()
     for name in (table, "model/blocks/seq2seq/seq2seq_0/attn/dense_value/kernel"):
         delta_ref = o.params[name].numpy() - w0[name]
         if name == table:  # rows of ids that never occurred only see the L2 term: compare the rows that got data gradients
-            ids = np.unique(batch["length"][:, 0]) if context == "length" else np.arange(delta_ref.shape[0])
+            ids = {"length": np.unique(batch["length"][:, 0]), "id": np.arange(delta_ref.shape[0])}.get(context, np.unique(batch["format"][:, 0]))
             assert H.rel_l2((w[name] - w0[name])[ids], delta_ref[ids]) < 0.15, name
         else:
             assert H.rel_l2(w[name] - w0[name], delta_ref) < 0.1, name
@@ -136,3 +139,43 @@ def test_context_demo_call_and_evaluation():
     for k in ("left", "top", "width", "height"):
         want = float(oscores[k + "_score_num"]) / float(oscores[k + "_score_den"])
         assert scores[k] == pytest.approx(want, abs=0.08), k  # argmax ties under TF32 may flip single elements
+
+
+def test_canvas_context_gradients_and_errors():
+    """canvas / canvas_add: gradients of the canvas columns' tables against autograd (fp32 path), the never-read canvas heads of
+    ``context="canvas"`` get exactly zero data gradient, and rico (no canvas columns) is refused like the reference's assertion."""
+    from flex_dm_b200.mfp import MFP
+
+    cols = make_input_columns("crello")
+    for context in ("canvas", "canvas_add"):
+        m = MFP(cols, num_blocks=1, masking_method="random", context=context, latent_dim=256, dropout=0.0, l2=1e-2, seed=9)
+        m.set_weights(H.perturbed_weights(m.engine, seed=4))
+        eng = m.engine
+        eng.set_gemm_impl(1)
+        batch = make_synthetic_batch(cols, 5, 7, seed=2, lengths="ragged")
+        staged = m.stage(batch)
+        B, S, length, dcols = m._bind(staged)
+        assert S == (8 if context == "canvas" else 7)
+        tasks = torch.zeros(B, dtype=torch.int32, device="cuda")
+        m._set_context(tasks)
+        eng.mask_corrupt(length, dcols, tasks, 7, 0)
+        eng.forward(length, None, True, 7, 0)
+        row = torch.zeros(eng.metrics_width, device="cuda")
+        eng.loss(length, dcols, eng.masks, row, 1.0 / B, True)
+        eng.backward(length, None, True, 7, 0)
+        torch.cuda.synchronize()
+        o = O.OracleMFP(cols, num_blocks=1, masking_method="random", dropout=0.0, l2=None, dtype=torch.float64, context=context)
+        o.params = H.oracle_params_from_engine(eng)
+        inputs = o.to_torch(_padded(batch) if context == "canvas" else batch)
+        targets, mod, masks = O.preprocess_for_train(inputs, o.input_columns, tasks.cpu(), O.PhiloxDraws(7, 0))
+        r = o.step_from(targets, mod, masks, tasks.cpu(), None)
+        assert float(row[3 * len(m.keys)].cpu()) == pytest.approx(r["data_loss"], rel=H.F32_LOSS_RTOL)
+        got = eng.get_weights(eng.grads)
+        names = ["model/encoder/input_layer/%s/embeddings" % k for k in eng.canvas_keys]
+        names += ["model/encoder/input_layer/left/embeddings", "model/encoder/input_layer/image_embedding/kernel", "model/blocks/seq2seq/seq2seq_0/attn/dense_key/kernel"]
+        for name in names:
+            assert H.rel_l2(got[name], r["grads"][name].numpy()) < H.F32_GRAD_REL_L2, (context, name)
+        if context == "canvas":
+            assert np.all(got["model/decoder/decoders/group/kernel"] == 0.0) and np.all(r["grads"]["model/decoder/decoders/group/kernel"].numpy() == 0.0)
+    with pytest.raises(AssertionError):
+        MFP(make_input_columns("rico"), num_blocks=1, context="canvas", latent_dim=256)
