@@ -32,7 +32,7 @@ def test_context_train_steps_track_the_oracle(dataset, method, context):
     m.seed = 33
     m.compile(optimizer=Adam(learning_rate=1e-3, clipnorm=1.0))
     table = "model/encoder/input_layer/%s/embeddings" % {"id": "task", "length": "length"}.get(context, "format")
-    rows = {"id": len(m.task_names), "length": 50}.get(context, cols["format"]["input_dim"] + 2)
+    rows = len(m.task_names) if context == "id" else 50 if context == "length" else cols["format"]["input_dim"] + 2
     assert table in m.get_weights() and m.get_weights()[table].shape == (rows, 256)
     assert ("model/decoder/decoders/format/kernel" in m.get_weights()) == (context == "canvas")  # decoder.py:25 use_canvas
     o = O.OracleMFP(cols, num_blocks=2, masking_method=method, dropout=0.1, l2=1e-2, dtype=torch.float64, learning_rate=1e-3, clipnorm=1.0, context=context)
@@ -49,7 +49,7 @@ def test_context_train_steps_track_the_oracle(dataset, method, context):
     for name in (table, "model/blocks/seq2seq/seq2seq_0/attn/dense_value/kernel"):
         delta_ref = o.params[name].numpy() - w0[name]
         if name == table:  # rows of ids that never occurred only see the L2 term: compare the rows that got data gradients
-            ids = {"length": np.unique(batch["length"][:, 0]), "id": np.arange(delta_ref.shape[0])}.get(context, np.unique(batch["format"][:, 0]))
+            ids = np.unique(batch["length"][:, 0]) if context == "length" else np.arange(delta_ref.shape[0]) if context == "id" else np.unique(batch["format"][:, 0])
             assert H.rel_l2((w[name] - w0[name])[ids], delta_ref[ids]) < 0.15, name
         else:
             assert H.rel_l2(w[name] - w0[name], delta_ref) < 0.1, name
