@@ -396,8 +396,51 @@ def layer_norm(x, gamma, beta):
     return (x - mu) / torch.sqrt(var + LN_EPS) * gamma + beta
 
 
+# ---- TF32 emulation (test utility): what the B200 product path computes in --------------------------------------------------------
+# The engine's GEMMs (every Dense forward / dgrad / wgrad, QK^T and PV) multiply operands rounded to TF32 (10 explicit mantissa bits,
+# round to nearest, ties away: the TMA unit's TFLOAT32 conversion and cvt.rna.tf32.f32) and accumulate in fp32.  ``emulate_tf32()`` makes
+# this oracle do the same in float64 -- forward and backward products -- so that tests can state what TF32 *predicts* for a quantity
+# and tell rounding from defects (tests/test_oracle_known_answers.py::test_tf32_emulation_bounds_the_stated_tolerances).
+def tf32_round(x: torch.Tensor) -> torch.Tensor:
+    bits = x.detach().to(torch.float32).contiguous().view(torch.int32)
+    bits = (bits + 0x1000) & ~0x1FFF  # sign-magnitude: adding half an ulp of the kept mantissa to the raw bits rounds the magnitude
+    return bits.view(torch.float32).to(x.dtype)
+
+
+class _Tf32MatMul(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return tf32_round(a) @ tf32_round(b)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        gr, ar, br = tf32_round(g), tf32_round(a), tf32_round(b)
+        if b.dim() == 2 and a.dim() > 2:  # Dense over (B, S, K): the weight gradient contracts over all tokens
+            return gr @ br.transpose(-1, -2), ar.reshape(-1, a.shape[-1]).transpose(0, 1) @ gr.reshape(-1, g.shape[-1])
+        return gr @ br.transpose(-1, -2), ar.transpose(-1, -2) @ gr
+
+
+_matmul = torch.matmul
+
+
+class emulate_tf32:
+    """``with emulate_tf32(): ...`` -- every matrix product of the model runs on TF32-rounded operands (forward and backward)."""
+
+    def __enter__(self):
+        global _matmul
+        self._saved = _matmul
+        _matmul = _Tf32MatMul.apply
+        return self
+
+    def __exit__(self, *exc):
+        global _matmul
+        _matmul = self._saved
+
+
 def dense(x, p, name):
-    return x @ p[name + "/kernel"] + p[name + "/bias"]  # A12
+    return _matmul(x, p[name + "/kernel"]) + p[name + "/bias"]  # A12
 
 
 def encoder_forward(p, inputs, input_columns, pos_keep=None, pos_rate=0.0, context=None):
@@ -417,7 +460,7 @@ def encoder_forward(p, inputs, input_columns, pos_keep=None, pos_rate=0.0, conte
             is_masked = (inputs[key] == MASK_VALUE).all(dim=2)  # encoder.py:165
             is_unused = (inputs[key] == NULL_VALUE).all(dim=2)  # encoder.py:166
             special = p[base + "_special/embeddings"]
-            x = xin @ p[base + "/kernel"] + p[base + "/bias"]  # encoder.py:173
+            x = _matmul(xin, p[base + "/kernel"]) + p[base + "/bias"]  # encoder.py:173
             x = torch.where(is_masked[..., None], special[0], x)  # encoder.py:174
             x = torch.where(is_unused[..., None], special[1], x)  # encoder.py:175
         seq = seq + x  # encoder.py:194-197
@@ -452,12 +495,12 @@ def mhsa_forward(p, prefix, x, mask):
     q = heads(dense(x, p, prefix + "/dense_query"))
     k = heads(dense(x, p, prefix + "/dense_key"))
     v = heads(dense(x, p, prefix + "/dense_value"))
-    score = q @ k.transpose(-1, -2)
+    score = _matmul(q, k.transpose(-1, -2))
     score = score / math.sqrt(float(dh))  # transformer.py:62-63
     m = mask.to(x.dtype)[:, None, None, :]
     score = score + (-1e9) * (1.0 - m)  # transformer.py:73
     w = torch.softmax(score, dim=-1)
-    out = (w @ v).permute(0, 2, 1, 3).reshape(B, S, D)
+    out = _matmul(w, v).permute(0, 2, 1, 3).reshape(B, S, D)
     return dense(out, p, prefix + "/combine_heads")
 
 
@@ -466,6 +509,14 @@ def dropout(x, keep, rate):
     if keep is None:
         return x
     return x * keep.to(x.dtype) * (1.0 / (1.0 - rate))
+
+
+_relu_hook = None  # test utility: callable(block index, pre-activations) -> activations; lets a test record the FFN pre-activations or
+#                    force single ReLU gates (tests/test_oracle_known_answers.py::test_relu_gate_at_the_tf32_rounding_edge)
+
+
+def ffn_relu(i, pre):
+    return torch.relu(pre) if _relu_hook is None else _relu_hook(i, pre)
 
 
 def blocks_forward(p, x, mask, num_blocks, drop=None, rate=0.0, block_type="deepsvg"):
@@ -477,7 +528,7 @@ def blocks_forward(p, x, mask, num_blocks, drop=None, rate=0.0, block_type="deep
             y = mhsa_forward(p, b + "/attn", x, mask)
             y = dropout(y, None if drop is None else drop[(i, 0)], rate)
             x = layer_norm(x + y, p[b + "/norm1/gamma"], p[b + "/norm1/beta"])
-            y = torch.relu(dense(x, p, b + "/mlp/layer_with_weights-0"))
+            y = ffn_relu(i, dense(x, p, b + "/mlp/layer_with_weights-0"))
             y = dense(y, p, b + "/mlp/layer_with_weights-1")
             y = dropout(y, None if drop is None else drop[(i, 1)], rate)
             x = layer_norm(x + y, p[b + "/norm2/gamma"], p[b + "/norm2/beta"])
@@ -487,7 +538,7 @@ def blocks_forward(p, x, mask, num_blocks, drop=None, rate=0.0, block_type="deep
         y = dropout(y, None if drop is None else drop[(i, 0)], rate)
         x = x + y
         y = layer_norm(x, p[b + "/norm2/gamma"], p[b + "/norm2/beta"])
-        y = torch.relu(dense(y, p, b + "/mlp/layer_with_weights-0"))  # transformer.py:163-166
+        y = ffn_relu(i, dense(y, p, b + "/mlp/layer_with_weights-0"))  # transformer.py:163-166
         y = dense(y, p, b + "/mlp/layer_with_weights-1")
         y = dropout(y, None if drop is None else drop[(i, 1)], rate)
         x = x + y

@@ -151,12 +151,123 @@ def test_oracle_merge_matches_reference_python(case):
             assert np.array_equal(got, ref), key
 
 
+# ================================================================================================= a ReLU gate at the rounding edge
+# The ``crello_ctx_canvas`` fixture holds ONE FFN pre-activation of the last block -- document 0, oracle row 8, unit 369: +5.7e-4 where
+# the layer's pre-activations have rms 0.83 -- that lies inside the error TF32 operand rounding puts on that GEMM (up to 2.7e-3 with
+# round-to-nearest, 4.4e-3 with truncation).  Its row carries a large share of the loss gradient (``random`` masking leaves few rows with
+# masked fields), so whether that single gate is open decides 10.8 % of the L2 norm and 0.265 of the +-1 projection of
+# d loss / d blocks/seq2seq_1/mlp/layer_with_weights-0/kernel.  Both outcomes are correct TF32 results; the float64 reference run (the
+# golden file) and the fp32 engine path see the gate open.
+EDGE_GATES = {"crello_ctx_canvas": [(1, (0, 8, 369))]}  # case: [(block, (document, oracle row, FFN unit))]
+EDGE_VARIABLE = "model/blocks/seq2seq/seq2seq_1/mlp/layer_with_weights-0/kernel"
+
+
+def oracle_step(case, closed_gates=(), tf32=None, record=None):
+    """The oracle's train step on a fixture -> (grads dict of numpy, params after Adam); ``closed_gates`` forces single ReLU gates of the
+    FFNs shut, ``tf32`` = an operand-rounding function to run every matrix product in emulated TF32, ``record`` = dict that receives
+    the FFN pre-activations per block."""
+    g, cols, batch, method, L, seed, step = load(case)
+    input_dtype = INPUT_DTYPE.get(case, "set")
+    o = O.OracleMFP(cols, num_blocks=L, masking_method=method, dropout=RATE, l2=L2, learning_rate=LR, clipnorm=1.0,
+                    block_type=BLOCK_TYPE.get(case, "deepsvg"), input_dtype=input_dtype, context=CONTEXT.get(case))
+    o.params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float64, bias_scale=0.05, input_dtype=input_dtype, context=CONTEXT.get(case))
+    draws = O.PhiloxDraws(seed, step)
+    tasks = torch.as_tensor(g["tasks"])
+    targets, mod, masks = O.preprocess_for_train(o.to_torch(batch), o.input_columns, tasks, draws, input_dtype)
+    B, S = batch["left"].shape[:2]
+
+    def hook(i, pre):
+        if record is not None:
+            record[i] = pre.detach().clone()
+        keep = torch.ones_like(pre)
+        for block, index in closed_gates:
+            if block == i:
+                keep[index] = 0.0
+        return torch.relu(pre) * keep
+
+    saved_hook, saved_round = O._relu_hook, O.tf32_round
+    O._relu_hook = hook
+    try:
+        if tf32 is None:
+            r = o.step_from(targets, mod, masks, tasks, o.dropout_masks(draws, B, S))
+        else:
+            O.tf32_round = tf32
+            with O.emulate_tf32():
+                r = o.step_from(targets, mod, masks, tasks, o.dropout_masks(draws, B, S))
+    finally:
+        O._relu_hook, O.tf32_round = saved_hook, saved_round
+    return OrderedDict((k, v.numpy()) for k, v in r["grads"].items()), OrderedDict((k, v.detach().numpy()) for k, v in o.params.items())
+
+
+def summaries(grads, params):
+    """The per-variable summaries a golden file keeps (make_golden.py): norm, +-1 projection and first 8 entries of the gradient, first 8
+    entries of the updated variable."""
+    out = {}
+    for name, gr in grads.items():
+        gr = gr.reshape(-1)
+        out["gradnorm/" + name] = np.linalg.norm(gr)
+        out["gradproj/" + name] = gr @ projection_vector(name, gr.size)
+        out["gradhead/" + name] = gr[:8].copy()
+        out["newhead/" + name] = params[name].reshape(-1)[:8].copy()
+    return out
+
+
+def tf32_truncate(x):
+    bits = x.detach().to(torch.float32).contiguous().view(torch.int32) & ~0x1FFF
+    return bits.view(torch.float32).to(x.dtype)
+
+
+def test_relu_gate_at_the_tf32_rounding_edge():
+    """The evidence behind ``EDGE_GATES``, all on the CPU: the gate's pre-activation is smaller than TF32's error on
+    it; closing that one gate reproduces the deviation the TF32 engine path showed on the GPU (projection off by 0.27 of the gradient's
+    norm; bound 0.20); and a TF32 emulation lands on either side depending on the rounding mode -- round-to-nearest keeps the gate open
+    and agrees with the golden gradient, truncation closes it and agrees with the closed-gate gradient."""
+    case = "crello_ctx_canvas"
+    (block, index), = EDGE_GATES[case]
+    g = np.load(os.path.join(GOLDEN, case + ".npz"))
+    pv = projection_vector(EDGE_VARIABLE, 256 * 512)
+    pre, pre_rna, pre_rz = {}, {}, {}
+    exact, exact_params = oracle_step(case, record=pre)
+    scale = np.linalg.norm(exact[EDGE_VARIABLE])
+    for key, value in summaries(exact, exact_params).items():  # the gate-open run is the one the golden file pins, summarised the same way
+        assert np.allclose(value, g[key], rtol=1e-8, atol=1e-10 * max(scale, 1.0)), key
+
+    def deviation(a, b):
+        d = (a[EDGE_VARIABLE] - b[EDGE_VARIABLE]).reshape(-1)
+        return np.linalg.norm(d) / scale, abs(d @ pv) / scale
+
+    rna, _ = oracle_step(case, tf32=O.tf32_round, record=pre_rna)
+    rz, _ = oracle_step(case, tf32=tf32_truncate, record=pre_rz)
+    value = float(pre[block][index])
+    assert 0.0 < value < 1e-3 and float(pre[block].pow(2).mean().sqrt()) > 0.5  # +5.7e-4 against rms 0.83
+    assert float((pre_rna[block] - pre[block]).abs().max()) > 2.0 * value  # the layer's TF32 error is several times the gate's margin
+    assert float(pre_rna[block][index]) > 0.0 > float(pre_rz[block][index])  # open under round-to-nearest, shut under truncation
+    closed, closed_params = oracle_step(case, closed_gates=EDGE_GATES[case])
+    l2, proj = deviation(closed, exact)
+    assert l2 == pytest.approx(0.1076, abs=2e-3) and proj == pytest.approx(0.265, abs=5e-3)  # the GPU observation: 0.27
+    assert proj > 4 * H.GRAD_REL_L2  # ... which is over the golden check's bound, hence the dual reference in the GPU test
+    assert max(deviation(rna, exact)) < 1e-2 and max(deviation(rz, closed)) < 1e-2
+    # every other gate that truncation flips sits on a row without masked fields (no gradient reaches it): the closed-gate run differs
+    # from the truncation run by rounding only, for every variable
+    for name in exact:
+        if not name.endswith("dense_key/bias"):
+            d = np.linalg.norm(rz[name] - closed[name]) / max(np.linalg.norm(closed[name]), 1e-9)
+            assert d < H.GRAD_REL_L2, (name, d)
+    shut = summaries(closed, closed_params)
+    assert abs(shut["gradproj/" + EDGE_VARIABLE] - float(g["gradproj/" + EDGE_VARIABLE])) / scale == pytest.approx(proj)
+
+
 # ================================================================================================= GPU (C ABI)
 # Open item (DESIGN.md section 7, --context canvas): on the TF32 product path the +-1 projection of ONE gradient of this case (the last
-# block's first FFN kernel) is off by 0.27 of the gradient's norm (bound: 0.20) while masks, logits, losses and every gradient checked
-# before it are within tolerance, the fp32 path passes the whole case, and the TF32 training curve of the same model tracks the oracle
-# (tests/test_gpu_context.py).  The GPU budget of the round ended before it could be traced; not hidden: expected-to-fail, not removed.
-_OPEN = {("crello_ctx_canvas", 0): "TF32 path: gradient projection of blocks/seq2seq_1/mlp/layer_with_weights-0/kernel 33 % over the bound (untraced)"}
+# block's first FFN kernel) was measured 0.27 of the gradient's norm off the golden value (bound: 0.20) while masks, logits, losses and
+# every gradient checked before it were within tolerance and the fp32 path passed the whole case.  Traced on the CPU after the round's GPU
+# budget had ended (test_relu_gate_at_the_tf32_rounding_edge above): one ReLU gate of the fixture lies inside TF32's rounding error and
+# closing it moves exactly that projection by 0.265.  The test below therefore compares the TF32 path with whichever of the two oracle
+# runs -- gate open (the golden file) or gate shut (the oracle, run here) -- the engine's gradient of that variable is nearer to, and
+# holds EVERY variable to that one run.  That comparison has not run on a GPU yet, so the case keeps its non-strict expected-to-fail
+# mark until it has been seen to pass there (an XPASS in the round-end GPU run is that confirmation).
+_OPEN = {("crello_ctx_canvas", 0): "TF32 path: a ReLU gate of the fixture at the rounding edge (0.27 vs bound 0.20 against the golden run); "
+                                   "dual-reference comparison not yet confirmed on a GPU"}
 
 
 def _engine_cases():
@@ -235,6 +346,14 @@ def test_engine_matches_reference_python(case, impl):
     specs = O.variable_specs(cols, L, 256, input_dtype, CONTEXT.get(case))
     got_grads = eng.get_weights(eng.grads)
     w0 = eng.get_weights()
+    if impl == 0 and case in EDGE_GATES:
+        # the reference run this TF32 result belongs to: gate open (golden file) or shut (oracle) -- decided by the one variable the gate
+        # dominates, then applied to all of them
+        closed = summaries(*oracle_step(case, closed_gates=EDGE_GATES[case]))
+        gg = got_grads[EDGE_VARIABLE].astype(np.float64).reshape(-1) + 2.0 * L2 * w0[EDGE_VARIABLE].astype(np.float64).reshape(-1)
+        proj = gg @ projection_vector(EDGE_VARIABLE, gg.size)
+        if abs(proj - closed["gradproj/" + EDGE_VARIABLE]) < abs(proj - float(g["gradproj/" + EDGE_VARIABLE])):
+            g = {**{k: g[k] for k in g.files}, **closed}
     for name in specs:
         gg = got_grads[name].astype(np.float64).reshape(-1)
         if specs[name][2]:

@@ -216,3 +216,55 @@ def test_train_step_runs_and_loss_decreases():
     for i in range(30):
         last = o.train_step(b, seed=1, step=0)["data_loss"]
     assert last < first
+
+
+def test_tf32_emulation_bounds_the_stated_tolerances():
+    """What TF32 operand rounding (forward and backward products; ``O.emulate_tf32``) does to two golden cases, computed on the CPU in
+    float64: the logits move by 6e-3 to 7e-3 (a third of ``LOGIT_ATOL``), the loss by under 2e-4 relative (a tenth of ``LOSS_RTOL``) and
+    whole gradients by 1 to 2 % of their norm (``GRAD_REL_L2`` is 5 %; most of that is single ReLU gates of these 27- to 64-row batches
+    changing sides, see tests/test_golden_reference.py::test_relu_gate_at_the_tf32_rounding_edge) -- i.e. the tolerances the GPU tests
+    state for the product path (tests/helpers.py) are TF32-sized, not slack."""
+    import os
+
+    from tests import helpers as H
+    from tests.test_golden_reference import CASES, CONTEXT, GOLDEN, projection_vector
+
+    assert O.tf32_round(torch.tensor([1.0 + 2.0 ** -11, 1.0 + 2.0 ** -12, -1.0 - 2.0 ** -11, 3.0], dtype=torch.float64)).tolist() == [1.0 + 2.0 ** -10, 1.0, -1.0 - 2.0 ** -10, 3.0]
+    for case in ("crello_random", "crello_ctx_canvas"):
+        dataset, method, L, seed, step = CASES[case]
+        g = np.load(os.path.join(GOLDEN, case + ".npz"))
+        cols = make_input_columns(dataset, max_length=50)
+        batch = OrderedDict((k[3:], g[k]) for k in g.files if k.startswith("in/"))
+        ctx = CONTEXT.get(case)
+        o = O.OracleMFP(cols, num_blocks=L, masking_method=method, dropout=0.1, l2=1e-2, context=ctx)
+        params = O.init_params(cols, L, 256, 11, torch.float64, bias_scale=0.05, context=ctx)
+        draws = O.PhiloxDraws(seed, step)
+        tasks = torch.as_tensor(g["tasks"])
+        targets, mod, masks = O.preprocess_for_train(o.to_torch(batch), o.input_columns, tasks, draws, "set")
+        B, S = batch["left"].shape[:2]
+        drop = o.dropout_masks(draws, B, S)
+
+        def run():
+            p = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in params.items())
+            total, _, _, _, _, outputs = o.loss_from(p, targets, mod, masks, tasks, drop)
+            total.backward()
+            grads = OrderedDict((k, (v.grad if v.grad is not None else torch.zeros_like(v)).numpy()) for k, v in p.items())
+            return float(total.detach()), OrderedDict((k, v.detach()) for k, v in outputs.items()), grads
+
+        loss, outs, grads = run()
+        with O.emulate_tf32():
+            loss_t, outs_t, grads_t = run()
+        assert abs(loss_t - loss) / loss < H.LOSS_RTOL / 4
+        logit_err = max(float((outs_t[key] - outs[key]).abs().max()) for key in outs)
+        assert H.LOGIT_ATOL / 10 < logit_err < H.LOGIT_ATOL / 2, logit_err
+        worst = 0.0
+        for name, gr in grads.items():
+            scale = max(np.linalg.norm(gr), 1e-9)
+            if name.endswith("dense_key/bias"):
+                continue  # exact gradient = the L2 term only (softmax is shift invariant)
+            err = np.linalg.norm(grads_t[name] - gr) / scale
+            worst = max(worst, err)
+            assert err < H.GRAD_REL_L2 / 2, (case, name, err)
+            pv = projection_vector(name, gr.size)
+            assert abs((grads_t[name] - gr).reshape(-1) @ pv) < H.GRAD_REL_L2 * scale * 4 / 2, (case, name)
+        assert H.GRAD_REL_L2 / 10 < worst < H.GRAD_REL_L2 / 2, worst  # the emulation is on, and it uses a fifth to a half of the tolerance
