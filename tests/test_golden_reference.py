@@ -217,6 +217,46 @@ def tf32_truncate(x):
     return bits.view(torch.float32).to(x.dtype)
 
 
+def pick_reference_run(case, g, total_grads):
+    """The reference run a TF32 result of ``case`` belongs to: the golden file (every gate as in float64) or, for a fixture with a gate at
+    the rounding edge, the oracle's run with that gate shut -- decided by the one variable the gate dominates (whichever projection the
+    result is nearer to), then applied to every variable and to the Adam step.  Returns a golden-file-like mapping."""
+    if case not in EDGE_GATES:
+        return g
+    closed = summaries(*oracle_step(case, closed_gates=EDGE_GATES[case]))
+    proj = total_grads[EDGE_VARIABLE] @ projection_vector(EDGE_VARIABLE, total_grads[EDGE_VARIABLE].size)
+    if abs(proj - closed["gradproj/" + EDGE_VARIABLE]) < abs(proj - float(g["gradproj/" + EDGE_VARIABLE])):
+        return {**{k: g[k] for k in g.files}, **closed}
+    return g
+
+
+def check_gradient_summaries(total_grads, g, grad_tol):
+    """Gradients of the total loss (data + L2), flat float64 per variable, against the summaries of a reference run."""
+    for name, gg in total_grads.items():
+        scale = max(float(g["gradnorm/" + name]), 1e-9)
+        if name.endswith("dense_key/bias"):
+            # softmax is shift-invariant: the exact data gradient of the key bias is 0 (what is left in the golden value is
+            # the L2 term); the engine's is the rounding noise of the column sum of dK -- bound it by the kernel's gradient
+            scale = max(scale, float(g["gradnorm/" + name.replace("/bias", "/kernel")]))
+        assert abs(np.linalg.norm(gg) - float(g["gradnorm/" + name])) <= grad_tol * scale, name
+        assert abs(gg @ projection_vector(name, gg.size) - float(g["gradproj/" + name])) <= grad_tol * scale * 4, name
+        assert np.abs(gg[:8] - g["gradhead/" + name]).max() <= grad_tol * scale, name
+
+
+def check_adam_heads(new_weights, g, impl):
+    """The variables after L2 + per-variable clipnorm + one Adam step against a reference run."""
+    for name, w in new_weights.items():
+        # The first Adam step is lr * g / (|g| + 3.2e-6) on the clipped gradient: entries far above that scale move by
+        # exactly +-lr (compared strictly); entries whose exact gradient is ~0 move by up to lr in the direction of the
+        # rounding noise, in the engine and in a float32 TensorFlow run alike (bounded by 2 lr).
+        gref = g["gradhead/" + name] * min(1.0, 1.0 / max(float(g["gradnorm/" + name]), 1e-12))
+        # (TF32: a clipped entry of 1e-3 is 1e-3 of the gradient's norm, the size of the product path's own rounding error)
+        strict = np.abs(gref) > (1e-3 if impl == 1 else 5e-3)
+        diff = np.abs(w[:8] - g["newhead/" + name])
+        assert diff[strict].max(initial=0.0) <= 5e-6, name
+        assert diff.max() <= 2.0 * LR + 5e-6, name
+
+
 def test_relu_gate_at_the_tf32_rounding_edge():
     """The evidence behind ``EDGE_GATES``, all on the CPU: the gate's pre-activation is smaller than TF32's error on
     it; closing that one gate reproduces the deviation the TF32 engine path showed on the GPU (projection off by 0.27 of the gradient's
@@ -255,6 +295,42 @@ def test_relu_gate_at_the_tf32_rounding_edge():
             assert d < H.GRAD_REL_L2, (name, d)
     shut = summaries(closed, closed_params)
     assert abs(shut["gradproj/" + EDGE_VARIABLE] - float(g["gradproj/" + EDGE_VARIABLE])) / scale == pytest.approx(proj)
+
+
+def _flat(d):
+    return OrderedDict((k, np.asarray(v, dtype=np.float64).reshape(-1)) for k, v in d.items())
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_engine_checks_accept_the_oracle_run(case):
+    """The comparison helpers of the GPU test below, exercised on the CPU: the oracle's own gradients and Adam step pass them at the
+    fp32-path tolerances against every golden file (so a failure on the GPU is the engine's, not the helpers')."""
+    g = np.load(os.path.join(GOLDEN, case + ".npz"))
+    grads, params = oracle_step(case)
+    assert pick_reference_run(case, g, _flat(grads)) is g  # float64 gates are the golden file's
+    check_gradient_summaries(_flat(grads), g, H.F32_GRAD_REL_L2)
+    check_adam_heads(_flat(params), g, 1)
+
+
+def test_engine_checks_follow_the_gate_of_a_tf32_run():
+    """... and on the edge fixture a TF32-emulated run is held to the reference run on its side of the gate: round-to-nearest to the
+    golden file, truncation to the closed-gate oracle run -- each passes the product path's tolerances there and fails against the
+    other run."""
+    case = "crello_ctx_canvas"
+    g = np.load(os.path.join(GOLDEN, case + ".npz"))
+    rna, rna_params = oracle_step(case, tf32=O.tf32_round)
+    rz, rz_params = oracle_step(case, tf32=tf32_truncate)
+    assert pick_reference_run(case, g, _flat(rna)) is g
+    check_gradient_summaries(_flat(rna), g, H.GRAD_REL_L2)
+    check_adam_heads(_flat(rna_params), g, 0)
+    ref = pick_reference_run(case, g, _flat(rz))
+    assert ref is not g and float(ref["data_loss"]) == float(g["data_loss"])  # everything but the gradient summaries stays the golden file's
+    check_gradient_summaries(_flat(rz), ref, H.GRAD_REL_L2)
+    check_adam_heads(_flat(rz_params), ref, 0)
+    with pytest.raises(AssertionError):
+        check_gradient_summaries(_flat(rz), g, H.GRAD_REL_L2)
+    with pytest.raises(AssertionError):
+        check_gradient_summaries(_flat(rna), ref, H.GRAD_REL_L2)
 
 
 # ================================================================================================= GPU (C ABI)
@@ -346,43 +422,19 @@ def test_engine_matches_reference_python(case, impl):
     specs = O.variable_specs(cols, L, 256, input_dtype, CONTEXT.get(case))
     got_grads = eng.get_weights(eng.grads)
     w0 = eng.get_weights()
-    if impl == 0 and case in EDGE_GATES:
-        # the reference run this TF32 result belongs to: gate open (golden file) or shut (oracle) -- decided by the one variable the gate
-        # dominates, then applied to all of them
-        closed = summaries(*oracle_step(case, closed_gates=EDGE_GATES[case]))
-        gg = got_grads[EDGE_VARIABLE].astype(np.float64).reshape(-1) + 2.0 * L2 * w0[EDGE_VARIABLE].astype(np.float64).reshape(-1)
-        proj = gg @ projection_vector(EDGE_VARIABLE, gg.size)
-        if abs(proj - closed["gradproj/" + EDGE_VARIABLE]) < abs(proj - float(g["gradproj/" + EDGE_VARIABLE])):
-            g = {**{k: g[k] for k in g.files}, **closed}
+    total = OrderedDict()
     for name in specs:
         gg = got_grads[name].astype(np.float64).reshape(-1)
-        if specs[name][2]:
-            gg = gg + 2.0 * L2 * w0[name].astype(np.float64).reshape(-1)
-        scale = max(float(g["gradnorm/" + name]), 1e-9)
-        if name.endswith("dense_key/bias"):
-            # softmax is shift-invariant: the exact data gradient of the key bias is 0 (what is left in the golden value is
-            # the L2 term); the engine's is the rounding noise of the column sum of dK -- bound it by the kernel's gradient
-            scale = max(scale, float(g["gradnorm/" + name.replace("/bias", "/kernel")]))
-        assert abs(np.linalg.norm(gg) - float(g["gradnorm/" + name])) <= grad_tol * scale, name
-        assert abs(gg @ projection_vector(name, gg.size) - float(g["gradproj/" + name])) <= grad_tol * scale * 4, name
-        assert np.abs(gg[:8] - g["gradhead/" + name]).max() <= grad_tol * scale, name
+        total[name] = gg + 2.0 * L2 * w0[name].astype(np.float64).reshape(-1) if specs[name][2] else gg
+    if impl == 0:
+        g = pick_reference_run(case, g, total)
+    check_gradient_summaries(total, g, grad_tol)
     # ---- L2 + per-variable clipnorm + Adam, one step
     l2_out = torch.zeros(1, device="cuda")
     eng.optimizer_step(1, LR, 1.0, l2_out)
     torch.cuda.synchronize()
     assert float(l2_out.cpu()) == pytest.approx(float(g["total_loss"]) - float(g["data_loss"]), rel=1e-5)
-    w1 = eng.get_weights()
-    for name in specs:
-        w = w1[name].astype(np.float64).reshape(-1)
-        # The first Adam step is lr * g / (|g| + 3.2e-6) on the clipped gradient: entries far above that scale move by
-        # exactly +-lr (compared strictly); entries whose exact gradient is ~0 move by up to lr in the direction of the
-        # rounding noise, in the engine and in a float32 TensorFlow run alike (bounded by 2 lr).
-        gref = g["gradhead/" + name] * min(1.0, 1.0 / max(float(g["gradnorm/" + name]), 1e-12))
-        # (TF32: a clipped entry of 1e-3 is 1e-3 of the gradient's norm, the size of the product path's own rounding error)
-        strict = np.abs(gref) > (1e-3 if impl == 1 else 5e-3)
-        diff = np.abs(w[:8] - g["newhead/" + name])
-        assert diff[strict].max(initial=0.0) <= 5e-6, name
-        assert diff.max() <= 2.0 * LR + 5e-6, name
+    check_adam_heads({name: w.astype(np.float64).reshape(-1) for name, w in eng.get_weights().items() if name in specs}, g, impl)
 
 
 # ================================================================================================= demo / eval entry
