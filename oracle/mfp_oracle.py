@@ -466,6 +466,10 @@ def encoder_forward(p, inputs, input_columns, pos_keep=None, pos_rate=0.0, conte
         seq = seq + x  # encoder.py:194-197
     pos_name = "model/encoder/input_layer/const/embeddings/embeddings"
     if pos_name in p:  # use_pos_token (encoder.py:251-252): PositionEmbedding tiled over the batch, under its own Dropout
+        if context in ("id", "length", "canvas"):
+            # the reference prepends the token first and then adds positions 0..S to token + elements (encoder.py:247-252); that
+            # combination is not restated here (and refused by the product path, flex_dm_b200/mfp.py)
+            raise NotImplementedError("context=%r with a position embedding (input_dtype != 'set') is not restated by the oracle" % (context,))
         B = seq.shape[0]
         emb = p[pos_name][:S][None].expand(B, -1, -1)
         seq = seq + dropout(emb, pos_keep, pos_rate)
