@@ -132,6 +132,7 @@ class MFP:
         self._dist = None
         self._overlap = False
         self.history: List[Dict[str, float]] = []
+        self.stop_training = False
 
     # ------------------------------------------------------------------ distributed (document-sharded DP)
     def enable_data_parallel(self, dist_module, world_size: int, overlap: bool = False):
@@ -324,7 +325,13 @@ class MFP:
             iterator = iter(dataset)
         else:
             iterator = DevicePrefetcher(self, dataset)  # H2D copies of step i+1 run under the compute of step i
+        from .callbacks import CallbackList
+
+        hooks = CallbackList(callbacks, self)  # Keras-style objects (flex_dm_b200.callbacks, helpers/callbacks.py:36-66) or callables
+        self.stop_training = False
+        hooks.on_train_begin()
         for epoch in range(epochs):
+            hooks.on_epoch_begin(epoch)
             logs = self._run_epoch(iterator, steps_per_epoch, True, staged=True)
             if validation_data is not None and (epoch + 1) % max(1, validation_freq) == 0:
                 val = self._run_epoch(iter(validation_data), validation_steps or 1, False)
@@ -334,10 +341,12 @@ class MFP:
                 self.history.append(logs)
                 break
             self.history.append(logs)
-            for cb in callbacks or []:
-                cb(epoch, logs, self)
+            hooks.on_epoch_end(epoch, logs)
             if verbose:
                 logger.info("Epoch %d/%d - %s", epoch + 1, epochs, " - ".join("%s: %.4f" % kv for kv in logs.items()))
+            if self.stop_training:  # set by a callback (Keras: model.stop_training)
+                break
+        hooks.on_train_end()
         return self.history
 
     def evaluate(self, dataset: Iterable, batch_size=None, steps: Optional[int] = None) -> List[float]:

@@ -160,3 +160,103 @@ def test_evaluate_matches_oracle_scores(dataset, task_mode, group_keys):
             assert abs(val - num / den) <= max(1.0, 0.02 * den) / den, (key, val, num / den)  # argmax flips from TF32 near-ties
         else:
             assert val == pytest.approx(num / den, abs=5e-3), key
+
+
+# ================================================================================================= fit's callback protocol (CPU)
+class _FitStub:
+    """``MFP.fit`` with the engine taken out: the epoch runner is scripted, everything else (validation schedule, history, callback
+    dispatch, stop_training) is the product code."""
+
+    def __new__(cls, train_logs, val_logs):
+        from flex_dm_b200.mfp import MFP
+
+        class Stub(MFP):
+            def __init__(self):  # no engine
+                self.history, self.stop_training, self.saved = [], False, []
+                self._train, self._val = iter(train_logs), iter(val_logs)
+
+            def _run_epoch(self, iterator, steps, train, staged=False):
+                from collections import OrderedDict
+                return OrderedDict(next(self._train if train else self._val))
+
+            def save_weights(self, path):
+                self.saved.append(path)
+
+        return Stub()
+
+
+class _Dataset(list):
+    yields_device_batches = True  # keeps fit from wrapping the (never read) dataset in a DevicePrefetcher
+
+
+def test_fit_drives_the_reference_callback_list(tmp_path):
+    """train.py:79-88 with ``callbacks=get_callbacks(args, dataspec, checkpoint_path)`` (helpers/callbacks.py:36-66): best.ckpt is
+    written when ``val_total_score`` improves (mode max) and only on epochs that validated (validation_freq), per-epoch scalars are
+    logged, hooks fire in Keras' order, plain callables keep working."""
+    import json
+    from types import SimpleNamespace
+
+    from flex_dm_b200.callbacks import Callback, ModelCheckpoint, get_callbacks
+
+    train = [{"loss": 5.0 - e, "total_score": 0.1 * e} for e in range(6)]
+    val = [{"loss": 4.0, "total_score": 0.30}, {"loss": 3.0, "total_score": 0.50}, {"loss": 2.5, "total_score": 0.40}]
+    model = _FitStub(train, val)
+    events = []
+
+    class Spy(Callback):
+        def on_train_begin(self, logs=None):
+            events.append("begin")
+
+        def on_epoch_begin(self, epoch, logs=None):
+            events.append("epoch_begin %d" % epoch)
+
+        def on_epoch_end(self, epoch, logs=None):
+            events.append("epoch_end %d %s" % (epoch, "val" if "val_total_score" in logs else "-"))
+
+        def on_train_end(self, logs=None):
+            events.append("end")
+
+    seen = []
+    args = SimpleNamespace(job_dir=str(tmp_path))
+    os.makedirs(os.path.join(args.job_dir, "logs", "stale"))
+    ckpt = os.path.join(args.job_dir, "checkpoints", "best.ckpt")
+    cbs = get_callbacks(args, None, ckpt)
+    assert [type(c).__name__ for c in cbs] == ["ScalarLogger", "ModelCheckpoint", "TerminateOnNaN", "GarbageCollector"]
+    assert not os.path.exists(os.path.join(args.job_dir, "logs", "stale"))  # the log dir is overwritten, as in the reference
+    history = model.fit(_Dataset(), steps_per_epoch=2, epochs=6, validation_data=_Dataset(), validation_steps=1, validation_freq=2,
+                        callbacks=cbs + [Spy(), lambda epoch, logs, m: seen.append((epoch, m is model))], verbose=0)
+    assert len(history) == 6 and [("val_loss" in h) for h in history] == [False, True] * 3
+    assert model.saved == [ckpt, ckpt]  # epochs 2 (0.30) and 4 (0.50); epoch 6 (0.40) did not improve; odd epochs had nothing to monitor
+    assert cbs[1].best == 0.50
+    assert events == ["begin"] + [e for k in range(6) for e in ("epoch_begin %d" % k, "epoch_end %d %s" % (k, "val" if k % 2 else "-"))] + ["end"]
+    assert seen == [(k, True) for k in range(6)]
+    lines = [json.loads(x) for x in open(os.path.join(args.job_dir, "logs", "scalars.jsonl"))]
+    assert [r["epoch"] for r in lines] == list(range(6)) and lines[1]["val_total_score"] == 0.30 and "val_loss" not in lines[0]
+    with pytest.raises(NotImplementedError):
+        ModelCheckpoint(ckpt)  # save_weights_only=False: a whole-model SavedModel has no counterpart
+    assert ModelCheckpoint(ckpt, save_weights_only=True, monitor="val_acc").mode == "max" and ModelCheckpoint(ckpt, save_weights_only=True).mode == "min"
+
+
+def test_fit_stops_on_request_and_on_a_non_finite_loss():
+    from flex_dm_b200.callbacks import Callback, TerminateOnNaN
+
+    class StopAfter(Callback):
+        def on_epoch_end(self, epoch, logs=None):
+            self.model.stop_training = epoch == 1
+
+    ended = []
+
+    class End(Callback):
+        def on_train_end(self, logs=None):
+            ended.append(True)
+
+    model = _FitStub([{"loss": 1.0}] * 5, [])
+    assert len(model.fit(_Dataset(), steps_per_epoch=1, epochs=5, callbacks=[StopAfter(), End()], verbose=0)) == 2 and ended == [True]
+    model = _FitStub([{"loss": 1.0}, {"loss": float("nan")}, {"loss": 1.0}], [])
+    history = model.fit(_Dataset(), steps_per_epoch=1, epochs=3, callbacks=[TerminateOnNaN(), End()], verbose=0)
+    assert len(history) == 2 and np.isnan(history[-1]["loss"]) and ended == [True, True]
+    stub = _FitStub([], [])
+    cb = TerminateOnNaN()
+    cb.set_model(stub)
+    cb.on_epoch_end(0, {"loss": float("inf")})
+    assert stub.stop_training
