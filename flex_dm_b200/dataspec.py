@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from . import io_lib
+from .spec import ATTRIBUTE_GROUPS  # noqa: F401  (the notebooks import it from mfp.data.spec, spec.py:364-377)
 
 
 # ----------------------------------------------------------------------------------------------------------------------------------
@@ -216,6 +217,15 @@ def write_tfrecord(path: str, records: Sequence[bytes]):
     ptrs = (ctypes.c_char_p * max(n, 1))(*records)
     lens = (ctypes.c_uint64 * max(n, 1))(*[len(r) for r in records])
     io_lib.check(lib.fdio_tfrecord_write(path.encode(), ptrs, lens, n))
+
+
+def set_visual_default(decoded_data: Dict) -> Dict:
+    """``data/spec.py:16-21`` (demo_crello's "attr" view): every element of an unbatched document drawn black, opaque, in a dummy font."""
+    for element in decoded_data["elements"]:
+        element["color"] = [0.0, 0.0, 0.0]
+        element["opacity"] = 1.0
+        element["font_family"] = "DummyFont"
+    return decoded_data
 
 
 class TFRecordFile:

@@ -48,6 +48,32 @@ def get_task_ids(task_names: List[str], masking_method: str) -> List[int]:
     return ids
 
 
+def merge_inputs_and_prediction(inputs: Dict, input_columns: Dict, masks: Dict, prediction: Dict) -> Dict:
+    """``mfp.py:46-69`` as the notebooks import it (demo_rico: applied once more to ``model(example, demo_args=...)``'s return value
+    with the *full* column dict, which copies the demo-only columns -- ``id``, ``uuid`` -- into the prediction).  Inside ``MFP.__call__``
+    the same merge is the engine's ``merge_prediction`` kernel; this is the host-level function for already-materialised outputs:
+    prediction where ``masks[key]`` is set, ground truth (one-hot for categorical columns) elsewhere, canvas and demo-only columns copied.
+    Like the reference it updates and returns ``prediction``."""
+    for key, column in input_columns.items():
+        if not column["is_sequence"]:
+            prediction[key] = inputs[key]  # keep canvas attributes
+        elif key not in masks:
+            continue  # demo only attributes
+        else:
+            pred = prediction[key]
+            mask = torch.as_tensor(masks[key]).to(device=pred.device, dtype=torch.bool)
+            value = torch.as_tensor(inputs[key]).to(pred.device)
+            if column["type"] == "numerical":
+                prediction[key] = torch.where(mask[..., None], pred, value.to(pred.dtype))
+            else:
+                gt = torch.nn.functional.one_hot(value.to(torch.int64), column["input_dim"]).to(pred.dtype)
+                prediction[key] = torch.where(mask[..., None, None], pred, gt)
+    for key, column in input_columns.items():  # copy unpredicted items for visualization
+        if column.get("demo_only", False):
+            prediction[key] = inputs[key]
+    return prediction
+
+
 def init_weights(engine: Engine, seed: int = 0) -> "OrderedDict[str, np.ndarray]":
     """Keras default initialisers: Dense glorot-uniform kernel / zero bias,
     Embedding U(-0.05, 0.05), LayerNorm gamma = 1 / beta = 0."""

@@ -260,3 +260,45 @@ def test_fit_stops_on_request_and_on_a_non_finite_loss():
     cb.set_model(stub)
     cb.on_epoch_end(0, {"loss": float("inf")})
     assert stub.stop_training
+
+
+def test_notebook_imports_resolve_and_merge_matches_the_oracle():
+    """The names the reference notebooks import (demo_rico / demo_crello cell 1): ``merge_inputs_and_prediction`` from the MFP module,
+    ``get_seq_mask`` / ``get_initial_masks`` from masking, ``ATTRIBUTE_GROUPS`` / ``DataSpec`` / ``set_visual_default`` from the data
+    module.  The host-level merge equals the oracle's restatement of mfp.py:46-69, is idempotent (the notebook applies it to an already
+    merged prediction) and copies demo-only columns."""
+    from flex_dm_b200.dataspec import ATTRIBUTE_GROUPS, DataSpec, set_visual_default  # noqa: F401
+    from flex_dm_b200.masking import get_initial_masks, get_seq_mask
+    from flex_dm_b200.mfp import MFP, merge_inputs_and_prediction  # noqa: F401
+
+    assert sorted(ATTRIBUTE_GROUPS["crello"]) == ["attr", "img", "pos", "txt", "type"]
+    doc = set_visual_default({"elements": [{"color": [1.0, 0.5, 0.0], "opacity": 0.3, "font_family": "X", "left": 0.1}]})
+    assert doc["elements"][0] == {"color": [0.0, 0.0, 0.0], "opacity": 1.0, "font_family": "DummyFont", "left": 0.1}
+    cols = make_input_columns("crello")
+    assert cols["id"].get("demo_only") and cols["uuid"].get("demo_only")  # strings, demo only (crello-spec.yml)
+    batch = make_synthetic_batch(cols, 3, 6, seed=4, lengths="ragged")
+    inputs = {k: torch.as_tensor(v) for k, v in batch.items()}
+    inputs["id"] = np.array([[b"doc%d" % b] for b in range(3)], dtype=object)
+    inputs["uuid"] = np.array([[b"a"] * 6] * 3, dtype=object)
+    seq_mask = get_seq_mask(inputs["length"])
+    masks = get_initial_masks({k: v for k, v in cols.items() if not v.get("demo_only")}, seq_mask)
+    gen = torch.Generator().manual_seed(0)
+    for key in ("left", "color", "image_embedding"):
+        masks[key] = (torch.rand(seq_mask.shape, generator=gen) < 0.5) & seq_mask
+    prediction = {}
+    for key, c in cols.items():
+        if c["is_sequence"] and not c.get("demo_only"):
+            shape = tuple(inputs[key].shape) + ((c["input_dim"],) if c["type"] == "categorical" else ())
+            prediction[key] = torch.randn(shape, generator=gen)
+    ref = O.merge_inputs_and_prediction(inputs, cols, masks, {k: v.clone() for k, v in prediction.items()})
+    got = merge_inputs_and_prediction(inputs, cols, masks, prediction)
+    assert got is prediction and got["uuid"] is inputs["uuid"] and got["id"] is inputs["id"]
+    assert set(got) == set(ref)
+    for key in ref:
+        if key not in ("id", "uuid"):
+            assert torch.equal(torch.as_tensor(got[key]), torch.as_tensor(ref[key])), key
+    assert torch.equal(got["left"].argmax(-1)[~masks["left"]], inputs["left"][~masks["left"]])  # one-hot ground truth where not masked
+    again = merge_inputs_and_prediction(inputs, cols, masks, {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in got.items()})
+    for key in ref:
+        if key not in ("id", "uuid"):
+            assert torch.equal(torch.as_tensor(again[key]), torch.as_tensor(got[key])), key
