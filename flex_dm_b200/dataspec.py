@@ -638,10 +638,31 @@ class RecordDataset:
         idx = np.asarray(picked, dtype=np.int64)
         return self.spec.parse_records(self.pointers[idx], self.lengths[idx], pad_to=self.pad_to, pin_memory=self.pin_memory, strings=self.strings)
 
-    def __iter__(self) -> Iterator[Dict]:
+    def __iter__(self) -> "BatchIterator":
         if self.prefetch <= 0:
-            return self._batches()
-        return _Prefetched(self._batches(), self.prefetch)
+            return BatchIterator(self._batches())
+        return BatchIterator(_Prefetched(self._batches(), self.prefetch))
+
+
+class BatchIterator:
+    """``iter(dataset)``: a Python iterator that also answers ``tf.data``'s ``iterator.get_next()`` (eval.py:47-49).  Where TensorFlow
+    raises ``OutOfRangeError`` at the end of a non-repeating dataset this raises ``StopIteration``."""
+
+    def __init__(self, source: Iterator[Dict]):
+        self._source = source
+
+    def __iter__(self) -> "BatchIterator":
+        return self
+
+    def __next__(self) -> Dict:
+        return next(self._source)
+
+    get_next = __next__
+
+    def close(self) -> None:
+        close = getattr(self._source, "close", None)
+        if close is not None:
+            close()
 
 
 class _Prefetched:

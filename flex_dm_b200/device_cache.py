@@ -86,7 +86,12 @@ class DeviceCachedDataset:
             out[k] = t
         return OrderedDict((k, out[k]) for k in self.spec.columns if k in out)
 
-    def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:
+    def __iter__(self):
+        from .dataspec import BatchIterator  # (dataspec imports this module lazily, too)
+
+        return BatchIterator(self._generate())
+
+    def _generate(self) -> Iterator[Dict[str, torch.Tensor]]:
         src = self.source
         rng = np.random.Generator(np.random.PCG64([src.seed, src._epoch]))
         src._epoch += 1

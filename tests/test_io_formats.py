@@ -449,6 +449,23 @@ def test_prefetch_surfaces_parse_errors(tmp_path):
         next(it)
 
 
+def test_dataset_iterator_answers_get_next(crello_dir):
+    """eval.py:47-49 drives the dataset with ``iterator = iter(dataset)`` / ``iterator.get_next()``: same batches as ``next``; the end
+    of a non-repeating split is ``StopIteration``."""
+    root, written = crello_dir
+    spec = DataSpec("crello", root, batch_size=4)
+    for prefetch in (0, 2):
+        a = iter(spec.make_dataset("val", shuffle=False, prefetch=prefetch))
+        b = iter(spec.make_dataset("val", shuffle=False, prefetch=prefetch))
+        steps = spec.steps_per_epoch("val")
+        for _ in range(steps):
+            x, y = a.get_next(), next(b)
+            assert list(x) == list(y) and all(np.array_equal(np.asarray(x[k]), np.asarray(y[k])) for k in x)
+        with pytest.raises(StopIteration):
+            a.get_next()
+        a.close()
+
+
 def test_unbatch_undoes_lookup_and_discretisation(crello_dir):
     root, written = crello_dir
     spec = DataSpec("crello", root, batch_size=4)
