@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -427,6 +428,13 @@ int mfp_bind(mfp_engine* h, int32_t B, int32_t S, void* workspace, int64_t works
   if (!h || !workspace || !params) { set_error("mfp_bind: null argument"); return MFP_ERR_ARG; }
   if (B < 1 || S < 1) { set_error("mfp_bind: bad shape"); return MFP_ERR_ARG; }
   if (S > 384) { set_error("mfp_bind: S = %d exceeds the attention kernels' shared-memory plan (max 384)", S); return MFP_ERR_UNSUPPORTED; }
+  {  // element counts and row offsets are 32-bit inside the kernels: the widest row-major array ([T, LW] logits, [T, 768] qkv) must stay below 2^31 entries
+    const long long widest = std::max<long long>(h->sc.LW, 3LL * h->cfg.latent_dim);
+    if ((long long)B * S * widest >= (1LL << 31)) {
+      set_error("mfp_bind: B * S = %lld elements exceed 32-bit indexing of a %lld-column array; split the batch", (long long)B * S, widest);
+      return MFP_ERR_UNSUPPORTED;
+    }
+  }
   if (h->cfg.input_dtype != 0 && S > h->cfg.length_input_dim + 1) {
     set_error("mfp_bind: S = %d exceeds the PositionEmbedding table (%d rows)", S, h->cfg.length_input_dim + 1);
     return MFP_ERR_ARG;

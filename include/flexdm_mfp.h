@@ -105,7 +105,9 @@ int mfp_get_variable(const mfp_engine* h, int32_t index, mfp_variable* out);
 int32_t mfp_logit_width(const mfp_engine* h);                      /* padded row width of the logits matrix */
 int32_t mfp_field_logit_offset(const mfp_engine* h, int32_t field); /* first column of a field's head (decoder.py:96-110) */
 
-/* Workspace for a (B, S) batch shape; mfp_bind fixes the shape and all buffers (TMA descriptors are built here). */
+/* Workspace for a (B, S) batch shape; mfp_bind fixes the shape and all buffers (TMA descriptors are built here).
+ * Limits (MFP_ERR_UNSUPPORTED): S <= 384; B * S * max(logit_width, 3 * latent_dim) < 2^31 (row offsets are 32-bit in the kernels;
+ * at S = 128 that is 11 915 crello documents per step and GPU, far beyond what 180 GB of workspace holds). */
 int64_t mfp_workspace_bytes(const mfp_engine* h, int32_t B, int32_t S);
 int mfp_bind(mfp_engine* h, int32_t B, int32_t S, void* workspace, int64_t workspace_bytes,
              float* params, float* grads, float* adam_m, float* adam_v);
