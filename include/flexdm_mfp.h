@@ -107,7 +107,8 @@ int32_t mfp_field_logit_offset(const mfp_engine* h, int32_t field); /* first col
 
 /* Workspace for a (B, S) batch shape; mfp_bind fixes the shape and all buffers (TMA descriptors are built here).
  * Limits (MFP_ERR_UNSUPPORTED): S <= 384; B * S * max(logit_width, 3 * latent_dim) < 2^31 (row offsets are 32-bit in the kernels;
- * at S = 128 that is 11 915 crello documents per step and GPU, far beyond what 180 GB of workspace holds). */
+ * at S = 128 and L = 4 that is 11 915 crello documents per step and GPU, whose workspace (110 KB per element) would fill the GPU's
+ * 180 GB anyway). */
 int64_t mfp_workspace_bytes(const mfp_engine* h, int32_t B, int32_t S);
 int mfp_bind(mfp_engine* h, int32_t B, int32_t S, void* workspace, int64_t workspace_bytes,
              float* params, float* grads, float* adam_m, float* adam_v);
