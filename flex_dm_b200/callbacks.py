@@ -102,8 +102,9 @@ class GarbageCollector(Callback):
 
 
 class ScalarLogger(Callback):
-    """What the reference's TensorBoard callback records per epoch (``epoch_<name>`` scalars of the train and validation logs), as JSON
-    lines in ``<log_dir>/scalars.jsonl`` -- TensorBoard's event-file format belongs to TensorFlow and is not written here."""
+    """What the reference's TensorBoard callback records per epoch (the train and validation logs), as JSON lines in
+    ``<log_dir>/scalars.jsonl``: the dependency-free form (``TensorBoard`` below writes real event files where the ``tensorboard`` package
+    is installed)."""
 
     def __init__(self, log_dir: str):
         self.log_dir = log_dir
@@ -127,6 +128,42 @@ class ScalarLogger(Callback):
             self._file = None
 
 
+class TensorBoard(Callback):
+    """``tf.keras.callbacks.TensorBoard(log_dir, write_graph=False, profile_batch=0)`` (``helpers/callbacks.py:44-48``) at its default
+    ``update_freq="epoch"``: the epoch's logs as ``epoch_<name>`` scalars, training values into ``<log_dir>/train`` and ``val_*`` values
+    into ``<log_dir>/validation``, step = epoch.  Event files are written by the ``tensorboard`` package's own writer
+    (``torch.utils.tensorboard``); constructing the callback raises ``ImportError`` where that package is missing (``get_callbacks`` then
+    falls back to ``ScalarLogger``).  Graph and profiler output (``write_graph`` / ``profile_batch``) have no counterpart: ncu is the
+    profiler of this path."""
+
+    def __init__(self, log_dir: str = "logs", write_graph: bool = False, profile_batch=0, **_ignored):
+        from torch.utils.tensorboard import SummaryWriter  # noqa: F401  (fail at construction, not at the first epoch)
+
+        self.log_dir = log_dir
+        self._writers: Dict[str, object] = {}
+
+    def _writer(self, name: str):
+        if name not in self._writers:
+            from torch.utils.tensorboard import SummaryWriter
+
+            self._writers[name] = SummaryWriter(log_dir=os.path.join(self.log_dir, name))
+        return self._writers[name]
+
+    def on_epoch_end(self, epoch: int, logs: Optional[Dict] = None) -> None:
+        for key, value in (logs or {}).items():
+            if key.startswith("val_"):
+                self._writer("validation").add_scalar("epoch_" + key[4:], float(value), global_step=epoch)
+            else:
+                self._writer("train").add_scalar("epoch_" + key, float(value), global_step=epoch)
+        for w in self._writers.values():
+            w.flush()
+
+    def on_train_end(self, logs: Optional[Dict] = None) -> None:
+        for w in self._writers.values():
+            w.close()
+        self._writers = {}
+
+
 def get_callbacks(args, dataspec, checkpoint_path: str) -> List[Callback]:
     """``helpers/callbacks.py:36-66``: same arguments (``args.job_dir``), same list order and the same ModelCheckpoint settings."""
     log_dir = os.path.join(args.job_dir, "logs")
@@ -135,8 +172,12 @@ def get_callbacks(args, dataspec, checkpoint_path: str) -> List[Callback]:
         shutil.rmtree(log_dir)
     logger.info("checkpoint_path=%s", checkpoint_path)
     logger.info("log_dir=%s", log_dir)
+    try:
+        tensorboard: Callback = TensorBoard(log_dir=log_dir, write_graph=False, profile_batch=0)
+    except ImportError:  # no tensorboard package: keep the scalars as JSON lines
+        tensorboard = ScalarLogger(log_dir)
     checkpoint = ModelCheckpoint(checkpoint_path, save_weights_only=True, monitor="val_total_score", mode="max", save_best_only=True, verbose=1)
-    return [ScalarLogger(log_dir), checkpoint, TerminateOnNaN(), GarbageCollector()]
+    return [tensorboard, checkpoint, TerminateOnNaN(), GarbageCollector()]
 
 
 class CallbackList:

@@ -196,7 +196,7 @@ def test_fit_drives_the_reference_callback_list(tmp_path):
     import json
     from types import SimpleNamespace
 
-    from flex_dm_b200.callbacks import Callback, ModelCheckpoint, get_callbacks
+    from flex_dm_b200.callbacks import Callback, ModelCheckpoint, ScalarLogger, get_callbacks
 
     train = [{"loss": 5.0 - e, "total_score": 0.1 * e} for e in range(6)]
     val = [{"loss": 4.0, "total_score": 0.30}, {"loss": 3.0, "total_score": 0.50}, {"loss": 2.5, "total_score": 0.40}]
@@ -221,10 +221,11 @@ def test_fit_drives_the_reference_callback_list(tmp_path):
     os.makedirs(os.path.join(args.job_dir, "logs", "stale"))
     ckpt = os.path.join(args.job_dir, "checkpoints", "best.ckpt")
     cbs = get_callbacks(args, None, ckpt)
-    assert [type(c).__name__ for c in cbs] == ["ScalarLogger", "ModelCheckpoint", "TerminateOnNaN", "GarbageCollector"]
+    assert [type(c).__name__ for c in cbs] == ["TensorBoard", "ModelCheckpoint", "TerminateOnNaN", "GarbageCollector"]
+    scalars = ScalarLogger(os.path.join(args.job_dir, "logs"))  # the dependency-free logger next to it
     assert not os.path.exists(os.path.join(args.job_dir, "logs", "stale"))  # the log dir is overwritten, as in the reference
     history = model.fit(_Dataset(), steps_per_epoch=2, epochs=6, validation_data=_Dataset(), validation_steps=1, validation_freq=2,
-                        callbacks=cbs + [Spy(), lambda epoch, logs, m: seen.append((epoch, m is model))], verbose=0)
+                        callbacks=cbs + [scalars, Spy(), lambda epoch, logs, m: seen.append((epoch, m is model))], verbose=0)
     assert len(history) == 6 and [("val_loss" in h) for h in history] == [False, True] * 3
     assert model.saved == [ckpt, ckpt]  # epochs 2 (0.30) and 4 (0.50); epoch 6 (0.40) did not improve; odd epochs had nothing to monitor
     assert cbs[1].best == 0.50
@@ -232,6 +233,14 @@ def test_fit_drives_the_reference_callback_list(tmp_path):
     assert seen == [(k, True) for k in range(6)]
     lines = [json.loads(x) for x in open(os.path.join(args.job_dir, "logs", "scalars.jsonl"))]
     assert [r["epoch"] for r in lines] == list(range(6)) and lines[1]["val_total_score"] == 0.30 and "val_loss" not in lines[0]
+    # the TensorBoard callback wrote Keras' layout: epoch_<name> scalars, training under logs/train, val_* under logs/validation
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+
+    for sub, want in (("train", [(e, 5.0 - e) for e in range(6)]), ("validation", [(1, 4.0), (3, 3.0), (5, 2.5)])):
+        events = EventAccumulator(os.path.join(args.job_dir, "logs", sub))
+        events.Reload()
+        assert sorted(events.Tags()["scalars"]) == ["epoch_loss", "epoch_total_score"]
+        assert [(e.step, e.value) for e in events.Scalars("epoch_loss")] == want
     with pytest.raises(NotImplementedError):
         ModelCheckpoint(ckpt)  # save_weights_only=False: a whole-model SavedModel has no counterpart
     assert ModelCheckpoint(ckpt, save_weights_only=True, monitor="val_acc").mode == "max" and ModelCheckpoint(ckpt, save_weights_only=True).mode == "min"

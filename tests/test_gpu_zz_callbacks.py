@@ -1,7 +1,6 @@
 """train.py:79-88 with the reference's callback list on the GPU engine (collected last on purpose: the callback protocol itself is
 covered on the CPU by tests/test_api_surface.py; this is the end-to-end flow that leaves ``best.ckpt`` for eval.py:169-172)."""
 import itertools
-import json
 import os
 from types import SimpleNamespace
 
@@ -39,5 +38,9 @@ def test_fit_with_the_reference_callback_list_leaves_the_best_checkpoint(tmp_pat
     other.load_weights(ckpt)  # eval.py:169-172
     for name, w in snapshots[best_epoch].items():
         assert np.array_equal(other.get_weights()[name], w), name
-    lines = [json.loads(x) for x in open(os.path.join(args.job_dir, "logs", "scalars.jsonl"))]
-    assert [r["epoch"] for r in lines] == [0, 1, 2, 3] and lines[1]["val_total_score"] == history[1]["val_total_score"]
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+
+    events = EventAccumulator(os.path.join(args.job_dir, "logs", "validation"))
+    events.Reload()
+    got = [(e.step, e.value) for e in events.Scalars("epoch_total_score")]
+    assert [s for s, _ in got] == [1, 3] and got[0][1] == pytest.approx(history[1]["val_total_score"], rel=1e-6)
