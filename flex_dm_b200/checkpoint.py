@@ -14,7 +14,9 @@ sits above the bytes:
 * the writer: variables + object graph + the ``checkpoint`` state file Keras leaves next to the bundle.
 
 TensorFlow is not available here, so files written by TF itself could not be tested: the formats follow the published
-specifications and are pinned by round trips and by hand-assembled fixtures in ``tests/test_io_formats.py`` ("parity unpinned" in DESIGN.md).
+specifications and are pinned by round trips and by hand-assembled fixtures in ``tests/test_io_formats.py``; the object-graph message and
+the dtype numbers are also checked against the TensorFlow-authored protobuf classes inside the ``tensorboard`` package
+(``tests/test_tf_authored_pins.py``).  The bundle's table format and ``BundleEntryProto`` stay "parity unpinned" (DESIGN.md section 2).
 """
 import ctypes
 import os
