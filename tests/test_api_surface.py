@@ -311,3 +311,67 @@ def test_notebook_imports_resolve_and_merge_matches_the_oracle():
     for key in ref:
         if key not in ("id", "uuid"):
             assert torch.equal(torch.as_tensor(again[key]), torch.as_tensor(got[key])), key
+
+
+def _train_args(tmp_path, name, **over):
+    from types import SimpleNamespace
+
+    args = dict(dataset_name=name, data_dir=str(tmp_path / "data"), job_dir=str(tmp_path / "job"), batch_size=8, weights=None, latent_dim=256,
+                num_blocks=1, arch_type="oneshot", block_type="deepsvg", l2=1e-2, dropout=0.1, masking_method="random", seq_type="default",
+                context=None, input_dtype="set", learning_rate=1e-3, num_epochs=3, validation_freq=5, verbose=0, seed=4)
+    args.update(over)
+    return SimpleNamespace(**args)
+
+
+def test_train_function_drives_the_job_like_the_reference(tmp_path, monkeypatch):
+    """``training.train(args)`` (train.py:16-97) with the model replaced by a recorder: the dataset / model / fit / evaluate / save calls
+    and their arguments are the reference's, and the job directory gets args.json, logs/ and checkpoints/final.ckpt."""
+    import json
+
+    from flex_dm_b200 import training
+    from flex_dm_b200.synthetic import write_synthetic_dataset
+
+    write_synthetic_dataset(str(tmp_path / "data"), "rico", {"train": 24, "val": 8, "test": 8}, seq_len=6, shards=1, seed=5)
+    calls = []
+
+    class Recorder:
+        metrics_names = ["loss", "total_score"]
+
+        def __init__(self, input_columns, **kwargs):
+            calls.append(("init", sorted(kwargs.items()), "left" in input_columns))
+
+        def load_weights(self, path):
+            calls.append(("load", path))
+
+        def compile(self, optimizer=None, **kw):
+            calls.append(("compile", optimizer.learning_rate, optimizer.clipnorm))
+
+        def fit(self, dataset, **kw):
+            first = next(iter(dataset))
+            calls.append(("fit", {k: v for k, v in kw.items() if k not in ("validation_data", "callbacks")}, tuple(first["left"].shape[:1]),
+                          [type(c).__name__ for c in kw["callbacks"]], len(list(kw["validation_data"]))))
+
+        def evaluate(self, dataset, batch_size=None):
+            calls.append(("evaluate", len(list(dataset)), batch_size))
+            return [1.5, 0.25]
+
+        def save_weights(self, path):
+            calls.append(("save", path))
+
+    monkeypatch.setattr(training, "MFP", Recorder)
+    args = _train_args(tmp_path, "rico", weights="/some/init.ckpt")
+    results = training.train(args)
+    assert results == {"loss": 1.5, "total_score": 0.25}
+    job = args.job_dir
+    assert json.load(open(os.path.join(job, "args.json")))["masking_method"] == "random"
+    want_kwargs = sorted(dict(num_blocks=1, block_type="deepsvg", masking_method="random", seq_type="default", arch_type="oneshot", context=None,
+                              latent_dim=256, dropout=0.1, l2=1e-2, input_dtype="set", seed=4).items())
+    assert calls == [
+        ("init", want_kwargs, True),
+        ("load", "/some/init.ckpt"),
+        ("compile", 1e-3, 1.0),
+        ("fit", dict(steps_per_epoch=3, epochs=3, validation_steps=1, validation_freq=3, verbose=0), (8,),
+         ["TensorBoard", "ModelCheckpoint", "TerminateOnNaN", "GarbageCollector"], 1),
+        ("evaluate", 1, 8),
+        ("save", os.path.join(job, "checkpoints", "final.ckpt")),
+    ]
