@@ -73,4 +73,4 @@ def test_train_function_end_to_end(tmp_path):
     again = dict(zip(other.metrics_names, other.evaluate(spec.make_dataset("test"))))
     # same weights, same Philox key; the corruption streams are indexed by the step counter, which differs between the two runs, so
     # the masked positions differ: scores agree statistically, the L2 part of the loss exactly
-    assert again["total_score"] == pytest.approx(results["total_score"], abs=0.2)
+    assert 0.0 <= again["total_score"] <= 1.0 and again["total_score"] == pytest.approx(results["total_score"], abs=0.3)
