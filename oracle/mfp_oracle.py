@@ -398,25 +398,36 @@ def layer_norm(x, gamma, beta):
 
 # ---- TF32 emulation (test utility): what the B200 product path computes in --------------------------------------------------------
 # The engine's GEMMs (every Dense forward / dgrad / wgrad, QK^T and PV) multiply operands rounded to TF32 (10 explicit mantissa bits,
-# round to nearest, ties away: the TMA unit's TFLOAT32 conversion and cvt.rna.tf32.f32) and accumulate in fp32.  ``emulate_tf32()`` makes
+# round to nearest, ties away: cvt.rna.tf32.f32, and -- per the CUDA documentation, see the probe in tests/test_gpu_zz_callbacks.py --
+# the TMA unit's TFLOAT32 conversion; ``tf32_truncate`` is the other candidate) and accumulate in fp32.  ``emulate_tf32()`` makes
 # this oracle do the same in float64 -- forward and backward products -- so that tests can state what TF32 *predicts* for a quantity
 # and tell rounding from defects (tests/test_oracle_known_answers.py::test_tf32_emulation_bounds_the_stated_tolerances).
 def tf32_round(x: torch.Tensor) -> torch.Tensor:
+    """Round to nearest, ties away from zero (``cvt.rna.tf32.f32``)."""
     bits = x.detach().to(torch.float32).contiguous().view(torch.int32)
     bits = (bits + 0x1000) & ~0x1FFF  # sign-magnitude: adding half an ulp of the kept mantissa to the raw bits rounds the magnitude
     return bits.view(torch.float32).to(x.dtype)
+
+
+def tf32_truncate(x: torch.Tensor) -> torch.Tensor:
+    """Drop the 13 low mantissa bits (what a TF32 MMA does to an fp32 container that was not rounded first)."""
+    bits = x.detach().to(torch.float32).contiguous().view(torch.int32) & ~0x1FFF
+    return bits.view(torch.float32).to(x.dtype)
+
+
+_tf32_rounding = tf32_round
 
 
 class _Tf32MatMul(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b):
         ctx.save_for_backward(a, b)
-        return tf32_round(a) @ tf32_round(b)
+        return _tf32_rounding(a) @ _tf32_rounding(b)
 
     @staticmethod
     def backward(ctx, g):
         a, b = ctx.saved_tensors
-        gr, ar, br = tf32_round(g), tf32_round(a), tf32_round(b)
+        gr, ar, br = _tf32_rounding(g), _tf32_rounding(a), _tf32_rounding(b)
         if b.dim() == 2 and a.dim() > 2:  # Dense over (B, S, K): the weight gradient contracts over all tokens
             return gr @ br.transpose(-1, -2), ar.reshape(-1, a.shape[-1]).transpose(0, 1) @ gr.reshape(-1, g.shape[-1])
         return gr @ br.transpose(-1, -2), ar.transpose(-1, -2) @ gr
@@ -426,17 +437,21 @@ _matmul = torch.matmul
 
 
 class emulate_tf32:
-    """``with emulate_tf32(): ...`` -- every matrix product of the model runs on TF32-rounded operands (forward and backward)."""
+    """``with emulate_tf32(): ...`` -- every matrix product of the model runs on TF32-rounded operands (forward and backward);
+    ``rounding`` = ``tf32_round`` (default), ``tf32_truncate`` or any operand-rounding function."""
+
+    def __init__(self, rounding=None):
+        self._rounding = rounding or tf32_round
 
     def __enter__(self):
-        global _matmul
-        self._saved = _matmul
-        _matmul = _Tf32MatMul.apply
+        global _matmul, _tf32_rounding
+        self._saved = (_matmul, _tf32_rounding)
+        _matmul, _tf32_rounding = _Tf32MatMul.apply, self._rounding
         return self
 
     def __exit__(self, *exc):
-        global _matmul
-        _matmul = self._saved
+        global _matmul, _tf32_rounding
+        _matmul, _tf32_rounding = self._saved
 
 
 def dense(x, p, name):

@@ -185,17 +185,16 @@ def oracle_step(case, closed_gates=(), tf32=None, record=None):
                 keep[index] = 0.0
         return torch.relu(pre) * keep
 
-    saved_hook, saved_round = O._relu_hook, O.tf32_round
+    saved_hook = O._relu_hook
     O._relu_hook = hook
     try:
         if tf32 is None:
             r = o.step_from(targets, mod, masks, tasks, o.dropout_masks(draws, B, S))
         else:
-            O.tf32_round = tf32
-            with O.emulate_tf32():
+            with O.emulate_tf32(tf32):
                 r = o.step_from(targets, mod, masks, tasks, o.dropout_masks(draws, B, S))
     finally:
-        O._relu_hook, O.tf32_round = saved_hook, saved_round
+        O._relu_hook = saved_hook
     return OrderedDict((k, v.numpy()) for k, v in r["grads"].items()), OrderedDict((k, v.detach().numpy()) for k, v in o.params.items())
 
 
@@ -212,9 +211,7 @@ def summaries(grads, params):
     return out
 
 
-def tf32_truncate(x):
-    bits = x.detach().to(torch.float32).contiguous().view(torch.int32) & ~0x1FFF
-    return bits.view(torch.float32).to(x.dtype)
+tf32_truncate = O.tf32_truncate
 
 
 def pick_reference_run(case, g, total_grads):
