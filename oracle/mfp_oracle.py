@@ -480,14 +480,6 @@ def encoder_forward(p, inputs, input_columns, pos_keep=None, pos_rate=0.0, conte
             x = torch.where(is_unused[..., None], special[1], x)  # encoder.py:175
         seq = seq + x  # encoder.py:194-197
     pos_name = "model/encoder/input_layer/const/embeddings/embeddings"
-    if pos_name in p:  # use_pos_token (encoder.py:251-252): PositionEmbedding tiled over the batch, under its own Dropout
-        if context in ("id", "length", "canvas"):
-            # the reference prepends the token first and then adds positions 0..S to token + elements (encoder.py:247-252); that
-            # combination is not restated here (and refused by the product path, flex_dm_b200/mfp.py)
-            raise NotImplementedError("context=%r with a position embedding (input_dtype != 'set') is not restated by the oracle" % (context,))
-        B = seq.shape[0]
-        emb = p[pos_name][:S][None].expand(B, -1, -1)
-        seq = seq + dropout(emb, pos_keep, pos_rate)
     canvas = 0.0
     for key in canvas_columns(input_columns, context):  # encoder.py:156-160,182-183,198-199: embed, sum over the sub-target axis, add up
         canvas = canvas + p["model/encoder/input_layer/%s/embeddings" % key][inputs[key].to(torch.int64)].sum(dim=1)
@@ -500,6 +492,12 @@ def encoder_forward(p, inputs, input_columns, pos_keep=None, pos_rate=0.0, conte
             canvas = p["model/encoder/input_layer/%s/embeddings" % ("task" if context == "id" else "length")][ids.to(torch.int64)]
         seq = torch.cat([canvas[:, None, :], seq], dim=1)  # :247-248
         seq_mask = get_seq_mask(inputs["length"] + 1, S + 1)  # :249
+    if pos_name in p:
+        # use_pos_token (encoder.py:251-252): PositionEmbedding tiled over the batch, under its own Dropout -- added AFTER a context token
+        # was put in front, i.e. the token takes position 0 and element s position s + 1 (transformer.py:24-29 ranges over shape[1])
+        B, P = seq.shape[0], seq.shape[1]
+        emb = p[pos_name][:P][None].expand(B, -1, -1)
+        seq = seq + dropout(emb, pos_keep, pos_rate)
     return seq, seq_mask
 
 

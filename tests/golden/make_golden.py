@@ -77,11 +77,15 @@ CASES = OrderedDict([
     # sum added to every element; no token, so the batch may be full length): encoder.py:34-37,177-199,228-249, decoder.py:25-43
     ("crello_ctx_canvas", ("crello", "random", 3, 9, 2, 25, 0, [8, 1, 5], None)),
     ("crello_ctx_canvas_add", ("crello", "elem_pos_attr_img_txt", 3, 8, 2, 27, 1, [8, 1, 6], [4, 1, 6])),
+    # --context id with --input_dtype shuffled_set: the token is put in front first and the PositionEmbedding (with its dropout) is added to
+    # token + elements afterwards (encoder.py:247-252).  Oracle only: the product path refuses the combination (flex_dm_b200/mfp.py).
+    ("rico_ctx_id_shuffled", ("rico", "elem_pos_attr", 4, 9, 2, 31, 2, [8, 3, 1, 5], [0, 3, 1, 4])),
 ])
-CONTEXT = {"crello_ctx_id": "id", "rico_ctx_length": "length", "crello_ctx_canvas": "canvas", "crello_ctx_canvas_add": "canvas_add"}
+CONTEXT = {"crello_ctx_id": "id", "rico_ctx_length": "length", "crello_ctx_canvas": "canvas", "crello_ctx_canvas_add": "canvas_add",
+           "rico_ctx_id_shuffled": "id"}
 TOKEN_CONTEXTS = ("id", "length", "canvas")  # contexts that put a token into the sequence
 BLOCK_TYPE = {"crello_postln": "transformer"}
-INPUT_DTYPE = {"rico_shuffled": "shuffled_set", "crello_sorted": "sorted_set"}
+INPUT_DTYPE = {"rico_shuffled": "shuffled_set", "crello_sorted": "sorted_set", "rico_ctx_id_shuffled": "shuffled_set"}
 
 
 def block_dropout_script(draws, B, S, num_blocks, lengths=None):
@@ -92,6 +96,15 @@ def block_dropout_script(draws, B, S, num_blocks, lengths=None):
     if lengths is not None:
         keep = {k: v[:, :S] for k, v in O.context_dropout_layout(keep, torch.as_tensor(np.asarray(lengths)) - 1).items()}
     return [("dropout", keep[(i, j)].numpy()) for i in range(num_blocks) for j in (0, 1)]
+
+
+def pos_dropout_script(draws, B, S, lengths=None):
+    """Keep-mask of the PositionEmbedding's Dropout (engine row layout); with a context token gathered into the reference's order and
+    cut to its positions like the blocks' masks."""
+    keep = torch.from_numpy(draws.pos_dropout_keep((B, S, D), RATE))
+    if lengths is not None:
+        keep = O.context_dropout_layout({"pos": keep}, torch.as_tensor(np.asarray(lengths)) - 1)["pos"][:, :S]
+    return [("dropout", keep.numpy())]
 
 
 def rng_script(cols, B, S, tasks, draws, num_blocks, training, pos_dropout=False, ctx_lengths=None):
@@ -125,7 +138,7 @@ def rng_script(cols, B, S, tasks, draws, num_blocks, training, pos_dropout=False
             s.append(discard(seq[k]))
     if training:
         if pos_dropout:  # the encoder's PositionEmbedding dropout comes before the blocks'
-            s.append(("dropout", draws.pos_dropout_keep((B, S, D), RATE)))
+            s += pos_dropout_script(draws, B, S, ctx_lengths)
         s += block_dropout_script(draws, B, S, num_blocks, ctx_lengths)
     return s
 
@@ -235,7 +248,7 @@ def run_case(name, spec):
     model.reset_step_state()
     mod64 = {k: (v.to(torch.float64) if v.is_floating_point() else v) for k, v in captured["mod"].items()}
     targets64 = {k: (v.to(torch.float64) if v.is_floating_point() else v.clone()) for k, v in captured["targets"].items()}
-    tfc.rng = tfc.ScriptedRNG(([("dropout", draws.pos_dropout_keep((B, S, D), RATE))] if input_dtype != "set" else []) +
+    tfc.rng = tfc.ScriptedRNG((pos_dropout_script(draws, B, S, ctx_lengths) if input_dtype != "set" else []) +
                               block_dropout_script(draws, B, S, L, ctx_lengths))
     logits = model.model(mod64, True)
     for k, v in logits.items():

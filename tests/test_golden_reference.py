@@ -32,10 +32,15 @@ CASES = {  # name: (dataset, masking_method, num_blocks, seed, step)
     # --context canvas (token = sum of the canvas columns' embeddings) / canvas_add (that sum added to every element; no token)
     "crello_ctx_canvas": ("crello", "random", 2, 25, 0),
     "crello_ctx_canvas_add": ("crello", "elem_pos_attr_img_txt", 2, 27, 1),
+    # --context id with --input_dtype shuffled_set: positions are added after the token was put in front (encoder.py:247-252).  Pins the
+    # oracle only (ORACLE_ONLY): the product path refuses the combination (tests/test_api_surface.py)
+    "rico_ctx_id_shuffled": ("rico", "random_elem_pos_attr", 2, 31, 2),
 }
+ORACLE_ONLY = {"rico_ctx_id_shuffled"}
 BLOCK_TYPE = {"crello_postln": "transformer"}
-INPUT_DTYPE = {"rico_shuffled": "shuffled_set", "crello_sorted": "sorted_set"}
-CONTEXT = {"crello_ctx_id": "id", "rico_ctx_length": "length", "crello_ctx_canvas": "canvas", "crello_ctx_canvas_add": "canvas_add"}
+INPUT_DTYPE = {"rico_shuffled": "shuffled_set", "crello_sorted": "sorted_set", "rico_ctx_id_shuffled": "shuffled_set"}
+CONTEXT = {"crello_ctx_id": "id", "rico_ctx_length": "length", "crello_ctx_canvas": "canvas", "crello_ctx_canvas_add": "canvas_add",
+           "rico_ctx_id_shuffled": "id"}
 TOKEN_CASES = {c for c, ctx in CONTEXT.items() if ctx != "canvas_add"}  # cases whose batch keeps a free row for the context token
 
 
@@ -84,8 +89,8 @@ def test_oracle_matches_reference_python(case):
     inputs = o.to_torch(batch)
     targets, mod, masks = O.preprocess_for_train(inputs, o.input_columns, tasks, draws, input_dtype)
     if input_dtype != "set":  # the batch the reference's shuffle_inputs / sort_inputs produced (tensor_utils.py:14-76)
-        for key in o.input_columns:
-            assert np.array_equal(targets[key].numpy(), g["tgt/" + key]), key
+        for key, column in o.input_columns.items():
+            assert np.array_equal(cut(targets[key].numpy(), case) if column["is_sequence"] else targets[key].numpy(), g["tgt/" + key]), key
     # ---- masking path: bit-exact against the reference's preprocess_for_train (mfp.py:95-138)
     for key, column in o.input_columns.items():
         seq = column["is_sequence"]
@@ -345,6 +350,8 @@ _OPEN = {("crello_ctx_canvas", 0): "TF32 path: a ReLU gate of the fixture at the
 
 def _engine_cases():
     for case in CASES:
+        if case in ORACLE_ONLY:
+            continue
         for impl, name in ((1, "fp32-simt"), (0, "tf32-tcgen05")):
             marks = [pytest.mark.xfail(reason=_OPEN[(case, impl)], strict=False)] if (case, impl) in _OPEN else []
             yield pytest.param(case, impl, id="%s-%s" % (case, name), marks=marks)

@@ -268,14 +268,3 @@ def test_tf32_emulation_bounds_the_stated_tolerances():
             pv = projection_vector(name, gr.size)
             assert abs((grads_t[name] - gr).reshape(-1) @ pv) < H.GRAD_REL_L2 * scale * 4 / 2, (case, name)
         assert H.GRAD_REL_L2 / 10 < worst < H.GRAD_REL_L2 / 2, worst  # the emulation is on, and it uses a fifth to a half of the tolerance
-
-
-def test_oracle_refuses_what_it_does_not_restate():
-    """A token context together with a position embedding: the reference adds positions after prepending the token
-    (encoder.py:247-252); neither the oracle nor the product path (tests/test_api_surface.py) implements that order, and neither
-    computes something else silently."""
-    cols = make_input_columns("crello")
-    o = O.OracleMFP(cols, num_blocks=1, masking_method="random", dropout=0.0, l2=None, input_dtype="shuffled_set", context="id")
-    batch = make_synthetic_batch(cols, 2, 5, seed=0, lengths="ragged")
-    with pytest.raises(NotImplementedError):
-        o.train_step(batch, seed=1, step=0)
