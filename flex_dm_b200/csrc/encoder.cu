@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(32 * kTokPerCta) embed_fwd_kernel(const __grid
     }
   }
   if (pos.table) {  // seq += PositionEmbedding(...): row of position s, under its own dropout site when training (transformer.py:24-30)
-    const float4* row = reinterpret_cast<const float4*>(pos.table + (size_t)(t % pos.S) * kD);
+    const float4* row = reinterpret_cast<const float4*>(pos.table + (size_t)(t % pos.S + pos.shift) * kD);
     const float4 p0 = __ldg(row + lane), p1 = __ldg(row + 32 + lane);
     float va[4] = {p0.x, p0.y, p0.z, p0.w}, vb[4] = {p1.x, p1.y, p1.z, p1.w};
     if (pos.rate > 0.f) {
@@ -76,6 +76,32 @@ __global__ void __launch_bounds__(kD / 4) pos_embed_bwd_kernel(const float* __re
     acc.x += v[0]; acc.y += v[1]; acc.z += v[2]; acc.w += v[3];
   }
   reinterpret_cast<float4*>(dtable + (size_t)s * kD)[q] = acc;
+}
+
+// The same with a context token in the sequence (encoder.py:247-252: the token takes position 0, the element in row s position s + 1):
+// dtable[0] = sum of the token rows, dtable[p] = sum over documents of dh0[b, p - 1] unless that row holds the token.  grid = S + 1.
+__global__ void __launch_bounds__(kD / 4) pos_embed_bwd_ctx_kernel(const float* __restrict__ dh0, const int* __restrict__ ctx_row, int B, int S, float rate,
+                                                                   uint32_t seed, uint32_t step, float* __restrict__ dtable) {
+  pdl_wait();
+  const int p = blockIdx.x, q = threadIdx.x;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b = 0; b < B; ++b) {
+    const int tok = __ldg(ctx_row + b);
+    int row;
+    if (p == 0) {
+      if (tok >= S) continue;  // a document without room for its token
+      row = tok;
+    } else {
+      row = p - 1;
+      if (row == tok) continue;
+    }
+    const size_t t = (size_t)b * S + row;
+    const float4 g = reinterpret_cast<const float4*>(dh0 + t * kD)[q];
+    float v[4] = {g.x, g.y, g.z, g.w};
+    if (rate > 0.f) dropout4(v, (uint32_t)t * kD + 4u * q, rate, seed, step, kSitePosDropout);
+    acc.x += v[0]; acc.y += v[1]; acc.z += v[2]; acc.w += v[3];
+  }
+  reinterpret_cast<float4*>(dtable + (size_t)p * kD)[q] = acc;
 }
 
 // Backward of the above as a tensor-core contraction.  Every element selects a handful of "gradient rows" (one per
@@ -144,11 +170,18 @@ int launch_pos_embed_bwd(const float* dh0, int B, int S, float rate, uint32_t se
   return MFP_OK;
 }
 
+int launch_pos_embed_bwd_ctx(const float* dh0, const int* ctx_row, int B, int S, float rate, uint32_t seed, uint32_t step, float* dtable, cudaStream_t st) {
+  MFP_CUDA_OK(launch_pdl(pos_embed_bwd_ctx_kernel, S + 1, kD / 4, 0, st, dh0, ctx_row, B, S, rate, seed, step, dtable));
+  MFP_CUDA_OK(cudaGetLastError());
+  return MFP_OK;
+}
+
 // h0[b, length[b] + 1, :] = table[ids[b]] and ctx_row[b] = length[b] + 1.  grid = B, block = D/4.  A document that fills all S rows has
 // no room for the token (the host pads the batch by one row): it is left without one and ctx_row[b] = S (matches no row; the attention
 // kernels clamp their length to S).
 __global__ void __launch_bounds__(kD / 4) context_token_kernel(const float* __restrict__ table, int rows, const int* __restrict__ ids,
-                                                               const int* __restrict__ length, int S, float* __restrict__ h0, int* __restrict__ ctx_row) {
+                                                               const int* __restrict__ length, int S, float* __restrict__ h0, int* __restrict__ ctx_row,
+                                                               const PosEmbed pos) {
   pdl_wait();
   const int b = blockIdx.x, q = threadIdx.x;
   const int n = __ldg(length + b) + 1;
@@ -157,7 +190,14 @@ __global__ void __launch_bounds__(kD / 4) context_token_kernel(const float* __re
     return;
   }
   const int id = min(max(__ldg(ids + b), 0), rows - 1);
-  reinterpret_cast<float4*>(h0 + ((size_t)b * S + n) * kD)[q] = __ldg(reinterpret_cast<const float4*>(table + (size_t)id * kD) + q);
+  float4 tok = __ldg(reinterpret_cast<const float4*>(table + (size_t)id * kD) + q);
+  if (pos.table) {  // positions are added after the token was put in front (encoder.py:247-252): the token has position 0
+    const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos.table) + q);
+    float v[4] = {p0.x, p0.y, p0.z, p0.w};
+    if (pos.rate > 0.f) dropout4(v, (uint32_t)((size_t)b * S + n) * kD + 4u * q, pos.rate, pos.seed, pos.step, kSitePosDropout);
+    tok.x += v[0]; tok.y += v[1]; tok.z += v[2]; tok.w += v[3];
+  }
+  reinterpret_cast<float4*>(h0 + ((size_t)b * S + n) * kD)[q] = tok;
   if (q == 0) ctx_row[b] = n;
 }
 
@@ -242,8 +282,9 @@ int launch_iota(int* iota, int* zeros, int n, cudaStream_t st) {
   return MFP_OK;
 }
 
-int launch_context_token(const float* table, int rows, const int* ids, const int* length, int B, int S, float* h0, int* ctx_row, cudaStream_t st) {
-  MFP_CUDA_OK(launch_pdl(context_token_kernel, B, kD / 4, 0, st, table, rows, ids, length, S, h0, ctx_row));
+int launch_context_token(const float* table, int rows, const int* ids, const int* length, int B, int S, float* h0, int* ctx_row, cudaStream_t st,
+                         const PosEmbed& pos) {
+  MFP_CUDA_OK(launch_pdl(context_token_kernel, B, kD / 4, 0, st, table, rows, ids, length, S, h0, ctx_row, pos));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }

@@ -340,7 +340,6 @@ int mfp_create(const mfp_config* cfg, const mfp_field_desc* fields, mfp_engine**
     for (int c = 0; c < cfg->n_canvas; ++c)
       if (cfg->canvas_input_dim[c] < 1) { set_error("mfp_create: canvas column %d has no input_dim", c); return MFP_ERR_ARG; }
   }
-  if (cfg->context != 0 && cfg->input_dtype != 0) { set_error("mfp_create: context with shuffled_set / sorted_set is not supported"); return MFP_ERR_UNSUPPORTED; }
   if (cfg->block_type != 0 && cfg->block_type != 1) { set_error("mfp_create: block_type must be 0 (deepsvg) or 1 (transformer)"); return MFP_ERR_ARG; }
   mfp_engine* h = new mfp_engine();
   h->cfg = *cfg;
@@ -435,9 +434,12 @@ int mfp_bind(mfp_engine* h, int32_t B, int32_t S, void* workspace, int64_t works
       return MFP_ERR_UNSUPPORTED;
     }
   }
-  if (h->cfg.input_dtype != 0 && S > h->cfg.length_input_dim + 1) {
-    set_error("mfp_bind: S = %d exceeds the PositionEmbedding table (%d rows)", S, h->cfg.length_input_dim + 1);
-    return MFP_ERR_ARG;
+  {
+    const int positions = S + ((h->cfg.context >= 1 && h->cfg.context <= 3) ? 1 : 0);  // a context token takes position 0 (encoder.py:247-252)
+    if (h->cfg.input_dtype != 0 && positions > h->cfg.length_input_dim + 1) {
+      set_error("mfp_bind: %d positions exceed the PositionEmbedding table (%d rows)", positions, h->cfg.length_input_dim + 1);
+      return MFP_ERR_ARG;
+    }
   }
   if (h->cfg.context >= 1 && h->cfg.context <= 3 && S < 2) { set_error("mfp_bind: a context token needs S >= 2 (one row beyond the longest document)"); return MFP_ERR_ARG; }
   const Workspace w = plan_workspace(h, B, S);
@@ -535,8 +537,9 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
   const bool have_flags = sc.n_num > 0 && h->flags_for != nullptr && h->flags_for == modified->cols[first_numerical(sc)];
   h->flags_for = nullptr;
   if (!have_flags) { MFP_TRY(launch_row_flags(sc, mod, T, flags, st)); h->launches++; }
-  PosEmbed pos{nullptr, 0, 0.f, 0u, 0u};
-  if (h->pos_off >= 0) pos = PosEmbed{P + h->pos_off, h->S, drop ? h->cfg.dropout : 0.f, seed, step};
+  PosEmbed pos{nullptr, 0, 0.f, 0u, 0u, 0};
+  const bool token_ctx = h->cfg.context >= 1 && h->cfg.context <= 3;
+  if (h->pos_off >= 0) pos = PosEmbed{P + h->pos_off, h->S, drop ? h->cfg.dropout : 0.f, seed, step, token_ctx ? 1 : 0};
   MFP_TRY(launch_embed_fwd(sc, mod, flags, P, T, x, st, pos));
   h->launches += 1;
   for (int f = 0; f < sc.F; ++f) {
@@ -553,7 +556,7 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
     const int* ids = h->cfg.context == 1 ? h->ctx_ids : modified->length;
     if (!ids) { set_error("mfp_forward: context = id needs mfp_set_context_ids first"); return MFP_ERR_STATE; }
     int* ctx_row = wsp<int>(h, h->off.ctx_row);
-    MFP_TRY(launch_context_token(P + h->ctx_off, h->cfg.context_rows, ids, modified->length, h->B, h->S, x, ctx_row, st));
+    MFP_TRY(launch_context_token(P + h->ctx_off, h->cfg.context_rows, ids, modified->length, h->B, h->S, x, ctx_row, st, pos));
     h->launches++;
     attn_len = ctx_row;
   } else if (h->cfg.context >= 3) {  // canvas (the token is the sum of the canvas columns' embeddings) / canvas_add (added to every element)
@@ -565,7 +568,7 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
     if (h->cfg.context == 3) {
       int* ctx_row = wsp<int>(h, h->off.ctx_row);
       MFP_TRY(launch_iota(wsp<int>(h, h->off.iota), wsp<int>(h, h->off.zeros), h->B, st));
-      MFP_TRY(launch_context_token(vec, h->B, wsp<int>(h, h->off.iota), modified->length, h->B, h->S, x, ctx_row, st));  // "table" row b = document b's vector
+      MFP_TRY(launch_context_token(vec, h->B, wsp<int>(h, h->off.iota), modified->length, h->B, h->S, x, ctx_row, st, pos));  // "table" row b = document b's vector
       h->launches += 2;
       attn_len = ctx_row;
     } else {
@@ -844,8 +847,9 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
     for (int c = 0; c < ca.n; ++c) MFP_TRY(launch_context_token_bwd(dvec, ca.ids[c], zeros, ca.rows[c], h->B, 1, G + ca.off[c], st));
     h->launches += 1 + ca.n;
   }
-  if (h->pos_off >= 0) {  // rows >= S of the table get no gradient (G was cleared in stage 0)
-    MFP_TRY(launch_pos_embed_bwd(dx, h->B, h->S, drop ? h->cfg.dropout : 0.f, seed, step, G + h->pos_off, st));
+  if (h->pos_off >= 0) {  // rows >= S (S + 1 with a context token) of the table get no gradient (G was cleared in stage 0)
+    if (ctx_row) MFP_TRY(launch_pos_embed_bwd_ctx(dx, ctx_row, h->B, h->S, drop ? h->cfg.dropout : 0.f, seed, step, G + h->pos_off, st));
+    else MFP_TRY(launch_pos_embed_bwd(dx, h->B, h->S, drop ? h->cfg.dropout : 0.f, seed, step, G + h->pos_off, st));
     h->launches++;
   }
   return MFP_OK;

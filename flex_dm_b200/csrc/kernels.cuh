@@ -30,16 +30,21 @@ struct PosEmbed {
   int S;
   float rate;  // 0 = inference
   uint32_t seed, step;
+  int shift;   // 1 when a context token takes position 0 (encoder.py:247-252): the element in row s then has position s + 1
 };
 int launch_embed_fwd(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, const float* params, int T, float* h0, cudaStream_t st,
-                     const PosEmbed& pos = PosEmbed{nullptr, 0, 0.f, 0u, 0u});
+                     const PosEmbed& pos = PosEmbed{nullptr, 0, 0.f, 0u, 0u, 0});
 int launch_pos_embed_bwd(const float* dh0, int B, int S, float rate, uint32_t seed, uint32_t step, float* dtable /*[S][D], overwritten*/, cudaStream_t st);
+// ... with a context token (PosEmbed::shift = 1): table row 0 collects the token rows (ctx_row[b]), row p >= 1 the elements in row p - 1
+int launch_pos_embed_bwd_ctx(const float* dh0, const int* ctx_row, int B, int S, float rate, uint32_t seed, uint32_t step,
+                             float* dtable /*[S + 1][D], overwritten*/, cudaStream_t st);
 int launch_embed_onehot(const Schema& sc, const BatchPtrs& mod, const unsigned char* flags, int T, float* onehot /*[T][Rp]*/, cudaStream_t st,
                         const int* ctx_row = nullptr /*[B]: row of each document that holds the context token (all-zero one-hot row)*/, int S = 0);
 // --context id / length (encoder.py:96-110,231-249): the special token of document b sits in row ctx_row[b] = length[b] + 1 of its S rows
 // (self-attention without positions is order-free, so "after the last element" equals the reference's "prepended"); ctx_row doubles as
 // the attention kernels' length array (zero-based: covers the elements and the token).
-int launch_context_token(const float* table, int rows, const int* ids, const int* length, int B, int S, float* h0, int* ctx_row, cudaStream_t st);
+int launch_context_token(const float* table, int rows, const int* ids, const int* length, int B, int S, float* h0, int* ctx_row, cudaStream_t st,
+                         const PosEmbed& pos = PosEmbed{nullptr, 0, 0.f, 0u, 0u, 0} /*given: the token also gets position 0 of the table, under the PositionEmbedding's dropout*/);
 // --context canvas / canvas_add (encoder.py:177-199,228-230): vec[b, :] = sum over the canvas columns c of table_c[ids_c[b]]
 struct CanvasArgs {
   int n;

@@ -98,6 +98,8 @@ def init_weights(engine: Engine, seed: int = 0) -> "OrderedDict[str, np.ndarray]
 class MFP:
     """MFP trainer (mfp.py:210-347) on the B200 engine."""
 
+    allow_unverified = False  # True: accept switch combinations whose GPU parity test has not been run yet (tests only)
+
     def __init__(
         self,
         input_columns: Dict,
@@ -121,8 +123,11 @@ class MFP:
             raise ValueError("input_dtype=%r (args.py: set | shuffled_set | sorted_set)" % (input_dtype,))
         if context not in (None, "id", "length", "canvas", "canvas_add"):  # encoder.py:11 CONTEXT_NAMES
             raise AssertionError("context=%r (encoder.py:28: one of None, 'id', 'canvas', 'length', 'canvas_add')" % (context,))
-        if context is not None and input_dtype != "set":
-            raise NotImplementedError("context=%r with input_dtype=%r is not supported" % (context, input_dtype))
+        if context is not None and input_dtype != "set" and not MFP.allow_unverified:
+            # encoder.py:247-252 (positions added after the token was put in front) is implemented in the engine and pinned for the oracle
+            # by a reference-run golden, but has not run on a GPU yet: refused until the parity test has been seen to pass there
+            raise NotImplementedError("context=%r with input_dtype=%r is not verified on a GPU yet (set MFP.allow_unverified = True to try it)"
+                                      % (context, input_dtype))
         for flag, value, supported in (("seq_type", seq_type, "default"),
                                        ("use_elemwise_noise", use_elemwise_noise, False)):
             if value != supported:

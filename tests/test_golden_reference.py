@@ -32,11 +32,13 @@ CASES = {  # name: (dataset, masking_method, num_blocks, seed, step)
     # --context canvas (token = sum of the canvas columns' embeddings) / canvas_add (that sum added to every element; no token)
     "crello_ctx_canvas": ("crello", "random", 2, 25, 0),
     "crello_ctx_canvas_add": ("crello", "elem_pos_attr_img_txt", 2, 27, 1),
-    # --context id with --input_dtype shuffled_set: positions are added after the token was put in front (encoder.py:247-252).  Pins the
-    # oracle only (ORACLE_ONLY): the product path refuses the combination (tests/test_api_surface.py)
+    # --context id with --input_dtype shuffled_set: positions are added after the token was put in front (encoder.py:247-252).  The oracle
+    # is pinned by it; the engine implements it (PosEmbed::shift, pos_embed_bwd_ctx_kernel) but the code was written after the round's GPU
+    # time had run out, so the product path refuses the combination unless MFP.allow_unverified is set and the engine case below is
+    # expected-to-fail (non-strict) until it has been seen to pass on a B200
     "rico_ctx_id_shuffled": ("rico", "random_elem_pos_attr", 2, 31, 2),
 }
-ORACLE_ONLY = {"rico_ctx_id_shuffled"}
+UNVERIFIED = {"rico_ctx_id_shuffled"}
 BLOCK_TYPE = {"crello_postln": "transformer"}
 INPUT_DTYPE = {"rico_shuffled": "shuffled_set", "crello_sorted": "sorted_set", "rico_ctx_id_shuffled": "shuffled_set"}
 CONTEXT = {"crello_ctx_id": "id", "rico_ctx_length": "length", "crello_ctx_canvas": "canvas", "crello_ctx_canvas_add": "canvas_add",
@@ -350,8 +352,8 @@ _OPEN = {("crello_ctx_canvas", 0): "TF32 path: a ReLU gate of the fixture at the
 
 def _engine_cases():
     for case in CASES:
-        if case in ORACLE_ONLY:
-            continue
+        if case in UNVERIFIED:
+            continue  # run from tests/test_gpu_zz_callbacks.py, after everything else: never-run kernel code must not be able to disturb this file
         for impl, name in ((1, "fp32-simt"), (0, "tf32-tcgen05")):
             marks = [pytest.mark.xfail(reason=_OPEN[(case, impl)], strict=False)] if (case, impl) in _OPEN else []
             yield pytest.param(case, impl, id="%s-%s" % (case, name), marks=marks)
@@ -364,8 +366,12 @@ def test_engine_matches_reference_python(case, impl):
 
     g, cols, batch, method, L, seed, step = load(case)
     input_dtype = INPUT_DTYPE.get(case, "set")
-    m = MFP(cols, num_blocks=L, block_type=BLOCK_TYPE.get(case, "deepsvg"), masking_method=method, input_dtype=input_dtype, latent_dim=256,
-            dropout=RATE, l2=L2, seed=0, context=CONTEXT.get(case))
+    MFP.allow_unverified = case in UNVERIFIED
+    try:
+        m = MFP(cols, num_blocks=L, block_type=BLOCK_TYPE.get(case, "deepsvg"), masking_method=method, input_dtype=input_dtype, latent_dim=256,
+                dropout=RATE, l2=L2, seed=0, context=CONTEXT.get(case))
+    finally:
+        MFP.allow_unverified = False
     m._pad_context = False  # the golden batches already keep one free row per document (see CASES)
     params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float64, bias_scale=0.05, input_dtype=input_dtype, context=CONTEXT.get(case))
     m.set_weights({k: v.numpy().astype(np.float32) for k, v in params.items()})
@@ -383,7 +389,7 @@ def test_engine_matches_reference_python(case, impl):
         torch.cuda.synchronize()
         assert np.array_equal(perm.cpu().numpy(), g["perm"])
         for f, key in enumerate(m.keys):
-            assert np.array_equal(dcols[f].cpu().numpy(), g["tgt/" + key]), key
+            assert np.array_equal(cut(dcols[f].cpu().numpy(), case), g["tgt/" + key]), key
     eng.mask_corrupt(length, dcols, tasks, seed, step)
     torch.cuda.synchronize()
     # ---- masking: bit-exact against the reference's preprocess_for_train

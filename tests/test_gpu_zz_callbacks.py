@@ -113,3 +113,16 @@ def test_tf32_operand_rounding_of_the_product_path_is_recorded():
         assert below == 1.0 and (seen[(operand, "negative, above half")] == -above)
         rules.add((operand, rule))
     warnings.warn("TF32 operand rounding of the tcgen05 GEMM path: %s" % ", ".join("%s operand: %s" % r for r in sorted(rules)))
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["fp32-simt", "tf32-tcgen05"])
+@pytest.mark.xfail(reason="engine path written without GPU time; not yet run on a B200", strict=False)
+def test_engine_cases_not_yet_run_on_a_gpu(impl):
+    """The reference-run goldens whose engine path was written after the round's GPU time had run out (tests/test_golden_reference.py::
+    UNVERIFIED: --context id with --input_dtype shuffled_set), through the same checks as every other golden case -- collected last so that
+    never-run kernel code cannot disturb the verified tests; an XPASS here is the confirmation that lets MFP.allow_unverified go."""
+    from tests.test_golden_reference import UNVERIFIED
+    from tests.test_golden_reference import test_engine_matches_reference_python as check
+
+    for case in sorted(UNVERIFIED):
+        check(case, impl)
