@@ -62,7 +62,10 @@ typedef struct {
                         * id), 2 = "length" (of its zero-based length) joins the sequence as one more token that every element attends to and
                         * that the heads ignore.  The engine keeps the token in row length[b] + 1 of the document's S rows (attention without
                         * positions is order-free, so this equals the reference's prepended token up to summation order): every document
-                        * needs length[b] + 1 < S -- the host mirror pads the batch by one row.  Not combined with input_dtype != 0. */
+                        * needs length[b] + 1 < S -- the host mirror pads the batch by one row.  With input_dtype != 0 the reference adds the
+                        * positions after the token was put in front (encoder.py:247-252): the token takes table row 0 and the element in row s
+                        * table row s + 1 (S + 1 <= length_input_dim + 1 needed).  That combination has not run on a GPU yet;
+                        * the host mirror refuses it by default. */
   int32_t context_rows; /* rows of that embedding table: len(get_task_names(...)) for "id", input_columns["length"]["input_dim"] for "length" */
   /* context = 3 ("canvas") / 4 ("canvas_add") (encoder.py:34-37,177-199,228-249; decoder.py:25-43): the canvas-level categorical columns
    * (valid_input_columns with use_canvas: every non-sequence column but "length") are embedded (tables of input_dim + 2 rows) and
