@@ -80,12 +80,14 @@ CASES = OrderedDict([
     # --context id with --input_dtype shuffled_set: the token is put in front first and the PositionEmbedding (with its dropout) is added to
     # token + elements afterwards (encoder.py:247-252).  Oracle only: the product path refuses the combination (flex_dm_b200/mfp.py).
     ("rico_ctx_id_shuffled", ("rico", "elem_pos_attr", 4, 9, 2, 31, 2, [8, 3, 1, 5], [0, 3, 1, 4])),
+    # ... and --context length with --input_dtype sorted_set on crello (numerical fields, loss conditions)
+    ("crello_ctx_length_sorted", ("crello", "random", 3, 10, 2, 33, 1, [9, 4, 1], None)),
 ])
 CONTEXT = {"crello_ctx_id": "id", "rico_ctx_length": "length", "crello_ctx_canvas": "canvas", "crello_ctx_canvas_add": "canvas_add",
-           "rico_ctx_id_shuffled": "id"}
+           "rico_ctx_id_shuffled": "id", "crello_ctx_length_sorted": "length"}
 TOKEN_CONTEXTS = ("id", "length", "canvas")  # contexts that put a token into the sequence
 BLOCK_TYPE = {"crello_postln": "transformer"}
-INPUT_DTYPE = {"rico_shuffled": "shuffled_set", "crello_sorted": "sorted_set", "rico_ctx_id_shuffled": "shuffled_set"}
+INPUT_DTYPE = {"rico_shuffled": "shuffled_set", "crello_sorted": "sorted_set", "rico_ctx_id_shuffled": "shuffled_set", "crello_ctx_length_sorted": "sorted_set"}
 
 
 def block_dropout_script(draws, B, S, num_blocks, lengths=None):

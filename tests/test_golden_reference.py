@@ -37,12 +37,14 @@ CASES = {  # name: (dataset, masking_method, num_blocks, seed, step)
     # time had run out, so the product path refuses the combination unless MFP.allow_unverified is set and the engine case below is
     # expected-to-fail (non-strict) until it has been seen to pass on a B200
     "rico_ctx_id_shuffled": ("rico", "random_elem_pos_attr", 2, 31, 2),
+    "crello_ctx_length_sorted": ("crello", "random", 2, 33, 1),  # ... and --context length with --input_dtype sorted_set
 }
-UNVERIFIED = {"rico_ctx_id_shuffled"}
+UNVERIFIED = {"rico_ctx_id_shuffled", "crello_ctx_length_sorted"}
 BLOCK_TYPE = {"crello_postln": "transformer"}
-INPUT_DTYPE = {"rico_shuffled": "shuffled_set", "crello_sorted": "sorted_set", "rico_ctx_id_shuffled": "shuffled_set"}
+INPUT_DTYPE = {"rico_shuffled": "shuffled_set", "crello_sorted": "sorted_set", "rico_ctx_id_shuffled": "shuffled_set",
+               "crello_ctx_length_sorted": "sorted_set"}
 CONTEXT = {"crello_ctx_id": "id", "rico_ctx_length": "length", "crello_ctx_canvas": "canvas", "crello_ctx_canvas_add": "canvas_add",
-           "rico_ctx_id_shuffled": "id"}
+           "rico_ctx_id_shuffled": "id", "crello_ctx_length_sorted": "length"}
 TOKEN_CASES = {c for c, ctx in CONTEXT.items() if ctx != "canvas_add"}  # cases whose batch keeps a free row for the context token
 
 
