@@ -51,8 +51,8 @@ __global__ void __launch_bounds__(32 * kTokPerCta) embed_fwd_kernel(const __grid
     const float4 p0 = __ldg(row + lane), p1 = __ldg(row + 32 + lane);
     float va[4] = {p0.x, p0.y, p0.z, p0.w}, vb[4] = {p1.x, p1.y, p1.z, p1.w};
     if (pos.rate > 0.f) {
-      dropout4(va, (uint32_t)t * kD + 4u * lane, pos.rate, pos.seed, pos.step, kSitePosDropout);
-      dropout4(vb, (uint32_t)t * kD + 128u + 4u * lane, pos.rate, pos.seed, pos.step, kSitePosDropout);
+      dropout4(va, ((uint32_t)t + pos.row0) * kD + 4u * lane, pos.rate, pos.seed, pos.step, kSitePosDropout);
+      dropout4(vb, ((uint32_t)t + pos.row0) * kD + 128u + 4u * lane, pos.rate, pos.seed, pos.step, kSitePosDropout);
     }
     a0.x += va[0]; a0.y += va[1]; a0.z += va[2]; a0.w += va[3];
     a1.x += vb[0]; a1.y += vb[1]; a1.z += vb[2]; a1.w += vb[3];
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(32 * kTokPerCta) embed_fwd_kernel(const __grid
 
 // d(PositionEmbedding table)[s] = sum over documents of dh0[b, s] under the same dropout mask.  grid = S, block = D/4 threads.
 __global__ void __launch_bounds__(kD / 4) pos_embed_bwd_kernel(const float* __restrict__ dh0, int B, int S, float rate, uint32_t seed, uint32_t step,
-                                                               float* __restrict__ dtable) {
+                                                               float* __restrict__ dtable, uint32_t row0) {
   pdl_wait();
   const int s = blockIdx.x, q = threadIdx.x;  // float4 index within the row
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kD / 4) pos_embed_bwd_kernel(const float* __re
     const size_t t = (size_t)b * S + s;
     const float4 g = reinterpret_cast<const float4*>(dh0 + t * kD)[q];
     float v[4] = {g.x, g.y, g.z, g.w};
-    if (rate > 0.f) dropout4(v, (uint32_t)t * kD + 4u * q, rate, seed, step, kSitePosDropout);
+    if (rate > 0.f) dropout4(v, ((uint32_t)t + row0) * kD + 4u * q, rate, seed, step, kSitePosDropout);
     acc.x += v[0]; acc.y += v[1]; acc.z += v[2]; acc.w += v[3];
   }
   reinterpret_cast<float4*>(dtable + (size_t)s * kD)[q] = acc;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kD / 4) pos_embed_bwd_kernel(const float* __re
 // The same with a context token in the sequence (encoder.py:247-252: the token takes position 0, the element in row s position s + 1):
 // dtable[0] = sum of the token rows, dtable[p] = sum over documents of dh0[b, p - 1] unless that row holds the token.  grid = S + 1.
 __global__ void __launch_bounds__(kD / 4) pos_embed_bwd_ctx_kernel(const float* __restrict__ dh0, const int* __restrict__ ctx_row, int B, int S, float rate,
-                                                                   uint32_t seed, uint32_t step, float* __restrict__ dtable) {
+                                                                   uint32_t seed, uint32_t step, float* __restrict__ dtable, uint32_t row0) {
   pdl_wait();
   const int p = blockIdx.x, q = threadIdx.x;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kD / 4) pos_embed_bwd_ctx_kernel(const float* 
     const size_t t = (size_t)b * S + row;
     const float4 g = reinterpret_cast<const float4*>(dh0 + t * kD)[q];
     float v[4] = {g.x, g.y, g.z, g.w};
-    if (rate > 0.f) dropout4(v, (uint32_t)t * kD + 4u * q, rate, seed, step, kSitePosDropout);
+    if (rate > 0.f) dropout4(v, ((uint32_t)t + row0) * kD + 4u * q, rate, seed, step, kSitePosDropout);
     acc.x += v[0]; acc.y += v[1]; acc.z += v[2]; acc.w += v[3];
   }
   reinterpret_cast<float4*>(dtable + (size_t)p * kD)[q] = acc;
@@ -164,14 +164,15 @@ int launch_embed_fwd(const Schema& sc, const BatchPtrs& mod, const unsigned char
   return MFP_OK;
 }
 
-int launch_pos_embed_bwd(const float* dh0, int B, int S, float rate, uint32_t seed, uint32_t step, float* dtable, cudaStream_t st) {
-  MFP_CUDA_OK(launch_pdl(pos_embed_bwd_kernel, S, kD / 4, 0, st, dh0, B, S, rate, seed, step, dtable));
+int launch_pos_embed_bwd(const float* dh0, int B, int S, float rate, uint32_t seed, uint32_t step, float* dtable, cudaStream_t st, uint32_t row0) {
+  MFP_CUDA_OK(launch_pdl(pos_embed_bwd_kernel, S, kD / 4, 0, st, dh0, B, S, rate, seed, step, dtable, row0));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
 
-int launch_pos_embed_bwd_ctx(const float* dh0, const int* ctx_row, int B, int S, float rate, uint32_t seed, uint32_t step, float* dtable, cudaStream_t st) {
-  MFP_CUDA_OK(launch_pdl(pos_embed_bwd_ctx_kernel, S + 1, kD / 4, 0, st, dh0, ctx_row, B, S, rate, seed, step, dtable));
+int launch_pos_embed_bwd_ctx(const float* dh0, const int* ctx_row, int B, int S, float rate, uint32_t seed, uint32_t step, float* dtable, cudaStream_t st,
+                             uint32_t row0) {
+  MFP_CUDA_OK(launch_pdl(pos_embed_bwd_ctx_kernel, S + 1, kD / 4, 0, st, dh0, ctx_row, B, S, rate, seed, step, dtable, row0));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(kD / 4) context_token_kernel(const float* __re
   if (pos.table) {  // positions are added after the token was put in front (encoder.py:247-252): the token has position 0
     const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos.table) + q);
     float v[4] = {p0.x, p0.y, p0.z, p0.w};
-    if (pos.rate > 0.f) dropout4(v, (uint32_t)((size_t)b * S + n) * kD + 4u * q, pos.rate, pos.seed, pos.step, kSitePosDropout);
+    if (pos.rate > 0.f) dropout4(v, ((uint32_t)((size_t)b * S + n) + pos.row0) * kD + 4u * q, pos.rate, pos.seed, pos.step, kSitePosDropout);
     tok.x += v[0]; tok.y += v[1]; tok.z += v[2]; tok.w += v[3];
   }
   reinterpret_cast<float4*>(h0 + ((size_t)b * S + n) * kD)[q] = tok;

@@ -30,7 +30,7 @@ struct BlockLayout {
 struct Workspace {
   // byte offsets into the caller's workspace
   size_t vars, flags, perm, x, ln1, qkv, attn, xmid, ln2, hid, stats, lse, logits, dlogits, dx, dtmp, dy, dqkv, dhid, dattn, dh0m, onehot, rowgrad, part, idx_true, idx_pred,
-      norms, ctx_row, canvas_vec, dcanvas, iota, zeros, total;
+      norms, ctx_row, canvas_vec, dcanvas, iota, zeros, det, ln_part, total;
 };
 
 }  // namespace mfp
@@ -58,6 +58,8 @@ struct mfp_engine {
   std::vector<long long> stage_lo, stage_hi;  // flat-buffer range whose gradients are final after backward stage s (see mfp_backward_stages)
   const void* flags_for = nullptr;  // modified column (first numerical field) the workspace row flags were just derived from
   int gemm_impl = 0;
+  int deterministic = 0;   // mfp_set_deterministic: fixed-order gradient reductions (bit-identical steps from run to run)
+  uint32_t doc0 = 0;       // mfp_set_doc_offset: global index of the bound batch's first document (data-parallel shard)
   int64_t launches = 0;
   // optional per-kernel-class device timing (bench.py roofline): CUDA event pairs around each launch
   bool profiling = false;
@@ -233,6 +235,8 @@ static Workspace plan_workspace(const mfp_engine* h, int B, int S) {
   w.dcanvas = take((size_t)B * D * fl);
   w.iota = take((size_t)B * sizeof(int));
   w.zeros = take((size_t)B * sizeof(int));
+  w.det = take(kDetWsFloats * fl);
+  w.ln_part = take((size_t)kLnBwdMaxCtas * 2 * D * fl);
   w.total = cur;
   return w;
 }
@@ -296,9 +300,11 @@ static int gemm(mfp_engine* h, const float* A, int a_mn, int lda, const float* B
   c.splits = splits;
   c.ep = ep;
   c.colsum = (h->gemm_impl == 0) ? colsum : nullptr;
+  if (h->deterministic) { c.det_ws = wsp<float>(h, h->off.det); c.det_ws_floats = kDetWsFloats; }
   h->launches++;
+  if (h->deterministic && h->gemm_impl == 0 && (splits > 1 || colsum)) h->launches++;  // splitk_reduce_kernel
   if (colsum && h->gemm_impl != 0) {
-    MFP_TRY(launch_colsum(Bp, K, N, ldb, colsum, st));
+    MFP_TRY(launch_colsum(Bp, K, N, ldb, colsum, st, h->deterministic != 0));
     h->launches++;
   }
   // algorithmic bytes: each operand and the output once, plus the residual / ReLU-mask operand
@@ -463,7 +469,7 @@ int mfp_sample_tasks(mfp_engine* h, const int32_t* allowed_host, int32_t n_allow
   ts.n = n_allowed;
   for (int i = 0; i < n_allowed; ++i) ts.ids[i] = allowed_host[i];
   h->launches++;
-  return launch_sample_tasks(ts, h->B, seed, step, tasks_out, (cudaStream_t)stream);
+  return launch_sample_tasks(ts, h->B, seed, step, tasks_out, (cudaStream_t)stream, h->doc0);
 }
 
 int mfp_mask_corrupt(mfp_engine* h, const mfp_batch* inputs, const int32_t* tasks, uint32_t seed, uint32_t step, void* const* modified_cols,
@@ -474,7 +480,7 @@ int mfp_mask_corrupt(mfp_engine* h, const mfp_batch* inputs, const int32_t* task
   h->launches++;
   h->flags_for = h->sc.n_num > 0 ? modified_cols[first_numerical(h->sc)] : nullptr;  // the encoder's row flags come out of the same pass
   return launch_mask_corrupt(h->sc, to_batch(h, inputs), tasks, nullptr, h->B, h->S, seed, step, out, (cudaStream_t)stream,
-                             wsp<unsigned char>(h, h->off.flags));
+                             wsp<unsigned char>(h, h->off.flags), h->doc0);
 }
 
 int mfp_shuffle_inputs(mfp_engine* h, const mfp_batch* inputs, uint32_t seed, uint32_t step, void* const* shuffled_cols, int32_t* perm_out, void* stream) {
@@ -487,7 +493,7 @@ int mfp_shuffle_inputs(mfp_engine* h, const mfp_batch* inputs, uint32_t seed, ui
   }
   int* perm = wsp<int>(h, h->off.perm);
   h->launches += 2;
-  MFP_TRY(launch_shuffle_inputs(h->sc, to_batch(h, inputs), h->B, h->S, seed, step, perm, out, (cudaStream_t)stream, h->cfg.input_dtype == 2));
+  MFP_TRY(launch_shuffle_inputs(h->sc, to_batch(h, inputs), h->B, h->S, seed, step, perm, out, (cudaStream_t)stream, h->cfg.input_dtype == 2, h->doc0));
   if (perm_out) MFP_CUDA_OK(cudaMemcpyAsync(perm_out, perm, (size_t)h->T * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return MFP_OK;
 }
@@ -530,6 +536,7 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
   float* x = wsp<float>(h, h->off.x);
   const size_t TD = (size_t)T * D;
   const bool drop = training && h->cfg.dropout > 0.f;
+  const uint32_t row0 = h->doc0 * (uint32_t)h->S;  // global index of this batch's first row (dropout counters)
 
   // ---- encoder (encoder.py:147-199)
   // special-token flags of the numerical fields: already written by the mask/corrupt pass when it produced exactly these
@@ -537,9 +544,9 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
   const bool have_flags = sc.n_num > 0 && h->flags_for != nullptr && h->flags_for == modified->cols[first_numerical(sc)];
   h->flags_for = nullptr;
   if (!have_flags) { MFP_TRY(launch_row_flags(sc, mod, T, flags, st)); h->launches++; }
-  PosEmbed pos{nullptr, 0, 0.f, 0u, 0u, 0};
+  PosEmbed pos{nullptr, 0, 0.f, 0u, 0u, 0, 0u};
   const bool token_ctx = h->cfg.context >= 1 && h->cfg.context <= 3;
-  if (h->pos_off >= 0) pos = PosEmbed{P + h->pos_off, h->S, drop ? h->cfg.dropout : 0.f, seed, step, token_ctx ? 1 : 0};
+  if (h->pos_off >= 0) pos = PosEmbed{P + h->pos_off, h->S, drop ? h->cfg.dropout : 0.f, seed, step, token_ctx ? 1 : 0, h->doc0 * (uint32_t)h->S};
   MFP_TRY(launch_embed_fwd(sc, mod, flags, P, T, x, st, pos));
   h->launches += 1;
   for (int f = 0; f < sc.F; ++f) {
@@ -604,7 +611,7 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
       GemmEpilogue q2 = make_epilogue(xmid, D);
       q2.bias = P + b.bo;
       q2.residual = xi; q2.ldr = D;
-      if (drop) { q2.drop_enabled = 1; q2.drop_rate = h->cfg.dropout; q2.drop_seed = seed; q2.drop_step = step; q2.drop_site = kSiteDropout + 2 * i; }
+      if (drop) { q2.drop_enabled = 1; q2.drop_rate = h->cfg.dropout; q2.drop_seed = seed; q2.drop_step = step; q2.drop_site = kSiteDropout + 2 * i; q2.drop_row0 = row0; }
       MFP_TRY(gemm(h, attn, 0, D, P + b.wo, 1, D, T, D, D, q2, 1, st));
       MFP_TRY(launch_layernorm_fwd(xmid, P + b.g1, P + b.be1, T, ln2, stats, stats + T, st));
       GemmEpilogue q3 = make_epilogue(hid, kF);
@@ -614,7 +621,7 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
       GemmEpilogue q4 = make_epilogue(ln1, D);
       q4.bias = P + b.b2;
       q4.residual = ln2; q4.ldr = D;
-      if (drop) { q4.drop_enabled = 1; q4.drop_rate = h->cfg.dropout; q4.drop_seed = seed; q4.drop_step = step; q4.drop_site = kSiteDropout + 2 * i + 1; }
+      if (drop) { q4.drop_enabled = 1; q4.drop_rate = h->cfg.dropout; q4.drop_seed = seed; q4.drop_step = step; q4.drop_site = kSiteDropout + 2 * i + 1; q4.drop_row0 = row0; }
       MFP_TRY(gemm(h, hid, 0, kF, P + b.w2, 1, D, T, D, kF, q4, 1, st));
       MFP_TRY(launch_layernorm_fwd(ln1, P + b.g2, P + b.be2, T, xo, stats + 2 * T, stats + 3 * T, st));
       h->launches += 3;
@@ -632,7 +639,7 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
     GemmEpilogue e2 = make_epilogue(xmid, D);
     e2.bias = P + b.bo;
     e2.residual = xi; e2.ldr = D;
-    if (drop) { e2.drop_enabled = 1; e2.drop_rate = h->cfg.dropout; e2.drop_seed = seed; e2.drop_step = step; e2.drop_site = kSiteDropout + 2 * i; }
+    if (drop) { e2.drop_enabled = 1; e2.drop_rate = h->cfg.dropout; e2.drop_seed = seed; e2.drop_step = step; e2.drop_site = kSiteDropout + 2 * i; e2.drop_row0 = row0; }
     MFP_TRY(gemm(h, attn, 0, D, P + b.wo, 1, D, T, D, D, e2, 1, st));
     MFP_TRY(launch_layernorm_fwd(xmid, P + b.g2, P + b.be2, T, ln2, stats + 2 * T, stats + 3 * T, st));
     GemmEpilogue e3 = make_epilogue(hid, kF);
@@ -642,7 +649,7 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
     GemmEpilogue e4 = make_epilogue(xo, D);
     e4.bias = P + b.b2;
     e4.residual = xmid; e4.ldr = D;
-    if (drop) { e4.drop_enabled = 1; e4.drop_rate = h->cfg.dropout; e4.drop_seed = seed; e4.drop_step = step; e4.drop_site = kSiteDropout + 2 * i + 1; }
+    if (drop) { e4.drop_enabled = 1; e4.drop_rate = h->cfg.dropout; e4.drop_seed = seed; e4.drop_step = step; e4.drop_site = kSiteDropout + 2 * i + 1; e4.drop_row0 = row0; }
     MFP_TRY(gemm(h, hid, 0, kF, P + b.w2, 1, D, T, D, kF, e4, 1, st));
     h->launches += 3;
   }
@@ -700,6 +707,8 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
   float* G = h->grads;
   const size_t TD = (size_t)T * D;
   const bool drop = training && h->cfg.dropout > 0.f;
+  const uint32_t row0 = h->doc0 * (uint32_t)h->S;
+  float* ln_det = h->deterministic ? wsp<float>(h, h->off.ln_part) : nullptr;
   float* x = wsp<float>(h, h->off.x);
   // --context: the forward pass left every document's context-token row in the workspace; it is also the attention length array
   const int* ctx_row = (h->cfg.context >= 1 && h->cfg.context <= 3) ? wsp<int>(h, h->off.ctx_row) : nullptr;
@@ -738,7 +747,7 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
       const float* z2 = ln1;
       const float* x1 = ln2;
       MFP_TRY(launch_layernorm_bwd(z2, dx, P + b.g2, stats + 2 * T, stats + 3 * T, nullptr, T, dx, G + b.g2, G + b.be2, st, nullptr, 0, nullptr,
-                                   drop ? dyb : nullptr, h->cfg.dropout, seed, step, kSiteDropout + 2 * i + 1));
+                                   drop ? dyb : nullptr, h->cfg.dropout, seed, step, kSiteDropout + 2 * i + 1, row0, ln_det));
       const float* dy2 = drop ? dyb : dx;
       MFP_TRY(gemm(h, hid, 1, kF, dy2, 1, D, kF, D, T, make_epilogue(G + b.w2, D), wgrad_splits(kF, D, T), st, G + b.b2));
       GemmEpilogue ph = make_epilogue(dhid, kF);
@@ -749,7 +758,7 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
       p1.residual = dx; p1.ldr = D;
       MFP_TRY(gemm(h, dhid, 0, kF, P + b.w1, 0, kF, T, D, kF, p1, 1, st));
       MFP_TRY(launch_layernorm_bwd(xmid, dx, P + b.g1, stats, stats + T, nullptr, T, dx, G + b.g1, G + b.be1, st, nullptr, 0, nullptr,
-                                   drop ? dyb : nullptr, h->cfg.dropout, seed, step, kSiteDropout + 2 * i));
+                                   drop ? dyb : nullptr, h->cfg.dropout, seed, step, kSiteDropout + 2 * i, row0, ln_det));
       const float* dy1 = drop ? dyb : dx;
       MFP_TRY(gemm(h, attn, 1, D, dy1, 1, D, D, D, T, make_epilogue(G + b.wo, D), wgrad_splits(D, D, T), st, G + b.bo));
       MFP_TRY(gemm(h, dy1, 0, D, P + b.wo, 0, D, T, D, D, make_epilogue(dattn, D), 1, st));
@@ -776,7 +785,7 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
     const float* dy = dx;
     if (drop) {
       if (i == L - 1) {
-        MFP_TRY(launch_dropout_bwd(dx, T, h->cfg.dropout, seed, step, kSiteDropout + 2 * i + 1, dyb, st));
+        MFP_TRY(launch_dropout_bwd(dx, T, h->cfg.dropout, seed, step, kSiteDropout + 2 * i + 1, dyb, st, row0));
         h->launches++;
       }
       dy = dyb;
@@ -788,7 +797,7 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
     MFP_TRY(gemm(h, ln2, 1, D, dhid, 1, kF, D, kF, T, make_epilogue(G + b.w1, kF), wgrad_splits(D, kF, T), st, G + b.b1));
     MFP_TRY(gemm(h, dhid, 0, kF, P + b.w1, 0, kF, T, D, kF, make_epilogue(dtmp, D), 1, st));
     MFP_TRY(launch_layernorm_bwd(xmid, dtmp, P + b.g2, stats + 2 * T, stats + 3 * T, dx, T, dx, G + b.g2, G + b.be2, st, nullptr, 0, nullptr,
-                                 drop ? dyb : nullptr, h->cfg.dropout, seed, step, kSiteDropout + 2 * i));
+                                 drop ? dyb : nullptr, h->cfg.dropout, seed, step, kSiteDropout + 2 * i, row0, ln_det));
     // attention branch: xmid = x_in + drop(attn.Wo + bo)
     dy = drop ? dyb : dx;
     MFP_TRY(gemm(h, attn, 1, D, dy, 1, D, D, D, T, make_epilogue(G + b.wo, D), wgrad_splits(D, D, T), st, G + b.bo));
@@ -802,10 +811,10 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
     MFP_TRY(gemm(h, dqkv, 0, 3 * D, P + b.wqkv, 0, 3 * D, T, D, 3 * D, make_epilogue(dtmp, D), 1, st));
     if (i == 0)
       MFP_TRY(launch_layernorm_bwd(xi, dtmp, P + b.g1, stats, stats + T, dx, T, dx, G + b.g1, G + b.be1, st, wsp<unsigned char>(h, h->off.flags), sc.n_num,
-                                   sc.n_num > 0 ? wsp<float>(h, h->off.dh0m) : nullptr));
+                                   sc.n_num > 0 ? wsp<float>(h, h->off.dh0m) : nullptr, nullptr, 0.f, 0u, 0u, 0u, 0u, ln_det));
     else
       MFP_TRY(launch_layernorm_bwd(xi, dtmp, P + b.g1, stats, stats + T, dx, T, dx, G + b.g1, G + b.be1, st, nullptr, 0, nullptr, drop ? dyb : nullptr,
-                                   h->cfg.dropout, seed, step, kSiteDropout + 2 * (i - 1) + 1));
+                                   h->cfg.dropout, seed, step, kSiteDropout + 2 * (i - 1) + 1, row0, ln_det));
     h->launches += 3;
   }
   if (last_stage < L + 1) return MFP_OK;
@@ -848,8 +857,8 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
     h->launches += 1 + ca.n;
   }
   if (h->pos_off >= 0) {  // rows >= S (S + 1 with a context token) of the table get no gradient (G was cleared in stage 0)
-    if (ctx_row) MFP_TRY(launch_pos_embed_bwd_ctx(dx, ctx_row, h->B, h->S, drop ? h->cfg.dropout : 0.f, seed, step, G + h->pos_off, st));
-    else MFP_TRY(launch_pos_embed_bwd(dx, h->B, h->S, drop ? h->cfg.dropout : 0.f, seed, step, G + h->pos_off, st));
+    if (ctx_row) MFP_TRY(launch_pos_embed_bwd_ctx(dx, ctx_row, h->B, h->S, drop ? h->cfg.dropout : 0.f, seed, step, G + h->pos_off, st, row0));
+    else MFP_TRY(launch_pos_embed_bwd(dx, h->B, h->S, drop ? h->cfg.dropout : 0.f, seed, step, G + h->pos_off, st, row0));
     h->launches++;
   }
   return MFP_OK;
@@ -884,6 +893,18 @@ int64_t mfp_launch_count(const mfp_engine* h) { return h ? h->launches : 0; }
 int mfp_set_gemm_impl(mfp_engine* h, int32_t impl) {
   if (!h || impl < 0 || impl > 1) { set_error("mfp_set_gemm_impl: bad argument"); return MFP_ERR_ARG; }
   h->gemm_impl = impl;
+  return MFP_OK;
+}
+
+int mfp_set_deterministic(mfp_engine* h, int32_t on) {
+  if (!h) { set_error("mfp_set_deterministic: null engine"); return MFP_ERR_ARG; }
+  h->deterministic = on ? 1 : 0;
+  return MFP_OK;
+}
+
+int mfp_set_doc_offset(mfp_engine* h, int64_t first_document) {
+  if (!h || first_document < 0 || first_document > 0x7fffffffLL) { set_error("mfp_set_doc_offset: bad argument"); return MFP_ERR_ARG; }
+  h->doc0 = (uint32_t)first_document;
   return MFP_OK;
 }
 

@@ -29,7 +29,7 @@ __device__ __forceinline__ void epilogue_store4(float (&v)[4], int row, int col,
     v[0] = s.x > 0.0f ? v[0] : 0.0f; v[1] = s.y > 0.0f ? v[1] : 0.0f;
     v[2] = s.z > 0.0f ? v[2] : 0.0f; v[3] = s.w > 0.0f ? v[3] : 0.0f;
   }
-  if (ep.drop_enabled) dropout4(v, (uint32_t)row * (uint32_t)N + (uint32_t)col, ep.drop_rate, ep.drop_seed, ep.drop_step, ep.drop_site);
+  if (ep.drop_enabled) dropout4(v, ((uint32_t)row + ep.drop_row0) * (uint32_t)N + (uint32_t)col, ep.drop_rate, ep.drop_seed, ep.drop_step, ep.drop_site);
   if (ep.rowflag && ep.rowflag[row]) { v[0] = v[1] = v[2] = v[3] = 0.0f; }
   if (ep.residual && lead_split) {
     const float4 r = *reinterpret_cast<const float4*>(ep.residual + (size_t)row * ep.ldr + col);
@@ -68,6 +68,8 @@ struct GemmTune {
 
 struct GemmTiles {
   int tiles_m, tiles_n, splits, kb_per_split;
+  int slab_rows;  // > 0 (deterministic split-K): split s stores its tiles, without reduction, at row offset s * slab_rows of the scratch output
+  int det_colsum; // column-sum partials are stored per (split, m-tile) slot instead of atomically added
 };
 
 // AUX: the epilogue stages a residual / ReLU-mask operand (two more 4 KB chunks per epilogue warp).  Without it the 32 KB saved
@@ -287,7 +289,13 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (lane == 0) mbar_arrive(empty_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        if (active) {
+        if (tl.det_colsum) {  // slot (split, m-tile): summed in slot order by splitk_reduce_kernel (CTAs without a share store zeros)
+#pragma unroll
+          for (int i = 0; i < BN / 128; ++i) {
+            const int col = n0 + (chunk0 + 4 * i) * 32 + atom * 8 + half * 4;
+            if (col < N) *reinterpret_cast<float4*>(colsum + (size_t)(split * tl.tiles_m + mt) * N + col) = acc[i];
+          }
+        } else if (active) {
 #pragma unroll
           for (int i = 0; i < BN / 128; ++i) {
             const int col = n0 + (chunk0 + 4 * i) * 32 + atom * 8 + half * 4;
@@ -312,6 +320,7 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int m0 = (r / tl.tiles_n) * kBM, n0 = (r % tl.tiles_n) * BN;
       const int row0 = m0 + q * 32;
       const int row = row0 + lane;
+      const int out_row0 = row0 + split * tl.slab_rows;
       const bool lead_split = (split == 0);
       const bool use_aux = aux_mode != 0 && (aux_mode == 2 || lead_split);
       const int nchunks = min(BN / 32, (N - n0 + 31) / 32);
@@ -373,7 +382,7 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             v[2] = a.z > 0.0f ? v[2] : 0.0f; v[3] = a.w > 0.0f ? v[3] : 0.0f;
           }
           if constexpr (EPI & kEpiDropout)
-            dropout4(v, (uint32_t)row * (uint32_t)N + (uint32_t)(col0 + 4 * j), ep.drop_rate, ep.drop_seed, ep.drop_step, ep.drop_site);
+            dropout4(v, ((uint32_t)row + ep.drop_row0) * (uint32_t)N + (uint32_t)(col0 + 4 * j), ep.drop_rate, ep.drop_seed, ep.drop_step, ep.drop_site);
           if constexpr (EPI & kEpiRowflag) {
             if (flagged) { v[0] = v[1] = v[2] = v[3] = 0.0f; }
           }
@@ -384,7 +393,7 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
         if (lane == 0) {
           if (ep.atomic) tma_reduce_add_2d(&tmOut, epi + ob * kChunkBytes, col0, row0);
-          else tma_store_2d(&tmOut, epi + ob * kChunkBytes, col0, row0);
+          else tma_store_2d(&tmOut, epi + ob * kChunkBytes, col0, out_row0);
           tma_commit_group();
         }
         ob ^= 1;
@@ -467,6 +476,36 @@ __global__ void __launch_bounds__(256) gemm_simt(const float* __restrict__ A, in
     if (row >= M) continue;
     float v[4] = {acc[i][0], acc[i][1], acc[i][2], acc[i][3]};
     epilogue_store4(v, row, n0 + tx * 4, N, ep, blockIdx.z == 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- deterministic split-K
+// out[m, n] = sum over splits s (ascending) of part[s][m][n]; colsum[n] += sum over slots (ascending) of colpart[slot][n].
+// One thread per float4 of the output; the column sums are taken by the first CTAs.  Fixed summation order: bit-identical
+// results from run to run, whatever order the GEMM's CTAs finished in.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splits, size_t slab_floats, int M, int N, float* __restrict__ out,
+                                                            int ldo, const float* __restrict__ colpart, int slots, float* __restrict__ colsum) {
+  pdl_wait();
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index into [M, N]
+  const size_t n4 = (size_t)M * N / 4;
+  if (part && i < n4) {
+    float4 acc = reinterpret_cast<const float4*>(part)[i];
+    for (int s = 1; s < splits; ++s) {
+      const float4 v = reinterpret_cast<const float4*>(part + (size_t)s * slab_floats)[i];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const size_t e = i * 4, m = e / N, n = e - m * N;
+    *reinterpret_cast<float4*>(out + m * ldo + n) = acc;
+  }
+  if (colpart && i < (size_t)N / 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < slots; ++s) {
+      const float4 v = reinterpret_cast<const float4*>(colpart + (size_t)s * N)[i];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float4* dst = reinterpret_cast<float4*>(colsum) + i;
+    const float4 o = *dst;
+    *dst = make_float4(o.x + acc.x, o.y + acc.y, o.z + acc.z, o.w + acc.w);
   }
 }
 
@@ -631,14 +670,34 @@ static int launch_tcgen05(TensorMapCache* cache, const GemmCall& c, cudaStream_t
   tl.tiles_m = (c.M + kBM - 1) / kBM;
   tl.tiles_n = (c.N + BN - 1) / BN;
   GemmEpilogue ep = c.ep;
-  if (tl.splits > 1) ep.atomic = 1;
+  tl.slab_rows = 0;
+  tl.det_colsum = 0;
+  float* colsum = c.colsum;
+  const bool det = c.det_ws != nullptr;
+  const bool det_split = det && tl.splits > 1;
+  float* det_col = nullptr;
+  if (det_split || (det && c.colsum)) {
+    tl.slab_rows = det_split ? tl.tiles_m * kBM : 0;
+    const size_t part_floats = det_split ? (size_t)tl.splits * tl.slab_rows * c.N : 0;
+    const size_t col_floats = c.colsum ? (size_t)tl.splits * tl.tiles_m * c.N : 0;
+    if (part_floats + col_floats > c.det_ws_floats) { set_error("gemm: deterministic scratch too small (%zu > %zu floats)", part_floats + col_floats, c.det_ws_floats); return MFP_ERR_ARG; }
+    if (det_split) {
+      if (c.ep.bias || c.ep.residual || c.ep.relu || c.ep.relu_src || c.ep.drop_enabled || c.ep.rowflag) { set_error("gemm: deterministic split-K takes a plain epilogue"); return MFP_ERR_ARG; }
+      mo = cache->get(c.det_ws, c.N, (uint64_t)tl.splits * tl.slab_rows, c.N, 32, 32, kMapEpilogue);
+      if (!mo) return MFP_ERR_CUDA;
+      mx = mo;
+    }
+    if (c.colsum) { det_col = c.det_ws + part_floats; colsum = det_col; tl.det_colsum = 1; }
+  } else if (tl.splits > 1) {
+    ep.atomic = 1;
+  }
   const int num_tiles = tl.tiles_m * tl.tiles_n * tl.splits;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   static const bool trace_on = getenv("FLEXDM_GEMM_TRACE") != nullptr;  // debugging aid: prints per-role wait cycles of every launch
   static unsigned long long* trace = nullptr;
   if (trace_on && !trace) { MFP_CUDA_OK(cudaMalloc(&trace, 148 * 8 * sizeof(unsigned long long))); }
   if (trace_on) MFP_CUDA_OK(cudaMemsetAsync(trace, 0, 148 * 8 * sizeof(unsigned long long), stream));
-  MFP_CUDA_OK(launch_pdl(gemm_tf32_tcgen05<BN, EPI>, grid, kGemmThreads, L::kTotal, stream, *ma, *mb, *mo, *mx, c.M, c.N, c.K, a_mode, b_mode, tl, ep, c.colsum,
+  MFP_CUDA_OK(launch_pdl(gemm_tf32_tcgen05<BN, EPI>, grid, kGemmThreads, L::kTotal, stream, *ma, *mb, *mo, *mx, c.M, c.N, c.K, a_mode, b_mode, tl, ep, colsum,
                          tune, trace_on ? trace : nullptr));
   if (trace_on) {
     unsigned long long hbuf[148 * 8];
@@ -652,6 +711,12 @@ static int launch_tcgen05(TensorMapCache* cache, const GemmCall& c, cudaStream_t
             (double)num_tiles / grid, acc[0], acc[7], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6]);
   }
   MFP_CUDA_OK(cudaGetLastError());
+  if (det_split || det_col) {
+    const size_t n4 = det_split ? (size_t)c.M * c.N / 4 : (size_t)c.N / 4;
+    MFP_CUDA_OK(launch_pdl(splitk_reduce_kernel, (unsigned)((n4 + 255) / 256), 256, 0, stream, det_split ? (const float*)c.det_ws : (const float*)nullptr, tl.splits,
+                           (size_t)tl.slab_rows * c.N, c.M, c.N, c.ep.out, c.ep.ldo, (const float*)det_col, tl.splits * tl.tiles_m, c.colsum));
+    MFP_CUDA_OK(cudaGetLastError());
+  }
   return MFP_OK;
 }
 
@@ -660,7 +725,7 @@ int launch_gemm(TensorMapCache* cache, const GemmCall& c, int impl, cudaStream_t
   if ((c.N % 4) || (c.ep.ldo % 4)) { set_error("gemm: N and ldo must be multiples of 4 (N=%d ldo=%d)", c.N, c.ep.ldo); return MFP_ERR_ARG; }
   if (impl == 1) {
     if (c.colsum) { set_error("gemm: the SIMT bring-up kernel has no fused column sum"); return MFP_ERR_ARG; }
-    int splits = c.splits < 1 ? 1 : c.splits;
+    int splits = (c.splits < 1 || c.det_ws) ? 1 : c.splits;  // deterministic mode: no atomic accumulation over splits
     int k_per_split = ((c.K + splits - 1) / splits + 15) / 16 * 16;
     splits = (c.K + k_per_split - 1) / k_per_split;
     GemmEpilogue ep = c.ep;

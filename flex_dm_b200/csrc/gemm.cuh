@@ -34,6 +34,7 @@ struct GemmEpilogue {
   int drop_enabled;
   float drop_rate;
   uint32_t drop_seed, drop_step, drop_site;
+  uint32_t drop_row0;  // global index of row 0 (data-parallel shards): dropout counters are formed from global rows
 };
 
 inline GemmEpilogue make_epilogue(float* out, int ldo) {
@@ -49,7 +50,13 @@ struct GemmCall {
   int splits;  // split-K factor (>1 forces atomic accumulation into a zeroed/pre-filled output)
   GemmEpilogue ep;
   float* colsum;  // optional [N]: += column sums of the (MN-major) B operand over K, i.e. the bias gradient of a wgrad GEMM
+  // Deterministic reductions (mfp_set_deterministic): split-K partial tiles and the column-sum partials of every CTA go to this scratch
+  // block with plain stores and are summed in a fixed order by a second kernel, instead of TMA reduce-add / atomicAdd in arrival order.
+  float* det_ws;        // nullptr = arrival-order accumulation (the fast default)
+  size_t det_ws_floats;
 };
+
+constexpr size_t kDetWsFloats = (size_t)148 * 128 * 256 + (size_t)148 * 2048;  // one wave of 128 x 256 partial tiles + column-sum partials
 
 // TMA descriptors, cached per (pointer, geometry): building one costs a driver call.
 enum MapKind : uint32_t { kMapOperandK = 0, kMapOperandMN = 1, kMapEpilogue = 2 };

@@ -6,11 +6,11 @@
 
 namespace mfp {
 
-__global__ void sample_tasks_kernel(TaskSet allowed, int B, uint32_t seed, uint32_t step, int* __restrict__ tasks) {
+__global__ void sample_tasks_kernel(TaskSet allowed, int B, uint32_t seed, uint32_t step, uint32_t doc0, int* __restrict__ tasks) {
   pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  const U4 r = philox4x32_10((uint32_t)b, kFieldTask, 0u, 0u, seed, step);
+  const U4 r = philox4x32_10((uint32_t)b + doc0, kFieldTask, 0u, 0u, seed, step);
   tasks[b] = allowed.ids[mulhi_range(r.x, (uint32_t)allowed.n)];
 }
 
@@ -25,13 +25,14 @@ __device__ __forceinline__ float2 box_muller(uint32_t xa, uint32_t xb) {
 // mode 0: train (tasks != null), mode 1: test (test_masks given)
 __global__ void __launch_bounds__(256) mask_corrupt_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs in,
                                                            const int* __restrict__ tasks, const __grid_constant__ MaskPtrs test_masks, int mode, int B,
-                                                           int S, uint32_t seed, uint32_t step, const __grid_constant__ ModifiedPtrs out,
+                                                           int S, uint32_t seed, uint32_t step, uint32_t doc0, const __grid_constant__ ModifiedPtrs out,
                                                            unsigned char* __restrict__ flags) {
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= B * S) return;
   const int b = t / S, s = t - b * S;
+  const uint32_t gt = (uint32_t)t + doc0 * (uint32_t)S;  // global element index: the Philox counters of a sharded batch are the single-process ones
   const int n_valid = in.length[b] + 1;  // mask.py:28-29
   const bool valid = s < n_valid;
   const int type_c = sc.f[sc.type_field].C;
@@ -39,13 +40,13 @@ __global__ void __launch_bounds__(256) mask_corrupt_kernel(const __grid_constant
   const int task = (mode == 0) ? tasks[b] : -1;
   int elem_sel = -1;
   if (task == 1) {  // masking.py:98-113
-    const U4 r = philox4x32_10((uint32_t)b, kFieldElem, 0u, 0u, seed, step);
+    const U4 r = philox4x32_10((uint32_t)b + doc0, kFieldElem, 0u, 0u, seed, step);
     elem_sel = (int)(u01(r.x) * (float)n_valid);
   }
   // random_masking draws three uniforms per (element, field): lane f computes the Philox block of field f once and the field
   // loop broadcasts it (every lane recomputing every field's block was a third of this kernel's time)
   U4 rf = {0u, 0u, 0u, 0u};
-  if (task == 0 && lane < sc.F) rf = philox4x32_10((uint32_t)t, (uint32_t)lane, kStreamRandomU, 0u, seed, step);
+  if (task == 0 && lane < sc.F) rf = philox4x32_10(gt, (uint32_t)lane, kStreamRandomU, 0u, seed, step);
   for (int f = 0; f < sc.F; ++f) {
     const FieldDev fd = sc.f[f];
     // filter_padding (masking.py:24-53)
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(256) mask_corrupt_kernel(const __grid_constant
         int v = unused ? fd.input_dim + 1 : src[lane];
         if (action == 1) v = fd.input_dim;
         if (action == 2) {
-          const U4 r = philox4x32_10((uint32_t)t, (uint32_t)f, kStreamRandomCat + (uint32_t)lane, 0u, seed, step);
+          const U4 r = philox4x32_10(gt, (uint32_t)f, kStreamRandomCat + (uint32_t)lane, 0u, seed, step);
           v = (int)mulhi_range(r.x, (uint32_t)fd.input_dim);
         }
         reinterpret_cast<int*>(out.cols[f])[(size_t)t * fd.C + lane] = v;
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(256) mask_corrupt_kernel(const __grid_constant
         if (action == 1) {
           v = make_float4(kMaskValue, kMaskValue, kMaskValue, kMaskValue);
         } else if (action == 2) {
-          const U4 r = philox4x32_10((uint32_t)t, (uint32_t)f, kStreamRandomNum + (uint32_t)q, 0u, seed, step);
+          const U4 r = philox4x32_10(gt, (uint32_t)f, kStreamRandomNum + (uint32_t)q, 0u, seed, step);
           const float2 z0 = box_muller(r.x, r.y), z1 = box_muller(r.z, r.w);
           v = make_float4(z0.x * 0.1f, z0.y * 0.1f, z1.x * 0.1f, z1.y * 0.1f);  // stddev 0.1, masking.py:91
         } else if (unused) {
@@ -149,12 +150,12 @@ __global__ void __launch_bounds__(256) row_flags_kernel(const __grid_constant__ 
 
 // shuffle_inputs (tensor_utils.py:47-76): grid = documents.  perm[b][r] = source position of output position r: the valid positions
 // ordered by their Philox key (ties by position), padding in place.
-__global__ void __launch_bounds__(128) shuffle_perm_kernel(const int* __restrict__ length, int S, uint32_t seed, uint32_t step, int* __restrict__ perm) {
+__global__ void __launch_bounds__(128) shuffle_perm_kernel(const int* __restrict__ length, int S, uint32_t seed, uint32_t step, uint32_t doc0, int* __restrict__ perm) {
   pdl_wait();
   extern __shared__ uint32_t skeys[];  // [S]
   const int b = blockIdx.x;
   const int n = min(S, length[b] + 1);
-  for (int s = threadIdx.x; s < n; s += blockDim.x) skeys[s] = philox4x32_10((uint32_t)(b * S + s), kFieldShuffle, 0u, 0u, seed, step).x;
+  for (int s = threadIdx.x; s < n; s += blockDim.x) skeys[s] = philox4x32_10((uint32_t)(b * S + s) + doc0 * (uint32_t)S, kFieldShuffle, 0u, 0u, seed, step).x;
   __syncthreads();
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
     if (s >= n) { perm[b * S + s] = s; continue; }
@@ -209,9 +210,9 @@ __global__ void __launch_bounds__(256) gather_columns_kernel(const __grid_consta
 }
 
 int launch_shuffle_inputs(const Schema& sc, const BatchPtrs& in, int B, int S, uint32_t seed, uint32_t step, int* perm, const ModifiedPtrs& out,
-                          cudaStream_t st, bool sorted) {
+                          cudaStream_t st, bool sorted, uint32_t doc0) {
   if (sorted) MFP_CUDA_OK(launch_pdl(sort_perm_kernel, B, 128, S * sizeof(long long), st, sc, in, S, perm));
-  else MFP_CUDA_OK(launch_pdl(shuffle_perm_kernel, B, 128, S * sizeof(uint32_t), st, in.length, S, seed, step, perm));
+  else MFP_CUDA_OK(launch_pdl(shuffle_perm_kernel, B, 128, S * sizeof(uint32_t), st, in.length, S, seed, step, doc0, perm));
   MFP_CUDA_OK(cudaGetLastError());
   const int T = B * S;
   MFP_CUDA_OK(launch_pdl(gather_columns_kernel, (T + 7) / 8, 256, 0, st, sc, in, perm, B, S, out));
@@ -219,18 +220,18 @@ int launch_shuffle_inputs(const Schema& sc, const BatchPtrs& in, int B, int S, u
   return MFP_OK;
 }
 
-int launch_sample_tasks(const TaskSet& allowed, int B, uint32_t seed, uint32_t step, int* tasks, cudaStream_t st) {
-  MFP_CUDA_OK(launch_pdl(sample_tasks_kernel, (B + 127) / 128, 128, 0, st, allowed, B, seed, step, tasks));
+int launch_sample_tasks(const TaskSet& allowed, int B, uint32_t seed, uint32_t step, int* tasks, cudaStream_t st, uint32_t doc0) {
+  MFP_CUDA_OK(launch_pdl(sample_tasks_kernel, (B + 127) / 128, 128, 0, st, allowed, B, seed, step, doc0, tasks));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
 
 int launch_mask_corrupt(const Schema& sc, const BatchPtrs& in, const int* tasks, const MaskPtrs* test_masks, int B, int S, uint32_t seed,
-                        uint32_t step, const ModifiedPtrs& out, cudaStream_t st, unsigned char* flags) {
+                        uint32_t step, const ModifiedPtrs& out, cudaStream_t st, unsigned char* flags, uint32_t doc0) {
   MaskPtrs tm{};
   if (test_masks) tm = *test_masks;
   const int T = B * S;
-  MFP_CUDA_OK(launch_pdl(mask_corrupt_kernel, (T + 7) / 8, 256, 0, st, sc, in, tasks, tm, test_masks ? 1 : 0, B, S, seed, step, out, flags));
+  MFP_CUDA_OK(launch_pdl(mask_corrupt_kernel, (T + 7) / 8, 256, 0, st, sc, in, tasks, tm, test_masks ? 1 : 0, B, S, seed, step, doc0, out, flags));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }

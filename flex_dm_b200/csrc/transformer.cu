@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                             const unsigned char* __restrict__ rowflags, int n_masked, float* __restrict__ dx_masked,
                                                             float* __restrict__ dx_drop, float drop_rate, uint32_t drop_seed, uint32_t drop_step,
-                                                            uint32_t drop_site) {
+                                                            uint32_t drop_site, uint32_t drop_row0, float* __restrict__ det_part) {
   pdl_wait();
   __shared__ float red[2][8][kD];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -77,8 +77,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     // that no separate dropout-backward pass re-reads dx
     if (dx_drop) {
       float va[4] = {o[0], o[1], o[2], o[3]}, vb[4] = {o[4], o[5], o[6], o[7]};
-      dropout4(va, (uint32_t)t * kD + 4u * lane, drop_rate, drop_seed, drop_step, drop_site);
-      dropout4(vb, (uint32_t)t * kD + 128u + 4u * lane, drop_rate, drop_seed, drop_step, drop_site);
+      dropout4(va, ((uint32_t)t + drop_row0) * kD + 4u * lane, drop_rate, drop_seed, drop_step, drop_site);
+      dropout4(vb, ((uint32_t)t + drop_row0) * kD + 128u + 4u * lane, drop_rate, drop_seed, drop_step, drop_site);
       float4* po = reinterpret_cast<float4*>(dx_drop + (size_t)t * kD);
       po[lane] = make_float4(va[0], va[1], va[2], va[3]);
       po[32 + lane] = make_float4(vb[0], vb[1], vb[2], vb[3]);
@@ -103,8 +103,21 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   float sg = 0.f, sb = 0.f;
 #pragma unroll
   for (int w = 0; w < 8; ++w) { sg += red[0][w][c]; sb += red[1][w][c]; }
-  atomicAdd(dgamma + c, sg);
-  atomicAdd(dbeta + c, sb);
+  if (det_part) {  // deterministic mode: per-CTA partials, summed in CTA order by ln_param_reduce_kernel
+    det_part[(size_t)blockIdx.x * 2 * kD + c] = sg;
+    det_part[(size_t)blockIdx.x * 2 * kD + kD + c] = sb;
+  } else {
+    atomicAdd(dgamma + c, sg);
+    atomicAdd(dbeta + c, sb);
+  }
+}
+
+__global__ void __launch_bounds__(2 * kD) ln_param_reduce_kernel(const float* __restrict__ part, int ctas, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_wait();
+  const int c = threadIdx.x;  // [0, kD): gamma, [kD, 2 kD): beta
+  float acc = 0.f;
+  for (int b = 0; b < ctas; ++b) acc += part[(size_t)b * 2 * kD + c];
+  if (c < kD) dgamma[c] += acc; else dbeta[c - kD] += acc;
 }
 
 // ------------------------------------------------------------------------------------------------- attention core
@@ -268,13 +281,13 @@ __global__ void __launch_bounds__(kAttnThreads) attention_bwd_kernel(const float
 
 // ------------------------------------------------------------------------------------------------- small kernels
 __global__ void __launch_bounds__(256) dropout_bwd_kernel(const float* __restrict__ dx, size_t n4, float rate, uint32_t seed, uint32_t step,
-                                                          uint32_t site, float* __restrict__ dy) {
+                                                          uint32_t site, float* __restrict__ dy, uint32_t row0) {
   pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 g = reinterpret_cast<const float4*>(dx)[i];
   float v[4] = {g.x, g.y, g.z, g.w};
-  dropout4(v, (uint32_t)(i * 4), rate, seed, step, site);
+  dropout4(v, (uint32_t)(i * 4) + row0 * kD, rate, seed, step, site);
   reinterpret_cast<float4*>(dy)[i] = make_float4(v[0], v[1], v[2], v[3]);
 }
 
@@ -312,11 +325,15 @@ int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, 
 
 int launch_layernorm_bwd(const float* x, const float* dy, const float* gamma, const float* mean, const float* rstd, const float* dres, int T,
                          float* dx, float* dgamma, float* dbeta, cudaStream_t st, const unsigned char* rowflags, int n_masked, float* dx_masked,
-                         float* dx_drop, float drop_rate, uint32_t drop_seed, uint32_t drop_step, uint32_t drop_site) {
-  const int grid = min((T + 7) / 8, 148 * 4);
+                         float* dx_drop, float drop_rate, uint32_t drop_seed, uint32_t drop_step, uint32_t drop_site, uint32_t drop_row0, float* det_part) {
+  const int grid = min((T + 7) / 8, kLnBwdMaxCtas);
   MFP_CUDA_OK(launch_pdl(layernorm_bwd_kernel, grid, 256, 0, st, x, dy, gamma, mean, rstd, dres, T, dx, dgamma, dbeta, rowflags, n_masked, dx_masked, dx_drop, drop_rate,
-                                             drop_seed, drop_step, drop_site));
+                                             drop_seed, drop_step, drop_site, drop_row0, det_part));
   MFP_CUDA_OK(cudaGetLastError());
+  if (det_part) {
+    MFP_CUDA_OK(launch_pdl(ln_param_reduce_kernel, 1, 2 * kD, 0, st, (const float*)det_part, grid, dgamma, dbeta));
+    MFP_CUDA_OK(cudaGetLastError());
+  }
   return MFP_OK;
 }
 
@@ -348,9 +365,9 @@ int launch_attention_bwd(const float* qkv, const float* out, const float* lse, c
   return MFP_OK;
 }
 
-int launch_dropout_bwd(const float* dx, int T, float rate, uint32_t seed, uint32_t step, uint32_t site, float* dy, cudaStream_t st) {
+int launch_dropout_bwd(const float* dx, int T, float rate, uint32_t seed, uint32_t step, uint32_t site, float* dy, cudaStream_t st, uint32_t row0) {
   const size_t n4 = (size_t)T * kD / 4;
-  MFP_CUDA_OK(launch_pdl(dropout_bwd_kernel, (unsigned)((n4 + 255) / 256), 256, 0, st, dx, n4, rate, seed, step, site, dy));
+  MFP_CUDA_OK(launch_pdl(dropout_bwd_kernel, (unsigned)((n4 + 255) / 256), 256, 0, st, dx, n4, rate, seed, step, site, dy, row0));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
@@ -362,8 +379,8 @@ int launch_masked_copies(const float* src, const unsigned char* flags, int n_cop
   return MFP_OK;
 }
 
-int launch_colsum(const float* x, int rows, int cols, int ld, float* out, cudaStream_t st) {
-  const int chunks = min(128, (rows + 63) / 64);
+int launch_colsum(const float* x, int rows, int cols, int ld, float* out, cudaStream_t st, bool deterministic) {
+  const int chunks = deterministic ? 1 : min(128, (rows + 63) / 64);  // one chunk: no atomics between CTAs (bring-up path only)
   const int rows_per_chunk = (rows + chunks - 1) / chunks;
   MFP_CUDA_OK(launch_pdl(colsum_kernel, dim3((cols + 255) / 256, chunks), 256, 0, st, x, rows, cols, ld, rows_per_chunk, out));
   MFP_CUDA_OK(cudaGetLastError());

@@ -96,6 +96,8 @@ _SIGNATURES = {
                                             ctypes.c_void_p]),
     "mfp_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "mfp_set_gemm_impl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
+    "mfp_set_deterministic": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
+    "mfp_set_doc_offset": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
     "mfp_profile_begin": (ctypes.c_int, [ctypes.c_void_p]),
     "mfp_profile_end": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double)]),
     "mfp_debug_attention": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
@@ -418,6 +420,14 @@ class Engine:
     def set_gemm_impl(self, impl: int):
         """0 = tcgen05 TF32 (product path), 1 = fp32 SIMT bring-up GEMM (tests only)."""
         _check(self.lib, self.lib.mfp_set_gemm_impl(self.handle, int(impl)), "mfp_set_gemm_impl")
+
+    def set_deterministic(self, on: bool = True):
+        """Fixed-order gradient reductions: two runs of the same step are bit-identical (slower than the arrival-order default)."""
+        _check(self.lib, self.lib.mfp_set_deterministic(self.handle, 1 if on else 0), "mfp_set_deterministic")
+
+    def set_doc_offset(self, first_document: int):
+        """Global index of the bound batch's first document (data-parallel shard): Philox counters follow global indices."""
+        _check(self.lib, self.lib.mfp_set_doc_offset(self.handle, int(first_document)), "mfp_set_doc_offset")
 
     def launch_count(self) -> int:
         return int(self.lib.mfp_launch_count(self.handle))

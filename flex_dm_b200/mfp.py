@@ -98,8 +98,6 @@ def init_weights(engine: Engine, seed: int = 0) -> "OrderedDict[str, np.ndarray]
 class MFP:
     """MFP trainer (mfp.py:210-347) on the B200 engine."""
 
-    allow_unverified = False  # True: accept switch combinations whose GPU parity test has not been run yet (tests only)
-
     def __init__(
         self,
         input_columns: Dict,
@@ -123,11 +121,6 @@ class MFP:
             raise ValueError("input_dtype=%r (args.py: set | shuffled_set | sorted_set)" % (input_dtype,))
         if context not in (None, "id", "length", "canvas", "canvas_add"):  # encoder.py:11 CONTEXT_NAMES
             raise AssertionError("context=%r (encoder.py:28: one of None, 'id', 'canvas', 'length', 'canvas_add')" % (context,))
-        if context is not None and input_dtype != "set" and not MFP.allow_unverified:
-            # encoder.py:247-252 (positions added after the token was put in front) is implemented in the engine and pinned for the oracle
-            # by a reference-run golden, but has not run on a GPU yet: refused until the parity test has been seen to pass there
-            raise NotImplementedError("context=%r with input_dtype=%r is not verified on a GPU yet (set MFP.allow_unverified = True to try it)"
-                                      % (context, input_dtype))
         for flag, value, supported in (("seq_type", seq_type, "default"),
                                        ("use_elemwise_noise", use_elemwise_noise, False)):
             if value != supported:
@@ -160,13 +153,19 @@ class MFP:
         self._ring = None
         self._ring_pos = 0
         self._world = 1
+        self._rank = 0
         self._dist = None
         self._overlap = False
         self.history: List[Dict[str, float]] = []
         self.stop_training = False
 
     # ------------------------------------------------------------------ distributed (document-sharded DP)
-    def enable_data_parallel(self, dist_module, world_size: int, overlap: bool = False):
+    def set_deterministic(self, on: bool = True):
+        """Fixed-order gradient reductions (``mfp_set_deterministic``): identical runs give bit-identical weights, as the reference's
+        seeding intends (train.py:18-23).  Off by default: the arrival-order reductions are faster."""
+        self.engine.set_deterministic(on)
+
+    def enable_data_parallel(self, dist_module, world_size: int, overlap: bool = False, rank: Optional[int] = None):
         """Shard batches over documents; one all-reduce of the flat gradient buffer per step.
         ``overlap=True`` runs the backward in stages and starts each stage's gradient slice as soon as it is final.  Measured on
         2 x B200 it does not pay (2.713 vs 2.70 ms per step): the persistent GEMM kernels hold every SM, so the NCCL kernels only
@@ -174,6 +173,10 @@ class MFP:
         self._overlap = bool(overlap)
         self._dist = dist_module
         self._world = int(world_size)
+        # rank r holds documents [r * B_local, (r + 1) * B_local) of the global batch: the engine forms every Philox counter (task ids,
+        # mask draws, dropout) from GLOBAL document indices, so the sharded step is the single-process step (train.py:25) on the
+        # concatenated batch, not N copies of the same random pattern
+        self._rank = int(dist_module.get_rank() if rank is None else rank)
         self._stage_ranges = self.engine.backward_stage_ranges()
         broadcast_parameters(dist_module, self.engine.params, 0)  # every rank starts from rank 0's initialisation
 
@@ -237,6 +240,8 @@ class MFP:
             cols = [torch.nn.functional.pad(c, (0, 0, 0, 1)) for c in cols]
         B, S = cols[0].shape[:2]
         self.engine.bind(int(B), int(S))
+        if self._world > 1:
+            self.engine.set_doc_offset(self._rank * int(B))
         if self._ring is None:
             self._ring = torch.zeros((256, self.engine.metrics_width), dtype=torch.float32, device=self.device)
         return int(B), int(S), staged["length"].reshape(-1), cols
@@ -334,15 +339,14 @@ class MFP:
         return rows
 
     def _run_epoch(self, iterator, steps: int, train: bool, staged: bool = False) -> "OrderedDict[str, float]":
-        if steps > self._ring.shape[0] if self._ring is not None else False:
-            self._ring = torch.zeros((steps, self.engine.metrics_width), dtype=torch.float32, device=self.device)
+        # one metrics row per step of the epoch stays on the device until the epoch ends: the ring must hold them all
+        if self._ring is None or steps > self._ring.shape[0]:
+            self._ring = torch.zeros((max(256, steps), self.engine.metrics_width), dtype=torch.float32, device=self.device)
             self._ring_pos = 0
         rows = []
         for _ in range(steps):
             batch = next(iterator)
             rows.append(self.train_step(batch, staged=staged) if train else self.test_step(batch, staged=staged))
-            if len(rows) == self._ring.shape[0]:
-                break
         stacked = self._reduce_rows(torch.stack(rows)).cpu().numpy()
         per_step = [self.metrics_from_row(r) for r in stacked]
         return OrderedDict((k, float(np.mean([m[k] for m in per_step]))) for k in per_step[0])  # A15: epoch mean of add_metric values

@@ -195,6 +195,18 @@ int64_t mfp_launch_count(const mfp_engine* h);
  * independent of TF32 rounding. */
 int mfp_set_gemm_impl(mfp_engine* h, int32_t impl);
 
+/* Deterministic gradient reductions (train.py:18-23 seeds everything "for reproducibility"; Keras on one device has a fixed reduction
+ * order).  on != 0: split-K weight gradients, the fused bias-gradient column sums and the LayerNorm gamma / beta gradients are written
+ * as per-CTA partials and summed in a fixed order by a second kernel, instead of TMA reduce-add / atomicAdd in arrival order -- two
+ * runs of the same step are then bit-identical.  Off (default) is the faster arrival-order accumulation. */
+int mfp_set_deterministic(mfp_engine* h, int32_t on);
+
+/* Data-parallel shards (train.py:25 is the reference's single-process stub): index of the bound batch's first document in the GLOBAL
+ * batch.  Every Philox counter of the step (task ids mfp.py:34-43, random_masking / elem_masking draws masking.py:98-113,227-269,
+ * shuffle keys, dropout keep-masks transformer.py:218,224) is formed from global document / element indices, so rank r with
+ * first_document = r * B_local draws exactly what a single process draws for those documents.  Default 0. */
+int mfp_set_doc_offset(mfp_engine* h, int64_t first_document);
+
 /* Optional device timing of kernel classes (bench.py's roofline): between begin and end every launch of the class is
  * bracketed by CUDA events on the launching stream; end synchronises and returns the summed milliseconds, the launch
  * count and the algorithmic HBM bytes (every operand and output once) per class (host arrays of MFP_PROFILE_CLASSES

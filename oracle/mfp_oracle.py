@@ -98,26 +98,27 @@ class PhiloxDraws:
     """The B200 path's RNG contract, restated.  ``field`` is the index of the column among the
     sequence columns (``get_valid_input_columns`` order); token = b*S+s."""
 
-    def __init__(self, seed: int, step: int = 0):
-        self.seed, self.step = int(seed), int(step)
+    def __init__(self, seed: int, step: int = 0, doc_offset: int = 0):
+        # doc_offset: global index of the batch's first document (mfp_set_doc_offset): counters follow global document / element indices
+        self.seed, self.step, self.doc0 = int(seed), int(step), int(doc_offset)
 
     def tasks(self, B: int, allowed: List[int]) -> np.ndarray:
-        x0, _, _, _ = philox.philox4x32_10(np.arange(B), philox.FIELD_TASK, 0, 0, self.seed, self.step)
+        x0, _, _, _ = philox.philox4x32_10(np.arange(B) + self.doc0, philox.FIELD_TASK, 0, 0, self.seed, self.step)
         return np.asarray(allowed, dtype=np.int32)[philox.mulhi_range(x0, len(allowed))]
 
     def uniforms(self, field: int, B: int, S: int):
-        x0, x1, x2, _ = philox.philox4x32_10(np.arange(B * S), field, philox.STREAM_RANDOM_U, 0, self.seed, self.step)
+        x0, x1, x2, _ = philox.philox4x32_10(np.arange(B * S) + self.doc0 * S, field, philox.STREAM_RANDOM_U, 0, self.seed, self.step)
         return [philox.u01(x).reshape(B, S) for x in (x0, x1, x2)]
 
     def rand_cat(self, field: int, B: int, S: int, C: int, input_dim: int) -> np.ndarray:
-        t = np.arange(B * S)[:, None]
+        t = (np.arange(B * S) + self.doc0 * S)[:, None]
         c = np.arange(C)[None, :]
         x0, _, _, _ = philox.philox4x32_10(t, field, philox.STREAM_RANDOM_CAT + c, 0, self.seed, self.step)
         return philox.mulhi_range(x0, input_dim).reshape(B, S, C).astype(np.int32)
 
     def rand_num(self, field: int, B: int, S: int, C: int) -> np.ndarray:
         assert C % 4 == 0
-        t = np.arange(B * S)[:, None]
+        t = (np.arange(B * S) + self.doc0 * S)[:, None]
         q = np.arange(C // 4)[None, :]
         x0, x1, x2, x3 = philox.philox4x32_10(t, field, philox.STREAM_RANDOM_NUM + q, 0, self.seed, self.step)
         z0, z1 = philox.box_muller(x0, x1)
@@ -126,14 +127,14 @@ class PhiloxDraws:
         return (z * np.float32(0.1)).astype(np.float32)  # stddev=0.1, masking.py:91
 
     def elem_u(self, B: int) -> np.ndarray:
-        x0, _, _, _ = philox.philox4x32_10(np.arange(B), philox.FIELD_ELEM, 0, 0, self.seed, self.step)
+        x0, _, _, _ = philox.philox4x32_10(np.arange(B) + self.doc0, philox.FIELD_ELEM, 0, 0, self.seed, self.step)
         return philox.u01(x0)
 
     def shuffle_perm(self, lengths: np.ndarray, S: int) -> np.ndarray:
         """(B,S) source position of every output position: valid positions ordered by their Philox key (ties by position), padding in place."""
         B = len(lengths)
         perm = np.tile(np.arange(S, dtype=np.int64), (B, 1))
-        x0, _, _, _ = philox.philox4x32_10(np.arange(B * S), philox.FIELD_SHUFFLE, 0, 0, self.seed, self.step)
+        x0, _, _, _ = philox.philox4x32_10(np.arange(B * S) + self.doc0 * S, philox.FIELD_SHUFFLE, 0, 0, self.seed, self.step)
         keys = x0.reshape(B, S).astype(np.int64)
         for b in range(B):
             n = int(lengths[b])
@@ -141,11 +142,11 @@ class PhiloxDraws:
         return perm
 
     def pos_dropout_keep(self, shape, rate: float) -> np.ndarray:
-        return philox.dropout_keep(int(np.prod(shape)), philox.SITE_POS_DROPOUT, rate, self.seed, self.step).reshape(shape)
+        return philox.dropout_keep(int(np.prod(shape)), philox.SITE_POS_DROPOUT, rate, self.seed, self.step, self.doc0 * int(np.prod(shape[1:]))).reshape(shape)
 
     def dropout_keep(self, block: int, branch: int, shape, rate: float) -> np.ndarray:
         n = int(np.prod(shape))
-        return philox.dropout_keep(n, philox.SITE_DROPOUT + 2 * block + branch, rate, self.seed, self.step).reshape(shape)
+        return philox.dropout_keep(n, philox.SITE_DROPOUT + 2 * block + branch, rate, self.seed, self.step, self.doc0 * int(np.prod(shape[1:]))).reshape(shape)
 
 
 # ----------------------------------------------------------------------------------------------- masking.py
@@ -398,14 +399,15 @@ def layer_norm(x, gamma, beta):
 
 # ---- TF32 emulation (test utility): what the B200 product path computes in --------------------------------------------------------
 # The engine's GEMMs (every Dense forward / dgrad / wgrad, QK^T and PV) multiply operands rounded to TF32 (10 explicit mantissa bits,
-# round to nearest, ties away: cvt.rna.tf32.f32, and -- per the CUDA documentation, see the probe in tests/test_gpu_zz_callbacks.py --
-# the TMA unit's TFLOAT32 conversion; ``tf32_truncate`` is the other candidate) and accumulate in fp32.  ``emulate_tf32()`` makes
+# round to nearest, ties to even: what the TMA unit's TFLOAT32 conversion does, measured on a B200 by
+# tests/test_gpu_parity.py::test_tf32_operand_rounding_of_the_product_path; ``tf32_truncate`` is what an unrounded fp32 container
+# would get from the MMA) and accumulate in fp32.  ``emulate_tf32()`` makes
 # this oracle do the same in float64 -- forward and backward products -- so that tests can state what TF32 *predicts* for a quantity
 # and tell rounding from defects (tests/test_oracle_known_answers.py::test_tf32_emulation_bounds_the_stated_tolerances).
 def tf32_round(x: torch.Tensor) -> torch.Tensor:
-    """Round to nearest, ties away from zero (``cvt.rna.tf32.f32``)."""
+    """Round to nearest, ties to even (the measured rule of the TFLOAT32 tensor maps; ``cvt.rna`` would round ties away)."""
     bits = x.detach().to(torch.float32).contiguous().view(torch.int32)
-    bits = (bits + 0x1000) & ~0x1FFF  # sign-magnitude: adding half an ulp of the kept mantissa to the raw bits rounds the magnitude
+    bits = (bits + 0xFFF + ((bits >> 13) & 1)) & ~0x1FFF  # sign-magnitude: rounding the raw bits rounds the magnitude
     return bits.view(torch.float32).to(x.dtype)
 
 
@@ -857,10 +859,10 @@ class OracleMFP:
         reg = l2_regulariser(params, self.specs, self.l2) if self.l2 is not None else 0.0
         return data_loss + reg, data_loss, losses, scores, metrics, outputs
 
-    def train_step(self, batch, seed=0, step=0, training_dropout=True):
+    def train_step(self, batch, seed=0, step=0, training_dropout=True, doc_offset=0):
         """One Keras default train_step: sample tasks, corrupt, forward, loss (+L2), backward, clip, Adam."""
         inputs = self.to_torch(batch)
-        draws = PhiloxDraws(seed, step)
+        draws = PhiloxDraws(seed, step, doc_offset)
         B = inputs["length"].shape[0]
         tasks = torch.from_numpy(draws.tasks(B, self.allowed_tasks))
         targets, modified, masks = preprocess_for_train(inputs, self.input_columns, tasks, draws, self.input_dtype)

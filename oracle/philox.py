@@ -62,10 +62,12 @@ def box_muller(xa, xb):
     return (r * np.cos(t)).astype(np.float32), (r * np.sin(t)).astype(np.float32)
 
 
-def dropout_keep(n_elements: int, site: int, rate: float, seed: int, step: int) -> np.ndarray:
+def dropout_keep(n_elements: int, site: int, rate: float, seed: int, step: int, first_element: int = 0) -> np.ndarray:
     """Keep-mask (bool, n_elements) of one dropout site: element e uses word e&3 of
-    philox(counter=(e>>2, site, 0, 0), key=(seed, step)); keep iff u >= rate."""
+    philox(counter=(e>>2, site, 0, 0), key=(seed, step)); keep iff u >= rate.  ``first_element`` (a multiple of 4) is the global
+    index of element 0 when the rows are a shard of a larger batch (mfp_set_doc_offset)."""
+    assert first_element % 4 == 0
     n4 = (n_elements + 3) // 4
-    x = philox4x32_10(np.arange(n4), site, 0, 0, seed, step)
+    x = philox4x32_10(np.arange(n4) + first_element // 4, site, 0, 0, seed, step)
     u = u01(np.stack(x, axis=1).reshape(-1)[:n_elements])
     return u >= np.float32(rate)

@@ -75,7 +75,7 @@ CASES = OrderedDict([
     ("rico_ctx_length", ("rico", "elem_pos_attr", 4, 9, 2, 23, 1, [8, 3, 1, 5], [3, 1, 4, 3])),
     # --context canvas (token = sum of the canvas columns' embeddings; the decoder gains never-read canvas heads) and canvas_add (that
     # sum added to every element; no token, so the batch may be full length): encoder.py:34-37,177-199,228-249, decoder.py:25-43
-    ("crello_ctx_canvas", ("crello", "random", 3, 9, 2, 25, 0, [8, 1, 5], None)),
+    ("crello_ctx_canvas", ("crello", "random", 3, 9, 2, 49, 0, [8, 1, 5], None)),
     ("crello_ctx_canvas_add", ("crello", "elem_pos_attr_img_txt", 3, 8, 2, 27, 1, [8, 1, 6], [4, 1, 6])),
     # --context id with --input_dtype shuffled_set: the token is put in front first and the PositionEmbedding (with its dropout) is added to
     # token + elements afterwards (encoder.py:247-252).  Oracle only: the product path refuses the combination (flex_dm_b200/mfp.py).

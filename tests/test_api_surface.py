@@ -13,8 +13,7 @@ from oracle import mfp_oracle as O
 from tests import helpers as H
 
 
-@pytest.mark.parametrize("kwargs", [{"context": "id", "input_dtype": "shuffled_set"}, {"context": "canvas", "input_dtype": "sorted_set"},
-                                    {"seq_type": "flat"}, {"use_elemwise_noise": True}])
+@pytest.mark.parametrize("kwargs", [{"seq_type": "flat"}, {"use_elemwise_noise": True}])
 def test_unsupported_switches_raise_instead_of_being_ignored(kwargs):
     from flex_dm_b200.mfp import MFP
 

@@ -30,16 +30,13 @@ CASES = {  # name: (dataset, masking_method, num_blocks, seed, step)
     "crello_ctx_id": ("crello", "elem_pos_attr_img_txt", 2, 21, 2),
     "rico_ctx_length": ("rico", "elem_pos_attr", 2, 23, 1),
     # --context canvas (token = sum of the canvas columns' embeddings) / canvas_add (that sum added to every element; no token)
-    "crello_ctx_canvas": ("crello", "random", 2, 25, 0),
+    "crello_ctx_canvas": ("crello", "random", 2, 49, 0),
     "crello_ctx_canvas_add": ("crello", "elem_pos_attr_img_txt", 2, 27, 1),
-    # --context id with --input_dtype shuffled_set: positions are added after the token was put in front (encoder.py:247-252).  The oracle
-    # is pinned by it; the engine implements it (PosEmbed::shift, pos_embed_bwd_ctx_kernel) but the code was written after the round's GPU
-    # time had run out, so the product path refuses the combination unless MFP.allow_unverified is set and the engine case below is
-    # expected-to-fail (non-strict) until it has been seen to pass on a B200
+    # --context id with --input_dtype shuffled_set: positions are added after the token was put in front (encoder.py:247-252; engine:
+    # PosEmbed::shift, pos_embed_bwd_ctx_kernel)
     "rico_ctx_id_shuffled": ("rico", "random_elem_pos_attr", 2, 31, 2),
     "crello_ctx_length_sorted": ("crello", "random", 2, 33, 1),  # ... and --context length with --input_dtype sorted_set
 }
-UNVERIFIED = {"rico_ctx_id_shuffled", "crello_ctx_length_sorted"}
 BLOCK_TYPE = {"crello_postln": "transformer"}
 INPUT_DTYPE = {"rico_shuffled": "shuffled_set", "crello_sorted": "sorted_set", "rico_ctx_id_shuffled": "shuffled_set",
                "crello_ctx_length_sorted": "sorted_set"}
@@ -160,17 +157,10 @@ def test_oracle_merge_matches_reference_python(case):
             assert np.array_equal(got, ref), key
 
 
-# ================================================================================================= a ReLU gate at the rounding edge
-# The ``crello_ctx_canvas`` fixture holds ONE FFN pre-activation of the last block -- document 0, oracle row 8, unit 369: +5.7e-4 where
-# the layer's pre-activations have rms 0.83 -- that lies inside the error TF32 operand rounding puts on that GEMM (up to 2.7e-3 with
-# round-to-nearest, 4.4e-3 with truncation).  Its row carries a large share of the loss gradient (``random`` masking leaves few rows with
-# masked fields), so whether that single gate is open decides 10.8 % of the L2 norm and 0.265 of the +-1 projection of
-# d loss / d blocks/seq2seq_1/mlp/layer_with_weights-0/kernel.  Both outcomes are correct TF32 results; the float64 reference run (the
-# golden file) and the fp32 engine path see the gate open.
-EDGE_GATES = {"crello_ctx_canvas": [(1, (0, 8, 369))]}  # case: [(block, (document, oracle row, FFN unit))]
-EDGE_VARIABLE = "model/blocks/seq2seq/seq2seq_1/mlp/layer_with_weights-0/kernel"
-
-
+# ================================================================================================= oracle runs with hooks
+# (tools/tf32_gate_scan.py uses these to check that no fixture hinges on a single ReLU gate inside TF32's rounding error: round 1's
+# --context canvas fixture did -- one gate carried 10.8 % of a gradient's norm and either side is a correct TF32 result -- and was
+# regenerated with another seed instead of teaching the test to accept two answers.)
 def oracle_step(case, closed_gates=(), tf32=None, record=None):
     """The oracle's train step on a fixture -> (grads dict of numpy, params after Adam); ``closed_gates`` forces single ReLU gates of the
     FFNs shut, ``tf32`` = an operand-rounding function to run every matrix product in emulated TF32, ``record`` = dict that receives
@@ -223,19 +213,6 @@ def summaries(grads, params):
 tf32_truncate = O.tf32_truncate
 
 
-def pick_reference_run(case, g, total_grads):
-    """The reference run a TF32 result of ``case`` belongs to: the golden file (every gate as in float64) or, for a fixture with a gate at
-    the rounding edge, the oracle's run with that gate shut -- decided by the one variable the gate dominates (whichever projection the
-    result is nearer to), then applied to every variable and to the Adam step.  Returns a golden-file-like mapping."""
-    if case not in EDGE_GATES:
-        return g
-    closed = summaries(*oracle_step(case, closed_gates=EDGE_GATES[case]))
-    proj = total_grads[EDGE_VARIABLE] @ projection_vector(EDGE_VARIABLE, total_grads[EDGE_VARIABLE].size)
-    if abs(proj - closed["gradproj/" + EDGE_VARIABLE]) < abs(proj - float(g["gradproj/" + EDGE_VARIABLE])):
-        return {**{k: g[k] for k in g.files}, **closed}
-    return g
-
-
 def check_gradient_summaries(total_grads, g, grad_tol):
     """Gradients of the total loss (data + L2), flat float64 per variable, against the summaries of a reference run."""
     for name, gg in total_grads.items():
@@ -263,46 +240,6 @@ def check_adam_heads(new_weights, g, impl):
         assert diff.max() <= 2.0 * LR + 5e-6, name
 
 
-def test_relu_gate_at_the_tf32_rounding_edge():
-    """The evidence behind ``EDGE_GATES``, all on the CPU: the gate's pre-activation is smaller than TF32's error on
-    it; closing that one gate reproduces the deviation the TF32 engine path showed on the GPU (projection off by 0.27 of the gradient's
-    norm; bound 0.20); and a TF32 emulation lands on either side depending on the rounding mode -- round-to-nearest keeps the gate open
-    and agrees with the golden gradient, truncation closes it and agrees with the closed-gate gradient."""
-    case = "crello_ctx_canvas"
-    (block, index), = EDGE_GATES[case]
-    g = np.load(os.path.join(GOLDEN, case + ".npz"))
-    pv = projection_vector(EDGE_VARIABLE, 256 * 512)
-    pre, pre_rna, pre_rz = {}, {}, {}
-    exact, exact_params = oracle_step(case, record=pre)
-    scale = np.linalg.norm(exact[EDGE_VARIABLE])
-    for key, value in summaries(exact, exact_params).items():  # the gate-open run is the one the golden file pins, summarised the same way
-        assert np.allclose(value, g[key], rtol=1e-8, atol=1e-10 * max(scale, 1.0)), key
-
-    def deviation(a, b):
-        d = (a[EDGE_VARIABLE] - b[EDGE_VARIABLE]).reshape(-1)
-        return np.linalg.norm(d) / scale, abs(d @ pv) / scale
-
-    rna, _ = oracle_step(case, tf32=O.tf32_round, record=pre_rna)
-    rz, _ = oracle_step(case, tf32=tf32_truncate, record=pre_rz)
-    value = float(pre[block][index])
-    assert 0.0 < value < 1e-3 and float(pre[block].pow(2).mean().sqrt()) > 0.5  # +5.7e-4 against rms 0.83
-    assert float((pre_rna[block] - pre[block]).abs().max()) > 2.0 * value  # the layer's TF32 error is several times the gate's margin
-    assert float(pre_rna[block][index]) > 0.0 > float(pre_rz[block][index])  # open under round-to-nearest, shut under truncation
-    closed, closed_params = oracle_step(case, closed_gates=EDGE_GATES[case])
-    l2, proj = deviation(closed, exact)
-    assert l2 == pytest.approx(0.1076, abs=2e-3) and proj == pytest.approx(0.265, abs=5e-3)  # the GPU observation: 0.27
-    assert proj > 4 * H.GRAD_REL_L2  # ... which is over the golden check's bound, hence the dual reference in the GPU test
-    assert max(deviation(rna, exact)) < 1e-2 and max(deviation(rz, closed)) < 1e-2
-    # every other gate that truncation flips sits on a row without masked fields (no gradient reaches it): the closed-gate run differs
-    # from the truncation run by rounding only, for every variable
-    for name in exact:
-        if not name.endswith("dense_key/bias"):
-            d = np.linalg.norm(rz[name] - closed[name]) / max(np.linalg.norm(closed[name]), 1e-9)
-            assert d < H.GRAD_REL_L2, (name, d)
-    shut = summaries(closed, closed_params)
-    assert abs(shut["gradproj/" + EDGE_VARIABLE] - float(g["gradproj/" + EDGE_VARIABLE])) / scale == pytest.approx(proj)
-
-
 def _flat(d):
     return OrderedDict((k, np.asarray(v, dtype=np.float64).reshape(-1)) for k, v in d.items())
 
@@ -313,52 +250,25 @@ def test_engine_checks_accept_the_oracle_run(case):
     fp32-path tolerances against every golden file (so a failure on the GPU is the engine's, not the helpers')."""
     g = np.load(os.path.join(GOLDEN, case + ".npz"))
     grads, params = oracle_step(case)
-    assert pick_reference_run(case, g, _flat(grads)) is g  # float64 gates are the golden file's
     check_gradient_summaries(_flat(grads), g, H.F32_GRAD_REL_L2)
     check_adam_heads(_flat(params), g, 1)
 
 
-def test_engine_checks_follow_the_gate_of_a_tf32_run():
-    """... and on the edge fixture a TF32-emulated run is held to the reference run on its side of the gate: round-to-nearest to the
-    golden file, truncation to the closed-gate oracle run -- each passes the product path's tolerances there and fails against the
-    other run."""
-    case = "crello_ctx_canvas"
-    g = np.load(os.path.join(GOLDEN, case + ".npz"))
-    rna, rna_params = oracle_step(case, tf32=O.tf32_round)
-    rz, rz_params = oracle_step(case, tf32=tf32_truncate)
-    assert pick_reference_run(case, g, _flat(rna)) is g
-    check_gradient_summaries(_flat(rna), g, H.GRAD_REL_L2)
-    check_adam_heads(_flat(rna_params), g, 0)
-    ref = pick_reference_run(case, g, _flat(rz))
-    assert ref is not g and float(ref["data_loss"]) == float(g["data_loss"])  # everything but the gradient summaries stays the golden file's
-    check_gradient_summaries(_flat(rz), ref, H.GRAD_REL_L2)
-    check_adam_heads(_flat(rz_params), ref, 0)
-    with pytest.raises(AssertionError):
-        check_gradient_summaries(_flat(rz), g, H.GRAD_REL_L2)
-    with pytest.raises(AssertionError):
-        check_gradient_summaries(_flat(rna), ref, H.GRAD_REL_L2)
+def test_engine_checks_accept_a_tf32_emulated_run():
+    """... and the oracle's TF32 emulation (round-to-nearest-even operands, the rule measured on the tcgen05 path by
+    tests/test_gpu_parity.py::test_tf32_operand_rounding_of_the_product_path) passes them at the product path's tolerances."""
+    for case in ("crello_ctx_canvas", "crello_postln"):
+        g = np.load(os.path.join(GOLDEN, case + ".npz"))
+        rna, rna_params = oracle_step(case, tf32=O.tf32_round)
+        check_gradient_summaries(_flat(rna), g, H.GRAD_REL_L2)
+        check_adam_heads(_flat(rna_params), g, 0)
 
 
 # ================================================================================================= GPU (C ABI)
-# Open item (DESIGN.md section 7, --context canvas): on the TF32 product path the +-1 projection of ONE gradient of this case (the last
-# block's first FFN kernel) was measured 0.27 of the gradient's norm off the golden value (bound: 0.20) while masks, logits, losses and
-# every gradient checked before it were within tolerance and the fp32 path passed the whole case.  Traced on the CPU after the round's GPU
-# budget had ended (test_relu_gate_at_the_tf32_rounding_edge above): one ReLU gate of the fixture lies inside TF32's rounding error and
-# closing it moves exactly that projection by 0.265.  The test below therefore compares the TF32 path with whichever of the two oracle
-# runs -- gate open (the golden file) or gate shut (the oracle, run here) -- the engine's gradient of that variable is nearer to, and
-# holds EVERY variable to that one run.  That comparison has not run on a GPU yet, so the case keeps its non-strict expected-to-fail
-# mark until it has been seen to pass there (an XPASS in the round-end GPU run is that confirmation).
-_OPEN = {("crello_ctx_canvas", 0): "TF32 path: a ReLU gate of the fixture at the rounding edge (0.27 vs bound 0.20 against the golden run); "
-                                   "dual-reference comparison not yet confirmed on a GPU"}
-
-
 def _engine_cases():
     for case in CASES:
-        if case in UNVERIFIED:
-            continue  # run from tests/test_gpu_zz_callbacks.py, after everything else: never-run kernel code must not be able to disturb this file
         for impl, name in ((1, "fp32-simt"), (0, "tf32-tcgen05")):
-            marks = [pytest.mark.xfail(reason=_OPEN[(case, impl)], strict=False)] if (case, impl) in _OPEN else []
-            yield pytest.param(case, impl, id="%s-%s" % (case, name), marks=marks)
+            yield pytest.param(case, impl, id="%s-%s" % (case, name))
 
 
 @pytest.mark.gpu
@@ -368,12 +278,8 @@ def test_engine_matches_reference_python(case, impl):
 
     g, cols, batch, method, L, seed, step = load(case)
     input_dtype = INPUT_DTYPE.get(case, "set")
-    MFP.allow_unverified = case in UNVERIFIED
-    try:
-        m = MFP(cols, num_blocks=L, block_type=BLOCK_TYPE.get(case, "deepsvg"), masking_method=method, input_dtype=input_dtype, latent_dim=256,
-                dropout=RATE, l2=L2, seed=0, context=CONTEXT.get(case))
-    finally:
-        MFP.allow_unverified = False
+    m = MFP(cols, num_blocks=L, block_type=BLOCK_TYPE.get(case, "deepsvg"), masking_method=method, input_dtype=input_dtype, latent_dim=256,
+            dropout=RATE, l2=L2, seed=0, context=CONTEXT.get(case))
     m._pad_context = False  # the golden batches already keep one free row per document (see CASES)
     params = O.init_params(cols, L, 256, WEIGHT_SEED, torch.float64, bias_scale=0.05, input_dtype=input_dtype, context=CONTEXT.get(case))
     m.set_weights({k: v.numpy().astype(np.float32) for k, v in params.items()})
@@ -438,8 +344,6 @@ def test_engine_matches_reference_python(case, impl):
     for name in specs:
         gg = got_grads[name].astype(np.float64).reshape(-1)
         total[name] = gg + 2.0 * L2 * w0[name].astype(np.float64).reshape(-1) if specs[name][2] else gg
-    if impl == 0:
-        g = pick_reference_run(case, g, total)
     check_gradient_summaries(total, g, grad_tol)
     # ---- L2 + per-variable clipnorm + Adam, one step
     l2_out = torch.zeros(1, device="cuda")

@@ -1,0 +1,145 @@
+"""Parity at the BENCHMARKED shape (BASELINE.json configs[1]..[3]: B = 256 documents, S = 128, L = 4; what bench.py times).
+
+The float64 oracle cannot run 256 x 128 elements through four blocks in test time, but documents are independent through the
+whole step (attention never crosses documents, the loss is a sum over documents divided by B, metrics.py:265-277) and every
+Philox counter is formed from global document / element indices (``mfp_set_doc_offset`` / ``PhiloxDraws(doc_offset=...)``).
+So the engine runs the FULL batch -- all 256 M-tiles of every GEMM, multi-tile persistent loops, double-buffered accumulators,
+split-K over K = 32768 rows, 2048 attention units -- and the oracle re-computes WINDOWS of documents at their global offsets:
+
+* task ids, masks and corrupted inputs of the window: bit-exact;
+* training-mode logits (same dropout keep-masks) of the window's rows: the stated tolerances;
+* loss and per-variable gradients of ``(1/B) * sum over the window's documents``: the engine gets exactly that quantity by
+  running its loss kernel with the masks of every other document cleared, followed by the full-size backward pass.
+
+Windows sit in different M-tiles (first, middle, last documents).  Both GEMM paths; crello ``random`` (cfg2), crello
+``elem_pos_attr_img_txt`` (cfg3) and rico ``elem_pos_attr`` with the sort branch (cfg4)."""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from flex_dm_b200.spec import make_input_columns, make_synthetic_batch
+from oracle import mfp_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+B, S, L = 256, 128, 4
+SEED, STEP = 17, 3
+
+
+def _engine_step(dataset, method, impl, lengths):
+    from flex_dm_b200.mfp import MFP
+
+    cols = make_input_columns(dataset, max_length=S)
+    m = MFP(cols, num_blocks=L, masking_method=method, latent_dim=256, dropout=0.1, l2=1e-2, seed=0)
+    m.set_weights(H.perturbed_weights(m.engine, 0))
+    m.engine.set_gemm_impl(impl)
+    batch = make_synthetic_batch(cols, B, S, seed=5, lengths=lengths)
+    staged = m.stage(batch)
+    _, _, length, dcols = m._bind(staged)
+    eng = m.engine
+    tasks = eng.sample_tasks(m.task_ids, SEED, STEP).clone()
+    eng.mask_corrupt(length, dcols, tasks, SEED, STEP)
+    logits = torch.empty((B * S, eng.logit_width), device="cuda")
+    eng.forward(length, None, True, SEED, STEP, logits_out=logits)
+    return cols, m, batch, length, dcols, tasks, logits
+
+
+def _window_oracle(cols, m, batch, lo, hi):
+    """The oracle on documents [lo, hi) of the batch at their global offset: masks, training logits, sum-loss / B and its gradients."""
+    sub = {k: v[lo:hi] for k, v in batch.items()}
+    draws = O.PhiloxDraws(SEED, STEP, doc_offset=lo)
+    tasks = draws.tasks(hi - lo, m.task_ids)
+    icols = m.input_columns
+    targets, omod, omasks = O.preprocess_for_train(H.to_torch(sub), icols, torch.as_tensor(tasks), draws)
+    keep = {(i, j): torch.from_numpy(draws.dropout_keep(i, j, (hi - lo, S, 256), 0.1)) for i in range(L) for j in (0, 1)}
+    params = OrderedDict((k, v.requires_grad_(True)) for k, v in H.oracle_params_from_engine(m.engine).items())
+    outputs = O.model_forward(params, omod, icols, L, keep, 0.1)
+    sort_flag = (torch.as_tensor(tasks) == m.task_names.index("pos")) if m.sort_pos else None
+    total, losses, scores, _ = O.loss_layer(targets, outputs, omasks, cols, sort_flag)
+    scaled = total * (hi - lo) / B  # loss_layer takes the mean over ITS batch (metrics.py:277); the engine divides by the global B
+    scaled.backward()
+    grads = OrderedDict((k, (v.grad if v.grad is not None else torch.zeros_like(v)).numpy()) for k, v in params.items())
+    return tasks, omod, omasks, outputs, float(scaled.detach()), losses, scores, grads
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["fp32-simt", "tf32-tcgen05"])
+@pytest.mark.parametrize("dataset,method,lengths", [("crello", "random", "full"), ("crello", "elem_pos_attr_img_txt", "ragged"),
+                                                    ("rico", "elem_pos_attr", "ragged")], ids=["cfg2", "cfg3", "cfg4"])
+def test_full_shape_step_matches_oracle_on_document_windows(dataset, method, lengths, impl):
+    cols, m, batch, length, dcols, tasks, logits = _engine_step(dataset, method, impl, lengths)
+    eng = m.engine
+    logit_atol, loss_rtol, grad_tol = (H.F32_LOGIT_ATOL, H.F32_LOSS_RTOL, H.F32_GRAD_REL_L2) if impl == 1 else (H.LOGIT_ATOL, H.LOSS_RTOL, H.GRAD_REL_L2)
+    got_logits = m.split_logits(logits, B, S)
+    full_masks = [t.clone() for t in eng.masks]
+    F = len(m.keys)
+    # 128 rows per document = one M-tile each: first / middle / last tiles.  Eight documents per window: a gradient summed over fewer
+    # elements hangs on individual ReLU gates that TF32 rounding may flip (tools/tf32_gate_scan.py), which is fixture noise, not parity
+    windows = [(0, 8), (124, 132), (248, 256)]
+    for lo, hi in windows:
+        otasks, omod, omasks, outputs, oloss, olosses, oscores, ograds = _window_oracle(cols, m, batch, lo, hi)
+        assert np.array_equal(tasks[lo:hi].cpu().numpy(), otasks)
+        for f, key in enumerate(m.keys):
+            assert np.array_equal(full_masks[f][lo:hi].cpu().numpy().astype(bool), omasks[key].numpy()), key
+            got = eng.modified[f][lo:hi].cpu().numpy()
+            if cols[key]["type"] == "categorical":
+                assert np.array_equal(got, omod[key].numpy().astype(np.int32)), key
+            else:
+                assert np.allclose(got, omod[key].numpy(), atol=1e-6, rtol=0), key
+        valid = (np.arange(S)[None, :] <= batch["length"][lo:hi].reshape(-1, 1))
+        for key in m.keys:
+            ref = outputs[key].detach().numpy()
+            err = np.abs(got_logits[key][lo:hi].cpu().numpy() - ref)[valid].max()
+            assert err <= logit_atol, (key, lo, err)
+        # loss + gradients of (1/B) * sum over the window: every other document's masks cleared, full-size loss + backward kernels
+        for f in range(F):
+            eng.masks[f].zero_()
+            eng.masks[f][lo:hi].copy_(full_masks[f][lo:hi])
+        row = torch.zeros(eng.metrics_width, device="cuda")
+        eng.loss(length, dcols, eng.masks, row, 1.0 / B, True, sort_tasks=tasks if m.sort_pos else None)
+        eng.backward(length, None, True, SEED, STEP)
+        torch.cuda.synchronize()
+        r = row.cpu().numpy()
+        assert r[3 * F] == pytest.approx(oloss, rel=loss_rtol), (lo, r[3 * F], oloss)
+        for f, key in enumerate(m.keys):
+            # rico "pos" documents pair predictions and targets after sorting the PREDICTED elements by the argmax of their logits
+            # (tensor_utils.py:14-44 with from_logits): a TF32 near-tie re-pairs two elements and moves a per-field loss discretely
+            key_rtol = 1e-2 if (m.sort_pos and impl == 0) else loss_rtol
+            assert r[3 * f] == pytest.approx(float(olosses[key]) * (hi - lo) / B, rel=key_rtol, abs=1e-6), key
+        got_grads = eng.get_weights(eng.grads)
+        table = []
+        for name, g in ograds.items():
+            gn = np.linalg.norm(g)
+            if gn < 1e-9 or name.endswith("dense_key/bias"):
+                # softmax is shift-invariant: the exact gradient of the key bias is 0; what the engine holds is the rounding noise of the
+                # column sum of dK -- bounded relative to the kernel's gradient
+                sibling = np.linalg.norm(ograds[name.replace("/bias", "/kernel")]) if name.endswith("/bias") else 0.0
+                assert np.linalg.norm(got_grads[name]) <= grad_tol * max(sibling, 1e-6), name
+            else:
+                table.append((H.rel_l2(got_grads[name], g), name))
+        worst = max(table)
+        assert worst[0] <= grad_tol, (lo, worst)
+    for f in range(F):
+        eng.masks[f].copy_(full_masks[f])
+
+
+def test_full_shape_tf32_path_agrees_with_fp32_path_on_the_whole_batch():
+    """All 256 documents at once: loss row and every gradient of the tcgen05 path against the fp32 SIMT path of the same engine
+    (same masks, same dropout) -- the document windows above tie the fp32 path to the oracle."""
+    rows, grads = [], []
+    for impl in (1, 0):
+        cols, m, batch, length, dcols, tasks, logits = _engine_step("crello", "random", impl, "full")
+        eng = m.engine
+        row = torch.zeros(eng.metrics_width, device="cuda")
+        eng.loss(length, dcols, eng.masks, row, 1.0 / B, True)
+        eng.backward(length, None, True, SEED, STEP)
+        torch.cuda.synchronize()
+        rows.append(row.cpu().numpy())
+        grads.append(eng.get_weights(eng.grads))
+    F = (len(rows[0]) - 2) // 3
+    assert rows[1][3 * F] == pytest.approx(rows[0][3 * F], rel=H.LOSS_RTOL)
+    for name, g in grads[0].items():
+        if np.linalg.norm(g) > 1e-7 and not name.endswith("dense_key/bias"):  # (exact gradient 0: rounding noise on both paths)
+            assert H.rel_l2(grads[1][name], g) <= H.GRAD_REL_L2 / 2, name

@@ -467,3 +467,40 @@ def test_full_size_step_properties():
     for _ in range(5):
         last = m.metrics_from_row(m.train_step(batch))["loss"]
     assert np.isfinite(last) and last < first
+
+
+def test_tf32_operand_rounding_of_the_product_path():
+    """What the tcgen05 GEMM does to fp32 operands below TF32's 10-bit mantissa: the TMA unit converts TFLOAT32 maps with
+    round-to-nearest, ties to even (measured on a B200; the MMA alone would truncate) -- the rule ``oracle.tf32_round`` /
+    ``oracle.emulate_tf32`` restate, on which the stated TF32 tolerances rest.  The products below are exact in fp32 under any rule,
+    so the results identify it."""
+    import torch
+
+    from flex_dm_b200.engine import debug_gemm
+
+    up, half, lo = 2.0 ** -10, 2.0 ** -11, 2.0 ** -13
+    cases = {"above half an ulp": 1.0 + half + lo, "tie": 1.0 + half, "below half an ulp": 1.0 + half - lo, "negative, above half": -(1.0 + half + lo)}
+    seen = {}
+    for operand in ("A", "B"):  # the value sits in the A (token-major activations) or in the B (weights) operand
+        for label, value in cases.items():
+            M = N = 128
+            K = 32
+            A = torch.zeros(M, K)
+            Bm = torch.zeros(N, K)
+            A[:, 0] = value if operand == "A" else 1.0
+            Bm[:, 0] = 1.0 if operand == "A" else value
+            out = debug_gemm(A.cuda(), 0, Bm.T.contiguous().cuda(), 1, M, N, K, impl=0)  # forward layout: x . W, W stored [K][N]
+            torch.cuda.synchronize()
+            got = out.cpu()
+            assert bool((got == got[0, 0]).all())
+            seen[(operand, label)] = float(got[0, 0])
+    rules = set()
+    for (operand, label), got in seen.items():
+        sign = -1.0 if label.startswith("negative") else 1.0
+        assert got in (sign * 1.0, sign * (1.0 + up)), (operand, label, got)
+    for operand in ("A", "B"):
+        above, tie, below = (seen[(operand, k)] for k in ("above half an ulp", "tie", "below half an ulp"))
+        rule = "truncation" if above == 1.0 else ("nearest, ties away" if tie == 1.0 + up else "nearest, ties to even")
+        assert below == 1.0 and (seen[(operand, "negative, above half")] == -above)
+        rules.add((operand, rule))
+    assert rules == {("A", "nearest, ties to even"), ("B", "nearest, ties to even")}, rules

@@ -1,5 +1,5 @@
-"""train.py:79-88 with the reference's callback list on the GPU engine (collected last on purpose: the callback protocol itself is
-covered on the CPU by tests/test_api_surface.py; this is the end-to-end flow that leaves ``best.ckpt`` for eval.py:169-172)."""
+"""train.py:79-88 with the reference's callback list on the GPU engine (the callback protocol itself is covered on the CPU by
+tests/test_api_surface.py; this is the end-to-end flow that leaves ``best.ckpt`` for eval.py:169-172)."""
 import itertools
 import os
 from types import SimpleNamespace
@@ -74,55 +74,3 @@ def test_train_function_end_to_end(tmp_path):
     # same weights, same Philox key; the corruption streams are indexed by the step counter, which differs between the two runs, so
     # the masked positions differ: scores agree statistically, the L2 part of the loss exactly
     assert 0.0 <= again["total_score"] <= 1.0 and again["total_score"] == pytest.approx(results["total_score"], abs=0.3)
-
-
-def test_tf32_operand_rounding_of_the_product_path_is_recorded():
-    """What the tcgen05 GEMM does to fp32 operands below TF32's 10-bit mantissa.  DESIGN.md section 2 states round-to-nearest (the TMA
-    unit converts TFLOAT32 maps; the MMA itself would truncate); the oracle's TF32 emulation (oracle.emulate_tf32) and the ReLU-gate
-    analysis of tests/test_golden_reference.py depend on which it is.  The products below are exact in fp32 under either rule, so the
-    result identifies the rule; it is reported as a warning and only garbage fails.  (Written without GPU time: not yet run on a B200.)"""
-    import warnings
-
-    import torch
-
-    from flex_dm_b200.engine import debug_gemm
-
-    up, half, lo = 2.0 ** -10, 2.0 ** -11, 2.0 ** -13
-    cases = {"above half an ulp": 1.0 + half + lo, "tie": 1.0 + half, "below half an ulp": 1.0 + half - lo, "negative, above half": -(1.0 + half + lo)}
-    seen = {}
-    for operand in ("A", "B"):  # the value sits in the A (token-major activations) or in the B (weights) operand
-        for label, value in cases.items():
-            M = N = 128
-            K = 32
-            A = torch.zeros(M, K)
-            Bm = torch.zeros(N, K)
-            A[:, 0] = value if operand == "A" else 1.0
-            Bm[:, 0] = 1.0 if operand == "A" else value
-            out = debug_gemm(A.cuda(), 0, Bm.T.contiguous().cuda(), 1, M, N, K, impl=0)  # forward layout: x . W, W stored [K][N]
-            torch.cuda.synchronize()
-            got = out.cpu()
-            assert bool((got == got[0, 0]).all())
-            seen[(operand, label)] = float(got[0, 0])
-    rules = set()
-    for (operand, label), got in seen.items():
-        sign = -1.0 if label.startswith("negative") else 1.0
-        assert got in (sign * 1.0, sign * (1.0 + up)), (operand, label, got)
-    for operand in ("A", "B"):
-        above, tie, below = (seen[(operand, k)] for k in ("above half an ulp", "tie", "below half an ulp"))
-        rule = "truncation" if above == 1.0 else ("nearest, ties away" if tie == 1.0 + up else "nearest, ties to even")
-        assert below == 1.0 and (seen[(operand, "negative, above half")] == -above)
-        rules.add((operand, rule))
-    warnings.warn("TF32 operand rounding of the tcgen05 GEMM path: %s" % ", ".join("%s operand: %s" % r for r in sorted(rules)))
-
-
-@pytest.mark.parametrize("impl", [1, 0], ids=["fp32-simt", "tf32-tcgen05"])
-@pytest.mark.xfail(reason="engine path written without GPU time; not yet run on a B200", strict=False)
-def test_engine_cases_not_yet_run_on_a_gpu(impl):
-    """The reference-run goldens whose engine path was written after the round's GPU time had run out (tests/test_golden_reference.py::
-    UNVERIFIED: --context id with --input_dtype shuffled_set), through the same checks as every other golden case -- collected last so that
-    never-run kernel code cannot disturb the verified tests; an XPASS here is the confirmation that lets MFP.allow_unverified go."""
-    from tests.test_golden_reference import UNVERIFIED
-    from tests.test_golden_reference import test_engine_matches_reference_python as check
-
-    for case in sorted(UNVERIFIED):
-        check(case, impl)

@@ -9,7 +9,7 @@ for arg in "$@"; do
   if [ "$arg" = "ref" ]; then echo "== reference arm"; timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>&1; echo "rc=$?"; cat gpurun_out/bench_ref.json; fi
   if [ "$arg" = "sanitize" ]; then
     echo "== compute-sanitizer memcheck (context token, document gather)"
-    timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_context.py tests/test_gpu_input_pipeline.py tests/test_gpu_zz_callbacks.py -q -m gpu --no-header -p no:cacheprovider -k "gradients or device_cached or train_py or not_yet_run" > gpurun_out/sanitizer.log 2>&1; echo "rc=$?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitizer.log | tail -4
+    timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_context.py tests/test_gpu_input_pipeline.py tests/test_gpu_train_flow.py -q -m gpu --no-header -p no:cacheprovider -k "gradients or device_cached or train_py or ctx_id_shuffled" > gpurun_out/sanitizer.log 2>&1; echo "rc=$?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitizer.log | tail -4
   fi
 done
 nproc

@@ -5,7 +5,7 @@ For every fixture of tests/test_golden_reference.py the float64 oracle is run as
 forced to the other side.  Printed per gate: block, (document, oracle row, unit), the pre-activation in float64 / RNA / truncation, and the
 largest per-variable change of the gradient (L2, relative to the variable's gradient norm) that flipping it causes.  A gate with a change
 above ``tests/helpers.py::GRAD_REL_L2`` makes the fixture's gradient checks depend on the rounding mode of the product path: list it in
-``EDGE_GATES`` of tests/test_golden_reference.py (the GPU test then accepts either side) or pick another seed when making new fixtures.
+pick another seed for it (tests/golden/make_golden.py): round 1's ``--context canvas`` fixture was regenerated for that reason.
 This is how the open item of ``--context canvas`` was traced.  Usage: python tools/tf32_gate_scan.py [case ...]"""
 import os
 import sys
