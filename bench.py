@@ -28,6 +28,20 @@ UNIT = "elements/s"
 B_PER_GPU, SEQ_LEN, NUM_BLOCKS, LATENT = 256, 128, 4, 256
 N_DEVICE_BATCHES = 4  # rotate distinct resident batches: 4 x 135 MB of inputs > the 126 MB L2
 
+# BASELINE.json configs[0..4] = cfg1..cfg5.  B is documents per GPU, except cfg5 where it is the GLOBAL batch (strong scaling).
+CONFIGS = {
+    1: dict(name="cfg1: crello MFP --masking_method random, 2-layer d=256 h=8 seq_len=32 bs=4 (the reference's CPU-runnable case)",
+            dataset="crello", method="random", L=2, S=32, B=4, scaling="weak"),
+    2: dict(name="cfg2: crello Ours-IMP (--masking_method random) full config, seq_len=128", dataset="crello", method="random", L=4, S=128, B=256,
+            scaling="weak"),
+    3: dict(name="cfg3: crello Ours-EXP (--masking_method elem_pos_attr_img_txt) full config, seq_len=128", dataset="crello",
+            method="elem_pos_attr_img_txt", L=4, S=128, B=256, scaling="weak"),
+    4: dict(name="cfg4: rico Ours-EXP (--masking_method elem_pos_attr, sort_pos loss branch) full config, seq_len=128", dataset="rico",
+            method="elem_pos_attr", L=4, S=128, B=256, scaling="weak"),
+    5: dict(name="cfg5: crello Ours-IMP global bs=512 seq_len=128, documents sharded over the GPUs + NCCL gradient all-reduce", dataset="crello",
+            method="random", L=4, S=128, B=512, scaling="strong"),
+}
+
 
 def flops_per_element(cols, S, L, D=256):
     """F_fwd = 2 D sum(d_num) + L (16 D^2 + 4 S D) + 2 D sum(W); train = 3 x."""
@@ -88,6 +102,27 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def cpu_cfg1_throughput(steps=10):
+    """BASELINE.json configs[0] exactly (L=2, D=256, H=8, S=32, B=4, crello, random): the oracle's fp32 port on all host threads."""
+    import torch
+
+    from flex_dm_b200.spec import make_input_columns, make_synthetic_batch
+    from oracle import mfp_oracle as O
+
+    w = CONFIGS[1]
+    cols = make_input_columns(w["dataset"], max_length=50)
+    batch = make_synthetic_batch(cols, w["B"], w["S"], seed=0, lengths="full")
+    o = O.OracleMFP(cols, num_blocks=w["L"], masking_method=w["method"], dropout=0.1, l2=1e-2, dtype=torch.float32)
+    for i in range(3):
+        o.train_step(batch, seed=0, step=i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        r = o.train_step(batch, seed=0, step=3 + i)
+    el = time.perf_counter() - t0
+    return {"value": w["B"] * w["S"] * steps / el, "unit": UNIT, "ms_per_step": 1e3 * el / steps, "steps": steps, "loss_last_step": r["loss"],
+            "workload": w["name"]}
+
+
 def cpu_port_throughput(budget_s=20.0, docs=8, threads=None):
     """The oracle's fp32 'port' of the reference train step (all masking variants, eager op sequence) on the host
     cores, on a bounded sample of the workload: `docs` full-length documents of the same schema / depth."""
@@ -110,7 +145,8 @@ def cpu_port_throughput(budget_s=20.0, docs=8, threads=None):
             break
     return {"value": docs * SEQ_LEN * steps / el, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": "%d steps of %d full-length crello documents (S=%d, L=%d, D=%d), fp32 PyTorch-CPU restatement of the TF eager op sequence "
-                      "(TensorFlow is not installable here)" % (steps, docs, SEQ_LEN, NUM_BLOCKS, LATENT)}
+                      "(TensorFlow is not installable here)" % (steps, docs, SEQ_LEN, NUM_BLOCKS, LATENT),
+            "cfg1": cpu_cfg1_throughput()}
 
 
 def run_reference(args):
@@ -125,21 +161,23 @@ def run_reference(args):
     from oracle import mfp_oracle as O
 
     torch.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: take every host core back
-    docs = 8
-    cols = make_input_columns("crello", max_length=SEQ_LEN)
-    batch = make_synthetic_batch(cols, docs, SEQ_LEN, seed=0, lengths="full")
-    o = O.OracleMFP(cols, num_blocks=NUM_BLOCKS, masking_method="random", dropout=0.1, l2=1e-2, dtype=torch.float32)
+    w = CONFIGS[args.config]
+    docs = min(8, w["B"])  # a bounded sample of the workload per step: 8 full-length documents (cfg1: its 4 documents = the whole config)
+    S, L = w["S"], w["L"]
+    cols = make_input_columns(w["dataset"], max_length=max(50, S))
+    batch = make_synthetic_batch(cols, docs, S, seed=0, lengths="full")
+    o = O.OracleMFP(cols, num_blocks=L, masking_method=w["method"], dropout=0.1, l2=1e-2, dtype=torch.float32)
     for i in range(args.warmup):
         o.train_step(batch, seed=0, step=i)
     t0 = time.perf_counter()
     for i in range(args.steps):
         o.train_step(batch, seed=0, step=args.warmup + i)
     el = time.perf_counter() - t0
-    value = docs * SEQ_LEN * args.steps / el
-    sample = "each step = %d full-length documents (S=%d) of the crello workload; fp32 PyTorch-CPU port of the reference op sequence" % (docs, SEQ_LEN)
+    value = docs * S * args.steps / el
+    sample = "each step = %d full-length documents (S=%d, L=%d) of %s; fp32 PyTorch-CPU port of the reference op sequence" % (docs, S, L, w["name"])
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "crello Ours-IMP (masking_method=random) L=4 D=256 H=8 seq_len=128, CPU sample of %d documents per step" % docs},
+            "config": {"workload": "%s, CPU sample of %d documents per step" % (w["name"], docs)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -225,25 +263,144 @@ def tfrecord_leg(model, timed, steps):
         shutil.rmtree(root, ignore_errors=True)
 
 
+def input_columns_for(w):
+    from flex_dm_b200.spec import make_input_columns
+
+    return make_input_columns(w["dataset"], max_length=max(50, w["S"]))
+
+
+def step0_golden(config):
+    """The float64 oracle's loss of this configuration's first step (tools/make_bench_golden.py -> tests/golden/bench_step0.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "tests", "golden", "bench_step0.json"))).get("cfg%d" % config)
+    except Exception:
+        return None
+
+
+class Workload:
+    """One bench configuration on this rank: model, resident + pinned batches, the step function."""
+
+    def __init__(self, config, world, rank, dev, dist):
+        import torch
+
+        from flex_dm_b200.mfp import MFP, Adam
+        from flex_dm_b200.spec import make_synthetic_batch
+
+        self.w = w = CONFIGS[config]
+        self.config, self.world, self.rank, self.dev, self.dist = config, world, rank, dev, dist
+        self.S, self.L = w["S"], w["L"]
+        if w["scaling"] == "strong":
+            if w["B"] % world:
+                raise SystemExit("cfg%d: global batch %d does not divide over %d GPUs" % (config, w["B"], world))
+            self.B = w["B"] // world
+        else:
+            self.B = w["B"]
+        self.cols = cols = input_columns_for(w)
+        self.model = model = MFP(cols, num_blocks=self.L, masking_method=w["method"], latent_dim=LATENT, dropout=0.1, l2=1e-2, seed=0, device=dev)
+        model.compile(optimizer=Adam(learning_rate=1e-4, clipnorm=1.0))
+        if world > 1:
+            model.enable_data_parallel(dist, world)
+        # synthetic data: distinct batches per rank (seed = 1000 * rank + i), pinned on the host for the e2e leg
+        host = [make_synthetic_batch(cols, self.B, self.S, seed=1000 * rank + i, lengths="full") for i in range(N_DEVICE_BATCHES)]
+        needed = [k for k, c in model.input_columns.items() if k == "length" or c["is_sequence"]]
+        self.pinned = [{k: torch.from_numpy(b[k]).pin_memory() for k in needed} for b in host]
+        self.resident = [model.stage(b) for b in self.pinned]
+        torch.cuda.synchronize()
+        self.elements_per_step = self.B * self.S  # every document is full length: valid elements = B * S
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.pinned[0].values())
+
+    def step_resident(self, i):
+        return self.model.train_step(self.resident[i % N_DEVICE_BATCHES], staged=True)
+
+    def global_loss(self, row):
+        """Loss of the GLOBAL batch from this rank's metrics row: the additive columns are summed over the ranks (metrics.py:265-277)."""
+        import torch
+
+        from flex_dm_b200.parallel import reduce_metric_rows
+
+        rows = row.detach().reshape(1, -1).to(self.dev)
+        if self.world > 1:
+            rows = reduce_metric_rows(self.dist, rows)
+        return self.model.metrics_from_row(rows[0])["loss"]
+
+
+def dp_check(config, world, rank, dev, dist, steps=3):
+    """N GPUs on document shards vs ONE GPU on the concatenated batch (the reference is single-process: train.py:25), both with
+    fixed-order reductions: per-step global loss, the weights after `steps` Adam updates, and a cross-rank checksum of the replicated
+    parameters.  Ragged documents; shard r holds documents [r * B, (r + 1) * B) of the global batch."""
+    import torch
+
+    from flex_dm_b200.mfp import MFP, Adam
+    from flex_dm_b200.parallel import reduce_metric_rows
+    from flex_dm_b200.spec import make_synthetic_batch
+
+    w = CONFIGS[config]
+    B = w["B"] // world if w["scaling"] == "strong" else w["B"]
+    S, L = w["S"], w["L"]
+    cols = input_columns_for(w)
+
+    def fresh():
+        m = MFP(cols, num_blocks=L, masking_method=w["method"], latent_dim=LATENT, dropout=0.1, l2=1e-2, seed=0, device=dev)
+        m.compile(optimizer=Adam(learning_rate=1e-3, clipnorm=1.0))
+        m.set_deterministic(True)
+        return m
+
+    def shard(r, i):
+        return make_synthetic_batch(cols, B, S, seed=7000 + 1000 * r + i, lengths="ragged")
+
+    sharded = fresh()
+    sharded.enable_data_parallel(dist, world)
+    w0 = sharded.engine.params.clone()
+    rows = torch.stack([sharded.train_step(shard(rank, i)).clone() for i in range(steps)])
+    rows = reduce_metric_rows(dist, rows)
+    losses = [sharded.metrics_from_row(r)["loss"] for r in rows]
+    # replicated parameters: every rank must hold the same bits
+    bits = sharded.engine.params.view(torch.int32).to(torch.int64)
+    checksum = torch.stack([bits.sum(), (bits * (torch.arange(bits.numel(), device=dev) % 8191 + 1)).sum()])
+    gathered = [torch.zeros_like(checksum) for _ in range(world)]
+    dist.all_gather(gathered, checksum)
+    same = all(bool(torch.equal(g, gathered[0])) for g in gathered)
+    out = None
+    if rank == 0:
+        single = fresh()
+        ref_losses = []
+        for i in range(steps):
+            parts = [shard(r, i) for r in range(world)]
+            batch = {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
+            ref_losses.append(single.metrics_from_row(single.train_step(batch))["loss"])
+        torch.cuda.synchronize()
+        dw = (single.engine.params - sharded.engine.params).abs().max().item()
+        moved = (single.engine.params - w0).abs().max().item()
+        out = {"steps": steps, "documents_per_gpu": B, "global_batch": B * world, "lengths": "ragged", "deterministic": True,
+               "loss_single_gpu": ref_losses, "loss_sharded": losses,
+               "max_rel_loss_diff": max(abs(a - b) / abs(b) for a, b in zip(losses, ref_losses)),
+               "max_abs_dw": dw, "max_abs_update": moved, "param_checksums_equal_across_ranks": same}
+        del single
+    del sharded
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)  # ~0.7 s timed region: long enough for several nvidia-smi clock samples
+    ap.add_argument("--steps", type=int, default=200)  # ~0.6 s timed region: long enough for several nvidia-smi clock samples
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[config - 1]; the metric is quoted on 2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end and roofline legs (ncu launch-list runs)")
     ap.add_argument("--no-tfrecord", action="store_true", help="skip the TFRecord input-pipeline leg (N=1 only)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short value-only runs of the other BASELINE configs")
+    ap.add_argument("--no-check-dp", action="store_true", help="N > 1: skip the sharded-vs-single-GPU equivalence check")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
-
-    from flex_dm_b200.mfp import MFP, Adam
-    from flex_dm_b200.spec import make_input_columns, make_synthetic_batch
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -255,22 +412,6 @@ def main():
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-
-    cols = make_input_columns("crello", max_length=SEQ_LEN)
-    model = MFP(cols, num_blocks=NUM_BLOCKS, masking_method="random", latent_dim=LATENT, dropout=0.1, l2=1e-2, seed=0, device=dev)
-    model.compile(optimizer=Adam(learning_rate=1e-4, clipnorm=1.0))
-    if world > 1:
-        model.enable_data_parallel(dist, world)
-
-    # synthetic data: distinct batches per rank (seed = rank), pinned on the host for the e2e leg
-    host = [make_synthetic_batch(cols, B_PER_GPU, SEQ_LEN, seed=1000 * rank + i, lengths="full") for i in range(N_DEVICE_BATCHES)]
-    needed = [k for k, c in model.input_columns.items() if k == "length" or c["is_sequence"]]
-    pinned = [{k: torch.from_numpy(b[k]).pin_memory() for k in needed} for b in host]
-    resident = [model.stage(b) for b in pinned]
-    torch.cuda.synchronize()
-    elements_per_step = B_PER_GPU * SEQ_LEN  # every document is full length: valid elements = B*S
-    h2d_bytes = sum(t.numel() * t.element_size() for t in pinned[0].values())
-    d2h_bytes = model.engine.metrics_width * 4
 
     def barrier():
         if world > 1:
@@ -290,20 +431,53 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- device-resident leg (value)
-    def step_resident(i):
-        model.train_step(resident[i % N_DEVICE_BATCHES], staged=True)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
 
-    for i in range(args.warmup):
-        step_resident(i)
+    def value_leg(config, steps, warmup, before_timed=None):
+        """Device-resident throughput of one configuration: (workload, ms total, launches, step-0 global loss)."""
+        wl = Workload(config, world, rank, dev, dist)
+        loss0 = wl.global_loss(wl.step_resident(0))
+        for i in range(1, warmup):
+            wl.step_resident(i)
+        launches0 = wl.model.engine.launch_count()
+        if before_timed is not None:
+            before_timed()
+        ms = timed(wl.step_resident, steps)
+        return wl, ms, wl.model.engine.launch_count() - launches0, loss0
+
+    def check_step0(config, loss0):
+        """The engine's first-step loss against the committed float64 oracle value (N = 1: rank 0's batch 0 is the golden batch)."""
+        g = step0_golden(config)
+        if g is None or world != 1:
+            return None
+        rel = abs(loss0 - g["loss"]) / abs(g["loss"])
+        assert rel <= 2e-3, "cfg%d: step-0 loss %.6f differs from the oracle's %.6f (rel %.2e > 2e-3)" % (config, loss0, g["loss"], rel)
+        return {"engine": loss0, "oracle_f64": g["loss"], "rel_err": rel, "tolerance": 2e-3, "source": "tests/golden/bench_step0.json"}
+
+    # ---- device-resident leg (value)
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = model.engine.launch_count()
-    ms = timed(step_resident, args.steps)
-    launches = model.engine.launch_count() - launches0
+    wl, ms, launches, loss0 = value_leg(args.config, args.steps, args.warmup, before_timed=sampler.start if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
+    model, w = wl.model, wl.w
+    elements_per_step = wl.elements_per_step
     value = world * elements_per_step * args.steps / (ms * 1e-3)
+    step0 = check_step0(args.config, loss0)
+    h2d_bytes = wl.h2d_bytes
+    d2h_bytes = model.engine.metrics_width * 4
+    train_flops, gemm_flops = flops_per_element(wl.cols, wl.S, wl.L, LATENT)
+
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms / args.steps, "gpu_launches": int(launches),
+                              "note": "partial line (--no-e2e): not a bench result"}), flush=True)
+        return
 
     # ---- end-to-end leg: host (pinned) batches through the public input pipeline (flex_dm_b200.data.DevicePrefetcher, what
     # MFP.fit uses): every step's columns are copied from pinned host memory inside the timed region, on a copy stream,
@@ -315,55 +489,40 @@ def main():
     def host_batches():
         i = 0
         while True:
-            yield pinned[i % N_DEVICE_BATCHES]
+            yield wl.pinned[i % N_DEVICE_BATCHES]
             i += 1
 
-    feeder = None
+    feeder = DevicePrefetcher(model, host_batches())
 
     def step_e2e(i):
         row = model.train_step(next(feeder), staged=True)
         rows_host[i % args.steps].copy_(row, non_blocking=True)
 
-    if args.no_e2e:
-        if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms / args.steps, "gpu_launches": int(launches),
-                              "note": "partial line (--no-e2e): not a bench result"}), flush=True)
-        return
-    feeder = DevicePrefetcher(model, host_batches())
     for i in range(3):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
     e2e_value = world * elements_per_step * args.steps / (ms_e2e * 1e-3)
-    last = model.metrics_from_row(rows_host[args.steps - 1])
-    assert np.isfinite(last["loss"]), last
+    last_loss = wl.global_loss(rows_host[args.steps - 1])
+    assert np.isfinite(last_loss), last_loss
 
-    # ---- input-side leg (N = 1): the same step fed from TFRecord files through DataSpec.make_dataset (native SequenceExample parser on
+    # ---- input-side leg (N = 1, cfg2): the same step fed from TFRecord files through DataSpec.make_dataset (native SequenceExample parser on
     # host threads -> pinned batches -> DevicePrefetcher), i.e. train.py's own data path; reported beside e2e, not instead of it.
     input_pipeline = None
-    if world == 1 and not args.no_tfrecord:
+    if world == 1 and args.config == 2 and not args.no_tfrecord:
         try:
             input_pipeline = tfrecord_leg(model, timed, min(args.steps, 40))
         except Exception as e:  # an auxiliary leg must never cost the headline line (e.g. no writable temp directory on the box)
             input_pipeline = {"error": "%s: %s" % (type(e).__name__, e)}
 
     # ---- roofline of the dominant kernel (the TF32 tcgen05 GEMM): separate instrumented pass, CUDA events per launch
-    train_flops, gemm_flops = flops_per_element(cols, SEQ_LEN, NUM_BLOCKS, LATENT)
     prof_steps = 3
     torch.cuda.synchronize()
     model.engine.profile_begin()
     for i in range(prof_steps):
-        step_resident(i)
+        wl.step_resident(i)
     prof = model.engine.profile_end()
     gemm_ms, gemm_launches, gemm_bytes = prof["gemm"]
     attn_ms, attn_launches, attn_bytes = prof["attention"]
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     gemm_gbs = gemm_bytes / (gemm_ms * 1e-3) / 1e9 if gemm_ms > 0 else 0.0
     gemm_tflops = gemm_flops * elements_per_step * prof_steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     # The dominant kernel class is the TF32 tcgen05 GEMM (all Dense forward / dgrad / wgrad contractions).  With fp32
@@ -379,33 +538,67 @@ def main():
         traffic_src = "profiles/kernel_traffic.json: " + kt["source"]
     except Exception:
         pass
+    step_s = ms / args.steps * 1e-3
     roofline = {"bound": "hbm", "kernel": "gemm_tf32_tcgen05", "achieved": gemm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gemm_gbs / hbm_peak,
                 "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": gemm_bytes / max(gemm_launches, 1), "peak_source": src + " hbm_gbs",
                 "gemm_ms_per_step": gemm_ms / prof_steps, "gemm_launches_per_step": gemm_launches // prof_steps,
                 "gemm_algorithmic_bytes_per_step": gemm_bytes / prof_steps,
                 "tensor": {"achieved": gemm_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": gemm_tflops / tensor_peak,
-                           "peak_source": src + " bf16_tflops_sustained (no TF32 peak was measured; TF32 dense is nominally half of bf16)"},
+                           "peak_source": src + " bf16_tflops_sustained (no TF32 peak is in MEASURED_PEAKS.json; TF32 dense is nominally half of bf16)"},
                 "attention": {"ms_per_step": attn_ms / prof_steps, "launches_per_step": attn_launches // prof_steps,
                               "achieved": attn_bytes / (attn_ms * 1e-3) / 1e9 if attn_ms > 0 else 0.0, "unit": "GB/s",
                               "frac": (attn_bytes / (attn_ms * 1e-3) / 1e9 / hbm_peak) if attn_ms > 0 else 0.0},
-                "step_tensor_roofline_frac": train_flops * elements_per_step / (ms / args.steps * 1e-3) / 1e12 / tensor_peak}
+                "step_tensor_roofline_frac": train_flops * elements_per_step / step_s / 1e12 / tensor_peak,
+                # ~95 KB per element is the HBM floor of the step with per-sub-layer fusion and an fp32 residual stream
+                "step_hbm_roofline_frac": 95e3 * elements_per_step / step_s / 1e9 / hbm_peak}
+
+    # ---- N > 1: the sharded step against the single-process step on the concatenated batch
+    check = None
+    if world > 1 and not args.no_check_dp:
+        check = dp_check(args.config, world, rank, dev, dist)
+
+    # ---- the other BASELINE configs, value only (short runs; each line carries its own step-0 parity check and roofline fractions)
+    others = None
+    if not args.no_other_configs and args.config == 2:
+        others = {}
+        del feeder
+        for c in (3, 4, 5):
+            if CONFIGS[c]["scaling"] == "strong" and CONFIGS[c]["B"] % world:
+                continue
+            o_wl, o_ms, o_launches, o_loss0 = value_leg(c, min(args.steps, 100), 5)
+            o_steps = min(args.steps, 100)
+            tf, _ = flops_per_element(o_wl.cols, o_wl.S, o_wl.L, LATENT)
+            o_val = world * o_wl.elements_per_step * o_steps / (o_ms * 1e-3)
+            others["cfg%d" % c] = {"workload": "%s, %d documents per GPU" % (o_wl.w["name"], o_wl.B), "value": o_val, "unit": UNIT,
+                                   "ms_per_step": o_ms / o_steps, "steps": o_steps, "scaling": o_wl.w["scaling"], "global_batch": o_wl.B * world,
+                                   "gpu_launches_per_step": o_launches / o_steps, "train_flop_per_element": tf,
+                                   "step_tensor_roofline_frac": tf * o_wl.elements_per_step / (o_ms / o_steps * 1e-3) / 1e12 / tensor_peak,
+                                   "loss_step0": check_step0(c, o_loss0) or {"engine": o_loss0}}
+            del o_wl
+            torch.cuda.empty_cache()
 
     if world > 1:
         dist.barrier()
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_port_throughput(args.cpu_budget)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": "tf32",
                 "data": "synthetic",
-                "config": {"workload": "crello Ours-IMP (masking_method=random) full config: L=4 D=256 H=8 FFN=512 seq_len=128, %d documents per GPU, "
-                                       "all documents full length, dropout=0.1 l2=1e-2 Adam(1e-4, clipnorm=1.0)" % B_PER_GPU,
-                           "global_batch": B_PER_GPU * world, "seq_len": SEQ_LEN, "parallelism": "dp%d" % world,
+                "config": {"workload": "%s: L=%d D=256 H=8 FFN=512, %d documents per GPU, all documents full length, dropout=0.1 l2=1e-2 "
+                                       "Adam(1e-4, clipnorm=1.0)" % (w["name"], wl.L, wl.B),
+                           "global_batch": wl.B * world, "seq_len": wl.S, "parallelism": "dp%d" % world,
                            "l2_flush": "inputs larger than L2: %d distinct resident batches (%.0f MB) rotate; activations per step 1.6 GB" % (N_DEVICE_BATCHES, N_DEVICE_BATCHES * h2d_bytes / 1e6),
-                           "loss_last_step": last["loss"]},
+                           "loss_step0": step0 if step0 is not None else {"engine": loss0, "note": "global loss (metric rows summed over ranks); the oracle value is pinned at N=1"},
+                           "loss_last_step": last_loss},
                 "roofline": roofline, "cpu_baseline": cpu,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps,
+                        "h2d_gbs_per_gpu": h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9},
                 "gpu_launches": int(launches), "clocks": clocks}
+        if check is not None:
+            line["dp_check"] = check
+        if others:
+            line["other_configs"] = others
         if input_pipeline is not None:
             line["input_pipeline"] = input_pipeline
         print(json.dumps(line), flush=True)
