@@ -369,12 +369,23 @@ def dp_check(config, world, rank, dev, dist, steps=3):
             batch = {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
             ref_losses.append(single.metrics_from_row(single.train_step(batch))["loss"])
         torch.cuda.synchronize()
-        dw = (single.engine.params - sharded.engine.params).abs().max().item()
-        moved = (single.engine.params - w0).abs().max().item()
+        # The key bias of every attention layer has an exactly-zero data gradient (softmax is shift-invariant): what both runs hold
+        # there is rounding noise, which Adam normalises into +-lr moves.  Those 256-float slices are left out of the comparison.
+        keep = torch.ones_like(w0)
+        for name, (off, rows, vcols, ld, _) in single.engine.variables.items():
+            if name.endswith("dense_key/bias"):
+                keep[off:off + vcols] = 0.0
+        upd_single, upd_sharded = (single.engine.params - w0) * keep, (sharded.engine.params - w0) * keep
+        g_single, g_sharded = single.engine.grads * keep, sharded.engine.grads * keep
         out = {"steps": steps, "documents_per_gpu": B, "global_batch": B * world, "lengths": "ragged", "deterministic": True,
                "loss_single_gpu": ref_losses, "loss_sharded": losses,
                "max_rel_loss_diff": max(abs(a - b) / abs(b) for a, b in zip(losses, ref_losses)),
-               "max_abs_dw": dw, "max_abs_update": moved, "param_checksums_equal_across_ranks": same}
+               "last_step_gradient_rel_l2_diff": ((g_single - g_sharded).norm() / g_single.norm()).item(),
+               "weight_update_rel_l2_diff": ((upd_single - upd_sharded).norm() / upd_single.norm()).item(),
+               "weight_update_max_abs": upd_single.abs().max().item(), "weight_update_max_abs_diff": (upd_single - upd_sharded).abs().max().item(),
+               "note": "Adam moves every entry by ~lr per step whatever its size, so entries whose gradient is at rounding-noise level may differ by up to "
+                       "2 lr per step between two correct runs; the L2 figures are the meaningful ones",
+               "param_checksums_equal_across_ranks": same}
         del single
     del sharded
     torch.cuda.empty_cache()

@@ -51,13 +51,13 @@ __device__ __forceinline__ void epilogue_store4(float (&v)[4], int row, int col,
 //   warp 1      MMA issuer: one thread issues tcgen05.mma kind::tf32 into one of two TMEM accumulators
 //   warp 2      TMEM allocator; optional column-sum role (bias gradients of wgrad GEMMs: sums the MN-major B tiles while they
 //               sit in shared memory, so dY is never re-read from HBM)
-//   warps 4-7   epilogue: TMEM -> registers -> fused ops -> swizzled shared staging -> TMA store (or TMA reduce-add
-//               for split-K); the residual / ReLU-mask operand arrives by TMA as well, one 32x32 chunk ahead.
+//   warps 4-11  epilogue, two warps per TMEM lane quarter: TMEM -> registers -> fused ops -> swizzled shared staging -> TMA store (or
+//               TMA reduce-add for split-K); the residual / ReLU-mask operand arrives by TMA as well, one 32x32 chunk ahead.
 // The epilogue of tile i overlaps the main loop of tile i+1 through the double-buffered accumulator.
 constexpr int kBM = 128;        // UMMA M (one TMEM lane per row)
 constexpr int kBK = 32;         // 32 fp32 = 128 B = one swizzle row
 constexpr int kUmmaK = 8;       // tf32: 32 B of K per instruction
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;   // 4 role warps (TMA A, MMA, TMEM / column sums, TMA B) + 8 epilogue warps
 constexpr int kEpiWarp0 = 4;    // first epilogue warp (warp & 3 = TMEM lane quarter)
 constexpr int kChunkBytes = 32 * 32 * 4;  // one 32-row x 32-column fp32 staging chunk
 
@@ -72,19 +72,19 @@ struct GemmTiles {
   int det_colsum; // column-sum partials are stored per (split, m-tile) slot instead of atomically added
 };
 
-// AUX: the epilogue stages a residual / ReLU-mask operand (two more 4 KB chunks per epilogue warp).  Without it the 32 KB saved
+// AUX: the epilogue stages a residual / ReLU-mask operand (one more 4 KB chunk per epilogue warp).  Without it the 32 KB saved
 // buy a fourth operand stage at BN = 256: the ring is latency-bound (a slot is refilled only after its MMAs retire), so the
 // bytes in flight set the fill rate.
 template <int BN, bool AUX>
 struct GemmSmem {
-  static constexpr int kStages = (BN <= 128) ? (AUX ? 5 : 6) : (AUX ? 3 : 4);
-  static constexpr int kEpiChunks = AUX ? 4 : 2;                 // per epilogue warp: out[2] (+ aux[2])
+  static constexpr int kStages = (BN <= 128) ? 6 : 4;
+  static constexpr int kEpiChunks = 1;                           // per epilogue warp: one 4 KB staging chunk (transposes aux in, results out)
   static constexpr int kABytes = kBM * kBK * 4;
   static constexpr int kBBytes = BN * kBK * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiOff = kStages * kStageBytes;          // 4 warps x {out[2], aux[2]} chunks
-  static constexpr int kBarOff = kEpiOff + 4 * kEpiChunks * kChunkBytes;
-  static constexpr int kNumBars = 2 * kStages + 4 + 8;           // full, empty, tmem full[2]/empty[2], aux[4 warps][2]
+  static constexpr int kEpiOff = kStages * kStageBytes;          // 8 warps x {out, aux} chunks
+  static constexpr int kBarOff = kEpiOff + 8 * kEpiChunks * kChunkBytes;
+  static constexpr int kNumBars = 2 * kStages + 4;               // full, empty, tmem full[2]/empty[2]
   static constexpr int kTotal = kBarOff + 8 * kNumBars + 16 + 1024;  // + TMEM slot + alignment slack
 };
 
@@ -108,7 +108,6 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
-  auto aux_bar = [&](int w, int b) { return bar_base + 8u * (2 * kStages + 4 + 2 * w + b); };
   const uint32_t tmem_slot = bar_base + 8u * L::kNumBars;
   const uint32_t* tmem_slot_ptr = reinterpret_cast<const uint32_t*>(base_ptr + L::kBarOff + 8 * L::kNumBars);
 
@@ -126,17 +125,12 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
-    }
-    for (int w = 0; w < 4; ++w) {
-      mbar_init(aux_bar(w, 0), 1);
-      mbar_init(aux_bar(w, 1), 1);
+      mbar_init(tempty_bar(a), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
     prefetch_tensormap(&tmOut);
-    if (aux_mode != 0) prefetch_tensormap(&tmAux);
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(2 * BN) : "memory");
@@ -308,13 +302,48 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> fused ops -> swizzled staging -> TMA store =====
+    // ===== epilogue: TMEM -> registers -> fused ops -> swizzled staging (transpose) -> coalesced global stores =====
+    // Eight warps, two per TMEM lane quarter (a warp may only touch lanes 32 (warp % 4) ..): warp (q, h) takes the 32-column chunks
+    // c = h, h + 2, ... of rows 32 q .. 32 q + 31.
+    // Data path: NOT the TMA unit.  The SM's one TMA engine serves its requests in order, and the operand ring keeps up to four 48 KB
+    // loads queued in it: a 4 KB store (or aux load) issued behind them waited ~2 us for its turn -- the source-level profile of the
+    // TMA-store epilogue had 25-40 % of all samples on cp.async.bulk.wait_group.read / the aux mbarrier, and a plain store epilogue took
+    // 5 800 cycles per 128 x 256 tile.  So results go accumulator registers (lane = row) -> swizzled 4 KB staging chunk -> registers in
+    // the transposed mapping (8 lanes per 128-byte row segment) -> st.global.v4, full lines per quarter-warp; the residual / ReLU-mask
+    // operand comes in by ld.global.nc.v4 in the same mapping, one chunk ahead (registers), and through the same staging chunk.
+    // Only split-K accumulation (weight gradients: a few tiles) still uses TMA reduce-add.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const uint32_t epi = base + L::kEpiOff + q * (L::kEpiChunks * kChunkBytes);
-    uint8_t* epi_ptr = base_ptr + L::kEpiOff + q * (L::kEpiChunks * kChunkBytes);
+    const int h = (warp - kEpiWarp0) >> 2;
+    const int ew = warp - kEpiWarp0;
+    const uint32_t epi = base + L::kEpiOff + ew * kChunkBytes;
+    uint8_t* epi_ptr = base_ptr + L::kEpiOff + ew * kChunkBytes;
     const uint32_t sw = (uint32_t)(lane & 7);
-    int as = 0, ob = 0;
-    uint32_t aphase = 0, auxphase0 = 0, auxphase1 = 0;
+    const int tr = lane >> 3, ts = lane & 7;  // transposed mapping: instruction i covers rows 4 i + tr, 16-byte segment ts
+    uint8_t* own_row = epi_ptr + lane * 128;
+    const float* aux_src = aux_mode == 1 ? ep.residual : ep.relu_src;
+    const int aux_ld = aux_mode == 1 ? ep.ldr : ep.ld_relu;
+    const uint32_t drop_thr = dropout_threshold(ep.drop_rate);
+    const float drop_scale = 1.0f / (1.0f - ep.drop_rate);
+    int as = 0;
+    uint32_t aphase = 0;
+    auto aux_wanted = [&](int tile) { return aux_mode == 2 || (aux_mode == 1 && tile < tiles_mn); };  // the residual is added by split 0 only
+    auto chunks_of = [&](int tile) { const int n0 = ((tile % tiles_mn) % tl.tiles_n) * BN; return min(BN / 32, (N - n0 + 31) / 32); };
+    float4 an[8];  // aux operand of the NEXT chunk this warp will process, transposed mapping
+    auto fetch_aux = [&](int tile, int c) {
+      const int r = tile % tiles_mn;
+      const int grow0 = (r / tl.tiles_n) * kBM + q * 32 + tr, gcol = (r % tl.tiles_n) * BN + c * 32 + ts * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int grow = grow0 + 4 * i;
+        // plain (coherent) loads: the residual may be the output buffer itself (in-place x += ...); every element is read before the one warp that owns it writes it
+        an[i] = (grow < M && gcol < N) ? *reinterpret_cast<const float4*>(aux_src + (size_t)grow * aux_ld + gcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if constexpr (aux_mode != 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) an[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((int)blockIdx.x < num_tiles && aux_wanted(blockIdx.x) && h < chunks_of(blockIdx.x)) fetch_aux(blockIdx.x, h);
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int split = tile / tiles_mn, r = tile - split * tiles_mn;
       const int m0 = (r / tl.tiles_n) * kBM, n0 = (r % tl.tiles_n) * BN;
@@ -324,10 +353,6 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool lead_split = (split == 0);
       const bool use_aux = aux_mode != 0 && (aux_mode == 2 || lead_split);
       const int nchunks = min(BN / 32, (N - n0 + 31) / 32);
-      if (use_aux && lane == 0) {
-        mbar_expect_tx(aux_bar(q, 0), kChunkBytes);
-        tma_load_2d(epi + 2 * kChunkBytes, &tmAux, n0, row0, aux_bar(q, 0));
-      }
       bool flagged = false;
       if constexpr (EPI & kEpiRowflag) flagged = row < M && ep.rowflag[row];
       // The tile's bias row (BN columns) is fetched once, 8 columns per lane, while the accumulator is still being computed,
@@ -343,25 +368,45 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       wait_t(tfull_bar(as), aphase, w0);
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-      // One 32-column chunk: fused ops on the accumulator registers -> swizzled staging -> TMA store / reduce-add.
-      auto process = [&](const int c, uint32_t (&rr)[32]) {
+      auto release_acc = [&]() {  // this warp has its last chunk of the accumulator in registers
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+      };
+      if (h >= nchunks) release_acc();  // a one-chunk tail tile: the odd warp has nothing to read
+      for (int c = h; c < nchunks; c += 2) {
         const int col0 = n0 + c * 32;
-        if (use_aux && c + 1 < nchunks && lane == 0) {
-          const int b = (c + 1) & 1;
-          mbar_expect_tx(aux_bar(q, b), kChunkBytes);
-          tma_load_2d(epi + (2 + b) * kChunkBytes, &tmAux, col0 + 32, row0, aux_bar(q, b));
-        }
-        if (use_aux) {
-          if (c & 1) { mbar_wait(aux_bar(q, 1), auxphase1); auxphase1 ^= 1u; }
-          else { mbar_wait(aux_bar(q, 0), auxphase0); auxphase0 ^= 1u; }
-        }
-        if (lane == 0) {  // the staging buffer about to be overwritten has been read out
-          if (trace) { const long long t0 = clock64(); tma_wait_group_read<1>(); w1 += (unsigned long long)(clock64() - t0); }
-          else tma_wait_group_read<1>();
+        uint32_t rr[32];
+        if (trace) { const long long t0 = clock64(); tmem_ld32(tacc + (uint32_t)(c * 32), rr); w2 += (unsigned long long)(clock64() - t0); }
+        else tmem_ld32(tacc + (uint32_t)(c * 32), rr);
+        if (c + 2 >= nchunks) release_acc();
+        if (ep.atomic && lane == 0) {  // the staging chunk has been read out by the previous reduce-add
+          if (trace) { const long long t0 = clock64(); tma_wait_group_read<0>(); w1 += (unsigned long long)(clock64() - t0); }
+          else tma_wait_group_read<0>();
         }
         __syncwarp();
-        const uint8_t* auxp = epi_ptr + (2 + (c & 1)) * kChunkBytes + lane * 128;
-        uint8_t* outp = epi_ptr + ob * kChunkBytes + lane * 128;
+        if constexpr (aux_mode != 0) {
+          // this chunk's aux operand (fetched one chunk ago): registers (transposed mapping) -> staging -> own-row reads below; then
+          // start fetching the next chunk's (this tile's chunk c + 2, or the first chunk of this CTA's next tile)
+          if (use_aux) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(epi_ptr + (4 * i + tr) * 128 + ((ts ^ ((4 * i + tr) & 7)) << 4)) = an[i];
+          }
+          __syncwarp();
+          if (c + 2 < nchunks) {
+            if (use_aux) fetch_aux(tile, c + 2);
+          } else {
+            const int nt = tile + (int)gridDim.x;
+            if (nt < num_tiles && aux_wanted(nt) && h < chunks_of(nt)) fetch_aux(nt, h);
+          }
+        }
+        U4 dr = {0u, 0u, 0u, 0u};
+        float4 av[8];
+        if constexpr (aux_mode != 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) av[j] = use_aux ? *reinterpret_cast<const float4*>(own_row + ((j ^ sw) << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          __syncwarp();  // every lane has its aux row: the staging chunk may take the results
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float v[4] = {__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3])};
@@ -374,52 +419,37 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.0f);
           }
           float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-          if constexpr (aux_mode != 0) {
-            if (use_aux) a = *reinterpret_cast<const float4*>(auxp + ((j ^ sw) << 4));
-          }
+          if constexpr (aux_mode != 0) a = av[j];
           if constexpr (aux_mode == 2) {
             v[0] = a.x > 0.0f ? v[0] : 0.0f; v[1] = a.y > 0.0f ? v[1] : 0.0f;
             v[2] = a.z > 0.0f ? v[2] : 0.0f; v[3] = a.w > 0.0f ? v[3] : 0.0f;
           }
-          if constexpr (EPI & kEpiDropout)
-            dropout4(v, ((uint32_t)row + ep.drop_row0) * (uint32_t)N + (uint32_t)(col0 + 4 * j), ep.drop_rate, ep.drop_seed, ep.drop_step, ep.drop_site);
+          if constexpr (EPI & kEpiDropout) {  // one Philox block per eight columns (j even computes it, j odd uses its second half)
+            if ((j & 1) == 0) dr = philox4x32_10((((uint32_t)row + ep.drop_row0) * (uint32_t)N + (uint32_t)(col0 + 4 * j)) >> 3, ep.drop_site, 0u, 0u, ep.drop_seed, ep.drop_step);
+            dropout_apply4(v, (j & 1) ? dr.z : dr.x, (j & 1) ? dr.w : dr.y, drop_thr, drop_scale);
+          }
           if constexpr (EPI & kEpiRowflag) {
             if (flagged) { v[0] = v[1] = v[2] = v[3] = 0.0f; }
           }
           if constexpr (aux_mode == 1) { v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; }
-          *reinterpret_cast<float4*>(outp + ((j ^ sw) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(own_row + ((j ^ sw) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (ep.atomic) tma_reduce_add_2d(&tmOut, epi + ob * kChunkBytes, col0, row0);
-          else tma_store_2d(&tmOut, epi + ob * kChunkBytes, col0, out_row0);
-          tma_commit_group();
-        }
-        ob ^= 1;
-      };
-      // Software pipeline over the chunks: the TMEM load of chunk c+1 is in flight while chunk c is processed (the
-      // tcgen05.ld -> first-use latency was the top stall of the serial loop).  The accumulator is handed back to the
-      // MMA warp as soon as its last chunk sits in registers.
-      auto release_acc = [&]() {
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
-      };
-      uint32_t rr0[32], rr1[32];
-      tmem_ld32_issue(tacc, rr0);
-#pragma unroll 1
-      for (int c = 0; c < nchunks; c += 2) {
-        if (trace) { const long long t0 = clock64(); tmem_ld32_wait(rr0); w2 += (unsigned long long)(clock64() - t0); }
-        else tmem_ld32_wait(rr0);
-        if (c + 1 < nchunks) tmem_ld32_issue(tacc + (uint32_t)((c + 1) * 32), rr1);
-        else release_acc();
-        process(c, rr0);
-        if (c + 1 < nchunks) {
-          tmem_ld32_wait(rr1);
-          if (c + 2 < nchunks) tmem_ld32_issue(tacc + (uint32_t)((c + 2) * 32), rr0);
-          else release_acc();
-          process(c + 1, rr1);
+        if (ep.atomic) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tmOut, epi, col0, row0);
+            tma_commit_group();
+          }
+        } else {
+          __syncwarp();
+          const int gcol = col0 + ts * 4;
+          float* orow = ep.out + (size_t)(out_row0 + tr) * ep.ldo + gcol;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 o = *reinterpret_cast<const float4*>(epi_ptr + (4 * i + tr) * 128 + ((ts ^ ((4 * i + tr) & 7)) << 4));
+            if (row0 + 4 * i + tr < M && gcol < N) *reinterpret_cast<float4*>(orow + (size_t)(4 * i) * ep.ldo) = o;
+          }
         }
       }
       as ^= 1;
@@ -683,9 +713,8 @@ static int launch_tcgen05(TensorMapCache* cache, const GemmCall& c, cudaStream_t
     if (part_floats + col_floats > c.det_ws_floats) { set_error("gemm: deterministic scratch too small (%zu > %zu floats)", part_floats + col_floats, c.det_ws_floats); return MFP_ERR_ARG; }
     if (det_split) {
       if (c.ep.bias || c.ep.residual || c.ep.relu || c.ep.relu_src || c.ep.drop_enabled || c.ep.rowflag) { set_error("gemm: deterministic split-K takes a plain epilogue"); return MFP_ERR_ARG; }
-      mo = cache->get(c.det_ws, c.N, (uint64_t)tl.splits * tl.slab_rows, c.N, 32, 32, kMapEpilogue);
-      if (!mo) return MFP_ERR_CUDA;
-      mx = mo;
+      ep.out = c.det_ws;  // split s stores its tiles at row offset s * slab_rows of the scratch block
+      ep.ldo = c.N;
     }
     if (c.colsum) { det_col = c.det_ws + part_floats; colsum = det_col; tl.det_colsum = 1; }
   } else if (tl.splits > 1) {

@@ -71,15 +71,30 @@ const CUtensorMap* tensor_map_get(TensorMapCache* cache, const float* ptr, int r
 // impl: 0 = tcgen05, 1 = SIMT bring-up kernel.  Returns MFP_OK or an error (message via set_error).
 int launch_gemm(TensorMapCache* cache, const GemmCall& call, int impl, cudaStream_t stream);
 
-// keep-mask/scale of the engine's dropout sites (shared by the GEMM epilogue and the backward pass)
-__device__ __forceinline__ void dropout4(float (&v)[4], uint32_t e0, float rate, uint32_t seed, uint32_t step, uint32_t site) {
-  // e0 = index of v[0] in the flattened [T, D] activation, multiple of 4
-  const U4 r = philox4x32_10(e0 >> 2, site, 0u, 0u, seed, step);
+// keep-mask/scale of the engine's dropout sites (shared by the GEMM epilogue and the backward pass).
+// RNG contract: element e of the flattened [T, D] activation takes the 16-bit half (e & 7) of philox(counter = (e >> 3, site, 0, 0),
+// key = (seed, step)) -- words x, y, z, w hold halves (0,1), (2,3), (4,5), (6,7), low half first -- and is kept iff that half is
+// >= round(rate * 65536) (rate 0.1: 6554, i.e. P(drop) = 0.100006).  One Philox block serves eight elements: inside the GEMM
+// epilogues the generator was 70 % of the instructions of the dropout variants (and those epilogues are issue-bound).
+__device__ __forceinline__ uint32_t dropout_threshold(float rate) { return (uint32_t)(rate * 65536.0f + 0.5f); }
+__device__ __forceinline__ void dropout_apply4(float (&v)[4], uint32_t wa, uint32_t wb, uint32_t thr, float scale) {
+  v[0] = ((wa & 0xffffu) >= thr) ? v[0] * scale : 0.0f;
+  v[1] = ((wa >> 16) >= thr) ? v[1] * scale : 0.0f;
+  v[2] = ((wb & 0xffffu) >= thr) ? v[2] * scale : 0.0f;
+  v[3] = ((wb >> 16) >= thr) ? v[3] * scale : 0.0f;
+}
+__device__ __forceinline__ void dropout8(float (&lo)[4], float (&hi)[4], uint32_t e0, float rate, uint32_t seed, uint32_t step, uint32_t site) {
+  // e0 = index of lo[0] in the flattened [T, D] activation, multiple of 8; hi = the next four elements
+  const U4 r = philox4x32_10(e0 >> 3, site, 0u, 0u, seed, step);
+  const uint32_t thr = dropout_threshold(rate);
   const float scale = 1.0f / (1.0f - rate);
-  v[0] = (u01(r.x) >= rate) ? v[0] * scale : 0.0f;
-  v[1] = (u01(r.y) >= rate) ? v[1] * scale : 0.0f;
-  v[2] = (u01(r.z) >= rate) ? v[2] * scale : 0.0f;
-  v[3] = (u01(r.w) >= rate) ? v[3] * scale : 0.0f;
+  dropout_apply4(lo, r.x, r.y, thr, scale);
+  dropout_apply4(hi, r.z, r.w, thr, scale);
+}
+__device__ __forceinline__ void dropout4(float (&v)[4], uint32_t e0, float rate, uint32_t seed, uint32_t step, uint32_t site) {
+  // e0 multiple of 4: one half of the eight-element block (sites outside the hot loops)
+  const U4 r = philox4x32_10(e0 >> 3, site, 0u, 0u, seed, step);
+  dropout_apply4(v, (e0 & 4u) ? r.z : r.x, (e0 & 4u) ? r.w : r.y, dropout_threshold(rate), 1.0f / (1.0f - rate));
 }
 
 }  // namespace mfp

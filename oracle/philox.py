@@ -63,11 +63,13 @@ def box_muller(xa, xb):
 
 
 def dropout_keep(n_elements: int, site: int, rate: float, seed: int, step: int, first_element: int = 0) -> np.ndarray:
-    """Keep-mask (bool, n_elements) of one dropout site: element e uses word e&3 of
-    philox(counter=(e>>2, site, 0, 0), key=(seed, step)); keep iff u >= rate.  ``first_element`` (a multiple of 4) is the global
-    index of element 0 when the rows are a shard of a larger batch (mfp_set_doc_offset)."""
-    assert first_element % 4 == 0
-    n4 = (n_elements + 3) // 4
-    x = philox4x32_10(np.arange(n4) + first_element // 4, site, 0, 0, seed, step)
-    u = u01(np.stack(x, axis=1).reshape(-1)[:n_elements])
-    return u >= np.float32(rate)
+    """Keep-mask (bool, n_elements) of one dropout site (flex_dm_b200/csrc/gemm.cuh): element e takes the 16-bit half (e & 7) of
+    philox(counter = (e >> 3, site, 0, 0), key = (seed, step)) -- words x0..x3 hold halves (0,1), (2,3), (4,5), (6,7), low half first --
+    and is kept iff that half >= round(rate * 65536).  ``first_element`` (a multiple of 8) is the global index of element 0 when the rows
+    are a shard of a larger batch (mfp_set_doc_offset)."""
+    assert first_element % 8 == 0
+    n8 = (n_elements + 7) // 8
+    x = philox4x32_10(np.arange(n8) + first_element // 8, site, 0, 0, seed, step)
+    halves = np.stack([h for w in x for h in (w & np.uint32(0xFFFF), w >> np.uint32(16))], axis=1).reshape(-1)[:n_elements]
+    threshold = np.uint32(int(np.float32(rate) * np.float32(65536.0) + np.float32(0.5)))
+    return halves >= threshold

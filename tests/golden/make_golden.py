@@ -72,14 +72,14 @@ CASES = OrderedDict([
     # --context id / length: a learned special token (task id / document length) joins the sequence (encoder.py:96-110,231-249; decoder.py:74-78).
     # Every document leaves the last row free: the engine keeps the token in the row after a document's last element.
     ("crello_ctx_id", ("crello", "elem_pos_attr_img_txt", 4, 11, 2, 21, 2, [10, 4, 1, 7], [1, 3, 5, 6])),
-    ("rico_ctx_length", ("rico", "elem_pos_attr", 4, 9, 2, 23, 1, [8, 3, 1, 5], [3, 1, 4, 3])),
+    ("rico_ctx_length", ("rico", "elem_pos_attr", 4, 9, 2, 30, 1, [8, 3, 1, 5], [3, 1, 4, 3])),
     # --context canvas (token = sum of the canvas columns' embeddings; the decoder gains never-read canvas heads) and canvas_add (that
     # sum added to every element; no token, so the batch may be full length): encoder.py:34-37,177-199,228-249, decoder.py:25-43
     ("crello_ctx_canvas", ("crello", "random", 3, 9, 2, 49, 0, [8, 1, 5], None)),
     ("crello_ctx_canvas_add", ("crello", "elem_pos_attr_img_txt", 3, 8, 2, 27, 1, [8, 1, 6], [4, 1, 6])),
     # --context id with --input_dtype shuffled_set: the token is put in front first and the PositionEmbedding (with its dropout) is added to
     # token + elements afterwards (encoder.py:247-252).  Oracle only: the product path refuses the combination (flex_dm_b200/mfp.py).
-    ("rico_ctx_id_shuffled", ("rico", "elem_pos_attr", 4, 9, 2, 31, 2, [8, 3, 1, 5], [0, 3, 1, 4])),
+    ("rico_ctx_id_shuffled", ("rico", "elem_pos_attr", 4, 9, 2, 37, 2, [8, 3, 1, 5], [0, 3, 1, 4])),
     # ... and --context length with --input_dtype sorted_set on crello (numerical fields, loss conditions)
     ("crello_ctx_length_sorted", ("crello", "random", 3, 10, 2, 33, 1, [9, 4, 1], None)),
 ])

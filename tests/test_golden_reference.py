@@ -28,13 +28,13 @@ CASES = {  # name: (dataset, masking_method, num_blocks, seed, step)
     # --context id / length (encoder.py:96-110,231-249): the batch keeps one free row per document for the context token; the
     # reference ran on the same batch cut to its longest document, so its arrays have one column less (``cut``)
     "crello_ctx_id": ("crello", "elem_pos_attr_img_txt", 2, 21, 2),
-    "rico_ctx_length": ("rico", "elem_pos_attr", 2, 23, 1),
+    "rico_ctx_length": ("rico", "elem_pos_attr", 2, 30, 1),
     # --context canvas (token = sum of the canvas columns' embeddings) / canvas_add (that sum added to every element; no token)
     "crello_ctx_canvas": ("crello", "random", 2, 49, 0),
     "crello_ctx_canvas_add": ("crello", "elem_pos_attr_img_txt", 2, 27, 1),
     # --context id with --input_dtype shuffled_set: positions are added after the token was put in front (encoder.py:247-252; engine:
     # PosEmbed::shift, pos_embed_bwd_ctx_kernel)
-    "rico_ctx_id_shuffled": ("rico", "random_elem_pos_attr", 2, 31, 2),
+    "rico_ctx_id_shuffled": ("rico", "random_elem_pos_attr", 2, 37, 2),
     "crello_ctx_length_sorted": ("crello", "random", 2, 33, 1),  # ... and --context length with --input_dtype sorted_set
 }
 BLOCK_TYPE = {"crello_postln": "transformer"}
@@ -254,14 +254,17 @@ def test_engine_checks_accept_the_oracle_run(case):
     check_adam_heads(_flat(params), g, 1)
 
 
-def test_engine_checks_accept_a_tf32_emulated_run():
-    """... and the oracle's TF32 emulation (round-to-nearest-even operands, the rule measured on the tcgen05 path by
-    tests/test_gpu_parity.py::test_tf32_operand_rounding_of_the_product_path) passes them at the product path's tolerances."""
-    for case in ("crello_ctx_canvas", "crello_postln"):
-        g = np.load(os.path.join(GOLDEN, case + ".npz"))
-        rna, rna_params = oracle_step(case, tf32=O.tf32_round)
-        check_gradient_summaries(_flat(rna), g, H.GRAD_REL_L2)
-        check_adam_heads(_flat(rna_params), g, 0)
+@pytest.mark.parametrize("case", list(CASES))
+def test_fixtures_are_stable_under_tf32_rounding(case):
+    """Every fixture must be a fair target for the TF32 product path: the oracle's TF32 emulation (round-to-nearest-even operands, the rule
+    measured on the tcgen05 path by tests/test_gpu_parity.py::test_tf32_operand_rounding_of_the_product_path) passes the GPU test's checks at
+    the product path's tolerances.  A fixture that fails here hinges on a discrete event inside TF32's rounding error -- a ReLU gate at zero
+    (tools/tf32_gate_scan.py), or two predicted elements of a rico ``pos`` document swapping places in the argmax sort of the loss
+    (tensor_utils.py:14-44) -- and gets another seed in tests/golden/make_golden.py instead of a test that accepts two answers."""
+    g = np.load(os.path.join(GOLDEN, case + ".npz"))
+    rna, rna_params = oracle_step(case, tf32=O.tf32_round)
+    check_gradient_summaries(_flat(rna), g, H.GRAD_REL_L2)
+    check_adam_heads(_flat(rna_params), g, 0)
 
 
 # ================================================================================================= GPU (C ABI)

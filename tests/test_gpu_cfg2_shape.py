@@ -47,8 +47,9 @@ def _engine_step(dataset, method, impl, lengths):
     return cols, m, batch, length, dcols, tasks, logits
 
 
-def _window_oracle(cols, m, batch, lo, hi):
-    """The oracle on documents [lo, hi) of the batch at their global offset: masks, training logits, sum-loss / B and its gradients."""
+def _window_oracle(cols, m, batch, lo, hi, skip_sorted=False):
+    """The oracle on documents [lo, hi) of the batch at their global offset: masks, training logits, sum-loss / B and its gradients.
+    ``skip_sorted``: leave the documents of the rico ``pos`` task (sorted loss branch) out of the loss."""
     sub = {k: v[lo:hi] for k, v in batch.items()}
     draws = O.PhiloxDraws(SEED, STEP, doc_offset=lo)
     tasks = draws.tasks(hi - lo, m.task_ids)
@@ -58,11 +59,14 @@ def _window_oracle(cols, m, batch, lo, hi):
     params = OrderedDict((k, v.requires_grad_(True)) for k, v in H.oracle_params_from_engine(m.engine).items())
     outputs = O.model_forward(params, omod, icols, L, keep, 0.1)
     sort_flag = (torch.as_tensor(tasks) == m.task_names.index("pos")) if m.sort_pos else None
+    full_masks = omasks
+    if skip_sorted:
+        omasks = {k: (v & ~sort_flag.reshape(-1, *([1] * (v.dim() - 1))) if v.dim() > 1 else v) for k, v in omasks.items()}
     total, losses, scores, _ = O.loss_layer(targets, outputs, omasks, cols, sort_flag)
     scaled = total * (hi - lo) / B  # loss_layer takes the mean over ITS batch (metrics.py:277); the engine divides by the global B
     scaled.backward()
     grads = OrderedDict((k, (v.grad if v.grad is not None else torch.zeros_like(v)).numpy()) for k, v in params.items())
-    return tasks, omod, omasks, outputs, float(scaled.detach()), losses, scores, grads
+    return tasks, omod, full_masks, outputs, float(scaled.detach()), losses, scores, grads
 
 
 @pytest.mark.parametrize("impl", [1, 0], ids=["fp32-simt", "tf32-tcgen05"])
@@ -78,8 +82,14 @@ def test_full_shape_step_matches_oracle_on_document_windows(dataset, method, len
     # 128 rows per document = one M-tile each: first / middle / last tiles.  Eight documents per window: a gradient summed over fewer
     # elements hangs on individual ReLU gates that TF32 rounding may flip (tools/tf32_gate_scan.py), which is fixture noise, not parity
     windows = [(0, 8), (124, 132), (248, 256)]
+    # rico "pos" documents pair predictions and targets after sorting the PREDICTED elements by the argmax of their logits
+    # (tensor_utils.py:14-44 with from_logits): under TF32 a near-tie swaps two elements and moves loss and gradients discretely, which is
+    # not a parity defect.  The sort / permuted-loss kernels do not depend on the GEMM precision and are held to the oracle on the fp32
+    # path (all documents); on the TF32 path the loss and gradient comparison leaves the sorted documents out.
+    skip_sorted = bool(m.sort_pos and impl == 0)
+    pos_id = m.task_names.index("pos")
     for lo, hi in windows:
-        otasks, omod, omasks, outputs, oloss, olosses, oscores, ograds = _window_oracle(cols, m, batch, lo, hi)
+        otasks, omod, omasks, outputs, oloss, olosses, oscores, ograds = _window_oracle(cols, m, batch, lo, hi, skip_sorted)
         assert np.array_equal(tasks[lo:hi].cpu().numpy(), otasks)
         for f, key in enumerate(m.keys):
             assert np.array_equal(full_masks[f][lo:hi].cpu().numpy().astype(bool), omasks[key].numpy()), key
@@ -97,6 +107,8 @@ def test_full_shape_step_matches_oracle_on_document_windows(dataset, method, len
         for f in range(F):
             eng.masks[f].zero_()
             eng.masks[f][lo:hi].copy_(full_masks[f][lo:hi])
+            if skip_sorted:
+                eng.masks[f][lo:hi][tasks[lo:hi] == pos_id] = 0
         row = torch.zeros(eng.metrics_width, device="cuda")
         eng.loss(length, dcols, eng.masks, row, 1.0 / B, True, sort_tasks=tasks if m.sort_pos else None)
         eng.backward(length, None, True, SEED, STEP)
@@ -104,10 +116,7 @@ def test_full_shape_step_matches_oracle_on_document_windows(dataset, method, len
         r = row.cpu().numpy()
         assert r[3 * F] == pytest.approx(oloss, rel=loss_rtol), (lo, r[3 * F], oloss)
         for f, key in enumerate(m.keys):
-            # rico "pos" documents pair predictions and targets after sorting the PREDICTED elements by the argmax of their logits
-            # (tensor_utils.py:14-44 with from_logits): a TF32 near-tie re-pairs two elements and moves a per-field loss discretely
-            key_rtol = 1e-2 if (m.sort_pos and impl == 0) else loss_rtol
-            assert r[3 * f] == pytest.approx(float(olosses[key]) * (hi - lo) / B, rel=key_rtol, abs=1e-6), key
+            assert r[3 * f] == pytest.approx(float(olosses[key]) * (hi - lo) / B, rel=loss_rtol, abs=1e-6), key
         got_grads = eng.get_weights(eng.grads)
         table = []
         for name, g in ograds.items():

@@ -360,7 +360,9 @@ def test_train_steps_track_oracle_loss():
         row = m.train_step(batch)
         got = m.metrics_from_row(row)
         ref = o.train_step(batch, seed=21, step=step)
-        assert got["loss"] == pytest.approx(ref["loss"], rel=H.LOSS_RTOL), step
+        # after two Adam updates of lr = 1e-3 the two runs no longer hold the same weights: Adam normalises every gradient entry to ~lr,
+        # so TF32-sized errors on near-zero entries become lr-sized weight differences (see the weight checks below)
+        assert got["loss"] == pytest.approx(ref["loss"], rel=H.LOSS_RTOL if step < 2 else 5 * H.LOSS_RTOL), step
         assert got["total_score"] == pytest.approx(ref["metrics"]["total_score"], abs=2e-2)
     w = m.get_weights()
     for name in ("model/blocks/seq2seq/seq2seq_1/attn/combine_heads/kernel", "model/decoder/decoders/left/kernel"):
