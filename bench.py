@@ -303,11 +303,17 @@ class Workload:
         # synthetic data: distinct batches per rank (seed = 1000 * rank + i), pinned on the host for the e2e leg
         host = [make_synthetic_batch(cols, self.B, self.S, seed=1000 * rank + i, lengths="full") for i in range(N_DEVICE_BATCHES)]
         needed = [k for k, c in model.input_columns.items() if k == "length" or c["is_sequence"]]
+        from flex_dm_b200.data import pack_batch
+
         self.pinned = [{k: torch.from_numpy(b[k]).pin_memory() for k in needed} for b in host]
+        # the input pipeline's packed column format (flex_dm_b200.data.pack_batch): embedding rows of elements whose type does not carry
+        # the field are not stored -- the reference's filter_padding overwrites them with <UNUSED> before the model reads them
+        self.pinned_packed = [{k: torch.from_numpy(v).pin_memory() for k, v in pack_batch({k: b[k] for k in needed}, cols).items()} for b in host]
         self.resident = [model.stage(b) for b in self.pinned]
         torch.cuda.synchronize()
         self.elements_per_step = self.B * self.S  # every document is full length: valid elements = B * S
-        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.pinned[0].values())
+        self.h2d_bytes_dense = sum(t.numel() * t.element_size() for t in self.pinned[0].values())
+        self.h2d_bytes = sum(t.numel() * t.element_size() for b in self.pinned_packed for t in b.values()) // len(self.pinned_packed)
 
     def step_resident(self, i):
         return self.model.train_step(self.resident[i % N_DEVICE_BATCHES], staged=True)
@@ -497,21 +503,25 @@ def main():
 
     rows_host = torch.empty((args.steps, model.engine.metrics_width), dtype=torch.float32).pin_memory()
 
-    def host_batches():
+    def host_batches(source):
         i = 0
         while True:
-            yield wl.pinned[i % N_DEVICE_BATCHES]
+            yield source[i % N_DEVICE_BATCHES]
             i += 1
 
-    feeder = DevicePrefetcher(model, host_batches())
+    def e2e_leg(source):
+        feeder = DevicePrefetcher(model, host_batches(source))
 
-    def step_e2e(i):
-        row = model.train_step(next(feeder), staged=True)
-        rows_host[i % args.steps].copy_(row, non_blocking=True)
+        def step_e2e(i):
+            row = model.train_step(next(feeder), staged=True)
+            rows_host[i % args.steps].copy_(row, non_blocking=True)
 
-    for i in range(3):
-        step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
+        for i in range(3):
+            step_e2e(i)
+        return timed(step_e2e, args.steps)
+
+    ms_e2e_dense = e2e_leg(wl.pinned)        # dense DataSpec.parse_fn columns: 4136 B per element for crello
+    ms_e2e = e2e_leg(wl.pinned_packed)       # packed columns (the pipeline's default format)
     e2e_value = world * elements_per_step * args.steps / (ms_e2e * 1e-3)
     last_loss = wl.global_loss(rows_host[args.steps - 1])
     assert np.isfinite(last_loss), last_loss
@@ -573,7 +583,6 @@ def main():
     others = None
     if not args.no_other_configs and args.config == 2:
         others = {}
-        del feeder
         for c in (3, 4, 5):
             if CONFIGS[c]["scaling"] == "strong" and CONFIGS[c]["B"] % world:
                 continue
@@ -599,12 +608,17 @@ def main():
                 "config": {"workload": "%s: L=%d D=256 H=8 FFN=512, %d documents per GPU, all documents full length, dropout=0.1 l2=1e-2 "
                                        "Adam(1e-4, clipnorm=1.0)" % (w["name"], wl.L, wl.B),
                            "global_batch": wl.B * world, "seq_len": wl.S, "parallelism": "dp%d" % world,
-                           "l2_flush": "inputs larger than L2: %d distinct resident batches (%.0f MB) rotate; activations per step 1.6 GB" % (N_DEVICE_BATCHES, N_DEVICE_BATCHES * h2d_bytes / 1e6),
+                           "l2_flush": "inputs larger than L2: %d distinct resident batches (%.0f MB) rotate; activations per step 1.6 GB" % (N_DEVICE_BATCHES, N_DEVICE_BATCHES * wl.h2d_bytes_dense / 1e6),
                            "loss_step0": step0 if step0 is not None else {"engine": loss0, "note": "global loss (metric rows summed over ranks); the oracle value is pinned at N=1"},
                            "loss_last_step": last_loss},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps,
-                        "h2d_gbs_per_gpu": h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9},
+                        "h2d_gbs_per_gpu": h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9,
+                        "input_format": "packed columns in pinned host memory (flex_dm_b200.data.pack_batch: embedding rows of elements whose type does not "
+                                        "carry the field are not stored) -> DevicePrefetcher (copy stream) -> MFP.train_step; metrics row read back every step",
+                        "dense_columns": {"value": world * elements_per_step * args.steps / (ms_e2e_dense * 1e-3), "unit": UNIT,
+                                          "ms_per_step": ms_e2e_dense / args.steps, "h2d_bytes_per_step": wl.h2d_bytes_dense,
+                                          "h2d_gbs_per_gpu": wl.h2d_bytes_dense / (ms_e2e_dense / args.steps * 1e-3) / 1e9}},
                 "gpu_launches": int(launches), "clocks": clocks}
         if check is not None:
             line["dp_check"] = check

@@ -68,6 +68,10 @@ struct Schema {
 struct BatchPtrs {
   const int* length;             // [B] zero-based
   const void* cols[kMaxFields];  // int32 [T,C] or float [T,C]
+  // Packed numerical columns (mfp_set_packed_rows): rowmap[f] != null means cols[f] is float [n_rows, C] holding only the elements that
+  // carry the field (valid position and type gate), and rowmap[f][t] is element t's row or -1 -- a missing row reads as <UNUSED>, which
+  // is what filter_padding (masking.py:24-53) turns those elements into anyway.
+  const int* rowmap[kMaxFields];
 };
 
 struct MaskPtrs {

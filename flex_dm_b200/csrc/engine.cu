@@ -48,7 +48,8 @@ struct mfp_engine {
   long long ctx_off = -1;  // --context id / length: embedding table of the context token, rows = cfg.context_rows
   const int32_t* ctx_ids = nullptr;  // --context id: device task ids of the current batch (mfp_set_context_ids)
   long long canvas_off[MFP_MAX_CANVAS] = {0};  // --context canvas / canvas_add: embedding tables of the canvas columns
-  const int32_t* canvas_ids[MFP_MAX_CANVAS] = {nullptr};  // device columns of the current batch (mfp_set_canvas_columns)
+  const int32_t* canvas_ids[MFP_MAX_CANVAS] = {nullptr};
+  const int32_t* rowmaps[MFP_MAX_FIELDS] = {nullptr};  // packed numerical input / target columns (mfp_set_packed_rows)  // device columns of the current batch (mfp_set_canvas_columns)
   // bound state
   int B = 0, S = 0, T = 0;
   uint8_t* ws = nullptr;
@@ -244,11 +245,22 @@ static Workspace plan_workspace(const mfp_engine* h, int B, int S) {
 template <typename Tp>
 static Tp* wsp(const mfp_engine* h, size_t off) { return reinterpret_cast<Tp*>(h->ws + off); }
 
-static BatchPtrs to_batch(const mfp_engine* h, const mfp_batch* b) {
+// packed: the batch is the caller's input / target batch, whose numerical columns may be packed (mfp_set_packed_rows); the engine's own
+// modified columns are always dense
+static BatchPtrs to_batch(const mfp_engine* h, const mfp_batch* b, bool packed = false) {
   BatchPtrs p{};
   p.length = b->length;
-  for (int f = 0; f < h->sc.F; ++f) p.cols[f] = b->cols[f];
+  for (int f = 0; f < h->sc.F; ++f) {
+    p.cols[f] = b->cols[f];
+    p.rowmap[f] = (packed && h->sc.f[f].kind == 1) ? h->rowmaps[f] : nullptr;
+  }
   return p;
+}
+
+static bool any_packed(const mfp_engine* h) {
+  for (int f = 0; f < h->sc.F; ++f)
+    if (h->rowmaps[f]) return true;
+  return false;
 }
 
 static int canvas_args(const mfp_engine* h, CanvasArgs* ca) {
@@ -479,13 +491,14 @@ int mfp_mask_corrupt(mfp_engine* h, const mfp_batch* inputs, const int32_t* task
   for (int f = 0; f < h->sc.F; ++f) { out.cols[f] = modified_cols[f]; out.masks[f] = masks_out[f]; }
   h->launches++;
   h->flags_for = h->sc.n_num > 0 ? modified_cols[first_numerical(h->sc)] : nullptr;  // the encoder's row flags come out of the same pass
-  return launch_mask_corrupt(h->sc, to_batch(h, inputs), tasks, nullptr, h->B, h->S, seed, step, out, (cudaStream_t)stream,
+  return launch_mask_corrupt(h->sc, to_batch(h, inputs, true), tasks, nullptr, h->B, h->S, seed, step, out, (cudaStream_t)stream,
                              wsp<unsigned char>(h, h->off.flags), h->doc0);
 }
 
 int mfp_shuffle_inputs(mfp_engine* h, const mfp_batch* inputs, uint32_t seed, uint32_t step, void* const* shuffled_cols, int32_t* perm_out, void* stream) {
   MFP_TRY(check_bound(h));
   if (!inputs || !shuffled_cols) { set_error("mfp_shuffle_inputs: null argument"); return MFP_ERR_ARG; }
+  if (any_packed(h)) { set_error("mfp_shuffle_inputs: packed columns are not supported here (expand them first)"); return MFP_ERR_UNSUPPORTED; }
   ModifiedPtrs out{};
   for (int f = 0; f < h->sc.F; ++f) {
     if (!shuffled_cols[f] || shuffled_cols[f] == inputs->cols[f]) { set_error("mfp_shuffle_inputs: output columns must be distinct buffers"); return MFP_ERR_ARG; }
@@ -505,13 +518,23 @@ int mfp_mask_for_test(mfp_engine* h, const mfp_batch* inputs, const uint8_t* con
   for (int f = 0; f < h->sc.F; ++f) { out.cols[f] = modified_cols[f]; tm.m[f] = masks[f]; }
   h->launches++;
   h->flags_for = h->sc.n_num > 0 ? modified_cols[first_numerical(h->sc)] : nullptr;
-  return launch_mask_corrupt(h->sc, to_batch(h, inputs), nullptr, &tm, h->B, h->S, 0, 0, out, (cudaStream_t)stream, wsp<unsigned char>(h, h->off.flags));
+  return launch_mask_corrupt(h->sc, to_batch(h, inputs, true), nullptr, &tm, h->B, h->S, 0, 0, out, (cudaStream_t)stream, wsp<unsigned char>(h, h->off.flags));
 }
 
 int mfp_set_context_ids(mfp_engine* h, const int32_t* task_ids) {
   if (!h) { set_error("mfp_set_context_ids: null engine"); return MFP_ERR_ARG; }
   if (h->cfg.context != 1) { set_error("mfp_set_context_ids: the engine was not created with context = id"); return MFP_ERR_STATE; }
   h->ctx_ids = task_ids;
+  return MFP_OK;
+}
+
+int mfp_set_packed_rows(mfp_engine* h, const int32_t* const* rowmaps) {
+  if (!h) { set_error("mfp_set_packed_rows: null engine"); return MFP_ERR_ARG; }
+  for (int f = 0; f < h->sc.F; ++f) {
+    const int32_t* m = rowmaps ? rowmaps[f] : nullptr;
+    if (m && h->sc.f[f].kind != 1) { set_error("mfp_set_packed_rows: field %d is categorical (only numerical columns pack)", f); return MFP_ERR_ARG; }
+    h->rowmaps[f] = m;
+  }
   return MFP_OK;
 }
 
@@ -667,7 +690,7 @@ int mfp_loss(mfp_engine* h, const mfp_batch* targets, const uint8_t* const* mask
   MFP_TRY(check_bound(h));
   if (!metrics_out) { set_error("mfp_loss: metrics_out is required"); return MFP_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
-  const BatchPtrs tg = to_batch(h, targets);
+  const BatchPtrs tg = to_batch(h, targets, true);
   MaskPtrs mp{};
   for (int f = 0; f < h->sc.F; ++f) mp.m[f] = masks[f];
   LossBuffers buf{wsp<float>(h, h->off.part), wsp<int>(h, h->off.idx_true), wsp<int>(h, h->off.idx_pred)};

@@ -156,7 +156,9 @@ __global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ Schem
       }
     } else {
       // metrics.py:52-57,246-248: sum_d (yhat - y)^2; score = 0.5 cos + 0.5 (l2_normalize eps 1e-12)
-      const float* y = reinterpret_cast<const float*>(targets.cols[f]) + tt * fd.C;
+      // packed target column (mfp_set_packed_rows): w implies a valid element that carries the field, i.e. a row exists
+      const size_t yrow = targets.rowmap[f] ? (size_t)max(__ldg(targets.rowmap[f] + tt), 0) : tt;
+      const float* y = reinterpret_cast<const float*>(targets.cols[f]) + yrow * fd.C;
       const float* x = lrow + fd.logit_off;
       float sq = 0.f, yy = 0.f, xx = 0.f, xy = 0.f;
       for (int c = lane; c < fd.C; c += 32) {

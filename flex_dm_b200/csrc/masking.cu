@@ -50,7 +50,13 @@ __global__ void __launch_bounds__(256) mask_corrupt_kernel(const __grid_constant
   for (int f = 0; f < sc.F; ++f) {
     const FieldDev fd = sc.f[f];
     // filter_padding (masking.py:24-53)
-    const bool unused = !valid || (fd.has_cond && !((fd.cond_mask >> type_val) & 1ull));
+    bool unused = !valid || (fd.has_cond && !((fd.cond_mask >> type_val) & 1ull));
+    size_t src_row = (size_t)t;
+    if (fd.kind == 1 && in.rowmap[f]) {  // packed column: element t's row, or none (<UNUSED>)
+      const int pr = __ldg(in.rowmap[f] + t);
+      unused = unused || pr < 0;
+      src_row = pr < 0 ? 0 : (size_t)pr;
+    }
     int action = 0;  // 0 keep filtered, 1 <MASK>, 2 random token
     bool mfp = false;
     if (mode == 1) {
@@ -81,7 +87,7 @@ __global__ void __launch_bounds__(256) mask_corrupt_kernel(const __grid_constant
         reinterpret_cast<int*>(out.cols[f])[(size_t)t * fd.C + lane] = v;
       }
     } else {
-      const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in.cols[f]) + (size_t)t * fd.C);
+      const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in.cols[f]) + src_row * fd.C);
       float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out.cols[f]) + (size_t)t * fd.C);
       bool all_mask = true, all_null = true;  // the encoder's by-value special-token test (row_flags_kernel), on what is written
       int q_begin = lane;

@@ -97,6 +97,7 @@ _SIGNATURES = {
     "mfp_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "mfp_set_gemm_impl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     "mfp_set_deterministic": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
+    "mfp_set_packed_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     "mfp_set_doc_offset": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
     "mfp_profile_begin": (ctypes.c_int, [ctypes.c_void_p]),
     "mfp_profile_end": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double)]),
@@ -420,6 +421,17 @@ class Engine:
     def set_gemm_impl(self, impl: int):
         """0 = tcgen05 TF32 (product path), 1 = fp32 SIMT bring-up GEMM (tests only)."""
         _check(self.lib, self.lib.mfp_set_gemm_impl(self.handle, int(impl)), "mfp_set_gemm_impl")
+
+    def set_packed_rows(self, rowmaps: Optional[List[Optional[torch.Tensor]]]):
+        """Declares the numerical columns of the following input / target batches packed (``mfp_set_packed_rows``): ``rowmaps[f]`` is a
+        device int32 ``[B*S]`` tensor (element -> row of the packed column, -1 = none) or None for a dense column; None clears."""
+        if rowmaps is None or all(r is None for r in rowmaps):
+            self._rowmaps = None
+            _check(self.lib, self.lib.mfp_set_packed_rows(self.handle, None), "mfp_set_packed_rows")
+            return
+        self._rowmaps = rowmaps  # keeps the tensors alive while the engine holds their pointers
+        ptrs = _PTR_ARRAY(*[(r.data_ptr() if r is not None else None) for r in rowmaps])
+        _check(self.lib, self.lib.mfp_set_packed_rows(self.handle, ctypes.cast(ptrs, ctypes.POINTER(ctypes.c_void_p))), "mfp_set_packed_rows")
 
     def set_deterministic(self, on: bool = True):
         """Fixed-order gradient reductions: two runs of the same step are bit-identical (slower than the arrival-order default)."""

@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import checkpoint
+from .data import ROWS_SUFFIX, unpack_column
 from .engine import Engine
 from .masking import get_task_names
 from .parallel import all_reduce_gradient_slice, all_reduce_gradients, broadcast_parameters, reduce_metric_rows
@@ -214,6 +215,10 @@ class MFP:
             if x.device != self.device:
                 x = x.to(self.device, non_blocking=non_blocking)
             out[key] = x.contiguous()
+            if key + ROWS_SUFFIX in inputs:  # packed numerical column (flex_dm_b200.data.pack_batch): its element -> row map travels with it
+                r = inputs[key + ROWS_SUFFIX]
+                r = torch.from_numpy(r) if isinstance(r, np.ndarray) else r
+                out[key + ROWS_SUFFIX] = r.to(device=self.device, dtype=torch.int32, non_blocking=non_blocking).contiguous()
         return out
 
     def host_columns(self, inputs: Dict) -> Dict[str, torch.Tensor]:
@@ -229,17 +234,36 @@ class MFP:
                 x = torch.from_numpy(x)
             want = torch.float32 if column.get("type") == "numerical" else torch.int32
             out[key] = (x if x.dtype == want else x.to(want)).contiguous()
+            if key + ROWS_SUFFIX in inputs:
+                r = inputs[key + ROWS_SUFFIX]
+                r = torch.from_numpy(r) if isinstance(r, np.ndarray) else r
+                out[key + ROWS_SUFFIX] = (r if r.dtype == torch.int32 else r.to(torch.int32)).contiguous()
         return out
 
-    def _bind(self, staged: Dict[str, torch.Tensor]):
+    def _bind(self, staged: Dict[str, torch.Tensor], dense: bool = False):
+        """Binds the engine to the batch's shape.  Packed numerical columns (``flex_dm_b200.data.pack_batch``) are handed to the engine as
+        they are (``mfp_set_packed_rows``); ``dense=True`` -- or a path the engine does not take packed columns on (shuffled / sorted
+        inputs) -- expands them on the device first."""
+        rows = [staged.get(k + ROWS_SUFFIX) for k in self.keys]
+        if any(r is not None for r in rows) and (dense or self.input_dtype != "set"):
+            staged = dict(staged)
+            for k, r in zip(self.keys, rows):
+                if r is not None:
+                    staged[k] = unpack_column(staged[k], r)
+                    del staged[k + ROWS_SUFFIX]
+            rows = [None] * len(self.keys)
         cols = [staged[k] for k in self.keys]
         self._staged = staged
-        if self.context in ("id", "length", "canvas") and self._pad_context:
+        pad = self.context in ("id", "length", "canvas") and self._pad_context
+        if pad:
             # the context token (encoder.py:231-249) takes the row after each document's last element: one more (padding) row so
             # that full-length documents have one too; callers see the caller's S again (``_crop``)
-            cols = [torch.nn.functional.pad(c, (0, 0, 0, 1)) for c in cols]
-        B, S = cols[0].shape[:2]
+            cols = [c if r is not None else torch.nn.functional.pad(c, (0, 0, 0, 1)) for c, r in zip(cols, rows)]
+            rows = [None if r is None else torch.nn.functional.pad(r, (0, 1), value=-1) for r in rows]
+        first_dense = next(c for c, r in zip(cols, rows) if r is None)
+        B, S = first_dense.shape[:2]
         self.engine.bind(int(B), int(S))
+        self.engine.set_packed_rows([None if r is None else r.reshape(-1).contiguous() for r in rows])
         if self._world > 1:
             self.engine.set_doc_offset(self._rank * int(B))
         if self._ring is None:
@@ -397,7 +421,7 @@ class MFP:
         """MFP.call (mfp.py:298-347)."""
         is_demo = True if demo_args else False
         staged = self.stage(inputs)
-        B, S, length, cols = self._bind(staged)
+        B, S, length, cols = self._bind(staged, dense=True)  # merge_inputs_and_prediction copies ground-truth values: dense columns
         eng, seed, step = self.engine, self.seed, self._step
         tasks = eng.sample_tasks(self.task_ids, seed, step)  # mfp.py:301
         if is_demo and "tasks" in demo_args:  # preprocess_for_test(..., demo_args.get("tasks", tasks)) (mfp.py:307-312)
@@ -512,7 +536,7 @@ class MFP:
         encoder -> blocks -> decoder on already-corrupted inputs; returns the raw per-field outputs
         (decoder.py:96-110): categorical ``(B,S,C,input_dim)``, numerical ``(B,S,C)``."""
         staged = self.stage(modified_inputs)
-        B, S, length, cols = self._bind(staged)
+        B, S, length, cols = self._bind(staged, dense=True)  # already-corrupted inputs feed the encoder GEMMs directly
         eng = self.engine
         if self.context == "id":
             t = modified_inputs["task"]  # added by preprocess_for_train / preprocess_for_test (mfp.py:91,137)

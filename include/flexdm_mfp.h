@@ -145,6 +145,15 @@ int mfp_set_context_ids(mfp_engine* h, const int32_t* task_ids);
 /* --context canvas / canvas_add: the canvas columns of the current batch (n_canvas device int32 [B] arrays, config order); kept like the ids. */
 int mfp_set_canvas_columns(mfp_engine* h, const int32_t* const* columns);
 
+/* Packed numerical columns.  A numerical sequence column of DataSpec.parse_fn (data/spec.py:255-287: float [B,S,512]) is mostly rows
+ * the model never reads: filter_padding (masking.py:24-53) overwrites every padded position and every element whose type does not
+ * carry the field (loss_condition, data/crello-spec.yml:88-121) with <UNUSED>, and LossLayer gates the same elements out of the loss
+ * (metrics.py:251-267).  rowmaps[f] != NULL (device int32 [B*S]) declares that cols[f] of the batches passed to mfp_mask_corrupt,
+ * mfp_mask_for_test (inputs) and mfp_loss (targets) is float [n_rows, C] holding only the rows that ARE read, rowmaps[f][t] being
+ * element t's row or -1.  Results are identical to the dense column; host->device traffic and the corruption pass's reads shrink to the
+ * rows in use.  The pointers are kept until the next call; rowmaps = NULL returns to dense columns.  Not accepted by mfp_shuffle_inputs. */
+int mfp_set_packed_rows(mfp_engine* h, const int32_t* const* rowmaps);
+
 int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint32_t seed, uint32_t step,
                 float* logits_out, void* stream);
 
