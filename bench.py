@@ -280,6 +280,8 @@ def step0_golden(config):
 class Workload:
     """One bench configuration on this rank: model, resident + pinned batches, the step function."""
 
+    gemm_impl = 0
+
     def __init__(self, config, world, rank, dev, dist):
         import torch
 
@@ -298,6 +300,7 @@ class Workload:
         self.cols = cols = input_columns_for(w)
         self.model = model = MFP(cols, num_blocks=self.L, masking_method=w["method"], latent_dim=LATENT, dropout=0.1, l2=1e-2, seed=0, device=dev)
         model.compile(optimizer=Adam(learning_rate=1e-4, clipnorm=1.0))
+        model.engine.set_gemm_impl(Workload.gemm_impl)
         if world > 1:
             model.enable_data_parallel(dist, world)
         # synthetic data: distinct batches per rank (seed = 1000 * rank + i), pinned on the host for the e2e leg
@@ -412,6 +415,7 @@ def main():
     ap.add_argument("--no-tfrecord", action="store_true", help="skip the TFRecord input-pipeline leg (N=1 only)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short value-only runs of the other BASELINE configs")
     ap.add_argument("--no-check-dp", action="store_true", help="N > 1: skip the sharded-vs-single-GPU equivalence check")
+    ap.add_argument("--gemm-impl", type=int, default=0, choices=[0, 2], help="0 = TF32 product path (default), 2 = fp32-accurate 3xTF32 GEMMs + fp32 attention")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -455,7 +459,35 @@ def main():
         pass
     src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+
+    def measure_tf32_peak(n=8192, seconds=0.6):
+        """Dense TF32 GEMM throughput of this GPU (cuBLAS through torch.matmul with TF32 allowed, fp32 operands in HBM, fp32 accumulate):
+        the denominator for the tensor view of a path that computes in kind::tf32.  MEASURED_PEAKS.json holds only the bf16 figure."""
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            a = torch.randn((n, n), device=dev)
+            b = torch.randn((n, n), device=dev)
+            for _ in range(3):
+                torch.matmul(a, b)
+            torch.cuda.synchronize()
+            best, total, iters = 0.0, 0.0, 0
+            t_end = time.perf_counter() + seconds
+            while time.perf_counter() < t_end:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(4):
+                    torch.matmul(a, b)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 4
+                best = max(best, 2.0 * n ** 3 / (ms * 1e-3) / 1e12)
+                total += ms
+                iters += 1
+            return {"burst": best, "sustained": 2.0 * n ** 3 / (total / iters * 1e-3) / 1e12, "how": "torch.matmul fp32 %d^3 with allow_tf32, best of / mean over %d x 4 launches" % (n, iters)}
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
 
     def value_leg(config, steps, warmup, before_timed=None):
         """Device-resident throughput of one configuration: (workload, ms total, launches, step-0 global loss)."""
@@ -477,6 +509,15 @@ def main():
         rel = abs(loss0 - g["loss"]) / abs(g["loss"])
         assert rel <= 2e-3, "cfg%d: step-0 loss %.6f differs from the oracle's %.6f (rel %.2e > 2e-3)" % (config, loss0, g["loss"], rel)
         return {"engine": loss0, "oracle_f64": g["loss"], "rel_err": rel, "tolerance": 2e-3, "source": "tests/golden/bench_step0.json"}
+
+    Workload.gemm_impl = args.gemm_impl
+    tf32 = measure_tf32_peak() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([tf32["sustained"] if tf32 else 0.0], device=dev)
+        dist.broadcast(t, 0)
+        tensor_peak = float(t.item())
+    else:
+        tensor_peak = tf32["sustained"]
 
     # ---- device-resident leg (value)
     sampler = ClockSampler(local_rank)
@@ -566,11 +607,14 @@ def main():
                 "gemm_ms_per_step": gemm_ms / prof_steps, "gemm_launches_per_step": gemm_launches // prof_steps,
                 "gemm_algorithmic_bytes_per_step": gemm_bytes / prof_steps,
                 "tensor": {"achieved": gemm_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": gemm_tflops / tensor_peak,
-                           "peak_source": src + " bf16_tflops_sustained (no TF32 peak is in MEASURED_PEAKS.json; TF32 dense is nominally half of bf16)"},
+                           "peak_source": "TF32 dense GEMM measured in this run (cuBLAS, %s): burst %.1f / sustained %.1f TFLOP/s; MEASURED_PEAKS.json "
+                                          "bf16_tflops_sustained = %.1f for comparison" % (tf32["how"] if tf32 else "rank 0", tf32["burst"] if tf32 else 0.0, tensor_peak, bf16_peak),
+                           "vs_bf16_peak_frac": gemm_tflops / bf16_peak},
                 "attention": {"ms_per_step": attn_ms / prof_steps, "launches_per_step": attn_launches // prof_steps,
                               "achieved": attn_bytes / (attn_ms * 1e-3) / 1e9 if attn_ms > 0 else 0.0, "unit": "GB/s",
                               "frac": (attn_bytes / (attn_ms * 1e-3) / 1e9 / hbm_peak) if attn_ms > 0 else 0.0},
                 "step_tensor_roofline_frac": train_flops * elements_per_step / step_s / 1e12 / tensor_peak,
+                "step_tensor_roofline_frac_vs_bf16_peak": train_flops * elements_per_step / step_s / 1e12 / bf16_peak,
                 # ~95 KB per element is the HBM floor of the step with per-sub-layer fusion and an fp32 residual stream
                 "step_hbm_roofline_frac": 95e3 * elements_per_step / step_s / 1e9 / hbm_peak}
 
@@ -603,7 +647,8 @@ def main():
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_port_throughput(args.cpu_budget)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": "tf32",
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
+                "dtype": "tf32" if args.gemm_impl == 0 else "f32 (3xTF32 tensor-core GEMMs, fp32 attention)",
                 "data": "synthetic",
                 "config": {"workload": "%s: L=%d D=256 H=8 FFN=512, %d documents per GPU, all documents full length, dropout=0.1 l2=1e-2 "
                                        "Adam(1e-4, clipnorm=1.0)" % (w["name"], wl.L, wl.B),

@@ -30,7 +30,7 @@ struct BlockLayout {
 struct Workspace {
   // byte offsets into the caller's workspace
   size_t vars, flags, perm, x, ln1, qkv, attn, xmid, ln2, hid, stats, lse, logits, dlogits, dx, dtmp, dy, dqkv, dhid, dattn, dh0m, onehot, rowgrad, part, idx_true, idx_pred,
-      norms, ctx_row, canvas_vec, dcanvas, iota, zeros, det, ln_part, total;
+      norms, ctx_row, canvas_vec, dcanvas, iota, zeros, det, ln_part, lo_a, lo_b, total;
 };
 
 }  // namespace mfp
@@ -238,6 +238,11 @@ static Workspace plan_workspace(const mfp_engine* h, int B, int S) {
   w.zeros = take((size_t)B * sizeof(int));
   w.det = take(kDetWsFloats * fl);
   w.ln_part = take((size_t)kLnBwdMaxCtas * 2 * D * fl);
+  // 3xTF32 mode: low parts of the two operands of one GEMM (the widest operands are [T, LW] logits gradients and [T, 768] qkv)
+  const size_t widest = std::max<size_t>(std::max<size_t>(h->sc.LW, 3 * D), std::max<size_t>((size_t)h->sc.Rp, 512));
+  const size_t lo_rows = std::max<size_t>(T, 512);  // weight operands have up to 512 rows (FFN2, numerical Dense) whatever T is
+  w.lo_a = take(lo_rows * widest * fl);
+  w.lo_b = take(lo_rows * widest * fl);
   w.total = cur;
   return w;
 }
@@ -311,18 +316,29 @@ static int gemm(mfp_engine* h, const float* A, int a_mn, int lda, const float* B
   c.M = M; c.N = N; c.K = K;
   c.splits = splits;
   c.ep = ep;
-  c.colsum = (h->gemm_impl == 0) ? colsum : nullptr;
+  c.colsum = (h->gemm_impl != 1) ? colsum : nullptr;
   if (h->deterministic) { c.det_ws = wsp<float>(h, h->off.det); c.det_ws_floats = kDetWsFloats; }
+  if (h->gemm_impl == 2) {
+    // 3xTF32: x_lo = x - tf32(x) of both operands (same layout and pitch), then a_hi b_hi + a_lo b_hi + a_hi b_lo in one accumulator.
+    // An operand is [rows = M|N][K] with pitch ld (K-major) or [K][M|N] (MN-major).
+    float* alo = wsp<float>(h, h->off.lo_a);
+    float* blo = wsp<float>(h, h->off.lo_b);
+    // (whole pitch rows: widths like the one-hot matrix's R are not multiples of 4, pitches are)
+    MFP_TRY(launch_split_tf32_lo(A, a_mn ? K : M, lda, lda, alo, st));
+    MFP_TRY(launch_split_tf32_lo(Bp, b_mn ? K : N, ldb, ldb, blo, st));
+    c.a_lo = alo; c.b_lo = blo;
+    h->launches += 2;
+  }
   h->launches++;
-  if (h->deterministic && h->gemm_impl == 0 && (splits > 1 || colsum)) h->launches++;  // splitk_reduce_kernel
-  if (colsum && h->gemm_impl != 0) {
+  if (h->deterministic && h->gemm_impl != 1 && (splits > 1 || colsum)) h->launches++;  // splitk_reduce_kernel
+  if (colsum && h->gemm_impl == 1) {
     MFP_TRY(launch_colsum(Bp, K, N, ldb, colsum, st, h->deterministic != 0));
     h->launches++;
   }
   // algorithmic bytes: each operand and the output once, plus the residual / ReLU-mask operand
   const double bytes = 4.0 * ((double)M * K + (double)N * K + (double)M * N * ((ep.residual || ep.relu_src) ? 2.0 : 1.0));
   ProfScope prof(h, MFP_PROFILE_GEMM, st, bytes);
-  return launch_gemm(h->maps, c, h->gemm_impl, st);
+  return launch_gemm(h->maps, c, h->gemm_impl == 2 ? 0 : h->gemm_impl, st);
 }
 
 // split-K factor of a weight-gradient GEMM (K = tokens): enough CTAs for ~2 per SM
@@ -914,7 +930,7 @@ int mfp_merge_prediction(mfp_engine* h, int32_t field, const void* input_col, co
 int64_t mfp_launch_count(const mfp_engine* h) { return h ? h->launches : 0; }
 
 int mfp_set_gemm_impl(mfp_engine* h, int32_t impl) {
-  if (!h || impl < 0 || impl > 1) { set_error("mfp_set_gemm_impl: bad argument"); return MFP_ERR_ARG; }
+  if (!h || impl < 0 || impl > 2) { set_error("mfp_set_gemm_impl: bad argument"); return MFP_ERR_ARG; }
   h->gemm_impl = impl;
   return MFP_OK;
 }

@@ -68,6 +68,7 @@ struct GemmTune {
 
 struct GemmTiles {
   int tiles_m, tiles_n, splits, kb_per_split;
+  int passes;     // 1, or 3 for the compensated 3xTF32 mode (see the kernel)
   int slab_rows;  // > 0 (deterministic split-K): split s stores its tiles, without reduction, at row offset s * slab_rows of the scratch output
   int det_colsum; // column-sum partials are stored per (split, m-tile) slot instead of atomically added
 };
@@ -95,7 +96,8 @@ enum : int { kEpiBias = 1, kEpiRelu = 2, kEpiResidual = 4, kEpiReluMask = 8, kEp
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
-                  const __grid_constant__ CUtensorMap tmAux, int M, int N, int K, int a_mn, int b_mn, GemmTiles tl, GemmEpilogue ep,
+                  const __grid_constant__ CUtensorMap tmALo, const __grid_constant__ CUtensorMap tmBLo, int M, int N, int K, int a_mn, int b_mn, GemmTiles tl,
+                  GemmEpilogue ep,
                   float* __restrict__ colsum, GemmTune tune, unsigned long long* __restrict__ trace) {
   constexpr int aux_mode = (EPI & kEpiResidual) ? 1 : ((EPI & kEpiReluMask) ? 2 : 0);
   using L = GemmSmem<BN, aux_mode != 0>;
@@ -113,7 +115,11 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_kb = (K + kBK - 1) / kBK;
+  // 3xTF32 (tl.passes == 3): the K loop runs three times over the operands -- (A, B), (A_lo, B), (A, B_lo), x_lo = x - tf32(x) -- into the
+  // same accumulator: a_hi b_hi + a_lo b_hi + a_hi b_lo, fp32-accurate products on the TF32 tensor cores (only the producers and the
+  // column-sum role know; k-block kb of the tripled range is block kb % kb_single of pass kb / kb_single)
+  const int kb_single = (K + kBK - 1) / kBK;
+  const int num_kb = kb_single * tl.passes;
   const int tiles_mn = tl.tiles_m * tl.tiles_n;
   const int num_tiles = tiles_mn * tl.splits;
   const bool do_colsum = (colsum != nullptr);
@@ -131,6 +137,7 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
     prefetch_tensormap(&tmOut);
+    if (tl.passes == 3) { prefetch_tensormap(&tmALo); prefetch_tensormap(&tmBLo); }
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(2 * BN) : "memory");
@@ -170,29 +177,32 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int split = tile / tiles_mn, r = tile - split * tiles_mn;
         const int m0 = (r / tl.tiles_n) * kBM, n0 = (r % tl.tiles_n) * BN;
         const int kb0 = split * tl.kb_per_split, kb1 = min(num_kb, kb0 + tl.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kbt = kb0; kbt < kb1; ++kbt) {
+          const int pass = kbt / kb_single, kb = kbt - pass * kb_single;
+          const CUtensorMap* mapA = (pass == 1) ? &tmALo : &tmA;
+          const CUtensorMap* mapB = (pass == 2) ? &tmBLo : &tmB;
           wait_t(empty_bar(stage), phase ^ 1u, w0);
           const uint32_t sa = base + stage * L::kStageBytes;
           const uint32_t sb = sa + L::kABytes;
           if (is_a) {
             mbar_expect_tx(full_bar(stage), L::kABytes);
             if (a_mn == 0) {
-              tma_load_2d(sa, &tmA, kb * kBK, m0, full_bar(stage));
+              tma_load_2d(sa, mapA, kb * kBK, m0, full_bar(stage));
             } else if (a_mn == 2) {
-              tma_load_3d(sa, &tmA, 0, kb * kBK, m0 >> 5, full_bar(stage));
+              tma_load_3d(sa, mapA, 0, kb * kBK, m0 >> 5, full_bar(stage));
             } else {
 #pragma unroll
-              for (int j = 0; j < kBM / 32; ++j) tma_load_2d(sa + j * (kBK * 128), &tmA, m0 + 32 * j, kb * kBK, full_bar(stage));
+              for (int j = 0; j < kBM / 32; ++j) tma_load_2d(sa + j * (kBK * 128), mapA, m0 + 32 * j, kb * kBK, full_bar(stage));
             }
           } else {
             mbar_expect_tx(full_bar(stage), L::kBBytes);
             if (b_mn == 0) {
-              tma_load_2d(sb, &tmB, kb * kBK, n0, full_bar(stage));
+              tma_load_2d(sb, mapB, kb * kBK, n0, full_bar(stage));
             } else if (b_mn == 2) {
-              tma_load_3d(sb, &tmB, 0, kb * kBK, n0 >> 5, full_bar(stage));
+              tma_load_3d(sb, mapB, 0, kb * kBK, n0 >> 5, full_bar(stage));
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * (kBK * 128), &tmB, n0 + 32 * j, kb * kBK, full_bar(stage));
+              for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * (kBK * 128), mapB, n0 + 32 * j, kb * kBK, full_bar(stage));
             }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -268,7 +278,7 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int i = 0; i < BN / 128; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
-          if (active) {
+          if (active && kb / kb_single != 1) {  // 3xTF32: pass 1 shows the B tiles a second time (hi from pass 0 + lo from pass 2 = the fp32 sum)
             const uint8_t* cb = base_ptr + stage * L::kStageBytes + L::kABytes + chunk0 * (kBK * 128) + half * 16;
 #pragma unroll 4
             for (int k = k_first; k < k_first + rows_per; ++k) {
@@ -539,6 +549,31 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------- 3xTF32 operand split
+// lo = x - tf32(x), tf32() = round to nearest even on 10 mantissa bits: exactly what the TFLOAT32 tensor maps deliver as the "hi" part
+// (measured: tests/test_gpu_parity.py::test_tf32_operand_rounding_of_the_product_path), so hi + lo == x exactly in fp32.
+__global__ void __launch_bounds__(256) split_tf32_lo_kernel(const float* __restrict__ x, int rows, int cols4, int ld4, float* __restrict__ lo) {
+  pdl_wait();
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * cols4) return;
+  const size_t r = i / cols4, c = i - r * cols4;
+  const float4 v = reinterpret_cast<const float4*>(x)[r * ld4 + c];
+  auto low = [](float f) {
+    uint32_t b = __float_as_uint(f);
+    b = (b + 0xFFFu + ((b >> 13) & 1u)) & ~0x1FFFu;
+    return f - __uint_as_float(b);
+  };
+  reinterpret_cast<float4*>(lo)[r * ld4 + c] = make_float4(low(v.x), low(v.y), low(v.z), low(v.w));
+}
+
+int launch_split_tf32_lo(const float* x, int rows, int cols, int ld, float* lo, cudaStream_t stream) {
+  if ((cols % 4) || (ld % 4)) { set_error("split_tf32_lo: cols and pitch must be multiples of 4"); return MFP_ERR_ARG; }
+  const size_t n4 = (size_t)rows * (cols / 4);
+  MFP_CUDA_OK(launch_pdl(split_tf32_lo_kernel, (unsigned)((n4 + 255) / 256), 256, 0, stream, x, rows, cols / 4, ld / 4, lo));
+  MFP_CUDA_OK(cudaGetLastError());
+  return MFP_OK;
+}
+
 // ------------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -684,17 +719,24 @@ static int launch_tcgen05(TensorMapCache* cache, const GemmCall& c, cudaStream_t
   int a_mode = 0, b_mode = 0;
   const CUtensorMap* ma = c.a.mn_major ? mn_map(c.a, c.M, kBM, &a_mode) : cache->get(c.a.ptr, c.K, c.M, c.a.ld, kBK, kBM, kMapOperandK);
   const CUtensorMap* mb = c.b.mn_major ? mn_map(c.b, c.N, BN, &b_mode) : cache->get(c.b.ptr, c.K, c.N, c.b.ld, kBK, BN, kMapOperandK);
-  const CUtensorMap* mo = cache->get(c.ep.out, c.N, c.M, c.ep.ldo, 32, 32, kMapEpilogue);
-  const CUtensorMap* mx = mo;
-  if (c.ep.residual) mx = cache->get(c.ep.residual, c.N, c.M, c.ep.ldr, 32, 32, kMapEpilogue);
-  if (c.ep.relu_src) mx = cache->get(c.ep.relu_src, c.N, c.M, c.ep.ld_relu, 32, 32, kMapEpilogue);
-  if (!ma || !mb || !mo || !mx) return MFP_ERR_CUDA;
+  const CUtensorMap* mo = cache->get(c.ep.out, c.N, c.M, c.ep.ldo, 32, 32, kMapEpilogue);  // split-K reduce-add target
+  // 3xTF32: the low parts x - tf32(x) of both operands, same geometry (pitch = the operand's own)
+  const CUtensorMap *mal = ma, *mbl = mb;
+  if (c.a_lo && c.b_lo) {
+    GemmOperand alo = c.a, blo = c.b;
+    alo.ptr = c.a_lo; blo.ptr = c.b_lo;
+    int unused_mode = 0;
+    mal = c.a.mn_major ? mn_map(alo, c.M, kBM, &unused_mode) : cache->get(alo.ptr, c.K, c.M, alo.ld, kBK, kBM, kMapOperandK);
+    mbl = c.b.mn_major ? mn_map(blo, c.N, BN, &unused_mode) : cache->get(blo.ptr, c.K, c.N, blo.ld, kBK, BN, kMapOperandK);
+  }
+  if (!ma || !mb || !mo || !mal || !mbl) return MFP_ERR_CUDA;
   static const GemmTune tune = {env_u32("FLEXDM_MN_LBO", kBK * 128), env_u32("FLEXDM_MN_SBO", 512), env_u32("FLEXDM_K_LBO", 16), env_u32("FLEXDM_K_SBO", 1024),
                                 k_atom32() ? 1u : 2u};
-  const int num_kb = (c.K + kBK - 1) / kBK;
+  GemmTiles tl;
+  tl.passes = (c.a_lo && c.b_lo) ? 3 : 1;
+  const int num_kb = tl.passes * ((c.K + kBK - 1) / kBK);
   int splits = c.splits < 1 ? 1 : c.splits;
   if (splits > num_kb) splits = num_kb;
-  GemmTiles tl;
   tl.kb_per_split = (num_kb + splits - 1) / splits;
   tl.splits = (num_kb + tl.kb_per_split - 1) / tl.kb_per_split;  // no empty split
   tl.tiles_m = (c.M + kBM - 1) / kBM;
@@ -726,7 +768,7 @@ static int launch_tcgen05(TensorMapCache* cache, const GemmCall& c, cudaStream_t
   static unsigned long long* trace = nullptr;
   if (trace_on && !trace) { MFP_CUDA_OK(cudaMalloc(&trace, 148 * 8 * sizeof(unsigned long long))); }
   if (trace_on) MFP_CUDA_OK(cudaMemsetAsync(trace, 0, 148 * 8 * sizeof(unsigned long long), stream));
-  MFP_CUDA_OK(launch_pdl(gemm_tf32_tcgen05<BN, EPI>, grid, kGemmThreads, L::kTotal, stream, *ma, *mb, *mo, *mx, c.M, c.N, c.K, a_mode, b_mode, tl, ep, colsum,
+  MFP_CUDA_OK(launch_pdl(gemm_tf32_tcgen05<BN, EPI>, grid, kGemmThreads, L::kTotal, stream, *ma, *mb, *mo, *mal, *mbl, c.M, c.N, c.K, a_mode, b_mode, tl, ep, colsum,
                          tune, trace_on ? trace : nullptr));
   if (trace_on) {
     unsigned long long hbuf[148 * 8];

@@ -52,6 +52,9 @@ struct GemmCall {
   float* colsum;  // optional [N]: += column sums of the (MN-major) B operand over K, i.e. the bias gradient of a wgrad GEMM
   // Deterministic reductions (mfp_set_deterministic): split-K partial tiles and the column-sum partials of every CTA go to this scratch
   // block with plain stores and are summed in a fixed order by a second kernel, instead of TMA reduce-add / atomicAdd in arrival order.
+  // 3xTF32 (mfp_set_gemm_impl(h, 2)): x_lo = x - tf32(x) of both operands, same layout and pitch as a / b (split_tf32_lo); both or neither
+  const float* a_lo;
+  const float* b_lo;
   float* det_ws;        // nullptr = arrival-order accumulation (the fast default)
   size_t det_ws_floats;
 };
@@ -68,8 +71,10 @@ void tensor_map_cache_trim(TensorMapCache*);  // call at the start of a launcher
 const CUtensorMap* tensor_map_get(TensorMapCache* cache, const float* ptr, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
                                   MapKind kind);
 
-// impl: 0 = tcgen05, 1 = SIMT bring-up kernel.  Returns MFP_OK or an error (message via set_error).
+// impl: 0 = tcgen05 (TF32, or 3xTF32 when call.a_lo / b_lo are given), 1 = SIMT bring-up kernel.  Returns MFP_OK or an error (message via set_error).
 int launch_gemm(TensorMapCache* cache, const GemmCall& call, int impl, cudaStream_t stream);
+// lo[i] = x[i] - tf32_rne(x[i]) over a [rows, cols] matrix of pitch ld (lo has the same pitch): the compensation operand of the 3xTF32 mode
+int launch_split_tf32_lo(const float* x, int rows, int cols, int ld, float* lo, cudaStream_t stream);
 
 // keep-mask/scale of the engine's dropout sites (shared by the GEMM epilogue and the backward pass).
 // RNG contract: element e of the flattened [T, D] activation takes the 16-bit half (e & 7) of philox(counter = (e >> 3, site, 0, 0),

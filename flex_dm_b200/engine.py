@@ -419,7 +419,7 @@ class Engine:
         return {"gemm": (float(ms[0]), int(n[0]), float(nbytes[0])), "attention": (float(ms[1]), int(n[1]), float(nbytes[1]))}
 
     def set_gemm_impl(self, impl: int):
-        """0 = tcgen05 TF32 (product path), 1 = fp32 SIMT bring-up GEMM (tests only)."""
+        """0 = tcgen05 TF32 (product path), 1 = fp32 SIMT bring-up GEMM (tests only), 2 = fp32-accurate 3xTF32 tensor-core GEMMs + fp32 attention."""
         _check(self.lib, self.lib.mfp_set_gemm_impl(self.handle, int(impl)), "mfp_set_gemm_impl")
 
     def set_packed_rows(self, rowmaps: Optional[List[Optional[torch.Tensor]]]):

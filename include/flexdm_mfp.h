@@ -199,9 +199,13 @@ int mfp_merge_prediction(mfp_engine* h, int32_t field, const void* input_col, co
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t mfp_launch_count(const mfp_engine* h);
 
-/* Bring-up / test hook: 0 = tcgen05 TF32 GEMMs and attention (default, the product path), 1 = fp32 SIMT GEMM with the
- * same epilogue and fp32 SIMT attention.  The parity tests use 1 to pin every other kernel at fp32 accuracy,
- * independent of TF32 rounding. */
+/* Arithmetic of the dense contractions (the reference computes them in fp32, transformer.py:61-75; TensorFlow >= 2.4 itself uses TF32 on
+ * Ampere and later):
+ *   0 = tcgen05 kind::tf32 GEMMs and attention, operands rounded to TF32 (nearest even), fp32 accumulation: the product path (default);
+ *   1 = fp32 SIMT GEMM with the same epilogue and fp32 SIMT attention: bring-up / test hook that pins every other kernel at fp32
+ *       accuracy, independent of TF32 rounding;
+ *   2 = fp32-accurate on the tensor cores: compensated "3xTF32" GEMMs (a_hi b_hi + a_lo b_hi + a_hi b_lo with x_lo = x - tf32(x), one
+ *       accumulator, same fused epilogues) and the fp32 SIMT attention core.  About 2-3x the GEMM time of mode 0. */
 int mfp_set_gemm_impl(mfp_engine* h, int32_t impl);
 
 /* Deterministic gradient reductions (train.py:18-23 seeds everything "for reproducibility"; Keras on one device has a fixed reduction

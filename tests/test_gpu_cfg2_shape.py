@@ -69,13 +69,13 @@ def _window_oracle(cols, m, batch, lo, hi, skip_sorted=False):
     return tasks, omod, full_masks, outputs, float(scaled.detach()), losses, scores, grads
 
 
-@pytest.mark.parametrize("impl", [1, 0], ids=["fp32-simt", "tf32-tcgen05"])
+@pytest.mark.parametrize("impl", [1, 0, 2], ids=["fp32-simt", "tf32-tcgen05", "3xtf32-tcgen05"])
 @pytest.mark.parametrize("dataset,method,lengths", [("crello", "random", "full"), ("crello", "elem_pos_attr_img_txt", "ragged"),
                                                     ("rico", "elem_pos_attr", "ragged")], ids=["cfg2", "cfg3", "cfg4"])
 def test_full_shape_step_matches_oracle_on_document_windows(dataset, method, lengths, impl):
     cols, m, batch, length, dcols, tasks, logits = _engine_step(dataset, method, impl, lengths)
     eng = m.engine
-    logit_atol, loss_rtol, grad_tol = (H.F32_LOGIT_ATOL, H.F32_LOSS_RTOL, H.F32_GRAD_REL_L2) if impl == 1 else (H.LOGIT_ATOL, H.LOSS_RTOL, H.GRAD_REL_L2)
+    logit_atol, loss_rtol, grad_tol = H.tolerances(impl)
     got_logits = m.split_logits(logits, B, S)
     full_masks = [t.clone() for t in eng.masks]
     F = len(m.keys)

@@ -202,12 +202,12 @@ def _oracle_run(cols, m, batch, tasks, seed, step, drop=None):
     return outputs, float(total.detach()), losses, scores, metrics, grads, omod, omasks
 
 
-@pytest.mark.parametrize("impl", [1, 0], ids=["fp32-simt", "tf32-tcgen05"])
+@pytest.mark.parametrize("impl", [1, 0, 2], ids=["fp32-simt", "tf32-tcgen05", "3xtf32-tcgen05"])
 @pytest.mark.parametrize("dataset,method,B,S,L", CONFIGS)
 def test_forward_loss_backward_match_oracle(dataset, method, B, S, L, impl):
     cols, m = _model(dataset, method, L)
     m.engine.set_gemm_impl(impl)
-    logit_atol, loss_rtol, grad_tol = (H.F32_LOGIT_ATOL, H.F32_LOSS_RTOL, H.F32_GRAD_REL_L2) if impl == 1 else (H.LOGIT_ATOL, H.LOSS_RTOL, H.GRAD_REL_L2)
+    logit_atol, loss_rtol, grad_tol = H.tolerances(impl)
     batch = make_synthetic_batch(cols, B, S, seed=1, lengths="ragged")
     staged = m.stage(batch)
     _, _, length, dcols = m._bind(staged)
