@@ -281,6 +281,7 @@ class Workload:
     """One bench configuration on this rank: model, resident + pinned batches, the step function."""
 
     gemm_impl = 0
+    transport = "auto"  # gradient exchange at N > 1: "auto" (NVLS kernel when available), "nvls", "nccl"
 
     def __init__(self, config, world, rank, dev, dist):
         import torch
@@ -302,7 +303,7 @@ class Workload:
         model.compile(optimizer=Adam(learning_rate=1e-4, clipnorm=1.0))
         model.engine.set_gemm_impl(Workload.gemm_impl)
         if world > 1:
-            model.enable_data_parallel(dist, world)
+            model.enable_data_parallel(dist, world, transport=Workload.transport)
         # synthetic data: distinct batches per rank (seed = 1000 * rank + i), pinned on the host for the e2e leg
         host = [make_synthetic_batch(cols, self.B, self.S, seed=1000 * rank + i, lengths="full") for i in range(N_DEVICE_BATCHES)]
         needed = [k for k, c in model.input_columns.items() if k == "length" or c["is_sequence"]]
@@ -358,7 +359,7 @@ def dp_check(config, world, rank, dev, dist, steps=3):
         return make_synthetic_batch(cols, B, S, seed=7000 + 1000 * r + i, lengths="ragged")
 
     sharded = fresh()
-    sharded.enable_data_parallel(dist, world)
+    sharded.enable_data_parallel(dist, world, transport=Workload.transport)
     w0 = sharded.engine.params.clone()
     rows = torch.stack([sharded.train_step(shard(rank, i)).clone() for i in range(steps)])
     rows = reduce_metric_rows(dist, rows)
@@ -415,6 +416,7 @@ def main():
     ap.add_argument("--no-tfrecord", action="store_true", help="skip the TFRecord input-pipeline leg (N=1 only)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short value-only runs of the other BASELINE configs")
     ap.add_argument("--no-check-dp", action="store_true", help="N > 1: skip the sharded-vs-single-GPU equivalence check")
+    ap.add_argument("--transport", default="auto", choices=["auto", "nvls", "nccl"], help="N > 1: gradient all-reduce transport")
     ap.add_argument("--gemm-impl", type=int, default=0, choices=[0, 2], help="0 = TF32 product path (default), 2 = fp32-accurate 3xTF32 GEMMs + fp32 attention")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -511,6 +513,7 @@ def main():
         return {"engine": loss0, "oracle_f64": g["loss"], "rel_err": rel, "tolerance": 2e-3, "source": "tests/golden/bench_step0.json"}
 
     Workload.gemm_impl = args.gemm_impl
+    Workload.transport = args.transport
     tf32 = measure_tf32_peak() if rank == 0 else None
     if world > 1:
         t = torch.tensor([tf32["sustained"] if tf32 else 0.0], device=dev)
@@ -653,6 +656,8 @@ def main():
                 "config": {"workload": "%s: L=%d D=256 H=8 FFN=512, %d documents per GPU, all documents full length, dropout=0.1 l2=1e-2 "
                                        "Adam(1e-4, clipnorm=1.0)" % (w["name"], wl.L, wl.B),
                            "global_batch": wl.B * world, "seq_len": wl.S, "parallelism": "dp%d" % world,
+                           "gradient_exchange": None if world == 1 else ("one NVLS kernel on the step's stream (multimem.ld_reduce / multimem.st, csrc/allreduce.cu)"
+                                                                         if model._nvls is not None else "ncclAllReduce of the flat gradient buffer"),
                            "l2_flush": "inputs larger than L2: %d distinct resident batches (%.0f MB) rotate; activations per step 1.6 GB" % (N_DEVICE_BATCHES, N_DEVICE_BATCHES * wl.h2d_bytes_dense / 1e6),
                            "loss_step0": step0 if step0 is not None else {"engine": loss0, "note": "global loss (metric rows summed over ranks); the oracle value is pinned at N=1"},
                            "loss_last_step": last_loss},

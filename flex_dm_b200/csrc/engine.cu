@@ -30,7 +30,7 @@ struct BlockLayout {
 struct Workspace {
   // byte offsets into the caller's workspace
   size_t vars, flags, perm, x, ln1, qkv, attn, xmid, ln2, hid, stats, lse, logits, dlogits, dx, dtmp, dy, dqkv, dhid, dattn, dh0m, onehot, rowgrad, part, idx_true, idx_pred,
-      norms, ctx_row, canvas_vec, dcanvas, iota, zeros, det, ln_part, lo_a, lo_b, total;
+      norms, ctx_row, canvas_vec, dcanvas, iota, zeros, det, ln_part, lo_a, lo_b, ar_sync, total;
 };
 
 }  // namespace mfp
@@ -59,6 +59,7 @@ struct mfp_engine {
   std::vector<long long> stage_lo, stage_hi;  // flat-buffer range whose gradients are final after backward stage s (see mfp_backward_stages)
   const void* flags_for = nullptr;  // modified column (first numerical field) the workspace row flags were just derived from
   int gemm_impl = 0;
+  uint32_t ar_calls = 0;   // NVLS all-reduce calls since the last bind (monotonic barrier flags)
   int deterministic = 0;   // mfp_set_deterministic: fixed-order gradient reductions (bit-identical steps from run to run)
   uint32_t doc0 = 0;       // mfp_set_doc_offset: global index of the bound batch's first document (data-parallel shard)
   int64_t launches = 0;
@@ -243,6 +244,7 @@ static Workspace plan_workspace(const mfp_engine* h, int B, int S) {
   const size_t lo_rows = std::max<size_t>(T, 512);  // weight operands have up to 512 rows (FFN2, numerical Dense) whatever T is
   w.lo_a = take(lo_rows * widest * fl);
   w.lo_b = take(lo_rows * widest * fl);
+  w.ar_sync = take(256);
   w.total = cur;
   return w;
 }
@@ -487,6 +489,8 @@ int mfp_bind(mfp_engine* h, int32_t B, int32_t S, void* workspace, int64_t works
   std::vector<VarDev> vd(h->vars.size());
   for (size_t i = 0; i < vd.size(); ++i) vd[i] = VarDev{h->vars[i].offset, h->vars[i].rows, h->vars[i].cols, h->vars[i].ld, h->vars[i].l2};
   MFP_CUDA_OK(cudaMemcpy(h->ws + w.vars, vd.data(), vd.size() * sizeof(VarDev), cudaMemcpyHostToDevice));
+  MFP_CUDA_OK(cudaMemset(h->ws + w.ar_sync, 0, 256));
+  h->ar_calls = 0;
   return MFP_OK;
 }
 
@@ -945,6 +949,17 @@ int mfp_set_doc_offset(mfp_engine* h, int64_t first_document) {
   if (!h || first_document < 0 || first_document > 0x7fffffffLL) { set_error("mfp_set_doc_offset: bad argument"); return MFP_ERR_ARG; }
   h->doc0 = (uint32_t)first_document;
   return MFP_OK;
+}
+
+int mfp_allreduce_gradients_nvls(mfp_engine* h, float* multicast_grads, void* const* signal_pads_dev, int32_t first_slot, int32_t rank, int32_t world,
+                                 uint32_t call, void* stream) {
+  MFP_TRY(check_bound(h));
+  if (!h->grads || !multicast_grads || !signal_pads_dev) { set_error("mfp_allreduce_gradients_nvls: null argument"); return MFP_ERR_ARG; }
+  if (call == 0) { set_error("mfp_allreduce_gradients_nvls: call numbers start at 1"); return MFP_ERR_ARG; }
+  h->launches++;
+  h->ar_calls++;
+  return launch_nvls_allreduce(multicast_grads, reinterpret_cast<uint32_t* const*>(signal_pads_dev), first_slot, rank, world, (size_t)h->param_count, call,
+                               h->ar_calls, wsp<uint32_t>(h, h->off.ar_sync), (cudaStream_t)stream);
 }
 
 int mfp_profile_begin(mfp_engine* h) {

@@ -108,4 +108,10 @@ int launch_regularization_loss(const VarDev* vars, int V, const float* params, f
 int launch_optimizer(const VarDev* vars, int V, float* params, const float* grads, float* m, float* v, float* norms /*[V][16][2] partial sums*/, int t, float lr,
                      float clipnorm, float l2, float* l2_loss_out, cudaStream_t st);
 
+// allreduce.cu: two-shot NVLS all-reduce (multimem.ld_reduce / multimem.st) of a buffer that lives at the same offset of every rank's
+// symmetric memory; pads_dev = device array of the ranks' signal pads, slot0 = first uint32 slot this engine may use (2 * world slots),
+// call = 1, 2, 3, ... since the pads were zeroed (monotonic flags), local_call = the same count since `sync` (two uint32 in local memory) was zeroed
+int launch_nvls_allreduce(float* multicast, uint32_t* const* pads_dev, int slot0, int rank, int world, size_t n_floats, uint32_t call, uint32_t local_call,
+                          uint32_t* sync, cudaStream_t st);
+
 }  // namespace mfp

@@ -97,6 +97,8 @@ _SIGNATURES = {
     "mfp_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "mfp_set_gemm_impl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     "mfp_set_deterministic": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
+    "mfp_allreduce_gradients_nvls": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                                    ctypes.c_uint32, ctypes.c_void_p]),
     "mfp_set_packed_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     "mfp_set_doc_offset": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
     "mfp_profile_begin": (ctypes.c_int, [ctypes.c_void_p]),
@@ -432,6 +434,18 @@ class Engine:
         self._rowmaps = rowmaps  # keeps the tensors alive while the engine holds their pointers
         ptrs = _PTR_ARRAY(*[(r.data_ptr() if r is not None else None) for r in rowmaps])
         _check(self.lib, self.lib.mfp_set_packed_rows(self.handle, ctypes.cast(ptrs, ctypes.POINTER(ctypes.c_void_p))), "mfp_set_packed_rows")
+
+    def set_gradient_buffer(self, buf: torch.Tensor):
+        """Rebinds the flat gradient buffer (e.g. to a symmetric-memory tensor for the NVLS all-reduce); takes effect at the next ``bind``."""
+        if buf.numel() != self.param_count or buf.dtype != torch.float32 or buf.device != self.device:
+            raise ValueError("gradient buffer must be %d float32 on %s" % (self.param_count, self.device))
+        self.grads = buf
+        self.B = self.S = 0  # force mfp_bind with the new pointer
+
+    def allreduce_gradients_nvls(self, multicast_ptr: int, signal_pads_dev: int, first_slot: int, rank: int, world: int, call: int):
+        """``mfp_allreduce_gradients_nvls``: sum of the ranks' gradient buffers through the switch, one kernel on the current stream."""
+        _check(self.lib, self.lib.mfp_allreduce_gradients_nvls(self.handle, ctypes.c_void_p(multicast_ptr), ctypes.c_void_p(signal_pads_dev), int(first_slot),
+                                                               int(rank), int(world), int(call) & 0xFFFFFFFF, _stream()), "mfp_allreduce_gradients_nvls")
 
     def set_deterministic(self, on: bool = True):
         """Fixed-order gradient reductions: two runs of the same step are bit-identical (slower than the arrival-order default)."""

@@ -220,6 +220,15 @@ int mfp_set_deterministic(mfp_engine* h, int32_t on);
  * first_document = r * B_local draws exactly what a single process draws for those documents.  Default 0. */
 int mfp_set_doc_offset(mfp_engine* h, int64_t first_document);
 
+/* Data-parallel gradient exchange without NCCL on the critical path (the reference has no distributed code,
+ * train.py:25): two-shot all-reduce over NVLink SHARP in ONE kernel on `stream`.  Requirements: the gradient buffer bound by mfp_bind
+ * lives at the same offset of every rank's symmetric memory, `multicast_grads` is the multicast address of that buffer (every rank's
+ * copy behind one address), `signal_pads_dev` a device array of the `world` ranks' signal pads (uint32 slots, zero-initialised;
+ * slots [first_slot, first_slot + world) are used), `call` = 1, 2, 3, ... counts the calls since the pads were zeroed (same on every
+ * rank).  On return (in stream order) every rank's buffer holds the sum over ranks.  All waits are bounded and trap. */
+int mfp_allreduce_gradients_nvls(mfp_engine* h, float* multicast_grads, void* const* signal_pads_dev, int32_t first_slot, int32_t rank,
+                                 int32_t world, uint32_t call, void* stream);
+
 /* Optional device timing of kernel classes (bench.py's roofline): between begin and end every launch of the class is
  * bracketed by CUDA events on the launching stream; end synchronises and returns the summed milliseconds, the launch
  * count and the algorithmic HBM bytes (every operand and output once) per class (host arrays of MFP_PROFILE_CLASSES
