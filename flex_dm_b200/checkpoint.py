@@ -310,6 +310,10 @@ def save_variables(prefix: str, weights: Dict[str, np.ndarray]):
     lib = io_lib.load_library()
     directory = os.path.dirname(os.path.abspath(prefix))
     os.makedirs(directory, exist_ok=True)
+    # like TensorFlow, write under a temporary prefix and rename into place: a failed or interrupted save leaves the previous checkpoint
+    # (best.ckpt) intact
+    final_prefix, prefix = prefix, "%s.tempstate%d" % (prefix, os.getpid())
+    temp_files = [prefix + ".index", prefix + ".data-00000-of-00001"]
     writer = io_lib.check_handle(lib.fdio_bundle_writer_create(prefix.encode()))
     try:
         for name, value in weights.items():
@@ -322,9 +326,15 @@ def save_variables(prefix: str, weights: Dict[str, np.ndarray]):
         graph = ObjectGraph.from_variable_paths(list(weights.keys())).serialize()
         io_lib.check(lib.fdio_bundle_writer_add(writer, OBJECT_GRAPH_KEY.encode(), DT_STRING, 0, None, graph, len(graph)))
     except Exception:
-        lib.fdio_bundle_writer_finish(writer)  # frees the writer; the partial files are overwritten by the next save
+        lib.fdio_bundle_writer_finish(writer)  # frees the writer (there is no abort entry point); its partial files are temporaries
+        for f in temp_files:
+            if os.path.exists(f):
+                os.remove(f)
         raise
     io_lib.check(lib.fdio_bundle_writer_finish(writer))
+    os.replace(temp_files[1], final_prefix + ".data-00000-of-00001")  # data first: an index never points at a missing shard
+    os.replace(temp_files[0], final_prefix + ".index")
+    prefix = final_prefix
     base = os.path.basename(prefix)
     with open(os.path.join(directory, "checkpoint"), "w") as f:
         f.write('model_checkpoint_path: "%s"\nall_model_checkpoint_paths: "%s"\n' % (base, base))

@@ -95,7 +95,15 @@ _DTYPES = {"int": io_lib.INT64, "int32": io_lib.INT64, "int64": io_lib.INT64, "f
 # the native parser applies; calling one directly (primary_label, spec.py:188-191, and un-preprocessing in unbatch) is host-side
 # bookkeeping on a handful of values.
 class _Lookup:
-    """Keras ``StringLookup`` / ``IntegerLookup`` in ``output_mode="int"``: ``[mask_token] + [OOV] * num_oov_indices + vocabulary``."""
+    """Keras ``StringLookup`` / ``IntegerLookup`` in ``output_mode="int"``: ``[mask_token] + [OOV] * num_oov_indices + vocabulary``.
+
+    Version note.  The target is the API the reference states it was verified on, TensorFlow 2.8 (README.md:8-10), where both layers default
+    to NO mask slot (``mask_token=None``).  The reference's spec files still carry the pre-2.6 keyword ``mask_value`` for ``length``
+    (data/crello-spec.yml:6-13); it is honoured when given.  On TensorFlow <= 2.5 an ``IntegerLookup`` WITHOUT an explicit
+    ``mask_value`` reserved index 0 (default ``mask_value=0``): for crello's ``canvas_width`` / ``canvas_height``
+    (``lookup: {num_oov_indices: 0}``) such a checkpoint has one more row in those tables (``--context canvas`` / ``canvas_add`` only) and
+    every index shifted by one, and does not load here (``load_weights`` reports the shape mismatch); pass ``mask_value: 0`` in the spec
+    to reproduce that layout.  Not checkable offline: TensorFlow cannot be installed in this environment."""
 
     oov_token = None
 
@@ -598,9 +606,17 @@ class RecordDataset:
             yield from self._global_stream(rng)
             return
         rank, world = self.shard
-        for k, i in enumerate(self._global_stream(rng)):  # identical on every rank (same seed): keep every world-th document
-            if k % world == rank:
-                yield i
+        if self.repeat:
+            for k, i in enumerate(self._global_stream(rng)):  # identical on every rank (same seed): keep every world-th document
+                if k % world == rank:
+                    yield i
+            return
+        # one finite pass (val / test): every rank gets ceil(n / world) documents -- the last round wraps to the head of the pass -- so that all
+        # ranks run the same number of batches (metric rows are all-reduced collectively; an uneven split would hang or lose a batch)
+        order = list(self._global_stream(rng))
+        per = -(-len(order) // world)
+        for j in range(per):
+            yield order[(j * world + rank) % len(order)]
 
     def _global_stream(self, rng: np.random.Generator) -> Iterator[int]:
         n = len(self.pointers)

@@ -536,8 +536,9 @@ class MFP:
         filtered = [t.clone() for t in eng.modified]
         eng.mask_for_test(length, cols, masks_u8)  # modified_inputs of preprocess_for_test
         masks = [m.reshape(B, S).bool().clone() for m in masks_u8]
-        num_masked = sum(masks[f].sum(dim=-1) for f in cat).cpu().numpy()
-        num_update = torch.from_numpy(np.round(num_masked / num_iter).astype(np.int64)).to(self.device)  # numpy rounding, as in :152-153
+        num_masked = sum(masks[f].sum(dim=-1) for f in cat)
+        # np.round(num_masked / num_iter) of :152-153, on the device (both round half to even): no host synchronisation in the decode loop
+        num_update = torch.round(num_masked.to(torch.float64) / num_iter).to(torch.int64)
         logits = torch.empty((B * S, eng.logit_width), dtype=torch.float32, device=self.device)
         final = None
         rows = torch.arange(B, device=self.device)
