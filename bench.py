@@ -313,7 +313,7 @@ class Workload:
         # the input pipeline's packed column format (flex_dm_b200.data.pack_batch): embedding rows of elements whose type does not carry
         # the field are not stored -- the reference's filter_padding overwrites them with <UNUSED> before the model reads them
         self.pinned_packed = [{k: torch.from_numpy(v).pin_memory() for k, v in pack_batch({k: b[k] for k in needed}, cols).items()} for b in host]
-        self.resident = [model.stage(b) for b in self.pinned]
+        self.resident = [model.stage(b) for b in self.pinned_packed]  # HBM-resident batches, in the same (packed) format the pipeline delivers
         torch.cuda.synchronize()
         self.elements_per_step = self.B * self.S  # every document is full length: valid elements = B * S
         self.h2d_bytes_dense = sum(t.numel() * t.element_size() for t in self.pinned[0].values())
@@ -658,7 +658,7 @@ def main():
                            "global_batch": wl.B * world, "seq_len": wl.S, "parallelism": "dp%d" % world,
                            "gradient_exchange": None if world == 1 else ("one NVLS kernel on the step's stream (multimem.ld_reduce / multimem.st, csrc/allreduce.cu)"
                                                                          if model._nvls is not None else "ncclAllReduce of the flat gradient buffer"),
-                           "l2_flush": "inputs larger than L2: %d distinct resident batches (%.0f MB) rotate; activations per step 1.6 GB" % (N_DEVICE_BATCHES, N_DEVICE_BATCHES * wl.h2d_bytes_dense / 1e6),
+                           "l2_flush": "inputs larger than L2: %d distinct resident batches (packed columns, %.0f MB) rotate; activations per step 1.6 GB" % (N_DEVICE_BATCHES, N_DEVICE_BATCHES * h2d_bytes / 1e6),
                            "loss_step0": step0 if step0 is not None else {"engine": loss0, "note": "global loss (metric rows summed over ranks); the oracle value is pinned at N=1"},
                            "loss_last_step": last_loss},
                 "roofline": roofline, "cpu_baseline": cpu,

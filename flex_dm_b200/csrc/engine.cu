@@ -237,7 +237,7 @@ static Workspace plan_workspace(const mfp_engine* h, int B, int S) {
   w.dcanvas = take((size_t)B * D * fl);
   w.iota = take((size_t)B * sizeof(int));
   w.zeros = take((size_t)B * sizeof(int));
-  w.det = take(kDetWsFloats * fl);
+  w.det = take(3 * kDetWsFloats * fl);  // one third per problem of a group launch
   w.ln_part = take((size_t)kLnBwdMaxCtas * 2 * D * fl);
   // 3xTF32 mode: low parts of the two operands of one GEMM (the widest operands are [T, LW] logits gradients and [T, 768] qkv)
   const size_t widest = std::max<size_t>(std::max<size_t>(h->sc.LW, 3 * D), std::max<size_t>((size_t)h->sc.Rp, 512));
@@ -341,6 +341,49 @@ static int gemm(mfp_engine* h, const float* A, int a_mn, int lda, const float* B
   const double bytes = 4.0 * ((double)M * K + (double)N * K + (double)M * N * ((ep.residual || ep.relu_src) ? 2.0 : 1.0));
   ProfScope prof(h, MFP_PROFILE_GEMM, st, bytes);
   return launch_gemm(h->maps, c, h->gemm_impl == 2 ? 0 : h->gemm_impl, st);
+}
+
+// A GEMM of a group launch: the arguments of gemm() as a value.
+struct GemmArgs {
+  const float* A; int a_mn, lda;
+  const float* B; int b_mn, ldb;
+  int M, N, K;
+  GemmEpilogue ep;
+  int splits;
+  float* colsum;
+};
+
+// Independent GEMMs (no output of one is an input of another) as ONE launch on the tcgen05 path: a weight gradient and the input
+// gradient off the same dY, the encoder's weight gradients.  Their tiles form one tile space (problem 0 first), so the split-K reduce-add
+// epilogue of a weight-gradient tile runs under the next tile's main loop and one drain / prologue / ramp per extra problem disappears.
+// Other GEMM implementations (SIMT bring-up, 3xTF32 with its shared operand scratch) run them one after the other.
+static int gemm_group(mfp_engine* h, const GemmArgs* g, int n, cudaStream_t st) {
+  if (h->gemm_impl != 0 || n == 1) {
+    for (int i = 0; i < n; ++i) MFP_TRY(gemm(h, g[i].A, g[i].a_mn, g[i].lda, g[i].B, g[i].b_mn, g[i].ldb, g[i].M, g[i].N, g[i].K, g[i].ep, g[i].splits, st, g[i].colsum));
+    return MFP_OK;
+  }
+  GemmCall calls[3];
+  double bytes = 0.0;
+  if (n > 3) { set_error("gemm_group: at most 3 problems"); return MFP_ERR_ARG; }
+  for (int i = 0; i < n; ++i) {
+    GemmCall& c = calls[i];
+    c = GemmCall{};
+    c.a = GemmOperand{g[i].A, g[i].a_mn, g[i].lda};
+    c.b = GemmOperand{g[i].B, g[i].b_mn, g[i].ldb};
+    c.M = g[i].M; c.N = g[i].N; c.K = g[i].K;
+    c.splits = g[i].splits;
+    c.ep = g[i].ep;
+    c.colsum = g[i].colsum;
+    if (h->deterministic) {  // every problem of the launch sums its partials in its own third of the scratch block
+      c.det_ws = wsp<float>(h, h->off.det) + (size_t)i * kDetWsFloats;
+      c.det_ws_floats = kDetWsFloats;
+      if (g[i].splits > 1 || g[i].colsum) h->launches++;  // splitk_reduce_kernel
+    }
+    bytes += 4.0 * ((double)c.M * c.K + (double)c.N * c.K + (double)c.M * c.N * ((c.ep.residual || c.ep.relu_src) ? 2.0 : 1.0));
+  }
+  h->launches++;
+  ProfScope prof(h, MFP_PROFILE_GEMM, st, bytes);
+  return launch_gemm_group(h->maps, calls, n, st);
 }
 
 // split-K factor of a weight-gradient GEMM (K = tokens): enough CTAs for ~2 per SM
@@ -767,8 +810,10 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
   if (first_stage == 0) {
     MFP_CUDA_OK(cudaMemsetAsync(G, 0, (size_t)h->param_count * sizeof(float), st));
     // ---- heads: dX = dlogits . Wh^T ; dWh = X^T . dlogits ; dbh = colsum(dlogits)
-    MFP_TRY(gemm(h, dlogits, 0, sc.LW, P + h->wh, 0, sc.LW, T, D, sc.LW, make_epilogue(dx, D), 1, st));
-    MFP_TRY(gemm(h, x + L * TD, 1, D, dlogits, 1, sc.LW, D, sc.LW, T, make_epilogue(G + h->wh, sc.LW), wgrad_splits(D, sc.LW, T), st, G + h->bh));
+    const GemmArgs gh[2] = {
+        {x + L * TD, 1, D, dlogits, 1, sc.LW, D, sc.LW, T, make_epilogue(G + h->wh, sc.LW), wgrad_splits(D, sc.LW, T), G + h->bh},
+        {dlogits, 0, sc.LW, P + h->wh, 0, sc.LW, T, D, sc.LW, make_epilogue(dx, D), 1, nullptr}};
+    MFP_TRY(gemm_group(h, gh, 2, st));
   }
   for (int i = L - 1; i >= 0; --i) {
     if (L - i < first_stage || L - i > last_stage) continue;  // stage L - i
@@ -833,25 +878,30 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
       }
       dy = dyb;
     }
-    MFP_TRY(gemm(h, hid, 1, kF, dy, 1, D, kF, D, T, make_epilogue(G + b.w2, D), wgrad_splits(kF, D, T), st, G + b.b2));
+    // every weight gradient shares its launch with the input gradient that hangs off the same dY (gemm_group)
     GemmEpilogue eh = make_epilogue(dhid, kF);
     eh.relu_src = hid; eh.ld_relu = kF;
-    MFP_TRY(gemm(h, dy, 0, D, P + b.w2, 0, D, T, kF, D, eh, 1, st));
-    MFP_TRY(gemm(h, ln2, 1, D, dhid, 1, kF, D, kF, T, make_epilogue(G + b.w1, kF), wgrad_splits(D, kF, T), st, G + b.b1));
-    MFP_TRY(gemm(h, dhid, 0, kF, P + b.w1, 0, kF, T, D, kF, make_epilogue(dtmp, D), 1, st));
+    const GemmArgs g1[2] = {{hid, 1, kF, dy, 1, D, kF, D, T, make_epilogue(G + b.w2, D), wgrad_splits(kF, D, T), G + b.b2},
+                            {dy, 0, D, P + b.w2, 0, D, T, kF, D, eh, 1, nullptr}};
+    MFP_TRY(gemm_group(h, g1, 2, st));
+    const GemmArgs g2[2] = {{ln2, 1, D, dhid, 1, kF, D, kF, T, make_epilogue(G + b.w1, kF), wgrad_splits(D, kF, T), G + b.b1},
+                            {dhid, 0, kF, P + b.w1, 0, kF, T, D, kF, make_epilogue(dtmp, D), 1, nullptr}};
+    MFP_TRY(gemm_group(h, g2, 2, st));
     MFP_TRY(launch_layernorm_bwd(xmid, dtmp, P + b.g2, stats + 2 * T, stats + 3 * T, dx, T, dx, G + b.g2, G + b.be2, st, nullptr, 0, nullptr,
                                  drop ? dyb : nullptr, h->cfg.dropout, seed, step, kSiteDropout + 2 * i, row0, ln_det));
     // attention branch: xmid = x_in + drop(attn.Wo + bo)
     dy = drop ? dyb : dx;
-    MFP_TRY(gemm(h, attn, 1, D, dy, 1, D, D, D, T, make_epilogue(G + b.wo, D), wgrad_splits(D, D, T), st, G + b.bo));
-    MFP_TRY(gemm(h, dy, 0, D, P + b.wo, 0, D, T, D, D, make_epilogue(dattn, D), 1, st));
+    const GemmArgs g3[2] = {{attn, 1, D, dy, 1, D, D, D, T, make_epilogue(G + b.wo, D), wgrad_splits(D, D, T), G + b.bo},
+                            {dy, 0, D, P + b.wo, 0, D, T, D, D, make_epilogue(dattn, D), 1, nullptr}};
+    MFP_TRY(gemm_group(h, g3, 2, st));
     {
       ProfScope prof(h, MFP_PROFILE_ATTENTION, st, 4.0 * T * (3.0 * D + D + D + 3.0 * D) + 4.0 * h->B * kH * h->S);  // qkv, out, dout in; dqkv out
       if (h->gemm_impl == 0 && h->S <= 128) MFP_TRY(launch_attention_bwd_tc(h->maps, qkv, attn, lse, dattn, attn_len, h->B, h->S, dqkv, st));
       else MFP_TRY(launch_attention_bwd(qkv, attn, lse, dattn, attn_len, h->B, h->S, dqkv, st));
     }
-    MFP_TRY(gemm(h, ln1, 1, D, dqkv, 1, 3 * D, D, 3 * D, T, make_epilogue(G + b.wqkv, 3 * D), wgrad_splits(D, 3 * D, T), st, G + b.bqkv));
-    MFP_TRY(gemm(h, dqkv, 0, 3 * D, P + b.wqkv, 0, 3 * D, T, D, 3 * D, make_epilogue(dtmp, D), 1, st));
+    const GemmArgs g4[2] = {{ln1, 1, D, dqkv, 1, 3 * D, D, 3 * D, T, make_epilogue(G + b.wqkv, 3 * D), wgrad_splits(D, 3 * D, T), G + b.bqkv},
+                            {dqkv, 0, 3 * D, P + b.wqkv, 0, 3 * D, T, D, 3 * D, make_epilogue(dtmp, D), 1, nullptr}};
+    MFP_TRY(gemm_group(h, g4, 2, st));
     if (i == 0)
       MFP_TRY(launch_layernorm_bwd(xi, dtmp, P + b.g1, stats, stats + T, dx, T, dx, G + b.g1, G + b.be1, st, wsp<unsigned char>(h, h->off.flags), sc.n_num,
                                    sc.n_num > 0 ? wsp<float>(h, h->off.dh0m) : nullptr, nullptr, 0.f, 0u, 0u, 0u, 0u, ln_det));
@@ -867,12 +917,18 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
   float* rowgrad = wsp<float>(h, h->off.rowgrad);
   MFP_TRY(launch_embed_onehot(sc, mod, flags, T, onehot, st, ctx_row, h->S));
   MFP_CUDA_OK(cudaMemsetAsync(rowgrad, 0, (size_t)sc.Rp * D * sizeof(float), st));
-  MFP_TRY(gemm(h, onehot, 1, sc.Rp, dx, 1, D, sc.R, D, T, make_epilogue(rowgrad, D), wgrad_splits(sc.R, D, T), st));
-  for (int f = 0; f < sc.F; ++f) {
-    const FieldDev& fd = sc.f[f];
-    if (fd.kind != 1) continue;
-    MFP_TRY(gemm(h, reinterpret_cast<const float*>(mod.cols[f]), 1, fd.C, wsp<float>(h, h->off.dh0m) + (size_t)fd.num_slot * TD, 1, D, fd.C, D, T,
-                 make_epilogue(G + fd.kernel_off, D), wgrad_splits(fd.C, D, T), st));
+  {
+    GemmArgs ge[3];
+    int ng = 0;
+    ge[ng++] = GemmArgs{onehot, 1, sc.Rp, dx, 1, D, sc.R, D, T, make_epilogue(rowgrad, D), wgrad_splits(sc.R, D, T), nullptr};
+    for (int f = 0; f < sc.F; ++f) {
+      const FieldDev& fd = sc.f[f];
+      if (fd.kind != 1) continue;
+      if (ng == 3) { MFP_TRY(gemm_group(h, ge, ng, st)); ng = 0; }
+      ge[ng++] = GemmArgs{reinterpret_cast<const float*>(mod.cols[f]), 1, fd.C, wsp<float>(h, h->off.dh0m) + (size_t)fd.num_slot * TD, 1, D, fd.C, D, T,
+                          make_epilogue(G + fd.kernel_off, D), wgrad_splits(fd.C, D, T), nullptr};
+    }
+    MFP_TRY(gemm_group(h, ge, ng, st));
   }
   MFP_TRY(launch_embed_scatter(sc, rowgrad, G, st));
   h->launches += 2;

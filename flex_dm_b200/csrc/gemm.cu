@@ -93,12 +93,28 @@ struct GemmSmem {
 // warps are issue-bound (one warp per scheduler), every dead branch in their loop costs throughput.
 enum : int { kEpiBias = 1, kEpiRelu = 2, kEpiResidual = 4, kEpiReluMask = 8, kEpiDropout = 16, kEpiRowflag = 32 };
 
+// One GEMM of a launch.  A launch carries up to kMaxGroup INDEPENDENT problems whose tiles form one tile space (problem 0's tiles first):
+// a weight gradient and the input gradient that hangs off the same dY run as one launch -- every CTA takes its one long split-K tile of
+// the weight gradient and then its share of the input-gradient tiles, so the reduce-add epilogue of the first overlaps the main loop of
+// the second through the double-buffered accumulator, and one launch boundary (drain, prologue, ramp) disappears.
+constexpr int kMaxGroup = 3;
+struct GemmProblem {
+  CUtensorMap tmA, tmB, tmOut, tmALo, tmBLo;
+  int M, N, K, a_mn, b_mn;
+  GemmTiles tl;
+  GemmEpilogue ep;
+  float* colsum;
+  int tile0;     // first index of this problem's tiles in the launch's tile space
+  int aux_kind;  // 0, or the kernel's aux_mode (1 residual, 2 ReLU mask) when this problem uses the aux operand
+};
+struct GemmGroup {
+  int n, total_tiles, any_colsum, pad;
+  GemmProblem p[kMaxGroup];
+};
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
-                  const __grid_constant__ CUtensorMap tmALo, const __grid_constant__ CUtensorMap tmBLo, int M, int N, int K, int a_mn, int b_mn, GemmTiles tl,
-                  GemmEpilogue ep,
-                  float* __restrict__ colsum, GemmTune tune, unsigned long long* __restrict__ trace) {
+gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned long long* __restrict__ trace) {
   constexpr int aux_mode = (EPI & kEpiResidual) ? 1 : ((EPI & kEpiReluMask) ? 2 : 0);
   using L = GemmSmem<BN, aux_mode != 0>;
   constexpr int kStages = L::kStages;
@@ -115,29 +131,32 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // 3xTF32 (tl.passes == 3): the K loop runs three times over the operands -- (A, B), (A_lo, B), (A, B_lo), x_lo = x - tf32(x) -- into the
-  // same accumulator: a_hi b_hi + a_lo b_hi + a_hi b_lo, fp32-accurate products on the TF32 tensor cores (only the producers and the
-  // column-sum role know; k-block kb of the tripled range is block kb % kb_single of pass kb / kb_single)
-  const int kb_single = (K + kBK - 1) / kBK;
-  const int num_kb = kb_single * tl.passes;
-  const int tiles_mn = tl.tiles_m * tl.tiles_n;
-  const int num_tiles = tiles_mn * tl.splits;
-  const bool do_colsum = (colsum != nullptr);
+  const int num_tiles = grp.total_tiles;
+  const bool any_colsum = grp.any_colsum != 0;
+  // which problem a tile of the launch's tile space belongs to
+  auto problem_of = [&](int tile) {
+    int pi = 0;
+    if (grp.n > 1 && tile >= grp.p[1].tile0) pi = 1;
+    if (grp.n > 2 && tile >= grp.p[2].tile0) pi = 2;
+    return pi;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), 2);                   // the A producer and the B producer each arrive with their own byte count
-      mbar_init(empty_bar(s), do_colsum ? 2 : 1);  // MMA commit (+ the column-sum warp)
+      mbar_init(full_bar(s), 2);                    // the A producer and the B producer each arrive with their own byte count
+      mbar_init(empty_bar(s), any_colsum ? 2 : 1);  // MMA commit (+ the column-sum warp, which then attends every tile of the launch)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    prefetch_tensormap(&tmA);
-    prefetch_tensormap(&tmB);
-    prefetch_tensormap(&tmOut);
-    if (tl.passes == 3) { prefetch_tensormap(&tmALo); prefetch_tensormap(&tmBLo); }
+    for (int i = 0; i < grp.n; ++i) {
+      prefetch_tensormap(&grp.p[i].tmA);
+      prefetch_tensormap(&grp.p[i].tmB);
+      prefetch_tensormap(&grp.p[i].tmOut);
+      if (grp.p[i].tl.passes == 3) { prefetch_tensormap(&grp.p[i].tmALo); prefetch_tensormap(&grp.p[i].tmBLo); }
+    }
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(2 * BN) : "memory");
@@ -161,6 +180,9 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(bar, parity);
     }
   };
+  // 3xTF32 (tl.passes == 3): the K loop runs three times over the operands -- (A, B), (A_lo, B), (A, B_lo), x_lo = x - tf32(x) -- into the
+  // same accumulator: a_hi b_hi + a_lo b_hi + a_hi b_lo, fp32-accurate products on the TF32 tensor cores (only the producers and the
+  // column-sum role know; k-block kbt of the tripled range is block kbt % kb_single of pass kbt / kb_single)
 
   if (warp == 0 || warp == 3) {
     // ===== TMA producers: warp 0 feeds the A half of every stage, warp 3 the B half =====
@@ -174,13 +196,19 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int split = tile / tiles_mn, r = tile - split * tiles_mn;
+        const GemmProblem& P = grp.p[problem_of(tile)];
+        const GemmTiles tl = P.tl;
+        const int a_mn = P.a_mn, b_mn = P.b_mn;
+        const int kb_single = (P.K + kBK - 1) / kBK, num_kb = kb_single * tl.passes;
+        const int tiles_mn = tl.tiles_m * tl.tiles_n;
+        const int lt = tile - P.tile0;
+        const int split = lt / tiles_mn, r = lt - split * tiles_mn;
         const int m0 = (r / tl.tiles_n) * kBM, n0 = (r % tl.tiles_n) * BN;
         const int kb0 = split * tl.kb_per_split, kb1 = min(num_kb, kb0 + tl.kb_per_split);
         for (int kbt = kb0; kbt < kb1; ++kbt) {
           const int pass = kbt / kb_single, kb = kbt - pass * kb_single;
-          const CUtensorMap* mapA = (pass == 1) ? &tmALo : &tmA;
-          const CUtensorMap* mapB = (pass == 2) ? &tmBLo : &tmB;
+          const CUtensorMap* mapA = (pass == 1) ? &P.tmALo : &P.tmA;
+          const CUtensorMap* mapB = (pass == 2) ? &P.tmBLo : &P.tmB;
           wait_t(empty_bar(stage), phase ^ 1u, w0);
           const uint32_t sa = base + stage * L::kStageBytes;
           const uint32_t sb = sa + L::kABytes;
@@ -213,24 +241,29 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      // instruction descriptor: c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13), a_major bit15, b_major bit16, N>>3 [17,23), M>>4 [24,29)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn ? 1 : 0) << 15) | ((uint32_t)(b_mn ? 1 : 0) << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-      // Shared-memory descriptors: built once for stage 0 / k-step 0; the address field (bits [0,14), units of 16 B) is all that
-      // changes, so a stage or k-step is one 64-bit add.  This thread's instruction stream is serial and sits on the critical path
-      // (measured: ~1000 cycles per k-block against 512 of tensor time), so nothing is recomputed inside the loop.
+      // Shared-memory descriptors: built per tile for stage 0 / k-step 0; the address field (bits [0,14), units of 16 B) is all that
+      // changes inside a tile, so a stage or k-step is one 64-bit add.  This thread's instruction stream is serial and sits on the
+      // critical path (measured: ~1000 cycles per k-block against 512 of tensor time), so nothing is recomputed inside the k loop.
       // K-major: 8 fp32 of K = 32 B inside the 128 B swizzle row (SWIZZLE_128B, 8-row atoms 1024 B apart).
       // MN-major: 8 K-rows = two 4-row 512 B atoms of SWIZZLE_128B_BASE32B (SBO), 32-wide MN chunks kBK*128 B apart (LBO).
-      const uint64_t da0 = a_mn ? make_smem_desc(base, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(base, tune.k_lbo, tune.k_sbo, tune.k_layout);
-      const uint64_t db0 = b_mn ? make_smem_desc(base + L::kABytes, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(base + L::kABytes, tune.k_lbo, tune.k_sbo, tune.k_layout);
-      const uint64_t a_step = a_mn ? (1024u >> 4) : (32u >> 4), b_step = b_mn ? (1024u >> 4) : (32u >> 4);
       constexpr uint64_t kStageStep = (uint64_t)(L::kStageBytes >> 4);
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
-      uint64_t da = da0, db = db0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int split = tile / tiles_mn;
+        const GemmProblem& P = grp.p[problem_of(tile)];
+        const GemmTiles tl = P.tl;
+        const int a_mn = P.a_mn, b_mn = P.b_mn;
+        // instruction descriptor: c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13), a_major bit15, b_major bit16, N>>3 [17,23), M>>4 [24,29)
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn ? 1 : 0) << 15) | ((uint32_t)(b_mn ? 1 : 0) << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+        const uint64_t da0 = a_mn ? make_smem_desc(base, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(base, tune.k_lbo, tune.k_sbo, tune.k_layout);
+        const uint64_t db0 = b_mn ? make_smem_desc(base + L::kABytes, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(base + L::kABytes, tune.k_lbo, tune.k_sbo, tune.k_layout);
+        const uint64_t a_step = a_mn ? (1024u >> 4) : (32u >> 4), b_step = b_mn ? (1024u >> 4) : (32u >> 4);
+        const int num_kb = ((P.K + kBK - 1) / kBK) * tl.passes;
+        const int tiles_mn = tl.tiles_m * tl.tiles_n;
+        const int split = (tile - P.tile0) / tiles_mn;
         const int kb0 = split * tl.kb_per_split, kb1 = min(num_kb, kb0 + tl.kb_per_split);
+        uint64_t da = da0 + (uint64_t)stage * kStageStep, db = db0 + (uint64_t)stage * kStageStep;
         wait_t(tempty_bar(as), aphase ^ 1u, w1);  // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
@@ -259,17 +292,25 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // for the Dense layers: 16 or 8 rows per CTA; otherwise m-tile 0 takes them all), so that no CTA's ring is held up by
     // this role.  Thread t owns two groups of 4 consecutive columns, 128 columns apart: chunk (t>>3) + 4i (32 columns, 4 KB
     // apart), 32-byte atom (t>>1)&3, half t&1; a quarter-warp reads one contiguous 128-byte row per LDS.128 (conflict-free under
-    // the 32-byte-atom swizzle).
-    if (do_colsum) {
+    // the 32-byte-atom swizzle).  In a launch that mixes problems with and without a column sum this warp attends every tile (the
+    // ring's empty barriers count it) and only sums where one is asked for.
+    if (any_colsum) {
       const int chunk0 = lane >> 3, atom = (lane >> 1) & 3, half = lane & 1;
-      const bool share = (32 % tl.tiles_m) == 0;
-      const int rows_per = share ? 32 / tl.tiles_m : 32;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int split = tile / tiles_mn, r = tile - split * tiles_mn;
+        const GemmProblem& P = grp.p[problem_of(tile)];
+        const GemmTiles tl = P.tl;
+        float* colsum = P.colsum;
+        const int N = P.N;
+        const int kb_single = (P.K + kBK - 1) / kBK, num_kb = kb_single * tl.passes;
+        const int tiles_mn = tl.tiles_m * tl.tiles_n;
+        const bool share = (32 % tl.tiles_m) == 0;
+        const int rows_per = share ? 32 / tl.tiles_m : 32;
+        const int lt = tile - P.tile0;
+        const int split = lt / tiles_mn, r = lt - split * tiles_mn;
         const int mt = r / tl.tiles_n;
-        const bool active = share || mt == 0;
+        const bool active = colsum != nullptr && (share || mt == 0);
         const int k_first = share ? mt * rows_per : 0;
         const int n0 = (r % tl.tiles_n) * BN;
         const int kb0 = split * tl.kb_per_split, kb1 = min(num_kb, kb0 + tl.kb_per_split);
@@ -293,7 +334,7 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (lane == 0) mbar_arrive(empty_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        if (tl.det_colsum) {  // slot (split, m-tile): summed in slot order by splitk_reduce_kernel (CTAs without a share store zeros)
+        if (colsum != nullptr && tl.det_colsum) {  // slot (split, m-tile): summed in slot order by splitk_reduce_kernel (CTAs without a share store zeros)
 #pragma unroll
           for (int i = 0; i < BN / 128; ++i) {
             const int col = n0 + (chunk0 + 4 * i) * 32 + atom * 8 + half * 4;
@@ -320,7 +361,7 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // TMA-store epilogue had 25-40 % of all samples on cp.async.bulk.wait_group.read / the aux mbarrier, and a plain store epilogue took
     // 5 800 cycles per 128 x 256 tile.  So results go accumulator registers (lane = row) -> swizzled 4 KB staging chunk -> registers in
     // the transposed mapping (8 lanes per 128-byte row segment) -> st.global.v4, full lines per quarter-warp; the residual / ReLU-mask
-    // operand comes in by ld.global.nc.v4 in the same mapping, one chunk ahead (registers), and through the same staging chunk.
+    // operand comes in by ld.global.v4 in the same mapping, one chunk ahead (registers), and through the same staging chunk.
     // Only split-K accumulation (weight gradients: a few tiles) still uses TMA reduce-add.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int h = (warp - kEpiWarp0) >> 2;
@@ -330,46 +371,64 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t sw = (uint32_t)(lane & 7);
     const int tr = lane >> 3, ts = lane & 7;  // transposed mapping: instruction i covers rows 4 i + tr, 16-byte segment ts
     uint8_t* own_row = epi_ptr + lane * 128;
-    const float* aux_src = aux_mode == 1 ? ep.residual : ep.relu_src;
-    const int aux_ld = aux_mode == 1 ? ep.ldr : ep.ld_relu;
-    const uint32_t drop_thr = dropout_threshold(ep.drop_rate);
-    const float drop_scale = 1.0f / (1.0f - ep.drop_rate);
     int as = 0;
     uint32_t aphase = 0;
-    auto aux_wanted = [&](int tile) { return aux_mode == 2 || (aux_mode == 1 && tile < tiles_mn); };  // the residual is added by split 0 only
-    auto chunks_of = [&](int tile) { const int n0 = ((tile % tiles_mn) % tl.tiles_n) * BN; return min(BN / 32, (N - n0 + 31) / 32); };
+    // geometry of a tile of the launch's tile space (for this warp: rows of its quarter, chunks of its parity)
+    struct TileGeo { const GemmProblem* P; int split, m0, n0, nchunks; bool use_aux; };
+    auto geo_of = [&](int tile) {
+      TileGeo g;
+      g.P = &grp.p[problem_of(tile)];
+      const GemmTiles& tl = g.P->tl;
+      const int tiles_mn = tl.tiles_m * tl.tiles_n;
+      const int lt = tile - g.P->tile0;
+      g.split = lt / tiles_mn;
+      const int r = lt - g.split * tiles_mn;
+      g.m0 = (r / tl.tiles_n) * kBM;
+      g.n0 = (r % tl.tiles_n) * BN;
+      g.nchunks = min(BN / 32, (g.P->N - g.n0 + 31) / 32);
+      g.use_aux = aux_mode != 0 && g.P->aux_kind != 0 && (aux_mode == 2 || g.split == 0);  // the residual is added by split 0 only
+      return g;
+    };
     float4 an[8];  // aux operand of the NEXT chunk this warp will process, transposed mapping
-    auto fetch_aux = [&](int tile, int c) {
-      const int r = tile % tiles_mn;
-      const int grow0 = (r / tl.tiles_n) * kBM + q * 32 + tr, gcol = (r % tl.tiles_n) * BN + c * 32 + ts * 4;
+    auto fetch_aux = [&](const TileGeo& g, int c) {
+      const float* aux_src = aux_mode == 1 ? g.P->ep.residual : g.P->ep.relu_src;
+      const int aux_ld = aux_mode == 1 ? g.P->ep.ldr : g.P->ep.ld_relu;
+      const int grow0 = g.m0 + q * 32 + tr, gcol = g.n0 + c * 32 + ts * 4;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int grow = grow0 + 4 * i;
         // plain (coherent) loads: the residual may be the output buffer itself (in-place x += ...); every element is read before the one warp that owns it writes it
-        an[i] = (grow < M && gcol < N) ? *reinterpret_cast<const float4*>(aux_src + (size_t)grow * aux_ld + gcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+        an[i] = (grow < g.P->M && gcol < g.P->N) ? *reinterpret_cast<const float4*>(aux_src + (size_t)grow * aux_ld + gcol) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     if constexpr (aux_mode != 0) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) an[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if ((int)blockIdx.x < num_tiles && aux_wanted(blockIdx.x) && h < chunks_of(blockIdx.x)) fetch_aux(blockIdx.x, h);
+      if ((int)blockIdx.x < num_tiles) {
+        const TileGeo g0 = geo_of(blockIdx.x);
+        if (g0.use_aux && h < g0.nchunks) fetch_aux(g0, h);
+      }
     }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int split = tile / tiles_mn, r = tile - split * tiles_mn;
-      const int m0 = (r / tl.tiles_n) * kBM, n0 = (r % tl.tiles_n) * BN;
+      const TileGeo g = geo_of(tile);
+      const GemmEpilogue& ep = g.P->ep;
+      const GemmTiles& tl = g.P->tl;
+      const int M = g.P->M, N = g.P->N;
+      const int split = g.split, m0 = g.m0, n0 = g.n0, nchunks = g.nchunks;
+      const bool use_aux = g.use_aux;
       const int row0 = m0 + q * 32;
       const int row = row0 + lane;
       const int out_row0 = row0 + split * tl.slab_rows;
       const bool lead_split = (split == 0);
-      const bool use_aux = aux_mode != 0 && (aux_mode == 2 || lead_split);
-      const int nchunks = min(BN / 32, (N - n0 + 31) / 32);
+      const uint32_t drop_thr = dropout_threshold(ep.drop_rate);
+      const float drop_scale = 1.0f / (1.0f - ep.drop_rate);
       bool flagged = false;
-      if constexpr (EPI & kEpiRowflag) flagged = row < M && ep.rowflag[row];
+      if constexpr (EPI & kEpiRowflag) flagged = ep.rowflag != nullptr && row < M && ep.rowflag[row];
       // The tile's bias row (BN columns) is fetched once, 8 columns per lane, while the accumulator is still being computed,
       // and handed out by warp shuffles: a global load per chunk would put its L2 latency on the epilogue's critical path.
       float bt[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if constexpr (EPI & kEpiBias) {
-        if (lead_split && lane < BN / 8) {
+        if (ep.bias != nullptr && lead_split && lane < BN / 8) {
           const int bc = n0 + lane * 8;
           if (bc < N) { const float4 t = __ldg(reinterpret_cast<const float4*>(ep.bias + bc)); bt[0] = t.x; bt[1] = t.y; bt[2] = t.z; bt[3] = t.w; }
           if (bc + 4 < N) { const float4 t = __ldg(reinterpret_cast<const float4*>(ep.bias + bc + 4)); bt[4] = t.x; bt[5] = t.y; bt[6] = t.z; bt[7] = t.w; }
@@ -390,7 +449,7 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (trace) { const long long t0 = clock64(); tmem_ld32(tacc + (uint32_t)(c * 32), rr); w2 += (unsigned long long)(clock64() - t0); }
         else tmem_ld32(tacc + (uint32_t)(c * 32), rr);
         if (c + 2 >= nchunks) release_acc();
-        if (ep.atomic && lane == 0) {  // the staging chunk has been read out by the previous reduce-add
+        if (lane == 0) {  // the staging chunk has been read out by an earlier tile's reduce-add (a no-op when none is pending)
           if (trace) { const long long t0 = clock64(); tma_wait_group_read<0>(); w1 += (unsigned long long)(clock64() - t0); }
           else tma_wait_group_read<0>();
         }
@@ -404,10 +463,13 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           __syncwarp();
           if (c + 2 < nchunks) {
-            if (use_aux) fetch_aux(tile, c + 2);
+            if (use_aux) fetch_aux(g, c + 2);
           } else {
             const int nt = tile + (int)gridDim.x;
-            if (nt < num_tiles && aux_wanted(nt) && h < chunks_of(nt)) fetch_aux(nt, h);
+            if (nt < num_tiles) {
+              const TileGeo gn = geo_of(nt);
+              if (gn.use_aux && h < gn.nchunks) fetch_aux(gn, h);
+            }
           }
         }
         U4 dr = {0u, 0u, 0u, 0u};
@@ -425,18 +487,24 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int e = 0; e < 4; ++e) v[e] += __shfl_sync(0xffffffffu, bt[(j & 1) * 4 + e], c * 4 + (j >> 1));
           }
           if constexpr (EPI & kEpiRelu) {
+            if (ep.relu) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.0f);
+              for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.0f);
+            }
           }
           float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
           if constexpr (aux_mode != 0) a = av[j];
           if constexpr (aux_mode == 2) {
-            v[0] = a.x > 0.0f ? v[0] : 0.0f; v[1] = a.y > 0.0f ? v[1] : 0.0f;
-            v[2] = a.z > 0.0f ? v[2] : 0.0f; v[3] = a.w > 0.0f ? v[3] : 0.0f;
+            if (use_aux) {
+              v[0] = a.x > 0.0f ? v[0] : 0.0f; v[1] = a.y > 0.0f ? v[1] : 0.0f;
+              v[2] = a.z > 0.0f ? v[2] : 0.0f; v[3] = a.w > 0.0f ? v[3] : 0.0f;
+            }
           }
           if constexpr (EPI & kEpiDropout) {  // one Philox block per eight columns (j even computes it, j odd uses its second half)
-            if ((j & 1) == 0) dr = philox4x32_10((((uint32_t)row + ep.drop_row0) * (uint32_t)N + (uint32_t)(col0 + 4 * j)) >> 3, ep.drop_site, 0u, 0u, ep.drop_seed, ep.drop_step);
-            dropout_apply4(v, (j & 1) ? dr.z : dr.x, (j & 1) ? dr.w : dr.y, drop_thr, drop_scale);
+            if (ep.drop_enabled) {
+              if ((j & 1) == 0) dr = philox4x32_10((((uint32_t)row + ep.drop_row0) * (uint32_t)N + (uint32_t)(col0 + 4 * j)) >> 3, ep.drop_site, 0u, 0u, ep.drop_seed, ep.drop_step);
+              dropout_apply4(v, (j & 1) ? dr.z : dr.x, (j & 1) ? dr.w : dr.y, drop_thr, drop_scale);
+            }
           }
           if constexpr (EPI & kEpiRowflag) {
             if (flagged) { v[0] = v[1] = v[2] = v[3] = 0.0f; }
@@ -448,7 +516,7 @@ gemm_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_reduce_add_2d(&tmOut, epi, col0, row0);
+            tma_reduce_add_2d(&g.P->tmOut, epi, col0, row0);
             tma_commit_group();
           }
         } else {
@@ -692,16 +760,21 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int EPI>
-static int launch_tcgen05(TensorMapCache* cache, const GemmCall& c, cudaStream_t stream) {
-  using L = GemmSmem<BN, (EPI & (kEpiResidual | kEpiReluMask)) != 0>;
-  static_assert(L::kTotal <= 227 * 1024, "GEMM shared memory exceeds the 227 KB per-CTA limit");
-  static bool attr_set = false;
-  if (!attr_set) {
-    MFP_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tcgen05<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    attr_set = true;
-  }
-  cache->trim();
+static int epi_bits(const GemmEpilogue& ep) {
+  return (ep.bias ? kEpiBias : 0) | (ep.relu ? kEpiRelu : 0) | (ep.residual ? kEpiResidual : 0) | (ep.relu_src ? kEpiReluMask : 0) |
+         (ep.drop_enabled ? kEpiDropout : 0) | (ep.rowflag ? kEpiRowflag : 0);
+}
+
+// What has to follow a problem's GEMM in deterministic mode: the fixed-order sum of its split-K / column-sum partials.
+struct DetReduce {
+  bool split = false;
+  float* col = nullptr;
+  int splits = 0, tiles_m = 0, slab_rows = 0;
+};
+
+// Tensor maps, tiling and epilogue of one problem of a launch (tile width BN is the launch's).
+template <int BN>
+static int prepare_problem(TensorMapCache* cache, const GemmCall& c, int epi_launch, GemmProblem* P, DetReduce* red) {
   if (c.ep.residual && c.ep.relu_src) { set_error("gemm: residual and relu_src cannot be combined"); return MFP_ERR_ARG; }
   if (c.colsum && !c.b.mn_major) { set_error("gemm: the fused column sum needs an MN-major B operand"); return MFP_ERR_ARG; }
   // MN-major operand [K][MN] with pitch ld: 2-D boxes of 32 columns x kBK rows, or -- when MN is whole 32-column blocks -- a 3-D
@@ -730,8 +803,6 @@ static int launch_tcgen05(TensorMapCache* cache, const GemmCall& c, cudaStream_t
     mbl = c.b.mn_major ? mn_map(blo, c.N, BN, &unused_mode) : cache->get(blo.ptr, c.K, c.N, blo.ld, kBK, BN, kMapOperandK);
   }
   if (!ma || !mb || !mo || !mal || !mbl) return MFP_ERR_CUDA;
-  static const GemmTune tune = {env_u32("FLEXDM_MN_LBO", kBK * 128), env_u32("FLEXDM_MN_SBO", 512), env_u32("FLEXDM_K_LBO", 16), env_u32("FLEXDM_K_SBO", 1024),
-                                k_atom32() ? 1u : 2u};
   GemmTiles tl;
   tl.passes = (c.a_lo && c.b_lo) ? 3 : 1;
   const int num_kb = tl.passes * ((c.K + kBK - 1) / kBK);
@@ -746,30 +817,64 @@ static int launch_tcgen05(TensorMapCache* cache, const GemmCall& c, cudaStream_t
   tl.det_colsum = 0;
   float* colsum = c.colsum;
   const bool det = c.det_ws != nullptr;
-  const bool det_split = det && tl.splits > 1;
-  float* det_col = nullptr;
-  if (det_split || (det && c.colsum)) {
-    tl.slab_rows = det_split ? tl.tiles_m * kBM : 0;
-    const size_t part_floats = det_split ? (size_t)tl.splits * tl.slab_rows * c.N : 0;
+  red->split = det && tl.splits > 1;
+  red->col = nullptr;
+  if (red->split || (det && c.colsum)) {
+    tl.slab_rows = red->split ? tl.tiles_m * kBM : 0;
+    const size_t part_floats = red->split ? (size_t)tl.splits * tl.slab_rows * c.N : 0;
     const size_t col_floats = c.colsum ? (size_t)tl.splits * tl.tiles_m * c.N : 0;
     if (part_floats + col_floats > c.det_ws_floats) { set_error("gemm: deterministic scratch too small (%zu > %zu floats)", part_floats + col_floats, c.det_ws_floats); return MFP_ERR_ARG; }
-    if (det_split) {
+    if (red->split) {
       if (c.ep.bias || c.ep.residual || c.ep.relu || c.ep.relu_src || c.ep.drop_enabled || c.ep.rowflag) { set_error("gemm: deterministic split-K takes a plain epilogue"); return MFP_ERR_ARG; }
       ep.out = c.det_ws;  // split s stores its tiles at row offset s * slab_rows of the scratch block
       ep.ldo = c.N;
     }
-    if (c.colsum) { det_col = c.det_ws + part_floats; colsum = det_col; tl.det_colsum = 1; }
+    if (c.colsum) { red->col = c.det_ws + part_floats; colsum = red->col; tl.det_colsum = 1; }
   } else if (tl.splits > 1) {
     ep.atomic = 1;
   }
-  const int num_tiles = tl.tiles_m * tl.tiles_n * tl.splits;
-  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  red->splits = tl.splits; red->tiles_m = tl.tiles_m; red->slab_rows = tl.slab_rows;
+  P->tmA = *ma; P->tmB = *mb; P->tmOut = *mo; P->tmALo = *mal; P->tmBLo = *mbl;
+  P->M = c.M; P->N = c.N; P->K = c.K; P->a_mn = a_mode; P->b_mn = b_mode;
+  P->tl = tl;
+  P->ep = ep;
+  P->colsum = colsum;
+  const int launch_aux = (epi_launch & kEpiResidual) ? 1 : ((epi_launch & kEpiReluMask) ? 2 : 0);
+  P->aux_kind = (c.ep.residual || c.ep.relu_src) ? launch_aux : 0;
+  return MFP_OK;
+}
+
+template <int BN, int EPI>
+static int launch_tcgen05(TensorMapCache* cache, const GemmCall* calls, int n, cudaStream_t stream) {
+  using L = GemmSmem<BN, (EPI & (kEpiResidual | kEpiReluMask)) != 0>;
+  static_assert(L::kTotal <= 227 * 1024, "GEMM shared memory exceeds the 227 KB per-CTA limit");
+  static_assert(sizeof(GemmGroup) <= 4000, "kernel parameters must stay under 4 KB");
+  static bool attr_set = false;
+  if (!attr_set) {
+    MFP_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tcgen05<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  cache->trim();
+  static const GemmTune tune = {env_u32("FLEXDM_MN_LBO", kBK * 128), env_u32("FLEXDM_MN_SBO", 512), env_u32("FLEXDM_K_LBO", 16), env_u32("FLEXDM_K_SBO", 1024),
+                                k_atom32() ? 1u : 2u};
+  GemmGroup grp;
+  memset(&grp, 0, sizeof(grp));
+  DetReduce red[kMaxGroup];
+  grp.n = n;
+  int tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    MFP_TRY(prepare_problem<BN>(cache, calls[i], EPI, &grp.p[i], &red[i]));
+    grp.p[i].tile0 = tiles;
+    tiles += grp.p[i].tl.tiles_m * grp.p[i].tl.tiles_n * grp.p[i].tl.splits;
+    if (grp.p[i].colsum) grp.any_colsum = 1;
+  }
+  grp.total_tiles = tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
   static const bool trace_on = getenv("FLEXDM_GEMM_TRACE") != nullptr;  // debugging aid: prints per-role wait cycles of every launch
   static unsigned long long* trace = nullptr;
   if (trace_on && !trace) { MFP_CUDA_OK(cudaMalloc(&trace, 148 * 8 * sizeof(unsigned long long))); }
   if (trace_on) MFP_CUDA_OK(cudaMemsetAsync(trace, 0, 148 * 8 * sizeof(unsigned long long), stream));
-  MFP_CUDA_OK(launch_pdl(gemm_tf32_tcgen05<BN, EPI>, grid, kGemmThreads, L::kTotal, stream, *ma, *mb, *mo, *mal, *mbl, c.M, c.N, c.K, a_mode, b_mode, tl, ep, colsum,
-                         tune, trace_on ? trace : nullptr));
+  MFP_CUDA_OK(launch_pdl(gemm_tf32_tcgen05<BN, EPI>, grid, kGemmThreads, L::kTotal, stream, grp, tune, trace_on ? trace : nullptr));
   if (trace_on) {
     unsigned long long hbuf[148 * 8];
     MFP_CUDA_OK(cudaStreamSynchronize(stream));
@@ -777,23 +882,51 @@ static int launch_tcgen05(TensorMapCache* cache, const GemmCall& c, cudaStream_t
     double acc[8] = {};
     for (int b = 0; b < grid && b < 148; ++b)
       for (int k = 0; k < 8; ++k) acc[k] += (double)hbuf[b * 8 + k] / grid;
-    fprintf(stderr, "gemm trace M=%d N=%d K=%d a_mn=%d b_mn=%d epi=%d splits=%d tiles/cta=%.2f | producer: wait_empty %.0f of %.0f | mma: wait_full %.0f wait_tempty %.0f | "
-            "epilogue(w4): wait_tfull %.0f wait_store %.0f wait_tmem_ld %.0f of %.0f cycles\n", c.M, c.N, c.K, c.a.mn_major, c.b.mn_major, EPI, tl.splits,
-            (double)num_tiles / grid, acc[0], acc[7], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6]);
+    const GemmCall& c = calls[0];
+    fprintf(stderr, "gemm trace problems=%d first: M=%d N=%d K=%d a_mn=%d b_mn=%d epi=%d splits=%d tiles/cta=%.2f | producer: wait_empty %.0f of %.0f | mma: wait_full %.0f wait_tempty %.0f | "
+            "epilogue(w4): wait_tfull %.0f wait_store %.0f wait_tmem_ld %.0f of %.0f cycles\n", n, c.M, c.N, c.K, c.a.mn_major, c.b.mn_major, EPI, grp.p[0].tl.splits,
+            (double)tiles / grid, acc[0], acc[7], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6]);
   }
   MFP_CUDA_OK(cudaGetLastError());
-  if (det_split || det_col) {
-    const size_t n4 = det_split ? (size_t)c.M * c.N / 4 : (size_t)c.N / 4;
-    MFP_CUDA_OK(launch_pdl(splitk_reduce_kernel, (unsigned)((n4 + 255) / 256), 256, 0, stream, det_split ? (const float*)c.det_ws : (const float*)nullptr, tl.splits,
-                           (size_t)tl.slab_rows * c.N, c.M, c.N, c.ep.out, c.ep.ldo, (const float*)det_col, tl.splits * tl.tiles_m, c.colsum));
+  for (int i = 0; i < n; ++i) {
+    if (!red[i].split && !red[i].col) continue;
+    const GemmCall& c = calls[i];
+    const size_t n4 = red[i].split ? (size_t)c.M * c.N / 4 : (size_t)c.N / 4;
+    MFP_CUDA_OK(launch_pdl(splitk_reduce_kernel, (unsigned)((n4 + 255) / 256), 256, 0, stream, red[i].split ? (const float*)c.det_ws : (const float*)nullptr, red[i].splits,
+                           (size_t)red[i].slab_rows * c.N, c.M, c.N, c.ep.out, c.ep.ldo, (const float*)red[i].col, red[i].splits * red[i].tiles_m, c.colsum));
     MFP_CUDA_OK(cudaGetLastError());
   }
   return MFP_OK;
 }
 
-int launch_gemm(TensorMapCache* cache, const GemmCall& c, int impl, cudaStream_t stream) {
+static int check_call(const GemmCall& c) {
   if (c.M <= 0 || c.N <= 0 || c.K <= 0) { set_error("gemm: empty problem %dx%dx%d", c.M, c.N, c.K); return MFP_ERR_ARG; }
   if ((c.N % 4) || (c.ep.ldo % 4)) { set_error("gemm: N and ldo must be multiples of 4 (N=%d ldo=%d)", c.N, c.ep.ldo); return MFP_ERR_ARG; }
+  return MFP_OK;
+}
+
+// One launch for up to kMaxGroup independent problems (tcgen05 path); `epi` = union of their epilogue bits.
+static int launch_tcgen05_any(TensorMapCache* cache, const GemmCall* calls, int n, int epi, bool wide, cudaStream_t stream) {
+#define MFP_GEMM_CASE(E) \
+  case (E): return wide ? launch_tcgen05<256, (E)>(cache, calls, n, stream) : launch_tcgen05<128, (E)>(cache, calls, n, stream);
+  switch (epi) {
+    MFP_GEMM_CASE(0)                                           // dgrad / wgrad
+    MFP_GEMM_CASE(kEpiBias)                                    // QKV, heads
+    MFP_GEMM_CASE(kEpiBias | kEpiRelu)                         // FFN 1
+    MFP_GEMM_CASE(kEpiBias | kEpiResidual)                     // attention output / FFN 2, eval
+    MFP_GEMM_CASE(kEpiBias | kEpiResidual | kEpiDropout)       // attention output / FFN 2, training
+    MFP_GEMM_CASE(kEpiResidual | kEpiRowflag)                  // encoder Dense of a numerical field
+    MFP_GEMM_CASE(kEpiReluMask)                                // dgrad through the FFN ReLU (alone or next to a weight gradient)
+    MFP_GEMM_CASE(kEpiResidual)                                // dgrad + the gradient of the skip path (post-LayerNorm block)
+    default:
+      set_error("gemm: epilogue combination 0x%x is not instantiated", epi);
+      return MFP_ERR_UNSUPPORTED;
+  }
+#undef MFP_GEMM_CASE
+}
+
+int launch_gemm(TensorMapCache* cache, const GemmCall& c, int impl, cudaStream_t stream) {
+  MFP_TRY(check_call(c));
   if (impl == 1) {
     if (c.colsum) { set_error("gemm: the SIMT bring-up kernel has no fused column sum"); return MFP_ERR_ARG; }
     int splits = (c.splits < 1 || c.det_ws) ? 1 : c.splits;  // deterministic mode: no atomic accumulation over splits
@@ -806,24 +939,26 @@ int launch_gemm(TensorMapCache* cache, const GemmCall& c, int impl, cudaStream_t
     MFP_CUDA_OK(cudaGetLastError());
     return MFP_OK;
   }
-  const int epi = (c.ep.bias ? kEpiBias : 0) | (c.ep.relu ? kEpiRelu : 0) | (c.ep.residual ? kEpiResidual : 0) | (c.ep.relu_src ? kEpiReluMask : 0) |
-                  (c.ep.drop_enabled ? kEpiDropout : 0) | (c.ep.rowflag ? kEpiRowflag : 0);
-#define MFP_GEMM_CASE(E) \
-  case (E): return (c.N <= 128) ? launch_tcgen05<128, (E)>(cache, c, stream) : launch_tcgen05<256, (E)>(cache, c, stream);
-  switch (epi) {
-    MFP_GEMM_CASE(0)                                           // dgrad / wgrad
-    MFP_GEMM_CASE(kEpiBias)                                    // QKV, heads
-    MFP_GEMM_CASE(kEpiBias | kEpiRelu)                         // FFN 1
-    MFP_GEMM_CASE(kEpiBias | kEpiResidual)                     // attention output / FFN 2, eval
-    MFP_GEMM_CASE(kEpiBias | kEpiResidual | kEpiDropout)       // attention output / FFN 2, training
-    MFP_GEMM_CASE(kEpiResidual | kEpiRowflag)                  // encoder Dense of a numerical field
-    MFP_GEMM_CASE(kEpiReluMask)                                // dgrad through the FFN ReLU
-    MFP_GEMM_CASE(kEpiResidual)                                // dgrad + the gradient of the skip path (post-LayerNorm block)
-    default:
-      set_error("gemm: epilogue combination 0x%x is not instantiated", epi);
-      return MFP_ERR_UNSUPPORTED;
+  return launch_tcgen05_any(cache, &c, 1, epi_bits(c.ep), c.N > 128, stream);
+}
+
+int launch_gemm_group(TensorMapCache* cache, const GemmCall* calls, int n, cudaStream_t stream) {
+  if (n < 1 || n > kMaxGroup) { set_error("gemm group: 1..%d problems", kMaxGroup); return MFP_ERR_ARG; }
+  int epi = 0;
+  bool wide = false;
+  for (int i = 0; i < n; ++i) {
+    MFP_TRY(check_call(calls[i]));
+    const int e = epi_bits(calls[i].ep);
+    // the kernel's epilogue variant is compiled in: problems of one launch may differ only in whether they use the aux operand / bias /
+    // ReLU / dropout / row flags of that variant (all guarded at run time), not in the KIND of aux operand
+    if ((e & kEpiResidual) && (epi & kEpiReluMask) || (e & kEpiReluMask) && (epi & kEpiResidual)) {
+      set_error("gemm group: residual and ReLU-mask epilogues cannot share a launch");
+      return MFP_ERR_ARG;
+    }
+    epi |= e;
+    wide = wide || calls[i].N > 128;
   }
-#undef MFP_GEMM_CASE
+  return launch_tcgen05_any(cache, calls, n, epi, wide, stream);
 }
 
 }  // namespace mfp

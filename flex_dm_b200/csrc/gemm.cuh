@@ -73,6 +73,9 @@ const CUtensorMap* tensor_map_get(TensorMapCache* cache, const float* ptr, int r
 
 // impl: 0 = tcgen05 (TF32, or 3xTF32 when call.a_lo / b_lo are given), 1 = SIMT bring-up kernel.  Returns MFP_OK or an error (message via set_error).
 int launch_gemm(TensorMapCache* cache, const GemmCall& call, int impl, cudaStream_t stream);
+// Up to three INDEPENDENT problems in one tcgen05 launch (a weight gradient next to the input gradient off the same dY, the encoder's
+// weight gradients): their tiles form one tile space, so epilogues overlap the next problem's main loop and launch boundaries disappear.
+int launch_gemm_group(TensorMapCache* cache, const GemmCall* calls, int n, cudaStream_t stream);
 // lo[i] = x[i] - tf32_rne(x[i]) over a [rows, cols] matrix of pitch ld (lo has the same pitch): the compensation operand of the 3xTF32 mode
 int launch_split_tf32_lo(const float* x, int rows, int cols, int ld, float* lo, cudaStream_t stream);
 

@@ -77,10 +77,18 @@ __global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ Schem
     for (int c = lane; c < sc.LW / 4; c += 32) d4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
   }
+  // the element's per-field weights in one go: lane f loads field f's mask byte (independent loads; one per field inside the loop below
+  // put ten dependent L2 latencies on every warp's critical path)
+  bool my_w = false;
+  if (lane < sc.F) {
+    const FieldDev& fl = sc.f[lane];
+    // metrics.py:251-267: mfp mask (unsorted position) x type gate (sorted target) x seq mask
+    my_w = valid && masks.m[lane][t] && (!fl.has_cond || ((fl.cond_mask >> type_true) & 1ull));
+  }
+  const unsigned wbits = __ballot_sync(0xffffffffu, my_w);
   for (int f = 0; f < sc.F; ++f) {
     const FieldDev& fd = sc.f[f];
-    // metrics.py:251-267: mfp mask (unsorted position) x type gate (sorted target) x seq mask
-    const bool w = valid && masks.m[f][t] && (!fd.has_cond || ((fd.cond_mask >> type_true) & 1ull));
+    const bool w = (wbits >> f) & 1u;
     float loss = 0.f, score = 0.f, den = 0.f;
     if (!w) {
       // nothing to add: the row was cleared above
@@ -161,13 +169,30 @@ __global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ Schem
       const float* y = reinterpret_cast<const float*>(targets.cols[f]) + yrow * fd.C;
       const float* x = lrow + fd.logit_off;
       float sq = 0.f, yy = 0.f, xx = 0.f, xy = 0.f;
-      for (int c = lane; c < fd.C; c += 32) {
-        const float d = x[c] - y[c];
-        sq += d * d;
-        yy += y[c] * y[c];
-        xx += x[c] * x[c];
-        xy += x[c] * y[c];
-        if (drow) drow[fd.logit_off + c] = 2.0f * d * inv_batch;
+      // 16-byte accesses (logit_off and C are multiples of 4; rows are 128-byte aligned), four independent load pairs in flight per lane
+      const float4* x4 = reinterpret_cast<const float4*>(x);
+      const float4* y4 = reinterpret_cast<const float4*>(y);
+      float4* d4 = drow ? reinterpret_cast<float4*>(drow + fd.logit_off) : nullptr;
+      const float g2 = 2.0f * inv_batch;
+      for (int c0 = 0; c0 < fd.C / 4; c0 += 128) {
+        float4 xv4[4], yv4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + lane + 32 * u;
+          xv4[u] = c < fd.C / 4 ? x4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+          yv4[u] = c < fd.C / 4 ? y4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + lane + 32 * u;
+          const float4 a = xv4[u], b = yv4[u];
+          const float4 d = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+          sq += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+          yy += b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+          xx += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+          xy += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+          if (d4 && c < fd.C / 4) d4[c] = make_float4(g2 * d.x, g2 * d.y, g2 * d.z, g2 * d.w);
+        }
       }
       sq = warp_sum(sq); yy = warp_sum(yy); xx = warp_sum(xx); xy = warp_sum(xy);
       loss = sq;

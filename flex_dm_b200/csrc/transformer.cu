@@ -31,8 +31,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 
 // dx = dres + rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)),  dxhat = dy * gamma
 // dgamma += sum_t dy * xhat, dbeta += sum_t dy  (per-CTA register/shared reduction, one atomic per column per CTA)
-// One warp per row; lane l owns the eight consecutive columns 8 l .. 8 l + 7 (32 contiguous bytes: one Philox block of the dropout
-// contract, gemm.cuh).
+// One warp per row; lane l owns columns [4 l, 4 l + 4) and [128 + 4 l, ...): every warp-wide 16-byte access covers 512 contiguous bytes
+// (eight consecutive columns per lane -- one Philox block of the dropout contract -- measured 8 % slower: half-used sectors per access).
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ dres, int T, float* __restrict__ dx,
@@ -43,13 +43,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   pdl_wait();
   __shared__ float red[2][8][kD];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * lane), gb = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * lane + 1);
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + lane), gb = __ldg(reinterpret_cast<const float4*>(gamma) + 32 + lane);
   float dg[8] = {}, db[8] = {};
   for (int t = blockIdx.x * 8 + warp; t < T; t += gridDim.x * 8) {
     const float mu = mean[t], rs = rstd[t];
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)t * kD);
     const float4* dr = reinterpret_cast<const float4*>(dy + (size_t)t * kD);
-    const float4 xa = xr[2 * lane], xb = xr[2 * lane + 1], da = dr[2 * lane], dbv = dr[2 * lane + 1];
+    const float4 xa = xr[lane], xb = xr[32 + lane], da = dr[lane], dbv = dr[32 + lane];
     const float xh[8] = {(xa.x - mu) * rs, (xa.y - mu) * rs, (xa.z - mu) * rs, (xa.w - mu) * rs, (xb.x - mu) * rs, (xb.y - mu) * rs, (xb.z - mu) * rs, (xb.w - mu) * rs};
     const float dyv[8] = {da.x, da.y, da.z, da.w, dbv.x, dbv.y, dbv.z, dbv.w};
     const float g[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
@@ -69,33 +69,36 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     for (int i = 0; i < 8; ++i) o[i] = rs * (dxh[i] - s1 - xh[i] * s2);
     if (dres) {
       const float4* rr = reinterpret_cast<const float4*>(dres + (size_t)t * kD);
-      const float4 ra = rr[2 * lane], rb = rr[2 * lane + 1];
+      const float4 ra = rr[lane], rb = rr[32 + lane];
       o[0] += ra.x; o[1] += ra.y; o[2] += ra.z; o[3] += ra.w; o[4] += rb.x; o[5] += rb.y; o[6] += rb.z; o[7] += rb.w;
     }
     float4* out = reinterpret_cast<float4*>(dx + (size_t)t * kD);
-    out[2 * lane] = make_float4(o[0], o[1], o[2], o[3]);
-    out[2 * lane + 1] = make_float4(o[4], o[5], o[6], o[7]);
+    out[lane] = make_float4(o[0], o[1], o[2], o[3]);
+    out[32 + lane] = make_float4(o[4], o[5], o[6], o[7]);
     // the gradient entering the next (earlier) sub-layer's branch is dx under that branch's dropout mask: written here so
     // that no separate dropout-backward pass re-reads dx
     if (dx_drop) {
       float va[4] = {o[0], o[1], o[2], o[3]}, vb[4] = {o[4], o[5], o[6], o[7]};
-      dropout8(va, vb, ((uint32_t)t + drop_row0) * kD + 8u * lane, drop_rate, drop_seed, drop_step, drop_site);
+      dropout4(va, ((uint32_t)t + drop_row0) * kD + 4u * lane, drop_rate, drop_seed, drop_step, drop_site);
+      dropout4(vb, ((uint32_t)t + drop_row0) * kD + 128u + 4u * lane, drop_rate, drop_seed, drop_step, drop_site);
       float4* po = reinterpret_cast<float4*>(dx_drop + (size_t)t * kD);
-      po[2 * lane] = make_float4(va[0], va[1], va[2], va[3]);
-      po[2 * lane + 1] = make_float4(vb[0], vb[1], vb[2], vb[3]);
+      po[lane] = make_float4(va[0], va[1], va[2], va[3]);
+      po[32 + lane] = make_float4(vb[0], vb[1], vb[2], vb[3]);
     }
     // encoder: copies of dx with the rows of special-token elements zeroed, one per numerical field (B operand of its Dense wgrad)
     for (int s = 0; s < n_masked; ++s) {
       const bool keep = rowflags[(size_t)s * T + t] == 0;
       float4* mo = reinterpret_cast<float4*>(dx_masked + ((size_t)s * T + t) * kD);
-      mo[2 * lane] = keep ? make_float4(o[0], o[1], o[2], o[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-      mo[2 * lane + 1] = keep ? make_float4(o[4], o[5], o[6], o[7]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      mo[lane] = keep ? make_float4(o[0], o[1], o[2], o[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      mo[32 + lane] = keep ? make_float4(o[4], o[5], o[6], o[7]) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    red[0][warp][8 * lane + i] = dg[i];
-    red[1][warp][8 * lane + i] = db[i];
+  for (int i = 0; i < 4; ++i) {
+    red[0][warp][4 * lane + i] = dg[i];
+    red[0][warp][128 + 4 * lane + i] = dg[4 + i];
+    red[1][warp][4 * lane + i] = db[i];
+    red[1][warp][128 + 4 * lane + i] = db[4 + i];
   }
   __syncthreads();
   const int c = threadIdx.x;
