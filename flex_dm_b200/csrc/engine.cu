@@ -713,7 +713,11 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
       h->launches += 3;
       continue;
     }
-    MFP_TRY(launch_layernorm_fwd(xi, P + b.g1, P + b.be1, T, ln1, stats, stats + T, st));
+    // LayerNorms of the pre-LN block (transformer.py:216,222) ride the epilogue of the GEMM that produces their input rows (N = 256: an
+    // output tile holds whole rows): LN2 in the attention output projection, the next block's LN1 in FFN 2.  Only the first block's LN1
+    // (input = the encoder's sum of embeddings) and the SIMT bring-up path run the standalone kernel.
+    const bool fuse_ln = h->gemm_impl != 1;
+    if (i == 0 || !fuse_ln) { MFP_TRY(launch_layernorm_fwd(xi, P + b.g1, P + b.be1, T, ln1, stats, stats + T, st)); h->launches++; }
     GemmEpilogue e1 = make_epilogue(qkv, 3 * D);
     e1.bias = P + b.bqkv;
     MFP_TRY(gemm(h, ln1, 0, D, P + b.wqkv, 1, 3 * D, T, 3 * D, D, e1, 1, st));
@@ -726,8 +730,9 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
     e2.bias = P + b.bo;
     e2.residual = xi; e2.ldr = D;
     if (drop) { e2.drop_enabled = 1; e2.drop_rate = h->cfg.dropout; e2.drop_seed = seed; e2.drop_step = step; e2.drop_site = kSiteDropout + 2 * i; e2.drop_row0 = row0; }
+    if (fuse_ln) { e2.ln_out = ln2; e2.ln_ldo = D; e2.ln_gamma = P + b.g2; e2.ln_beta = P + b.be2; e2.ln_mean = stats + 2 * T; e2.ln_rstd = stats + 3 * T; }
     MFP_TRY(gemm(h, attn, 0, D, P + b.wo, 1, D, T, D, D, e2, 1, st));
-    MFP_TRY(launch_layernorm_fwd(xmid, P + b.g2, P + b.be2, T, ln2, stats + 2 * T, stats + 3 * T, st));
+    if (!fuse_ln) { MFP_TRY(launch_layernorm_fwd(xmid, P + b.g2, P + b.be2, T, ln2, stats + 2 * T, stats + 3 * T, st)); h->launches++; }
     GemmEpilogue e3 = make_epilogue(hid, kF);
     e3.bias = P + b.b1;
     e3.relu = 1;
@@ -736,8 +741,13 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
     e4.bias = P + b.b2;
     e4.residual = xmid; e4.ldr = D;
     if (drop) { e4.drop_enabled = 1; e4.drop_rate = h->cfg.dropout; e4.drop_seed = seed; e4.drop_step = step; e4.drop_site = kSiteDropout + 2 * i + 1; e4.drop_row0 = row0; }
+    if (fuse_ln && i + 1 < L) {  // the next block's LN1
+      const BlockLayout& nb = h->blocks[i + 1];
+      float* nstats = wsp<float>(h, h->off.stats) + (size_t)(i + 1) * 4 * T;
+      e4.ln_out = wsp<float>(h, h->off.ln1) + (i + 1) * TD; e4.ln_ldo = D; e4.ln_gamma = P + nb.g1; e4.ln_beta = P + nb.be1; e4.ln_mean = nstats; e4.ln_rstd = nstats + T;
+    }
     MFP_TRY(gemm(h, hid, 0, kF, P + b.w2, 1, D, T, D, kF, e4, 1, st));
-    h->launches += 3;
+    h->launches += 1;  // attention
   }
   // ---- decoder heads (decoder.py:72-111)
   float* logits = wsp<float>(h, h->off.logits);

@@ -91,7 +91,7 @@ struct GemmSmem {
 
 // Epilogue variants are compiled in (EPI bit mask), so each instantiation carries only the code it runs: the epilogue
 // warps are issue-bound (one warp per scheduler), every dead branch in their loop costs throughput.
-enum : int { kEpiBias = 1, kEpiRelu = 2, kEpiResidual = 4, kEpiReluMask = 8, kEpiDropout = 16, kEpiRowflag = 32 };
+enum : int { kEpiBias = 1, kEpiRelu = 2, kEpiResidual = 4, kEpiReluMask = 8, kEpiDropout = 16, kEpiRowflag = 32, kEpiLayerNorm = 64 };
 
 // One GEMM of a launch.  A launch carries up to kMaxGroup INDEPENDENT problems whose tiles form one tile space (problem 0's tiles first):
 // a weight gradient and the input gradient that hangs off the same dY run as one launch -- every CTA takes its one long split-K tile of
@@ -443,12 +443,15 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
         if (lane == 0) mbar_arrive(tempty_bar(as));
       };
       if (h >= nchunks) release_acc();  // a one-chunk tail tile: the odd warp has nothing to read
+      float ln_s1 = 0.f, ln_s2 = 0.f;
       for (int c = h; c < nchunks; c += 2) {
         const int col0 = n0 + c * 32;
         uint32_t rr[32];
         if (trace) { const long long t0 = clock64(); tmem_ld32(tacc + (uint32_t)(c * 32), rr); w2 += (unsigned long long)(clock64() - t0); }
         else tmem_ld32(tacc + (uint32_t)(c * 32), rr);
-        if (c + 2 >= nchunks) release_acc();
+        if constexpr (!(EPI & kEpiLayerNorm)) {
+          if (c + 2 >= nchunks) release_acc();
+        }
         if (lane == 0) {  // the staging chunk has been read out by an earlier tile's reduce-add (a no-op when none is pending)
           if (trace) { const long long t0 = clock64(); tma_wait_group_read<0>(); w1 += (unsigned long long)(clock64() - t0); }
           else tma_wait_group_read<0>();
@@ -511,7 +514,13 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
           }
           if constexpr (aux_mode == 1) { v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; }
           *reinterpret_cast<float4*>(own_row + ((j ^ sw) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+          if constexpr (EPI & kEpiLayerNorm) {  // row statistics + the finished values back into the accumulator for the second pass
+            ln_s1 += (v[0] + v[1]) + (v[2] + v[3]);
+            ln_s2 += (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
+            rr[4 * j] = __float_as_uint(v[0]); rr[4 * j + 1] = __float_as_uint(v[1]); rr[4 * j + 2] = __float_as_uint(v[2]); rr[4 * j + 3] = __float_as_uint(v[3]);
+          }
         }
+        if constexpr (EPI & kEpiLayerNorm) tmem_st32(tacc + (uint32_t)(c * 32), rr);
         if (ep.atomic) {
           fence_proxy_async_smem();
           __syncwarp();
@@ -528,6 +537,43 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
             const float4 o = *reinterpret_cast<const float4*>(epi_ptr + (4 * i + tr) * 128 + ((ts ^ ((4 * i + tr) & 7)) << 4));
             if (row0 + 4 * i + tr < M && gcol < N) *reinterpret_cast<float4*>(orow + (size_t)(4 * i) * ep.ldo) = o;
           }
+        }
+      }
+      if constexpr (EPI & kEpiLayerNorm) {
+        // ---- fused LayerNorm of the rows just produced (N == BN: this tile holds whole rows; the two warps of a lane quarter hold the even
+        // and the odd chunks of the same 32 rows).  Pass 1 above left the values in the accumulator and per-lane partial sums; the partner
+        // warp's come through the staging chunks; pass 2 re-reads the values and writes the normalised rows.
+        tmem_st_wait();
+        __syncwarp();
+        *reinterpret_cast<float2*>(epi_ptr + lane * 8) = make_float2(ln_s1, ln_s2);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // both warps of the quarter have published their sums
+        const float2 other = *reinterpret_cast<const float2*>(base_ptr + L::kEpiOff + (ew ^ 4) * kChunkBytes + lane * 8);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // ... and read the partner's, before the staging chunks are reused
+        const float mean = (ln_s1 + other.x) * (1.0f / BN);
+        const float var = fmaxf((ln_s2 + other.y) * (1.0f / BN) - mean * mean, 0.0f);
+        const float rstd = rsqrtf(var + kLnEps);
+        if (h == 0 && row < M) { ep.ln_mean[row] = mean; ep.ln_rstd[row] = rstd; }
+        for (int c = h; c < nchunks; c += 2) {
+          const int col0 = n0 + c * 32;
+          uint32_t rr[32];
+          tmem_ld32(tacc + (uint32_t)(c * 32), rr);
+          if (c + 2 >= nchunks) release_acc();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + col0) + j), b4 = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + col0) + j);
+            *reinterpret_cast<float4*>(own_row + ((j ^ sw) << 4)) =
+                make_float4((__uint_as_float(rr[4 * j]) - mean) * rstd * g4.x + b4.x, (__uint_as_float(rr[4 * j + 1]) - mean) * rstd * g4.y + b4.y,
+                            (__uint_as_float(rr[4 * j + 2]) - mean) * rstd * g4.z + b4.z, (__uint_as_float(rr[4 * j + 3]) - mean) * rstd * g4.w + b4.w);
+          }
+          __syncwarp();
+          const int gcol = col0 + ts * 4;
+          float* orow = ep.ln_out + (size_t)(row0 + tr) * ep.ln_ldo + gcol;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 o = *reinterpret_cast<const float4*>(epi_ptr + (4 * i + tr) * 128 + ((ts ^ ((4 * i + tr) & 7)) << 4));
+            if (row0 + 4 * i + tr < M) *reinterpret_cast<float4*>(orow + (size_t)(4 * i) * ep.ln_ldo) = o;
+          }
+          __syncwarp();
         }
       }
       as ^= 1;
@@ -762,7 +808,7 @@ static int num_sms() {
 
 static int epi_bits(const GemmEpilogue& ep) {
   return (ep.bias ? kEpiBias : 0) | (ep.relu ? kEpiRelu : 0) | (ep.residual ? kEpiResidual : 0) | (ep.relu_src ? kEpiReluMask : 0) |
-         (ep.drop_enabled ? kEpiDropout : 0) | (ep.rowflag ? kEpiRowflag : 0);
+         (ep.drop_enabled ? kEpiDropout : 0) | (ep.rowflag ? kEpiRowflag : 0) | (ep.ln_out ? kEpiLayerNorm : 0);
 }
 
 // What has to follow a problem's GEMM in deterministic mode: the fixed-order sum of its split-K / column-sum partials.
@@ -777,6 +823,10 @@ template <int BN>
 static int prepare_problem(TensorMapCache* cache, const GemmCall& c, int epi_launch, GemmProblem* P, DetReduce* red) {
   if (c.ep.residual && c.ep.relu_src) { set_error("gemm: residual and relu_src cannot be combined"); return MFP_ERR_ARG; }
   if (c.colsum && !c.b.mn_major) { set_error("gemm: the fused column sum needs an MN-major B operand"); return MFP_ERR_ARG; }
+  if (c.ep.ln_out && (c.N != BN || c.splits > 1 || !c.ep.ln_gamma || !c.ep.ln_beta || !c.ep.ln_mean || !c.ep.ln_rstd || (c.ep.ln_ldo % 4))) {
+    set_error("gemm: the fused LayerNorm needs N == %d (whole rows in one tile), no split-K, and gamma / beta / mean / rstd", BN);
+    return MFP_ERR_ARG;
+  }
   // MN-major operand [K][MN] with pitch ld: 2-D boxes of 32 columns x kBK rows, or -- when MN is whole 32-column blocks -- a 3-D
   // view [MN / 32][K][32] whose box (32, kBK, tile / 32) brings a whole stage in one instruction (mode 2 in the kernel)
   auto mn_map = [&](const GemmOperand& o, int mn, int tile_mn, int* mode) -> const CUtensorMap* {
@@ -915,6 +965,8 @@ static int launch_tcgen05_any(TensorMapCache* cache, const GemmCall* calls, int 
     MFP_GEMM_CASE(kEpiBias | kEpiRelu)                         // FFN 1
     MFP_GEMM_CASE(kEpiBias | kEpiResidual)                     // attention output / FFN 2, eval
     MFP_GEMM_CASE(kEpiBias | kEpiResidual | kEpiDropout)       // attention output / FFN 2, training
+    MFP_GEMM_CASE(kEpiBias | kEpiResidual | kEpiLayerNorm)                 // ... with the following LayerNorm fused, eval
+    MFP_GEMM_CASE(kEpiBias | kEpiResidual | kEpiDropout | kEpiLayerNorm)   // ... training
     MFP_GEMM_CASE(kEpiResidual | kEpiRowflag)                  // encoder Dense of a numerical field
     MFP_GEMM_CASE(kEpiReluMask)                                // dgrad through the FFN ReLU (alone or next to a weight gradient)
     MFP_GEMM_CASE(kEpiResidual)                                // dgrad + the gradient of the skip path (post-LayerNorm block)

@@ -35,6 +35,15 @@ struct GemmEpilogue {
   float drop_rate;
   uint32_t drop_seed, drop_step, drop_site;
   uint32_t drop_row0;  // global index of row 0 (data-parallel shards): dropout counters are formed from global rows
+  // Fused LayerNorm of the output rows (N == 256: one tile holds whole rows): besides out = v, the epilogue writes
+  // ln_out = (v - mean) * rstd * ln_gamma + ln_beta and the row statistics the LayerNorm backward needs (eps = 1e-3, biased variance:
+  // transformer.py:216,222 via Keras LayerNormalization).  ln_out == nullptr: off.
+  float* ln_out;
+  int ln_ldo;
+  const float* ln_gamma;
+  const float* ln_beta;
+  float* ln_mean;
+  float* ln_rstd;
 };
 
 inline GemmEpilogue make_epilogue(float* out, int ldo) {

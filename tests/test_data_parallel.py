@@ -70,9 +70,17 @@ def _worker(rank, world, port, out):
         inputs = {k: torch.as_tensor(v) for k, v in batch.items()}
         targets, modified, masks = O.preprocess_for_train(inputs, icols, torch.as_tensor(tasks), O.PhiloxDraws(3, 0))
         sl = lambda d: {k: (v[lo:hi] if torch.is_tensor(v) and v.shape[:1] == (B,) else v) for k, v in d.items()}
+        # what a rank really does (MFP.enable_data_parallel -> mfp_set_doc_offset): it corrupts ITS documents with Philox counters formed
+        # from their global indices -- and gets exactly the global batch's draws for them
+        shard_inputs = {k: torch.as_tensor(v) for k, v in shard.items()}
+        t_l, mod_l, masks_l = O.preprocess_for_train(shard_inputs, icols, torch.as_tensor(tasks[lo:hi]), O.PhiloxDraws(3, 0, doc_offset=lo))
+        for k in icols:
+            if icols[k]["is_sequence"]:
+                assert torch.equal(mod_l[k], sl(modified)[k]) and torch.equal(masks_l[k], sl(masks)[k]), k
+        assert np.array_equal(O.PhiloxDraws(3, 0, doc_offset=lo).tasks(hi - lo, [0, 1, 3]), O.PhiloxDraws(3, 0).tasks(B, [0, 1, 3])[lo:hi])
         p = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in params.items())
-        out_l = O.model_forward(p, sl(modified), icols, L)
-        total, losses, scores, _ = O.loss_layer(sl(targets), out_l, sl(masks), cols)
+        out_l = O.model_forward(p, mod_l, icols, L)
+        total, losses, scores, _ = O.loss_layer(t_l, out_l, masks_l, cols)
         (total * (hi - lo) / B).backward()
         g = _flat(OrderedDict((k, v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in p.items()))
         keys = list(O.get_valid_input_columns(cols).keys())
