@@ -716,7 +716,8 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
     // LayerNorms of the pre-LN block (transformer.py:216,222) ride the epilogue of the GEMM that produces their input rows (N = 256: an
     // output tile holds whole rows): LN2 in the attention output projection, the next block's LN1 in FFN 2.  Only the first block's LN1
     // (input = the encoder's sum of embeddings) and the SIMT bring-up path run the standalone kernel.
-    const bool fuse_ln = h->gemm_impl != 1;
+    static const bool fuse_ln_env = [] { const char* e = getenv("FLEXDM_FUSE_LN"); return !(e && e[0] == '0'); }();  // A/B switch
+    const bool fuse_ln = h->gemm_impl != 1 && fuse_ln_env;
     if (i == 0 || !fuse_ln) { MFP_TRY(launch_layernorm_fwd(xi, P + b.g1, P + b.be1, T, ln1, stats, stats + T, st)); h->launches++; }
     GemmEpilogue e1 = make_epilogue(qkv, 3 * D);
     e1.bias = P + b.bqkv;

@@ -31,9 +31,10 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 
 // dx = dres + rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)),  dxhat = dy * gamma
 // dgamma += sum_t dy * xhat, dbeta += sum_t dy  (per-CTA register/shared reduction, one atomic per column per CTA)
+// Four CTAs per SM (64 registers: at 80 the kernel lost a quarter of its loads in flight and a quarter of its bandwidth).
 // One warp per row; lane l owns columns [4 l, 4 l + 4) and [128 + 4 l, ...): every warp-wide 16-byte access covers 512 contiguous bytes
 // (eight consecutive columns per lane -- one Philox block of the dropout contract -- measured 8 % slower: half-used sectors per access).
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256, 4) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ dres, int T, float* __restrict__ dx,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
