@@ -23,7 +23,7 @@ __device__ __forceinline__ float2 box_muller(uint32_t xa, uint32_t xb) {
 }
 
 // mode 0: train (tasks != null), mode 1: test (test_masks given)
-__global__ void __launch_bounds__(256) mask_corrupt_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs in,
+__global__ void __launch_bounds__(256, 5) mask_corrupt_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs in,
                                                            const int* __restrict__ tasks, const __grid_constant__ MaskPtrs test_masks, int mode, int B,
                                                            int S, uint32_t seed, uint32_t step, uint32_t doc0, const __grid_constant__ ModifiedPtrs out,
                                                            unsigned char* __restrict__ flags) {
