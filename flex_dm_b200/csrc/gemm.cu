@@ -991,7 +991,12 @@ int launch_gemm(TensorMapCache* cache, const GemmCall& c, int impl, cudaStream_t
     MFP_CUDA_OK(cudaGetLastError());
     return MFP_OK;
   }
-  return launch_tcgen05_any(cache, &c, 1, epi_bits(c.ep), c.N > 128, stream);
+  // Tile width: 256 columns, except for narrow outputs and for small problems that would leave most SMs without a tile (a 64-document
+  // shard has 64 row tiles: at N = 256 that is 64 CTAs of 148) -- those take 128-column tiles, twice as many CTAs.
+  static const int small_tiles = [] { const char* e = getenv("FLEXDM_SMALL_TILES"); return e ? atoi(e) : 100; }();
+  const int tiles256 = ((c.M + kBM - 1) / kBM) * ((c.N + 255) / 256) * (c.splits < 1 ? 1 : c.splits);
+  const bool wide = c.N > 128 && !(tiles256 < small_tiles && c.N % 128 == 0 && !c.ep.ln_out);
+  return launch_tcgen05_any(cache, &c, 1, epi_bits(c.ep), wide, stream);
 }
 
 int launch_gemm_group(TensorMapCache* cache, const GemmCall* calls, int n, cudaStream_t stream) {
