@@ -386,16 +386,8 @@ static int gemm_group(mfp_engine* h, const GemmArgs* g, int n, cudaStream_t st) 
   return launch_gemm_group(h->maps, calls, n, st);
 }
 
-// split-K factor of a weight-gradient GEMM (K = tokens): enough CTAs for ~2 per SM
-// The GEMM is persistent (one CTA per SM, 128 x 256 tiles): pick the largest split count that still fits one wave.
-static int wgrad_splits(int M, int N, int K) {
-  const int bn = (N <= 128) ? 128 : 256;
-  const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
-  int s = 148 / tiles;
-  const int kb = (K + 31) / 32;
-  if (s > kb / 4) s = kb / 4;
-  return s < 1 ? 1 : s;
-}
+// split-K factor of a weight-gradient GEMM (K = tokens): one wave of the persistent GEMM's tiles (gemm.cu knows the tile shape)
+static int wgrad_splits(int M, int N, int K) { return gemm_wgrad_splits(M, N, K); }
 
 }  // namespace mfp
 

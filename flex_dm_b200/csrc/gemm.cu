@@ -76,12 +76,16 @@ struct GemmTiles {
 // AUX: the epilogue stages a residual / ReLU-mask operand (one more 4 KB chunk per epilogue warp).  Without it the 32 KB saved
 // buy a fourth operand stage at BN = 256: the ring is latency-bound (a slot is refilled only after its MMAs retire), so the
 // bytes in flight set the fill rate.
-template <int BN, bool AUX>
+// CG = 2: a CTA PAIR works on a 256 x BN tile (tcgen05.mma.cta_group::2): each CTA stages its own 128 rows of A and only its half of
+// the B tile (BN / 2 rows), so a k-block costs 32 KB of L2 -> shared traffic per SM instead of 48 KB, and the same shared memory holds
+// six stages instead of four.
+template <int BN, int CG>
 struct GemmSmem {
-  static constexpr int kStages = (BN <= 128) ? 6 : 4;
+  static constexpr int kStages = (BN <= 128 || CG == 2) ? 6 : 4;
   static constexpr int kEpiChunks = 1;                           // per epilogue warp: one 4 KB staging chunk (transposes aux in, results out)
   static constexpr int kABytes = kBM * kBK * 4;
-  static constexpr int kBBytes = BN * kBK * 4;
+  static constexpr int kBRows = BN / CG;                          // rows of the B tile this CTA stages
+  static constexpr int kBBytes = kBRows * kBK * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiOff = kStages * kStageBytes;          // 8 warps x {out, aux} chunks
   static constexpr int kBarOff = kEpiOff + 8 * kEpiChunks * kChunkBytes;
@@ -106,17 +110,25 @@ struct GemmProblem {
   float* colsum;
   int tile0;     // first index of this problem's tiles in the launch's tile space
   int aux_kind;  // 0, or the kernel's aux_mode (1 residual, 2 ReLU mask) when this problem uses the aux operand
+  int a_hint, b_hint;  // L2 eviction priority of the operand loads (tc.cuh l2_policy): 1 = another tile of this launch reads it again, 2 = last use
 };
 struct GemmGroup {
   int n, total_tiles, any_colsum, pad;
   GemmProblem p[kMaxGroup];
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned long long* __restrict__ trace) {
   constexpr int aux_mode = (EPI & kEpiResidual) ? 1 : ((EPI & kEpiReluMask) ? 2 : 0);
-  using L = GemmSmem<BN, aux_mode != 0>;
+  using L = GemmSmem<BN, CG>;
+  constexpr int kTileM = kBM * CG;  // rows of a tile of the launch's tile space (one CTA, or a CTA pair)
+  // CTA pair (CG == 2, launched as clusters of two): rank 0 is the leader -- it alone issues the MMAs, and the operand-ring "full"
+  // barriers and the accumulator "empty" barriers that its MMA thread waits on live in ITS shared memory: both CTAs' TMA loads complete
+  // on the leader's full barrier, the peer's epilogue warps arrive remotely on the leader's tempty barrier; tcgen05.commit multicasts
+  // the "slot free" and "accumulator ready" arrivals to both CTAs.
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int unit = (int)blockIdx.x / CG, units = (int)gridDim.x / CG;
   constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -143,12 +155,14 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), 2);                    // the A producer and the B producer each arrive with their own byte count
+      // the A producer and the B producer each arrive with their own byte count.  Pair: the leader's barrier collects both CTAs' loads;
+      // the peer's own full barrier only serves its column-sum warp, which the leader's column-sum warp notifies once the stage has landed
+      mbar_init(full_bar(s), rank == 0 ? 2 : 1);
       mbar_init(empty_bar(s), any_colsum ? 2 : 1);  // MMA commit (+ the column-sum warp, which then attends every tile of the launch)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);
+      mbar_init(tempty_bar(a), 8 * CG);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int i = 0; i < grp.n; ++i) {
@@ -159,11 +173,17 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
     }
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(2 * BN) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 2) {  // both CTAs of the pair, same warp
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(2 * BN) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(2 * BN) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync();  // the peer's barriers exist before anything arrives on them remotely
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_launch_dependents();  // one resident CTA per SM for the whole kernel: the next kernel's CTAs only queue up behind it
@@ -195,7 +215,7 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
       const bool is_a = (warp == 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles; tile += units) {
         const GemmProblem& P = grp.p[problem_of(tile)];
         const GemmTiles tl = P.tl;
         const int a_mn = P.a_mn, b_mn = P.b_mn;
@@ -203,8 +223,10 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
         const int tiles_mn = tl.tiles_m * tl.tiles_n;
         const int lt = tile - P.tile0;
         const int split = lt / tiles_mn, r = lt - split * tiles_mn;
-        const int m0 = (r / tl.tiles_n) * kBM, n0 = (r % tl.tiles_n) * BN;
+        // this CTA's rows of A and its rows of the B tile (pair: the second CTA takes the second half of both)
+        const int m0 = (r / tl.tiles_n) * kTileM + (int)rank * kBM, n0 = (r % tl.tiles_n) * BN + (int)rank * L::kBRows;
         const int kb0 = split * tl.kb_per_split, kb1 = min(num_kb, kb0 + tl.kb_per_split);
+        const uint64_t pol = l2_policy(is_a ? P.a_hint : P.b_hint);
         for (int kbt = kb0; kbt < kb1; ++kbt) {
           const int pass = kbt / kb_single, kb = kbt - pass * kb_single;
           const CUtensorMap* mapA = (pass == 1) ? &P.tmALo : &P.tmA;
@@ -212,25 +234,28 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
           wait_t(empty_bar(stage), phase ^ 1u, w0);
           const uint32_t sa = base + stage * L::kStageBytes;
           const uint32_t sb = sa + L::kABytes;
+          // pair: the leader's producers announce both CTAs' bytes on the leader's barrier; the peer's only load (their bytes may land
+          // before the announcement: the transaction count is signed, and the phase cannot complete before the leader's two arrivals)
+          const uint32_t fbar = (CG == 2) ? mapa_shared(full_bar(stage), 0u) : full_bar(stage);
           if (is_a) {
-            mbar_expect_tx(full_bar(stage), L::kABytes);
+            if (rank == 0) mbar_expect_tx(full_bar(stage), CG * L::kABytes);
             if (a_mn == 0) {
-              tma_load_2d(sa, mapA, kb * kBK, m0, full_bar(stage));
+              tma_ld2<CG>(sa, mapA, kb * kBK, m0, fbar, pol);
             } else if (a_mn == 2) {
-              tma_load_3d(sa, mapA, 0, kb * kBK, m0 >> 5, full_bar(stage));
+              tma_ld3<CG>(sa, mapA, 0, kb * kBK, m0 >> 5, fbar, pol);
             } else {
 #pragma unroll
-              for (int j = 0; j < kBM / 32; ++j) tma_load_2d(sa + j * (kBK * 128), mapA, m0 + 32 * j, kb * kBK, full_bar(stage));
+              for (int j = 0; j < kBM / 32; ++j) tma_ld2<CG>(sa + j * (kBK * 128), mapA, m0 + 32 * j, kb * kBK, fbar, pol);
             }
           } else {
-            mbar_expect_tx(full_bar(stage), L::kBBytes);
+            if (rank == 0) mbar_expect_tx(full_bar(stage), CG * L::kBBytes);
             if (b_mn == 0) {
-              tma_load_2d(sb, mapB, kb * kBK, n0, full_bar(stage));
+              tma_ld2<CG>(sb, mapB, kb * kBK, n0, fbar, pol);
             } else if (b_mn == 2) {
-              tma_load_3d(sb, mapB, 0, kb * kBK, n0 >> 5, full_bar(stage));
+              tma_ld3<CG>(sb, mapB, 0, kb * kBK, n0 >> 5, fbar, pol);
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * (kBK * 128), mapB, n0 + 32 * j, kb * kBK, full_bar(stage));
+              for (int j = 0; j < L::kBRows / 32; ++j) tma_ld2<CG>(sb + j * (kBK * 128), mapB, n0 + 32 * j, kb * kBK, fbar, pol);
             }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -240,7 +265,7 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       // Shared-memory descriptors: built per tile for stage 0 / k-step 0; the address field (bits [0,14), units of 16 B) is all that
       // changes inside a tile, so a stage or k-step is one 64-bit add.  This thread's instruction stream is serial and sits on the
       // critical path (measured: ~1000 cycles per k-block against 512 of tensor time), so nothing is recomputed inside the k loop.
@@ -249,13 +274,13 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
       constexpr uint64_t kStageStep = (uint64_t)(L::kStageBytes >> 4);
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles; tile += units) {
         const GemmProblem& P = grp.p[problem_of(tile)];
         const GemmTiles tl = P.tl;
         const int a_mn = P.a_mn, b_mn = P.b_mn;
         // instruction descriptor: c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13), a_major bit15, b_major bit16, N>>3 [17,23), M>>4 [24,29)
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn ? 1 : 0) << 15) | ((uint32_t)(b_mn ? 1 : 0) << 16) |
-                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
         const uint64_t da0 = a_mn ? make_smem_desc(base, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(base, tune.k_lbo, tune.k_sbo, tune.k_layout);
         const uint64_t db0 = b_mn ? make_smem_desc(base + L::kABytes, tune.mn_lbo, tune.mn_sbo, 1) : make_smem_desc(base + L::kABytes, tune.k_lbo, tune.k_sbo, tune.k_layout);
         const uint64_t a_step = a_mn ? (1024u >> 4) : (32u >> 4), b_step = b_mn ? (1024u >> 4) : (32u >> 4);
@@ -273,14 +298,14 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
           tcgen05_fence_after();
 #pragma unroll
           for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
-            umma_tf32(tacc, da + kk * a_step, db + kk * b_step, idesc, accumulate);
+            umma_tf32_cg<CG>(tacc, da + kk * a_step, db + kk * b_step, idesc, accumulate);
             accumulate = 1u;
           }
-          tcgen05_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+          tcgen05_commit_cg<CG>(empty_bar(stage));  // frees the smem slot (in both CTAs of a pair) once these MMAs retire
           da += kStageStep; db += kStageStep;
           if (++stage == kStages) { stage = 0; phase ^= 1u; da = da0; db = db0; }
         }
-        tcgen05_commit(tfull_bar(as));  // accumulator complete
+        tcgen05_commit_cg<CG>(tfull_bar(as));  // accumulator complete (both CTAs' epilogues)
         as ^= 1;
         if (as == 0) aphase ^= 1u;
       }
@@ -298,7 +323,7 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
       const int chunk0 = lane >> 3, atom = (lane >> 1) & 3, half = lane & 1;
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles; tile += units) {
         const GemmProblem& P = grp.p[problem_of(tile)];
         const GemmTiles tl = P.tl;
         float* colsum = P.colsum;
@@ -312,19 +337,23 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
         const int mt = r / tl.tiles_n;
         const bool active = colsum != nullptr && (share || mt == 0);
         const int k_first = share ? mt * rows_per : 0;
-        const int n0 = (r % tl.tiles_n) * BN;
+        const int n0 = (r % tl.tiles_n) * BN + (int)rank * L::kBRows;  // first column of the B rows this CTA stages
         const int kb0 = split * tl.kb_per_split, kb1 = min(num_kb, kb0 + tl.kb_per_split);
-        float4 acc[BN / 128];
+        constexpr int kColGroups = (L::kBRows + 127) / 128;
+        float4 acc[kColGroups];
 #pragma unroll
-        for (int i = 0; i < BN / 128; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < kColGroups; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
+          if constexpr (CG == 2) {  // the stage has landed in both CTAs: tell the peer's column-sum warp (its own full barrier sees no loads)
+            if (rank == 0 && lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(full_bar(stage), 1u));
+          }
           if (active && kb / kb_single != 1) {  // 3xTF32: pass 1 shows the B tiles a second time (hi from pass 0 + lo from pass 2 = the fp32 sum)
             const uint8_t* cb = base_ptr + stage * L::kStageBytes + L::kABytes + chunk0 * (kBK * 128) + half * 16;
 #pragma unroll 4
             for (int k = k_first; k < k_first + rows_per; ++k) {
 #pragma unroll
-              for (int i = 0; i < BN / 128; ++i) {
+              for (int i = 0; i < kColGroups; ++i) {
                 const float4 v = *reinterpret_cast<const float4*>(cb + i * 4 * (kBK * 128) + k * 128 + ((atom ^ (k & 3)) << 5));
                 acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
               }
@@ -336,15 +365,15 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
         }
         if (colsum != nullptr && tl.det_colsum) {  // slot (split, m-tile): summed in slot order by splitk_reduce_kernel (CTAs without a share store zeros)
 #pragma unroll
-          for (int i = 0; i < BN / 128; ++i) {
+          for (int i = 0; i < kColGroups; ++i) {
             const int col = n0 + (chunk0 + 4 * i) * 32 + atom * 8 + half * 4;
-            if (col < N) *reinterpret_cast<float4*>(colsum + (size_t)(split * tl.tiles_m + mt) * N + col) = acc[i];
+            if (col < N && (chunk0 + 4 * i) * 32 < L::kBRows) *reinterpret_cast<float4*>(colsum + (size_t)(split * tl.tiles_m + mt) * N + col) = acc[i];
           }
         } else if (active) {
 #pragma unroll
-          for (int i = 0; i < BN / 128; ++i) {
+          for (int i = 0; i < kColGroups; ++i) {
             const int col = n0 + (chunk0 + 4 * i) * 32 + atom * 8 + half * 4;
-            if (col < N) {  // N is a multiple of 4
+            if (col < N && (chunk0 + 4 * i) * 32 < L::kBRows) {  // N is a multiple of 4
               atomicAdd(colsum + col, acc[i].x); atomicAdd(colsum + col + 1, acc[i].y);
               atomicAdd(colsum + col + 2, acc[i].z); atomicAdd(colsum + col + 3, acc[i].w);
             }
@@ -383,7 +412,7 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
       const int lt = tile - g.P->tile0;
       g.split = lt / tiles_mn;
       const int r = lt - g.split * tiles_mn;
-      g.m0 = (r / tl.tiles_n) * kBM;
+      g.m0 = (r / tl.tiles_n) * kTileM + (int)rank * kBM;  // this CTA's 128 rows (= its TMEM lanes) of the tile
       g.n0 = (r % tl.tiles_n) * BN;
       g.nchunks = min(BN / 32, (g.P->N - g.n0 + 31) / 32);
       g.use_aux = aux_mode != 0 && g.P->aux_kind != 0 && (aux_mode == 2 || g.split == 0);  // the residual is added by split 0 only
@@ -404,12 +433,12 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
     if constexpr (aux_mode != 0) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) an[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if ((int)blockIdx.x < num_tiles) {
-        const TileGeo g0 = geo_of(blockIdx.x);
+      if (unit < num_tiles) {
+        const TileGeo g0 = geo_of(unit);
         if (g0.use_aux && h < g0.nchunks) fetch_aux(g0, h);
       }
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = unit; tile < num_tiles; tile += units) {
       const TileGeo g = geo_of(tile);
       const GemmEpilogue& ep = g.P->ep;
       const GemmTiles& tl = g.P->tl;
@@ -440,7 +469,10 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
       auto release_acc = [&]() {  // this warp has its last chunk of the accumulator in registers
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster_relaxed(mapa_shared(tempty_bar(as), 0u));  // the leader's MMA thread waits for both CTAs' epilogues
+          else mbar_arrive(tempty_bar(as));
+        }
       };
       if (h >= nchunks) release_acc();  // a one-chunk tail tile: the odd warp has nothing to read
       float ln_s1 = 0.f, ln_s2 = 0.f;
@@ -468,7 +500,7 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
           if (c + 2 < nchunks) {
             if (use_aux) fetch_aux(g, c + 2);
           } else {
-            const int nt = tile + (int)gridDim.x;
+            const int nt = tile + units;
             if (nt < num_tiles) {
               const TileGeo gn = geo_of(nt);
               if (gn.use_aux && h < gn.nchunks) fetch_aux(gn, h);
@@ -587,8 +619,10 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
   }
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync();  // neither CTA leaves (or frees its TMEM) while the pair's MMAs / remote arrivals may still touch it
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+    if constexpr (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
   }
 }
 
@@ -819,8 +853,10 @@ struct DetReduce {
 };
 
 // Tensor maps, tiling and epilogue of one problem of a launch (tile width BN is the launch's).
-template <int BN>
+template <int BN, int CG>
 static int prepare_problem(TensorMapCache* cache, const GemmCall& c, int epi_launch, GemmProblem* P, DetReduce* red) {
+  constexpr int kBRows = BN / CG;     // rows of the B tile one CTA stages (a CTA pair splits the tile's columns between its two CTAs)
+  constexpr int kTileM = kBM * CG;    // rows of a tile of the tile space
   if (c.ep.residual && c.ep.relu_src) { set_error("gemm: residual and relu_src cannot be combined"); return MFP_ERR_ARG; }
   if (c.colsum && !c.b.mn_major) { set_error("gemm: the fused column sum needs an MN-major B operand"); return MFP_ERR_ARG; }
   if (c.ep.ln_out && (c.N != BN || c.splits > 1 || !c.ep.ln_gamma || !c.ep.ln_beta || !c.ep.ln_mean || !c.ep.ln_rstd || (c.ep.ln_ldo % 4))) {
@@ -841,7 +877,7 @@ static int prepare_problem(TensorMapCache* cache, const GemmCall& c, int epi_lau
   };
   int a_mode = 0, b_mode = 0;
   const CUtensorMap* ma = c.a.mn_major ? mn_map(c.a, c.M, kBM, &a_mode) : cache->get(c.a.ptr, c.K, c.M, c.a.ld, kBK, kBM, kMapOperandK);
-  const CUtensorMap* mb = c.b.mn_major ? mn_map(c.b, c.N, BN, &b_mode) : cache->get(c.b.ptr, c.K, c.N, c.b.ld, kBK, BN, kMapOperandK);
+  const CUtensorMap* mb = c.b.mn_major ? mn_map(c.b, c.N, kBRows, &b_mode) : cache->get(c.b.ptr, c.K, c.N, c.b.ld, kBK, kBRows, kMapOperandK);
   const CUtensorMap* mo = cache->get(c.ep.out, c.N, c.M, c.ep.ldo, 32, 32, kMapEpilogue);  // split-K reduce-add target
   // 3xTF32: the low parts x - tf32(x) of both operands, same geometry (pitch = the operand's own)
   const CUtensorMap *mal = ma, *mbl = mb;
@@ -850,7 +886,7 @@ static int prepare_problem(TensorMapCache* cache, const GemmCall& c, int epi_lau
     alo.ptr = c.a_lo; blo.ptr = c.b_lo;
     int unused_mode = 0;
     mal = c.a.mn_major ? mn_map(alo, c.M, kBM, &unused_mode) : cache->get(alo.ptr, c.K, c.M, alo.ld, kBK, kBM, kMapOperandK);
-    mbl = c.b.mn_major ? mn_map(blo, c.N, BN, &unused_mode) : cache->get(blo.ptr, c.K, c.N, blo.ld, kBK, BN, kMapOperandK);
+    mbl = c.b.mn_major ? mn_map(blo, c.N, kBRows, &unused_mode) : cache->get(blo.ptr, c.K, c.N, blo.ld, kBK, kBRows, kMapOperandK);
   }
   if (!ma || !mb || !mo || !mal || !mbl) return MFP_ERR_CUDA;
   GemmTiles tl;
@@ -860,7 +896,7 @@ static int prepare_problem(TensorMapCache* cache, const GemmCall& c, int epi_lau
   if (splits > num_kb) splits = num_kb;
   tl.kb_per_split = (num_kb + splits - 1) / splits;
   tl.splits = (num_kb + tl.kb_per_split - 1) / tl.kb_per_split;  // no empty split
-  tl.tiles_m = (c.M + kBM - 1) / kBM;
+  tl.tiles_m = (c.M + kTileM - 1) / kTileM;
   tl.tiles_n = (c.N + BN - 1) / BN;
   GemmEpilogue ep = c.ep;
   tl.slab_rows = 0;
@@ -870,7 +906,7 @@ static int prepare_problem(TensorMapCache* cache, const GemmCall& c, int epi_lau
   red->split = det && tl.splits > 1;
   red->col = nullptr;
   if (red->split || (det && c.colsum)) {
-    tl.slab_rows = red->split ? tl.tiles_m * kBM : 0;
+    tl.slab_rows = red->split ? tl.tiles_m * kTileM : 0;
     const size_t part_floats = red->split ? (size_t)tl.splits * tl.slab_rows * c.N : 0;
     const size_t col_floats = c.colsum ? (size_t)tl.splits * tl.tiles_m * c.N : 0;
     if (part_floats + col_floats > c.det_ws_floats) { set_error("gemm: deterministic scratch too small (%zu > %zu floats)", part_floats + col_floats, c.det_ws_floats); return MFP_ERR_ARG; }
@@ -894,14 +930,14 @@ static int prepare_problem(TensorMapCache* cache, const GemmCall& c, int epi_lau
   return MFP_OK;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 static int launch_tcgen05(TensorMapCache* cache, const GemmCall* calls, int n, cudaStream_t stream) {
-  using L = GemmSmem<BN, (EPI & (kEpiResidual | kEpiReluMask)) != 0>;
+  using L = GemmSmem<BN, CG>;
   static_assert(L::kTotal <= 227 * 1024, "GEMM shared memory exceeds the 227 KB per-CTA limit");
   static_assert(sizeof(GemmGroup) <= 4000, "kernel parameters must stay under 4 KB");
   static bool attr_set = false;
   if (!attr_set) {
-    MFP_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tcgen05<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    MFP_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_tcgen05<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
   cache->trim();
@@ -913,18 +949,27 @@ static int launch_tcgen05(TensorMapCache* cache, const GemmCall* calls, int n, c
   grp.n = n;
   int tiles = 0;
   for (int i = 0; i < n; ++i) {
-    MFP_TRY(prepare_problem<BN>(cache, calls[i], EPI, &grp.p[i], &red[i]));
+    MFP_TRY((prepare_problem<BN, CG>(cache, calls[i], EPI, &grp.p[i], &red[i])));
     grp.p[i].tile0 = tiles;
     tiles += grp.p[i].tl.tiles_m * grp.p[i].tl.tiles_n * grp.p[i].tl.splits;
     if (grp.p[i].colsum) grp.any_colsum = 1;
   }
+  // A weight gradient next to the input gradient off the same dY: dY is read twice (as the MN-major B operand of the first, as the K-major
+  // A operand of the second), and the FFN's hidden activation as well (A operand of dW2, ReLU mask of the input gradient).  The first
+  // reads ask L2 to keep the lines, the last ones to drop them first (FLEXDM_L2_HINTS=0: off).
+  static const bool l2_hints = [] { const char* e = getenv("FLEXDM_L2_HINTS"); return !(e && e[0] == '0'); }();
+  if (l2_hints && n == 2 && grp.p[0].tl.splits > 1) {
+    if (calls[1].a.ptr == calls[0].b.ptr) { grp.p[0].b_hint = 1; grp.p[1].a_hint = 2; }
+    if (calls[1].ep.relu_src == calls[0].a.ptr) grp.p[0].a_hint = 1;
+  }
   grp.total_tiles = tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const int units = num_sms() / CG;  // CTAs, or CTA pairs (clusters of two: tcgen05 cta_group::2)
+  const int grid = (tiles < units ? tiles : units) * CG;
   static const bool trace_on = getenv("FLEXDM_GEMM_TRACE") != nullptr;  // debugging aid: prints per-role wait cycles of every launch
   static unsigned long long* trace = nullptr;
   if (trace_on && !trace) { MFP_CUDA_OK(cudaMalloc(&trace, 148 * 8 * sizeof(unsigned long long))); }
   if (trace_on) MFP_CUDA_OK(cudaMemsetAsync(trace, 0, 148 * 8 * sizeof(unsigned long long), stream));
-  MFP_CUDA_OK(launch_pdl(gemm_tf32_tcgen05<BN, EPI>, grid, kGemmThreads, L::kTotal, stream, grp, tune, trace_on ? trace : nullptr));
+  MFP_CUDA_OK(launch_pdl_cluster(gemm_tf32_tcgen05<BN, EPI, CG>, grid, kGemmThreads, L::kTotal, stream, CG, grp, tune, trace_on ? trace : nullptr));
   if (trace_on) {
     unsigned long long hbuf[148 * 8];
     MFP_CUDA_OK(cudaStreamSynchronize(stream));
@@ -933,8 +978,8 @@ static int launch_tcgen05(TensorMapCache* cache, const GemmCall* calls, int n, c
     for (int b = 0; b < grid && b < 148; ++b)
       for (int k = 0; k < 8; ++k) acc[k] += (double)hbuf[b * 8 + k] / grid;
     const GemmCall& c = calls[0];
-    fprintf(stderr, "gemm trace problems=%d first: M=%d N=%d K=%d a_mn=%d b_mn=%d epi=%d splits=%d tiles/cta=%.2f | producer: wait_empty %.0f of %.0f | mma: wait_full %.0f wait_tempty %.0f | "
-            "epilogue(w4): wait_tfull %.0f wait_store %.0f wait_tmem_ld %.0f of %.0f cycles\n", n, c.M, c.N, c.K, c.a.mn_major, c.b.mn_major, EPI, grp.p[0].tl.splits,
+    fprintf(stderr, "gemm trace cg=%d problems=%d first: M=%d N=%d K=%d a_mn=%d b_mn=%d epi=%d splits=%d tiles/cta=%.2f | producer: wait_empty %.0f of %.0f | mma: wait_full %.0f wait_tempty %.0f | "
+            "epilogue(w4): wait_tfull %.0f wait_store %.0f wait_tmem_ld %.0f of %.0f cycles\n", CG, n, c.M, c.N, c.K, c.a.mn_major, c.b.mn_major, EPI, grp.p[0].tl.splits,
             (double)tiles / grid, acc[0], acc[7], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6]);
   }
   MFP_CUDA_OK(cudaGetLastError());
@@ -956,9 +1001,11 @@ static int check_call(const GemmCall& c) {
 }
 
 // One launch for up to kMaxGroup independent problems (tcgen05 path); `epi` = union of their epilogue bits.
-static int launch_tcgen05_any(TensorMapCache* cache, const GemmCall* calls, int n, int epi, bool wide, cudaStream_t stream) {
-#define MFP_GEMM_CASE(E) \
-  case (E): return wide ? launch_tcgen05<256, (E)>(cache, calls, n, stream) : launch_tcgen05<128, (E)>(cache, calls, n, stream);
+static int launch_tcgen05_any(TensorMapCache* cache, const GemmCall* calls, int n, int epi, bool wide, bool pair, cudaStream_t stream) {
+#define MFP_GEMM_CASE(E)                                                                                \
+  case (E):                                                                                             \
+    return !wide ? launch_tcgen05<128, (E), 1>(cache, calls, n, stream)                                 \
+                 : (pair ? launch_tcgen05<256, (E), 2>(cache, calls, n, stream) : launch_tcgen05<256, (E), 1>(cache, calls, n, stream));
   switch (epi) {
     MFP_GEMM_CASE(0)                                           // dgrad / wgrad
     MFP_GEMM_CASE(kEpiBias)                                    // QKV, heads
@@ -975,6 +1022,25 @@ static int launch_tcgen05_any(TensorMapCache* cache, const GemmCall* calls, int 
       return MFP_ERR_UNSUPPORTED;
   }
 #undef MFP_GEMM_CASE
+}
+
+// CTA pairs (256-row tiles) for problems of at least one full pair tile; FLEXDM_GEMM_PAIR=0 keeps every launch on single CTAs
+static bool pair_mode(int M) {
+  static const bool on = [] { const char* e = getenv("FLEXDM_GEMM_PAIR"); return !(e && e[0] == '0'); }();
+  return on && M >= 2 * kBM;
+}
+
+// Split-K factor of a weight-gradient GEMM (K = tokens): the largest that keeps its tiles within one wave of the persistent kernel
+// (one tile per CTA, or per CTA pair), with at least four k-blocks per split.
+int gemm_wgrad_splits(int M, int N, int K) {
+  const int bn = (N <= 128) ? 128 : 256;
+  const bool pair = bn == 256 && pair_mode(M);
+  const int tile_m = pair ? 2 * kBM : kBM;
+  const int tiles = ((M + tile_m - 1) / tile_m) * ((N + bn - 1) / bn);
+  int s = (num_sms() / (pair ? 2 : 1)) / tiles;
+  const int kb = (K + kBK - 1) / kBK;
+  if (s > kb / 4) s = kb / 4;
+  return s < 1 ? 1 : s;
 }
 
 int launch_gemm(TensorMapCache* cache, const GemmCall& c, int impl, cudaStream_t stream) {
@@ -996,15 +1062,16 @@ int launch_gemm(TensorMapCache* cache, const GemmCall& c, int impl, cudaStream_t
   static const int small_tiles = [] { const char* e = getenv("FLEXDM_SMALL_TILES"); return e ? atoi(e) : 100; }();
   const int tiles256 = ((c.M + kBM - 1) / kBM) * ((c.N + 255) / 256) * (c.splits < 1 ? 1 : c.splits);
   const bool wide = c.N > 128 && !(tiles256 < small_tiles && c.N % 128 == 0 && !c.ep.ln_out);
-  return launch_tcgen05_any(cache, &c, 1, epi_bits(c.ep), wide, stream);
+  return launch_tcgen05_any(cache, &c, 1, epi_bits(c.ep), wide, wide && pair_mode(c.M), stream);
 }
 
 int launch_gemm_group(TensorMapCache* cache, const GemmCall* calls, int n, cudaStream_t stream) {
   if (n < 1 || n > kMaxGroup) { set_error("gemm group: 1..%d problems", kMaxGroup); return MFP_ERR_ARG; }
   int epi = 0;
-  bool wide = false;
+  bool wide = false, pair = true;
   for (int i = 0; i < n; ++i) {
     MFP_TRY(check_call(calls[i]));
+    pair = pair && pair_mode(calls[i].M);
     const int e = epi_bits(calls[i].ep);
     // the kernel's epilogue variant is compiled in: problems of one launch may differ only in whether they use the aux operand / bias /
     // ReLU / dropout / row flags of that variant (all guarded at run time), not in the KIND of aux operand
@@ -1015,7 +1082,7 @@ int launch_gemm_group(TensorMapCache* cache, const GemmCall* calls, int n, cudaS
     epi |= e;
     wide = wide || calls[i].N > 128;
   }
-  return launch_tcgen05_any(cache, calls, n, epi, wide, stream);
+  return launch_tcgen05_any(cache, calls, n, epi, wide, wide && pair, stream);
 }
 
 }  // namespace mfp

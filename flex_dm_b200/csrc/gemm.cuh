@@ -85,6 +85,8 @@ int launch_gemm(TensorMapCache* cache, const GemmCall& call, int impl, cudaStrea
 // Up to three INDEPENDENT problems in one tcgen05 launch (a weight gradient next to the input gradient off the same dY, the encoder's
 // weight gradients): their tiles form one tile space, so epilogues overlap the next problem's main loop and launch boundaries disappear.
 int launch_gemm_group(TensorMapCache* cache, const GemmCall* calls, int n, cudaStream_t stream);
+// split-K factor the engine asks for a weight gradient [M, N] over K tokens (one wave of the persistent kernel's tiles)
+int gemm_wgrad_splits(int M, int N, int K);
 // lo[i] = x[i] - tf32_rne(x[i]) over a [rows, cols] matrix of pitch ld (lo has the same pitch): the compensation operand of the 3xTF32 mode
 int launch_split_tf32_lo(const float* x, int rows, int cols, int ld, float* lo, cudaStream_t stream);
 

@@ -18,7 +18,8 @@ MAX_FIELDS = 16
 NAME_LEN = 96
 SORT_KEYS = ["type", "left", "top", "width", "height"]  # tensor_utils.py:11
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libflexdm_mfp.so")
+# FLEXDM_MFP_LIB: development aid for A/B runs of two builds of the same extension inside one GPU call (file name next to this module)
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), os.environ.get("FLEXDM_MFP_LIB", "libflexdm_mfp.so"))
 _lib = None
 
 

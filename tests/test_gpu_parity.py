@@ -91,6 +91,42 @@ def test_gemm_fused_epilogues(impl, M, N, K):
     assert (cs.cpu().double() - dY.double().sum(0)).abs().max().item() <= 1e-4 * dY.abs().sum(0).max().item()
 
 
+def test_gemm_cta_pair_tiles():
+    """Problems large enough for the 256-row tiles of CTA pairs (tcgen05 cta_group::2: each CTA stages its 128 rows of A and half of the
+    B tile): forward layout with bias + ReLU and a ragged last tile, residual in place, dgrad with a ReLU mask, and a split-K weight
+    gradient with the fused column sum (the peer CTA sums its own half of the columns)."""
+    from flex_dm_b200.engine import debug_gemm
+
+    M, N, K = 6400 + 72, 512, 256
+    g = torch.Generator().manual_seed(11)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(K, N, generator=g)   # forward: B is [K][N] (MN-major)
+    bias = torch.randn(N, generator=g)
+    R = torch.randn(M, N, generator=g)
+    scale = (A.double().abs() @ W.double().abs()).max().item()
+    out = debug_gemm(A.cuda(), 0, W.cuda(), 1, M, N, K, bias=bias.cuda(), relu=True, impl=0)
+    ref = torch.relu(A.double() @ W.double() + bias.double())
+    assert (out.cpu().double() - ref).abs().max().item() <= 2e-3 * scale
+    x = R.cuda().clone()
+    debug_gemm(A.cuda(), 0, W.cuda(), 1, M, N, K, bias=bias.cuda(), impl=0, out=x, residual=x)
+    ref = A.double() @ W.double() + bias.double() + R.double()
+    assert (x.cpu().double() - ref).abs().max().item() <= 2e-3 * scale
+    Wk = torch.randn(N, K, generator=g)  # dgrad: B is [N][K] (K-major)
+    out = debug_gemm(A.cuda(), 0, Wk.cuda(), 0, M, N, K, impl=0, relu_src=R.cuda())
+    ref = (A.double() @ Wk.double().T) * (R.double() > 0)
+    assert (out.cpu().double() - ref).abs().max().item() <= 2e-3 * scale
+    # weight gradient: D[512, 256] = X^T . dY over M tokens, split-K, colsum = sum_rows dY
+    X = torch.randn(M, 512, generator=g)
+    dY = torch.randn(M, 256, generator=g)
+    out = torch.zeros(512, 256, device="cuda")
+    cs = torch.zeros(256, device="cuda")
+    debug_gemm(X.cuda(), 1, dY.cuda(), 1, 512, 256, M, splits=37, impl=0, out=out, colsum=cs)
+    ref = X.double().T @ dY.double()
+    wscale = (X.double().abs().T @ dY.double().abs()).max().item()
+    assert (out.cpu().double() - ref).abs().max().item() <= 2e-3 * wscale
+    assert (cs.cpu().double() - dY.double().sum(0)).abs().max().item() <= 1e-4 * dY.abs().sum(0).max().item()
+
+
 # ----------------------------------------------------------------------------------------------- attention core
 def _attention_reference(qkv, length, B, S):
     """transformer.py:60-76 in float64: softmax(QK^T/sqrt(dh) - 1e9 (1 - key mask)) V per head."""
