@@ -275,8 +275,15 @@ constexpr int kAtBwdThreads = 384;  // warps 0-3: TMA / MMA / TMEM allocator / i
 __global__ void __launch_bounds__(kAtBwdThreads, 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid_constant__ CUtensorMap tmQkvMN, const __grid_constant__ CUtensorMap tmDoK,
                         const __grid_constant__ CUtensorMap tmDoMN, const __grid_constant__ CUtensorMap tmDqkv, const float* __restrict__ out,
-                        const float* __restrict__ lse, const int* __restrict__ length, int B, int S) {
+                        const float* __restrict__ lse, const int* __restrict__ length, int B, int S, unsigned long long* __restrict__ trace) {
   using L = AttnBwdSmem;
+  // FLEXDM_ATTN_TRACE: wait / work cycles per role, trace[blockIdx.x * 16 + k] (see the launcher for the slots)
+  unsigned long long tw[6] = {0, 0, 0, 0, 0, 0};
+  const long long t_begin = trace ? clock64() : 0;
+  auto timed_wait = [&](uint32_t bar, uint32_t parity, int slot) {
+    if (trace) { const long long t0 = clock64(); mbar_wait(bar, parity); tw[slot] += (unsigned long long)(clock64() - t0); }
+    else mbar_wait(bar, parity);
+  };
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -347,7 +354,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid
         const int n = min(S, __ldg(length + b) + 1);
         const int nk = (n + 7) >> 3;
         const uint32_t ph = (uint32_t)(i & 1);
-        mbar_wait(kfull, ph);
+        timed_wait(kfull, ph, 0);
         tcgen05_fence_after();
 #pragma unroll
         for (int kk = 0; kk < kDh / 8; ++kk) umma_tf32(tmem_base, dk_k + (uint64_t)(kk * 2), dq_k + (uint64_t)(kk * 2), idesc_s, kk > 0 ? 1u : 0u);
@@ -355,8 +362,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid
         for (int kk = 0; kk < kDh / 8; ++kk) umma_tf32(tmem_base + 128u, dv_k + (uint64_t)(kk * 2), ddo_k + (uint64_t)(kk * 2), idesc_s, kk > 0 ? 1u : 0u);
         tcgen05_commit(sfull);
         tcgen05_commit(kempty);
-        mbar_wait(pready, ph);
-        mbar_wait(mnfull, ph);
+        timed_wait(pready, ph, 1);
+        timed_wait(mnfull, ph, 2);
         tcgen05_fence_after();
         for (int kk = 0; kk < nk; ++kk)  // dV = P^T dO
           umma_tf32_ts(tmem_base + 256u, tmem_base + (uint32_t)(kk * 8), ddo_m + (uint64_t)(kk * 64), idesc_g, kk > 0 ? 1u : 0u);
@@ -367,6 +374,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid
         tcgen05_commit(ofull);
         tcgen05_commit(mnempty);
       }
+      if (trace) { trace[blockIdx.x * 16 + 0] = tw[0]; trace[blockIdx.x * 16 + 1] = tw[1]; trace[blockIdx.x * 16 + 2] = tw[2]; }
     }
   } else if (warp >= 4) {
     // Two compute groups of four warps (one warp per TMEM lane quarter each).  Both own all 128 keys (lanes); group g takes the
@@ -428,9 +436,12 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid
       const int u = blockIdx.x + i * gridDim.x, b = u / kH;
       const int n = min(S, __ldg(length + b) + 1);
       const bool key_valid = row < n;
+      long long tc0 = trace ? clock64() : 0;
       asm volatile("bar.sync 1, 256;" ::: "memory");  // lse_s / d_s of this unit are in place
-      mbar_wait(sfull, (uint32_t)(i & 1));
+      if (trace) { const long long t1 = clock64(); tw[3] += (unsigned long long)(t1 - tc0); tc0 = t1; }
+      timed_wait(sfull, (uint32_t)(i & 1), 0);
       tcgen05_fence_after();
+      if (trace) tc0 = clock64();
 #pragma unroll 1
       for (int c = 2 * g; c < 2 * g + 2; ++c) {  // 32 queries at a time
         uint32_t rs[32], rd[32];
@@ -458,12 +469,21 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pready);
+      if (trace) { const long long t1 = clock64(); tw[1] += (unsigned long long)(t1 - tc0); tc0 = t1; }  // P / dS computation
       asm volatile("bar.sync 2, 256;" ::: "memory");  // everyone is done with lse_s / d_s before the next unit overwrites them
       if (g == 1 && i + 1 < n_local) prepare(i + 1);
-      mbar_wait(ofull, (uint32_t)(i & 1));
+      if (trace) { const long long t1 = clock64(); tw[4] += (unsigned long long)(t1 - tc0); tc0 = t1; }  // barrier 2 + (group 1) prepare
+      timed_wait(ofull, (uint32_t)(i & 1), 2);
       tcgen05_fence_after();
+      if (trace) tc0 = clock64();
       if (g == 0) { store_tile(i, 0); store_tile(i, 1); }
       else store_tile(i, 2);
+      if (trace) tw[5] += (unsigned long long)(clock64() - tc0);  // stores
+    }
+    if (trace && lane == 0 && q == 0) {
+      unsigned long long* t = trace + blockIdx.x * 16 + 3 + g * 6;
+      t[0] = tw[0]; t[1] = tw[1]; t[2] = tw[2]; t[3] = tw[3]; t[4] = tw[4]; t[5] = tw[5];
+      if (g == 0) trace[blockIdx.x * 16 + 15] = (unsigned long long)(clock64() - t_begin);
     }
     if (lane == 0) tma_wait_group_read<0>();
   }
@@ -525,8 +545,24 @@ int launch_attention_bwd_tc(TensorMapCache* maps, const float* qkv, const float*
   if (!mqk || !mqm || !mdk || !mdm || !mg) return MFP_ERR_CUDA;
   const int units = B * kH;
   const int grid = units < sm_count() ? units : sm_count();
-  MFP_CUDA_OK(launch_pdl(attention_bwd_tc_kernel, grid, kAtBwdThreads, AttnBwdSmem::kTotal, st, *mqk, *mqm, *mdk, *mdm, *mg, out, lse, length, B, S));
+  static const bool trace_on = getenv("FLEXDM_ATTN_TRACE") != nullptr;  // debugging aid: per-role wait / work cycles of every launch
+  static unsigned long long* trace = nullptr;
+  if (trace_on && !trace) MFP_CUDA_OK(cudaMalloc(&trace, 148 * 16 * sizeof(unsigned long long)));
+  if (trace_on) MFP_CUDA_OK(cudaMemsetAsync(trace, 0, 148 * 16 * sizeof(unsigned long long), st));
+  MFP_CUDA_OK(launch_pdl(attention_bwd_tc_kernel, grid, kAtBwdThreads, AttnBwdSmem::kTotal, st, *mqk, *mqm, *mdk, *mdm, *mg, out, lse, length, B, S,
+                         trace_on ? trace : nullptr));
   MFP_CUDA_OK(cudaGetLastError());
+  if (trace_on) {
+    unsigned long long hb[148 * 16];
+    MFP_CUDA_OK(cudaStreamSynchronize(st));
+    MFP_CUDA_OK(cudaMemcpy(hb, trace, sizeof(hb), cudaMemcpyDeviceToHost));
+    double a[16] = {};
+    for (int b = 0; b < grid && b < 148; ++b)
+      for (int k = 0; k < 16; ++k) a[k] += (double)hb[b * 16 + k] / grid;
+    fprintf(stderr, "attention bwd trace units/cta=%.2f | mma: wait kfull %.0f pready %.0f mnfull %.0f | group0: sfull %.0f compute %.0f ofull %.0f bar1 %.0f bar2 %.0f store %.0f | "
+            "group1: sfull %.0f compute %.0f ofull %.0f bar1 %.0f bar2+prepare %.0f store %.0f | total %.0f cycles\n", (double)units / grid, a[0], a[1], a[2], a[3], a[4],
+            a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[15]);
+  }
   return MFP_OK;
 }
 
