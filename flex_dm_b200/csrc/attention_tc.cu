@@ -261,9 +261,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
 // second fetch hits L2).  Two independent single-slot rings: the K-major set is released as soon as S^T / dP^T are
 // done, the MN-major set after the three gradient GEMMs, so the next unit's loads fly under this unit's math.
 struct AttnBwdSmem {
-  static constexpr int kKmajOff = 0;                       // K, Q, V, dO   (K-major, SWIZZLE_128B)
-  static constexpr int kMnOff = 4 * kAtTileBytes;          // dO, Q, K      (MN-major, SWIZZLE_128B_ATOM_32B)
-  static constexpr int kDsOff = 7 * kAtTileBytes;          // dS^T as the MN-major A operand of dQ: 4 chunks x [128 keys][32 q]
+  static constexpr int kKmajOff = 0;                       // K, Q, V, dO, O   (K-major, SWIZZLE_128B; O only feeds D_i = dO_i . O_i)
+  static constexpr int kMnOff = 5 * kAtTileBytes;          // dO, Q, K      (MN-major, SWIZZLE_128B_ATOM_32B)
+  static constexpr int kDsOff = 8 * kAtTileBytes;          // dS^T as the MN-major A operand of dQ: 4 chunks x [128 keys][32 q]
   static constexpr int kStageOff = kDsOff + 4 * kAtTileBytes;  // 4 warps x 2 x [32][32] fp32
   static constexpr int kVecOff = kStageOff + 4 * 2 * 4096;     // lse[128], D[128]
   static constexpr int kBarOff = kVecOff + 1024;
@@ -274,7 +274,7 @@ struct AttnBwdSmem {
 constexpr int kAtBwdThreads = 384;  // warps 0-3: TMA / MMA / TMEM allocator / idle; warps 4-7 and 8-11: two compute groups
 __global__ void __launch_bounds__(kAtBwdThreads, 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid_constant__ CUtensorMap tmQkvMN, const __grid_constant__ CUtensorMap tmDoK,
-                        const __grid_constant__ CUtensorMap tmDoMN, const __grid_constant__ CUtensorMap tmDqkv, const float* __restrict__ out,
+                        const __grid_constant__ CUtensorMap tmDoMN, const __grid_constant__ CUtensorMap tmDqkv, const __grid_constant__ CUtensorMap tmOutK,
                         const float* __restrict__ lse, const int* __restrict__ length, int B, int S, unsigned long long* __restrict__ trace) {
   using L = AttnBwdSmem;
   // FLEXDM_ATTN_TRACE: wait / work cycles per role, trace[blockIdx.x * 16 + k] (see the launcher for the slots)
@@ -303,7 +303,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid
     mbar_init(kfull, 1); mbar_init(kempty, 5); mbar_init(mnfull, 1); mbar_init(mnempty, 1);  // kempty: MMA commit + the 4 warps that read dO
     mbar_init(sfull, 1); mbar_init(pready, 8); mbar_init(ofull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    prefetch_tensormap(&tmQkvK); prefetch_tensormap(&tmQkvMN); prefetch_tensormap(&tmDoK); prefetch_tensormap(&tmDoMN); prefetch_tensormap(&tmDqkv);
+    prefetch_tensormap(&tmQkvK); prefetch_tensormap(&tmQkvMN); prefetch_tensormap(&tmDoK); prefetch_tensormap(&tmDoMN); prefetch_tensormap(&tmDqkv); prefetch_tensormap(&tmOutK);
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512) : "memory");
@@ -323,12 +323,13 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid
         const int u = blockIdx.x + i * gridDim.x, b = u / kH, h = u % kH;
         const uint32_t ph = (uint32_t)(i & 1);
         mbar_wait(kempty, ph ^ 1u);
-        mbar_expect_tx(kfull, 4 * kAtTileBytes);
+        mbar_expect_tx(kfull, 5 * kAtTileBytes);
         const uint32_t sk = base + L::kKmajOff;
         tma_load_3d(sk, &tmQkvK, kD + h * kDh, 0, b, kfull);                          // K
         tma_load_3d(sk + kAtTileBytes, &tmQkvK, h * kDh, 0, b, kfull);                // Q
         tma_load_3d(sk + 2 * kAtTileBytes, &tmQkvK, 2 * kD + h * kDh, 0, b, kfull);   // V
         tma_load_3d(sk + 3 * kAtTileBytes, &tmDoK, h * kDh, 0, b, kfull);             // dO
+        tma_load_3d(sk + 4 * kAtTileBytes, &tmOutK, h * kDh, 0, b, kfull);            // O
         mbar_wait(mnempty, ph ^ 1u);
         mbar_expect_tx(mnfull, 3 * kAtTileBytes);
         const uint32_t sm = base + L::kMnOff;
@@ -388,24 +389,34 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvK, const __grid
     uint8_t* stage_ptr = base_ptr + L::kStageOff + (g * 4 + q) * 4096;
     uint8_t* ds_ptr = base_ptr + L::kDsOff;
     const uint8_t* do_ptr = base_ptr + L::kKmajOff + 3 * kAtTileBytes;
+    const uint8_t* o_ptr = base_ptr + L::kKmajOff + 4 * kAtTileBytes;
     const uint32_t sw = (uint32_t)(lane & 7);
     const float c2 = kAtScale * kLog2e;
 
-    auto prepare = [&](int i) {  // lse_i and D_i = dO_i . O_i of unit i -> shared memory (group 1: one query row per thread)
+    // lse of a unit for this thread's query row: fetched one unit ahead, so that its latency is off the path
+    auto load_lse = [&](int i) {
       const int u = blockIdx.x + i * gridDim.x, b = u / kH, h = u % kH;
+      return row < S ? __ldg(lse + ((size_t)b * kH + h) * S + row) : INFINITY;
+    };
+    float lse_next = (g == 1 && n_local > 0) ? load_lse(0) : 0.f;
+    // lse_i and D_i = dO_i . O_i of unit i -> shared memory (group 1: one query row per thread).  O comes with the K-major tiles by TMA
+    // (plain fp32 map): per-thread global loads of the O rows put a DRAM round trip (~3 800 cycles per unit, FLEXDM_ATTN_TRACE) on the
+    // path between two units' compute phases -- longer than the gradient MMAs it was meant to hide under.
+    auto prepare = [&](int i) {
       mbar_wait(kfull, (uint32_t)(i & 1));
-      float dsum = 0.f, l = INFINITY;
-      if (row < S) {
-        const float4* op = reinterpret_cast<const float4*>(out + ((size_t)b * S + row) * kD + h * kDh);
+      float dsum = 0.f;
+      const float l = lse_next;
+      if (row < S) {  // rows past the document are zero-filled by the TMA unit
+        const uint8_t* op = o_ptr + row * 128;
         const uint8_t* dp = do_ptr + row * 128;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float4 o = __ldg(op + k);
+          const float4 o = *reinterpret_cast<const float4*>(op + ((k ^ sw) << 4));
           const float4 gv = *reinterpret_cast<const float4*>(dp + ((k ^ sw) << 4));
           dsum += o.x * gv.x + o.y * gv.y + o.z * gv.z + o.w * gv.w;
         }
-        l = __ldg(lse + ((size_t)b * kH + h) * S + row);
       }
+      if (i + 1 < n_local) lse_next = load_lse(i + 1);
       lse_s[row] = l * kLog2e;
       d_s[row] = dsum;
       __syncwarp();
@@ -542,14 +553,15 @@ int launch_attention_bwd_tc(TensorMapCache* maps, const float* qkv, const float*
   const CUtensorMap* mdk = tensor_map_get(maps, dout, 3, odims, ostr, tbox, kMapOperandK);
   const CUtensorMap* mdm = tensor_map_get(maps, dout, 3, odims, ostr, tbox, kMapOperandMN);
   const CUtensorMap* mg = tensor_map_get(maps, dqkv, 3, qdims, qstr, sbox, kMapEpilogue);
-  if (!mqk || !mqm || !mdk || !mdm || !mg) return MFP_ERR_CUDA;
+  const CUtensorMap* mo = tensor_map_get(maps, out, 3, odims, ostr, tbox, kMapEpilogue);  // O rows as plain fp32 (not rounded to TF32), same swizzle as the K-major tiles
+  if (!mqk || !mqm || !mdk || !mdm || !mg || !mo) return MFP_ERR_CUDA;
   const int units = B * kH;
   const int grid = units < sm_count() ? units : sm_count();
   static const bool trace_on = getenv("FLEXDM_ATTN_TRACE") != nullptr;  // debugging aid: per-role wait / work cycles of every launch
   static unsigned long long* trace = nullptr;
   if (trace_on && !trace) MFP_CUDA_OK(cudaMalloc(&trace, 148 * 16 * sizeof(unsigned long long)));
   if (trace_on) MFP_CUDA_OK(cudaMemsetAsync(trace, 0, 148 * 16 * sizeof(unsigned long long), st));
-  MFP_CUDA_OK(launch_pdl(attention_bwd_tc_kernel, grid, kAtBwdThreads, AttnBwdSmem::kTotal, st, *mqk, *mqm, *mdk, *mdm, *mg, out, lse, length, B, S,
+  MFP_CUDA_OK(launch_pdl(attention_bwd_tc_kernel, grid, kAtBwdThreads, AttnBwdSmem::kTotal, st, *mqk, *mqm, *mdk, *mdm, *mg, *mo, lse, length, B, S,
                          trace_on ? trace : nullptr));
   MFP_CUDA_OK(cudaGetLastError());
   if (trace_on) {
