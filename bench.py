@@ -185,7 +185,8 @@ def run_reference(args):
 
 def tfrecord_leg(model, timed, steps):
     """Trains from a TFRecord export of one synthetic batch (256 full-length crello documents, reshuffled every pass): every step the
-    native reader parses 256 SequenceExamples (135 MB of columns) on the host threads into pinned memory."""
+    native reader parses 256 SequenceExamples on the host threads into pinned memory -- in the packed column format (55 MB of columns:
+    the embedding rows no element carries are never written), with the dense format (135 MB) timed beside it."""
     import shutil
     import tempfile
     import time
@@ -200,25 +201,31 @@ def tfrecord_leg(model, timed, steps):
     try:
         write_synthetic_dataset(root, "crello", {"train": B_PER_GPU}, seq_len=SEQ_LEN, lengths="full", shards=2, seed=123)
         spec = DataSpec(os.path.join(root, "crello-spec.yml"), root, batch_size=B_PER_GPU)
-        dataset = spec.make_dataset("train", shuffle=True, repeat=True, prefetch=3, pad_to=SEQ_LEN)
-        # host-only rate of the parser (no GPU work in flight)
-        it = iter(spec.make_dataset("train", shuffle=True, repeat=True, prefetch=0, pad_to=SEQ_LEN))
-        for _ in range(3):
-            next(it)
-        t0 = time.perf_counter()
+        # host-only rate of the parser (no GPU work in flight), both batch formats
         n_host = 10
-        for _ in range(n_host):
-            next(it)
-        host_ms = (time.perf_counter() - t0) * 1e3 / n_host
-        feeder = DevicePrefetcher(model, iter(dataset))
+        host_ms = {}
+        for packed in (False, True):
+            it = iter(spec.make_dataset("train", shuffle=True, repeat=True, prefetch=0, pad_to=SEQ_LEN, packed=packed))
+            for _ in range(3):
+                next(it)
+            t0 = time.perf_counter()
+            for _ in range(n_host):
+                next(it)
+            host_ms[packed] = (time.perf_counter() - t0) * 1e3 / n_host
         row_host = torch.empty((model.engine.metrics_width,), dtype=torch.float32).pin_memory()
 
-        def step(i):
-            row_host.copy_(model.train_step(next(feeder), staged=True), non_blocking=True)
+        def streamed(packed):
+            feeder = DevicePrefetcher(model, iter(spec.make_dataset("train", shuffle=True, repeat=True, prefetch=3, pad_to=SEQ_LEN, packed=packed)))
 
-        for i in range(3):
-            step(i)
-        ms = timed(step, steps)
+            def step(i):
+                row_host.copy_(model.train_step(next(feeder), staged=True), non_blocking=True)
+
+            for i in range(3):
+                step(i)
+            return timed(step, steps)
+
+        ms_dense = streamed(False)
+        ms = streamed(True)
         # the same split resident in HBM (make_dataset(cache="device")): batches are gathered on the GPU, nothing is parsed or copied per step
         cached = spec.make_dataset("train", shuffle=True, repeat=True, cache="device", pad_to=SEQ_LEN)
         cached_it = iter(cached)
@@ -256,9 +263,12 @@ def tfrecord_leg(model, timed, steps):
                                   "gather": {"ms": gather_ms, "algorithmic_bytes": gather_bytes, "achieved": gather_bytes / (gather_ms * 1e-3) / 1e9,
                                              "unit": "GB/s", "peak": peak, "frac": gather_bytes / (gather_ms * 1e-3) / 1e9 / peak},
                                   "source": "the parsed split kept ragged in HBM, batches cut out by mfp_gather_documents (DataSpec.make_dataset(cache='device'))"},
-                "host_parse_ms_per_batch": host_ms, "host_threads": spec._threads,
+                "dense_columns": {"value": B_PER_GPU * SEQ_LEN * steps / (ms_dense * 1e-3), "unit": UNIT, "ms_per_step": ms_dense / steps,
+                                  "host_parse_ms_per_batch": host_ms[False]},
+                "host_parse_ms_per_batch": host_ms[True], "host_threads": spec._threads,
                 "source": "TFRecord shards of tf.train.SequenceExample (256 synthetic crello documents, S=128) -> DataSpec.make_dataset(shuffle, repeat, "
-                          "prefetch=3) -> libflexdm_io parse_batch into pinned memory -> DevicePrefetcher -> MFP.train_step"}
+                          "prefetch=3, packed=True) -> libflexdm_io fdio_parse_batch_packed into pinned memory (packed numerical columns) -> DevicePrefetcher "
+                          "-> MFP.train_step; dense_columns = the same with fdio_parse_batch (dense DataSpec.parse_fn layout)"}
     finally:
         shutil.rmtree(root, ignore_errors=True)
 

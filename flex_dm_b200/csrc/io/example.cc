@@ -319,12 +319,14 @@ const char* what_for(int code, const Column& c, char* scratch, size_t n) {
   }
 }
 
+// skip (optional, one flag per column): columns a later pass writes (the packed columns of fdio_parse_batch_packed)
 void parse_record(const fdio_schema& s, const uint8_t* rec, size_t len, int32_t b, int32_t S, void* const* out, std::vector<Span>* found,
-                  RecordError* err) {
+                  RecordError* err, const uint8_t* skip = nullptr) {
   char scratch[160];
   int code = split_example(rec, len, s, found);
   if (code != FDIO_OK) { err->code = code; err->text = "record " + std::to_string(b) + ": malformed SequenceExample"; return; }
   for (size_t ci = 0; ci < s.cols.size(); ++ci) {
+    if (skip && skip[ci]) continue;
     const Column& c = s.cols[ci];
     const Span& sp = (*found)[ci];
     void* o = out ? out[ci] : nullptr;
@@ -378,6 +380,69 @@ void parse_record(const fdio_schema& s, const uint8_t* rec, size_t len, int32_t 
       else if (c.output == FDIO_OUT_FLOAT32) std::fill_n(static_cast<float*>(o) + base, cnt, 0.f);
       else std::fill_n(static_cast<int64_t*>(o) + 2 * base, 2 * cnt, int64_t(0));
     }
+  }
+}
+
+// Does element (b, t) carry packed column pc?  (fdio_parse_batch_packed; the length and gate columns are already in `out`)
+inline int carries(const fdio_schema& s, const fdio_pack_column& pc, void* const* out, int32_t length_column, int32_t b, int32_t S, int32_t t) {
+  if (t > static_cast<const int32_t*>(out[length_column])[size_t(b) * size_t(s.cols[size_t(length_column)].width)]) return 0;
+  if (pc.cond_column < 0) return 1;
+  const int32_t v = static_cast<const int32_t*>(out[pc.cond_column])[size_t(b) * size_t(S) + size_t(t)];
+  if (v < 0 || v >= pc.cond_n) return -1;
+  return pc.cond_mask[v] ? 1 : 0;
+}
+
+// Is this Feature exactly one packed FloatList of W values in the canonical encoding -- 12 <len> 0a <4W> <4W bytes> -- ?  Decided from
+// the few header bytes and the lengths alone: the payload of a row nothing will read is then not touched at all (the records are
+// memory-mapped: 59 % of crello's embedding bytes never leave the page cache).  Anything else is decoded in full by for_each_value.
+inline bool is_plain_float_row(const uint8_t* p, size_t n, size_t W) {
+  Wire w(p, n);
+  uint32_t field, type;
+  const uint8_t* lp; size_t ln;
+  if (!w.tag(&field, &type) || field != 2 || type != 2 || !w.bytes(&lp, &ln) || !w.done()) return false;
+  Wire l(lp, ln);
+  const uint8_t* fp; size_t fn;
+  if (!l.tag(&field, &type) || field != 1 || type != 2 || !l.bytes(&fp, &fn) || !l.done()) return false;
+  return fn == 4 * W;
+}
+
+// One packed column of one record: rows of the elements that carry it go to out[column] from row `row0` on, the row map gets the row or -1.
+void pack_record(const fdio_schema& s, const fdio_pack_column& pc, const Span& sp, int32_t b, int32_t S, void* const* out,
+                 int32_t length_column, int64_t row0, float* scratch_row, RecordError* err) {
+  char scratch[160];
+  const Column& c = s.cols[size_t(pc.column)];
+  const size_t W = size_t(c.width);
+  float* dst = static_cast<float*>(out[pc.column]);
+  int32_t* map = pc.rowmap + size_t(b) * size_t(S);
+  if (!sp.present) { describe(err, FDIO_ERR_INVALID, b, c, -1, "feature list is required but could not be found"); return; }
+  Wire w(sp.p, sp.n);
+  int64_t t = 0, row = row0;
+  while (!w.done()) {
+    uint32_t field, type;
+    if (!w.tag(&field, &type)) { describe(err, FDIO_ERR_CORRUPT, b, c, t, "malformed protobuf"); return; }
+    if (field != 1 || type != 2) { if (!w.skip(type)) { describe(err, FDIO_ERR_CORRUPT, b, c, t, "malformed protobuf"); return; } continue; }
+    const uint8_t* fp; size_t fn;
+    if (!w.bytes(&fp, &fn)) { describe(err, FDIO_ERR_CORRUPT, b, c, t, "malformed protobuf"); return; }
+    if (t >= S) { describe(err, FDIO_ERR_ARG, b, c, t, "more steps than the batch was sized for"); return; }
+    const int carry = carries(s, pc, out, length_column, b, S, int32_t(t));
+    if (carry < 0) { describe(err, FDIO_ERR_ARG, b, c, t, "the gating column's value is outside the loss_condition mask"); return; }
+    if (!carry && is_plain_float_row(fp, fn, W)) { map[t] = -1; ++t; continue; }  // well-formed and unread: not even decoded
+    float* row_dst = carry ? dst + size_t(row) * W : scratch_row;  // other encodings of a row nothing reads are decoded all the same (same errors as the dense parse)
+    int64_t n = for_each_value(c, fp, fn, [&](const Value& v, int64_t k) { if (k < int64_t(W)) row_dst[k] = v.f; return int(FDIO_OK); }, row_dst, W);
+    if (n < 0) { describe(err, n == FDIO_ERR_NOT_FOUND ? int(FDIO_ERR_INVALID) : int(n), b, c, t, what_for(int(n), c, scratch, sizeof(scratch))); return; }
+    if (n != int64_t(W)) {
+      snprintf(scratch, sizeof(scratch), "number of %s values != expected: values size %lld but output shape holds %zu", kDtypeName[c.dtype], (long long)n, W);
+      describe(err, FDIO_ERR_INVALID, b, c, t, scratch);
+      return;
+    }
+    map[t] = carry ? int32_t(row++) : -1;
+    ++t;
+  }
+  for (; t < S; ++t) {  // past the record's own steps: the dense parse holds zeros there, and so does a row an inconsistent length asks for
+    const int carry = carries(s, pc, out, length_column, b, S, int32_t(t));
+    if (carry < 0) { describe(err, FDIO_ERR_ARG, b, c, t, "the gating column's value is outside the loss_condition mask"); return; }
+    if (carry) { std::fill_n(dst + size_t(row) * W, W, 0.f); map[t] = int32_t(row++); }
+    else map[t] = -1;
   }
 }
 
@@ -487,6 +552,69 @@ int fdio_parse_batch(const fdio_schema* s, const uint8_t* const* records, const 
   return run_threads(B, n_threads, [&](int32_t lo, int32_t hi, RecordError* err) {
     std::vector<Span> found(s->cols.size());
     for (int32_t b = lo; b < hi && err->code == FDIO_OK; ++b) parse_record(*s, records[b], lens[b], b, S, out, &found, err);
+  });
+}
+
+int fdio_parse_batch_packed(const fdio_schema* s, const uint8_t* const* records, const uint64_t* lens, int32_t B, int32_t S, void* const* out,
+                            int32_t length_column, fdio_pack_column* pack, int32_t n_pack, int32_t n_threads) {
+  if (!s || !records || !lens || !out || B < 0 || S < 0 || (n_pack > 0 && !pack) || n_pack < 0)
+    return fdio::fail(FDIO_ERR_ARG, "fdio_parse_batch_packed: bad argument");
+  const int32_t ncol = int32_t(s->cols.size());
+  if (length_column < 0 || length_column >= ncol || s->cols[size_t(length_column)].is_sequence || s->cols[size_t(length_column)].output != FDIO_OUT_INT32)
+    return fdio::fail(FDIO_ERR_ARG, "fdio_parse_batch_packed: length_column must be an int32 context column");
+  std::vector<uint8_t> skip(size_t(ncol), 0);
+  for (int32_t k = 0; k < n_pack; ++k) {
+    const fdio_pack_column& pc = pack[k];
+    if (pc.column < 0 || pc.column >= ncol || skip[size_t(pc.column)]) return fdio::fail(FDIO_ERR_ARG, "fdio_parse_batch_packed: bad or repeated packed column");
+    const Column& c = s->cols[size_t(pc.column)];
+    if (!c.is_sequence || c.transform != FDIO_NONE || c.dtype != FDIO_FLOAT32 || c.output != FDIO_OUT_FLOAT32)
+      return fdio::fail(FDIO_ERR_ARG, "column '%s': only untransformed float32 sequence columns can be packed", c.name.c_str());
+    if (pc.cond_column >= 0) {
+      if (pc.cond_column >= ncol || !pc.cond_mask || pc.cond_n <= 0) return fdio::fail(FDIO_ERR_ARG, "column '%s': bad gating column", c.name.c_str());
+      const Column& g = s->cols[size_t(pc.cond_column)];
+      if (!g.is_sequence || g.width != 1 || g.output != FDIO_OUT_INT32) return fdio::fail(FDIO_ERR_ARG, "column '%s': the gating column must be an int32 sequence column of width 1", c.name.c_str());
+    }
+    if (!pc.rowmap && B > 0 && S > 0) return fdio::fail(FDIO_ERR_ARG, "column '%s': no row map", c.name.c_str());
+    skip[size_t(pc.column)] = 1;
+  }
+  for (int32_t ci = 0; ci < ncol; ++ci)
+    if (s->cols[size_t(ci)].output != FDIO_OUT_SKIP && !out[ci] && B > 0 && (S > 0 || !s->cols[size_t(ci)].is_sequence))
+      return fdio::fail(FDIO_ERR_ARG, "fdio_parse_batch_packed: no output buffer for column '%s'", s->cols[size_t(ci)].name.c_str());
+  // pass A: every other column (the length and gate columns among them)
+  int code = run_threads(B, n_threads, [&](int32_t lo, int32_t hi, RecordError* err) {
+    std::vector<Span> found(s->cols.size());
+    for (int32_t b = lo; b < hi && err->code == FDIO_OK; ++b) parse_record(*s, records[b], lens[b], b, S, out, &found, err, skip.data());
+  });
+  if (code != FDIO_OK) return code;
+  // rows per document and packed column -> first row of every document
+  std::vector<int64_t> row0(size_t(n_pack) * size_t(B + 1), 0);
+  for (int32_t k = 0; k < n_pack; ++k) {
+    int64_t* r = row0.data() + size_t(k) * size_t(B + 1);
+    for (int32_t b = 0; b < B; ++b) {
+      int64_t n = 0;
+      for (int32_t t = 0; t < S; ++t) {
+        const int carry = carries(*s, pack[k], out, length_column, b, S, t);
+        if (carry < 0) return fdio::fail(FDIO_ERR_ARG, "record %d, key '%s', index %d: the gating column's value is outside the loss_condition mask", b,
+                                         s->cols[size_t(pack[k].column)].name.c_str(), t);
+        n += carry;
+      }
+      r[b + 1] = r[b] + n;
+    }
+    pack[k].n_rows = r[B];
+    if (r[B] > pack[k].capacity_rows) return fdio::fail(FDIO_ERR_ARG, "column '%s': %lld rows in use, capacity %lld", s->cols[size_t(pack[k].column)].name.c_str(),
+                                                        (long long)r[B], (long long)pack[k].capacity_rows);
+  }
+  // pass B: the packed columns, every document at its own rows
+  return run_threads(B, n_threads, [&](int32_t lo, int32_t hi, RecordError* err) {
+    std::vector<Span> found(s->cols.size());
+    std::vector<float> scratch_row;
+    for (int32_t b = lo; b < hi && err->code == FDIO_OK; ++b) {
+      if (split_example(records[b], lens[b], *s, &found) != FDIO_OK) { err->code = FDIO_ERR_CORRUPT; err->text = "record " + std::to_string(b) + ": malformed SequenceExample"; return; }
+      for (int32_t k = 0; k < n_pack && err->code == FDIO_OK; ++k) {
+        scratch_row.resize(size_t(s->cols[size_t(pack[k].column)].width));
+        pack_record(*s, pack[k], found[size_t(pack[k].column)], b, S, out, length_column, row0[size_t(k) * size_t(B + 1) + size_t(b)], scratch_row.data(), err);
+      }
+    }
   });
 }
 

@@ -37,6 +37,18 @@ class Column(ctypes.Structure):
     ]
 
 
+class PackColumn(ctypes.Structure):  # fdio_pack_column (include/flexdm_io.h)
+    _fields_ = [
+        ("column", ctypes.c_int32),
+        ("cond_column", ctypes.c_int32),
+        ("cond_mask", c_u8p),
+        ("cond_n", ctypes.c_int32),
+        ("rowmap", ctypes.POINTER(ctypes.c_int32)),
+        ("capacity_rows", ctypes.c_int64),
+        ("n_rows", ctypes.c_int64),
+    ]
+
+
 _SIGNATURES = {
     "fdio_last_error": (ctypes.c_char_p, []),
     "fdio_version": (ctypes.c_int, []),
@@ -55,6 +67,9 @@ _SIGNATURES = {
                                         ctypes.POINTER(ctypes.c_int32), ctypes.c_int32]),
     "fdio_parse_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64), ctypes.c_int32,
                                         ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32]),
+    "fdio_parse_batch_packed": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64), ctypes.c_int32,
+                                               ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.POINTER(PackColumn), ctypes.c_int32,
+                                               ctypes.c_int32]),
     "fdio_bundle_open": (ctypes.c_void_p, [ctypes.c_char_p]),
     "fdio_bundle_close": (None, [ctypes.c_void_p]),
     "fdio_bundle_count": (ctypes.c_int32, [ctypes.c_void_p]),

@@ -103,6 +103,28 @@ int fdio_batch_steps(const fdio_schema* s, const uint8_t* const* records, const 
 int fdio_parse_batch(const fdio_schema* s, const uint8_t* const* records, const uint64_t* lens, int32_t B, int32_t S, void* const* out,
                      int32_t n_threads);
 
+/* Pass 2, packed form (the input pipeline's batch format, flex_dm_b200.data.pack_batch / mfp_set_packed_rows): the float32 sequence
+ * columns named in `pack` are written as [n_rows, width] -- only the rows of the elements that carry the column, document by document --
+ * next to an int32 [B, S] element -> row map (-1 = none), instead of dense [B, S, width]; every other column as fdio_parse_batch writes
+ * it.  An element (b, t) carries a packed column iff t <= the value the context column `length_column` holds for b (the zero-based
+ * length DataSpec's IntegerLookup yields: valid positions, masking.py:24-53 / mask.py:21-33) and, when the column has a gate, iff
+ * cond_mask[v] != 0 for the value v the width-1 int32 sequence column `cond_column` holds at (b, t) (loss_condition,
+ * data/crello-spec.yml:88-121; the mask is indexed by the preprocessed value).  Everywhere else filter_padding overwrites the value
+ * with <UNUSED> before the model reads it, so nothing is lost; 59 % of crello's embedding rows are never written.  out[column] must
+ * hold capacity_rows rows; n_rows receives the rows in use.  Values of elements that carry nothing are still decoded (errors do not
+ * depend on the format). */
+typedef struct {
+  int32_t column;          /* schema index: float32 sequence column, no transform, FDIO_OUT_FLOAT32 */
+  int32_t cond_column;     /* schema index of the gating int32 sequence column (width 1), or -1 */
+  const uint8_t* cond_mask;
+  int32_t cond_n;
+  int32_t* rowmap;         /* [B, S] */
+  int64_t capacity_rows;
+  int64_t n_rows;          /* out */
+} fdio_pack_column;
+int fdio_parse_batch_packed(const fdio_schema* s, const uint8_t* const* records, const uint64_t* lens, int32_t B, int32_t S, void* const* out,
+                            int32_t length_column, fdio_pack_column* pack, int32_t n_pack, int32_t n_threads);
+
 /* ---- TensorFlow tensor-bundle checkpoints (Model.load_weights / save_weights, train.py:67-69,94-97) ---
  * <prefix>.index is an immutable sorted string table (LevelDB table format: prefix-compressed blocks, restart
  * array, 5-byte block trailer, 48-byte footer with magic 0xdb4775248b80fb57); key "" holds BundleHeaderProto,

@@ -416,6 +416,37 @@ def test_dataset_batches_reproduce_the_exported_documents(crello_dir):
     assert "id" not in next(iter(spec.make_dataset("train")))
 
 
+def test_packed_batches_equal_pack_batch_of_the_dense_ones(crello_dir, tmp_path):
+    """``make_dataset(packed=True)`` writes the numerical columns packed straight from the records (``fdio_parse_batch_packed``): every
+    batch must be bit-identical to ``pack_batch`` of the dense batch -- the rows of the elements that carry the field (valid position and
+    type gate, data/crello-spec.yml:88-121), document by document, and the element -> row map -- for ragged batches, fixed-shape ones
+    (``pad_to``), one parser thread and many; every other column is unchanged."""
+    from flex_dm_b200.data import ROWS_SUFFIX, pack_batch
+
+    root, _ = crello_dir
+    for threads, pad_to in ((1, None), (5, None), (3, 20)):
+        spec = DataSpec("crello", root, batch_size=8, num_threads=threads)
+        cols = spec.make_input_columns()
+        dense = list(spec.make_dataset("train", shuffle=False, pad_to=pad_to))
+        packed = list(spec.make_dataset("train", shuffle=False, pad_to=pad_to, packed=True))
+        assert len(dense) == len(packed) == 5
+        n_packed_keys = 0
+        for d, p in zip(dense, packed):
+            want = pack_batch({k: v.numpy() for k, v in d.items()}, cols)
+            assert set(want.keys()) == set(p.keys())
+            for k, v in want.items():
+                got = p[k].numpy()
+                assert got.dtype == v.dtype and got.shape == v.shape and np.array_equal(got, v), k
+                n_packed_keys += k.endswith(ROWS_SUFFIX)
+            for k in ("image_embedding", "text_embedding"):
+                assert p[k].shape[0] < d[k].shape[0] * d[k].shape[1]  # fewer rows than elements: the type gate and the padding
+        assert n_packed_keys == 2 * 5
+    # a document with more elements than pad_to is reported like by the dense parse
+    spec = DataSpec("crello", root, batch_size=8)
+    with pytest.raises(ValueError):
+        next(iter(spec.make_dataset("train", shuffle=False, pad_to=3, packed=True)))
+
+
 def test_dataset_shuffle_repeat_and_prefetch(crello_dir):
     root, _ = crello_dir
     spec = DataSpec("crello", root, batch_size=8)
