@@ -15,6 +15,10 @@
 #include <atomic>
 #include <memory>
 #include <string>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <pthread.h>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -446,6 +450,64 @@ void pack_record(const fdio_schema& s, const fdio_pack_column& pc, const Span& s
   }
 }
 
+// Worker pool of the parser: a batch is parsed in one or two passes of <= 16 chunks each, several hundred times a second -- creating and
+// joining threads per pass cost more than some passes.  Workers are created on first use and live until the process ends (detached: the
+// library may be unloaded at exit while they sleep); one parse call at a time owns the pool, concurrent callers fall back to their own
+// thread (the DataSpec producer thread is the only caller in practice).
+class WorkerPool {
+ public:
+  // runs job(0 .. n-1), index 0 on the calling thread; returns when all are done
+  void run(int n, const std::function<void(int)>& job) {
+    if (n <= 1) { if (n == 1) job(0); return; }
+    std::unique_lock<std::mutex> owner(owner_, std::try_to_lock);
+    if (!owner.owns_lock()) { for (int i = 0; i < n; ++i) job(i); return; }
+    {
+      std::lock_guard<std::mutex> g(m_);
+      while (int(workers_) < n - 1) { std::thread([this, id = workers_] { loop(id); }).detach(); ++workers_; }
+      job_ = &job; n_ = n; pending_ = n - 1; ++epoch_;
+    }
+    wake_.notify_all();
+    job(0);
+    std::unique_lock<std::mutex> g(m_);
+    done_.wait(g, [this] { return pending_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  void loop(size_t id) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(int)>* job;
+      {
+        std::unique_lock<std::mutex> g(m_);
+        wake_.wait(g, [&] { return epoch_ != seen; });
+        seen = epoch_;
+        if (int(id) + 1 >= n_) continue;  // this pass uses fewer workers
+        job = job_;
+      }
+      (*job)(int(id) + 1);
+      std::lock_guard<std::mutex> g(m_);
+      if (--pending_ == 0) done_.notify_one();
+    }
+  }
+  std::mutex owner_, m_;
+  std::condition_variable wake_, done_;
+  const std::function<void(int)>* job_ = nullptr;
+  size_t workers_ = 0;
+  int n_ = 0, pending_ = 0;
+  uint64_t epoch_ = 0;
+};
+// never destroyed (its workers are detached); a forked child has none of the parent's threads and starts a pool of its own
+WorkerPool* g_pool = nullptr;
+WorkerPool& pool() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    g_pool = new WorkerPool();
+    pthread_atfork(nullptr, nullptr, [] { g_pool = new WorkerPool(); });
+  });
+  return *g_pool;
+}
+
 template <class Fn>
 int run_threads(int32_t B, int32_t n_threads, Fn&& fn) {  // fn(first, last, RecordError*)
   int T = std::max(1, std::min<int>(n_threads, B));
@@ -453,12 +515,11 @@ int run_threads(int32_t B, int32_t n_threads, Fn&& fn) {  // fn(first, last, Rec
   errs.resize(size_t(T));
   if (T == 1) fn(0, B, &errs[0]);
   else {
-    std::vector<std::thread> th;
-    for (int t = 0; t < T; ++t) {
-      int32_t lo = int32_t(int64_t(B) * t / T), hi = int32_t(int64_t(B) * (t + 1) / T);
-      th.emplace_back([&, lo, hi, t] { fn(lo, hi, &errs[size_t(t)]); });
-    }
-    for (auto& x : th) x.join();
+    const std::function<void(int)> job = [&](int t) {
+      const int32_t lo = int32_t(int64_t(B) * t / T), hi = int32_t(int64_t(B) * (t + 1) / T);
+      fn(lo, hi, &errs[size_t(t)]);
+    };
+    pool().run(T, job);
   }
   for (auto& e : errs)  // chunks are in record order: the first failing chunk holds the lowest failing record
     if (e.code != FDIO_OK) return fdio::fail(e.code, "%s", e.text.c_str());

@@ -15,6 +15,7 @@ import ctypes
 import glob
 import json
 import os
+import sys
 import queue
 import threading
 from collections import OrderedDict

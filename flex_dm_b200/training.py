@@ -37,7 +37,9 @@ def train(args) -> dict:
 
     spec = DataSpec(args.dataset_name, args.data_dir, batch_size=args.batch_size)
     splits = {
-        "train": spec.make_dataset("train", shuffle=True, repeat=True, seed=seed, cache="device" if getattr(args, "device_cache", False) else True),
+        # the training split streams in the packed column format (rows of numerical columns nothing reads are neither parsed nor copied)
+        "train": spec.make_dataset("train", shuffle=True, repeat=True, seed=seed, cache="device" if getattr(args, "device_cache", False) else True,
+                                   packed=not getattr(args, "device_cache", False)),
         "val": spec.make_dataset("val", cache=True),
         "test": spec.make_dataset("test", cache=True),
     }

@@ -447,6 +447,34 @@ def test_packed_batches_equal_pack_batch_of_the_dense_ones(crello_dir, tmp_path)
         next(iter(spec.make_dataset("train", shuffle=False, pad_to=3, packed=True)))
 
 
+def test_parser_worker_pool_survives_a_fork(crello_dir):
+    """The parser keeps a pool of worker threads between calls; a forked child (multiprocessing's default start method) has none of the
+    parent's threads and must start its own instead of waiting for workers that do not exist."""
+    import os
+
+    root, _ = crello_dir
+    spec = DataSpec("crello", root, batch_size=8, num_threads=4)
+    want = next(iter(spec.make_dataset("train", shuffle=False, packed=True)))
+    pid = os.fork()
+    if pid == 0:
+        code = 3
+        try:
+            got = next(iter(spec.make_dataset("train", shuffle=False, packed=True)))
+            code = 0 if all(np.array_equal(np.asarray(got[k]), np.asarray(want[k])) for k in want) else 4
+        finally:
+            os._exit(code)
+    deadline = __import__("time").time() + 60
+    while True:
+        done, status = os.waitpid(pid, os.WNOHANG)
+        if done:
+            break
+        if __import__("time").time() > deadline:
+            os.kill(pid, 9)
+            pytest.fail("the forked child hung in the parser")
+        __import__("time").sleep(0.05)
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
+
+
 def test_dataset_shuffle_repeat_and_prefetch(crello_dir):
     root, _ = crello_dir
     spec = DataSpec("crello", root, batch_size=8)
