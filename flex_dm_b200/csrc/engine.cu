@@ -627,12 +627,24 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
   if (h->pos_off >= 0) pos = PosEmbed{P + h->pos_off, h->S, drop ? h->cfg.dropout : 0.f, seed, step, token_ctx ? 1 : 0, h->doc0 * (uint32_t)h->S};
   MFP_TRY(launch_embed_fwd(sc, mod, flags, P, T, x, st, pos));
   h->launches += 1;
+  // The first block's LayerNorm 1 rides the epilogue of the LAST numerical field's Dense GEMM (its output rows are the finished encoder
+  // sum) when nothing else touches h0 afterwards: pre-LN blocks, no context token / canvas vector, a spec with numerical fields.
+  static const bool fuse_ln_env0 = [] { const char* e = getenv("FLEXDM_FUSE_LN"); return !(e && e[0] == '0'); }();
+  int last_num = -1;
+  for (int f = 0; f < sc.F; ++f)
+    if (sc.f[f].kind == 1) last_num = f;
+  const bool ln1_in_encoder = fuse_ln_env0 && h->gemm_impl != 1 && h->cfg.block_type == 0 && h->cfg.context == 0 && L > 0 && last_num >= 0;
   for (int f = 0; f < sc.F; ++f) {
     const FieldDev& fd = sc.f[f];
     if (fd.kind != 1) continue;
     GemmEpilogue ep = make_epilogue(x, D);
     ep.residual = x; ep.ldr = D;
     ep.rowflag = flags + (size_t)fd.num_slot * T;
+    if (ln1_in_encoder && f == last_num) {
+      float* stats0 = wsp<float>(h, h->off.stats);
+      ep.ln_out = wsp<float>(h, h->off.ln1); ep.ln_ldo = D; ep.ln_gamma = P + h->blocks[0].g1; ep.ln_beta = P + h->blocks[0].be1;
+      ep.ln_mean = stats0; ep.ln_rstd = stats0 + T;
+    }
     MFP_TRY(gemm(h, reinterpret_cast<const float*>(mod.cols[f]), 0, fd.C, P + fd.kernel_off, 1, D, T, D, fd.C, ep, 1, st));
   }
   // ---- context token (encoder.py:231-249): one more row per document, attended to by every element
@@ -710,7 +722,7 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
     // (input = the encoder's sum of embeddings) and the SIMT bring-up path run the standalone kernel.
     static const bool fuse_ln_env = [] { const char* e = getenv("FLEXDM_FUSE_LN"); return !(e && e[0] == '0'); }();  // A/B switch
     const bool fuse_ln = h->gemm_impl != 1 && fuse_ln_env;
-    if (i == 0 || !fuse_ln) { MFP_TRY(launch_layernorm_fwd(xi, P + b.g1, P + b.be1, T, ln1, stats, stats + T, st)); h->launches++; }
+    if ((i == 0 && !ln1_in_encoder) || !fuse_ln) { MFP_TRY(launch_layernorm_fwd(xi, P + b.g1, P + b.be1, T, ln1, stats, stats + T, st)); h->launches++; }
     GemmEpilogue e1 = make_epilogue(qkv, 3 * D);
     e1.bias = P + b.bqkv;
     MFP_TRY(gemm(h, ln1, 0, D, P + b.wqkv, 1, 3 * D, T, 3 * D, D, e1, 1, st));

@@ -1015,6 +1015,7 @@ static int launch_tcgen05_any(TensorMapCache* cache, const GemmCall* calls, int 
     MFP_GEMM_CASE(kEpiBias | kEpiResidual | kEpiLayerNorm)                 // ... with the following LayerNorm fused, eval
     MFP_GEMM_CASE(kEpiBias | kEpiResidual | kEpiDropout | kEpiLayerNorm)   // ... training
     MFP_GEMM_CASE(kEpiResidual | kEpiRowflag)                  // encoder Dense of a numerical field
+    MFP_GEMM_CASE(kEpiResidual | kEpiRowflag | kEpiLayerNorm)  // ... the last one, with the first block's LayerNorm 1 fused
     MFP_GEMM_CASE(kEpiReluMask)                                // dgrad through the FFN ReLU (alone or next to a weight gradient)
     MFP_GEMM_CASE(kEpiResidual)                                // dgrad + the gradient of the skip path (post-LayerNorm block)
     default:
