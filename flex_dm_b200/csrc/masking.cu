@@ -1,7 +1,7 @@
 // Input corruption of the MFP train step: preprocess_for_train / preprocess_for_test
 // (reference: src/mfp/mfp/models/mfp.py:72-138, models/masking.py:24-155,227-269).
-// One warp per element (b, s); every field of the element is produced in one pass, and only the variant the
-// document's task id selects is generated (the reference materialises all variants, then tf.where-selects).
+// Every field of an element is produced in one launch, and only the variant the document's task id selects is generated (the reference
+// materialises all variants, then tf.where-selects).
 #include "kernels.cuh"
 
 namespace mfp {
@@ -23,110 +23,149 @@ __device__ __forceinline__ float2 box_muller(uint32_t xa, uint32_t xb) {
 }
 
 // mode 0: train (tasks != null), mode 1: test (test_masks given)
-__global__ void __launch_bounds__(256, 5) mask_corrupt_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs in,
-                                                           const int* __restrict__ tasks, const __grid_constant__ MaskPtrs test_masks, int mode, int B,
-                                                           int S, uint32_t seed, uint32_t step, uint32_t doc0, const __grid_constant__ ModifiedPtrs out,
-                                                           unsigned char* __restrict__ flags) {
+// A CTA takes kMcElems consecutive elements.  Pass 0: one thread per element gathers what every field of it needs (validity, type, task,
+// elem_masking's pick).  Pass 1: one thread per (field, element), elements fastest -- a warp works on ONE field of 32 consecutive
+// elements, so the field's descriptor and kind are warp-uniform and the categorical loads / stores are coalesced; it writes the masks and
+// the categorical columns and leaves (action, source row) of the numerical fields in shared memory.  Pass 2: one warp per numerical row
+// (2 KB for the 512-float embeddings): copy / <MASK> / noise / <UNUSED>, and the encoder's by-value special-token flag of what was written.
+// (The first version ran one warp per element through all ten fields: 1 400 warp instructions per element, two thirds of them control
+// flow executed for one to three active lanes -- issue-bound at 72 us for 190 MB.)
+constexpr int kMcElems = 64;
+constexpr int kMcThreads = 256;
+constexpr int kMcMaxNum = 4;  // numerical fields per spec (crello: 2)
+__global__ void __launch_bounds__(kMcThreads, 4) mask_corrupt_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs in,
+                                                                    const int* __restrict__ tasks, const __grid_constant__ MaskPtrs test_masks, int mode, int B,
+                                                                    int S, uint32_t seed, uint32_t step, uint32_t doc0, const __grid_constant__ ModifiedPtrs out,
+                                                                    unsigned char* __restrict__ flags) {
   pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (t >= B * S) return;
-  const int b = t / S, s = t - b * S;
-  const uint32_t gt = (uint32_t)t + doc0 * (uint32_t)S;  // global element index: the Philox counters of a sharded batch are the single-process ones
-  const int n_valid = in.length[b] + 1;  // mask.py:28-29
-  const bool valid = s < n_valid;
-  const int type_c = sc.f[sc.type_field].C;
-  const int type_val = reinterpret_cast<const int*>(in.cols[sc.type_field])[(size_t)t * type_c];
-  const int task = (mode == 0) ? tasks[b] : -1;
-  int elem_sel = -1;
-  if (task == 1) {  // masking.py:98-113
-    const U4 r = philox4x32_10((uint32_t)b + doc0, kFieldElem, 0u, 0u, seed, step);
-    elem_sel = (int)(u01(r.x) * (float)n_valid);
+  __shared__ int s_type[kMcElems], s_task[kMcElems], s_row[kMcMaxNum][kMcElems];
+  __shared__ unsigned char s_valid[kMcElems], s_pick[kMcElems], s_act[kMcMaxNum][kMcElems];
+  const int T = B * S;
+  const int e0 = blockIdx.x * kMcElems;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ---- pass 0: per element
+  if (tid < kMcElems) {
+    const int t = e0 + tid;
+    int type_val = 0, task = -1;
+    bool valid = false, pick = false;
+    if (t < T) {
+      const int b = t / S, s = t - b * S;
+      const int n_valid = in.length[b] + 1;  // mask.py:28-29
+      valid = s < n_valid;
+      type_val = reinterpret_cast<const int*>(in.cols[sc.type_field])[(size_t)t * sc.f[sc.type_field].C];
+      task = (mode == 0) ? tasks[b] : -1;
+      if (task == 1) {  // masking.py:98-113
+        const U4 r = philox4x32_10((uint32_t)b + doc0, kFieldElem, 0u, 0u, seed, step);
+        pick = s == (int)(u01(r.x) * (float)n_valid);
+      }
+    }
+    s_type[tid] = type_val; s_task[tid] = task; s_valid[tid] = valid ? 1 : 0; s_pick[tid] = pick ? 1 : 0;
   }
-  // random_masking draws three uniforms per (element, field): lane f computes the Philox block of field f once and the field
-  // loop broadcasts it (every lane recomputing every field's block was a third of this kernel's time)
-  U4 rf = {0u, 0u, 0u, 0u};
-  if (task == 0 && lane < sc.F) rf = philox4x32_10(gt, (uint32_t)lane, kStreamRandomU, 0u, seed, step);
-  for (int f = 0; f < sc.F; ++f) {
-    const FieldDev fd = sc.f[f];
+  __syncthreads();
+  // ---- pass 1: per (field, element)
+  for (int idx = tid; idx < sc.F * kMcElems; idx += kMcThreads) {
+    const int f = idx / kMcElems, e = idx - f * kMcElems;
+    const int t = e0 + e;
+    if (t >= T) continue;
+    const FieldDev& fd = sc.f[f];
+    const uint32_t gt = (uint32_t)t + doc0 * (uint32_t)S;  // global element index: the Philox counters of a sharded batch are the single-process ones
+    const bool valid = s_valid[e] != 0;
+    const int task = s_task[e];
     // filter_padding (masking.py:24-53)
-    bool unused = !valid || (fd.has_cond && !((fd.cond_mask >> type_val) & 1ull));
-    size_t src_row = (size_t)t;
+    bool unused = !valid || (fd.has_cond && !((fd.cond_mask >> s_type[e]) & 1ull));
+    int src_row = t;
     if (fd.kind == 1 && in.rowmap[f]) {  // packed column: element t's row, or none (<UNUSED>)
       const int pr = __ldg(in.rowmap[f] + t);
       unused = unused || pr < 0;
-      src_row = pr < 0 ? 0 : (size_t)pr;
+      src_row = pr < 0 ? 0 : pr;
     }
     int action = 0;  // 0 keep filtered, 1 <MASK>, 2 random token
     bool mfp = false;
     if (mode == 1) {
       mfp = test_masks.m[f][t] != 0;
       action = mfp ? 1 : 0;
-    } else if (task == 0) {  // random_masking (masking.py:227-269); task is uniform over the warp (one document)
-      const uint32_t rx = __shfl_sync(0xffffffffu, rf.x, f), ry = __shfl_sync(0xffffffffu, rf.y, f), rz = __shfl_sync(0xffffffffu, rf.z, f);
-      mfp = valid && (u01(rx) < kMaskProb);
-      const bool chg = mfp && (u01(ry) < kChangeProb);
-      if (chg) action = (u01(rz) >= kThresh) ? 1 : 2;
+    } else if (task == 0) {  // random_masking (masking.py:227-269): three uniforms per (element, field)
+      const U4 rf = philox4x32_10(gt, (uint32_t)f, kStreamRandomU, 0u, seed, step);
+      mfp = valid && (u01(rf.x) < kMaskProb);
+      const bool chg = mfp && (u01(rf.y) < kChangeProb);
+      if (chg) action = (u01(rf.z) >= kThresh) ? 1 : 2;
     } else if (task == 1) {  // elem_masking (masking.py:136-155)
-      mfp = (s == elem_sel);
+      mfp = s_pick[e] != 0;
       action = mfp ? 1 : 0;
     } else {  // feat_masking of one attribute group (masking.py:116-133)
       mfp = valid && (fd.task_id == task);
       action = mfp ? 1 : 0;
     }
-    if (mode == 0 && lane == 0) out.masks[f][t] = mfp ? 1 : 0;
+    if (mode == 0) out.masks[f][t] = mfp ? 1 : 0;
     if (fd.kind == 0) {
-      if (lane < fd.C) {
-        const int* src = reinterpret_cast<const int*>(in.cols[f]) + (size_t)t * fd.C;
-        int v = unused ? fd.input_dim + 1 : src[lane];
+      const int* src = reinterpret_cast<const int*>(in.cols[f]) + (size_t)t * fd.C;
+      int* dst = reinterpret_cast<int*>(out.cols[f]) + (size_t)t * fd.C;
+      for (int c = 0; c < fd.C; ++c) {
+        int v = unused ? fd.input_dim + 1 : src[c];
         if (action == 1) v = fd.input_dim;
         if (action == 2) {
-          const U4 r = philox4x32_10(gt, (uint32_t)f, kStreamRandomCat + (uint32_t)lane, 0u, seed, step);
+          const U4 r = philox4x32_10(gt, (uint32_t)f, kStreamRandomCat + (uint32_t)c, 0u, seed, step);
           v = (int)mulhi_range(r.x, (uint32_t)fd.input_dim);
         }
-        reinterpret_cast<int*>(out.cols[f])[(size_t)t * fd.C + lane] = v;
+        dst[c] = v;
       }
     } else {
-      const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in.cols[f]) + src_row * fd.C);
-      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out.cols[f]) + (size_t)t * fd.C);
-      bool all_mask = true, all_null = true;  // the encoder's by-value special-token test (row_flags_kernel), on what is written
-      int q_begin = lane;
-      if (action == 0 && !unused) {
-        // plain copy (the common case): four 16-byte loads in flight per lane before the stores -- one dependent load/store pair
-        // per iteration left too few bytes in flight per SM (measured 3.4 TB/s for this kernel)
-        for (; q_begin + 96 < fd.C / 4; q_begin += 128) {
-          const float4 v0 = src[q_begin], v1 = src[q_begin + 32], v2 = src[q_begin + 64], v3 = src[q_begin + 96];
-          dst[q_begin] = v0; dst[q_begin + 32] = v1; dst[q_begin + 64] = v2; dst[q_begin + 96] = v3;
-          const float4 vs[4] = {v0, v1, v2, v3};
+      s_act[fd.num_slot][e] = (unsigned char)(action | (unused ? 4 : 0));
+      s_row[fd.num_slot][e] = src_row;
+    }
+  }
+  if (sc.n_num == 0) return;
+  __syncthreads();
+  // ---- pass 2: one warp per numerical row
+  for (int r = warp; r < sc.n_num * kMcElems; r += kMcThreads / 32) {
+    const int slot = r / kMcElems, e = r - slot * kMcElems;
+    const int t = e0 + e;
+    if (t >= T) continue;
+    int f = 0;
+    for (int k = 0; k < sc.F; ++k)
+      if (sc.f[k].kind == 1 && sc.f[k].num_slot == slot) f = k;
+    const FieldDev& fd = sc.f[f];
+    const uint32_t gt = (uint32_t)t + doc0 * (uint32_t)S;
+    const int action = s_act[slot][e] & 3;
+    const bool unused = (s_act[slot][e] & 4) != 0;
+    const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in.cols[f]) + (size_t)s_row[slot][e] * fd.C);
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out.cols[f]) + (size_t)t * fd.C);
+    bool all_mask = true, all_null = true;  // the encoder's by-value special-token test (row_flags_kernel), on what is written
+    int q_begin = lane;
+    if (action == 0 && !unused) {
+      // plain copy (the common case): four 16-byte loads in flight per lane before the stores
+      for (; q_begin + 96 < fd.C / 4; q_begin += 128) {
+        const float4 v0 = src[q_begin], v1 = src[q_begin + 32], v2 = src[q_begin + 64], v3 = src[q_begin + 96];
+        dst[q_begin] = v0; dst[q_begin + 32] = v1; dst[q_begin + 64] = v2; dst[q_begin + 96] = v3;
+        const float4 vs[4] = {v0, v1, v2, v3};
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            all_mask = all_mask && vs[k].x == kMaskValue && vs[k].y == kMaskValue && vs[k].z == kMaskValue && vs[k].w == kMaskValue;
-            all_null = all_null && vs[k].x == kNullValue && vs[k].y == kNullValue && vs[k].z == kNullValue && vs[k].w == kNullValue;
-          }
+        for (int k = 0; k < 4; ++k) {
+          all_mask = all_mask && vs[k].x == kMaskValue && vs[k].y == kMaskValue && vs[k].z == kMaskValue && vs[k].w == kMaskValue;
+          all_null = all_null && vs[k].x == kNullValue && vs[k].y == kNullValue && vs[k].z == kNullValue && vs[k].w == kNullValue;
         }
       }
-      for (int q = q_begin; q < fd.C / 4; q += 32) {
-        float4 v;
-        if (action == 1) {
-          v = make_float4(kMaskValue, kMaskValue, kMaskValue, kMaskValue);
-        } else if (action == 2) {
-          const U4 r = philox4x32_10(gt, (uint32_t)f, kStreamRandomNum + (uint32_t)q, 0u, seed, step);
-          const float2 z0 = box_muller(r.x, r.y), z1 = box_muller(r.z, r.w);
-          v = make_float4(z0.x * 0.1f, z0.y * 0.1f, z1.x * 0.1f, z1.y * 0.1f);  // stddev 0.1, masking.py:91
-        } else if (unused) {
-          v = make_float4(kNullValue, kNullValue, kNullValue, kNullValue);
-        } else {
-          v = src[q];
-        }
-        dst[q] = v;
-        all_mask = all_mask && v.x == kMaskValue && v.y == kMaskValue && v.z == kMaskValue && v.w == kMaskValue;
-        all_null = all_null && v.x == kNullValue && v.y == kNullValue && v.z == kNullValue && v.w == kNullValue;
+    }
+    for (int q = q_begin; q < fd.C / 4; q += 32) {
+      float4 v;
+      if (action == 1) {
+        v = make_float4(kMaskValue, kMaskValue, kMaskValue, kMaskValue);
+      } else if (action == 2) {
+        const U4 rr = philox4x32_10(gt, (uint32_t)f, kStreamRandomNum + (uint32_t)q, 0u, seed, step);
+        const float2 z0 = box_muller(rr.x, rr.y), z1 = box_muller(rr.z, rr.w);
+        v = make_float4(z0.x * 0.1f, z0.y * 0.1f, z1.x * 0.1f, z1.y * 0.1f);  // stddev 0.1, masking.py:91
+      } else if (unused) {
+        v = make_float4(kNullValue, kNullValue, kNullValue, kNullValue);
+      } else {
+        v = src[q];
       }
-      if (flags) {
-        all_mask = __all_sync(0xffffffffu, all_mask);
-        all_null = __all_sync(0xffffffffu, all_null);
-        if (lane == 0) flags[(size_t)fd.num_slot * B * S + t] = all_null ? 2 : (all_mask ? 1 : 0);
-      }
+      dst[q] = v;
+      all_mask = all_mask && v.x == kMaskValue && v.y == kMaskValue && v.z == kMaskValue && v.w == kMaskValue;
+      all_null = all_null && v.x == kNullValue && v.y == kNullValue && v.z == kNullValue && v.w == kNullValue;
+    }
+    if (flags) {
+      all_mask = __all_sync(0xffffffffu, all_mask);
+      all_null = __all_sync(0xffffffffu, all_null);
+      if (lane == 0) flags[(size_t)fd.num_slot * B * S + t] = all_null ? 2 : (all_mask ? 1 : 0);
     }
   }
 }
@@ -237,7 +276,8 @@ int launch_mask_corrupt(const Schema& sc, const BatchPtrs& in, const int* tasks,
   MaskPtrs tm{};
   if (test_masks) tm = *test_masks;
   const int T = B * S;
-  MFP_CUDA_OK(launch_pdl(mask_corrupt_kernel, (T + 7) / 8, 256, 0, st, sc, in, tasks, tm, test_masks ? 1 : 0, B, S, seed, step, doc0, out, flags));
+  if (sc.n_num > kMcMaxNum) { set_error("mask_corrupt: at most %d numerical fields", kMcMaxNum); return MFP_ERR_UNSUPPORTED; }
+  MFP_CUDA_OK(launch_pdl(mask_corrupt_kernel, (T + kMcElems - 1) / kMcElems, kMcThreads, 0, st, sc, in, tasks, tm, test_masks ? 1 : 0, B, S, seed, step, doc0, out, flags));
   MFP_CUDA_OK(cudaGetLastError());
   return MFP_OK;
 }
