@@ -55,6 +55,80 @@ __global__ void __launch_bounds__(128) sort_indices_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------- fused loss + gradient
+// Masked categorical sub-target of one element (one warp): softmax cross-entropy on clipped probabilities (Keras),
+// accuracy, and -- when drow is given -- the gradient.  NK = vocabulary entries per lane (ceil(V / 32)): the loops are unrolled for the
+// vocabulary at hand instead of for the largest one (crello's are 6-64 wide: one or two entries per lane, not eight; the kernel is
+// issue-bound).  Skipped entries would only have added 0.0f / compared -inf: the results are bit-identical.
+template <int NK>
+__device__ __forceinline__ void categorical_loss(const float* __restrict__ x, int V, int y, int lane, float inv_batch, float* __restrict__ dx, float& loss,
+                                           float& score, float& den) {
+  constexpr int kMaxVPerLane = NK;
+  float xv[kMaxVPerLane];
+  float mx = -INFINITY;
+  int arg = 0x7fffffff;
+#pragma unroll
+  for (int k = 0; k < kMaxVPerLane; ++k) {
+    const int v = lane + 32 * k;
+    xv[k] = (v < V) ? x[v] : -INFINITY;
+    if (xv[k] > mx) { mx = xv[k]; arg = v; }
+  }
+  // warp argmax, first index on ties (tf.argmax)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxVPerLane; ++k) {
+    xv[k] = (lane + 32 * k < V) ? expf(xv[k] - mx) : 0.f;
+    sum += xv[k];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  // A6: p clipped to [eps, 1-eps], log, softmax-CE on the logs: -log c_y + log sum_j c_j
+  float Z = 0.f, cy = 0.f, py = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxVPerLane; ++k) {
+    const int v = lane + 32 * k;
+    const float p = xv[k] * inv;
+    xv[k] = p;
+    if (v < V) {
+      const float cl = fminf(fmaxf(p, kCeEps), 1.0f - kCeEps);
+      Z += cl;
+      if (v == y) { cy = cl; py = p; }
+    }
+  }
+  Z = warp_sum(Z);
+  cy = warp_sum(cy);
+  py = warp_sum(py);
+  loss += -logf(cy) + logf(Z);
+  score += (arg == y) ? 1.f : 0.f;
+  den += 1.f;
+  if (dx) {
+    // g_v = dL/dp_v = m_v (-[v==y]/c_y + 1/Z), m_v = 1 inside the clip range; dx_v = p_v (g_v - sum_j g_j p_j)
+    const float invZ = 1.0f / Z;
+    float dot = 0.f;
+    float g[kMaxVPerLane];
+#pragma unroll
+    for (int k = 0; k < kMaxVPerLane; ++k) {
+      const int v = lane + 32 * k;
+      const float p = xv[k];
+      const bool inside = (v < V) && p >= kCeEps && p <= 1.0f - kCeEps;
+      g[k] = inside ? (invZ - ((v == y) ? 1.0f / cy : 0.f)) : 0.f;
+      dot += g[k] * p;
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int k = 0; k < kMaxVPerLane; ++k) {
+      const int v = lane + 32 * k;
+      if (v < V) dx[v] = xv[k] * (g[k] - dot) * inv_batch;
+    }
+  }
+  (void)py;
+}
+
 __global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ Schema sc, const __grid_constant__ BatchPtrs targets,
                                                    const __grid_constant__ MaskPtrs masks, const float* __restrict__ logits, int use_sort, int B, int S,
                                                    float inv_batch, float* __restrict__ dlogits, const __grid_constant__ LossBuffers buf) {
@@ -86,6 +160,7 @@ __global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ Schem
     my_w = valid && masks.m[lane][t] && (!fl.has_cond || ((fl.cond_mask >> type_true) & 1ull));
   }
   const unsigned wbits = __ballot_sync(0xffffffffu, my_w);
+  float my_loss = 0.f, my_score = 0.f, my_den = 0.f;
   for (int f = 0; f < sc.F; ++f) {
     const FieldDev& fd = sc.f[f];
     const bool w = (wbits >> f) & 1u;
@@ -97,70 +172,11 @@ __global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ Schem
       for (int c = 0; c < fd.C; ++c) {
         const int y = reinterpret_cast<const int*>(targets.cols[f])[tt * fd.C + c];
         const float* x = lrow + fd.logit_off + c * V;
-        float xv[kMaxVPerLane];
-        float mx = -INFINITY;
-        int arg = 0x7fffffff;
-#pragma unroll
-        for (int k = 0; k < kMaxVPerLane; ++k) {
-          const int v = lane + 32 * k;
-          xv[k] = (v < V) ? x[v] : -INFINITY;
-          if (xv[k] > mx) { mx = xv[k]; arg = v; }
-        }
-        // warp argmax, first index on ties (tf.argmax)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float om = __shfl_xor_sync(0xffffffffu, mx, o);
-          const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-          if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
-        }
-        float sum = 0.f;
-#pragma unroll
-        for (int k = 0; k < kMaxVPerLane; ++k) {
-          xv[k] = (lane + 32 * k < V) ? expf(xv[k] - mx) : 0.f;
-          sum += xv[k];
-        }
-        sum = warp_sum(sum);
-        const float inv = 1.0f / sum;
-        // A6: p clipped to [eps, 1-eps], log, softmax-CE on the logs: -log c_y + log sum_j c_j
-        float Z = 0.f, cy = 0.f, py = 0.f;
-#pragma unroll
-        for (int k = 0; k < kMaxVPerLane; ++k) {
-          const int v = lane + 32 * k;
-          const float p = xv[k] * inv;
-          xv[k] = p;
-          if (v < V) {
-            const float cl = fminf(fmaxf(p, kCeEps), 1.0f - kCeEps);
-            Z += cl;
-            if (v == y) { cy = cl; py = p; }
-          }
-        }
-        Z = warp_sum(Z);
-        cy = warp_sum(cy);
-        py = warp_sum(py);
-        loss += -logf(cy) + logf(Z);
-        score += (arg == y) ? 1.f : 0.f;
-        den += 1.f;
-        if (drow) {
-          // g_v = dL/dp_v = m_v (-[v==y]/c_y + 1/Z), m_v = 1 inside the clip range; dx_v = p_v (g_v - sum_j g_j p_j)
-          const float invZ = 1.0f / Z;
-          float dot = 0.f;
-          float g[kMaxVPerLane];
-#pragma unroll
-          for (int k = 0; k < kMaxVPerLane; ++k) {
-            const int v = lane + 32 * k;
-            const float p = xv[k];
-            const bool inside = (v < V) && p >= kCeEps && p <= 1.0f - kCeEps;
-            g[k] = inside ? (invZ - ((v == y) ? 1.0f / cy : 0.f)) : 0.f;
-            dot += g[k] * p;
-          }
-          dot = warp_sum(dot);
-#pragma unroll
-          for (int k = 0; k < kMaxVPerLane; ++k) {
-            const int v = lane + 32 * k;
-            if (v < V) drow[fd.logit_off + c * V + v] = xv[k] * (g[k] - dot) * inv_batch;
-          }
-        }
-        (void)py;
+        float* dx = drow ? drow + fd.logit_off + c * V : nullptr;
+        if (V <= 32) categorical_loss<1>(x, V, y, lane, inv_batch, dx, loss, score, den);
+        else if (V <= 64) categorical_loss<2>(x, V, y, lane, inv_batch, dx, loss, score, den);
+        else if (V <= 128) categorical_loss<4>(x, V, y, lane, inv_batch, dx, loss, score, den);
+        else categorical_loss<kMaxVPerLane>(x, V, y, lane, inv_batch, dx, loss, score, den);
       }
     } else {
       // metrics.py:52-57,246-248: sum_d (yhat - y)^2; score = 0.5 cos + 0.5 (l2_normalize eps 1e-12)
@@ -199,11 +215,12 @@ __global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ Schem
       score = 0.5f * xy * rsqrtf(fmaxf(yy, 1e-12f)) * rsqrtf(fmaxf(xx, 1e-12f)) + 0.5f;
       den = 1.f;
     }
-    if (lane == 0) {
-      buf.part[((size_t)0 * sc.F + f) * T + t] = loss;
-      buf.part[((size_t)1 * sc.F + f) * T + t] = score;
-      buf.part[((size_t)2 * sc.F + f) * T + t] = den;
-    }
+    if (lane == f) { my_loss = loss; my_score = score; my_den = den; }  // warp-uniform values: lane f keeps field f's
+  }
+  if (lane < sc.F) {  // one store per quantity for all fields of the element (was three single-lane stores per field)
+    buf.part[((size_t)0 * sc.F + lane) * T + t] = my_loss;
+    buf.part[((size_t)1 * sc.F + lane) * T + t] = my_score;
+    buf.part[((size_t)2 * sc.F + lane) * T + t] = my_den;
   }
 }
 
