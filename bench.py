@@ -579,8 +579,8 @@ def main():
             step_e2e(i)
         return timed(step_e2e, args.steps)
 
+    ms_e2e = e2e_leg(wl.pinned_packed)       # packed columns (the pipeline's default format): the headline leg runs right after `value`
     ms_e2e_dense = e2e_leg(wl.pinned)        # dense DataSpec.parse_fn columns: 4136 B per element for crello
-    ms_e2e = e2e_leg(wl.pinned_packed)       # packed columns (the pipeline's default format)
     e2e_value = world * elements_per_step * args.steps / (ms_e2e * 1e-3)
     last_loss = wl.global_loss(rows_host[args.steps - 1])
     assert np.isfinite(last_loss), last_loss
