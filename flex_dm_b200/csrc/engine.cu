@@ -29,7 +29,7 @@ struct BlockLayout {
 
 struct Workspace {
   // byte offsets into the caller's workspace
-  size_t vars, flags, perm, x, ln1, qkv, attn, xmid, ln2, hid, stats, lse, logits, dlogits, dx, dtmp, dy, dqkv, dhid, dattn, dh0m, onehot, rowgrad, part, idx_true, idx_pred,
+  size_t vars, flags, perm, x, ln1, qkv, attn, xmid, ln2, hid, gates, stats, lse, logits, dlogits, dx, dtmp, dy, dqkv, dhid, dattn, dh0m, onehot, rowgrad, part, idx_true, idx_pred,
       norms, ctx_row, canvas_vec, dcanvas, iota, zeros, det, ln_part, lo_a, lo_b, ar_sync, total;
 };
 
@@ -59,6 +59,7 @@ struct mfp_engine {
   std::vector<long long> stage_lo, stage_hi;  // flat-buffer range whose gradients are final after backward stage s (see mfp_backward_stages)
   const void* flags_for = nullptr;  // modified column (first numerical field) the workspace row flags were just derived from
   int gemm_impl = 0;
+  bool gates_valid = false;  // the last forward wrote the FFN's ReLU gates as bits (workspace `gates`): the backward reads those instead of hid
   uint32_t ar_calls = 0;   // NVLS all-reduce calls since the last bind (monotonic barrier flags)
   int deterministic = 0;   // mfp_set_deterministic: fixed-order gradient reductions (bit-identical steps from run to run)
   uint32_t doc0 = 0;       // mfp_set_doc_offset: global index of the bound batch's first document (data-parallel shard)
@@ -195,6 +196,16 @@ static void build_layout(mfp_engine* h) {
   h->stage_hi[0] = cur;
 }
 
+// rows per chunk plane of the FFN's ReLU gate words ([block][chunk of 32 hidden units][row]): whole 128-byte lines per warp of 32 rows
+static size_t gate_rows(size_t T) { return (T + 31) / 32 * 32; }
+// FLEXDM_RELU_BITS=0 keeps the hidden activation itself as the ReLU-mask operand of the FFN's input gradient (A/B switch, read per call)
+static bool relu_bits_enabled() { const char* e = getenv("FLEXDM_RELU_BITS"); return !(e && e[0] == '0'); }
+// algorithmic bytes of a GEMM: each operand and the output once, plus the residual / ReLU-mask operand (or the gate words: one bit per output)
+static double gemm_bytes(int M, int N, int K, const GemmEpilogue& ep) {
+  return 4.0 * ((double)M * K + (double)N * K + (double)M * N * ((ep.residual || ep.relu_src) ? 2.0 : 1.0)) +
+         ((ep.relu_bits || ep.relu_bits_out) ? (double)M * N / 8.0 : 0.0);
+}
+
 static Workspace plan_workspace(const mfp_engine* h, int B, int S) {
   Workspace w{};
   const size_t T = (size_t)B * S, L = h->cfg.num_blocks, D = kD, F = h->sc.F;
@@ -215,6 +226,7 @@ static Workspace plan_workspace(const mfp_engine* h, int B, int S) {
   w.xmid = take(L * T * D * fl);
   w.ln2 = take(L * T * D * fl);
   w.hid = take(L * T * kF * fl);
+  w.gates = take(L * (size_t)(kF / 32) * gate_rows(T) * sizeof(uint32_t));  // ReLU gates of the FFN hidden layer as bits: [block][chunk][row]
   w.stats = take(L * 4 * T * fl);
   w.lse = take(L * (size_t)B * kH * S * fl);
   w.logits = take(T * h->sc.LW * fl);
@@ -337,8 +349,7 @@ static int gemm(mfp_engine* h, const float* A, int a_mn, int lda, const float* B
     MFP_TRY(launch_colsum(Bp, K, N, ldb, colsum, st, h->deterministic != 0));
     h->launches++;
   }
-  // algorithmic bytes: each operand and the output once, plus the residual / ReLU-mask operand
-  const double bytes = 4.0 * ((double)M * K + (double)N * K + (double)M * N * ((ep.residual || ep.relu_src) ? 2.0 : 1.0));
+  const double bytes = gemm_bytes(M, N, K, ep);
   ProfScope prof(h, MFP_PROFILE_GEMM, st, bytes);
   return launch_gemm(h->maps, c, h->gemm_impl == 2 ? 0 : h->gemm_impl, st);
 }
@@ -379,7 +390,7 @@ static int gemm_group(mfp_engine* h, const GemmArgs* g, int n, cudaStream_t st) 
       c.det_ws_floats = kDetWsFloats;
       if (g[i].splits > 1 || g[i].colsum) h->launches++;  // splitk_reduce_kernel
     }
-    bytes += 4.0 * ((double)c.M * c.K + (double)c.N * c.K + (double)c.M * c.N * ((c.ep.residual || c.ep.relu_src) ? 2.0 : 1.0));
+    bytes += gemm_bytes(c.M, c.N, c.K, c.ep);
   }
   h->launches++;
   ProfScope prof(h, MFP_PROFILE_GEMM, st, bytes);
@@ -519,6 +530,7 @@ int mfp_bind(mfp_engine* h, int32_t B, int32_t S, void* workspace, int64_t works
   h->B = B; h->S = S; h->T = B * S;
   h->flags_for = nullptr;
   h->ws = reinterpret_cast<uint8_t*>(workspace);
+  h->gates_valid = false;
   h->off = w;
   h->params = params; h->grads = grads; h->adam_m = adam_m; h->adam_v = adam_v;
   std::vector<VarDev> vd(h->vars.size());
@@ -615,6 +627,10 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
   const size_t TD = (size_t)T * D;
   const bool drop = training && h->cfg.dropout > 0.f;
   const uint32_t row0 = h->doc0 * (uint32_t)h->S;  // global index of this batch's first row (dropout counters)
+  // FFN 1 also writes its ReLU gates as bits (64 bytes per row instead of the 2 KB of hid the input gradient would re-read as a mask)
+  const bool write_gates = h->gemm_impl != 1 && relu_bits_enabled();
+  h->gates_valid = write_gates;
+  const int gate_ld = (int)gate_rows((size_t)T);
 
   // ---- encoder (encoder.py:147-199)
   // special-token flags of the numerical fields: already written by the mask/corrupt pass when it produced exactly these
@@ -707,6 +723,7 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
       GemmEpilogue q3 = make_epilogue(hid, kF);
       q3.bias = P + b.b1;
       q3.relu = 1;
+      if (write_gates) { q3.relu_bits_out = wsp<uint32_t>(h, h->off.gates) + (size_t)i * (kF / 32) * gate_ld; q3.relu_bits_ld = gate_ld; }
       MFP_TRY(gemm(h, ln2, 0, D, P + b.w1, 1, kF, T, kF, D, q3, 1, st));
       GemmEpilogue q4 = make_epilogue(ln1, D);
       q4.bias = P + b.b2;
@@ -741,6 +758,7 @@ int mfp_forward(mfp_engine* h, const mfp_batch* modified, int32_t training, uint
     GemmEpilogue e3 = make_epilogue(hid, kF);
     e3.bias = P + b.b1;
     e3.relu = 1;
+    if (write_gates) { e3.relu_bits_out = wsp<uint32_t>(h, h->off.gates) + (size_t)i * (kF / 32) * gate_ld; e3.relu_bits_ld = gate_ld; }
     MFP_TRY(gemm(h, ln2, 0, D, P + b.w1, 1, kF, T, kF, D, e3, 1, st));
     GemmEpilogue e4 = make_epilogue(xo, D);
     e4.bias = P + b.b2;
@@ -821,6 +839,9 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
   float* dqkv = wsp<float>(h, h->off.dqkv);
   float* dhid = wsp<float>(h, h->off.dhid);
   float* dattn = wsp<float>(h, h->off.dattn);
+  // the FFN's ReLU gates as the forward's FFN 1 epilogue left them (bits), when it did and this path can read them
+  const bool use_gates = h->gates_valid && h->gemm_impl != 1 && relu_bits_enabled();
+  const int gate_ld = (int)gate_rows((size_t)T);
 
   if (first_stage == 0) {
     MFP_CUDA_OK(cudaMemsetAsync(G, 0, (size_t)h->param_count * sizeof(float), st));
@@ -840,6 +861,7 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
     const float* xmid = wsp<float>(h, h->off.xmid) + i * TD;
     const float* ln2 = wsp<float>(h, h->off.ln2) + i * TD;
     const float* hid = wsp<float>(h, h->off.hid) + (size_t)i * T * kF;
+    const uint32_t* gates = wsp<uint32_t>(h, h->off.gates) + (size_t)i * (kF / 32) * gate_ld;
     const float* stats = wsp<float>(h, h->off.stats) + (size_t)i * 4 * T;
     const float* lse = wsp<float>(h, h->off.lse) + (size_t)i * h->B * kH * h->S;
 
@@ -854,7 +876,8 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
       const float* dy2 = drop ? dyb : dx;
       MFP_TRY(gemm(h, hid, 1, kF, dy2, 1, D, kF, D, T, make_epilogue(G + b.w2, D), wgrad_splits(kF, D, T), st, G + b.b2));
       GemmEpilogue ph = make_epilogue(dhid, kF);
-      ph.relu_src = hid; ph.ld_relu = kF;
+      if (use_gates) { ph.relu_bits = gates; ph.relu_bits_ld = gate_ld; }
+      else { ph.relu_src = hid; ph.ld_relu = kF; }
       MFP_TRY(gemm(h, dy2, 0, D, P + b.w2, 0, D, T, kF, D, ph, 1, st));
       MFP_TRY(gemm(h, x1, 1, D, dhid, 1, kF, D, kF, T, make_epilogue(G + b.w1, kF), wgrad_splits(D, kF, T), st, G + b.b1));
       GemmEpilogue p1 = make_epilogue(dx, D);  // dx1 = dz2 (in dx) + dhid . W1^T, in place
@@ -895,7 +918,8 @@ int mfp_backward_stages(mfp_engine* h, const mfp_batch* modified, int32_t traini
     }
     // every weight gradient shares its launch with the input gradient that hangs off the same dY (gemm_group)
     GemmEpilogue eh = make_epilogue(dhid, kF);
-    eh.relu_src = hid; eh.ld_relu = kF;
+    if (use_gates) { eh.relu_bits = gates; eh.relu_bits_ld = gate_ld; }
+    else { eh.relu_src = hid; eh.ld_relu = kF; }
     const GemmArgs g1[2] = {{hid, 1, kF, dy, 1, D, kF, D, T, make_epilogue(G + b.w2, D), wgrad_splits(kF, D, T), G + b.b2},
                             {dy, 0, D, P + b.w2, 0, D, T, kF, D, eh, 1, nullptr}};
     MFP_TRY(gemm_group(h, g1, 2, st));

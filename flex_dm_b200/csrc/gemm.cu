@@ -29,6 +29,11 @@ __device__ __forceinline__ void epilogue_store4(float (&v)[4], int row, int col,
     v[0] = s.x > 0.0f ? v[0] : 0.0f; v[1] = s.y > 0.0f ? v[1] : 0.0f;
     v[2] = s.z > 0.0f ? v[2] : 0.0f; v[3] = s.w > 0.0f ? v[3] : 0.0f;
   }
+  if (ep.relu_bits) {
+    const uint32_t nib = ep.relu_bits[(size_t)(col >> 5) * ep.relu_bits_ld + row] >> (col & 31);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = ((nib >> j) & 1u) ? v[j] : 0.0f;
+  }
   if (ep.drop_enabled) dropout4(v, ((uint32_t)row + ep.drop_row0) * (uint32_t)N + (uint32_t)col, ep.drop_rate, ep.drop_seed, ep.drop_step, ep.drop_site);
   if (ep.rowflag && ep.rowflag[row]) { v[0] = v[1] = v[2] = v[3] = 0.0f; }
   if (ep.residual && lead_split) {
@@ -95,7 +100,9 @@ struct GemmSmem {
 
 // Epilogue variants are compiled in (EPI bit mask), so each instantiation carries only the code it runs: the epilogue
 // warps are issue-bound (one warp per scheduler), every dead branch in their loop costs throughput.
-enum : int { kEpiBias = 1, kEpiRelu = 2, kEpiResidual = 4, kEpiReluMask = 8, kEpiDropout = 16, kEpiRowflag = 32, kEpiLayerNorm = 64 };
+enum : int { kEpiBias = 1, kEpiRelu = 2, kEpiResidual = 4, kEpiReluMask = 8, kEpiDropout = 16, kEpiRowflag = 32, kEpiLayerNorm = 64,
+             kEpiReluBits = 128,   // ReLU gates read as bits (one word per row and 32-column chunk) instead of the aux operand
+             kEpiBitsOut = 256 };  // ... and written by the forward GEMM that applies the ReLU
 
 // One GEMM of a launch.  A launch carries up to kMaxGroup INDEPENDENT problems whose tiles form one tile space (problem 0's tiles first):
 // a weight gradient and the input gradient that hangs off the same dY run as one launch -- every CTA takes its one long split-K tile of
@@ -438,6 +445,20 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
         if (g0.use_aux && h < g0.nchunks) fetch_aux(g0, h);
       }
     }
+    // ReLU gates as bits (kEpiReluBits): lane = row, so a chunk's gates are ONE word per thread ([chunk][row] layout: a 128-byte line per
+    // warp); fetched one chunk ahead like the aux operand.  A problem of the launch without gate words gets all ones.
+    uint32_t gate_next = 0xffffffffu;
+    auto fetch_gates = [&](const TileGeo& g, int c) {
+      const int grow = g.m0 + q * 32 + lane;
+      const uint32_t* bits = g.P->ep.relu_bits;
+      return (bits != nullptr && grow < g.P->M) ? __ldg(bits + (size_t)((g.n0 >> 5) + c) * g.P->ep.relu_bits_ld + grow) : 0xffffffffu;
+    };
+    if constexpr (EPI & kEpiReluBits) {
+      if (unit < num_tiles) {
+        const TileGeo g0 = geo_of(unit);
+        if (h < g0.nchunks) gate_next = fetch_gates(g0, h);
+      }
+    }
     for (int tile = unit; tile < num_tiles; tile += units) {
       const TileGeo g = geo_of(tile);
       const GemmEpilogue& ep = g.P->ep;
@@ -507,6 +528,20 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
             }
           }
         }
+        uint32_t gates = 0xffffffffu, gates_out = 0u;
+        if constexpr (EPI & kEpiReluBits) {
+          gates = gate_next;
+          if (c + 2 < nchunks) {
+            gate_next = fetch_gates(g, c + 2);
+          } else {
+            const int nt = tile + units;
+            gate_next = 0xffffffffu;
+            if (nt < num_tiles) {
+              const TileGeo gn = geo_of(nt);
+              if (h < gn.nchunks) gate_next = fetch_gates(gn, h);
+            }
+          }
+        }
         U4 dr = {0u, 0u, 0u, 0u};
         float4 av[8];
         if constexpr (aux_mode != 0) {
@@ -535,6 +570,14 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
               v[2] = a.z > 0.0f ? v[2] : 0.0f; v[3] = a.w > 0.0f ? v[3] : 0.0f;
             }
           }
+          if constexpr (EPI & kEpiBitsOut) {  // after bias + ReLU: the gate is "the stored value is positive", what relu_src > 0 tests
+#pragma unroll
+            for (int e = 0; e < 4; ++e) gates_out |= (v[e] > 0.0f ? 1u : 0u) << (4 * j + e);
+          }
+          if constexpr (EPI & kEpiReluBits) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = ((gates >> (4 * j + e)) & 1u) ? v[e] : 0.0f;
+          }
           if constexpr (EPI & kEpiDropout) {  // one Philox block per eight columns (j even computes it, j odd uses its second half)
             if (ep.drop_enabled) {
               if ((j & 1) == 0) dr = philox4x32_10((((uint32_t)row + ep.drop_row0) * (uint32_t)N + (uint32_t)(col0 + 4 * j)) >> 3, ep.drop_site, 0u, 0u, ep.drop_seed, ep.drop_step);
@@ -553,6 +596,9 @@ gemm_tf32_tcgen05(const __grid_constant__ GemmGroup grp, GemmTune tune, unsigned
           }
         }
         if constexpr (EPI & kEpiLayerNorm) tmem_st32(tacc + (uint32_t)(c * 32), rr);
+        if constexpr (EPI & kEpiBitsOut) {
+          if (ep.relu_bits_out != nullptr && row < M) ep.relu_bits_out[(size_t)(col0 >> 5) * ep.relu_bits_ld + row] = gates_out;
+        }
         if (ep.atomic) {
           fence_proxy_async_smem();
           __syncwarp();
@@ -842,7 +888,8 @@ static int num_sms() {
 
 static int epi_bits(const GemmEpilogue& ep) {
   return (ep.bias ? kEpiBias : 0) | (ep.relu ? kEpiRelu : 0) | (ep.residual ? kEpiResidual : 0) | (ep.relu_src ? kEpiReluMask : 0) |
-         (ep.drop_enabled ? kEpiDropout : 0) | (ep.rowflag ? kEpiRowflag : 0) | (ep.ln_out ? kEpiLayerNorm : 0);
+         (ep.drop_enabled ? kEpiDropout : 0) | (ep.rowflag ? kEpiRowflag : 0) | (ep.ln_out ? kEpiLayerNorm : 0) |
+         (ep.relu_bits ? kEpiReluBits : 0) | (ep.relu_bits_out ? kEpiBitsOut : 0);
 }
 
 // What has to follow a problem's GEMM in deterministic mode: the fixed-order sum of its split-K / column-sum partials.
@@ -858,6 +905,12 @@ static int prepare_problem(TensorMapCache* cache, const GemmCall& c, int epi_lau
   constexpr int kBRows = BN / CG;     // rows of the B tile one CTA stages (a CTA pair splits the tile's columns between its two CTAs)
   constexpr int kTileM = kBM * CG;    // rows of a tile of the tile space
   if (c.ep.residual && c.ep.relu_src) { set_error("gemm: residual and relu_src cannot be combined"); return MFP_ERR_ARG; }
+  if (c.ep.relu_bits && c.ep.relu_src) { set_error("gemm: relu_bits and relu_src are two forms of the same operand"); return MFP_ERR_ARG; }
+  if ((c.ep.relu_bits || c.ep.relu_bits_out) && (c.ep.relu_bits_ld < c.M || (c.ep.relu_bits_ld % 32) || c.splits > 1)) {
+    set_error("gemm: ReLU gate words need relu_bits_ld >= M, a multiple of 32, and no split-K");
+    return MFP_ERR_ARG;
+  }
+  if (c.ep.relu_bits_out && !c.ep.relu) { set_error("gemm: relu_bits_out belongs to a ReLU epilogue"); return MFP_ERR_ARG; }
   if (c.colsum && !c.b.mn_major) { set_error("gemm: the fused column sum needs an MN-major B operand"); return MFP_ERR_ARG; }
   if (c.ep.ln_out && (c.N != BN || c.splits > 1 || !c.ep.ln_gamma || !c.ep.ln_beta || !c.ep.ln_mean || !c.ep.ln_rstd || (c.ep.ln_ldo % 4))) {
     set_error("gemm: the fused LayerNorm needs N == %d (whole rows in one tile), no split-K, and gamma / beta / mean / rstd", BN);
@@ -1017,6 +1070,8 @@ static int launch_tcgen05_any(TensorMapCache* cache, const GemmCall* calls, int 
     MFP_GEMM_CASE(kEpiResidual | kEpiRowflag)                  // encoder Dense of a numerical field
     MFP_GEMM_CASE(kEpiResidual | kEpiRowflag | kEpiLayerNorm)  // ... the last one, with the first block's LayerNorm 1 fused
     MFP_GEMM_CASE(kEpiReluMask)                                // dgrad through the FFN ReLU (alone or next to a weight gradient)
+    MFP_GEMM_CASE(kEpiReluBits)                                // ... with the gates as bits (no aux operand)
+    MFP_GEMM_CASE(kEpiBias | kEpiRelu | kEpiBitsOut)           // FFN 1 of a training step: also writes the gate words
     MFP_GEMM_CASE(kEpiResidual)                                // dgrad + the gradient of the skip path (post-LayerNorm block)
     default:
       set_error("gemm: epilogue combination 0x%x is not instantiated", epi);
@@ -1048,6 +1103,7 @@ int launch_gemm(TensorMapCache* cache, const GemmCall& c, int impl, cudaStream_t
   MFP_TRY(check_call(c));
   if (impl == 1) {
     if (c.colsum) { set_error("gemm: the SIMT bring-up kernel has no fused column sum"); return MFP_ERR_ARG; }
+    if (c.ep.relu_bits_out) { set_error("gemm: the SIMT bring-up kernel does not write ReLU gate words"); return MFP_ERR_ARG; }
     int splits = (c.splits < 1 || c.det_ws) ? 1 : c.splits;  // deterministic mode: no atomic accumulation over splits
     int k_per_split = ((c.K + splits - 1) / splits + 15) / 16 * 16;
     splits = (c.K + k_per_split - 1) / k_per_split;

@@ -20,6 +20,9 @@ struct GemmOperand {
 // Fused epilogue, applied per element in this order:
 //   v = acc; v += bias[col]; v = relu(v); v *= (relu_src[row,col] > 0); v = dropout(v);
 //   if (rowflag[row]) v = 0; v += residual[row,col]; out[row,col] = v   (or atomicAdd when atomic != 0)
+// ReLU gates as bits (tcgen05 path): a forward GEMM with relu_bits_out also writes, per row and 32-column chunk, the word whose bit k says
+// out[row, 32 chunk + k] > 0 -- layout [N / 32][relu_bits_ld] uint32, rows contiguous, so a warp of 32 rows moves one 128-byte line --
+// and the input-gradient GEMM through that ReLU takes relu_bits instead of relu_src: 1/32 of the bytes, no aux operand in its epilogue.
 struct GemmEpilogue {
   float* out;
   int ldo;
@@ -44,6 +47,9 @@ struct GemmEpilogue {
   const float* ln_beta;
   float* ln_mean;
   float* ln_rstd;
+  uint32_t* relu_bits_out;    // forward: gate words of the rows / chunks this GEMM writes (nullptr: off)
+  const uint32_t* relu_bits;  // backward: v *= bit(row, col) (instead of relu_src)
+  int relu_bits_ld;           // rows per chunk plane of either (>= M, multiple of 32)
 };
 
 inline GemmEpilogue make_epilogue(float* out, int ldo) {

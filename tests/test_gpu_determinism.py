@@ -17,14 +17,15 @@ from tests import helpers as H
 pytestmark = pytest.mark.gpu
 
 
-def _train(dataset, method, B, S, L, steps, deterministic, seed=3):
+def _train(dataset, method, B, S, L, steps, deterministic, seed=3, block_type="deepsvg", impl=0):
     from flex_dm_b200.mfp import MFP, Adam
 
     cols = make_input_columns(dataset, max_length=S)
-    m = MFP(cols, num_blocks=L, masking_method=method, latent_dim=256, dropout=0.1, l2=1e-2, seed=seed)
+    m = MFP(cols, num_blocks=L, block_type=block_type, masking_method=method, latent_dim=256, dropout=0.1, l2=1e-2, seed=seed)
     m.set_weights(H.perturbed_weights(m.engine, seed))
     m.compile(optimizer=Adam(learning_rate=1e-3, clipnorm=1.0))
     m.set_deterministic(deterministic)
+    m.engine.set_gemm_impl(impl)
     batches = [make_synthetic_batch(cols, B, S, seed=10 + i, lengths="ragged") for i in range(2)]
     rows = [m.train_step(batches[i % 2]).clone() for i in range(steps)]
     torch.cuda.synchronize()
@@ -48,6 +49,25 @@ def test_deterministic_mode_repeats_bit_for_bit(dataset, method, B, S, L):
             continue  # exact gradient 0 (softmax is shift-invariant): pure rounding noise of a column sum, in any order
         scale = max(np.abs(g4[name]).max(), 1e-8)
         assert np.abs(g3[name] - g4[name]).max() <= 2e-4 * scale + 1e-9, name
+
+
+@pytest.mark.parametrize("dataset,method,B,S,L,block_type,impl", [
+    ("crello", "random", 256, 128, 1, "deepsvg", 0),      # the benchmarked row count: several tiles per CTA pair (gate words prefetched across tiles)
+    ("crello", "elem_pos_attr_img_txt", 64, 128, 2, "deepsvg", 0),   # 64-document shard: narrow tiles on single CTAs
+    ("rico", "elem_pos_attr", 9, 20, 2, "transformer", 0),  # post-LayerNorm wiring, a partial row tile
+    ("rico", "elem_pos_attr", 9, 20, 1, "deepsvg", 2),      # 3xTF32 GEMMs (the same kernel, three passes)
+], ids=["cfg2-rows", "shard64", "postln-small", "3xtf32-small"])
+def test_relu_gate_bits_equal_the_mask_operand(monkeypatch, dataset, method, B, S, L, block_type, impl):
+    """FFN 1 writes its ReLU gates as one bit per hidden unit and the input-gradient GEMM of FFN 2 reads those words instead of re-reading
+    the hidden activation as a mask operand (transformer.py:161-171 through autodiff): a gate is a gate, so steps are bit-identical to the
+    mask-operand form (FLEXDM_RELU_BITS=0) in deterministic mode -- metrics rows, gradients and weights."""
+    w1, r1, g1 = _train(dataset, method, B, S, L, 2, True, block_type=block_type, impl=impl)
+    monkeypatch.setenv("FLEXDM_RELU_BITS", "0")
+    w2, r2, g2 = _train(dataset, method, B, S, L, 2, True, block_type=block_type, impl=impl)
+    assert np.array_equal(r1, r2)
+    for name in w1:
+        assert np.array_equal(g1[name], g2[name]), name
+        assert np.array_equal(w1[name], w2[name]), name
 
 
 def _shard_run(cols, method, batch, lo, hi, b_global, S, L, seed, step, impl):
