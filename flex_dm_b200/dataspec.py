@@ -15,7 +15,6 @@ import ctypes
 import glob
 import json
 import os
-import sys
 import queue
 import threading
 from collections import OrderedDict
