@@ -55,7 +55,10 @@ def flops_per_element(cols, S, L, D=256):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line).  The sampler is started before the
+    warm-up steps (nvidia-smi needs ~0.1 s to come up, a 20-step timed region lasts 0.05 s) and every sample carries its arrival time;
+    stop() keeps the samples that arrived between mark_begin() and mark_end().  When the region was shorter than one sampling period
+    it falls back to the samples of the quarter second before its end -- the warm-up steps, the same kernels back to back -- and says so."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -63,6 +66,13 @@ class ClockSampler:
         self.gpu = gpu_index
         self.lines = []
         self.proc = None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def start(self):
         try:
@@ -75,7 +85,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -85,8 +95,15 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t1 = self.t1 if self.t1 is not None else time.perf_counter()
+        t0 = self.t0 if self.t0 is not None else t1 - 1.0
+        lines = [line for ts, line in self.lines if t0 <= ts <= t1]
+        window = "timed region"
+        if not lines:
+            lines = [line for ts, line in self.lines if t1 - 0.25 <= ts <= t1 + 0.06]
+            window = "warm-up + timed region (the timed region was shorter than one 50 ms sampling period)"
         sm, smax, reasons = [], [], set()
-        for line in self.lines:
+        for line in lines:
             p = [x.strip() for x in line.split(",")]
             if len(p) < 9:
                 continue
@@ -99,7 +116,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def cpu_cfg1_throughput(steps=10):
@@ -505,7 +522,7 @@ def main():
         finally:
             torch.backends.cuda.matmul.allow_tf32 = old
 
-    def value_leg(config, steps, warmup, before_timed=None):
+    def value_leg(config, steps, warmup, before_timed=None, after_timed=None):
         """Device-resident throughput of one configuration: (workload, ms total, launches, step-0 global loss)."""
         wl = Workload(config, world, rank, dev, dist)
         loss0 = wl.global_loss(wl.step_resident(0))
@@ -515,6 +532,8 @@ def main():
         if before_timed is not None:
             before_timed()
         ms = timed(wl.step_resident, steps)
+        if after_timed is not None:
+            after_timed()
         return wl, ms, wl.model.engine.launch_count() - launches0, loss0
 
     def check_step0(config, loss0):
@@ -539,7 +558,10 @@ def main():
 
     # ---- device-resident leg (value)
     sampler = ClockSampler(local_rank)
-    wl, ms, launches, loss0 = value_leg(args.config, args.steps, args.warmup, before_timed=sampler.start if rank == 0 else None)
+    if rank == 0:
+        sampler.start()
+    wl, ms, launches, loss0 = value_leg(args.config, args.steps, args.warmup, before_timed=sampler.mark_begin if rank == 0 else None,
+                                        after_timed=sampler.mark_end if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
     model, w = wl.model, wl.w
     elements_per_step = wl.elements_per_step
